@@ -1,0 +1,134 @@
+/* kaldi_fp16_fused.h -- B200-native fused operator ABI (extension of the reference surface).
+ *
+ * The reference's Go layer (internal/gpu, internal/nnet) builds every layer out of
+ * ops_gemm + 5..7 one-element-per-thread kernels + explicit transposes
+ * (/root/reference/internal/gpu/ops.go:55-79,335-351, backward_ops.go:162-253,
+ *  internal/nnet/forward.go:589-790).  These entry points expose the same math as ONE
+ * tcgen05 GEMM launch with the surrounding ops fused into its epilogue and the
+ * splice / transpose folded into TMA coordinates and UMMA operand majors.
+ * Plain C: pointers are device pointers unless noted, sizes are ints, no C++/torch types.
+ */
+#ifndef KALDI_FP16_FUSED_H
+#define KALDI_FP16_FUSED_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- context: replaces the implicit (device 0, default stream, cuBLAS handle) state of
+ * ops_cublas_create (cpp/cuda/ops.cu:336-348).  The handle returned by ops_cublas_create IS a
+ * kfp16 context, so old callers keep working; multi-GPU callers create one per device. */
+typedef struct kfp16_ctx kfp16_ctx;
+kfp16_ctx *kfp16_ctx_create(int device_id);
+void kfp16_ctx_destroy(kfp16_ctx *ctx);
+/* cudaStream_t to launch on (NULL = legacy default stream, what the reference uses) */
+int kfp16_ctx_set_stream(kfp16_ctx *ctx, void *cuda_stream);
+void *kfp16_ctx_get_stream(kfp16_ctx *ctx);
+int kfp16_ctx_num_sms(kfp16_ctx *ctx);
+/* cap the persistent grid (0 = all SMs); used by tests to exercise multi-tile-per-CTA paths */
+int kfp16_ctx_set_max_ctas(kfp16_ctx *ctx, int max_ctas);
+/* stream used by the context-free reference entry points (ops_relu, ...); NULL = default */
+void kfp16_set_default_stream(void *cuda_stream);
+/* number of kernels this library has launched in the calling process (bench "gpu_launches") */
+unsigned long long kfp16_launch_count(void);
+const char *kfp16_last_error(void);
+
+enum {
+    KFP16_EPI_BIAS = 1 << 0,      /* + bias[n]            gpu.AddBias              ops.go:335 */
+    KFP16_EPI_RELU = 1 << 1,      /* max(x,0)             ops_relu                 ops.cu:26 */
+    KFP16_EPI_BN = 1 << 2,        /* x*scale[n]+shift[n]  ops_batchnorm_forward    ops.cu:171 */
+    KFP16_EPI_RESID = 1 << 3,     /* res_scale*R + x      ops_add_scaled (bypass)  ops.cu:207 */
+    KFP16_EPI_BETA = 1 << 4,      /* alpha*acc + beta*R   cublasGemmEx beta        ops.cu:381 */
+    KFP16_EPI_REF_ROUND = 1 << 5, /* fp16 rounding between stages where the reference stores fp16 */
+    KFP16_EPI_MASK = 1 << 6,      /* emit 1-bit relu mask (x>0) for the backward pass */
+    KFP16_EPI_SPLITK = 1 << 7,    /* internal */
+    KFP16_EPI_DROPOUT = 1 << 8,   /* inverted dropout (go/gotorch/layers.go:348-399 semantics) */
+    KFP16_EPI_GRADMASK = 1 << 9   /* x = mask_in bit ? x : 0   (ops_relu_backward fused) */
+};
+
+/* operand storage */
+enum { KFP16_K_MAJOR = 0, KFP16_MN_MAJOR = 1 };
+
+typedef struct {
+    const void *ptr; /* fp16, row-major as stored, points at row 0 */
+    int rows, cols;  /* stored shape */
+    int ld;          /* elements between rows (multiple of 8) */
+    int halo;        /* rows readable before row 0 and after row rows-1 */
+} kfp16_mat;
+
+typedef struct {
+    int M, N, K; /* per-group problem; K = kslabs*kslab_len */
+    /* A: K-major = stored [M x K]; MN-major = stored [K x M] (i.e. A^T, used by weight gradients)
+     * B: K-major = stored [N x K] (i.e. B^T);  MN-major = stored [K x N] (what ops_gemm takes) */
+    int a_major, b_major;
+    kfp16_mat A, B;
+    int groups;    /* 1..2 independent outputs sharing the launch */
+    int kslabs;    /* 1..2 K-slabs (time splice) */
+    int kslab_len; /* K per slab */
+    /* storage-coordinate offsets added per (group, slab): rows / cols of the STORED matrix */
+    int a_row_off[2][2], a_col_off[2][2];
+    int b_row_off[2][2], b_col_off[2][2];
+    void *D[2];       /* fp16 outputs [M x N], ld = ldd */
+    int ldd;
+    int d_halo;       /* replicate first / last output row into this many halo rows */
+    const void *R[2]; /* residual or C-in, fp16 [M x N], ld = ldr */
+    int ldr;
+    uint32_t flags;
+    float alpha, beta, res_scale;
+    const void *bias;      /* fp16 [N] */
+    const float *bn_scale; /* fp32 [N]  gamma/sqrt(var+eps) */
+    const float *bn_shift; /* fp32 [N]  beta - mean*scale   */
+    int vec_gstride;       /* group g reads bias/bn at + g*vec_gstride */
+    uint32_t *mask_out;
+    const uint32_t *mask_in;
+    int mask_ld; /* words per row */
+    /* split-K: >1 accumulates alpha*partial into fp32 ws[g] (must be zeroed / hold the running sum) */
+    int split_k;
+    float *ws[2];
+    int ws_ld;
+    float drop_p;
+    uint32_t drop_seed;
+    int force_bn; /* 0 = heuristic tile width; else 64/128/160/256 */
+} kfp16_gemm_desc;
+
+/* returns 0 on success, -1 on error (message via kfp16_last_error / ops_last_error) */
+int kfp16_gemm_ex(kfp16_ctx *ctx, const kfp16_gemm_desc *d);
+
+/* plain GEMM with operand majors: C[MxN] = alpha*op(A)*op(B) + beta*C, dense leading dims.
+ * transA: A stored [K x M]; transB: B stored [N x K].  (kaldi_gemm semantics, cgo_interface.cu:206) */
+int kfp16_gemm(kfp16_ctx *ctx, int M, int N, int K, float alpha, const void *A, int transA,
+               const void *B, int transB, float beta, void *C);
+
+/* ---- fused elementwise helpers used by the layer executor ---- */
+/* bn_scale = gamma/sqrt(var+eps), bn_shift = beta - mean*bn_scale   (ops.cu:171-187) */
+int kfp16_bn_fold(kfp16_ctx *ctx, const float *mean, const float *var, const float *gamma,
+                  const float *beta, float eps, float target_rms, int D, float *scale, float *shift);
+/* dZ = mask ? h(dY*scale[n]) : 0   (ops_batchnorm_backward + ops_relu_backward in one pass) */
+int kfp16_bn_relu_backward(kfp16_ctx *ctx, const void *dY, int ldy, const float *scale,
+                           const uint32_t *mask, int mask_ld, void *dZ, int ldz, int rows, int cols);
+/* x[t,:] = h(x[t,:] + bias)  (gpu.AddBias, ops.go:335-351; the reference runs a K=1 GEMM) */
+int kfp16_add_bias(kfp16_ctx *ctx, void *x, int ld, const void *bias, int rows, int cols);
+/* out[n] = sum_t X[t,n]  (AffineBackwardBias, backward_ops.go:228-253), fp32 accumulate */
+int kfp16_colsum(kfp16_ctx *ctx, const void *X, int ld, int rows, int cols, float *out_f32,
+                 void *out_f16);
+/* fp32 -> fp16 (round to nearest even), n elements */
+int kfp16_f32_to_f16(kfp16_ctx *ctx, const float *src, void *dst, size_t n);
+/* Padded activation layout: n_seq blocks of (seq_len + 2*halo) rows; X points at the very first
+ * row (the first halo row of sequence 0).  pad_edges replicates each sequence's first / last real
+ * row into its halo rows (the per-sequence form of the clamp in forward.go:714-722,760-770);
+ * fold_edges is its adjoint: edge row += sum of its halo rows, halo rows = 0. */
+int kfp16_pad_edges(kfp16_ctx *ctx, void *X, int ld, int n_seq, int seq_len, int cols, int halo);
+int kfp16_fold_edges(kfp16_ctx *ctx, void *G, int ld, int n_seq, int seq_len, int cols, int halo);
+/* multi-tensor SGD over one flat parameter bucket (ops_sgd_update semantics, backward_wrappers.cu:129-142)
+ *   g = grad_is_f32 ? (round_grad ? float(half(g32)) : g32) : float(g16) */
+int kfp16_sgd_update_flat(kfp16_ctx *ctx, float *w32, void *w16, const void *grad, int grad_is_f32,
+                          int round_grad, float grad_scale, float *velocity, float lr,
+                          float momentum, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KALDI_FP16_FUSED_H */

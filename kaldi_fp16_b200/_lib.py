@@ -1,0 +1,183 @@
+"""ctypes binding of libkaldi_fp16.so -- the same C ABI a cgo caller links (include/*.h).
+
+There is no fallback: if the shared library is missing or a symbol cannot be resolved the import
+fails loudly (build it with `python -m kaldi_fp16_b200.build` or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libkaldi_fp16.so"
+
+c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+c_u32, c_i64, c_u64 = C.c_uint32, C.c_int64, C.c_uint64
+FP = C.POINTER(C.c_float)
+
+
+class KMat(C.Structure):
+    _fields_ = [("ptr", c_void_p), ("rows", c_int), ("cols", c_int), ("ld", c_int), ("halo", c_int)]
+
+
+class GemmDesc(C.Structure):
+    """struct kfp16_gemm_desc (include/kaldi_fp16_fused.h)."""
+
+    _fields_ = [
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("a_major", c_int), ("b_major", c_int),
+        ("A", KMat), ("B", KMat),
+        ("groups", c_int), ("kslabs", c_int), ("kslab_len", c_int),
+        ("a_row_off", (c_int * 2) * 2), ("a_col_off", (c_int * 2) * 2),
+        ("b_row_off", (c_int * 2) * 2), ("b_col_off", (c_int * 2) * 2),
+        ("D", c_void_p * 2), ("ldd", c_int), ("d_halo", c_int),
+        ("R", c_void_p * 2), ("ldr", c_int),
+        ("flags", c_u32),
+        ("alpha", c_float), ("beta", c_float), ("res_scale", c_float),
+        ("bias", c_void_p), ("bn_scale", c_void_p), ("bn_shift", c_void_p),
+        ("vec_gstride", c_int),
+        ("mask_out", c_void_p), ("mask_in", c_void_p), ("mask_ld", c_int),
+        ("split_k", c_int), ("ws", c_void_p * 2), ("ws_ld", c_int),
+        ("drop_p", c_float), ("drop_seed", c_u32),
+        ("force_bn", c_int),
+    ]
+
+
+class GPUBatchPtrs(C.Structure):
+    """struct GPUBatchPtrs (include/kaldi_fp16_bridge.h; reference cpp/include/bridge.h:33-50)."""
+
+    _fields_ = [
+        ("d_features", c_void_p), ("d_ivectors", c_void_p), ("d_csr_row_ptr", c_void_p),
+        ("d_csr_col_idx", c_void_p), ("d_csr_labels", c_void_p), ("d_csr_weights", c_void_p),
+        ("d_buffer", c_void_p),
+        ("total_bytes", c_size_t), ("features_bytes", c_size_t), ("ivectors_bytes", c_size_t),
+        ("csr_rowptr_bytes", c_size_t), ("csr_colidx_bytes", c_size_t),
+        ("csr_labels_bytes", c_size_t), ("csr_weights_bytes", c_size_t),
+    ]
+
+
+EPI_BIAS, EPI_RELU, EPI_BN, EPI_RESID, EPI_BETA = 1, 2, 4, 8, 16
+EPI_REF_ROUND, EPI_MASK, EPI_SPLITK, EPI_DROPOUT, EPI_GRADMASK = 32, 64, 128, 256, 512
+K_MAJOR, MN_MAJOR = 0, 1
+
+# name -> (restype, argtypes).  Every symbol declared in include/*.h is listed here; the
+# "not gpu" test-suite checks the list against the headers and against the built library.
+SIGNATURES: dict[str, tuple] = {
+    # ---- kaldi_fp16_fused.h
+    "kfp16_ctx_create": (c_void_p, [c_int]),
+    "kfp16_ctx_destroy": (None, [c_void_p]),
+    "kfp16_ctx_set_stream": (c_int, [c_void_p, c_void_p]),
+    "kfp16_ctx_get_stream": (c_void_p, [c_void_p]),
+    "kfp16_ctx_num_sms": (c_int, [c_void_p]),
+    "kfp16_ctx_set_max_ctas": (c_int, [c_void_p, c_int]),
+    "kfp16_set_default_stream": (None, [c_void_p]),
+    "kfp16_launch_count": (c_u64, []),
+    "kfp16_last_error": (C.c_char_p, []),
+    "kfp16_gemm_ex": (c_int, [c_void_p, C.POINTER(GemmDesc)]),
+    "kfp16_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p]),
+    "kfp16_bn_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p]),
+    "kfp16_bn_relu_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int]),
+    "kfp16_add_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int]),
+    "kfp16_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "kfp16_f32_to_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "kfp16_pad_edges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "kfp16_fold_edges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "kfp16_sgd_update_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_float, c_float, c_size_t]),
+    # ---- kaldi_fp16_ops.h
+    "ops_cublas_create": (c_void_p, []),
+    "ops_cublas_destroy": (None, [c_void_p]),
+    "ops_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_int]),
+    "ops_gemm_strided": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_i64, c_void_p, c_int, c_i64, c_float, c_void_p, c_int, c_i64, c_int]),
+    "ops_relu": (c_int, [c_void_p, c_int]),
+    "ops_sigmoid": (c_int, [c_void_p, c_int]),
+    "ops_tanh_act": (c_int, [c_void_p, c_int]),
+    "ops_clipped_relu": (c_int, [c_void_p, c_int, c_float]),
+    "ops_softmax": (c_int, [c_void_p, c_int, c_int]),
+    "ops_log_softmax": (c_int, [c_void_p, c_int, c_int]),
+    "ops_batchnorm_forward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float]),
+    "ops_batchnorm_forward_rms": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_float]),
+    "ops_add_scaled": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float]),
+    "ops_add": (c_int, [c_void_p, c_void_p, c_int]),
+    "ops_copy": (c_int, [c_void_p, c_void_p, c_int]),
+    "ops_fill": (c_int, [c_void_p, c_int, c_float]),
+    "ops_concat_cols": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int]),
+    "ops_slice_cols": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int]),
+    "ops_combine_feature_maps": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "ops_subsample_rows": (None, [c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
+    "ops_relu_backward": (c_int, [c_void_p, c_void_p, c_int]),
+    "ops_sigmoid_backward": (c_int, [c_void_p, c_void_p, c_int]),
+    "ops_tanh_backward": (c_int, [c_void_p, c_void_p, c_int]),
+    "ops_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "ops_batchnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int]),
+    "ops_fp16_to_fp32": (c_int, [c_void_p, c_void_p, c_int]),
+    "ops_sgd_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int]),
+    "ops_last_error": (C.c_char_p, []),
+    "ops_clear_error": (None, []),
+    # ---- kaldi_fp16_bridge.h
+    "bridge_last_error": (C.c_char_p, []),
+    "bridge_clear_error": (None, []),
+    "bridge_gpu_init": (c_int, [c_int]),
+    "bridge_gpu_get_free_memory": (c_int, [C.POINTER(c_size_t), C.POINTER(c_size_t)]),
+    "bridge_gpu_sync": (c_int, []),
+    "bridge_gpu_malloc": (c_void_p, [c_size_t]),
+    "bridge_gpu_free": (None, [c_void_p]),
+    "bridge_host_alloc": (c_void_p, [c_size_t]),
+    "bridge_host_free": (None, [c_void_p]),
+    "bridge_transfer_fp16": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "bridge_read_fp16": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "bridge_transfer_int32": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "bridge_transfer_float32": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "bridge_read_float32": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "bridge_batch_alloc": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(GPUBatchPtrs)]),
+    "bridge_batch_transfer": (c_int, [C.POINTER(GPUBatchPtrs), c_void_p, c_size_t]),
+    "bridge_batch_free": (None, [C.POINTER(GPUBatchPtrs)]),
+    "bridge_gpu_memset": (None, [c_void_p, c_int, c_size_t]),
+    "bridge_fp16_to_fp32_gpu": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "bridge_fp32_to_fp16_gpu": (c_int, [c_void_p, c_void_p, c_size_t]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the native library and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. "
+            "Run `python -m kaldi_fp16_b200.build`; there is no CPU / PyTorch fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    missing = []
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    if missing:
+        raise ImportError(f"{LIB_PATH} does not export: {', '.join(missing)}")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    lib = load()
+    for getter in (lib.kfp16_last_error, lib.bridge_last_error):
+        e = getter()
+        if e:
+            return e.decode(errors="replace")
+    return "unknown error"
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise NativeError(f"{what}: {last_error()}")

@@ -1,0 +1,665 @@
+// HBM-bound elementwise / data-movement operators of the reference surface
+// (/root/reference/cpp/cuda/ops.cu:26-320, backward_wrappers.cu:41-142) plus the fused helpers the
+// layer executor uses.  The reference runs every one of them as one scalar __half element per
+// thread; here each thread moves 16 bytes per access (8 halves) and the grid is sized as a
+// multiple of the SM count with a grid-stride loop, so the kernels run at HBM speed.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kaldi_fp16_fused.h"
+#include "../../include/kaldi_fp16_ops.h"
+#include "host_common.h"
+
+namespace kfp16 {
+
+constexpr int kThreads = 256;
+
+static int num_sms_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// grid for `work` thread-items: enough CTAs to cover the work, capped at 8 resident CTAs per SM
+static int grid_for(size_t work) {
+  size_t blocks = (work + kThreads - 1) / kThreads;
+  const size_t cap = (size_t)num_sms_cached() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+struct alignas(16) Half8 {
+  __half2 v[4];
+};
+
+__device__ __forceinline__ Half8 ld8(const __half* p) { return *reinterpret_cast<const Half8*>(p); }
+__device__ __forceinline__ void st8(__half* p, const Half8& x) { *reinterpret_cast<Half8*>(p) = x; }
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Generic unary / binary map: op(float)->float on every element, fp16 storage.
+//   body:  n8 vectors of 8 halves handled with 16-byte accesses, then a scalar tail.
+template <class Op>
+__global__ void map1_kernel(__half* __restrict__ x, size_t n, Op op) {
+  const size_t n8 = n >> 3;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    Half8 a = ld8(x + i * 8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.v[j] = __halves2half2(op(a.v[j].x), op(a.v[j].y));
+    st8(x + i * 8, a);
+  }
+  for (size_t i = (n8 << 3) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = op(x[i]);
+}
+template <class Op>
+__global__ void map1_scalar_kernel(__half* __restrict__ x, size_t n, Op op) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = op(x[i]);
+}
+// dst = op(dst, src)
+template <class Op>
+__global__ void map2_kernel(__half* __restrict__ dst, const __half* __restrict__ src, size_t n, Op op) {
+  const size_t n8 = n >> 3;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    Half8 a = ld8(dst + i * 8);
+    const Half8 b = ld8(src + i * 8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.v[j] = __halves2half2(op(a.v[j].x, b.v[j].x), op(a.v[j].y, b.v[j].y));
+    st8(dst + i * 8, a);
+  }
+  for (size_t i = (n8 << 3) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = op(dst[i], src[i]);
+}
+template <class Op>
+__global__ void map2_scalar_kernel(__half* __restrict__ dst, const __half* __restrict__ src, size_t n, Op op) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = op(dst[i], src[i]);
+}
+
+template <class Op>
+static int run_map1(void* data, long long count, Op op, const char* what) {
+  if (count <= 0) return 0;
+  if (!data) { set_error("%s: null pointer", what); return -1; }
+  cudaStream_t s = default_stream();
+  if (al16(data)) map1_kernel<<<grid_for(((size_t)count + 7) / 8), kThreads, 0, s>>>((__half*)data, (size_t)count, op);
+  else map1_scalar_kernel<<<grid_for((size_t)count), kThreads, 0, s>>>((__half*)data, (size_t)count, op);
+  count_launch();
+  return check_launch(what) ? 0 : -1;
+}
+template <class Op>
+static int run_map2(void* dst, const void* src, long long count, Op op, const char* what) {
+  if (count <= 0) return 0;
+  if (!dst || !src) { set_error("%s: null pointer", what); return -1; }
+  cudaStream_t s = default_stream();
+  if (al16(dst) && al16(src))
+    map2_kernel<<<grid_for(((size_t)count + 7) / 8), kThreads, 0, s>>>((__half*)dst, (const __half*)src, (size_t)count, op);
+  else
+    map2_scalar_kernel<<<grid_for((size_t)count), kThreads, 0, s>>>((__half*)dst, (const __half*)src, (size_t)count, op);
+  count_launch();
+  return check_launch(what) ? 0 : -1;
+}
+
+// ---- functors (semantics: the cited reference kernels)
+struct ReluOp {   // ops.cu:26-37: only x < 0 is rewritten, so NaN and -0 pass through
+  __device__ __half operator()(__half x) const { return __hlt(x, __float2half(0.f)) ? __float2half(0.f) : x; }
+};
+struct SigmoidOp {  // ops.cu:39-47
+  __device__ __half operator()(__half x) const { return __float2half(1.0f / (1.0f + expf(-__half2float(x)))); }
+};
+struct TanhOp {  // ops.cu:49-57
+  __device__ __half operator()(__half x) const { return __float2half(tanhf(__half2float(x))); }
+};
+struct ClippedReluOp {  // ops.cu:59-68
+  float ceiling;
+  __device__ __half operator()(__half x) const { return __float2half(fmaxf(0.0f, fminf(__half2float(x), ceiling))); }
+};
+struct FillOp {
+  __half v;
+  __device__ __half operator()(__half) const { return v; }
+};
+struct AddScaledOp {  // ops.cu:207-217   dst = alpha*src + beta*dst
+  float alpha, beta;
+  __device__ __half operator()(__half d, __half s) const {
+    return __float2half(alpha * __half2float(s) + beta * __half2float(d));
+  }
+};
+struct AddOp {  // ops.cu:219-228
+  __device__ __half operator()(__half d, __half s) const { return __float2half(__half2float(d) + __half2float(s)); }
+};
+// backward_wrappers.cu:41-49 : dst = grad, src = saved activation
+struct ReluBwdOp {
+  __device__ __half operator()(__half g, __half x) const { return __hgt(x, __float2half(0.f)) ? g : __float2half(0.f); }
+};
+// backward_wrappers.cu:51-61 : half arithmetic, rounded after every multiply like the reference
+struct SigmoidBwdOp {
+  __device__ __half operator()(__half g, __half o) const {
+    return __hmul(__hmul(g, o), __hsub(__float2half(1.0f), o));
+  }
+};
+struct TanhBwdOp {  // backward_wrappers.cu:63-73
+  __device__ __half operator()(__half g, __half o) const {
+    return __hmul(g, __hsub(__float2half(1.0f), __hmul(o, o)));
+  }
+};
+
+// ---- per-column affine transform  y = x*scale[d] + shift[d]  (batch-norm family)
+// rows x cols, in place or out of place; cols % 8 == 0 and 16B alignment give the vector path.
+__global__ void colscale_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t rows, int cols,
+                                const float* __restrict__ mean, const float* __restrict__ var,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                float target_rms, int mode) {
+  // mode 0: gamma*(x-mean)/sqrt(var+eps)+beta   (ops.cu:171-187)
+  // mode 1: (x-mean)/sqrt(var+eps)*target_rms   (ops.cu:191-204)
+  // mode 2: x*gamma/sqrt(var+eps)               (backward_wrappers.cu:104-115)
+  const size_t total8 = rows * (size_t)cols / 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
+    const int d0 = (int)((i * 8) % (size_t)cols);
+    Half8 a = ld8(x + i * 8);
+    __half* h = reinterpret_cast<__half*>(&a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int d = d0 + j;
+      const float v = __half2float(h[j]);
+      float r;
+      if (mode == 0) r = gamma[d] * ((v - mean[d]) / sqrtf(var[d] + eps)) + beta[d];
+      else if (mode == 1) r = ((v - mean[d]) / sqrtf(var[d] + eps)) * target_rms;
+      else r = v * (gamma[d] / sqrtf(var[d] + eps));
+      h[j] = __float2half(r);
+    }
+    st8(y + i * 8, a);
+  }
+}
+__global__ void colscale_scalar_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t total, int cols,
+                                       const float* __restrict__ mean, const float* __restrict__ var,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                       float target_rms, int mode) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int d = (int)(i % (size_t)cols);
+    const float v = __half2float(x[i]);
+    float r;
+    if (mode == 0) r = gamma[d] * ((v - mean[d]) / sqrtf(var[d] + eps)) + beta[d];
+    else if (mode == 1) r = ((v - mean[d]) / sqrtf(var[d] + eps)) * target_rms;
+    else r = v * (gamma[d] / sqrtf(var[d] + eps));
+    y[i] = __float2half(r);
+  }
+}
+static int run_colscale(const void* x, void* y, long long rows, int cols, const float* mean, const float* var,
+                        const float* gamma, const float* beta, float eps, float rms, int mode, const char* what) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!x || !y) { set_error("%s: null pointer", what); return -1; }
+  cudaStream_t s = default_stream();
+  const size_t total = (size_t)rows * cols;
+  if ((cols % 8) == 0 && al16(x) && al16(y))
+    colscale_kernel<<<grid_for(total / 8), kThreads, 0, s>>>((const __half*)x, (__half*)y, (size_t)rows, cols, mean, var, gamma, beta, eps, rms, mode);
+  else
+    colscale_scalar_kernel<<<grid_for(total), kThreads, 0, s>>>((const __half*)x, (__half*)y, total, cols, mean, var, gamma, beta, eps, rms, mode);
+  count_launch();
+  return check_launch(what) ? 0 : -1;
+}
+
+// ---- strided 2-D block copy: dst[r, dcol0 + c] = src[row0 + r*rstride, scol0 + c]
+// covers concat_cols, slice_cols and subsample_rows (ops.cu:241-254, 290-320)
+__global__ void copy2d_kernel(__half* __restrict__ dst, long long ldd, int dcol0, const __half* __restrict__ src,
+                              long long lds, int scol0, long long row0, int rstride, long long rows, int cols,
+                              int vec) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (vec) {
+    const int c8 = cols >> 3;
+    const size_t total = (size_t)rows * c8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const long long r = (long long)(i / c8);
+      const int c = (int)(i % c8) * 8;
+      st8(dst + r * ldd + dcol0 + c, ld8(src + (row0 + r * rstride) * lds + scol0 + c));
+    }
+  } else {
+    const size_t total = (size_t)rows * cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const long long r = (long long)(i / cols);
+      const int c = (int)(i % cols);
+      dst[r * ldd + dcol0 + c] = src[(row0 + r * rstride) * lds + scol0 + c];
+    }
+  }
+}
+static int run_copy2d(void* dst, long long ldd, int dcol0, const void* src, long long lds, int scol0, long long row0,
+                      int rstride, long long rows, int cols, const char* what) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!dst || !src) { set_error("%s: null pointer", what); return -1; }
+  const int vec = (cols % 8 == 0) && (ldd % 8 == 0) && (lds % 8 == 0) && (dcol0 % 8 == 0) && (scol0 % 8 == 0) && al16(dst) && al16(src);
+  const size_t work = vec ? (size_t)rows * (cols / 8) : (size_t)rows * cols;
+  copy2d_kernel<<<grid_for(work), kThreads, 0, default_stream()>>>((__half*)dst, ldd, dcol0, (const __half*)src, lds, scol0, row0, rstride, rows, cols, vec);
+  count_launch();
+  return check_launch(what) ? 0 : -1;
+}
+
+// ---- combine_feature_maps (ops.cu:258-287): per row, [H*F1 | H*F2] -> H x (F1+F2); the row is
+// staged in shared memory so the permutation runs in place without the reference's temp buffer.
+__global__ void combine_fm_kernel(__half* __restrict__ data, int T, int total_dim, int height, int nf1, int nf2) {
+  extern __shared__ __half srow[];
+  const int tf = nf1 + nf2;
+  for (int t = blockIdx.x; t < T; t += gridDim.x) {
+    __half* row = data + (size_t)t * total_dim;
+    for (int i = threadIdx.x; i < total_dim; i += blockDim.x) srow[i] = row[i];
+    __syncthreads();
+    for (int d = threadIdx.x; d < total_dim; d += blockDim.x) {
+      const int h = d / tf, f = d % tf;
+      const int s = (f < nf1) ? h * nf1 + f : height * nf1 + h * nf2 + (f - nf1);
+      row[d] = srow[s];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- softmax / log-softmax, one warp-group (128 threads) per row, fp32 math (ops.cu:70-166).
+// The reference finds the row max with atomicMax on the float bit pattern, which is wrong for rows
+// whose maximum is negative (the result becomes inf/NaN); this computes the true maximum.
+template <bool LOG>
+__global__ void softmax_kernel(__half* __restrict__ data, int rows, int cols) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    __half* row = data + (size_t)r * cols;
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) m = fmaxf(m, __half2float(row[j]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffff, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < nw; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float s = 0.f;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) s += expf(__half2float(row[j]) - m);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    __syncthreads();
+    if (LOG) {
+      const float lse = m + logf(s);
+      for (int j = threadIdx.x; j < cols; j += blockDim.x) row[j] = __float2half(__half2float(row[j]) - lse);
+    } else {
+      // the reference rounds exp(x-max) to fp16 before normalising (ops.cu:96-110)
+      const float inv = 1.0f / s;
+      for (int j = threadIdx.x; j < cols; j += blockDim.x)
+        row[j] = __float2half(__half2float(__float2half(expf(__half2float(row[j]) - m))) * inv);
+    }
+  }
+}
+
+// ---- transpose dst[c*rows + r] = src[r*cols + c]  (backward_wrappers.cu:75-85), 32x32 smem tiles
+__global__ void transpose_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
+  __shared__ __half tile[32][34];
+  const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+  for (long long t = blockIdx.x; t < (long long)tiles_c * tiles_r; t += gridDim.x) {
+    const int tr = (int)(t / tiles_c) * 32, tc = (int)(t % tiles_c) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = tr + i, c = tc + threadIdx.x;
+      if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = tc + i, r = tr + threadIdx.x;
+      if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __half2float(src[i]);
+}
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
+}
+
+// ---- SGD with momentum on FP32 master weights (backward_wrappers.cu:129-142):
+//   g = float(grad); v = m*v + g; w32 -= lr*v; w16 = half(w32)
+// One launch covers a whole flat parameter bucket (the reference launches once per tensor).
+template <bool GRAD_F32>
+__global__ void sgd_kernel(float* __restrict__ w32, __half* __restrict__ w16, const void* __restrict__ grad,
+                           int round_grad, float grad_scale, float* __restrict__ vel, float lr, float mom, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float g;
+    if (GRAD_F32) {
+      g = reinterpret_cast<const float*>(grad)[i] * grad_scale;
+      if (round_grad) g = __half2float(__float2half_rn(g));
+    } else {
+      g = __half2float(reinterpret_cast<const __half*>(grad)[i]) * grad_scale;
+    }
+    const float v = mom * vel[i] + g;
+    vel[i] = v;
+    const float w = w32[i] - lr * v;
+    w32[i] = w;
+    w16[i] = __float2half_rn(w);
+  }
+}
+
+// ---- fused helpers for the layer executor ------------------------------------------------
+__global__ void bn_fold_kernel(const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                               float target_rms, int D, float* scale, float* shift) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float inv = 1.0f / sqrtf(var[d] + eps);
+  const float g = gamma ? gamma[d] : target_rms;
+  const float b = beta ? beta[d] : 0.0f;
+  const float s = g * inv;
+  scale[d] = s;
+  shift[d] = b - mean[d] * s;
+}
+
+// dZ = mask ? h(dY*scale[n]) : 0      (ops_batchnorm_backward then ops_relu_backward in one pass)
+__global__ void bn_relu_bwd_kernel(const __half* __restrict__ dY, int ldy, const float* __restrict__ scale,
+                                   const uint32_t* __restrict__ mask, int mask_ld, __half* __restrict__ dZ, int ldz,
+                                   size_t rows, int cols) {
+  const int c8 = cols >> 3;
+  const size_t total = rows * (size_t)c8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / c8;
+    const int c = (int)(i % c8) * 8;
+    Half8 a = ld8(dY + r * ldy + c);
+    __half* h = reinterpret_cast<__half*>(&a);
+    uint32_t bits = 0xFFu;
+    if (mask) bits = (mask[r * mask_ld + (c >> 5)] >> (c & 31)) & 0xFFu;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = __half2float(h[j]);
+      if (scale) v *= scale[c + j];
+      h[j] = ((bits >> j) & 1u) ? __float2half_rn(v) : __float2half(0.f);
+    }
+    st8(dZ + r * ldz + c, a);
+  }
+}
+
+// x[t,:] = h(x[t,:] + bias)   (gpu.AddBias, internal/gpu/ops.go:335-351)
+__global__ void add_bias_kernel(__half* __restrict__ x, int ld, const __half* __restrict__ bias, size_t rows, int cols) {
+  const size_t total = rows * (size_t)cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / cols;
+    const int c = (int)(i % cols);
+    __half* p = x + r * ld + c;
+    *p = __float2half_rn(__half2float(*p) + __half2float(bias[c]));
+  }
+}
+
+// column sums with fp32 accumulation: out[n] = sum_t X[t,n]   (AffineBackwardBias)
+// grid (col_chunks of 64 columns, row_splits); each thread owns 2 columns for a strided row set,
+// block-reduces in smem and adds its partial with one atomic per column.
+__global__ void colsum_kernel(const __half* __restrict__ X, int ld, size_t rows, int cols, float* __restrict__ out) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31;   // column pair
+  const int ty = threadIdx.x >> 5;   // 8 row lanes
+  const int c = blockIdx.x * 64 + tx * 2;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < cols) {
+    for (size_t r = (size_t)blockIdx.y * 8 + ty; r < rows; r += (size_t)gridDim.y * 8) {
+      const __half2 v = *reinterpret_cast<const __half2*>(X + r * ld + c);
+      s0 += __low2float(v);
+      s1 += __high2float(v);
+    }
+  }
+  red[ty][tx * 2] = s0;
+  red[ty][tx * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < cols) atomicAdd(out + cc, s);
+  }
+}
+
+// replicate row 0 / row rows-1 of every sequence block into its halo rows
+//   buffer rows: n_seq blocks of (seq_len + 2*halo) rows; X points at the first block's row -halo
+__global__ void pad_edges_kernel(__half* __restrict__ X, int ld, int n_seq, int seq_len, int cols, int halo) {
+  const int c8 = cols >> 3;
+  const size_t per_seq = (size_t)2 * halo * c8;
+  const size_t total = per_seq * n_seq;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int blk = seq_len + 2 * halo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int s = (int)(i / per_seq);
+    const size_t rem = i % per_seq;
+    const int hr = (int)(rem / c8);     // 0..2*halo-1
+    const int c = (int)(rem % c8) * 8;
+    const size_t base = (size_t)s * blk;
+    const size_t dst_row = hr < halo ? base + hr : base + halo + seq_len + (hr - halo);
+    const size_t src_row = hr < halo ? base + halo : base + halo + seq_len - 1;
+    st8(X + dst_row * ld + c, ld8(X + src_row * ld + c));
+  }
+}
+// adjoint of pad_edges: edge row += sum of its halo rows (fp32), halo rows = 0
+__global__ void fold_edges_kernel(__half* __restrict__ G, int ld, int n_seq, int seq_len, int cols, int halo) {
+  const int c8 = cols >> 3;
+  const size_t total = (size_t)n_seq * 2 * c8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int blk = seq_len + 2 * halo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int s = (int)(i / (2 * c8));
+    const int side = (int)((i / c8) & 1);
+    const int c = (int)(i % c8) * 8;
+    const size_t base = (size_t)s * blk;
+    const size_t edge = side == 0 ? base + halo : base + halo + seq_len - 1;
+    const size_t h0 = side == 0 ? base : base + halo + seq_len;
+    Half8 e = ld8(G + edge * ld + c);
+    __half* eh = reinterpret_cast<__half*>(&e);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = __half2float(eh[j]);
+    Half8 z;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z.v[j] = __float2half2_rn(0.f);
+    for (int k = 0; k < halo; ++k) {
+      Half8 h = ld8(G + (h0 + k) * ld + c);
+      const __half* hh = reinterpret_cast<const __half*>(&h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __half2float(hh[j]);
+      st8(G + (h0 + k) * ld + c, z);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) eh[j] = __float2half_rn(acc[j]);
+    st8(G + edge * ld + c, e);
+  }
+}
+
+}  // namespace kfp16
+
+using namespace kfp16;
+
+extern "C" {
+
+// ------------------------------------------------------------------ ops.h forward elementwise
+int ops_relu(void* data, int count) { return run_map1(data, count, ReluOp{}, "relu kernel"); }
+int ops_sigmoid(void* data, int count) { return run_map1(data, count, SigmoidOp{}, "sigmoid kernel"); }
+int ops_tanh_act(void* data, int count) { return run_map1(data, count, TanhOp{}, "tanh kernel"); }
+int ops_clipped_relu(void* data, int count, float ceiling) {
+  return run_map1(data, count, ClippedReluOp{ceiling}, "clipped_relu kernel");
+}
+int ops_fill(void* dst, int count, float val) { return run_map1(dst, count, FillOp{__float2half(val)}, "fill kernel"); }
+int ops_add_scaled(void* dst, const void* src, int count, float alpha, float beta) {
+  return run_map2(dst, src, count, AddScaledOp{alpha, beta}, "add_scaled kernel");
+}
+int ops_add(void* dst, const void* src, int count) { return run_map2(dst, src, count, AddOp{}, "add kernel"); }
+int ops_copy(void* dst, const void* src, int count) {
+  if (count <= 0) return 0;
+  return check_cuda(cudaMemcpyAsync(dst, src, (size_t)count * sizeof(__half), cudaMemcpyDeviceToDevice, default_stream()), "copy") ? 0 : -1;
+}
+
+static int run_softmax(void* data, int rows, int cols, bool log) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!data) { set_error("softmax: null pointer"); return -1; }
+  const int grid = rows < num_sms_cached() * 16 ? rows : num_sms_cached() * 16;
+  if (log) softmax_kernel<true><<<grid, 128, 0, default_stream()>>>((__half*)data, rows, cols);
+  else softmax_kernel<false><<<grid, 128, 0, default_stream()>>>((__half*)data, rows, cols);
+  count_launch();
+  return check_launch(log ? "log_softmax kernel" : "softmax kernel") ? 0 : -1;
+}
+int ops_softmax(void* data, int rows, int cols) { return run_softmax(data, rows, cols, false); }
+int ops_log_softmax(void* data, int rows, int cols) { return run_softmax(data, rows, cols, true); }
+
+int ops_batchnorm_forward(void* x, int T, int D, const float* mean, const float* var, const float* gamma,
+                          const float* beta, float epsilon) {
+  if (T > 0 && D > 0 && (!mean || !var || !gamma || !beta)) { set_error("batchnorm kernel: null statistics"); return -1; }
+  return run_colscale(x, x, T, D, mean, var, gamma, beta, epsilon, 1.0f, 0, "batchnorm kernel");
+}
+int ops_batchnorm_forward_rms(void* x, int T, int D, const float* mean, const float* var, float target_rms,
+                              float epsilon) {
+  if (T > 0 && D > 0 && (!mean || !var)) { set_error("batchnorm_rms kernel: null statistics"); return -1; }
+  return run_colscale(x, x, T, D, mean, var, nullptr, nullptr, epsilon, target_rms, 1, "batchnorm_rms kernel");
+}
+
+int ops_concat_cols(void* dst, int T, int dst_cols, const void* src, int src_cols, int dst_col_offset) {
+  return run_copy2d(dst, dst_cols, dst_col_offset, src, src_cols, 0, 0, 1, T, src_cols, "concat_cols kernel");
+}
+int ops_slice_cols(const void* src, int T, int src_cols, void* dst, int dst_cols, int src_col_offset) {
+  return run_copy2d(dst, dst_cols, 0, src, src_cols, src_col_offset, 0, 1, T, dst_cols, "slice_cols kernel");
+}
+void ops_subsample_rows(void* dst, const void* src, int in_rows, int cols, int stride, int row_offset) {
+  if (stride <= 0 || in_rows <= row_offset) return;
+  const int out_rows = (in_rows - row_offset + stride - 1) / stride;   // ops.cu:633
+  run_copy2d(dst, cols, 0, src, cols, 0, row_offset, stride, out_rows, cols, "subsample_rows kernel");
+}
+int ops_combine_feature_maps(void* data, int T, int total_dim, int height, int nf1, int nf2) {
+  if (T <= 0 || total_dim <= 0) return 0;
+  if (!data) { set_error("combine_feature_maps: null pointer"); return -1; }
+  if (height * (nf1 + nf2) != total_dim) { set_error("combine_feature_maps: height*(nf1+nf2) != total_dim (%d*(%d+%d) != %d)", height, nf1, nf2, total_dim); return -1; }
+  const size_t smem = (size_t)total_dim * sizeof(__half);
+  if (smem > 200 * 1024) { set_error("combine_feature_maps: row of %d halves exceeds shared memory", total_dim); return -1; }
+  if (smem > 48 * 1024 &&
+      !check_cuda(cudaFuncSetAttribute(combine_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "combine smem"))
+    return -1;
+  const int grid = T < num_sms_cached() * 8 ? T : num_sms_cached() * 8;
+  combine_fm_kernel<<<grid, kThreads, smem, default_stream()>>>((__half*)data, T, total_dim, height, nf1, nf2);
+  count_launch();
+  return check_launch("combine_feature_maps kernel") ? 0 : -1;
+}
+
+// ------------------------------------------------------------------ ops.h backward + optimiser
+int ops_relu_backward(const void* x, void* grad, int count) { return run_map2(grad, x, count, ReluBwdOp{}, "relu_backward"); }
+int ops_sigmoid_backward(const void* output, void* grad, int count) { return run_map2(grad, output, count, SigmoidBwdOp{}, "sigmoid_backward"); }
+int ops_tanh_backward(const void* output, void* grad, int count) { return run_map2(grad, output, count, TanhBwdOp{}, "tanh_backward"); }
+
+int ops_transpose(const void* src, void* dst, int M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  if (!src || !dst) { set_error("transpose: null pointer"); return -1; }
+  const long long tiles = (long long)((M + 31) / 32) * ((N + 31) / 32);
+  const long long cap = (long long)num_sms_cached() * 8;
+  transpose_kernel<<<(int)(tiles < cap ? tiles : cap), dim3(32, 8), 0, default_stream()>>>((const __half*)src, (__half*)dst, M, N);
+  count_launch();
+  return check_launch("transpose") ? 0 : -1;
+}
+int ops_batchnorm_backward(const void* grad_out, void* grad_in, const float* gamma, const float* variance, float eps,
+                           int rows, int cols) {
+  if (rows > 0 && cols > 0 && (!gamma || !variance)) { set_error("batchnorm_backward: null statistics"); return -1; }
+  return run_colscale(grad_out, grad_in, rows, cols, nullptr, variance, gamma, nullptr, eps, 1.0f, 2, "batchnorm_backward");
+}
+int ops_fp16_to_fp32(const void* src, float* dst, int count) {
+  if (count <= 0) return 0;
+  if (!src || !dst) { set_error("fp16_to_fp32: null pointer"); return -1; }
+  f16_to_f32_kernel<<<grid_for((size_t)count), kThreads, 0, default_stream()>>>((const __half*)src, dst, (size_t)count);
+  count_launch();
+  return check_launch("fp16_to_fp32") ? 0 : -1;
+}
+int ops_sgd_update(float* w_fp32, void* w_fp16, const void* grad_fp16, float* velocity, float lr, float momentum,
+                   int count) {
+  if (count <= 0) return 0;
+  if (!w_fp32 || !w_fp16 || !grad_fp16 || !velocity) { set_error("sgd_update: null pointer"); return -1; }
+  sgd_kernel<false><<<grid_for((size_t)count), kThreads, 0, default_stream()>>>(w_fp32, (__half*)w_fp16, grad_fp16, 0, 1.0f, velocity, lr, momentum, (size_t)count);
+  count_launch();
+  return check_launch("sgd_update") ? 0 : -1;
+}
+
+// ------------------------------------------------------------------ fused helpers (kaldi_fp16_fused.h)
+static cudaStream_t ctx_stream(kfp16_ctx* ctx) { return ctx ? ctx->stream : default_stream(); }
+
+int kfp16_bn_fold(kfp16_ctx* ctx, const float* mean, const float* var, const float* gamma, const float* beta,
+                  float eps, float target_rms, int D, float* scale, float* shift) {
+  if (D <= 0) return 0;
+  if (!mean || !var || !scale || !shift) { set_error("kfp16_bn_fold: null pointer"); return -1; }
+  bn_fold_kernel<<<(D + 255) / 256, 256, 0, ctx_stream(ctx)>>>(mean, var, gamma, beta, eps, target_rms, D, scale, shift);
+  count_launch();
+  return check_launch("kfp16_bn_fold") ? 0 : -1;
+}
+int kfp16_bn_relu_backward(kfp16_ctx* ctx, const void* dY, int ldy, const float* scale, const uint32_t* mask,
+                           int mask_ld, void* dZ, int ldz, int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!dY || !dZ || (cols % 8) || (ldy % 8) || (ldz % 8) || !al16(dY) || !al16(dZ)) {
+    set_error("kfp16_bn_relu_backward: needs 16B-aligned buffers and cols/ld %% 8 == 0"); return -1;
+  }
+  bn_relu_bwd_kernel<<<grid_for((size_t)rows * (cols / 8)), kThreads, 0, ctx_stream(ctx)>>>(
+      (const __half*)dY, ldy, scale, mask, mask_ld, (__half*)dZ, ldz, (size_t)rows, cols);
+  count_launch();
+  return check_launch("kfp16_bn_relu_backward") ? 0 : -1;
+}
+int kfp16_add_bias(kfp16_ctx* ctx, void* x, int ld, const void* bias, int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!x || !bias) { set_error("kfp16_add_bias: null pointer"); return -1; }
+  add_bias_kernel<<<grid_for((size_t)rows * cols), kThreads, 0, ctx_stream(ctx)>>>((__half*)x, ld, (const __half*)bias, (size_t)rows, cols);
+  count_launch();
+  return check_launch("kfp16_add_bias") ? 0 : -1;
+}
+int kfp16_colsum(kfp16_ctx* ctx, const void* X, int ld, int rows, int cols, float* out_f32, void* out_f16) {
+  if (cols <= 0) return 0;
+  if (!X || !out_f32 || (cols % 2) || (ld % 2)) { set_error("kfp16_colsum: needs fp32 output and even cols/ld"); return -1; }
+  cudaStream_t s = ctx_stream(ctx);
+  if (!check_cuda(cudaMemsetAsync(out_f32, 0, (size_t)cols * sizeof(float), s), "kfp16_colsum memset")) return -1;
+  if (rows > 0) {
+    const int gx = (cols + 63) / 64;
+    int gy = (num_sms_cached() * 4 + gx - 1) / gx;
+    const int max_gy = (rows + 63) / 64;
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    colsum_kernel<<<dim3(gx, gy), kThreads, 0, s>>>((const __half*)X, ld, (size_t)rows, cols, out_f32);
+    count_launch();
+    if (!check_launch("kfp16_colsum")) return -1;
+  }
+  if (out_f16) return kfp16_f32_to_f16(ctx, out_f32, out_f16, (size_t)cols);
+  return 0;
+}
+int kfp16_f32_to_f16(kfp16_ctx* ctx, const float* src, void* dst, size_t n) {
+  if (n == 0) return 0;
+  if (!src || !dst) { set_error("kfp16_f32_to_f16: null pointer"); return -1; }
+  f32_to_f16_kernel<<<grid_for(n), kThreads, 0, ctx_stream(ctx)>>>(src, (__half*)dst, n);
+  count_launch();
+  return check_launch("kfp16_f32_to_f16") ? 0 : -1;
+}
+int kfp16_pad_edges(kfp16_ctx* ctx, void* X, int ld, int n_seq, int seq_len, int cols, int halo) {
+  if (n_seq <= 0 || seq_len <= 0 || halo <= 0 || cols <= 0) return 0;
+  if (!X || (cols % 8) || (ld % 8) || !al16(X)) { set_error("kfp16_pad_edges: needs a 16B-aligned buffer and cols/ld %% 8 == 0"); return -1; }
+  pad_edges_kernel<<<grid_for((size_t)n_seq * 2 * halo * (cols / 8)), kThreads, 0, ctx_stream(ctx)>>>((__half*)X, ld, n_seq, seq_len, cols, halo);
+  count_launch();
+  return check_launch("kfp16_pad_edges") ? 0 : -1;
+}
+int kfp16_fold_edges(kfp16_ctx* ctx, void* G, int ld, int n_seq, int seq_len, int cols, int halo) {
+  if (n_seq <= 0 || seq_len <= 0 || halo <= 0 || cols <= 0) return 0;
+  if (!G || (cols % 8) || (ld % 8) || !al16(G)) { set_error("kfp16_fold_edges: needs a 16B-aligned buffer and cols/ld %% 8 == 0"); return -1; }
+  fold_edges_kernel<<<grid_for((size_t)n_seq * 2 * (cols / 8)), kThreads, 0, ctx_stream(ctx)>>>((__half*)G, ld, n_seq, seq_len, cols, halo);
+  count_launch();
+  return check_launch("kfp16_fold_edges") ? 0 : -1;
+}
+int kfp16_sgd_update_flat(kfp16_ctx* ctx, float* w32, void* w16, const void* grad, int grad_is_f32, int round_grad,
+                          float grad_scale, float* velocity, float lr, float momentum, size_t n) {
+  if (n == 0) return 0;
+  if (!w32 || !w16 || !grad || !velocity) { set_error("kfp16_sgd_update_flat: null pointer"); return -1; }
+  cudaStream_t s = ctx_stream(ctx);
+  if (grad_is_f32) sgd_kernel<true><<<grid_for(n), kThreads, 0, s>>>(w32, (__half*)w16, grad, round_grad, grad_scale, velocity, lr, momentum, n);
+  else sgd_kernel<false><<<grid_for(n), kThreads, 0, s>>>(w32, (__half*)w16, grad, 0, grad_scale, velocity, lr, momentum, n);
+  count_launch();
+  return check_launch("kfp16_sgd_update_flat") ? 0 : -1;
+}
+
+}  // extern "C"

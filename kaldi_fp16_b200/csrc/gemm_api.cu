@@ -1,0 +1,356 @@
+// Host side of the tcgen05 GEMM: TMA tensor maps, tile-shape dispatch, the fused C-ABI
+// (include/kaldi_fp16_fused.h) and the reference's ops_gemm / ops_cublas_* entry points
+// (/root/reference/cpp/cuda/ops.cu:336-433) re-implemented on top of it.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/kaldi_fp16_fused.h"
+#include "../../include/kaldi_fp16_ops.h"
+#include "gemm_sm100.cuh"
+#include "host_common.h"
+
+namespace kfp16 {
+
+// ------------------------------------------------------------------ errors / counters
+static thread_local char g_err[512] = {0};
+std::atomic<unsigned long long> g_launches{0};
+static cudaStream_t g_default_stream = nullptr;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err[0] ? g_err : nullptr; }
+void clear_error() { g_err[0] = 0; }
+cudaStream_t default_stream() { return g_default_stream; }
+
+bool check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return false;
+}
+bool check_launch(const char* what) { return check_cuda(cudaGetLastError(), what); }
+
+// ------------------------------------------------------------------ TMA tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D fp16 row-major matrix [outer x inner], `ld` elements between rows, 128B-swizzled boxes.
+static bool make_map_2d(CUtensorMap* m, const void* base, long long inner, long long outer,
+                        long long ld, int box_inner, int box_outer, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return false; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 8) != 0 || inner < 1 || outer < 1) {
+    set_error("%s: TMA needs 16-byte aligned base and ld %% 8 == 0 (ptr=%p ld=%lld inner=%lld outer=%lld)",
+              what, base, ld, inner, outer);
+    return false;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%dx%d", what,
+              (int)r, inner, outer, ld, box_inner, box_outer);
+    return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------ dispatch
+template <int BN, bool A_MN, bool B_MN>
+static bool launch_cfg(kfp16_ctx* ctx, const GemmParams& p, int grid) {
+  using Cfg = GemmCfg<BN, A_MN, B_MN>;
+  static bool attr_done = false;   // per instantiation
+  if (!attr_done) {
+    if (!check_cuda(cudaFuncSetAttribute(gemm_f16_sm100<BN, A_MN, B_MN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+                    "cudaFuncSetAttribute(gemm smem)"))
+      return false;
+    attr_done = true;
+  }
+  gemm_f16_sm100<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmemBytes, ctx->stream>>>(p);
+  count_launch();
+  return check_launch("gemm_f16_sm100 launch");
+}
+
+template <int BN>
+static bool launch_bn(kfp16_ctx* ctx, const GemmParams& p, int grid, bool a_mn, bool b_mn) {
+  if (!a_mn && !b_mn) return launch_cfg<BN, false, false>(ctx, p, grid);
+  if (!a_mn && b_mn) return launch_cfg<BN, false, true>(ctx, p, grid);
+  if (a_mn && !b_mn) return launch_cfg<BN, true, false>(ctx, p, grid);
+  return launch_cfg<BN, true, true>(ctx, p, grid);
+}
+
+static int pick_bn(int N, int m_tiles, int groups, int split_k, int ctas) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  if (N <= 160) return 160;
+  if (N <= 256) return 256;
+  // N > 256: weigh wave quantisation (cost ~ waves * BN; a wider tile re-reads A less)
+  const int cand[2] = {256, 128};
+  int best = 256;
+  double best_cost = 1e30;
+  for (int i = 0; i < 2; ++i) {
+    const int bn = cand[i];
+    const long long tiles = (long long)m_tiles * ((N + bn - 1) / bn) * groups * split_k;
+    const long long waves = (tiles + ctas - 1) / ctas;
+    const double cost = (double)waves * (bn + 24);
+    if (cost < best_cost * 0.97) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+// Generic SIMT fallback for shapes TMA cannot address (ld % 8 != 0, K == 1 bias trick, ...).
+// fp16 in, fp32 accumulate, fp16 out -- same numerics contract, negligible share of the work.
+__global__ void gemm_simt_fallback(int M, int N, int K, float alpha, const __half* A, long long a_sm,
+                                   long long a_sk, const __half* B, long long b_sk, long long b_sn,
+                                   float beta, __half* C, int ldc) {
+  __shared__ float sA[16][17], sB[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    sA[ty][tx] = (row < M && k0 + tx < K) ? __half2float(A[row * a_sm + (k0 + tx) * a_sk]) : 0.f;
+    sB[ty][tx] = (k0 + ty < K && col < N) ? __half2float(B[(k0 + ty) * b_sk + col * b_sn]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(sA[ty][k], sB[k][tx], acc);
+    __syncthreads();
+  }
+  if (row < M && col < N) {
+    float v = alpha * acc;
+    if (beta != 0.f) v += beta * __half2float(C[(size_t)row * ldc + col]);
+    C[(size_t)row * ldc + col] = __float2half_rn(v);
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace kfp16
+
+using namespace kfp16;
+
+extern "C" {
+
+// ------------------------------------------------------------------ context
+kfp16_ctx* kfp16_ctx_create(int device_id) {
+  int ndev = 0;
+  if (!check_cuda(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount")) return nullptr;
+  if (device_id < 0 || device_id >= ndev) { set_error("invalid device %d (have %d)", device_id, ndev); return nullptr; }
+  if (!check_cuda(cudaSetDevice(device_id), "cudaSetDevice")) return nullptr;
+  cudaDeviceProp prop;
+  if (!check_cuda(cudaGetDeviceProperties(&prop, device_id), "cudaGetDeviceProperties")) return nullptr;
+  if (prop.major != 10) {
+    set_error("kaldi_fp16_b200 needs an sm_100 GPU (found sm_%d%d); there is no fallback path", prop.major, prop.minor);
+    return nullptr;
+  }
+  kfp16_ctx* c = new kfp16_ctx();
+  c->device = device_id;
+  c->num_sms = prop.multiProcessorCount;
+  c->stream = g_default_stream;
+  return c;
+}
+void kfp16_ctx_destroy(kfp16_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->ws) cudaFree(ctx->ws);
+  delete ctx;
+}
+int kfp16_ctx_set_stream(kfp16_ctx* ctx, void* s) { if (!ctx) return -1; ctx->stream = (cudaStream_t)s; return 0; }
+void* kfp16_ctx_get_stream(kfp16_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int kfp16_ctx_num_sms(kfp16_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+int kfp16_ctx_set_max_ctas(kfp16_ctx* ctx, int n) { if (!ctx) return -1; ctx->max_ctas = n; return 0; }
+void kfp16_set_default_stream(void* s) { g_default_stream = (cudaStream_t)s; }
+unsigned long long kfp16_launch_count(void) { return g_launches.load(); }
+const char* kfp16_last_error(void) { return get_error(); }
+
+// ------------------------------------------------------------------ fused GEMM
+int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
+  if (!ctx || !d) { set_error("kfp16_gemm_ex: null argument"); return -1; }
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return 0;   // empty problem: nothing to do
+  const int groups = d->groups < 1 ? 1 : d->groups;
+  const int kslabs = d->kslabs < 1 ? 1 : d->kslabs;
+  const int kslab_len = d->kslab_len > 0 ? d->kslab_len : d->K;
+  if (groups > kMaxGroups || kslabs > kMaxSlabs) { set_error("kfp16_gemm_ex: at most 2 groups / 2 K-slabs"); return -1; }
+  if (kslabs * kslab_len != d->K) { set_error("kfp16_gemm_ex: K (%d) != kslabs*kslab_len (%d*%d)", d->K, kslabs, kslab_len); return -1; }
+  if ((d->N % 8) || (kslab_len % 8)) { set_error("kfp16_gemm_ex: N and K must be multiples of 8 (N=%d K=%d)", d->N, kslab_len); return -1; }
+  if (kslabs > 1 && (kslab_len % 16)) {
+    // a partial UMMA K step relies on TMA zero-fill past the matrix edge; between slabs there is none
+    set_error("kfp16_gemm_ex: kslab_len must be a multiple of 16 when K is spliced (got %d)", kslab_len); return -1;
+  }
+  const bool a_mn = d->a_major == KFP16_MN_MAJOR, b_mn = d->b_major == KFP16_MN_MAJOR;
+  uint32_t flags = d->flags & ~(uint32_t)KFP16_EPI_SPLITK;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.groups = groups; p.kslabs = kslabs; p.kslab_len = kslab_len;
+
+  const int m_tiles = (d->M + kBM - 1) / kBM;
+  const int kb_total = kslabs * ((kslab_len + kBK - 1) / kBK);
+  int split_k = d->split_k > 1 ? d->split_k : 1;
+  if (split_k > kb_total) split_k = kb_total;
+  if (split_k > 1) {   // make every split non-empty
+    const int per = (kb_total + split_k - 1) / split_k;
+    split_k = (kb_total + per - 1) / per;
+  }
+  if (d->split_k > 1) flags |= EPI_SPLITK;   // caller asked for fp32 accumulation into ws
+  p.split_k = split_k;
+
+  int ctas = ctx->num_sms;
+  if (ctx->max_ctas > 0 && ctx->max_ctas < ctas) ctas = ctx->max_ctas;
+  int bn = d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, groups, split_k, ctas);
+  if (bn != 64 && bn != 128 && bn != 160 && bn != 256) { set_error("kfp16_gemm_ex: unsupported tile width %d", bn); return -1; }
+  if (!(flags & EPI_SPLITK) && (bn % 64) != 0 && d->N > bn) {
+    // the last 64-wide store chunk of a 160-wide tile would spill into the next tile
+    set_error("kfp16_gemm_ex: tile width %d needs N <= %d unless split-K", bn, bn); return -1;
+  }
+
+  // operand maps (halo rows are part of the mapped tensor so spliced reads can address them)
+  const kfp16_mat& A = d->A; const kfp16_mat& B = d->B;
+  if (!A.ptr || !B.ptr) { set_error("kfp16_gemm_ex: null operand"); return -1; }
+  const __half* a_base = (const __half*)A.ptr - (long long)A.halo * A.ld;
+  const __half* b_base = (const __half*)B.ptr - (long long)B.halo * B.ld;
+  if (!make_map_2d(&p.tmA, a_base, A.cols, (long long)A.rows + 2 * A.halo, A.ld, 64, a_mn ? 64 : kBM, "A")) return -1;
+  if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? 64 : bn, "B")) return -1;
+  for (int g = 0; g < groups; ++g)
+    for (int s = 0; s < kslabs; ++s) {
+      p.a_row_off[g][s] = d->a_row_off[g][s] + A.halo; p.a_col_off[g][s] = d->a_col_off[g][s];
+      p.b_row_off[g][s] = d->b_row_off[g][s] + B.halo; p.b_col_off[g][s] = d->b_col_off[g][s];
+    }
+
+  p.flags = flags;
+  p.alpha = d->alpha; p.beta = d->beta; p.res_scale = d->res_scale;
+  p.bias = (const __half*)d->bias; p.bn_scale = d->bn_scale; p.bn_shift = d->bn_shift;
+  p.vec_gstride = d->vec_gstride;
+  p.mask_out = d->mask_out; p.mask_in = d->mask_in; p.mask_ld = d->mask_ld;
+  p.ws_ld = d->ws_ld; p.ldd = d->ldd; p.halo = d->d_halo;
+  p.drop_p = d->drop_p; p.drop_seed = d->drop_seed;
+  if ((flags & EPI_BIAS) && !p.bias) { set_error("kfp16_gemm_ex: EPI_BIAS without bias"); return -1; }
+  if ((flags & EPI_BN) && (!p.bn_scale || !p.bn_shift)) { set_error("kfp16_gemm_ex: EPI_BN without scale/shift"); return -1; }
+  if ((flags & EPI_MASK) && !p.mask_out) { set_error("kfp16_gemm_ex: EPI_MASK without mask_out"); return -1; }
+  if ((flags & EPI_GRADMASK) && !p.mask_in) { set_error("kfp16_gemm_ex: EPI_GRADMASK without mask_in"); return -1; }
+
+  for (int g = 0; g < groups; ++g) {
+    if (flags & EPI_SPLITK) {
+      if (!d->ws[g] || d->ws_ld < d->N || (d->ws_ld % 4) || !aligned16(d->ws[g])) {
+        set_error("kfp16_gemm_ex: split-K needs a 16B-aligned fp32 workspace with ws_ld >= N, ws_ld %% 4 == 0"); return -1;
+      }
+      p.ws[g] = d->ws[g];
+    } else {
+      if (!d->D[g]) { set_error("kfp16_gemm_ex: null output"); return -1; }
+      p.d_raw[g] = (__half*)d->D[g];
+      if (!make_map_2d(&p.tmD[g], d->D[g], d->N, d->M, d->ldd, 64, kBM, "D")) return -1;
+      if (flags & (EPI_RESID | EPI_BETA)) {
+        if (!d->R[g]) { set_error("kfp16_gemm_ex: residual / beta requested without R"); return -1; }
+        if (!make_map_2d(&p.tmR[g], d->R[g], d->N, d->M, d->ldr, 64, kBM, "R")) return -1;
+      }
+    }
+  }
+
+  const long long tiles = (long long)m_tiles * ((d->N + bn - 1) / bn) * groups * split_k;
+  const int grid = (int)(tiles < ctas ? tiles : ctas);
+  if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+  bool ok = false;
+  switch (bn) {
+    case 64: ok = launch_bn<64>(ctx, p, grid, a_mn, b_mn); break;
+    case 128: ok = launch_bn<128>(ctx, p, grid, a_mn, b_mn); break;
+    case 160: ok = launch_bn<160>(ctx, p, grid, a_mn, b_mn); break;
+    case 256: ok = launch_bn<256>(ctx, p, grid, a_mn, b_mn); break;
+  }
+  return ok ? 0 : -1;
+}
+
+int kfp16_gemm(kfp16_ctx* ctx, int M, int N, int K, float alpha, const void* A, int transA,
+               const void* B, int transB, float beta, void* C) {
+  if (!ctx) { set_error("kfp16_gemm: null context (create one with ops_cublas_create / kfp16_ctx_create)"); return -1; }
+  if (M <= 0 || N <= 0) return 0;
+  if (!A || !B || !C) { set_error("kfp16_gemm: null pointer"); return -1; }
+  const int lda = transA ? M : K, ldb = transB ? K : N;
+  const bool tma_ok = K > 0 && (N % 8) == 0 && (K % 8) == 0 && (lda % 8) == 0 && (ldb % 8) == 0 &&
+                      aligned16(A) && aligned16(B) && aligned16(C);
+  if (tma_ok) {
+    kfp16_gemm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.M = M; d.N = N; d.K = K;
+    d.a_major = transA ? KFP16_MN_MAJOR : KFP16_K_MAJOR;
+    d.b_major = transB ? KFP16_K_MAJOR : KFP16_MN_MAJOR;
+    d.A.ptr = A; d.A.rows = transA ? K : M; d.A.cols = transA ? M : K; d.A.ld = lda;
+    d.B.ptr = B; d.B.rows = transB ? N : K; d.B.cols = transB ? K : N; d.B.ld = ldb;
+    d.groups = 1; d.kslabs = 1; d.kslab_len = K;
+    d.D[0] = C; d.ldd = N; d.R[0] = C; d.ldr = N;
+    d.alpha = alpha; d.beta = beta;
+    d.flags = (beta != 0.0f) ? KFP16_EPI_BETA : 0;
+    return kfp16_gemm_ex(ctx, &d);
+  }
+  if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+  dim3 block(16, 16), grid((N + 15) / 16, (M + 15) / 16);
+  gemm_simt_fallback<<<grid, block, 0, ctx->stream>>>(
+      M, N, K, alpha, (const __half*)A, transA ? 1 : K, transA ? M : 1, (const __half*)B,
+      transB ? 1 : N, transB ? K : 1, beta, (__half*)C, N);
+  count_launch();
+  return check_launch("gemm_simt_fallback") ? 0 : -1;
+}
+
+// ------------------------------------------------------------------ reference surface (ops.h)
+void* ops_cublas_create(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  return (void*)kfp16_ctx_create(dev);
+}
+void ops_cublas_destroy(void* handle) { kfp16_ctx_destroy((kfp16_ctx*)handle); }
+
+// C = alpha*A*B + beta*C, row-major, dense: like the reference the lda/ldb/ldc arguments are
+// accepted but the leading dimensions are K, N, N (ops.cu:381-392 hard-wires them).
+int ops_gemm(void* handle, int M, int N, int K, float alpha, const void* A, int lda, const void* B,
+             int ldb, float beta, void* C, int ldc) {
+  (void)lda; (void)ldb; (void)ldc;
+  if (!handle) { set_error("ops_gemm: null handle"); return -1; }
+  if (kfp16_gemm((kfp16_ctx*)handle, M, N, K, alpha, A, 0, B, 0, beta, C) != 0) {
+    char tmp[400];
+    snprintf(tmp, sizeof(tmp), "%s", get_error() ? get_error() : "?");
+    set_error("ops_gemm failed: %s (M=%d N=%d K=%d)", tmp, M, N, K);
+    return -1;
+  }
+  return 0;
+}
+
+int ops_gemm_strided(void* handle, int M, int N, int K, float alpha, const void* A, int lda,
+                     int64_t strideA, const void* B, int ldb, int64_t strideB, float beta, void* C,
+                     int ldc, int64_t strideC, int batch_count) {
+  for (int b = 0; b < batch_count; ++b) {
+    if (ops_gemm(handle, M, N, K, alpha, (const __half*)A + b * strideA, lda,
+                 (const __half*)B + b * strideB, ldb, beta, (__half*)C + b * strideC, ldc) != 0)
+      return -1;
+  }
+  return 0;
+}
+
+const char* ops_last_error(void) { return get_error(); }
+void ops_clear_error(void) { clear_error(); }
+
+}  // extern "C"

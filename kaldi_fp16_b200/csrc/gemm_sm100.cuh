@@ -1,0 +1,418 @@
+// Hand-written sm_100a FP16 GEMM (FP32 accumulate in TMEM) with fused epilogue.
+//
+// Replaces the reference's only matrix multiply, cublasGemmEx behind ops_gemm
+// (/root/reference/cpp/cuda/ops.cu:366-400), and the transposes + extra GEMMs its Go
+// layer builds around it (internal/gpu/backward_ops.go:162-253, ops.go:335-351).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1      MMA issuer     (one elected thread, tcgen05.mma kind::f16, M=128 x N=BN x K=16)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       (tcgen05.ld -> fused epilogue -> swizzled smem -> TMA store,
+//                               or fp32 red.add for split-K)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Operands may be K-major or MN-major (no transpose kernels: the UMMA descriptors take
+// X^T / W^T directly) and the K dimension may be made of up to 2 "slabs" whose TMA
+// coordinates are offset independently -- that is how time-splicing [X(t-s) | X(t)] is fed
+// to the tensor cores without materialising the spliced matrix
+// (reference: internal/nnet/forward.go:699-790 builds it with 3 copies + 2 concat kernels).
+#pragma once
+#include "sm100_ptx.cuh"
+
+namespace kfp16 {
+
+constexpr int kBM = 128;          // UMMA M (cta_group::1)
+constexpr int kBK = 64;           // one 128-byte swizzle row of K per stage
+constexpr int kGemmThreads = 256; // 8 warps
+constexpr int kMaxGroups = 2;
+constexpr int kMaxSlabs = 2;
+
+enum EpiFlags : uint32_t {
+  EPI_BIAS = 1u << 0,       // + bias[n] (fp16 bias row, as gpu.AddBias)
+  EPI_RELU = 1u << 1,       // max(x,0) keeping NaN / -0 like kernel_relu
+  EPI_BN = 1u << 2,         // x*bn_scale[n] + bn_shift[n]   (inference batch-norm)
+  EPI_RESID = 1u << 3,      // out = res_scale*R + x         (TDNN-F bypass, ops_add_scaled)
+  EPI_BETA = 1u << 4,       // acc = alpha*acc + beta*R      (cuBLAS beta path)
+  EPI_REF_ROUND = 1u << 5,  // round to fp16 between fused stages exactly where the reference stores fp16
+  EPI_MASK = 1u << 6,       // emit relu bit-mask (x > 0), 1 bit / element
+  EPI_SPLITK = 1u << 7,     // fp32 red.add of the partial tile into ws (no fp16 store)
+  EPI_DROPOUT = 1u << 8,    // inverted dropout, counter-based mask (seed,row,col)
+  EPI_GRADMASK = 1u << 9,   // x = mask_in bit ? x : 0      (relu backward fused in producer)
+};
+
+struct GemmParams {
+  CUtensorMap tmA, tmB;
+  CUtensorMap tmD[kMaxGroups];  // per-group output view  (TMA store clips to the view)
+  CUtensorMap tmR[kMaxGroups];  // per-group residual / C-in view (TMA load)
+  int M, N, K;                  // per-group problem size; K = kslabs * kslab_len
+  int groups, kslabs, kslab_len;
+  int split_k;                  // >1 => EPI_SPLITK
+  int a_row_off[kMaxGroups][kMaxSlabs], a_col_off[kMaxGroups][kMaxSlabs];
+  int b_row_off[kMaxGroups][kMaxSlabs], b_col_off[kMaxGroups][kMaxSlabs];
+  uint32_t flags;
+  float alpha, beta, res_scale;
+  const __half* bias;           // [N]   (group g uses bias + g*bias_gstride)
+  const float* bn_scale;        // [N]
+  const float* bn_shift;        // [N]
+  int vec_gstride;              // per-group offset into bias/bn vectors
+  uint32_t* mask_out;           // [M x mask_ld] words
+  const uint32_t* mask_in;
+  int mask_ld;
+  float* ws[kMaxGroups];        // split-K fp32 accumulation target [M x ws_ld]
+  int ws_ld;
+  __half* d_raw[kMaxGroups];    // raw output pointer for halo replication
+  int ldd;
+  int halo;                     // replicate row 0 / row M-1 into `halo` rows before / after
+  float drop_p; uint32_t drop_seed;
+};
+
+// counter-based uniform in [0,1): shared by the CUDA epilogue and the CPU oracle (oracle/kaldi_oracle.c)
+__host__ __device__ inline float dropout_uniform(uint32_t seed, uint32_t row, uint32_t col) {
+  uint32_t x = seed ^ (row * 0x9E3779B1u) ^ (col * 0x85EBCA77u);
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+struct GemmCfg {
+  static constexpr int kAChunks = A_MN ? 2 : 1;                // 64-wide M chunks (MN-major)
+  static constexpr int kBChunks = B_MN ? (BN + 63) / 64 : 1;   // 64-wide N chunks (MN-major)
+  static constexpr int kABytes = kBM * kBK * 2;                // 16 KB
+  static constexpr int kBBytes = B_MN ? kBChunks * 64 * kBK * 2 : BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiBufBytes = kBM * 64 * 2;            // [128 x 64] fp16 staging, SW128
+  static constexpr int kNumEpiBufs = 2;
+  static constexpr int kSmemBudget = 227 * 1024 - 2048;        // barriers + alignment slack
+  static constexpr int kStagesRaw = (kSmemBudget - kNumEpiBufs * kEpiBufBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kNumEpiBufs * kEpiBufBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert(kStages >= 2, "tile too large for shared memory");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_f16_sm100(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN, A_MN, B_MN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kNumEpiBufs * Cfg::kEpiBufBytes);
+  uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]        epilogue -> MMA
+  uint64_t* rfull_bar = tempty_bar + 2;       // [2]        residual TMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int tiles_per_split = m_tiles * n_tiles * p.groups;
+  const int total_tiles = tiles_per_split * p.split_k;
+  const int kb_total = p.kslabs * ((p.kslab_len + kBK - 1) / kBK);   // k-blocks over all slabs
+  const int kb_per_slab = (p.kslab_len + kBK - 1) / kBK;
+  const int kb_per_split = (kb_total + p.split_k - 1) / p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    if (!(p.flags & EPI_SPLITK)) tma_prefetch_desc(&p.tmD[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+      mbar_init(&rfull_bar[i], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int id = tile;
+        const int n_blk = id % n_tiles; id /= n_tiles;
+        const int m_blk = id % m_tiles; id /= m_tiles;
+        const int g = id % p.groups;
+        const int ks = id / p.groups;
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int slab = kb / kb_per_slab;
+          const int k_in = (kb - slab * kb_per_slab) * kBK;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (!A_MN) {
+            tma_load_2d(sa, &p.tmA, &full_bar[stage], k_in + p.a_col_off[g][slab],
+                        m_blk * kBM + p.a_row_off[g][slab]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              tma_load_2d(sa + c * (64 * kBK * 2), &p.tmA, &full_bar[stage],
+                          m_blk * kBM + c * 64 + p.a_col_off[g][slab],
+                          k_in + p.a_row_off[g][slab]);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &p.tmB, &full_bar[stage], k_in + p.b_col_off[g][slab],
+                        n_blk * BN + p.b_row_off[g][slab]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < Cfg::kBChunks; ++c)
+              tma_load_2d(sb + c * (64 * kBK * 2), &p.tmB, &full_bar[stage],
+                          n_blk * BN + c * 64 + p.b_col_off[g][slab],
+                          k_in + p.b_row_off[g][slab]);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kBM, BN, A_MN, B_MN);
+      // K-major: 8-row groups 1024 B apart (SBO); MN-major: 64-wide chunks 8 KB apart (LBO),
+      // 8-k groups 1024 B apart (SBO).
+      constexpr uint32_t a_lbo = A_MN ? 64 * kBK * 2 : 16, a_sbo = 1024;
+      constexpr uint32_t b_lbo = B_MN ? 64 * kBK * 2 : 16, b_sbo = 1024;
+      constexpr uint32_t a_kstep = A_MN ? 2048 : 32;   // bytes per UMMA K=16
+      constexpr uint32_t b_kstep = B_MN ? 2048 : 32;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile / tiles_per_split;
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kb_total);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int slab = kb / kb_per_slab;
+          const int k_in = (kb - slab * kb_per_slab) * kBK;
+          const int k16s = min(kBK, p.kslab_len - k_in + 15) >> 4;   // partial last block (K % 64)
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, kLayoutSW128);
+          const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, kLayoutSW128);
+          for (int k = 0; k < k16s; ++k) {
+            umma_f16(d_tmem, adesc + ((uint64_t)(k * a_kstep) >> 4),
+                     bdesc + ((uint64_t)(k * b_kstep) >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ========================================================= epilogue
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 128;
+    const uint32_t flags = p.flags;
+    const bool use_r = (flags & (EPI_RESID | EPI_BETA)) != 0;
+    const bool ref_round = (flags & EPI_REF_ROUND) != 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t rphase[2] = {0, 0};
+    int chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int id = tile;
+      const int n_blk = id % n_tiles; id /= n_tiles;
+      const int m_blk = id % m_tiles; id /= m_tiles;
+      const int g = id % p.groups;
+      const int row = m_blk * kBM + row_in_tile;
+      const int n0 = n_blk * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + acc * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
+
+      if (flags & EPI_SPLITK) {
+        float* ws_row = p.ws[g] + (size_t)row * p.ws_ld;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_acc + c, v);
+          tmem_ld_wait();
+          if (row < p.M) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int col = n0 + c + j;
+              if (col + 4 <= p.N) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(ws_row + col),
+                             "f"(__uint_as_float(v[j]) * p.alpha),
+                             "f"(__uint_as_float(v[j + 1]) * p.alpha),
+                             "f"(__uint_as_float(v[j + 2]) * p.alpha),
+                             "f"(__uint_as_float(v[j + 3]) * p.alpha)
+                             : "memory");
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+
+      const int voff = g * p.vec_gstride;
+#pragma unroll 1
+      for (int c64 = 0; c64 < BN; c64 += 64, ++chunk_ctr) {
+        const int buf = chunk_ctr & 1;
+        uint8_t* sbuf = smem_epi + buf * Cfg::kEpiBufBytes;
+        // the TMA store that last read this buffer (2 chunks ago) must have drained
+        if (epi_tid == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        if (use_r) {
+          if (epi_tid == 0) {
+            mbar_arrive_expect_tx(&rfull_bar[buf], Cfg::kEpiBufBytes);
+            tma_load_2d(sbuf, &p.tmR[g], &rfull_bar[buf], n0 + c64, m_blk * kBM);
+          }
+          mbar_wait(&rfull_bar[buf], rphase[buf]);
+          rphase[buf] ^= 1;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = c64 + h * 32;
+          if (c >= BN) break;
+          uint32_t v[32];
+          tmem_ld_32x32(t_acc + c, v);
+          tmem_ld_wait();
+          uint32_t packed[16];
+          uint32_t maskword = 0;
+          uint32_t min_word = 0xFFFFFFFFu;
+          if (flags & EPI_GRADMASK) {
+            min_word = (row < p.M) ? __ldg(p.mask_in + (size_t)row * p.mask_ld + ((n0 + c) >> 5)) : 0u;
+          }
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {      // 8 columns = one 16-byte smem chunk
+            const int col = n0 + c + j8 * 8;
+            const bool col_ok = (col + 8 <= p.N);
+            // 16B chunk index inside the 128-byte staged row, XOR-swizzled like TMA SW128
+            const int chunk16 = (h * 4 + j8) ^ (row_in_tile & 7);
+            uint4* sptr = reinterpret_cast<uint4*>(sbuf + row_in_tile * 128 + chunk16 * 16);
+            float r[8];
+            if (use_r) {
+              uint4 rv = *sptr;
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { float2 f = __half22float2(rh[e]); r[2 * e] = f.x; r[2 * e + 1] = f.y; }
+            }
+            float bia[8], bsc[8], bsh[8];
+            if (flags & EPI_BIAS) {
+              uint4 bv = col_ok ? __ldg(reinterpret_cast<const uint4*>(p.bias + voff + col)) : make_uint4(0, 0, 0, 0);
+              const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { float2 f = __half22float2(bh[e]); bia[2 * e] = f.x; bia[2 * e + 1] = f.y; }
+            }
+            if (flags & EPI_BN) {
+#pragma unroll
+              for (int e = 0; e < 8; e += 4) {
+                float4 s4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bn_scale + voff + col + e)) : make_float4(0, 0, 0, 0);
+                float4 h4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bn_shift + voff + col + e)) : make_float4(0, 0, 0, 0);
+                bsc[e] = s4.x; bsc[e + 1] = s4.y; bsc[e + 2] = s4.z; bsc[e + 3] = s4.w;
+                bsh[e] = h4.x; bsh[e + 1] = h4.y; bsh[e + 2] = h4.z; bsh[e + 3] = h4.w;
+              }
+            }
+            __half out[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = j8 * 8 + e;
+              float x = __uint_as_float(v[j]) * p.alpha;
+              if (flags & EPI_BETA) x = fmaf(p.beta, r[e], x);
+              if (ref_round) x = __half2float(__float2half_rn(x));
+              if (flags & EPI_BIAS) {
+                x += bia[e];
+                if (ref_round) x = __half2float(__float2half_rn(x));
+              }
+              if (flags & EPI_RELU) {
+                x = (x < 0.0f) ? 0.0f : x;            // NaN and -0 pass through (ops.cu:26-37)
+                if (x > 0.0f) maskword |= (1u << j);
+              }
+              if (flags & EPI_DROPOUT) {
+                const float u = dropout_uniform(p.drop_seed, (uint32_t)row, (uint32_t)(col + e));
+                x = (u > p.drop_p) ? x * (1.0f / (1.0f - p.drop_p)) : 0.0f;
+                if (ref_round) x = __half2float(__float2half_rn(x));
+              }
+              if (flags & EPI_BN) {
+                x = fmaf(x, bsc[e], bsh[e]);
+                if (ref_round) x = __half2float(__float2half_rn(x));
+              }
+              if (flags & EPI_RESID) x = fmaf(p.res_scale, r[e], x);
+              if (flags & EPI_GRADMASK) x = ((min_word >> j) & 1u) ? x : 0.0f;
+              out[e] = __float2half_rn(x);
+            }
+            const uint4 ov = *reinterpret_cast<const uint4*>(out);
+            *sptr = ov;
+            packed[j8 * 4 + 0] = ov.x; packed[j8 * 4 + 1] = ov.y;
+            packed[j8 * 4 + 2] = ov.z; packed[j8 * 4 + 3] = ov.w;
+          }
+          if ((flags & EPI_MASK) && row < p.M && (n0 + c) < p.N)
+            p.mask_out[(size_t)row * p.mask_ld + ((n0 + c) >> 5)] = maskword;
+          // edge replication (whole-minibatch clamp of forward.go:714-722,760-770):
+          // row 0 -> `halo` rows before it, row M-1 -> `halo` rows after it
+          if (p.halo > 0 && row < p.M && (row == 0 || row == p.M - 1)) {
+#pragma unroll 1
+            for (int side = 0; side < 2; ++side) {
+              if (side == 0 && row != 0) continue;
+              if (side == 1 && row != p.M - 1) continue;
+#pragma unroll 1
+              for (int hh = 1; hh <= p.halo; ++hh) {
+                const long long rr = (side == 0) ? -(long long)hh : (long long)(p.M - 1 + hh);
+                __half* dptr = p.d_raw[g] + rr * p.ldd + n0 + c;
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8)
+                  if (n0 + c + j8 * 8 + 8 <= p.N)
+                    *reinterpret_cast<uint4*>(dptr + j8 * 8) =
+                        make_uint4(packed[j8 * 4], packed[j8 * 4 + 1], packed[j8 * 4 + 2], packed[j8 * 4 + 3]);
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (epi_tid == 0) {
+          tma_store_2d(&p.tmD[g], sbuf, n0 + c64, m_blk * kBM);
+          tma_store_commit();
+        }
+      }
+      // all tcgen05.ld of this accumulator stage are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (epi_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace kfp16

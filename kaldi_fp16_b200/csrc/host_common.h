@@ -1,0 +1,39 @@
+// Host-side plumbing shared by the C-ABI translation units: the thread-local error buffer
+// (same convention as the reference: int 0 / -1 + message read by *_last_error(),
+// /root/reference/cpp/cuda/ops.cu:12-20,329-330), the launch counter and the context.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+struct kfp16_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int max_ctas = 0;
+  cudaStream_t stream = nullptr;
+  // split-K workspace owned by the context (used when the caller passes none)
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+namespace kfp16 {
+
+void set_error(const char* fmt, ...);
+const char* get_error();   // nullptr when clear
+void clear_error();
+
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+cudaStream_t default_stream();
+
+// returns false (and sets the error) when a launch / runtime call failed
+bool check_launch(const char* what);
+bool check_cuda(cudaError_t e, const char* what);
+
+}  // namespace kfp16

@@ -1,0 +1,206 @@
+"""GPU parity of the tcgen05 GEMM against the numpy oracle (oracle/kaldi_oracle.py :: gemm, which
+restates ops_gemm, /root/reference/cpp/cuda/ops.cu:366-400) and, when present, against the
+reference's own compiled library (cublasGemmEx) on the same inputs.  Tolerance: FP16 storage with
+FP32 accumulation -> 1 fp16 ulp of the result + fp32 accumulation noise (tests/util.py::gemm_tol)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from kaldi_fp16_b200 import _lib, gpu
+from kaldi_fp16_b200._lib import (EPI_BETA, EPI_BIAS, EPI_BN, EPI_MASK, EPI_REF_ROUND, EPI_RELU, EPI_RESID, K_MAJOR,
+                                  MN_MAJOR)
+from oracle import kaldi_oracle as O
+from tests.util import assert_close, gemm_tol, make_desc, rand_f16, run_desc
+
+pytestmark = pytest.mark.gpu
+
+# (M, N, K): layer shapes of SURVEY 8(d) scaled down in M, plus ragged / tiny cases
+SHAPES = [
+    (128, 64, 64), (128, 256, 128), (256, 160, 320), (300, 1536, 320), (1000, 160, 3072), (777, 256, 1536),
+    (150, 6016, 256), (64, 200, 104), (1, 8, 8), (129, 72, 88), (515, 3080, 256), (2400, 40, 40), (1234, 128, 1152),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_ops_gemm_matches_oracle(handle, M, N, K):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A, B = rand_f16(rng, (M, K)), rand_f16(rng, (K, N), 0.1)
+    tA, tB, tC = gpu.TensorFromFP16(A), gpu.TensorFromFP16(B), gpu.ZeroTensor(M, N)
+    gpu.GEMM(handle, M, N, K, 1.0, tA, tB, 0.0, tC)
+    gpu.Sync()
+    want = O.gemm(A, B)
+    assert_close(tC.ToFP32(), want, gemm_tol(A, B, want), f"ops_gemm {M}x{N}x{K}")
+    for t in (tA, tB, tC):
+        t.Free()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 160, 320), (777, 256, 1536), (150, 6016, 256), (129, 72, 88)])
+def test_ops_gemm_matches_reference_library(handle, reflib, M, N, K):
+    """same inputs through the reference's cublasGemmEx path and through the new kernel"""
+    from tests.refbind import ref_half
+
+    rng = np.random.default_rng(11 + M + N + K)
+    A, B, C0 = rand_f16(rng, (M, K)), rand_f16(rng, (K, N), 0.1), rand_f16(rng, (M, N))
+    for alpha, beta in ((1.0, 0.0), (0.5, 1.0), (2.0, -0.25)):
+        rh = reflib.ops_cublas_create()
+        rA, rB, rC = ref_half(reflib, A), ref_half(reflib, B), ref_half(reflib, C0)
+        assert reflib.ops_gemm(rh, M, N, K, alpha, rA.ptr, K, rB.ptr, N, beta, rC.ptr, N) == 0
+        reflib.bridge_gpu_sync()
+        ref = rC.f32()
+        tA, tB, tC = gpu.TensorFromFP16(A), gpu.TensorFromFP16(B), gpu.TensorFromFP16(C0)
+        gpu.GEMM(handle, M, N, K, alpha, tA, tB, beta, tC)
+        gpu.Sync()
+        got = tC.ToFP32()
+        want = O.gemm(A, B, alpha, beta, C0)
+        tol = gemm_tol(A, B, want, alpha) + 2.0 ** -10 * np.abs(beta * C0)
+        assert_close(ref, want, tol, f"oracle vs reference cuBLAS a={alpha} b={beta}")   # pins the oracle
+        assert_close(got, ref, tol, f"kernel vs reference cuBLAS a={alpha} b={beta}")
+        for b in (rA, rB, rC):
+            b.free()
+        for t in (tA, tB, tC):
+            t.Free()
+        reflib.ops_cublas_destroy(rh)
+
+
+@pytest.mark.parametrize("transA,transB", [(0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(256, 128, 192), (300, 160, 1000), (1536, 320, 2000), (136, 1536, 520)])
+def test_gemm_operand_majors(handle, lib, M, N, K, transA, transB):
+    """dgrad (NT) and wgrad (TN) without transpose kernels (backward_ops.go:162-225)"""
+    rng = np.random.default_rng(5 + M + N + K + transA * 2 + transB)
+    A = rand_f16(rng, (K, M) if transA else (M, K))
+    B = rand_f16(rng, (N, K) if transB else (K, N), 0.1)
+    tA, tB, tC = gpu.TensorFromFP16(A), gpu.TensorFromFP16(B), gpu.ZeroTensor(M, N)
+    assert lib.kfp16_gemm(handle.ptr, M, N, K, 1.0, tA.Ptr, transA, tB.Ptr, transB, 0.0, tC.Ptr) == 0, _lib.last_error()
+    gpu.Sync()
+    want = O.gemm(A, B, transA=bool(transA), transB=bool(transB))
+    a = A.T if transA else A
+    b = B.T if transB else B
+    assert_close(tC.ToFP32(), want, gemm_tol(a, b, want), f"gemm tA={transA} tB={transB}")
+    for t in (tA, tB, tC):
+        t.Free()
+
+
+@pytest.mark.parametrize("bn", [64, 128, 160, 256])
+def test_gemm_tile_widths_multi_tile_per_cta(handle, lib, bn):
+    """force each tile width and a small persistent grid so every CTA walks several tiles"""
+    M, N, K = 1100, bn, 448
+    rng = np.random.default_rng(bn)
+    A, B = rand_f16(rng, (M, K)), rand_f16(rng, (K, N), 0.1)
+    tA, tB, tC = gpu.TensorFromFP16(A), gpu.TensorFromFP16(B), gpu.ZeroTensor(M, N)
+    lib.kfp16_ctx_set_max_ctas(handle.ptr, 3)
+    try:
+        d = make_desc(M, N, K, tA, tB, tC, force_bn=bn)
+        run_desc(handle, d)
+    finally:
+        lib.kfp16_ctx_set_max_ctas(handle.ptr, 0)
+    want = O.gemm(A, B)
+    assert_close(tC.ToFP32(), want, gemm_tol(A, B, want), f"bn={bn}")
+    for t in (tA, tB, tC):
+        t.Free()
+
+
+def test_fused_epilogue_affine_relu_bn_bypass(handle, lib):
+    """TDNN-F affine tail (forward.go:640-693): h(h(h(relu(h(h(acc)+b)))*s+t) ... + 0.66*X with the
+    reference's intermediate FP16 stores (EPI_REF_ROUND) -> must equal the unfused op sequence."""
+    M, N, K = 520, 256, 320
+    rng = np.random.default_rng(3)
+    A, W = rand_f16(rng, (M, K)), rand_f16(rng, (K, N), 0.08)
+    bias = rand_f16(rng, (N,), 0.1)
+    X = rand_f16(rng, (M, N))
+    mean, var = rng.standard_normal(N).astype(np.float32) * 0.1, (rng.random(N).astype(np.float32) + 0.5)
+    gamma, beta = (rng.random(N).astype(np.float32) + 0.5), rng.standard_normal(N).astype(np.float32) * 0.1
+    eps = 1e-3
+    # oracle: the reference's op sequence
+    z = O.gemm(A, W)
+    z = O.add_bias(z, bias)
+    z = O.relu(z)
+    z_relu = z
+    z = O.batchnorm_forward(z, mean, var, gamma, beta, eps)
+    want = O.add_scaled(z, X, 0.66, 1.0)
+    # fused
+    tA, tW, tX, tD = gpu.TensorFromFP16(A), gpu.TensorFromFP16(W), gpu.TensorFromFP16(X), gpu.ZeroTensor(M, N)
+    tb = gpu.TensorFromFP16(bias.reshape(1, -1))
+    dm, dv, dg, dbt = gpu.DeviceF32(mean), gpu.DeviceF32(var), gpu.DeviceF32(gamma), gpu.DeviceF32(beta)
+    sc, sh = gpu.DeviceF32(n=N), gpu.DeviceF32(n=N)
+    assert lib.kfp16_bn_fold(handle.ptr, dm.Ptr, dv.Ptr, dg.Ptr, dbt.Ptr, eps, 1.0, N, sc.Ptr, sh.Ptr) == 0
+    mask_ld = (N + 31) // 32
+    mask = gpu.DeviceF32(n=M * mask_ld)
+    d = make_desc(M, N, K, tA, tW, tD, flags=EPI_BIAS | EPI_RELU | EPI_BN | EPI_RESID | EPI_REF_ROUND | EPI_MASK,
+                  bias=tb.Ptr, bn_scale=sc.Ptr, bn_shift=sh.Ptr, res_scale=0.66, mask_out=mask.Ptr, mask_ld=mask_ld,
+                  ldr=N)
+    d.R[0] = tX.Ptr
+    run_desc(handle, d)
+    got = tD.ToFP32()
+    # scale/shift folding differs from gamma*(x-mean)/sqrt(var+eps)+beta by fp32 rounding: 1 extra ulp
+    tol = gemm_tol(A, W, want) * 3 + 2.0 ** -9 * np.abs(want) + 2e-3
+    assert_close(got, want, tol, "fused affine epilogue")
+    bits = mask.ToHost().view(np.uint32).reshape(M, mask_ld)
+    got_mask = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(M, -1)[:, :N].astype(bool)
+    want_mask = z_relu > 0
+    # elements whose pre-activation is within rounding of 0 may flip
+    near0 = np.abs(O.add_bias(O.gemm(A, W), bias)) < 1e-3
+    assert ((got_mask == want_mask) | near0).all()
+
+
+def test_spliced_k_slabs(handle, lib):
+    """TDNN-F splice as two K-slabs with shifted row coordinates (forward.go:699-790):
+    Y = [X(t-s) | X(t)] * W  without materialising the spliced matrix; rows outside [0,T) read the
+    replicated halo rows of the padded buffer."""
+    T, D, N, s, halo = 300, 192, 160, 3, 3
+    rng = np.random.default_rng(9)
+    X = rand_f16(rng, (T, D))
+    W = rand_f16(rng, (2 * D, N), 0.08)
+    Xp = np.concatenate([np.repeat(X[:1], halo, 0), X, np.repeat(X[-1:], halo, 0)], 0)
+    idx = np.clip(np.arange(T) - s, 0, T - 1)
+    want = O.gemm(np.concatenate([X[idx], X], 1), W)
+    tXp, tW, tD = gpu.TensorFromFP16(Xp), gpu.TensorFromFP16(W), gpu.ZeroTensor(T, N)
+    d = make_desc(T, N, 2 * D, tXp, tW, tD)
+    d.A.ptr = tXp.Ptr + halo * D * 2
+    d.A.rows, d.A.halo = T, halo
+    d.kslabs, d.kslab_len = 2, D
+    d.a_row_off[0][0], d.a_row_off[0][1] = -s, 0
+    d.b_row_off[0][0], d.b_row_off[0][1] = 0, D
+    run_desc(handle, d)
+    S = np.concatenate([X[idx], X], 1)
+    assert_close(tD.ToFP32(), want, gemm_tol(S, W, want), "spliced GEMM")
+
+
+def test_split_k_fp32_accumulate(handle, lib):
+    """weight-gradient shape: tiny output, long reduction -> split-K partials added in FP32"""
+    M, N, K = 320, 256, 5000
+    rng = np.random.default_rng(21)
+    At, B = rand_f16(rng, (K, M)), rand_f16(rng, (K, N), 0.05)
+    tA, tB = gpu.TensorFromFP16(At), gpu.TensorFromFP16(B)
+    ws = gpu.DeviceF32(n=M * N)
+    tD = gpu.ZeroTensor(M, N)
+    d = make_desc(M, N, K, tA, tB, tD, a_major=MN_MAJOR, b_major=MN_MAJOR, split_k=8, ws_ld=N)
+    d.ws[0] = ws.Ptr
+    run_desc(handle, d)
+    got = ws.ToHost().reshape(M, N)
+    want = (At.T.astype(np.float64) @ B.astype(np.float64))
+    absprod = np.abs(At.T).astype(np.float64) @ np.abs(B).astype(np.float64)
+    assert_close(got, want, 2.0 ** -19 * absprod + 1e-6, "split-K fp32")
+
+
+def test_gemm_errors_are_reported(handle, lib):
+    """error convention of ops.h: -1 + message from ops_last_error (ops.cu:12-20,393-397)"""
+    lib.ops_clear_error()
+    assert lib.ops_gemm(None, 8, 8, 8, 1.0, None, 8, None, 8, 0.0, None, 8) == -1
+    assert lib.ops_last_error() and b"null" in lib.ops_last_error()
+    lib.ops_clear_error()
+    assert lib.ops_last_error() is None
+    # empty problems are a no-op, not an error
+    assert lib.ops_gemm(handle.ptr, 0, 8, 8, 1.0, None, 8, None, 8, 0.0, None, 8) == 0
+
+
+def test_unaligned_shapes_take_the_simt_path(handle, lib):
+    """K=1 / odd leading dimensions (the reference's AddBias trick, ops.go:335-351) are legal"""
+    rng = np.random.default_rng(2)
+    for (M, N, K) in [(37, 23, 1), (50, 31, 77), (64, 40, 3)]:
+        A, B, C0 = rand_f16(rng, (M, K)), rand_f16(rng, (K, N)), rand_f16(rng, (M, N))
+        tA, tB, tC = gpu.TensorFromFP16(A), gpu.TensorFromFP16(B), gpu.TensorFromFP16(C0)
+        gpu.GEMM(handle, M, N, K, 1.0, tA, tB, 1.0, tC)
+        gpu.Sync()
+        want = O.gemm(A, B, 1.0, 1.0, C0)
+        assert_close(tC.ToFP32(), want, gemm_tol(A, B, want) + 2.0 ** -10 * np.abs(C0), f"simt {M}x{N}x{K}")
