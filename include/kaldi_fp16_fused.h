@@ -73,7 +73,6 @@ typedef struct {
     int b_row_off[2][2], b_col_off[2][2];
     void *D[2];       /* fp16 outputs [M x N], ld = ldd */
     int ldd;
-    int d_halo;       /* replicate first / last output row into this many halo rows */
     const void *R[2]; /* residual or C-in, fp16 [M x N], ld = ldr */
     int ldr;
     uint32_t flags;

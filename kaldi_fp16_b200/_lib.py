@@ -30,7 +30,7 @@ class GemmDesc(C.Structure):
         ("groups", c_int), ("kslabs", c_int), ("kslab_len", c_int),
         ("a_row_off", (c_int * 2) * 2), ("a_col_off", (c_int * 2) * 2),
         ("b_row_off", (c_int * 2) * 2), ("b_col_off", (c_int * 2) * 2),
-        ("D", c_void_p * 2), ("ldd", c_int), ("d_halo", c_int),
+        ("D", c_void_p * 2), ("ldd", c_int),
         ("R", c_void_p * 2), ("ldr", c_int),
         ("flags", c_u32),
         ("alpha", c_float), ("beta", c_float), ("res_scale", c_float),

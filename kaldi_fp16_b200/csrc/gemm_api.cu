@@ -248,7 +248,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   p.bias = (const __half*)d->bias; p.bn_scale = d->bn_scale; p.bn_shift = d->bn_shift;
   p.vec_gstride = d->vec_gstride;
   p.mask_out = d->mask_out; p.mask_in = d->mask_in; p.mask_ld = d->mask_ld;
-  p.ws_ld = d->ws_ld; p.ldd = d->ldd; p.halo = d->d_halo;
+  p.ws_ld = d->ws_ld;
   p.drop_p = d->drop_p; p.drop_seed = d->drop_seed;
   if ((flags & EPI_BIAS) && !p.bias) { set_error("kfp16_gemm_ex: EPI_BIAS without bias"); return -1; }
   if ((flags & EPI_BN) && (!p.bn_scale || !p.bn_shift)) { set_error("kfp16_gemm_ex: EPI_BN without scale/shift"); return -1; }
@@ -263,7 +263,6 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
       p.ws[g] = d->ws[g];
     } else {
       if (!d->D[g]) { set_error("kfp16_gemm_ex: null output"); return -1; }
-      p.d_raw[g] = (__half*)d->D[g];
       if (!make_map_2d(&p.tmD[g], d->D[g], d->N, d->M, d->ldd, 64, kBM, "D")) return -1;
       if (flags & (EPI_RESID | EPI_BETA)) {
         if (!d->R[g]) { set_error("kfp16_gemm_ex: residual / beta requested without R"); return -1; }

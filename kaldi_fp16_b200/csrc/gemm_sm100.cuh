@@ -61,9 +61,6 @@ struct GemmParams {
   int mask_ld;
   float* ws[kMaxGroups];        // split-K fp32 accumulation target [M x ws_ld]
   int ws_ld;
-  __half* d_raw[kMaxGroups];    // raw output pointer for halo replication
-  int ldd;
-  int halo;                     // replicate row 0 / row M-1 into `halo` rows before / after
   float drop_p; uint32_t drop_seed;
 };
 
@@ -72,6 +69,15 @@ __host__ __device__ inline float dropout_uniform(uint32_t seed, uint32_t row, ui
   uint32_t x = seed ^ (row * 0x9E3779B1u) ^ (col * 0x85EBCA77u);
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
   return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -235,7 +241,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     const bool use_r = (flags & (EPI_RESID | EPI_BETA)) != 0;
     const bool ref_round = (flags & EPI_REF_ROUND) != 0;
     int acc = 0; uint32_t acc_phase = 0;
-    uint32_t rphase[2] = {0, 0};
+    uint32_t rphase = 0;   // bit b = phase of rfull_bar[b]
+    const bool plain = (flags & ~(uint32_t)EPI_REF_ROUND) == 0;
     int chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int id = tile;
@@ -282,65 +289,93 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       for (int c64 = 0; c64 < BN; c64 += 64, ++chunk_ctr) {
         const int buf = chunk_ctr & 1;
         uint8_t* sbuf = smem_epi + buf * Cfg::kEpiBufBytes;
+        uint8_t* srow = sbuf + row_in_tile * 128;
         // the TMA store that last read this buffer (2 chunks ago) must have drained
         if (epi_tid == 0) tma_store_wait_read<1>();
         named_bar_sync(1, 128);
-        if (use_r) {
-          if (epi_tid == 0) {
-            mbar_arrive_expect_tx(&rfull_bar[buf], Cfg::kEpiBufBytes);
-            tma_load_2d(sbuf, &p.tmR[g], &rfull_bar[buf], n0 + c64, m_blk * kBM);
-          }
-          mbar_wait(&rfull_bar[buf], rphase[buf]);
-          rphase[buf] ^= 1;
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = c64 + h * 32;
-          if (c >= BN) break;
-          uint32_t v[32];
-          tmem_ld_32x32(t_acc + c, v);
+        if (plain) {
+          // ---- fast path: D = h(alpha * acc).  Kept separate so the common case is a short,
+          // fully unrolled instruction stream (the all-flags body below must stay a compact
+          // loop: unrolled it overflows the instruction cache and stalls the epilogue warps).
+          constexpr int kHalves = (BN % 64 == 0) ? 2 : 1;     // BN=160: last chunk is 32 wide
+          const int nh = (c64 + 64 <= BN) ? 2 : kHalves;
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(t_acc + c64, v0);
+          if (nh == 2) tmem_ld_32x32(t_acc + c64 + 32, v1);
           tmem_ld_wait();
-          uint32_t packed[16];
-          uint32_t maskword = 0;
-          uint32_t min_word = 0xFFFFFFFFu;
-          if (flags & EPI_GRADMASK) {
-            min_word = (row < p.M) ? __ldg(p.mask_in + (size_t)row * p.mask_ld + ((n0 + c) >> 5)) : 0u;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4 ov;
+            ov.x = pack_f16x2(__uint_as_float(v0[j8 * 8 + 0]) * p.alpha, __uint_as_float(v0[j8 * 8 + 1]) * p.alpha);
+            ov.y = pack_f16x2(__uint_as_float(v0[j8 * 8 + 2]) * p.alpha, __uint_as_float(v0[j8 * 8 + 3]) * p.alpha);
+            ov.z = pack_f16x2(__uint_as_float(v0[j8 * 8 + 4]) * p.alpha, __uint_as_float(v0[j8 * 8 + 5]) * p.alpha);
+            ov.w = pack_f16x2(__uint_as_float(v0[j8 * 8 + 6]) * p.alpha, __uint_as_float(v0[j8 * 8 + 7]) * p.alpha);
+            *reinterpret_cast<uint4*>(srow + ((j8 ^ (row_in_tile & 7)) << 4)) = ov;
           }
+          if (nh == 2) {
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {      // 8 columns = one 16-byte smem chunk
-            const int col = n0 + c + j8 * 8;
-            const bool col_ok = (col + 8 <= p.N);
-            // 16B chunk index inside the 128-byte staged row, XOR-swizzled like TMA SW128
-            const int chunk16 = (h * 4 + j8) ^ (row_in_tile & 7);
-            uint4* sptr = reinterpret_cast<uint4*>(sbuf + row_in_tile * 128 + chunk16 * 16);
-            float r[8];
-            if (use_r) {
-              uint4 rv = *sptr;
-              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { float2 f = __half22float2(rh[e]); r[2 * e] = f.x; r[2 * e + 1] = f.y; }
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint4 ov;
+              ov.x = pack_f16x2(__uint_as_float(v1[j8 * 8 + 0]) * p.alpha, __uint_as_float(v1[j8 * 8 + 1]) * p.alpha);
+              ov.y = pack_f16x2(__uint_as_float(v1[j8 * 8 + 2]) * p.alpha, __uint_as_float(v1[j8 * 8 + 3]) * p.alpha);
+              ov.z = pack_f16x2(__uint_as_float(v1[j8 * 8 + 4]) * p.alpha, __uint_as_float(v1[j8 * 8 + 5]) * p.alpha);
+              ov.w = pack_f16x2(__uint_as_float(v1[j8 * 8 + 6]) * p.alpha, __uint_as_float(v1[j8 * 8 + 7]) * p.alpha);
+              *reinterpret_cast<uint4*>(srow + (((4 + j8) ^ (row_in_tile & 7)) << 4)) = ov;
             }
-            float bia[8], bsc[8], bsh[8];
+          }
+        } else {
+          if (use_r) {
+            if (epi_tid == 0) {
+              mbar_arrive_expect_tx(&rfull_bar[buf], Cfg::kEpiBufBytes);
+              tma_load_2d(sbuf, &p.tmR[g], &rfull_bar[buf], n0 + c64, m_blk * kBM);
+            }
+            mbar_wait(&rfull_bar[buf], (rphase >> buf) & 1u);
+            rphase ^= (1u << buf);
+          }
+          uint32_t maskword = 0, gm_word = 0xFFFFFFFFu;
+#pragma unroll 1
+          for (int g8 = 0; g8 < 8; ++g8) {          // 8 columns = one 16-byte smem chunk
+            const int c = c64 + g8 * 8;
+            if (c >= BN) break;
+            const int col = n0 + c;
+            const bool col_ok = (col + 8 <= p.N);
+            uint32_t v[8];
+            tmem_ld_32x32_x8(t_acc + c, v);
+            if ((flags & EPI_GRADMASK) && (g8 & 3) == 0)
+              gm_word = (row < p.M && col < p.N) ? __ldg(p.mask_in + (size_t)row * p.mask_ld + (col >> 5)) : 0u;
+            uint4* sptr = reinterpret_cast<uint4*>(srow + ((g8 ^ (row_in_tile & 7)) << 4));
+            float r[8], bia[8], bsc[8], bsh[8];
+            if (use_r) {
+              const uint4 rv = *sptr;
+              float2 f;
+              f = unpack_f16x2(rv.x); r[0] = f.x; r[1] = f.y;
+              f = unpack_f16x2(rv.y); r[2] = f.x; r[3] = f.y;
+              f = unpack_f16x2(rv.z); r[4] = f.x; r[5] = f.y;
+              f = unpack_f16x2(rv.w); r[6] = f.x; r[7] = f.y;
+            }
             if (flags & EPI_BIAS) {
-              uint4 bv = col_ok ? __ldg(reinterpret_cast<const uint4*>(p.bias + voff + col)) : make_uint4(0, 0, 0, 0);
-              const __half2* bh = reinterpret_cast<const __half2*>(&bv);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { float2 f = __half22float2(bh[e]); bia[2 * e] = f.x; bia[2 * e + 1] = f.y; }
+              const uint4 bv = col_ok ? __ldg(reinterpret_cast<const uint4*>(p.bias + voff + col)) : make_uint4(0, 0, 0, 0);
+              float2 f;
+              f = unpack_f16x2(bv.x); bia[0] = f.x; bia[1] = f.y;
+              f = unpack_f16x2(bv.y); bia[2] = f.x; bia[3] = f.y;
+              f = unpack_f16x2(bv.z); bia[4] = f.x; bia[5] = f.y;
+              f = unpack_f16x2(bv.w); bia[6] = f.x; bia[7] = f.y;
             }
             if (flags & EPI_BN) {
 #pragma unroll
               for (int e = 0; e < 8; e += 4) {
-                float4 s4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bn_scale + voff + col + e)) : make_float4(0, 0, 0, 0);
-                float4 h4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bn_shift + voff + col + e)) : make_float4(0, 0, 0, 0);
+                const float4 s4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bn_scale + voff + col + e)) : make_float4(0, 0, 0, 0);
+                const float4 h4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bn_shift + voff + col + e)) : make_float4(0, 0, 0, 0);
                 bsc[e] = s4.x; bsc[e + 1] = s4.y; bsc[e + 2] = s4.z; bsc[e + 3] = s4.w;
                 bsh[e] = h4.x; bsh[e + 1] = h4.y; bsh[e + 2] = h4.z; bsh[e + 3] = h4.w;
               }
             }
-            __half out[8];
+            tmem_ld_wait();
+            float xo[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const int j = j8 * 8 + e;
-              float x = __uint_as_float(v[j]) * p.alpha;
+              const int j = (g8 & 3) * 8 + e;          // bit inside the 32-column mask word
+              float x = __uint_as_float(v[e]) * p.alpha;
               if (flags & EPI_BETA) x = fmaf(p.beta, r[e], x);
               if (ref_round) x = __half2float(__float2half_rn(x));
               if (flags & EPI_BIAS) {
@@ -361,33 +396,17 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
                 if (ref_round) x = __half2float(__float2half_rn(x));
               }
               if (flags & EPI_RESID) x = fmaf(p.res_scale, r[e], x);
-              if (flags & EPI_GRADMASK) x = ((min_word >> j) & 1u) ? x : 0.0f;
-              out[e] = __float2half_rn(x);
+              if (flags & EPI_GRADMASK) x = ((gm_word >> j) & 1u) ? x : 0.0f;
+              xo[e] = x;
             }
-            const uint4 ov = *reinterpret_cast<const uint4*>(out);
+            uint4 ov;
+            ov.x = pack_f16x2(xo[0], xo[1]); ov.y = pack_f16x2(xo[2], xo[3]);
+            ov.z = pack_f16x2(xo[4], xo[5]); ov.w = pack_f16x2(xo[6], xo[7]);
             *sptr = ov;
-            packed[j8 * 4 + 0] = ov.x; packed[j8 * 4 + 1] = ov.y;
-            packed[j8 * 4 + 2] = ov.z; packed[j8 * 4 + 3] = ov.w;
-          }
-          if ((flags & EPI_MASK) && row < p.M && (n0 + c) < p.N)
-            p.mask_out[(size_t)row * p.mask_ld + ((n0 + c) >> 5)] = maskword;
-          // edge replication (whole-minibatch clamp of forward.go:714-722,760-770):
-          // row 0 -> `halo` rows before it, row M-1 -> `halo` rows after it
-          if (p.halo > 0 && row < p.M && (row == 0 || row == p.M - 1)) {
-#pragma unroll 1
-            for (int side = 0; side < 2; ++side) {
-              if (side == 0 && row != 0) continue;
-              if (side == 1 && row != p.M - 1) continue;
-#pragma unroll 1
-              for (int hh = 1; hh <= p.halo; ++hh) {
-                const long long rr = (side == 0) ? -(long long)hh : (long long)(p.M - 1 + hh);
-                __half* dptr = p.d_raw[g] + rr * p.ldd + n0 + c;
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8)
-                  if (n0 + c + j8 * 8 + 8 <= p.N)
-                    *reinterpret_cast<uint4*>(dptr + j8 * 8) =
-                        make_uint4(packed[j8 * 4], packed[j8 * 4 + 1], packed[j8 * 4 + 2], packed[j8 * 4 + 3]);
-              }
+            if ((g8 & 3) == 3) {
+              if ((flags & EPI_MASK) && row < p.M && (col & ~31) < p.N)
+                p.mask_out[(size_t)row * p.mask_ld + (col >> 5)] = maskword;
+              maskword = 0;
             }
           }
         }
