@@ -127,6 +127,31 @@ int kfp16_sgd_update_flat(kfp16_ctx *ctx, float *w32, void *w16, const void *gra
                           int round_grad, float grad_scale, float *velocity, float lr,
                           float momentum, size_t n);
 
+/* ---- padded minibatch layout: dense [n_seq*seq_len x cols] <-> padded [n_seq*(seq_len+2*halo) x ld] */
+/* mode 0: halo rows = 0 (conv zero padding, forward.go:449)   1: replicate the edge row (splice clamp) */
+int kfp16_pack_rows(kfp16_ctx *ctx, const void *src, void *dst, int ld, int n_seq, int seq_len, int halo,
+                    int cols, int mode);
+int kfp16_unpack_rows(kfp16_ctx *ctx, const void *src, int ld, int col0, void *dst, int n_seq, int seq_len,
+                      int halo, int cols);
+/* dst[r, col0 + c] = src[r / blk, c]: per-sequence vector (ivector) appended to every frame of its block */
+int kfp16_bcast_rows(kfp16_ctx *ctx, const void *src, int cols, void *dst, int ld, int col0, int rows, int blk);
+/* adjoint of the broadcast: out[s, c] = sum over real rows of block s of G[r, col0 + c] */
+int kfp16_seq_sum(kfp16_ctx *ctx, const void *G, int ld, int col0, void *out, int cols, int n_seq, int seq_len,
+                  int halo);
+int kfp16_zero_halo(kfp16_ctx *ctx, void *X, int ld, int n_seq, int seq_len, int cols, int halo);
+/* y = h(x*scale[c] + shift[c]); shift may be NULL (batch-norm forward / backward with folded params) */
+int kfp16_scale_shift(kfp16_ctx *ctx, const void *x, void *y, int rows, int cols, const float *scale,
+                      const float *shift);
+/* dY = Y on real rows (0 on halo rows); *loss_dev += 0.5*sum(Y^2)   (cmd/sgdtest/main.go:258-267) */
+int kfp16_half_sq_loss(kfp16_ctx *ctx, const void *Y, void *dY, int n_seq, int seq_len, int halo, int cols,
+                       float *loss_dev);
+/* kfp16_bn_relu_backward + bias gradient in the same pass: db_accum[c] += sum_r dZ[r,c] (fp32, may be NULL) */
+int kfp16_bn_relu_backward_bias(kfp16_ctx *ctx, const void *dY, int ldy, const float *scale,
+                                const uint32_t *mask, int mask_ld, void *dZ, int ldz, int rows, int cols,
+                                float *db_accum);
+/* out_f32[n] += sum_t X[t,n]  (no memset: accumulates into the flat gradient bucket) */
+int kfp16_colsum_accum(kfp16_ctx *ctx, const void *X, int ld, int rows, int cols, float *out_f32);
+
 #ifdef __cplusplus
 }
 #endif

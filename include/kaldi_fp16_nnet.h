@@ -1,0 +1,112 @@
+/* kaldi_fp16_nnet.h -- network executor: the B200-native form of the reference's Go package
+ * internal/nnet (Model / Network.Forward / Network.Backward / TrainStep) behind a C ABI.
+ *
+ * The reference walks the layer list in Go and issues 10-20 cgo calls per layer
+ * (/root/reference/internal/nnet/forward.go:148-1001, network_backward.go:94-656,
+ * train_step.go:142-283).  Here the same xconfig text is compiled ONCE into a fixed launch
+ * plan over preallocated buffers (no per-op cudaMalloc), each layer is 1-2 fused tcgen05 GEMM
+ * launches per direction, parameters / FP32 masters / velocities / gradients live in flat
+ * buckets (one SGD launch, one all-reduce), and the whole step can be captured in a CUDA graph.
+ *
+ * Row layout: a minibatch is n_seq sequences of seq_len frames; every per-frame activation is
+ * stored "padded": n_seq blocks of (seq_len + 2*halo) rows, so that time splicing is a TMA row
+ * offset and clamps per sequence.  n_seq = 1 reproduces the reference's
+ * whole-minibatch clamping exactly.
+ */
+#ifndef KALDI_FP16_NNET_H
+#define KALDI_FP16_NNET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "kaldi_fp16_fused.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kfp16_net kfp16_net;
+
+typedef struct {
+    int n_seq;      /* sequences per minibatch (per GPU) */
+    int seq_len;    /* frames per sequence */
+    int ref_round;  /* 1: keep the reference's FP16 store between fused stages (bit-closer, same speed) */
+    int train;      /* 1: allocate backward buffers, FP32 masters, velocities, gradient bucket */
+    float lr;       /* SGDOptimizer.LR       (internal/gpu/optimize.go:30-38) */
+    float momentum; /* SGDOptimizer.Momentum */
+    int conv_cartesian; /* 1: time x height offsets as Cartesian product (Kaldi); 0: paired (quirk Q4) */
+} kfp16_net_opts;
+
+/* xconfig: the reference's model description (internal/nnet/xconfig.go:143); returns NULL on error */
+kfp16_net *kfp16_net_create(kfp16_ctx *ctx, const char *xconfig, const kfp16_net_opts *opts);
+void kfp16_net_destroy(kfp16_net *net);
+
+/* ---- introspection */
+int kfp16_net_num_layers(const kfp16_net *net);
+const char *kfp16_net_layer_name(const kfp16_net *net, int i);
+const char *kfp16_net_layer_type(const kfp16_net *net, int i);
+int kfp16_net_layer_dim(const kfp16_net *net, int i); /* output dim */
+int kfp16_net_padded_rows(const kfp16_net *net);      /* n_seq*(seq_len+2*halo) */
+int kfp16_net_halo(const kfp16_net *net);
+double kfp16_net_flops_forward(const kfp16_net *net); /* 2*M*N*K over the GEMMs, real rows only */
+
+/* ---- parameters: flat buckets.  name = "<layer>.<param>" as SGDOptimizer.RegisterParam keys
+ * (optimize.go:52): W, LinearW, AffineW, AffineBias, BigW, BigBias, SmallW, Bias */
+int kfp16_net_num_params(const kfp16_net *net);
+const char *kfp16_net_param_name(const kfp16_net *net, int i);
+int kfp16_net_param_shape(const kfp16_net *net, int i, int *rows, int *cols);
+size_t kfp16_net_param_offset(const kfp16_net *net, int i); /* element offset into the buckets */
+size_t kfp16_net_bucket_size(const kfp16_net *net);         /* elements */
+void *kfp16_net_params_f16(kfp16_net *net);   /* device, fp16 [bucket]  weights used by the GEMMs */
+float *kfp16_net_params_f32(kfp16_net *net);  /* device, fp32 master weights */
+float *kfp16_net_velocity(kfp16_net *net);    /* device, fp32 */
+float *kfp16_net_grads_f32(kfp16_net *net);   /* device, fp32 gradient bucket (all-reduce this) */
+/* host fp32 [rows x cols] -> truncating fp16 (gpu.TensorFromFP32, tensor.go:67-91) -> device; the
+ * FP32 master is set to float(fp16) as RegisterParam does (optimize.go:52-93) */
+int kfp16_net_set_param(kfp16_net *net, const char *name, const float *host, int rows, int cols);
+int kfp16_net_get_param(kfp16_net *net, const char *name, uint16_t *host_f16, int rows, int cols);
+/* which: for "batchnorm-component" layers "", for tdnnf "AffBN", prefinal "PfBN" / "BN", conv "BN" */
+int kfp16_net_set_bn(kfp16_net *net, const char *layer, const char *which, const float *mean,
+                     const float *var, const float *gamma, const float *beta, float eps, int dim);
+/* randTensor rule N(0,1)*sqrt(2/(rows+cols)), zero biases, identity BN (forward.go:1161-1187) */
+int kfp16_net_init_random(kfp16_net *net, uint64_t seed);
+
+/* ---- data: dense host fp16 [n_seq*seq_len x dim] (per-frame) or [n_seq x dim] (per-sequence
+ * inputs consumed through ReplaceIndex(x, t, 0)); uploads and lays the rows out padded */
+int kfp16_net_set_input(kfp16_net *net, const char *input_name, const uint16_t *host_f16, int rows, int cols);
+/* same from a device buffer already holding the dense fp16 rows (inputs resident in HBM) */
+int kfp16_net_set_input_device(kfp16_net *net, const char *input_name, const void *dev_f16, int rows, int cols);
+int kfp16_net_forward(kfp16_net *net);
+/* dense real rows of a layer's output -> host fp16 [n_seq*seq_len x dim] */
+int kfp16_net_get_output(kfp16_net *net, const char *layer, uint16_t *host_f16, int rows, int cols);
+
+/* ReLU mask (x > 0) saved by a tdnnf / prefinal layer's fused epilogue, one byte per element of the
+ * dense real rows (debug / tests) */
+int kfp16_net_get_mask(kfp16_net *net, const char *layer, uint8_t *host, int rows, int cols);
+
+/* ---- training step pieces (train = 1) */
+int kfp16_net_zero_grads(kfp16_net *net);
+/* loss = 0.5*||out||^2 over real rows of `layer` ("" = the layer named "output"), dOut = out */
+int kfp16_net_loss_half_sq(kfp16_net *net, const char *layer);
+int kfp16_net_set_output_grad(kfp16_net *net, const char *layer, const uint16_t *host_f16, int rows, int cols);
+int kfp16_net_backward(kfp16_net *net);
+/* gradient wrt a layer's output, dense real rows (tests) */
+int kfp16_net_get_grad(kfp16_net *net, const char *layer, uint16_t *host_f16, int rows, int cols);
+/* v = m*v + g*grad_scale; w32 -= lr*v; w16 = half(w32) over the whole bucket (one launch);
+ * round_grad = 1 rounds g to fp16 first, as the reference's FP16 gradient tensors do */
+int kfp16_net_sgd_step(kfp16_net *net, float grad_scale, int round_grad);
+int kfp16_net_set_lr(kfp16_net *net, float lr);
+/* accumulated loss since the last call (device->host sync) */
+int kfp16_net_read_loss(kfp16_net *net, float *loss);
+
+/* ---- CUDA graph of the step: phases bitmask 1 = zero_grads+forward+loss+backward, 2 = SGD.
+ * Capture once (buffers are fixed), then launch per minibatch after kfp16_net_set_input*. */
+int kfp16_net_capture(kfp16_net *net, int phases);
+int kfp16_net_launch(kfp16_net *net, int phases);
+/* kernels launched by one forward+loss+backward(+sgd) pass of this network */
+int kfp16_net_launches_per_step(const kfp16_net *net, int phases);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KALDI_FP16_NNET_H */

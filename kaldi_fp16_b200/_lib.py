@@ -43,6 +43,13 @@ class GemmDesc(C.Structure):
     ]
 
 
+class NetOpts(C.Structure):
+    """struct kfp16_net_opts (include/kaldi_fp16_nnet.h)."""
+
+    _fields_ = [("n_seq", c_int), ("seq_len", c_int), ("ref_round", c_int), ("train", c_int),
+                ("lr", c_float), ("momentum", c_float), ("conv_cartesian", c_int)]
+
+
 class GPUBatchPtrs(C.Structure):
     """struct GPUBatchPtrs (include/kaldi_fp16_bridge.h; reference cpp/include/bridge.h:33-50)."""
 
@@ -83,6 +90,54 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_pad_edges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "kfp16_fold_edges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "kfp16_sgd_update_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_float, c_float, c_size_t]),
+    "kfp16_pack_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "kfp16_unpack_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int]),
+    "kfp16_bcast_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int]),
+    "kfp16_seq_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int]),
+    "kfp16_zero_halo": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "kfp16_scale_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "kfp16_half_sq_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "kfp16_bn_relu_backward_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kfp16_colsum_accum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    # ---- kaldi_fp16_nnet.h
+    "kfp16_net_create": (c_void_p, [c_void_p, C.c_char_p, C.POINTER(NetOpts)]),
+    "kfp16_net_destroy": (None, [c_void_p]),
+    "kfp16_net_num_layers": (c_int, [c_void_p]),
+    "kfp16_net_layer_name": (C.c_char_p, [c_void_p, c_int]),
+    "kfp16_net_layer_type": (C.c_char_p, [c_void_p, c_int]),
+    "kfp16_net_layer_dim": (c_int, [c_void_p, c_int]),
+    "kfp16_net_padded_rows": (c_int, [c_void_p]),
+    "kfp16_net_halo": (c_int, [c_void_p]),
+    "kfp16_net_flops_forward": (C.c_double, [c_void_p]),
+    "kfp16_net_num_params": (c_int, [c_void_p]),
+    "kfp16_net_param_name": (C.c_char_p, [c_void_p, c_int]),
+    "kfp16_net_param_shape": (c_int, [c_void_p, c_int, C.POINTER(c_int), C.POINTER(c_int)]),
+    "kfp16_net_param_offset": (c_size_t, [c_void_p, c_int]),
+    "kfp16_net_bucket_size": (c_size_t, [c_void_p]),
+    "kfp16_net_params_f16": (c_void_p, [c_void_p]),
+    "kfp16_net_params_f32": (c_void_p, [c_void_p]),
+    "kfp16_net_velocity": (c_void_p, [c_void_p]),
+    "kfp16_net_grads_f32": (c_void_p, [c_void_p]),
+    "kfp16_net_set_param": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_get_param": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_set_bn": (c_int, [c_void_p, C.c_char_p, C.c_char_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int]),
+    "kfp16_net_init_random": (c_int, [c_void_p, c_u64]),
+    "kfp16_net_set_input": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_set_input_device": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_forward": (c_int, [c_void_p]),
+    "kfp16_net_get_output": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_get_mask": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_zero_grads": (c_int, [c_void_p]),
+    "kfp16_net_loss_half_sq": (c_int, [c_void_p, C.c_char_p]),
+    "kfp16_net_set_output_grad": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_backward": (c_int, [c_void_p]),
+    "kfp16_net_get_grad": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_sgd_step": (c_int, [c_void_p, c_float, c_int]),
+    "kfp16_net_set_lr": (c_int, [c_void_p, c_float]),
+    "kfp16_net_read_loss": (c_int, [c_void_p, C.POINTER(c_float)]),
+    "kfp16_net_capture": (c_int, [c_void_p, c_int]),
+    "kfp16_net_launch": (c_int, [c_void_p, c_int]),
+    "kfp16_net_launches_per_step": (c_int, [c_void_p, c_int]),
     # ---- kaldi_fp16_ops.h
     "ops_cublas_create": (c_void_p, []),
     "ops_cublas_destroy": (None, [c_void_p]),

@@ -210,7 +210,7 @@ static int run_colscale(const void* x, void* y, long long rows, int cols, const 
 // covers concat_cols, slice_cols and subsample_rows (ops.cu:241-254, 290-320)
 __global__ void copy2d_kernel(__half* __restrict__ dst, long long ldd, int dcol0, const __half* __restrict__ src,
                               long long lds, int scol0, long long row0, int rstride, long long rows, int cols,
-                              int vec) {
+                              int vec, int accumulate) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   if (vec) {
     const int c8 = cols >> 3;
@@ -218,31 +218,43 @@ __global__ void copy2d_kernel(__half* __restrict__ dst, long long ldd, int dcol0
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
       const long long r = (long long)(i / c8);
       const int c = (int)(i % c8) * 8;
-      st8(dst + r * ldd + dcol0 + c, ld8(src + (row0 + r * rstride) * lds + scol0 + c));
+      Half8 v = ld8(src + (row0 + r * rstride) * lds + scol0 + c);
+      if (accumulate) {
+        const Half8 o = ld8(dst + r * ldd + dcol0 + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = __half22float2(v.v[j]), b = __half22float2(o.v[j]);
+          v.v[j] = __floats2half2_rn(a.x + b.x, a.y + b.y);
+        }
+      }
+      st8(dst + r * ldd + dcol0 + c, v);
     }
   } else {
     const size_t total = (size_t)rows * cols;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
       const long long r = (long long)(i / cols);
       const int c = (int)(i % cols);
-      dst[r * ldd + dcol0 + c] = src[(row0 + r * rstride) * lds + scol0 + c];
+      __half v = src[(row0 + r * rstride) * lds + scol0 + c];
+      if (accumulate) v = __float2half_rn(__half2float(v) + __half2float(dst[r * ldd + dcol0 + c]));
+      dst[r * ldd + dcol0 + c] = v;
     }
   }
 }
 static int run_copy2d(void* dst, long long ldd, int dcol0, const void* src, long long lds, int scol0, long long row0,
-                      int rstride, long long rows, int cols, const char* what) {
+                      int rstride, long long rows, int cols, const char* what, cudaStream_t stream, int accumulate = 0) {
   if (rows <= 0 || cols <= 0) return 0;
   if (!dst || !src) { set_error("%s: null pointer", what); return -1; }
   const int vec = (cols % 8 == 0) && (ldd % 8 == 0) && (lds % 8 == 0) && (dcol0 % 8 == 0) && (scol0 % 8 == 0) && al16(dst) && al16(src);
   const size_t work = vec ? (size_t)rows * (cols / 8) : (size_t)rows * cols;
-  copy2d_kernel<<<grid_for(work), kThreads, 0, default_stream()>>>((__half*)dst, ldd, dcol0, (const __half*)src, lds, scol0, row0, rstride, rows, cols, vec);
+  copy2d_kernel<<<grid_for(work), kThreads, 0, stream>>>((__half*)dst, ldd, dcol0, (const __half*)src, lds, scol0, row0, rstride, rows, cols, vec, accumulate);
   count_launch();
   return check_launch(what) ? 0 : -1;
 }
 
 // ---- combine_feature_maps (ops.cu:258-287): per row, [H*F1 | H*F2] -> H x (F1+F2); the row is
 // staged in shared memory so the permutation runs in place without the reference's temp buffer.
-__global__ void combine_fm_kernel(__half* __restrict__ data, int T, int total_dim, int height, int nf1, int nf2) {
+__global__ void combine_fm_kernel(__half* __restrict__ data, int T, int total_dim, int height, int nf1, int nf2,
+                                  int inverse) {
   extern __shared__ __half srow[];
   const int tf = nf1 + nf2;
   for (int t = blockIdx.x; t < T; t += gridDim.x) {
@@ -252,7 +264,7 @@ __global__ void combine_fm_kernel(__half* __restrict__ data, int T, int total_di
     for (int d = threadIdx.x; d < total_dim; d += blockDim.x) {
       const int h = d / tf, f = d % tf;
       const int s = (f < nf1) ? h * nf1 + f : height * nf1 + h * nf2 + (f - nf1);
-      row[d] = srow[s];
+      if (inverse) row[s] = srow[d]; else row[d] = srow[s];
     }
     __syncthreads();
   }
@@ -476,6 +488,154 @@ __global__ void fold_edges_kernel(__half* __restrict__ G, int ld, int n_seq, int
   }
 }
 
+
+// ---- padded minibatch layout helpers ----------------------------------------------------
+// dense [n_seq*L x cols] -> padded [n_seq*(L+2h) x ld]; halo rows: mode 0 = zero, 1 = replicate edge
+__global__ void pack_rows_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int ld, int n_seq, int L,
+                                 int halo, int cols, int mode) {
+  const int blk = L + 2 * halo;
+  const size_t total = (size_t)n_seq * blk * cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / cols;
+    const int c = (int)(i % cols);
+    const int s = (int)(r / blk);
+    int t = (int)(r % blk) - halo;
+    __half v = __float2half(0.f);
+    if (t >= 0 && t < L) v = src[((size_t)s * L + t) * cols + c];
+    else if (mode == 1) v = src[((size_t)s * L + (t < 0 ? 0 : L - 1)) * cols + c];
+    dst[r * ld + c] = v;
+  }
+}
+// padded [.. x ld] (cols from col0) -> dense [n_seq*L x cols]
+__global__ void unpack_rows_kernel(const __half* __restrict__ src, int ld, int col0, __half* __restrict__ dst, int n_seq,
+                                   int L, int halo, int cols) {
+  const int blk = L + 2 * halo;
+  const size_t total = (size_t)n_seq * L * cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / cols;
+    const int c = (int)(i % cols);
+    const int s = (int)(r / L), t = (int)(r % L);
+    dst[i] = src[((size_t)s * blk + halo + t) * ld + col0 + c];
+  }
+}
+// dst[r, col0 + c] = src[r / blk, c]   (per-sequence vector broadcast to every frame of its block)
+__global__ void bcast_rows_kernel(const __half* __restrict__ src, int cols, __half* __restrict__ dst, int ld, int col0,
+                                  size_t rows, int blk) {
+  const size_t total = rows * cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / cols;
+    const int c = (int)(i % cols);
+    dst[r * ld + col0 + c] = src[(r / blk) * cols + c];
+  }
+}
+// out[s, c] = h( sum over the real rows of block s of G[r, col0 + c] )   (adjoint of the broadcast)
+__global__ void seq_sum_kernel(const __half* __restrict__ G, int ld, int col0, __half* __restrict__ out, int cols,
+                               int L, int halo) {
+  const int s = blockIdx.x;
+  const int blk = L + 2 * halo;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < L; ++t) acc += __half2float(G[((size_t)s * blk + halo + t) * ld + col0 + c]);
+    out[(size_t)s * cols + c] = __float2half_rn(acc);
+  }
+}
+__global__ void zero_halo_kernel(__half* __restrict__ X, int ld, int n_seq, int L, int cols, int halo) {
+  const size_t per_seq = (size_t)2 * halo * cols;
+  const size_t total = per_seq * n_seq;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int blk = L + 2 * halo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int s = (int)(i / per_seq);
+    const size_t rem = i % per_seq;
+    const int hr = (int)(rem / cols), c = (int)(rem % cols);
+    const size_t row = (size_t)s * blk + (hr < halo ? hr : L + hr);
+    X[row * ld + c] = __float2half(0.f);
+  }
+}
+// y = h(x*scale[c] + shift[c])  (shift may be null)
+__global__ void scale_shift_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t total, int cols,
+                                   const float* __restrict__ scale, const float* __restrict__ shift) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % cols);
+    const float v = __half2float(x[i]) * scale[c] + (shift ? shift[c] : 0.f);
+    y[i] = __float2half_rn(v);
+  }
+}
+// dY = Y on real rows, 0 on halo rows; *loss += 0.5*sum(Y^2)   (cmd/sgdtest/main.go:258-267)
+__global__ void half_sq_loss_kernel(const __half* __restrict__ Y, __half* __restrict__ dY, int n_seq, int L, int halo,
+                                    int cols, float* __restrict__ loss) {
+  __shared__ float red[32];
+  const int blk = L + 2 * halo;
+  const size_t total = (size_t)n_seq * blk * cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int t = (int)((i / cols) % blk) - halo;
+    __half v = __float2half(0.f);
+    if (t >= 0 && t < L) { v = Y[i]; const float f = __half2float(v); acc += 0.5f * f * f; }
+    dY[i] = v;
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
+    if (threadIdx.x == 0) atomicAdd(loss, v);
+  }
+}
+// dZ = mask ? h(dY*scale[c]) : 0 and db[c] += sum_r dZ[r,c]  (BN backward + ReLU backward + bias grad)
+// block (32 column-groups of 8, 8 row lanes); grid (ceil(cols/256), row_chunks)
+__global__ void bn_relu_bwd_colsum_kernel(const __half* __restrict__ dY, int ldy, const float* __restrict__ scale,
+                                          const uint32_t* __restrict__ mask, int mask_ld, __half* __restrict__ dZ,
+                                          int ldz, size_t rows, int cols, float* __restrict__ db) {
+  __shared__ float red[8][32][8];
+  const int cg = threadIdx.x, ry = threadIdx.y;
+  const int c = (blockIdx.x * 32 + cg) * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c < cols) {
+    float sc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j] = scale ? scale[c + j] : 1.0f;
+    const size_t rows_per = (rows + gridDim.y - 1) / gridDim.y;
+    const size_t r0 = (size_t)blockIdx.y * rows_per;
+    const size_t r1 = r0 + rows_per < rows ? r0 + rows_per : rows;
+    for (size_t r = r0 + ry; r < r1; r += 8) {
+      Half8 a = ld8(dY + r * ldy + c);
+      __half* h = reinterpret_cast<__half*>(&a);
+      uint32_t bits = 0xFFu;
+      if (mask) bits = (mask[r * mask_ld + (c >> 5)] >> (c & 31)) & 0xFFu;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __half o = ((bits >> j) & 1u) ? __float2half_rn(__half2float(h[j]) * sc[j]) : __float2half(0.f);
+        h[j] = o;
+        acc[j] += __half2float(o);
+      }
+      st8(dZ + r * ldz + c, a);
+    }
+  }
+  if (db) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[ry][cg][j] = acc[j];
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][cg][j];
+        atomicAdd(db + c + j, s);
+      }
+    }
+  }
+}
+// out[n] += sum_t X[t,n] without the leading memset (accumulates into the flat gradient bucket)
 }  // namespace kfp16
 
 using namespace kfp16;
@@ -499,17 +659,19 @@ int ops_copy(void* dst, const void* src, int count) {
   return check_cuda(cudaMemcpyAsync(dst, src, (size_t)count * sizeof(__half), cudaMemcpyDeviceToDevice, default_stream()), "copy") ? 0 : -1;
 }
 
-static int run_softmax(void* data, int rows, int cols, bool log) {
+}  // extern "C"
+int kfp16::softmax_on_stream(cudaStream_t stream, void* data, int rows, int cols, bool log) {
   if (rows <= 0 || cols <= 0) return 0;
   if (!data) { set_error("softmax: null pointer"); return -1; }
   const int grid = rows < num_sms_cached() * 16 ? rows : num_sms_cached() * 16;
-  if (log) softmax_kernel<true><<<grid, 128, 0, default_stream()>>>((__half*)data, rows, cols);
-  else softmax_kernel<false><<<grid, 128, 0, default_stream()>>>((__half*)data, rows, cols);
+  if (log) softmax_kernel<true><<<grid, 128, 0, stream>>>((__half*)data, rows, cols);
+  else softmax_kernel<false><<<grid, 128, 0, stream>>>((__half*)data, rows, cols);
   count_launch();
   return check_launch(log ? "log_softmax kernel" : "softmax kernel") ? 0 : -1;
 }
-int ops_softmax(void* data, int rows, int cols) { return run_softmax(data, rows, cols, false); }
-int ops_log_softmax(void* data, int rows, int cols) { return run_softmax(data, rows, cols, true); }
+extern "C" {
+int ops_softmax(void* data, int rows, int cols) { return kfp16::softmax_on_stream(default_stream(), data, rows, cols, false); }
+int ops_log_softmax(void* data, int rows, int cols) { return kfp16::softmax_on_stream(default_stream(), data, rows, cols, true); }
 
 int ops_batchnorm_forward(void* x, int T, int D, const float* mean, const float* var, const float* gamma,
                           const float* beta, float epsilon) {
@@ -523,17 +685,21 @@ int ops_batchnorm_forward_rms(void* x, int T, int D, const float* mean, const fl
 }
 
 int ops_concat_cols(void* dst, int T, int dst_cols, const void* src, int src_cols, int dst_col_offset) {
-  return run_copy2d(dst, dst_cols, dst_col_offset, src, src_cols, 0, 0, 1, T, src_cols, "concat_cols kernel");
+  return run_copy2d(dst, dst_cols, dst_col_offset, src, src_cols, 0, 0, 1, T, src_cols, "concat_cols kernel", default_stream());
 }
 int ops_slice_cols(const void* src, int T, int src_cols, void* dst, int dst_cols, int src_col_offset) {
-  return run_copy2d(dst, dst_cols, 0, src, src_cols, src_col_offset, 0, 1, T, dst_cols, "slice_cols kernel");
+  return run_copy2d(dst, dst_cols, 0, src, src_cols, src_col_offset, 0, 1, T, dst_cols, "slice_cols kernel", default_stream());
 }
 void ops_subsample_rows(void* dst, const void* src, int in_rows, int cols, int stride, int row_offset) {
   if (stride <= 0 || in_rows <= row_offset) return;
   const int out_rows = (in_rows - row_offset + stride - 1) / stride;   // ops.cu:633
-  run_copy2d(dst, cols, 0, src, cols, 0, row_offset, stride, out_rows, cols, "subsample_rows kernel");
+  run_copy2d(dst, cols, 0, src, cols, 0, row_offset, stride, out_rows, cols, "subsample_rows kernel", default_stream());
 }
 int ops_combine_feature_maps(void* data, int T, int total_dim, int height, int nf1, int nf2) {
+  return kfp16::ops_combine_feature_maps_on(default_stream(), data, T, total_dim, height, nf1, nf2, 0);
+}
+}  // extern "C"
+int kfp16::ops_combine_feature_maps_on(cudaStream_t stream, void* data, int T, int total_dim, int height, int nf1, int nf2, int inverse) {
   if (T <= 0 || total_dim <= 0) return 0;
   if (!data) { set_error("combine_feature_maps: null pointer"); return -1; }
   if (height * (nf1 + nf2) != total_dim) { set_error("combine_feature_maps: height*(nf1+nf2) != total_dim (%d*(%d+%d) != %d)", height, nf1, nf2, total_dim); return -1; }
@@ -543,10 +709,20 @@ int ops_combine_feature_maps(void* data, int T, int total_dim, int height, int n
       !check_cuda(cudaFuncSetAttribute(combine_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "combine smem"))
     return -1;
   const int grid = T < num_sms_cached() * 8 ? T : num_sms_cached() * 8;
-  combine_fm_kernel<<<grid, kThreads, smem, default_stream()>>>((__half*)data, T, total_dim, height, nf1, nf2);
+  combine_fm_kernel<<<grid, kThreads, smem, stream>>>((__half*)data, T, total_dim, height, nf1, nf2, inverse);
   count_launch();
   return check_launch("combine_feature_maps kernel") ? 0 : -1;
 }
+int kfp16::ops_concat_cols_on(cudaStream_t stream, void* dst, int T, int dst_cols, const void* src, int src_cols, int dst_col_offset) {
+  return run_copy2d(dst, dst_cols, dst_col_offset, src, src_cols, 0, 0, 1, T, src_cols, "concat_cols kernel", stream);
+}
+int kfp16::ops_slice_cols_on(cudaStream_t stream, const void* src, int T, int src_cols, void* dst, int dst_cols, int src_col_offset) {
+  return run_copy2d(dst, dst_cols, 0, src, src_cols, src_col_offset, 0, 1, T, dst_cols, "slice_cols kernel", stream);
+}
+int kfp16::ops_slice_add_on(cudaStream_t stream, const void* src, int T, int src_cols, void* dst, int dst_cols, int src_col_offset) {
+  return run_copy2d(dst, dst_cols, 0, src, src_cols, src_col_offset, 0, 1, T, dst_cols, "slice_add kernel", stream, 1);
+}
+extern "C" {
 
 // ------------------------------------------------------------------ ops.h backward + optimiser
 int ops_relu_backward(const void* x, void* grad, int count) { return run_map2(grad, x, count, ReluBwdOp{}, "relu_backward"); }
@@ -660,6 +836,92 @@ int kfp16_sgd_update_flat(kfp16_ctx* ctx, float* w32, void* w16, const void* gra
   else sgd_kernel<false><<<grid_for(n), kThreads, 0, s>>>(w32, (__half*)w16, grad, 0, grad_scale, velocity, lr, momentum, n);
   count_launch();
   return check_launch("kfp16_sgd_update_flat") ? 0 : -1;
+}
+
+int kfp16_pack_rows(kfp16_ctx* ctx, const void* src, void* dst, int ld, int n_seq, int seq_len, int halo, int cols,
+                    int mode) {
+  if (n_seq <= 0 || seq_len <= 0 || cols <= 0) return 0;
+  if (!src || !dst) { set_error("kfp16_pack_rows: null pointer"); return -1; }
+  pack_rows_kernel<<<grid_for((size_t)n_seq * (seq_len + 2 * halo) * cols), kThreads, 0, ctx_stream(ctx)>>>(
+      (const __half*)src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
+  count_launch();
+  return check_launch("kfp16_pack_rows") ? 0 : -1;
+}
+int kfp16_unpack_rows(kfp16_ctx* ctx, const void* src, int ld, int col0, void* dst, int n_seq, int seq_len, int halo,
+                      int cols) {
+  if (n_seq <= 0 || seq_len <= 0 || cols <= 0) return 0;
+  if (!src || !dst) { set_error("kfp16_unpack_rows: null pointer"); return -1; }
+  unpack_rows_kernel<<<grid_for((size_t)n_seq * seq_len * cols), kThreads, 0, ctx_stream(ctx)>>>(
+      (const __half*)src, ld, col0, (__half*)dst, n_seq, seq_len, halo, cols);
+  count_launch();
+  return check_launch("kfp16_unpack_rows") ? 0 : -1;
+}
+int kfp16_bcast_rows(kfp16_ctx* ctx, const void* src, int cols, void* dst, int ld, int col0, int rows, int blk) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!src || !dst || blk <= 0) { set_error("kfp16_bcast_rows: bad argument"); return -1; }
+  bcast_rows_kernel<<<grid_for((size_t)rows * cols), kThreads, 0, ctx_stream(ctx)>>>((const __half*)src, cols, (__half*)dst, ld, col0, (size_t)rows, blk);
+  count_launch();
+  return check_launch("kfp16_bcast_rows") ? 0 : -1;
+}
+int kfp16_seq_sum(kfp16_ctx* ctx, const void* G, int ld, int col0, void* out, int cols, int n_seq, int seq_len,
+                  int halo) {
+  if (n_seq <= 0 || cols <= 0) return 0;
+  if (!G || !out) { set_error("kfp16_seq_sum: null pointer"); return -1; }
+  seq_sum_kernel<<<n_seq, 256, 0, ctx_stream(ctx)>>>((const __half*)G, ld, col0, (__half*)out, cols, seq_len, halo);
+  count_launch();
+  return check_launch("kfp16_seq_sum") ? 0 : -1;
+}
+int kfp16_zero_halo(kfp16_ctx* ctx, void* X, int ld, int n_seq, int seq_len, int cols, int halo) {
+  if (n_seq <= 0 || halo <= 0 || cols <= 0) return 0;
+  if (!X) { set_error("kfp16_zero_halo: null pointer"); return -1; }
+  zero_halo_kernel<<<grid_for((size_t)n_seq * 2 * halo * cols), kThreads, 0, ctx_stream(ctx)>>>((__half*)X, ld, n_seq, seq_len, cols, halo);
+  count_launch();
+  return check_launch("kfp16_zero_halo") ? 0 : -1;
+}
+int kfp16_scale_shift(kfp16_ctx* ctx, const void* x, void* y, int rows, int cols, const float* scale,
+                      const float* shift) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!x || !y || !scale) { set_error("kfp16_scale_shift: null pointer"); return -1; }
+  scale_shift_kernel<<<grid_for((size_t)rows * cols), kThreads, 0, ctx_stream(ctx)>>>((const __half*)x, (__half*)y, (size_t)rows * cols, cols, scale, shift);
+  count_launch();
+  return check_launch("kfp16_scale_shift") ? 0 : -1;
+}
+int kfp16_half_sq_loss(kfp16_ctx* ctx, const void* Y, void* dY, int n_seq, int seq_len, int halo, int cols,
+                       float* loss_dev) {
+  if (n_seq <= 0 || cols <= 0) return 0;
+  if (!Y || !dY || !loss_dev) { set_error("kfp16_half_sq_loss: null pointer"); return -1; }
+  half_sq_loss_kernel<<<grid_for((size_t)n_seq * (seq_len + 2 * halo) * cols), kThreads, 0, ctx_stream(ctx)>>>(
+      (const __half*)Y, (__half*)dY, n_seq, seq_len, halo, cols, loss_dev);
+  count_launch();
+  return check_launch("kfp16_half_sq_loss") ? 0 : -1;
+}
+int kfp16_bn_relu_backward_bias(kfp16_ctx* ctx, const void* dY, int ldy, const float* scale, const uint32_t* mask,
+                                int mask_ld, void* dZ, int ldz, int rows, int cols, float* db_accum) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!dY || !dZ || (cols % 8) || (ldy % 8) || (ldz % 8) || !al16(dY) || !al16(dZ)) {
+    set_error("kfp16_bn_relu_backward_bias: needs 16B-aligned buffers and cols/ld %% 8 == 0"); return -1;
+  }
+  const int gx = (cols + 255) / 256;
+  int gy = (num_sms_cached() * 4 + gx - 1) / gx;
+  const int max_gy = (rows + 31) / 32;
+  if (gy > max_gy) gy = max_gy;
+  if (gy < 1) gy = 1;
+  bn_relu_bwd_colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, ctx_stream(ctx)>>>(
+      (const __half*)dY, ldy, scale, mask, mask_ld, (__half*)dZ, ldz, (size_t)rows, cols, db_accum);
+  count_launch();
+  return check_launch("kfp16_bn_relu_backward_bias") ? 0 : -1;
+}
+int kfp16_colsum_accum(kfp16_ctx* ctx, const void* X, int ld, int rows, int cols, float* out_f32) {
+  if (cols <= 0 || rows <= 0) return 0;
+  if (!X || !out_f32 || (cols % 2) || (ld % 2)) { set_error("kfp16_colsum_accum: needs fp32 output and even cols/ld"); return -1; }
+  const int gx = (cols + 63) / 64;
+  int gy = (num_sms_cached() * 4 + gx - 1) / gx;
+  const int max_gy = (rows + 63) / 64;
+  if (gy > max_gy) gy = max_gy;
+  if (gy < 1) gy = 1;
+  colsum_kernel<<<dim3(gx, gy), kThreads, 0, ctx_stream(ctx)>>>((const __half*)X, ld, (size_t)rows, cols, out_f32);
+  count_launch();
+  return check_launch("kfp16_colsum_accum") ? 0 : -1;
 }
 
 }  // extern "C"

@@ -197,7 +197,9 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   const int kslab_len = d->kslab_len > 0 ? d->kslab_len : d->K;
   if (groups > kMaxGroups || kslabs > kMaxSlabs) { set_error("kfp16_gemm_ex: at most 2 groups / 2 K-slabs"); return -1; }
   if (kslabs * kslab_len != d->K) { set_error("kfp16_gemm_ex: K (%d) != kslabs*kslab_len (%d*%d)", d->K, kslabs, kslab_len); return -1; }
-  if ((d->N % 8) || (kslab_len % 8)) { set_error("kfp16_gemm_ex: N and K must be multiples of 8 (N=%d K=%d)", d->N, kslab_len); return -1; }
+  // N is the contiguous dimension of D (and of an MN-major B); K only has to be 16-byte aligned
+  // where it is some operand's contiguous dimension, which the tensor-map builder checks (ld % 8)
+  if (d->N % 8) { set_error("kfp16_gemm_ex: N must be a multiple of 8 (N=%d)", d->N); return -1; }
   if (kslabs > 1 && (kslab_len % 16)) {
     // a partial UMMA K step relies on TMA zero-fill past the matrix edge; between slabs there is none
     set_error("kfp16_gemm_ex: kslab_len must be a multiple of 16 when K is spliced (got %d)", kslab_len); return -1;

@@ -36,4 +36,11 @@ cudaStream_t default_stream();
 bool check_launch(const char* what);
 bool check_cuda(cudaError_t e, const char* what);
 
+// stream-explicit forms of a few reference ops, used by the network executor (elementwise.cu)
+int softmax_on_stream(cudaStream_t stream, void* data, int rows, int cols, bool log);
+int ops_concat_cols_on(cudaStream_t stream, void* dst, int T, int dst_cols, const void* src, int src_cols, int dst_col_offset);
+int ops_slice_cols_on(cudaStream_t stream, const void* src, int T, int src_cols, void* dst, int dst_cols, int src_col_offset);
+int ops_slice_add_on(cudaStream_t stream, const void* src, int T, int src_cols, void* dst, int dst_cols, int src_col_offset);
+int ops_combine_feature_maps_on(cudaStream_t stream, void* data, int T, int total_dim, int height, int nf1, int nf2, int inverse);
+
 }  // namespace kfp16

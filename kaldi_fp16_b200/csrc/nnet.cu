@@ -1,0 +1,1226 @@
+// Network executor: xconfig -> fixed launch plan of fused tcgen05 GEMMs (include/kaldi_fp16_nnet.h).
+//
+// Replaces the per-layer op sequences the reference issues from Go
+// (/root/reference/internal/nnet/forward.go:148-1001, network_backward.go:94-656,
+//  train_step.go:142-283, model.go, layers.go, xconfig.go).  Layer semantics follow SURVEY.md
+// Appendix A; the backward pass is the exact transpose of the forward (the reference's backward
+// ignores splicing -- quirk Q2 -- and is only meaningful for time-stride 0, where both agree).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/kaldi_fp16_nnet.h"
+#include "host_common.h"
+
+using namespace kfp16;
+
+namespace {
+
+enum LType { L_INPUT, L_IDCT, L_LINEAR, L_BATCHNORM, L_SPECAUG, L_COMBINE, L_CONV, L_TDNNF, L_PREFINAL, L_OUTPUT };
+enum HaloMode { HALO_NONE = 0, HALO_ZERO = 1, HALO_REPL = 2 };
+
+struct Buf {
+  __half* p = nullptr;
+  int rows = 0, cols = 0;
+  size_t bytes() const { return (size_t)rows * cols * sizeof(__half); }
+};
+
+struct BNorm {
+  bool present = false;
+  int dim = 0;
+  float eps = 0.001f;          // forward.go:1185, weight_loader.go:447-450
+  float target_rms = 1.0f;
+  bool rms_only = false;       // batchnorm-component with target-rms != 1 (forward.go:349-374)
+  float *mean = nullptr, *var = nullptr, *gamma = nullptr, *beta = nullptr;   // fp32 [dim]
+  float *scale = nullptr, *shift = nullptr, *zero = nullptr;                  // folded; zero = [dim] of 0
+};
+
+struct Param {
+  std::string name;
+  int rows = 0, cols = 0;
+  size_t off = 0;
+  bool is_bias = false;
+};
+
+struct Layer {
+  LType type = L_INPUT;
+  std::string name, type_name;
+  std::map<std::string, std::string> kv;
+  std::vector<int> in;          // producer layer indices
+  bool in_replace = false;      // ReplaceIndex(x, t, 0): consumes a per-sequence input
+  int in_dim = 0, out_dim = 0;
+  bool per_seq = false;         // rows = n_seq (ivector branch) instead of padded frames
+  bool needs_grad = false;      // lies on a path from a parameter to the chain output
+  bool wants_dx = false;        // some producer needs the gradient wrt this layer's input
+  int halo_mode = HALO_NONE;    // how consumers expect the halo rows of `out`
+  int n_grad_consumers = 0;
+  Buf in_cat, d_in_cat;         // Append(...) materialised
+  Buf out, dout;                // activation / gradient wrt activation
+  Buf tmp_dx;                   // scratch for accumulating into a multi-consumer producer
+  // parameters (index into Net::params, -1 = none)
+  int pW = -1, pB = -1, pLin = -1, pAff = -1, pAffB = -1, pBig = -1, pBigB = -1, pSmall = -1;
+  BNorm bn, bn2;
+  // tdnnf
+  int stride = 0, bott_dim = 0;
+  float bypass = 0.f;
+  bool use_bypass = false;
+  Buf bott, dbott, dz;
+  uint32_t* mask = nullptr;
+  int mask_ld = 0;
+  // prefinal
+  int big_dim = 0, small_dim = 0;
+  Buf big, dbig, dys;
+  // idct
+  __half* idct_mat = nullptr;
+  double lifter = 22.0;
+  // output
+  bool log_softmax = false;
+  // combine-feature-maps
+  int height = 0, nf1 = 1, nf2 = 1;
+  int grads_seen = 0;
+};
+
+}  // namespace
+
+struct kfp16_net {
+  kfp16_ctx* ctx = nullptr;
+  kfp16_net_opts opts{};
+  int halo = 0, blk = 0, Tp = 0, T = 0;
+  std::vector<Layer> layers;
+  std::vector<Param> params;
+  size_t bucket = 0;
+  __half* w16 = nullptr;
+  float *w32 = nullptr, *vel = nullptr, *g32 = nullptr;
+  float* loss_dev = nullptr;
+  std::vector<void*> allocs;
+  __half* stage_in = nullptr;   // dense staging for host uploads / downloads
+  size_t stage_bytes = 0;
+  double flops_fwd = 0;
+  cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  int graph_launches[4] = {0, 0, 0, 0};
+  int out_layer = -1;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------ utilities
+std::string trim(const std::string& s) {
+  size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+  return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+}
+
+// split on whitespace outside parentheses: "input=Append(a, b)" stays one token
+std::vector<std::string> tokens(const std::string& line) {
+  std::vector<std::string> out;
+  std::string cur;
+  int depth = 0;
+  for (char c : line) {
+    if (c == '(') ++depth;
+    if (c == ')') --depth;
+    if ((c == ' ' || c == '\t') && depth == 0) {
+      if (!cur.empty()) { out.push_back(cur); cur.clear(); }
+    } else {
+      cur.push_back(c);
+    }
+  }
+  if (!cur.empty()) out.push_back(cur);
+  return out;
+}
+
+int kv_int(const Layer& l, const char* k, int def) {
+  auto it = l.kv.find(k);
+  if (it == l.kv.end()) return def;
+  char* e = nullptr;
+  long v = strtol(it->second.c_str(), &e, 10);
+  return (e && *e == 0) ? (int)v : def;
+}
+double kv_float(const Layer& l, const char* k, double def) {
+  auto it = l.kv.find(k);
+  if (it == l.kv.end()) return def;
+  char* e = nullptr;
+  double v = strtod(it->second.c_str(), &e);
+  return (e && *e == 0) ? v : def;
+}
+bool kv_bool(const Layer& l, const char* k, bool def) {
+  auto it = l.kv.find(k);
+  if (it == l.kv.end()) return def;
+  std::string v = it->second;
+  std::transform(v.begin(), v.end(), v.begin(), ::tolower);
+  if (v == "true" || v == "1" || v == "yes") return true;
+  if (v == "false" || v == "0" || v == "no") return false;
+  return def;
+}
+std::vector<int> kv_ints(const Layer& l, const char* k) {
+  std::vector<int> out;
+  auto it = l.kv.find(k);
+  if (it == l.kv.end()) return out;
+  std::stringstream ss(it->second);
+  std::string part;
+  while (std::getline(ss, part, ',')) {
+    part = trim(part);
+    if (!part.empty()) out.push_back(atoi(part.c_str()));
+  }
+  return out;
+}
+
+// internal/gpu/tensor.go:158-174 float32ToFP16Bits: truncating, flush-to-zero, exp>15 -> Inf
+uint16_t f32_to_f16_trunc(float f) {
+  uint32_t bits;
+  memcpy(&bits, &f, 4);
+  const uint16_t sign = (uint16_t)((bits >> 16) & 0x8000);
+  const int exp = (int)((bits >> 23) & 0xFF) - 127;
+  const uint32_t frac = bits & 0x7FFFFF;
+  if (exp > 15) return sign | 0x7C00;
+  if (exp < -14) return sign;
+  return (uint16_t)(sign | (uint16_t)((exp + 15) << 10) | (uint16_t)(frac >> 13));
+}
+float f16_bits_to_f32(uint16_t h) {
+  __half_raw r;
+  r.x = h;
+  return __half2float(__half(r));
+}
+
+bool dev_alloc(kfp16_net* n, void** p, size_t bytes, bool zero = true) {
+  if (bytes == 0) bytes = 16;
+  if (!check_cuda(cudaMalloc(p, bytes), "cudaMalloc (network buffer)")) return false;
+  n->allocs.push_back(*p);
+  if (zero && !check_cuda(cudaMemsetAsync(*p, 0, bytes, n->ctx->stream), "cudaMemset")) return false;
+  return true;
+}
+bool alloc_buf(kfp16_net* n, Buf& b, int rows, int cols) {
+  b.rows = rows;
+  b.cols = cols;
+  return dev_alloc(n, (void**)&b.p, b.bytes());
+}
+
+int find_layer(const kfp16_net* n, const std::string& name) {
+  for (size_t i = 0; i < n->layers.size(); ++i)
+    if (n->layers[i].name == name) return (int)i;
+  // "tdnnf7" also resolves "tdnnf7.xyz" style sub-names to the latest match (layers.go:357-370)
+  int best = -1;
+  for (size_t i = 0; i < n->layers.size(); ++i) {
+    const std::string& ln = n->layers[i].name;
+    if (ln.size() > name.size() && ln.compare(0, name.size(), name) == 0 && ln[name.size()] == '.') best = (int)i;
+  }
+  return best;
+}
+int find_param(const kfp16_net* n, const std::string& name) {
+  for (size_t i = 0; i < n->params.size(); ++i)
+    if (n->params[i].name == name) return (int)i;
+  return -1;
+}
+
+int add_param(kfp16_net* n, const std::string& name, int rows, int cols, bool is_bias = false) {
+  Param p;
+  p.name = name;
+  p.rows = rows;
+  p.cols = cols;
+  p.is_bias = is_bias;
+  p.off = n->bucket;
+  n->bucket += ((size_t)rows * cols + 127) & ~(size_t)127;   // 256-byte aligned fp16 sections
+  n->params.push_back(p);
+  return (int)n->params.size() - 1;
+}
+
+bool make_bn(kfp16_net* n, BNorm& bn, int dim, float target_rms, bool rms_only) {
+  bn.present = true;
+  bn.dim = dim;
+  bn.target_rms = target_rms;
+  bn.rms_only = rms_only;
+  float* base = nullptr;
+  if (!dev_alloc(n, (void**)&base, (size_t)dim * 7 * sizeof(float))) return false;
+  bn.mean = base;
+  bn.var = base + dim;
+  bn.gamma = base + 2 * dim;
+  bn.beta = base + 3 * dim;
+  bn.scale = base + 4 * dim;
+  bn.shift = base + 5 * dim;
+  bn.zero = base + 6 * dim;
+  std::vector<float> h((size_t)dim * 4, 0.f);   // identity: mean 0, var 1, gamma 1, beta 0
+  for (int i = 0; i < dim; ++i) { h[dim + i] = 1.f; h[2 * dim + i] = 1.f; }
+  if (!check_cuda(cudaMemcpyAsync(base, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, n->ctx->stream), "bn upload")) return false;
+  if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "bn upload sync")) return false;
+  return kfp16_bn_fold(n->ctx, bn.mean, bn.var, rms_only ? nullptr : bn.gamma, rms_only ? nullptr : bn.beta, bn.eps,
+                       target_rms, dim, bn.scale, bn.shift) == 0;
+}
+
+// ------------------------------------------------------------------------------ xconfig
+bool parse_input_spec(kfp16_net* n, Layer& l, int idx) {
+  auto it = l.kv.find("input");
+  if (it == l.kv.end() || it->second.empty()) {
+    if (l.type == L_INPUT) return true;
+    if (idx == 0) { set_error("layer %s has no input", l.name.c_str()); return false; }
+    l.in.push_back(idx - 1);
+    return true;
+  }
+  std::string spec = trim(it->second);
+  auto resolve = [&](const std::string& nm) -> int {
+    int r = find_layer(n, trim(nm));
+    if (r < 0) set_error("layer %s: input \"%s\" not found", l.name.c_str(), trim(nm).c_str());
+    return r;
+  };
+  if (spec.compare(0, 7, "Append(") == 0 && spec.back() == ')') {
+    std::string inner = spec.substr(7, spec.size() - 8);
+    // split on top-level commas
+    int depth = 0;
+    std::string cur;
+    std::vector<std::string> parts;
+    for (char c : inner) {
+      if (c == '(') ++depth;
+      if (c == ')') --depth;
+      if (c == ',' && depth == 0) { parts.push_back(cur); cur.clear(); } else cur.push_back(c);
+    }
+    if (!trim(cur).empty()) parts.push_back(cur);
+    for (auto& p : parts) {
+      std::string nm = trim(p);
+      if (nm.compare(0, 13, "ReplaceIndex(") == 0) nm = trim(nm.substr(13, nm.find(',') - 13));
+      int r = resolve(nm);
+      if (r < 0) return false;
+      l.in.push_back(r);
+    }
+    return true;
+  }
+  if (spec.compare(0, 13, "ReplaceIndex(") == 0) {
+    std::string nm = trim(spec.substr(13, spec.find(',') - 13));
+    int r = resolve(nm);
+    if (r < 0) return false;
+    l.in.push_back(r);
+    l.in_replace = true;
+    return true;
+  }
+  int r = resolve(spec);
+  if (r < 0) return false;
+  l.in.push_back(r);
+  return true;
+}
+
+bool parse_xconfig(kfp16_net* n, const char* text) {
+  static const std::map<std::string, LType> types = {
+      {"input", L_INPUT}, {"idct-layer", L_IDCT}, {"linear-component", L_LINEAR},
+      {"batchnorm-component", L_BATCHNORM}, {"spec-augment-layer", L_SPECAUG},
+      {"combine-feature-maps-layer", L_COMBINE}, {"conv-relu-batchnorm-layer", L_CONV},
+      {"tdnnf-layer", L_TDNNF}, {"prefinal-layer", L_PREFINAL}, {"output-layer", L_OUTPUT}};
+  std::stringstream ss(text);
+  std::string line;
+  int lineno = 0;
+  while (std::getline(ss, line)) {
+    ++lineno;
+    size_t hash = line.find('#');
+    if (hash != std::string::npos) line = line.substr(0, hash);
+    line = trim(line);
+    if (line.empty()) continue;
+    std::vector<std::string> tk = tokens(line);
+    Layer l;
+    l.type_name = tk[0];
+    auto tt = types.find(tk[0]);
+    if (tt == types.end()) {
+      set_error("xconfig line %d: unsupported layer type \"%s\"%s", lineno, tk[0].c_str(),
+                tk[0] == "attention-relu-batchnorm-layer" ? " (restricted self-attention runs on the CPU in the reference and is out of scope)" : "");
+      return false;
+    }
+    l.type = tt->second;
+    for (size_t i = 1; i < tk.size(); ++i) {
+      size_t eq = tk[i].find('=');
+      if (eq == std::string::npos) continue;
+      l.kv[tk[i].substr(0, eq)] = tk[i].substr(eq + 1);
+    }
+    l.name = l.kv.count("name") ? l.kv["name"] : "";
+    if (l.name.empty()) { set_error("xconfig line %d: layer without name", lineno); return false; }
+    if (find_layer(n, l.name) >= 0 && n->layers[find_layer(n, l.name)].name == l.name) {
+      set_error("xconfig line %d: duplicate layer name %s", lineno, l.name.c_str());
+      return false;
+    }
+    if (!parse_input_spec(n, l, (int)n->layers.size())) return false;
+    n->layers.push_back(l);
+  }
+  if (n->layers.empty()) { set_error("xconfig: no layers"); return false; }
+  return true;
+}
+
+// ------------------------------------------------------------------------------ plan
+bool resolve_dims(kfp16_net* n) {
+  // per-sequence inputs: consumed only through ReplaceIndex(x, t, 0) (the ivector, quirk Q6)
+  for (size_t i = 0; i < n->layers.size(); ++i) {
+    Layer& l = n->layers[i];
+    if (l.type != L_INPUT) continue;
+    bool any = false, all_replace = true;
+    for (auto& c : n->layers)
+      for (int src : c.in)
+        if (src == (int)i) { any = true; if (!c.in_replace) all_replace = false; }
+    l.per_seq = any && all_replace;
+  }
+  int max_halo = 0;
+  for (size_t i = 0; i < n->layers.size(); ++i) {
+    Layer& l = n->layers[i];
+    int in_dim = 0;
+    bool all_seq = !l.in.empty();
+    for (int src : l.in) { in_dim += n->layers[src].out_dim; all_seq = all_seq && n->layers[src].per_seq; }
+    l.in_dim = in_dim;
+    if (l.type != L_INPUT) l.per_seq = all_seq;
+    switch (l.type) {
+      case L_INPUT:
+        l.out_dim = kv_int(l, "dim", 0);
+        if (l.out_dim <= 0) { set_error("input layer %s missing dim", l.name.c_str()); return false; }
+        l.in_dim = l.out_dim;
+        break;
+      case L_IDCT:
+        l.out_dim = kv_int(l, "dim", l.in_dim);
+        l.lifter = kv_float(l, "cepstral-lifter", 22.0);
+        if (l.out_dim != l.in_dim) { set_error("idct-layer %s: dim %d != input dim %d", l.name.c_str(), l.out_dim, l.in_dim); return false; }
+        break;
+      case L_LINEAR:
+        l.out_dim = kv_int(l, "dim", 0);
+        if (l.out_dim <= 0) { set_error("linear-component %s missing dim", l.name.c_str()); return false; }
+        break;
+      case L_BATCHNORM: case L_SPECAUG:
+        l.out_dim = l.in_dim;
+        break;
+      case L_COMBINE:
+        l.out_dim = l.in_dim;
+        l.height = kv_int(l, "height", 0);
+        l.nf1 = kv_int(l, "num-filters1", 1);
+        l.nf2 = kv_int(l, "num-filters2", 1);
+        if (l.height * (l.nf1 + l.nf2) != l.in_dim) {
+          set_error("combine-feature-maps-layer %s: height*(nf1+nf2)=%d != input dim %d", l.name.c_str(), l.height * (l.nf1 + l.nf2), l.in_dim);
+          return false;
+        }
+        break;
+      case L_CONV:
+        set_error("conv-relu-batchnorm-layer %s: not wired into this executor build yet", l.name.c_str());
+        return false;
+      case L_TDNNF:
+        l.out_dim = kv_int(l, "dim", 0);
+        l.bott_dim = kv_int(l, "bottleneck-dim", 0);
+        if (l.out_dim <= 0 || l.bott_dim <= 0) { set_error("tdnnf-layer %s missing dim or bottleneck-dim", l.name.c_str()); return false; }
+        l.stride = kv_int(l, "time-stride", 3);
+        l.bypass = (float)kv_float(l, "bypass-scale", 0.66);
+        l.use_bypass = l.bypass > 0 && l.in_dim == l.out_dim;   // forward.go:688
+        if (l.stride < 0) { set_error("tdnnf-layer %s: negative time-stride", l.name.c_str()); return false; }
+        max_halo = std::max(max_halo, l.stride);
+        break;
+      case L_PREFINAL:
+        l.small_dim = kv_int(l, "small-dim", 0);
+        l.big_dim = kv_int(l, "big-dim", 0);
+        if (l.small_dim <= 0 || l.big_dim <= 0) { set_error("prefinal-layer %s missing small-dim or big-dim", l.name.c_str()); return false; }
+        l.out_dim = l.small_dim;
+        break;
+      case L_OUTPUT:
+        l.out_dim = kv_int(l, "dim", 0);
+        if (l.out_dim <= 0) { set_error("output-layer %s missing dim", l.name.c_str()); return false; }
+        l.log_softmax = kv_bool(l, "include-log-softmax", true);
+        break;
+    }
+    if (l.type != L_INPUT && l.in.empty()) { set_error("layer %s has no input", l.name.c_str()); return false; }
+  }
+  n->halo = max_halo;
+  n->blk = n->opts.seq_len + 2 * n->halo;
+  n->Tp = n->opts.n_seq * n->blk;
+  n->T = n->opts.n_seq * n->opts.seq_len;
+  // halo mode expected by consumers
+  for (auto& c : n->layers) {
+    if (c.type == L_TDNNF && c.stride > 0)
+      for (int src : c.in) n->layers[src].halo_mode = HALO_REPL;
+  }
+  // output layer + gradient reachability (Backward seeds only the chain output, network_backward.go:104-107)
+  n->out_layer = find_layer(n, "output");
+  if (n->out_layer < 0)
+    for (size_t i = 0; i < n->layers.size(); ++i)
+      if (n->layers[i].type == L_OUTPUT) { n->out_layer = (int)i; break; }
+  if (n->out_layer < 0) n->out_layer = (int)n->layers.size() - 1;
+  if (n->opts.train) {
+    std::vector<int> stack{n->out_layer};
+    while (!stack.empty()) {
+      int i = stack.back();
+      stack.pop_back();
+      if (n->layers[i].needs_grad) continue;
+      n->layers[i].needs_grad = true;
+      for (int src : n->layers[i].in) stack.push_back(src);
+    }
+    // a layer needs the gradient wrt its input only if something upstream has parameters
+    std::vector<bool> has_params_upstream(n->layers.size(), false);
+    for (size_t i = 0; i < n->layers.size(); ++i) {
+      const Layer& l = n->layers[i];
+      bool up = false;
+      for (int src : l.in) {
+        const Layer& s = n->layers[src];
+        bool own = s.type == L_LINEAR || s.type == L_TDNNF || s.type == L_PREFINAL || s.type == L_OUTPUT || s.type == L_CONV;
+        up = up || own || has_params_upstream[src];
+      }
+      has_params_upstream[i] = up;
+      n->layers[i].wants_dx = up;
+    }
+    for (auto& l : n->layers)
+      if (l.needs_grad && l.wants_dx)
+        for (int src : l.in) n->layers[src].n_grad_consumers++;
+  }
+  return true;
+}
+
+bool check_tma_dim(const Layer& l, int dim, const char* what) {
+  if (dim % 8) { set_error("layer %s: %s = %d must be a multiple of 8 (TMA rows are 16-byte aligned)", l.name.c_str(), what, dim); return false; }
+  return true;
+}
+
+bool build_plan(kfp16_net* n) {
+  const bool train = n->opts.train != 0;
+  // 1. parameters
+  for (auto& l : n->layers) {
+    switch (l.type) {
+      case L_LINEAR: l.pW = add_param(n, l.name + ".W", l.in_dim, l.out_dim); break;
+      case L_TDNNF: {
+        const int sp = l.stride > 0 ? 2 : 1;   // true spliced shapes (quirk Q1)
+        l.pLin = add_param(n, l.name + ".LinearW", sp * l.in_dim, l.bott_dim);
+        l.pAff = add_param(n, l.name + ".AffineW", sp * l.bott_dim, l.out_dim);
+        l.pAffB = add_param(n, l.name + ".AffineBias", 1, l.out_dim, true);
+        break;
+      }
+      case L_PREFINAL:
+        l.pBig = add_param(n, l.name + ".BigW", l.in_dim, l.big_dim);
+        l.pBigB = add_param(n, l.name + ".BigBias", 1, l.big_dim, true);
+        l.pSmall = add_param(n, l.name + ".SmallW", l.big_dim, l.small_dim);
+        break;
+      case L_OUTPUT:
+        l.pW = add_param(n, l.name + ".W", l.in_dim, l.out_dim);
+        l.pB = add_param(n, l.name + ".Bias", 1, l.out_dim, true);
+        break;
+      default: break;
+    }
+  }
+  if (!dev_alloc(n, (void**)&n->w16, std::max<size_t>(n->bucket, 8) * sizeof(__half))) return false;
+  if (train) {
+    if (!dev_alloc(n, (void**)&n->w32, std::max<size_t>(n->bucket, 8) * sizeof(float))) return false;
+    if (!dev_alloc(n, (void**)&n->vel, std::max<size_t>(n->bucket, 8) * sizeof(float))) return false;
+    if (!dev_alloc(n, (void**)&n->g32, std::max<size_t>(n->bucket, 8) * sizeof(float))) return false;
+  }
+  if (!dev_alloc(n, (void**)&n->loss_dev, 256)) return false;
+
+  // 2. activations
+  size_t max_dense = 16;
+  for (auto& l : n->layers) {
+    const int rows = l.per_seq ? n->opts.n_seq : n->Tp;
+    if (!check_tma_dim(l, l.out_dim, "output dim")) return false;
+    if (l.in.size() > 1) {
+      if (!alloc_buf(n, l.in_cat, rows, l.in_dim)) return false;
+      if (train && l.needs_grad && l.wants_dx && !alloc_buf(n, l.d_in_cat, rows, l.in_dim)) return false;
+    }
+    if (!alloc_buf(n, l.out, rows, l.out_dim)) return false;
+    max_dense = std::max(max_dense, (size_t)n->T * l.out_dim * sizeof(__half));
+    if (train && l.needs_grad) {
+      if (!alloc_buf(n, l.dout, rows, l.out_dim)) return false;
+      if (l.wants_dx && !alloc_buf(n, l.tmp_dx, rows, l.in_dim)) return false;
+    }
+    const double M = l.per_seq ? n->opts.n_seq : n->T;
+    switch (l.type) {
+      case L_IDCT: {
+        // makeIDCTMatrix (forward.go:1190-1210), through the truncating converter
+        const int D = l.out_dim;
+        std::vector<uint16_t> h((size_t)D * D);
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            double v = cos(M_PI * j * (i + 0.5) / D) * (j == 0 ? sqrt(1.0 / D) : sqrt(2.0 / D));
+            if (l.lifter > 0 && j > 0) v *= 1.0 + (l.lifter / 2.0) * sin(M_PI * j / l.lifter);
+            h[(size_t)i * D + j] = f32_to_f16_trunc((float)v);
+          }
+        if (!dev_alloc(n, (void**)&l.idct_mat, h.size() * 2)) return false;
+        if (!check_cuda(cudaMemcpy(l.idct_mat, h.data(), h.size() * 2, cudaMemcpyHostToDevice), "idct upload")) return false;
+        n->flops_fwd += 2.0 * M * D * D;
+        break;
+      }
+      case L_LINEAR:
+        if (!check_tma_dim(l, l.in_dim, "input dim")) return false;
+        n->flops_fwd += 2.0 * M * l.in_dim * l.out_dim;
+        break;
+      case L_BATCHNORM: {
+        const float rms = (float)kv_float(l, "target-rms", 1.0);
+        if (!make_bn(n, l.bn, l.in_dim, rms, rms != 1.0f)) return false;
+        break;
+      }
+      case L_TDNNF: {
+        if (!check_tma_dim(l, l.in_dim, "input dim") || !check_tma_dim(l, l.bott_dim, "bottleneck-dim")) return false;
+        if (l.stride > 0 && ((l.in_dim % 16) || (l.bott_dim % 16))) {
+          set_error("tdnnf-layer %s: spliced dims must be multiples of 16 (in %d, bottleneck %d)", l.name.c_str(), l.in_dim, l.bott_dim);
+          return false;
+        }
+        if (l.per_seq) { set_error("tdnnf-layer %s on a per-sequence input", l.name.c_str()); return false; }
+        const int sp = l.stride > 0 ? 2 : 1;
+        if (!alloc_buf(n, l.bott, n->Tp, l.bott_dim)) return false;
+        if (!make_bn(n, l.bn, l.out_dim, 1.0f, false)) return false;
+        l.mask_ld = (l.out_dim + 31) / 32;
+        if (!dev_alloc(n, (void**)&l.mask, (size_t)n->Tp * l.mask_ld * 4)) return false;
+        if (train && l.needs_grad) {
+          if (!alloc_buf(n, l.dbott, n->Tp, l.bott_dim)) return false;
+          if (!alloc_buf(n, l.dz, n->Tp, l.out_dim)) return false;
+        }
+        n->flops_fwd += 2.0 * M * (sp * l.in_dim) * l.bott_dim + 2.0 * M * (sp * l.bott_dim) * l.out_dim;
+        break;
+      }
+      case L_PREFINAL: {
+        if (!check_tma_dim(l, l.in_dim, "input dim") || !check_tma_dim(l, l.big_dim, "big-dim")) return false;
+        const int rows2 = l.per_seq ? n->opts.n_seq : n->Tp;
+        if (!alloc_buf(n, l.big, rows2, l.big_dim)) return false;
+        if (!make_bn(n, l.bn, l.big_dim, 1.0f, false)) return false;
+        if (!make_bn(n, l.bn2, l.small_dim, 1.0f, false)) return false;
+        l.mask_ld = (l.big_dim + 31) / 32;
+        if (!dev_alloc(n, (void**)&l.mask, (size_t)rows2 * l.mask_ld * 4)) return false;
+        if (train && l.needs_grad) {
+          if (!alloc_buf(n, l.dbig, rows2, l.big_dim)) return false;
+          if (!alloc_buf(n, l.dys, rows2, l.small_dim)) return false;
+        }
+        n->flops_fwd += 2.0 * M * l.in_dim * l.big_dim + 2.0 * M * l.big_dim * l.small_dim;
+        break;
+      }
+      case L_OUTPUT:
+        if (!check_tma_dim(l, l.in_dim, "input dim")) return false;
+        n->flops_fwd += 2.0 * M * l.in_dim * l.out_dim;
+        break;
+      default: break;
+    }
+  }
+  n->stage_bytes = max_dense;
+  if (!dev_alloc(n, (void**)&n->stage_in, n->stage_bytes)) return false;
+  return check_cuda(cudaStreamSynchronize(n->ctx->stream), "plan sync");
+}
+
+// ------------------------------------------------------------------------------ GEMM helpers
+kfp16_gemm_desc mk_desc(int M, int N, int K) {
+  kfp16_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = M; d.N = N; d.K = K;
+  d.groups = 1; d.kslabs = 1; d.kslab_len = K;
+  d.alpha = 1.0f;
+  d.a_major = KFP16_K_MAJOR;
+  d.b_major = KFP16_MN_MAJOR;
+  return d;
+}
+void set_A(kfp16_gemm_desc& d, const void* p, int rows, int cols) { d.A.ptr = p; d.A.rows = rows; d.A.cols = cols; d.A.ld = cols; d.A.halo = 0; }
+void set_B(kfp16_gemm_desc& d, const void* p, int rows, int cols) { d.B.ptr = p; d.B.rows = rows; d.B.cols = cols; d.B.ld = cols; d.B.halo = 0; }
+
+int pick_split_k(const kfp16_net* n, int M, int N, int groups, int K) {
+  const int m_tiles = (M + 127) / 128;
+  const int bn = N <= 64 ? 64 : N <= 128 ? 128 : N <= 160 ? 160 : 256;
+  const int n_tiles = (N + bn - 1) / bn;
+  const int tiles = m_tiles * n_tiles * groups;
+  const int kb = (K + 63) / 64;
+  int split = (2 * n->ctx->num_sms + tiles - 1) / tiles;
+  split = std::min(split, std::max(1, kb / 4));
+  return std::max(split, 2);   // >= 2 selects the fp32 accumulate path into the gradient bucket
+}
+
+__half* W16(kfp16_net* n, int p) { return n->w16 + n->params[p].off; }
+float* G32(kfp16_net* n, int p) { return n->g32 + n->params[p].off; }
+
+// dW[in x out] (+)= X^T * dY, fp32 into the gradient bucket.  Up to two row-shifted groups (splice).
+int wgrad(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int off0, int off1) {
+  const int in = X.cols, out = dY.cols;
+  kfp16_gemm_desc d = mk_desc(in, out, X.rows);
+  d.a_major = KFP16_MN_MAJOR;
+  set_A(d, X.p, X.rows, X.cols);
+  set_B(d, dY.p, dY.rows, dY.cols);
+  d.groups = groups;
+  d.a_row_off[0][0] = off0;
+  d.a_row_off[1][0] = off1;
+  d.split_k = pick_split_k(n, in, out, groups, X.rows);
+  d.ws[0] = G32(n, param);
+  d.ws[1] = G32(n, param) + (size_t)in * out;
+  d.ws_ld = out;
+  return kfp16_gemm_ex(n->ctx, &d);
+}
+
+// route a freshly computed input-gradient into the producer(s) of layer l
+int deliver_dx(kfp16_net* n, Layer& l, const Buf& dx) {
+  // dx: [rows x in_dim]; single producer: dx IS producer.dout when it was written in place
+  int col = 0;
+  for (int src : l.in) {
+    Layer& s = n->layers[src];
+    if (!s.needs_grad || !s.dout.p) { col += s.out_dim; continue; }
+    const bool first = s.grads_seen == 0;
+    s.grads_seen++;
+    if (l.in.size() == 1 && dx.p == s.dout.p) { col += s.out_dim; continue; }   // written in place
+    if (s.per_seq && !l.per_seq) {
+      // adjoint of the per-sequence broadcast
+      if (first) {
+        if (kfp16_seq_sum(n->ctx, dx.p, dx.cols, col, s.dout.p, s.out_dim, n->opts.n_seq, n->opts.seq_len, n->halo)) return -1;
+      } else {
+        set_error("layer %s: a per-sequence producer with several gradient consumers is not supported", s.name.c_str());
+        return -1;
+      }
+    } else if (first) {
+      if (ops_slice_cols_on(n->ctx->stream, dx.p, dx.rows, dx.cols, s.dout.p, s.out_dim, col)) return -1;
+    } else {
+      if (ops_slice_add_on(n->ctx->stream, dx.p, dx.rows, dx.cols, s.dout.p, s.out_dim, col)) return -1;
+    }
+    col += s.out_dim;
+  }
+  return 0;
+}
+
+// where layer l should write its input gradient so that no copy is needed
+Buf dx_target(kfp16_net* n, Layer& l) {
+  if (l.in.size() == 1) {
+    Layer& s = n->layers[l.in[0]];
+    if (s.needs_grad && s.dout.p && s.grads_seen == 0 && s.per_seq == l.per_seq) return s.dout;
+    return l.tmp_dx;
+  }
+  return l.d_in_cat;
+}
+
+const Buf& layer_input(kfp16_net* n, Layer& l) { return l.in.size() > 1 ? l.in_cat : n->layers[l.in[0]].out; }
+
+// ------------------------------------------------------------------------------ forward
+int fix_halo(kfp16_net* n, Layer& l, Buf& b, int mode) {
+  if (l.per_seq || n->halo == 0) return 0;
+  if (mode == HALO_REPL) return kfp16_pad_edges(n->ctx, b.p, b.cols, n->opts.n_seq, n->opts.seq_len, b.cols, n->halo);
+  if (mode == HALO_ZERO) return kfp16_zero_halo(n->ctx, b.p, b.cols, n->opts.n_seq, n->opts.seq_len, b.cols, n->halo);
+  return 0;
+}
+
+int forward_layer(kfp16_net* n, Layer& l) {
+  kfp16_ctx* ctx = n->ctx;
+  const uint32_t rr = n->opts.ref_round ? KFP16_EPI_REF_ROUND : 0;
+  if (l.type == L_INPUT) return 0;
+  const int rows = l.per_seq ? n->opts.n_seq : n->Tp;
+  if (l.in.size() > 1) {   // Append(...) (forward.go:264-310), per-sequence members broadcast (Q6)
+    int col = 0;
+    for (int src : l.in) {
+      Layer& s = n->layers[src];
+      if (s.per_seq && !l.per_seq) {
+        if (kfp16_bcast_rows(ctx, s.out.p, s.out_dim, l.in_cat.p, l.in_dim, col, rows, n->blk)) return -1;
+      } else {
+        if (ops_concat_cols_on(ctx->stream, l.in_cat.p, rows, l.in_dim, s.out.p, s.out_dim, col)) return -1;
+      }
+      col += s.out_dim;
+    }
+  }
+  const Buf& X = layer_input(n, l);
+  switch (l.type) {
+    case L_IDCT: {   // Y = h(X*M)  forward.go:317-330
+      kfp16_gemm_desc d = mk_desc(rows, l.out_dim, l.in_dim);
+      set_A(d, X.p, rows, l.in_dim);
+      set_B(d, l.idct_mat, l.in_dim, l.out_dim);
+      d.D[0] = l.out.p; d.ldd = l.out_dim;
+      if (kfp16_gemm_ex(ctx, &d)) return -1;
+      break;
+    }
+    case L_LINEAR: {   // Y = h(X*W)  forward.go:333-346
+      kfp16_gemm_desc d = mk_desc(rows, l.out_dim, l.in_dim);
+      set_A(d, X.p, rows, l.in_dim);
+      set_B(d, W16(n, l.pW), l.in_dim, l.out_dim);
+      d.D[0] = l.out.p; d.ldd = l.out_dim;
+      if (kfp16_gemm_ex(ctx, &d)) return -1;
+      break;
+    }
+    case L_BATCHNORM:   // forward.go:349-374
+      if (kfp16_scale_shift(ctx, X.p, l.out.p, rows, l.out_dim, l.bn.scale, l.bn.shift)) return -1;
+      break;
+    case L_SPECAUG:     // pass-through (forward.go:377-383)
+      if (!check_cuda(cudaMemcpyAsync(l.out.p, X.p, l.out.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "spec-augment copy")) return -1;
+      break;
+    case L_COMBINE:     // forward.go:386-405
+      if (!check_cuda(cudaMemcpyAsync(l.out.p, X.p, l.out.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "combine copy")) return -1;
+      if (ops_combine_feature_maps_on(ctx->stream, l.out.p, rows, l.out_dim, l.height, l.nf1, l.nf2, 0)) return -1;
+      break;
+    case L_TDNNF: {     // forward.go:589-695
+      const int s = l.stride, sp = s > 0 ? 2 : 1;
+      {  // bottleneck = [X(t-s) | X(t)] * Wlin
+        kfp16_gemm_desc d = mk_desc(rows, l.bott_dim, sp * l.in_dim);
+        set_A(d, X.p, rows, l.in_dim);
+        set_B(d, W16(n, l.pLin), sp * l.in_dim, l.bott_dim);
+        d.kslabs = sp; d.kslab_len = l.in_dim;
+        if (sp == 2) { d.a_row_off[0][0] = -s; d.a_row_off[0][1] = 0; d.b_row_off[0][0] = 0; d.b_row_off[0][1] = l.in_dim; }
+        d.D[0] = l.bott.p; d.ldd = l.bott_dim;
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+        if (s > 0 && fix_halo(n, l, l.bott, HALO_REPL)) return -1;
+      }
+      {  // Y = BN(ReLU([B(t) | B(t+s)] * Waff + b)) (+ bypass*X)
+        kfp16_gemm_desc d = mk_desc(rows, l.out_dim, sp * l.bott_dim);
+        set_A(d, l.bott.p, rows, l.bott_dim);
+        set_B(d, W16(n, l.pAff), sp * l.bott_dim, l.out_dim);
+        d.kslabs = sp; d.kslab_len = l.bott_dim;
+        if (sp == 2) { d.a_row_off[0][0] = 0; d.a_row_off[0][1] = s; d.b_row_off[0][0] = 0; d.b_row_off[0][1] = l.bott_dim; }
+        d.D[0] = l.out.p; d.ldd = l.out_dim;
+        d.flags = KFP16_EPI_BIAS | KFP16_EPI_RELU | KFP16_EPI_BN | KFP16_EPI_MASK | rr;
+        d.bias = W16(n, l.pAffB);
+        d.bn_scale = l.bn.scale; d.bn_shift = l.bn.shift;
+        d.mask_out = l.mask; d.mask_ld = l.mask_ld;
+        if (l.use_bypass) { d.flags |= KFP16_EPI_RESID; d.R[0] = X.p; d.ldr = l.in_dim; d.res_scale = l.bypass; }
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+      }
+      break;
+    }
+    case L_PREFINAL: {   // forward.go:912-968: affine(big) -> ReLU -> BN1 -> linear(small) -> BN2
+      kfp16_gemm_desc d = mk_desc(rows, l.big_dim, l.in_dim);
+      set_A(d, X.p, rows, l.in_dim);
+      set_B(d, W16(n, l.pBig), l.in_dim, l.big_dim);
+      d.D[0] = l.big.p; d.ldd = l.big_dim;
+      d.flags = KFP16_EPI_BIAS | KFP16_EPI_RELU | KFP16_EPI_BN | KFP16_EPI_MASK | rr;
+      d.bias = W16(n, l.pBigB);
+      d.bn_scale = l.bn.scale; d.bn_shift = l.bn.shift;
+      d.mask_out = l.mask; d.mask_ld = l.mask_ld;
+      if (kfp16_gemm_ex(ctx, &d)) return -1;
+      kfp16_gemm_desc e = mk_desc(rows, l.small_dim, l.big_dim);
+      set_A(e, l.big.p, rows, l.big_dim);
+      set_B(e, W16(n, l.pSmall), l.big_dim, l.small_dim);
+      e.D[0] = l.out.p; e.ldd = l.small_dim;
+      e.flags = KFP16_EPI_BN | rr;
+      e.bn_scale = l.bn2.scale; e.bn_shift = l.bn2.shift;
+      if (kfp16_gemm_ex(ctx, &e)) return -1;
+      break;
+    }
+    case L_OUTPUT: {     // forward.go:971-1001
+      kfp16_gemm_desc d = mk_desc(rows, l.out_dim, l.in_dim);
+      set_A(d, X.p, rows, l.in_dim);
+      set_B(d, W16(n, l.pW), l.in_dim, l.out_dim);
+      d.D[0] = l.out.p; d.ldd = l.out_dim;
+      d.flags = KFP16_EPI_BIAS | rr;
+      d.bias = W16(n, l.pB);
+      if (kfp16_gemm_ex(ctx, &d)) return -1;
+      if (l.log_softmax && softmax_on_stream(ctx->stream, l.out.p, rows, l.out_dim, true)) return -1;
+      break;
+    }
+    default: break;
+  }
+  if (l.halo_mode != HALO_NONE && fix_halo(n, l, l.out, l.halo_mode)) return -1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ backward
+int backward_layer(kfp16_net* n, Layer& l) {
+  kfp16_ctx* ctx = n->ctx;
+  if (!l.needs_grad || l.type == L_INPUT) return 0;
+  const int rows = l.per_seq ? n->opts.n_seq : n->Tp;
+  // adjoint of the halo fix-up applied to this layer's output in the forward pass
+  if (!l.per_seq && n->halo > 0) {
+    if (l.halo_mode == HALO_REPL && kfp16_fold_edges(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
+    if (l.halo_mode == HALO_ZERO && kfp16_zero_halo(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
+  }
+  const Buf& X = layer_input(n, l);
+  Buf dx = l.wants_dx ? dx_target(n, l) : Buf();
+  switch (l.type) {
+    case L_IDCT:
+    case L_LINEAR: {
+      const __half* W = l.type == L_IDCT ? l.idct_mat : W16(n, l.pW);
+      if (l.wants_dx) {   // dX = dY * W^T   (backward_ops.go:162-192)
+        kfp16_gemm_desc d = mk_desc(rows, l.in_dim, l.out_dim);
+        set_A(d, l.dout.p, rows, l.out_dim);
+        d.b_major = KFP16_K_MAJOR;
+        set_B(d, W, l.in_dim, l.out_dim);
+        d.D[0] = dx.p; d.ldd = l.in_dim;
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+      }
+      if (l.type == L_LINEAR && wgrad(n, X, l.dout, l.pW, 1, 0, 0)) return -1;   // backward_ops.go:195-225
+      break;
+    }
+    case L_BATCHNORM:   // dX = dY * gamma/sqrt(var+eps)  (backward_wrappers.cu:104-115)
+      if (l.wants_dx && kfp16_scale_shift(ctx, l.dout.p, dx.p, rows, l.out_dim, l.bn.scale, nullptr)) return -1;
+      break;
+    case L_SPECAUG:
+      if (l.wants_dx && !check_cuda(cudaMemcpyAsync(dx.p, l.dout.p, l.dout.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "spec-augment grad")) return -1;
+      break;
+    case L_COMBINE:     // inverse permutation
+      if (l.wants_dx) {
+        if (!check_cuda(cudaMemcpyAsync(dx.p, l.dout.p, l.dout.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "combine grad")) return -1;
+        if (ops_combine_feature_maps_on(ctx->stream, dx.p, rows, l.out_dim, l.height, l.nf1, l.nf2, 1)) return -1;
+      }
+      break;
+    case L_TDNNF: {
+      const int s = l.stride, sp = s > 0 ? 2 : 1;
+      // dZ = mask ? h(dY * bn_scale) : 0 ; db += colsum(dZ)
+      if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim, rows, l.out_dim, G32(n, l.pAffB))) return -1;
+      {  // dB(r) = dZ(r)*Waff[0:bn]^T + dZ(r-s)*Waff[bn:2bn]^T
+        kfp16_gemm_desc d = mk_desc(rows, l.bott_dim, sp * l.out_dim);
+        set_A(d, l.dz.p, rows, l.out_dim);
+        d.b_major = KFP16_K_MAJOR;
+        set_B(d, W16(n, l.pAff), sp * l.bott_dim, l.out_dim);
+        d.kslabs = sp; d.kslab_len = l.out_dim;
+        if (sp == 2) { d.a_row_off[0][0] = 0; d.a_row_off[0][1] = -s; d.b_row_off[0][0] = 0; d.b_row_off[0][1] = l.bott_dim; }
+        d.D[0] = l.dbott.p; d.ldd = l.bott_dim;
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+        if (s > 0 && kfp16_fold_edges(ctx, l.dbott.p, l.bott_dim, n->opts.n_seq, n->opts.seq_len, l.bott_dim, n->halo)) return -1;
+      }
+      // dWaff = [B(t) | B(t+s)]^T * dZ
+      if (wgrad(n, l.bott, l.dz, l.pAff, sp, 0, s)) return -1;
+      if (l.wants_dx) {   // dX(r) = dB(r+s)*Wlin[0:in]^T + dB(r)*Wlin[in:2in]^T (+ bypass*dY)
+        kfp16_gemm_desc d = mk_desc(rows, l.in_dim, sp * l.bott_dim);
+        set_A(d, l.dbott.p, rows, l.bott_dim);
+        d.b_major = KFP16_K_MAJOR;
+        set_B(d, W16(n, l.pLin), sp * l.in_dim, l.bott_dim);
+        d.kslabs = sp; d.kslab_len = l.bott_dim;
+        if (sp == 2) { d.a_row_off[0][0] = s; d.a_row_off[0][1] = 0; d.b_row_off[0][0] = 0; d.b_row_off[0][1] = l.in_dim; }
+        d.D[0] = dx.p; d.ldd = l.in_dim;
+        if (l.use_bypass) { d.flags |= KFP16_EPI_RESID; d.R[0] = l.dout.p; d.ldr = l.out_dim; d.res_scale = l.bypass; }
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+      }
+      // dWlin = [X(t-s) | X(t)]^T * dB
+      if (wgrad(n, X, l.dbott, l.pLin, sp, -s, 0)) return -1;
+      break;
+    }
+    case L_PREFINAL: {
+      // dYs = dY * bn2_scale
+      if (kfp16_scale_shift(ctx, l.dout.p, l.dys.p, rows, l.small_dim, l.bn2.scale, nullptr)) return -1;
+      {  // dG = mask ? h((dYs * Wsmall^T) * bn1_scale) : 0
+        kfp16_gemm_desc d = mk_desc(rows, l.big_dim, l.small_dim);
+        set_A(d, l.dys.p, rows, l.small_dim);
+        d.b_major = KFP16_K_MAJOR;
+        set_B(d, W16(n, l.pSmall), l.big_dim, l.small_dim);
+        d.D[0] = l.dbig.p; d.ldd = l.big_dim;
+        d.flags = KFP16_EPI_BN | KFP16_EPI_GRADMASK | (n->opts.ref_round ? KFP16_EPI_REF_ROUND : 0);
+        d.bn_scale = l.bn.scale; d.bn_shift = l.bn.zero;
+        d.mask_in = l.mask; d.mask_ld = l.mask_ld;
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+      }
+      if (wgrad(n, l.big, l.dys, l.pSmall, 1, 0, 0)) return -1;
+      if (kfp16_colsum_accum(ctx, l.dbig.p, l.big_dim, rows, l.big_dim, G32(n, l.pBigB))) return -1;
+      if (l.wants_dx) {
+        kfp16_gemm_desc d = mk_desc(rows, l.in_dim, l.big_dim);
+        set_A(d, l.dbig.p, rows, l.big_dim);
+        d.b_major = KFP16_K_MAJOR;
+        set_B(d, W16(n, l.pBig), l.in_dim, l.big_dim);
+        d.D[0] = dx.p; d.ldd = l.in_dim;
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+      }
+      if (wgrad(n, X, l.dbig, l.pBig, 1, 0, 0)) return -1;
+      break;
+    }
+    case L_OUTPUT: {   // log-softmax Jacobian is not applied (network_backward.go:243-244)
+      if (l.wants_dx) {
+        kfp16_gemm_desc d = mk_desc(rows, l.in_dim, l.out_dim);
+        set_A(d, l.dout.p, rows, l.out_dim);
+        d.b_major = KFP16_K_MAJOR;
+        set_B(d, W16(n, l.pW), l.in_dim, l.out_dim);
+        d.D[0] = dx.p; d.ldd = l.in_dim;
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+      }
+      if (wgrad(n, X, l.dout, l.pW, 1, 0, 0)) return -1;
+      if (kfp16_colsum_accum(ctx, l.dout.p, l.out_dim, rows, l.out_dim, G32(n, l.pB))) return -1;
+      break;
+    }
+    default: break;
+  }
+  if (l.wants_dx && deliver_dx(n, l, dx)) return -1;
+  return 0;
+}
+
+int run_phases(kfp16_net* n, int phases) {
+  if (phases & 1) {
+    if (kfp16_net_zero_grads(n)) return -1;
+    if (kfp16_net_forward(n)) return -1;
+    if (kfp16_net_loss_half_sq(n, "")) return -1;
+    if (kfp16_net_backward(n)) return -1;
+  }
+  if (phases & 2) {
+    if (kfp16_net_sgd_step(n, 1.0f, 1)) return -1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+kfp16_net* kfp16_net_create(kfp16_ctx* ctx, const char* xconfig, const kfp16_net_opts* opts) {
+  if (!ctx || !xconfig || !opts) { set_error("kfp16_net_create: null argument"); return nullptr; }
+  if (opts->n_seq <= 0 || opts->seq_len <= 0) { set_error("kfp16_net_create: n_seq and seq_len must be positive"); return nullptr; }
+  if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return nullptr;
+  std::unique_ptr<kfp16_net> n(new kfp16_net());
+  n->ctx = ctx;
+  n->opts = *opts;
+  bool ok = parse_xconfig(n.get(), xconfig) && resolve_dims(n.get()) && build_plan(n.get());
+  if (!ok) {
+    char msg[512];
+    snprintf(msg, sizeof(msg), "%s", get_error() ? get_error() : "?");
+    kfp16_net_destroy(n.release());
+    set_error("%s", msg);
+    return nullptr;
+  }
+  if (kfp16_net_init_random(n.get(), 42) != 0) { kfp16_net_destroy(n.release()); return nullptr; }
+  return n.release();
+}
+
+void kfp16_net_destroy(kfp16_net* n) {
+  if (!n) return;
+  for (auto& g : n->graph)
+    if (g) cudaGraphExecDestroy(g);
+  for (void* p : n->allocs) cudaFree(p);
+  delete n;
+}
+
+int kfp16_net_num_layers(const kfp16_net* n) { return n ? (int)n->layers.size() : 0; }
+const char* kfp16_net_layer_name(const kfp16_net* n, int i) { return (n && i >= 0 && i < (int)n->layers.size()) ? n->layers[i].name.c_str() : nullptr; }
+const char* kfp16_net_layer_type(const kfp16_net* n, int i) { return (n && i >= 0 && i < (int)n->layers.size()) ? n->layers[i].type_name.c_str() : nullptr; }
+int kfp16_net_layer_dim(const kfp16_net* n, int i) { return (n && i >= 0 && i < (int)n->layers.size()) ? n->layers[i].out_dim : 0; }
+int kfp16_net_padded_rows(const kfp16_net* n) { return n ? n->Tp : 0; }
+int kfp16_net_halo(const kfp16_net* n) { return n ? n->halo : 0; }
+double kfp16_net_flops_forward(const kfp16_net* n) { return n ? n->flops_fwd : 0.0; }
+
+int kfp16_net_num_params(const kfp16_net* n) { return n ? (int)n->params.size() : 0; }
+const char* kfp16_net_param_name(const kfp16_net* n, int i) { return (n && i >= 0 && i < (int)n->params.size()) ? n->params[i].name.c_str() : nullptr; }
+int kfp16_net_param_shape(const kfp16_net* n, int i, int* rows, int* cols) {
+  if (!n || i < 0 || i >= (int)n->params.size()) { set_error("kfp16_net_param_shape: bad index"); return -1; }
+  if (rows) *rows = n->params[i].rows;
+  if (cols) *cols = n->params[i].cols;
+  return 0;
+}
+size_t kfp16_net_param_offset(const kfp16_net* n, int i) { return (n && i >= 0 && i < (int)n->params.size()) ? n->params[i].off : 0; }
+size_t kfp16_net_bucket_size(const kfp16_net* n) { return n ? n->bucket : 0; }
+void* kfp16_net_params_f16(kfp16_net* n) { return n ? n->w16 : nullptr; }
+float* kfp16_net_params_f32(kfp16_net* n) { return n ? n->w32 : nullptr; }
+float* kfp16_net_velocity(kfp16_net* n) { return n ? n->vel : nullptr; }
+float* kfp16_net_grads_f32(kfp16_net* n) { return n ? n->g32 : nullptr; }
+
+int kfp16_net_set_param(kfp16_net* n, const char* name, const float* host, int rows, int cols) {
+  if (!n || !name || !host) { set_error("kfp16_net_set_param: null argument"); return -1; }
+  const int i = find_param(n, name);
+  if (i < 0) { set_error("kfp16_net_set_param: no parameter named %s", name); return -1; }
+  const Param& P = n->params[i];
+  if (P.rows != rows || P.cols != cols) { set_error("kfp16_net_set_param: %s is [%d x %d], got [%d x %d]", name, P.rows, P.cols, rows, cols); return -1; }
+  const size_t cnt = (size_t)rows * cols;
+  std::vector<uint16_t> h16(cnt);
+  std::vector<float> h32(cnt);
+  for (size_t k = 0; k < cnt; ++k) { h16[k] = f32_to_f16_trunc(host[k]); h32[k] = f16_bits_to_f32(h16[k]); }
+  if (!check_cuda(cudaMemcpy(n->w16 + P.off, h16.data(), cnt * 2, cudaMemcpyHostToDevice), "param upload")) return -1;
+  if (n->w32) {
+    if (!check_cuda(cudaMemcpy(n->w32 + P.off, h32.data(), cnt * 4, cudaMemcpyHostToDevice), "master upload")) return -1;
+    if (!check_cuda(cudaMemset(n->vel + P.off, 0, cnt * 4), "velocity reset")) return -1;
+  }
+  return 0;
+}
+int kfp16_net_get_param(kfp16_net* n, const char* name, uint16_t* host, int rows, int cols) {
+  if (!n || !name || !host) { set_error("kfp16_net_get_param: null argument"); return -1; }
+  const int i = find_param(n, name);
+  if (i < 0) { set_error("kfp16_net_get_param: no parameter named %s", name); return -1; }
+  const Param& P = n->params[i];
+  if (P.rows != rows || P.cols != cols) { set_error("kfp16_net_get_param: shape mismatch for %s", name); return -1; }
+  if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "sync")) return -1;
+  return check_cuda(cudaMemcpy(host, n->w16 + P.off, (size_t)rows * cols * 2, cudaMemcpyDeviceToHost), "param download") ? 0 : -1;
+}
+
+int kfp16_net_set_bn(kfp16_net* n, const char* layer, const char* which, const float* mean, const float* var,
+                     const float* gamma, const float* beta, float eps, int dim) {
+  if (!n || !layer || !mean || !var) { set_error("kfp16_net_set_bn: null argument"); return -1; }
+  const int i = find_layer(n, layer);
+  if (i < 0) { set_error("kfp16_net_set_bn: no layer %s", layer); return -1; }
+  Layer& l = n->layers[i];
+  BNorm* bn = &l.bn;
+  if (which && (!strcmp(which, "BN") || !strcmp(which, "bn2")) && l.type == L_PREFINAL) bn = &l.bn2;
+  if (!bn->present || bn->dim != dim) { set_error("kfp16_net_set_bn: layer %s has no batch-norm of dim %d", layer, dim); return -1; }
+  bn->eps = eps;
+  std::vector<float> ones(dim, 1.f), zeros(dim, 0.f);
+  const size_t b = (size_t)dim * sizeof(float);
+  if (!check_cuda(cudaMemcpy(bn->mean, mean, b, cudaMemcpyHostToDevice), "bn mean") ||
+      !check_cuda(cudaMemcpy(bn->var, var, b, cudaMemcpyHostToDevice), "bn var") ||
+      !check_cuda(cudaMemcpy(bn->gamma, gamma ? gamma : ones.data(), b, cudaMemcpyHostToDevice), "bn gamma") ||
+      !check_cuda(cudaMemcpy(bn->beta, beta ? beta : zeros.data(), b, cudaMemcpyHostToDevice), "bn beta"))
+    return -1;
+  const bool rms = bn->rms_only;
+  if (kfp16_bn_fold(n->ctx, bn->mean, bn->var, rms ? nullptr : bn->gamma, rms ? nullptr : bn->beta, eps, bn->target_rms, dim, bn->scale, bn->shift)) return -1;
+  return check_cuda(cudaStreamSynchronize(n->ctx->stream), "bn fold sync") ? 0 : -1;
+}
+
+int kfp16_net_init_random(kfp16_net* n, uint64_t seed) {
+  if (!n) { set_error("kfp16_net_init_random: null network"); return -1; }
+  std::mt19937_64 rng(seed);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  std::vector<uint16_t> h16(std::max<size_t>(n->bucket, 1), 0);
+  for (const Param& P : n->params) {
+    if (P.is_bias) continue;
+    const float scale = sqrtf(2.0f / (float)(P.rows + P.cols));   // forward.go:1161-1168
+    for (size_t k = 0; k < (size_t)P.rows * P.cols; ++k) h16[P.off + k] = f32_to_f16_trunc(nd(rng) * scale);
+  }
+  if (!check_cuda(cudaMemcpy(n->w16, h16.data(), n->bucket * 2, cudaMemcpyHostToDevice), "param upload")) return -1;
+  if (n->w32) {
+    std::vector<float> h32(n->bucket);
+    for (size_t k = 0; k < n->bucket; ++k) h32[k] = f16_bits_to_f32(h16[k]);
+    if (!check_cuda(cudaMemcpy(n->w32, h32.data(), n->bucket * 4, cudaMemcpyHostToDevice), "master upload")) return -1;
+    if (!check_cuda(cudaMemset(n->vel, 0, n->bucket * 4), "velocity reset")) return -1;
+  }
+  return 0;
+}
+
+static int set_input_common(kfp16_net* n, const char* input_name, const void* dense_dev, int rows, int cols) {
+  const int i = find_layer(n, input_name);
+  if (i < 0 || n->layers[i].type != L_INPUT) { set_error("kfp16_net_set_input: no input layer named %s", input_name); return -1; }
+  Layer& l = n->layers[i];
+  const int want_rows = l.per_seq ? n->opts.n_seq : n->T;
+  if (rows != want_rows || cols != l.out_dim) {
+    set_error("kfp16_net_set_input: %s expects [%d x %d], got [%d x %d]", input_name, want_rows, l.out_dim, rows, cols);
+    return -1;
+  }
+  if (l.per_seq)
+    return check_cuda(cudaMemcpyAsync(l.out.p, dense_dev, (size_t)rows * cols * 2, cudaMemcpyDeviceToDevice, n->ctx->stream), "input copy") ? 0 : -1;
+  // halo rows: replicate for spliced consumers, zero otherwise (finite values either way)
+  return kfp16_pack_rows(n->ctx, dense_dev, l.out.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, n->halo, cols, l.halo_mode == HALO_ZERO ? 0 : 1);
+}
+int kfp16_net_set_input_device(kfp16_net* n, const char* input_name, const void* dev, int rows, int cols) {
+  if (!n || !input_name || !dev) { set_error("kfp16_net_set_input_device: null argument"); return -1; }
+  return set_input_common(n, input_name, dev, rows, cols);
+}
+int kfp16_net_set_input(kfp16_net* n, const char* input_name, const uint16_t* host, int rows, int cols) {
+  if (!n || !input_name || !host) { set_error("kfp16_net_set_input: null argument"); return -1; }
+  const size_t bytes = (size_t)rows * cols * 2;
+  if (bytes > n->stage_bytes) { set_error("kfp16_net_set_input: [%d x %d] exceeds the staging buffer", rows, cols); return -1; }
+  // the staging buffer is reused by the next call: keep the copy and the scatter ordered on the stream
+  if (!check_cuda(cudaMemcpyAsync(n->stage_in, host, bytes, cudaMemcpyHostToDevice, n->ctx->stream), "input upload")) return -1;
+  if (set_input_common(n, input_name, n->stage_in, rows, cols)) return -1;
+  return check_cuda(cudaStreamSynchronize(n->ctx->stream), "input sync") ? 0 : -1;
+}
+
+int kfp16_net_forward(kfp16_net* n) {
+  if (!n) { set_error("kfp16_net_forward: null network"); return -1; }
+  for (auto& l : n->layers)
+    if (forward_layer(n, l)) return -1;
+  return 0;
+}
+
+static int read_dense(kfp16_net* n, const Layer& l, const Buf& b, uint16_t* host, int rows, int cols) {
+  const int want_rows = l.per_seq ? n->opts.n_seq : n->T;
+  if (!b.p) { set_error("layer %s: buffer not allocated (train = 0 or no gradient path)", l.name.c_str()); return -1; }
+  if (rows != want_rows || cols != b.cols) { set_error("layer %s is [%d x %d], got [%d x %d]", l.name.c_str(), want_rows, b.cols, rows, cols); return -1; }
+  const size_t bytes = (size_t)rows * cols * 2;
+  if (l.per_seq) {
+    if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "sync")) return -1;
+    return check_cuda(cudaMemcpy(host, b.p, bytes, cudaMemcpyDeviceToHost), "download") ? 0 : -1;
+  }
+  if (bytes > n->stage_bytes) { set_error("layer %s: output exceeds the staging buffer", l.name.c_str()); return -1; }
+  if (kfp16_unpack_rows(n->ctx, b.p, b.cols, 0, n->stage_in, n->opts.n_seq, n->opts.seq_len, n->halo, cols)) return -1;
+  if (!check_cuda(cudaMemcpyAsync(host, n->stage_in, bytes, cudaMemcpyDeviceToHost, n->ctx->stream), "download")) return -1;
+  return check_cuda(cudaStreamSynchronize(n->ctx->stream), "download sync") ? 0 : -1;
+}
+int kfp16_net_get_output(kfp16_net* n, const char* layer, uint16_t* host, int rows, int cols) {
+  if (!n || !layer || !host) { set_error("kfp16_net_get_output: null argument"); return -1; }
+  const int i = (layer[0] == 0) ? n->out_layer : find_layer(n, layer);
+  if (i < 0) { set_error("kfp16_net_get_output: no layer %s", layer); return -1; }
+  return read_dense(n, n->layers[i], n->layers[i].out, host, rows, cols);
+}
+int kfp16_net_get_grad(kfp16_net* n, const char* layer, uint16_t* host, int rows, int cols) {
+  if (!n || !layer || !host) { set_error("kfp16_net_get_grad: null argument"); return -1; }
+  const int i = (layer[0] == 0) ? n->out_layer : find_layer(n, layer);
+  if (i < 0) { set_error("kfp16_net_get_grad: no layer %s", layer); return -1; }
+  return read_dense(n, n->layers[i], n->layers[i].dout, host, rows, cols);
+}
+
+// ReLU mask of a tdnnf / prefinal layer as one byte per element, dense real rows (tests: lets the
+// oracle's backward use the same masks, so that only rounding-level differences remain)
+int kfp16_net_get_mask(kfp16_net* n, const char* layer, uint8_t* host, int rows, int cols) {
+  if (!n || !layer || !host) { set_error("kfp16_net_get_mask: null argument"); return -1; }
+  const int i = find_layer(n, layer);
+  if (i < 0 || !n->layers[i].mask) { set_error("kfp16_net_get_mask: layer %s has no ReLU mask", layer); return -1; }
+  const Layer& l = n->layers[i];
+  const int dim = l.type == L_PREFINAL ? l.big_dim : l.out_dim;
+  const int prow = l.per_seq ? n->opts.n_seq : n->Tp;
+  const int want_rows = l.per_seq ? n->opts.n_seq : n->T;
+  if (rows != want_rows || cols != dim) { set_error("kfp16_net_get_mask: %s mask is [%d x %d]", layer, want_rows, dim); return -1; }
+  std::vector<uint32_t> words((size_t)prow * l.mask_ld);
+  if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "sync")) return -1;
+  if (!check_cuda(cudaMemcpy(words.data(), l.mask, words.size() * 4, cudaMemcpyDeviceToHost), "mask download")) return -1;
+  for (int r = 0; r < rows; ++r) {
+    const int pr = l.per_seq ? r : (r / n->opts.seq_len) * n->blk + n->halo + (r % n->opts.seq_len);
+    for (int c = 0; c < cols; ++c) host[(size_t)r * cols + c] = (words[(size_t)pr * l.mask_ld + (c >> 5)] >> (c & 31)) & 1u;
+  }
+  return 0;
+}
+
+int kfp16_net_zero_grads(kfp16_net* n) {
+  if (!n || !n->g32) { set_error("kfp16_net_zero_grads: network was created with train = 0"); return -1; }
+  return check_cuda(cudaMemsetAsync(n->g32, 0, n->bucket * sizeof(float), n->ctx->stream), "zero grads") ? 0 : -1;
+}
+
+int kfp16_net_loss_half_sq(kfp16_net* n, const char* layer) {
+  if (!n) { set_error("kfp16_net_loss_half_sq: null network"); return -1; }
+  const int i = (!layer || layer[0] == 0) ? n->out_layer : find_layer(n, layer);
+  if (i < 0) { set_error("kfp16_net_loss_half_sq: no such layer"); return -1; }
+  Layer& l = n->layers[i];
+  if (!l.dout.p) { set_error("kfp16_net_loss_half_sq: layer %s has no gradient buffer (train = 0?)", l.name.c_str()); return -1; }
+  if (l.per_seq) return kfp16_half_sq_loss(n->ctx, l.out.p, l.dout.p, n->opts.n_seq, 1, 0, l.out_dim, n->loss_dev);
+  return kfp16_half_sq_loss(n->ctx, l.out.p, l.dout.p, n->opts.n_seq, n->opts.seq_len, n->halo, l.out_dim, n->loss_dev);
+}
+
+int kfp16_net_set_output_grad(kfp16_net* n, const char* layer, const uint16_t* host, int rows, int cols) {
+  if (!n || !host) { set_error("kfp16_net_set_output_grad: null argument"); return -1; }
+  const int i = (!layer || layer[0] == 0) ? n->out_layer : find_layer(n, layer);
+  if (i < 0) { set_error("kfp16_net_set_output_grad: no such layer"); return -1; }
+  Layer& l = n->layers[i];
+  if (!l.dout.p) { set_error("kfp16_net_set_output_grad: layer %s has no gradient buffer", l.name.c_str()); return -1; }
+  const int want_rows = l.per_seq ? n->opts.n_seq : n->T;
+  if (rows != want_rows || cols != l.out_dim) { set_error("kfp16_net_set_output_grad: shape mismatch"); return -1; }
+  const size_t bytes = (size_t)rows * cols * 2;
+  if (bytes > n->stage_bytes) { set_error("kfp16_net_set_output_grad: exceeds the staging buffer"); return -1; }
+  if (!check_cuda(cudaMemcpyAsync(n->stage_in, host, bytes, cudaMemcpyHostToDevice, n->ctx->stream), "grad upload")) return -1;
+  int rc;
+  if (l.per_seq) rc = check_cuda(cudaMemcpyAsync(l.dout.p, n->stage_in, bytes, cudaMemcpyDeviceToDevice, n->ctx->stream), "grad copy") ? 0 : -1;
+  else rc = kfp16_pack_rows(n->ctx, n->stage_in, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, n->halo, cols, 0);
+  if (rc) return -1;
+  return check_cuda(cudaStreamSynchronize(n->ctx->stream), "grad sync") ? 0 : -1;
+}
+
+int kfp16_net_backward(kfp16_net* n) {
+  if (!n || !n->g32) { set_error("kfp16_net_backward: network was created with train = 0"); return -1; }
+  for (auto& l : n->layers) l.grads_seen = 0;
+  n->layers[n->out_layer].grads_seen = 1;
+  for (int i = (int)n->layers.size() - 1; i >= 0; --i) {
+    Layer& l = n->layers[i];
+    if (!l.needs_grad || l.type == L_INPUT) continue;
+    if (l.grads_seen == 0) continue;   // nothing flowed into this layer
+    if (backward_layer(n, l)) return -1;
+  }
+  return 0;
+}
+
+int kfp16_net_sgd_step(kfp16_net* n, float grad_scale, int round_grad) {
+  if (!n || !n->g32) { set_error("kfp16_net_sgd_step: network was created with train = 0"); return -1; }
+  return kfp16_sgd_update_flat(n->ctx, n->w32, n->w16, n->g32, 1, round_grad, grad_scale, n->vel, n->opts.lr, n->opts.momentum, n->bucket);
+}
+int kfp16_net_set_lr(kfp16_net* n, float lr) {
+  if (!n) return -1;
+  if (n->graph[2] || n->graph[3]) { set_error("kfp16_net_set_lr: the SGD step is captured in a CUDA graph; re-capture after changing lr"); return -1; }
+  n->opts.lr = lr;
+  return 0;
+}
+int kfp16_net_read_loss(kfp16_net* n, float* loss) {
+  if (!n || !loss) { set_error("kfp16_net_read_loss: null argument"); return -1; }
+  if (!check_cuda(cudaMemcpyAsync(loss, n->loss_dev, 4, cudaMemcpyDeviceToHost, n->ctx->stream), "loss download")) return -1;
+  if (!check_cuda(cudaMemsetAsync(n->loss_dev, 0, 4, n->ctx->stream), "loss reset")) return -1;
+  return check_cuda(cudaStreamSynchronize(n->ctx->stream), "loss sync") ? 0 : -1;
+}
+
+int kfp16_net_capture(kfp16_net* n, int phases) {
+  if (!n || phases < 1 || phases > 3) { set_error("kfp16_net_capture: phases must be 1, 2 or 3"); return -1; }
+  if (!n->ctx->stream) { set_error("kfp16_net_capture: graph capture needs a non-default stream (kfp16_ctx_set_stream)"); return -1; }
+  // one eager pass first: sets kernel attributes (dynamic smem opt-in) outside the capture
+  if (run_phases(n, phases)) return -1;
+  if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "pre-capture sync")) return -1;
+  const unsigned long long before = kfp16_launch_count();
+  if (!check_cuda(cudaStreamBeginCapture(n->ctx->stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) return -1;
+  const int rc = run_phases(n, phases);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(n->ctx->stream, &g);
+  if (rc) { if (g) cudaGraphDestroy(g); return -1; }
+  if (!check_cuda(e, "cudaStreamEndCapture")) return -1;
+  if (n->graph[phases]) cudaGraphExecDestroy(n->graph[phases]);
+  const bool ok = check_cuda(cudaGraphInstantiate(&n->graph[phases], g, 0), "cudaGraphInstantiate");
+  cudaGraphDestroy(g);
+  n->graph_launches[phases] = (int)(kfp16_launch_count() - before);
+  return ok ? 0 : -1;
+}
+int kfp16_net_launch(kfp16_net* n, int phases) {
+  if (!n || phases < 1 || phases > 3 || !n->graph[phases]) { set_error("kfp16_net_launch: phases %d not captured", phases); return -1; }
+  if (!check_cuda(cudaGraphLaunch(n->graph[phases], n->ctx->stream), "cudaGraphLaunch")) return -1;
+  count_launch(n->graph_launches[phases]);
+  return 0;
+}
+int kfp16_net_launches_per_step(const kfp16_net* n, int phases) {
+  return (n && phases >= 1 && phases <= 3) ? n->graph_launches[phases] : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+"""Network-level parity on the GPU: the native executor (kaldi_fp16_b200.nnet over the C ABI) against
+the numpy oracle (oracle/nnet_oracle.py) on the reference's own acceptance nets
+(cmd/sgdtest/main.go:199-203, cmd/traintest/main.go:37-42, cmd/backtest/main.go:219-227)
+and on a spliced TDNN-F stack.  Tolerances: activations max-rel-err-vs-scale <= 2e-3,
+gradients <= 5e-3 of the tensor's max-abs, SGD'd weights <= 1e-3."""
+import numpy as np
+import pytest
+
+from kaldi_fp16_b200 import gpu, nnet
+from oracle import kaldi_oracle as O
+from oracle.nnet_oracle import OracleNet
+
+pytestmark = pytest.mark.gpu
+
+SGDTEST = """
+input name=input dim=40
+linear-component name=linear1 dim=128
+batchnorm-component name=bn1
+prefinal-layer name=prefinal small-dim=64 big-dim=128
+output-layer name=output dim=40 include-log-softmax=false
+"""
+TRAINTEST = """
+input name=input dim=40
+linear-component name=linear1 dim=128
+batchnorm-component name=bn1
+tdnnf-layer name=tdnnf1 dim=128 bottleneck-dim=64 time-stride=0 bypass-scale=0.66
+prefinal-layer name=prefinal small-dim=64 big-dim=128
+output-layer name=output dim=40 include-log-softmax=false
+"""
+BACKTEST = """
+input name=input dim=40
+input name=ivector dim=32
+idct-layer name=idct input=input dim=40
+linear-component name=linear1 input=Append(idct, ivector) dim=128
+batchnorm-component name=bn1
+tdnnf-layer name=tdnnf1 dim=128 bottleneck-dim=64 time-stride=0 bypass-scale=0.66
+tdnnf-layer name=tdnnf2 dim=128 bottleneck-dim=64 time-stride=0 bypass-scale=0.66
+prefinal-layer name=prefinal input=tdnnf2 small-dim=64 big-dim=128
+output-layer name=output dim=40 include-log-softmax=false
+"""
+SPLICED = """
+input name=input dim=64
+linear-component name=lin0 dim=256
+tdnnf-layer name=tdnnf1 dim=256 bottleneck-dim=64 time-stride=3 bypass-scale=0.66
+tdnnf-layer name=tdnnf2 dim=256 bottleneck-dim=64 time-stride=3 bypass-scale=0.66
+tdnnf-layer name=tdnnf3 dim=256 bottleneck-dim=64 time-stride=1 bypass-scale=0.66
+linear-component name=prefinal-l dim=64
+prefinal-layer name=prefinal-chain input=prefinal-l big-dim=256 small-dim=64
+output-layer name=output include-log-softmax=false dim=104
+prefinal-layer name=prefinal-xent input=prefinal-l big-dim=256 small-dim=64
+output-layer name=output-xent dim=104
+"""
+IVECTOR = """
+input dim=16 name=ivector
+input dim=40 name=input
+idct-layer name=idct input=input dim=40 cepstral-lifter=22
+linear-component name=ivector-linear dim=24 input=ReplaceIndex(ivector, t, 0)
+batchnorm-component name=ivector-batchnorm target-rms=0.025
+batchnorm-component name=idct-batchnorm input=idct
+combine-feature-maps-layer name=combine_inputs input=Append(idct-batchnorm, ivector-batchnorm) num-filters1=5 num-filters2=3 height=8
+linear-component name=lin1 dim=128
+tdnnf-layer name=tdnnf1 dim=128 bottleneck-dim=32 time-stride=2 bypass-scale=0.66
+output-layer name=output include-log-softmax=true dim=48
+"""
+
+
+def make_pair(handle, xconfig, n_seq, L, seed, randomize_bn=True, **kw):
+    # ref_round: keep the reference's FP16 store between fused epilogue stages, so that the ReLU
+    # masks (whose flips change a gradient element by its full value) agree with the op-by-op oracle
+    kw.setdefault("ref_round", True)
+    rng = np.random.default_rng(seed)
+    on = OracleNet(xconfig, n_seq, L)
+    on.init_random(rng)
+    for k in on.params:
+        if k.endswith("Bias"):
+            on.params[k] = O.to_f16_trunc((rng.standard_normal(on.params[k].shape) * 0.1).astype(np.float32))
+    net = nnet.NewNetwork(nnet.BuildModelFromString(xconfig), handle, n_seq, L, **kw)
+    assert set(net.params) == set(on.params), (sorted(net.params), sorted(on.params))
+    for k, w in on.params.items():
+        net.SetParam(k, w)
+    if randomize_bn:
+        for (layer, which), bn in on.bn.items():
+            d = bn["mean"].size
+            bn["mean"] = (rng.standard_normal(d) * 0.1).astype(np.float32)
+            bn["var"] = (rng.random(d) + 0.5).astype(np.float32)
+            if not (which == "" and float(on.by_name[layer].kv.get("target-rms", 1.0)) != 1.0):
+                bn["gamma"] = (rng.random(d) + 0.5).astype(np.float32)
+                bn["beta"] = (rng.standard_normal(d) * 0.1).astype(np.float32)
+            net.SetBN(layer, which, bn["mean"], bn["var"], bn["gamma"], bn["beta"], bn["eps"])
+    return on, net, rng
+
+
+def rel_to_scale(got, want):
+    return O.max_err_vs_scale(got, want)
+
+
+def check_forward_backward(on, net, inputs, per_seq=(), act_tol=2e-3, grad_tol=5e-3, check_layers=None):
+    acts = on.forward(inputs)
+    net.MarkPerSequence(*per_seq)
+    for name, x in inputs.items():
+        net.SetInput(name, x)
+    assert net.lib.kfp16_net_forward(net.ptr) == 0
+    for l in on.layers:
+        if l.type == "input" or (check_layers and l.name not in check_layers):
+            continue
+        got = net.Output(l.name)
+        err = rel_to_scale(got, acts[l.name])
+        assert err <= act_tol, f"forward {l.name}: err {err:.2e} > {act_tol}"
+    # backward with dOut = out
+    out = acts["output"]
+    # ReLU masks: must agree with the oracle's except where a pre-activation is within rounding of
+    # zero (< 0.5 % of elements); the gradient comparison then uses the kernel's masks
+    masks = {}
+    for l in on.layers:
+        if l.type in ("tdnnf-layer", "prefinal-layer") and l.name in on.saved and "mask" in on.saved[l.name]:
+            want = on.saved[l.name]["mask"]
+            got = net.Mask(l.name, want.shape[1])
+            assert np.mean(got != want) < 5e-3, f"relu mask {l.name}: {np.mean(got != want):.2%} differ"
+            masks[l.name] = got
+    wg, dact = on.backward("output", out, masks)
+    net.ZeroGrads()
+    net.Backward(None)
+    loss = net.ReadLoss()
+    want_loss = 0.5 * float((out.astype(np.float64) ** 2).sum())
+    assert abs(loss - want_loss) <= 2e-3 * max(want_loss, 1e-6), (loss, want_loss)
+    got_wg = net.WeightGrads()
+    for k, g in wg.items():
+        err = rel_to_scale(got_wg[k], g)
+        # bias gradients are short, cancellation-heavy column sums: the reference's own gate (1e-2,
+        # cmd/sgdtest/main.go:71) is the bound there
+        tol = 1e-2 if k.endswith("Bias") else grad_tol
+        assert err <= tol, f"weight grad {k}: err {err:.2e} > {tol}"
+    # parameters without a gradient path (xent branch) stay zero (network_backward.go:104-107)
+    for k in got_wg:
+        if k not in wg:
+            assert not got_wg[k].any(), f"{k} should receive no gradient"
+    return acts, wg, dact
+
+
+@pytest.mark.parametrize("xconfig,name", [(SGDTEST, "sgdtest"), (TRAINTEST, "traintest")])
+def test_acceptance_nets_forward_backward(handle, xconfig, name):
+    on, net, rng = make_pair(handle, xconfig, 1, 32, seed=hash(name) % 1000)
+    x = O.to_f16_rne((rng.random((32, 40)) * 2 - 1).astype(np.float32))     # rand.Float32()*2-1
+    check_forward_backward(on, net, {"input": x})
+    net.Free()
+
+
+def test_backtest_net_with_append(handle):
+    """cmd/backtest/main.go:217-293: Append(idct, ivector) with a [T x 32] ivector; every layer gets gradients"""
+    on, net, rng = make_pair(handle, BACKTEST, 1, 32, seed=5)
+    x = O.to_f16_rne((rng.random((32, 40)) * 2 - 1).astype(np.float32))
+    iv = O.to_f16_rne((rng.random((32, 32)) * 2 - 1).astype(np.float32))
+    acts, wg, dact = check_forward_backward(on, net, {"input": x, "ivector": iv})
+    for k in ("linear1.W", "tdnnf1.LinearW", "tdnnf2.AffineW", "prefinal.BigW", "output.W"):
+        assert np.abs(net.WeightGrads()[k]).max() > 0
+    net.Free()
+
+
+@pytest.mark.parametrize("n_seq,L", [(1, 96), (4, 50), (3, 41)])
+def test_spliced_tdnnf_stack(handle, n_seq, L):
+    """time-stride > 0: splice as TMA row offsets over the padded layout, per-sequence clamp
+    (n_seq=1 is the reference's whole-minibatch clamp, forward.go:714-722,760-770)"""
+    on, net, rng = make_pair(handle, SPLICED, n_seq, L, seed=n_seq * 100 + L)
+    x = O.to_f16_rne(rng.standard_normal((n_seq * L, 64)).astype(np.float32))
+    acts, wg, dact = check_forward_backward(on, net, {"input": x})
+    # activation gradients too
+    for lname in ("tdnnf2", "tdnnf1", "lin0"):
+        err = rel_to_scale(net.Grad(lname), dact[lname])
+        assert err <= 5e-3, f"dact {lname}: {err:.2e}"
+    net.Free()
+
+
+def test_ivector_branch_and_combine(handle):
+    """ReplaceIndex(ivector,t,0) -> per-sequence branch broadcast into Append + combine-feature-maps"""
+    n_seq, L = 3, 20
+    on, net, rng = make_pair(handle, IVECTOR, n_seq, L, seed=77)
+    x = O.to_f16_rne((rng.standard_normal((n_seq * L, 40)) * 3).astype(np.float32))
+    iv = O.to_f16_rne(rng.standard_normal((n_seq, 16)).astype(np.float32))
+    check_forward_backward(on, net, {"input": x, "ivector": iv}, per_seq=("ivector", "ivector-linear", "ivector-batchnorm"))
+    net.Free()
+
+
+def test_ref_round_mode_is_bit_closer(handle):
+    """EPI_REF_ROUND keeps the reference's FP16 store between fused stages: with it the fused TDNN-F
+    output equals the op-by-op oracle to <= 1 fp16 ulp almost everywhere"""
+    on, net, rng = make_pair(handle, TRAINTEST, 1, 64, seed=9, ref_round=True)
+    x = O.to_f16_rne((rng.random((64, 40)) * 2 - 1).astype(np.float32))
+    acts = on.forward({"input": x})
+    net.SetInput("input", x)
+    assert net.lib.kfp16_net_forward(net.ptr) == 0
+    got, want = net.Output("tdnnf1"), acts["tdnnf1"]
+    ulp = np.abs(got - want) / np.maximum(np.abs(want) * 2.0 ** -10, 2.0 ** -24)
+    assert np.mean(ulp <= 1.01) > 0.995                       # bypass add can cancel: bound the rest by scale
+    assert O.max_err_vs_scale(got, want) <= 1e-3
+    net.Free()
+
+
+def test_sgd_step_matches_oracle_and_loss_decreases(handle):
+    """cmd/sgdtest/main.go:196-321 + cmd/traintest/main.go:34-162: lr 1e-3, momentum 0.9, loss
+    0.5*||out||^2, dY = Y; first-step weights match the oracle; loss[last] < loss[0]"""
+    on, net, rng = make_pair(handle, TRAINTEST, 1, 32, seed=12, randomize_bn=False, lr=1e-3, momentum=0.9)
+    x = O.to_f16_rne((rng.random((32, 40)) * 2 - 1).astype(np.float32))
+    trainer = nnet.Trainer(net)
+    state = {}
+    losses, olosses = [], []
+    for step in range(20):
+        acts = on.forward({"input": x})
+        out = acts["output"]
+        olosses.append(0.5 * float((out.astype(np.float64) ** 2).sum()))
+        wg, _ = on.backward("output", out)
+        on.sgd(state, wg, 1e-3, 0.9)
+        losses.append(trainer.Step(x))
+        if step == 0:
+            for k in on.params:
+                err = rel_to_scale(net.GetParam(k), on.params[k])
+                assert err <= 1e-3, f"after 1 step {k}: {err:.2e}"
+    assert losses[-1] < losses[0], losses
+    assert abs(losses[0] - olosses[0]) <= 2e-3 * olosses[0]
+    assert abs(losses[-1] - olosses[-1]) <= 0.05 * olosses[0]
+    # Trainer.SetLR + weights non-zero (traintest/main.go:145-160)
+    trainer.SetLR(5e-4)
+    assert all(np.abs(w).max() > 0 for k, w in net.MasterWeights().items() if not k.endswith("Bias"))
+    net.Free()
+
+
+def test_graph_replay_equals_eager(handle, lib):
+    """the captured CUDA graph of zero_grads+forward+loss+backward+SGD reproduces the eager step"""
+    from kaldi_fp16_b200 import cudart
+    st = cudart.Stream()
+    lib.kfp16_ctx_set_stream(handle.ptr, st.ptr)
+    try:
+        on, net, rng = make_pair(handle, SPLICED, 2, 40, seed=4, lr=1e-3, momentum=0.9)
+        x = O.to_f16_rne(rng.standard_normal((80, 64)).astype(np.float32))
+        net.SetInput("input", x)
+        w0 = {k: net.GetParam(k) for k in net.params}
+        trainer = nnet.Trainer(net)
+        l_eager = trainer.Step(x)
+        w_eager = {k: net.GetParam(k) for k in net.params}
+        for k, w in w0.items():
+            net.SetParam(k, w)
+        net.Capture(3)           # runs one eager pass + the capture pass: reset weights again
+        for k, w in w0.items():
+            net.SetParam(k, w)
+        net.ReadLoss()
+        net.Launch(3)
+        st.synchronize()
+        l_graph = net.ReadLoss()
+        assert abs(l_graph - l_eager) <= 1e-4 * abs(l_eager)
+        for k in w0:
+            assert rel_to_scale(net.GetParam(k), w_eager[k]) <= 1e-3, k
+        assert lib.kfp16_net_launches_per_step(net.ptr, 3) > 10
+        net.Free()
+    finally:
+        lib.kfp16_ctx_set_stream(handle.ptr, None)
+        st.destroy()
+
+
+def test_xconfig_errors(handle, lib):
+    """unsupported / malformed models fail loudly with a message (no silent fallback)"""
+    for bad, frag in [("input name=input dim=40\nattention-relu-batchnorm-layer name=a num-heads=2", b"out of scope"),
+                      ("input name=input dim=40\nlinear-component name=l", b"missing dim"),
+                      ("input name=input dim=40\nlinear-component name=l dim=64 input=nope", b"not found"),
+                      ("input name=input dim=40\ntdnnf-layer name=t dim=100 bottleneck-dim=20 time-stride=3", b"multiple")]:
+        with pytest.raises(nnet.NNetError) as e:
+            nnet.NewNetwork(nnet.BuildModelFromString(bad), handle, 1, 8)
+        assert frag.decode() in str(e.value), str(e.value)
