@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the FP16 fwd+bwd(+SGD) step on B200, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one minibatch (64 sequences x 150 frames per GPU) through zero-grads, forward,
+0.5*||out||^2 objective (dY = Y, cmd/sgdtest/main.go:258-267), backward, gradient all-reduce
+(N > 1) and the momentum-SGD update.  `value` is whole-job frames/s with the inputs resident in
+HBM; `e2e` is the same step through the public host-buffer API (pinned host features -> H2D every
+step, loss read back every step).  One JSON line is printed by rank 0.
+
+--impl reference times the reference's own CPU engine (go/gotorch restated in C, oracle/
+gotorch_port.c -- there is no Go toolchain here) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_SEQ, SEQ_LEN = 64, 150
+GRAD_SCALE = 1.0 / (N_SEQ * SEQ_LEN)   # objective averaged over the frames of one GPU's minibatch
+LR = 1e-4
+
+
+def tdnnf_stack_xconfig(layers=16, dim=1536, bott=160, stride=3):
+    lines = [f"input name=input dim={dim}"]
+    for i in range(layers):
+        lines.append(f"tdnnf-layer name=tdnnf{i + 1} dim={dim} bottleneck-dim={bott} time-stride={stride} bypass-scale=0.66")
+    return "\n".join(lines) + "\n"
+
+
+def cnn_tdnn_xconfig(pdfs=6016):
+    """SURVEY Appendix D.2 (Kaldi cnn_tdnn_1a family in the reference's xconfig vocabulary)"""
+    l = ["input dim=100 name=ivector", "input dim=40 name=input",
+         "idct-layer name=idct input=input dim=40 cepstral-lifter=22",
+         "linear-component name=ivector-linear dim=200 input=ReplaceIndex(ivector, t, 0)",
+         "batchnorm-component name=ivector-batchnorm target-rms=0.025",
+         "batchnorm-component name=idct-batchnorm input=idct",
+         "combine-feature-maps-layer name=combine_inputs input=Append(idct-batchnorm, ivector-batchnorm) num-filters1=1 num-filters2=5 height=40"]
+    conv = [("cnn1", 40, 40, 1, 64), ("cnn2", 40, 40, 1, 64), ("cnn3", 40, 20, 2, 128), ("cnn4", 20, 20, 1, 128),
+            ("cnn5", 20, 10, 2, 256), ("cnn6", 10, 10, 1, 256)]
+    for name, hin, hout, sub, f in conv:
+        l.append(f"conv-relu-batchnorm-layer name={name} height-in={hin} height-out={hout} height-subsample-out={sub} "
+                 f"time-offsets=-1,0,1 height-offsets=-1,0,1 num-filters-out={f}")
+    l.append("tdnnf-layer name=tdnnf7 dim=1536 bottleneck-dim=256 time-stride=0")
+    for i in range(8, 19):
+        l.append(f"tdnnf-layer name=tdnnf{i} dim=1536 bottleneck-dim=160 time-stride=3")
+    l += ["linear-component name=prefinal-l dim=256",
+          "prefinal-layer name=prefinal-chain input=prefinal-l big-dim=1536 small-dim=256",
+          f"output-layer name=output include-log-softmax=false dim={pdfs}",
+          "prefinal-layer name=prefinal-xent input=prefinal-l big-dim=1536 small-dim=256",
+          f"output-layer name=output-xent dim={pdfs}"]
+    return "\n".join(l) + "\n"
+
+
+WORKLOADS = {
+    "tdnnf_stack": dict(xconfig=tdnnf_stack_xconfig, feat_dim=1536, ivec_dim=0,
+                        desc="TDNN-F stack 16 x (1536 hidden, 160 bottleneck, stride 3, bypass 0.66) fwd+bwd+SGD, 64 seqs x 150 frames per GPU (BASELINE configs[1])"),
+    "cnn_tdnn": dict(xconfig=cnn_tdnn_xconfig, feat_dim=40, ivec_dim=100,
+                     desc="full CNN-TDNN (6 conv + 12 TDNN-F + prefinal + 6016-pdf output) fwd+bwd+SGD, 64 seqs x 150 frames per GPU (BASELINE configs[2])"),
+}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the bench runs"""
+
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.marks = []
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def mark(self):
+        self.marks.append(time.time())
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = []
+        for line in Path(self.f.name).read_text().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                ts = time.mktime(time.strptime(parts[0].split(".")[0], "%Y/%m/%d %H:%M:%S")) + float("0." + parts[0].split(".")[1])
+                rows.append((ts, float(parts[2]), float(parts[3]), float(parts[4]), parts[5:9]))
+            except (ValueError, IndexError):
+                continue
+        os.unlink(self.f.name)
+        sel = rows
+        if len(self.marks) >= 2:
+            inside = [r for r in rows if self.marks[0] - 0.05 <= r[0] <= self.marks[-1] + 0.05]
+            if len(inside) >= 1:
+                sel = inside
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in sel for i in range(4) if r[4][i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median([r[1] for r in sel])), "sm_max_mhz": sel[0][2],
+                "power_w_max": max(r[3] for r in sel), "samples": len(sel), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def load_port():
+    so = ROOT / "oracle" / "_build" / "libgotorch_port.so"
+    if not so.exists():
+        subprocess.run(["make", "-C", str(ROOT / "oracle"), "port"], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    lib.gt_bench_tdnnf_stack.restype = C.c_double
+    lib.gt_bench_tdnnf_stack.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_double)]
+    return lib
+
+
+def cpu_sample(lib, frames: int) -> float:
+    """one fwd+bwd of the 16-layer TDNN-F stack on `frames` frames of one sequence; returns seconds"""
+    cs = C.c_double()
+    return lib.gt_bench_tdnnf_stack(16, 1536, 160, 3, 1, frames, 1, C.byref(cs))
+
+
+def cpu_baseline(budget_s: float = 12.0):
+    lib = load_port()
+    t_small = cpu_sample(lib, 4)
+    frames = int(max(4, min(SEQ_LEN, 4 * budget_s / max(t_small, 1e-3))))
+    t = cpu_sample(lib, frames)
+    return {"value": frames / t, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"TDNN-F stack (16 layers) fwd+bwd on 1 sequence x {frames} frames, float64, gotorch TDNNLayer loops "
+                      f"(single goroutine in the reference; host has {os.cpu_count()} cores), {t:.1f} s"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    lib = load_port()
+    per_step = max(1.0, min(6.0, 150.0 / max(1, args.steps + args.warmup)))
+    t_small = cpu_sample(lib, 4)
+    frames = int(max(4, min(SEQ_LEN, 4 * per_step / max(t_small, 1e-3))))
+    for _ in range(args.warmup):
+        cpu_sample(lib, frames)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample(lib, frames)
+    dt = time.perf_counter() - t0
+    val = frames * args.steps / dt
+    sample = (f"TDNN-F stack (16 layers) fwd+bwd, 1 sequence x {frames} frames per step, float64 gotorch TDNNLayer loops; "
+              f"reference CPU engine restated in C (no Go toolchain), single goroutine as in go/gotorch/layers.go:444-524; "
+              f"host has {os.cpu_count()} cores")
+    print(json.dumps({
+        "impl": "reference", "metric": "CNN-TDNN fwd+bwd frames/sec", "value": val, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload]["desc"], "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("KFP16_WORKLOAD", "tdnnf_stack"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    from kaldi_fp16_b200 import _lib, cudart, gpu, nnet
+    lib = _lib.load()          # raises if the CUDA library is missing: there is no fallback
+    dist = torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    gpu.Init(local)
+    handle = gpu.NewHandle()
+    if world > 1:
+        tstream = torch.cuda.Stream(device=local)
+        stream_ptr = tstream.cuda_stream
+    else:
+        tstream = None
+        st = cudart.Stream()
+        stream_ptr = st.ptr
+    lib.kfp16_ctx_set_stream(handle.ptr, stream_ptr)
+
+    wl = WORKLOADS[args.workload]
+    net = nnet.NewNetwork(nnet.BuildModelFromString(wl["xconfig"]()), handle, N_SEQ, SEQ_LEN, train=True, lr=LR,
+                          momentum=0.9, ref_round=False, seed=42, grad_scale=GRAD_SCALE)
+    T, fd, ivd = N_SEQ * SEQ_LEN, wl["feat_dim"], wl["ivec_dim"]
+    rng = np.random.default_rng(1234 + rank)
+    if args.workload == "cnn_tdnn":   # MFCC-like columns
+        feats = rng.standard_normal((T, fd)).astype(np.float32) * (10.0 * 0.9 ** np.arange(fd, dtype=np.float32))
+        feats[:, 0] = np.clip(60 + 20 * rng.standard_normal(T), -20, 105)
+    else:
+        feats = rng.standard_normal((T, fd)).astype(np.float32)
+    feat_bits = nnet.rne_fp16_bits(feats)
+    ivec_bits = nnet.rne_fp16_bits(np.clip(rng.standard_normal((N_SEQ, max(ivd, 1))), -3, 3).astype(np.float32)) if ivd else None
+
+    # inputs resident in HBM (device-timed leg) and in pinned host memory (e2e leg)
+    d_feat = gpu.TensorFromBits(feat_bits)
+    d_ivec = gpu.TensorFromBits(ivec_bits) if ivd else None
+    h_feat_ptr = lib.bridge_host_alloc(feat_bits.nbytes)
+    C.memmove(h_feat_ptr, feat_bits.ctypes.data, feat_bits.nbytes)
+    h_ivec_ptr = None
+    if ivd:
+        h_ivec_ptr = lib.bridge_host_alloc(ivec_bits.nbytes)
+        C.memmove(h_ivec_ptr, ivec_bits.ctypes.data, ivec_bits.nbytes)
+
+    def set_inputs_device():
+        assert lib.kfp16_net_set_input_device(net.ptr, b"input", d_feat.Ptr, T, fd) == 0, _lib.last_error()
+        if ivd:
+            assert lib.kfp16_net_set_input_device(net.ptr, b"ivector", d_ivec.Ptr, N_SEQ, ivd) == 0, _lib.last_error()
+
+    def set_inputs_host():
+        assert lib.kfp16_net_set_input(net.ptr, b"input", h_feat_ptr, T, fd) == 0, _lib.last_error()
+        if ivd:
+            assert lib.kfp16_net_set_input(net.ptr, b"ivector", h_ivec_ptr, N_SEQ, ivd) == 0, _lib.last_error()
+
+    set_inputs_device()
+    net.Capture(1)
+    net.Capture(2)
+    grads_t = None
+    if world > 1:
+        grads_t = torch.as_tensor(net.grads_as_cuda_array(), device=f"cuda:{local}")
+
+    def allreduce():
+        if world > 1:
+            with torch.cuda.stream(tstream):
+                dist.all_reduce(grads_t)     # sum: N-GPU step == 1-GPU step on the concatenated batch
+
+    def step_device():
+        set_inputs_device()
+        net.Launch(1)
+        allreduce()
+        net.Launch(2)
+
+    def sync_all():
+        cudart.synchronize()
+        if world > 1:
+            dist.barrier()
+            cudart.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.kfp16_launch_count()
+    e0, e1 = cudart.Event(), cudart.Event()
+    if sampler:
+        sampler.mark()
+    e0.record(stream_ptr)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream_ptr)
+    e1.synchronize()
+    sync_all()
+    if sampler:
+        sampler.mark()
+    ms = e0.elapsed_ms(e1)
+    launches = lib.kfp16_launch_count() - launches0
+    if world > 1:
+        t_ms = torch.tensor([ms], device=f"cuda:{local}")
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        ms = float(t_ms.item())
+    frames_per_step = T * world
+    value = frames_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end leg: pinned host buffers in, loss out, every step
+    e2e_steps = max(3, min(args.steps, 100))
+    net.ReadLoss()
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record(stream_ptr)
+    last_loss = 0.0
+    for _ in range(e2e_steps):
+        set_inputs_host()
+        net.Launch(1)
+        allreduce()
+        net.Launch(2)
+        last_loss = net.ReadLoss()
+    e1.record(stream_ptr)
+    e1.synchronize()
+    sync_all()
+    e2e_ms = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    if world > 1:
+        t_ms = torch.tensor([e2e_ms], device=f"cuda:{local}")
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t_ms.item())
+    e2e_value = frames_per_step * e2e_steps / (e2e_ms * 1e-3)
+    h2d = feat_bits.nbytes + (ivec_bits.nbytes if ivd else 0)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- roofline leg: CUDA-event pair around every GEMM launch, eager replay of the same step
+    lib.kfp16_ctx_set_profile(handle.ptr, 1)
+    ev0, ev1 = cudart.Event(), cudart.Event()
+    ev0.record(stream_ptr)
+    for _ in range(args.profile_steps):
+        set_inputs_device()
+        net.ZeroGrads()
+        assert lib.kfp16_net_forward(net.ptr) == 0
+        net.Backward(None)
+        allreduce()
+        net.SGDStep(GRAD_SCALE)
+    ev1.record(stream_ptr)
+    ev1.synchronize()
+    n_l, g_ms, g_fl = C.c_int(), C.c_double(), C.c_double()
+    lib.kfp16_ctx_profile_read(handle.ptr, C.byref(n_l), C.byref(g_ms), C.byref(g_fl))
+    lib.kfp16_ctx_set_profile(handle.ptr, 0)
+    burst, sustained, hbm, src = peaks()
+    achieved = g_fl.value / max(g_ms.value, 1e-9) / 1e9   # TFLOP/s
+    flops_fwd = lib.kfp16_net_flops_forward(net.ptr)
+    step_flops_real = g_fl.value / max(args.profile_steps, 1)
+
+    if rank == 0:
+        out = {
+            "metric": "CNN-TDNN fwd+bwd frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": wl["desc"], "frames_per_gpu_step": T, "global_frames_per_step": frames_per_step,
+                       "parallelism": f"dp{world}", "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush",
+                       "loss": "0.5*||out||^2, dY=Y", "optimizer": f"momentum SGD on FP32 masters, lr {LR}, m 0.9, grads scaled by 1/frames"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "last_loss": last_loss},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "kfp16::gemm_f16_sm100 (all tile variants)",
+                         "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src}); burst {burst}",
+                         "frac_of_burst": achieved / burst, "traffic": None,
+                         "launches_per_step": n_l.value // max(args.profile_steps, 1),
+                         "gemm_ms_per_step": g_ms.value / max(args.profile_steps, 1),
+                         "gemm_share_of_step": (g_ms.value / max(args.profile_steps, 1)) / (ms / args.steps),
+                         "flops_per_step_launched": step_flops_real, "flops_forward_real_rows": flops_fwd},
+            "step_tflops": step_flops_real / (ms / args.steps) / 1e9,
+            "step_frac_of_sustained_peak": step_flops_real / (ms / args.steps) / 1e9 / sustained,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline()
+            except Exception as e:  # noqa: BLE001 - the GPU number must still be reported
+                out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(out), flush=True)
+    net.Free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

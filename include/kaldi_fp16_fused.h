@@ -30,6 +30,10 @@ void *kfp16_ctx_get_stream(kfp16_ctx *ctx);
 int kfp16_ctx_num_sms(kfp16_ctx *ctx);
 /* cap the persistent grid (0 = all SMs); used by tests to exercise multi-tile-per-CTA paths */
 int kfp16_ctx_set_max_ctas(kfp16_ctx *ctx, int max_ctas);
+/* profile mode: a CUDA-event pair is recorded around every GEMM launch made through this context;
+ * profile_read waits for the stream, returns launches / summed kernel ms / summed 2*M*N*K and resets */
+int kfp16_ctx_set_profile(kfp16_ctx *ctx, int on);
+int kfp16_ctx_profile_read(kfp16_ctx *ctx, int *launches, double *total_ms, double *total_flops);
 /* stream used by the context-free reference entry points (ops_relu, ...); NULL = default */
 void kfp16_set_default_stream(void *cuda_stream);
 /* number of kernels this library has launched in the calling process (bench "gpu_launches") */

@@ -35,6 +35,8 @@ typedef struct {
     float lr;       /* SGDOptimizer.LR       (internal/gpu/optimize.go:30-38) */
     float momentum; /* SGDOptimizer.Momentum */
     int conv_cartesian; /* 1: time x height offsets as Cartesian product (Kaldi); 0: paired (quirk Q4) */
+    float grad_scale;   /* captured SGD phase: g *= grad_scale (0 = 1.0), e.g. 1/frames or 1/(N*frames) */
+    int round_grad;     /* captured SGD phase: round g to fp16 first (the reference's FP16 gradient tensors) */
 } kfp16_net_opts;
 
 /* xconfig: the reference's model description (internal/nnet/xconfig.go:143); returns NULL on error */

@@ -47,7 +47,8 @@ class NetOpts(C.Structure):
     """struct kfp16_net_opts (include/kaldi_fp16_nnet.h)."""
 
     _fields_ = [("n_seq", c_int), ("seq_len", c_int), ("ref_round", c_int), ("train", c_int),
-                ("lr", c_float), ("momentum", c_float), ("conv_cartesian", c_int)]
+                ("lr", c_float), ("momentum", c_float), ("conv_cartesian", c_int),
+                ("grad_scale", c_float), ("round_grad", c_int)]
 
 
 class GPUBatchPtrs(C.Structure):
@@ -77,6 +78,8 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_ctx_get_stream": (c_void_p, [c_void_p]),
     "kfp16_ctx_num_sms": (c_int, [c_void_p]),
     "kfp16_ctx_set_max_ctas": (c_int, [c_void_p, c_int]),
+    "kfp16_ctx_set_profile": (c_int, [c_void_p, c_int]),
+    "kfp16_ctx_profile_read": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "kfp16_set_default_stream": (None, [c_void_p]),
     "kfp16_launch_count": (c_u64, []),
     "kfp16_last_error": (C.c_char_p, []),

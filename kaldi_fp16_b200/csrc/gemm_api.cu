@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/kaldi_fp16_fused.h"
@@ -184,6 +185,32 @@ int kfp16_ctx_set_stream(kfp16_ctx* ctx, void* s) { if (!ctx) return -1; ctx->st
 void* kfp16_ctx_get_stream(kfp16_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int kfp16_ctx_num_sms(kfp16_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
 int kfp16_ctx_set_max_ctas(kfp16_ctx* ctx, int n) { if (!ctx) return -1; ctx->max_ctas = n; return 0; }
+int kfp16_ctx_set_profile(kfp16_ctx* ctx, int on) {
+  if (!ctx) return -1;
+  ctx->profile = on != 0;
+  return 0;
+}
+int kfp16_ctx_profile_read(kfp16_ctx* ctx, int* launches, double* total_ms, double* total_flops) {
+  if (!ctx) { set_error("kfp16_ctx_profile_read: null context"); return -1; }
+  if (!check_cuda(cudaStreamSynchronize(ctx->stream), "profile sync")) return -1;
+  double ms = 0, fl = 0;
+  const int n = (int)ctx->prof_flops.size();
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]) == cudaSuccess) ms += t;
+    fl += ctx->prof_flops[i];
+    if (getenv("KFP16_PROFILE_DUMP")) fprintf(stderr, "[kfp16 gemm] %8.2f us %7.1f TF  %s\n", t * 1e3, ctx->prof_flops[i] / (t * 1e9), ctx->prof_desc[i].c_str());
+    cudaEventDestroy(ctx->prof_ev[2 * i]);
+    cudaEventDestroy(ctx->prof_ev[2 * i + 1]);
+  }
+  ctx->prof_ev.clear();
+  ctx->prof_flops.clear();
+  ctx->prof_desc.clear();
+  if (launches) *launches = n;
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  return 0;
+}
 void kfp16_set_default_stream(void* s) { g_default_stream = (cudaStream_t)s; }
 unsigned long long kfp16_launch_count(void) { return g_launches.load(); }
 const char* kfp16_last_error(void) { return get_error(); }
@@ -276,12 +303,27 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   const long long tiles = (long long)m_tiles * ((d->N + bn - 1) / bn) * groups * split_k;
   const int grid = (int)(tiles < ctas ? tiles : ctas);
   if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ctx->profile) {
+    if (!check_cuda(cudaEventCreate(&ev0), "cudaEventCreate") || !check_cuda(cudaEventCreate(&ev1), "cudaEventCreate")) return -1;
+    cudaEventRecord(ev0, ctx->stream);
+  }
   bool ok = false;
   switch (bn) {
     case 64: ok = launch_bn<64>(ctx, p, grid, a_mn, b_mn); break;
     case 128: ok = launch_bn<128>(ctx, p, grid, a_mn, b_mn); break;
     case 160: ok = launch_bn<160>(ctx, p, grid, a_mn, b_mn); break;
     case 256: ok = launch_bn<256>(ctx, p, grid, a_mn, b_mn); break;
+  }
+  if (ctx->profile) {
+    cudaEventRecord(ev1, ctx->stream);
+    ctx->prof_ev.push_back(ev0);
+    ctx->prof_ev.push_back(ev1);
+    ctx->prof_flops.push_back(2.0 * d->M * d->N * d->K * groups);
+    char desc[160];
+    snprintf(desc, sizeof(desc), "M=%d N=%d K=%d g=%d slabs=%d split=%d bn=%d A%s B%s flags=0x%x grid=%d", d->M, d->N, d->K,
+             groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, grid);
+    ctx->prof_desc.push_back(desc);
   }
   return ok ? 0 : -1;
 }

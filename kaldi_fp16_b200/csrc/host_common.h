@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -19,6 +20,11 @@ struct kfp16_ctx {
   // split-K workspace owned by the context (used when the caller passes none)
   float* ws = nullptr;
   size_t ws_bytes = 0;
+  // profile mode: a CUDA event pair around every GEMM launch (bench.py roofline leg)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;     // start/stop pairs
+  std::vector<double> prof_flops;       // per pair
+  std::vector<std::string> prof_desc;   // per pair: shape / tiling of the launch
 };
 
 namespace kfp16 {

@@ -919,7 +919,7 @@ int run_phases(kfp16_net* n, int phases) {
     if (kfp16_net_backward(n)) return -1;
   }
   if (phases & 2) {
-    if (kfp16_net_sgd_step(n, 1.0f, 1)) return -1;
+    if (kfp16_net_sgd_step(n, n->opts.grad_scale != 0.f ? n->opts.grad_scale : 1.0f, n->opts.round_grad)) return -1;
   }
   return 0;
 }

@@ -54,12 +54,13 @@ class Network:
     """forward.go:111 NewNetwork + Forward / Backward; owns the native executor."""
 
     def __init__(self, model: Model, handle: gpu.Handle, n_seq: int, seq_len: int, train: bool = True,
-                 lr: float = 1e-3, momentum: float = 0.9, ref_round: bool = False, seed: Optional[int] = 42):
+                 lr: float = 1e-3, momentum: float = 0.9, ref_round: bool = False, seed: Optional[int] = 42,
+                 grad_scale: float = 1.0, round_grad: bool = True):
         self.lib = _lib.load()
         self.handle = handle
         self.n_seq, self.seq_len = n_seq, seq_len
         opts = NetOpts(n_seq=n_seq, seq_len=seq_len, ref_round=int(ref_round), train=int(train), lr=lr,
-                       momentum=momentum, conv_cartesian=1)
+                       momentum=momentum, conv_cartesian=1, grad_scale=grad_scale, round_grad=int(round_grad))
         self.ptr = self.lib.kfp16_net_create(handle.ptr, model.xconfig.encode(), C.byref(opts))
         if not self.ptr:
             raise _err("NewNetwork")
