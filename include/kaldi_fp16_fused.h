@@ -95,6 +95,7 @@ typedef struct {
     float drop_p;
     uint32_t drop_seed;
     int force_bn; /* 0 = heuristic tile width; else 64/128/160/256 */
+    int force_generic; /* 1 = run the run-time-flag epilogue even when a specialised one exists (tests) */
 } kfp16_gemm_desc;
 
 /* returns 0 on success, -1 on error (message via kfp16_last_error / ops_last_error) */

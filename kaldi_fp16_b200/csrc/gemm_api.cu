@@ -83,28 +83,69 @@ static bool make_map_2d(CUtensorMap* m, const void* base, long long inner, long 
 }
 
 // ------------------------------------------------------------------ dispatch
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EK>
 static bool launch_cfg(kfp16_ctx* ctx, const GemmParams& p, int grid) {
-  using Cfg = GemmCfg<BN, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, A_MN, B_MN, EK>;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
-    if (!check_cuda(cudaFuncSetAttribute(gemm_f16_sm100<BN, A_MN, B_MN>,
+    if (!check_cuda(cudaFuncSetAttribute(gemm_f16_sm100<BN, A_MN, B_MN, EK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
                     "cudaFuncSetAttribute(gemm smem)"))
       return false;
     attr_done = true;
   }
-  gemm_f16_sm100<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmemBytes, ctx->stream>>>(p);
+  gemm_f16_sm100<BN, A_MN, B_MN, EK><<<grid, kGemmThreads, Cfg::kSmemBytes, ctx->stream>>>(p);
   count_launch();
   return check_launch("gemm_f16_sm100 launch");
 }
 
+// Which epilogue specialisations exist per operand-major combination (everything else runs the
+// run-time-flag EK_GENERIC body):
+//   A K-major,  B MN-major (forward NN)        : all kinds
+//   A K-major,  B K-major  (input gradients NT): plain, residual, bn+gradmask
+//   A MN-major, B MN-major (weight gradients)  : split-K, plain
+//   A MN-major, B K-major  (kaldi_gemm TT)     : generic only
 template <int BN>
-static bool launch_bn(kfp16_ctx* ctx, const GemmParams& p, int grid, bool a_mn, bool b_mn) {
-  if (!a_mn && !b_mn) return launch_cfg<BN, false, false>(ctx, p, grid);
-  if (!a_mn && b_mn) return launch_cfg<BN, false, true>(ctx, p, grid);
-  if (a_mn && !b_mn) return launch_cfg<BN, true, false>(ctx, p, grid);
-  return launch_cfg<BN, true, true>(ctx, p, grid);
+static bool launch_bn(kfp16_ctx* ctx, const GemmParams& p, int grid, bool a_mn, bool b_mn, int ek) {
+  if (!a_mn && b_mn) {
+    switch (ek) {
+      case EK_PLAIN: return launch_cfg<BN, false, true, EK_PLAIN>(ctx, p, grid);
+      case EK_AFFINE: return launch_cfg<BN, false, true, EK_AFFINE>(ctx, p, grid);
+      case EK_AFFINE_RES: return launch_cfg<BN, false, true, EK_AFFINE_RES>(ctx, p, grid);
+      case EK_RESID: return launch_cfg<BN, false, true, EK_RESID>(ctx, p, grid);
+      case EK_BN_GRADMASK: return launch_cfg<BN, false, true, EK_BN_GRADMASK>(ctx, p, grid);
+      case EK_BN: return launch_cfg<BN, false, true, EK_BN>(ctx, p, grid);
+      case EK_BIAS: return launch_cfg<BN, false, true, EK_BIAS>(ctx, p, grid);
+      case EK_SPLITK: return launch_cfg<BN, false, true, EK_SPLITK>(ctx, p, grid);
+      default: return launch_cfg<BN, false, true, EK_GENERIC>(ctx, p, grid);
+    }
+  }
+  if (!a_mn && !b_mn) {
+    switch (ek) {
+      case EK_PLAIN: return launch_cfg<BN, false, false, EK_PLAIN>(ctx, p, grid);
+      case EK_RESID: return launch_cfg<BN, false, false, EK_RESID>(ctx, p, grid);
+      case EK_BN_GRADMASK: return launch_cfg<BN, false, false, EK_BN_GRADMASK>(ctx, p, grid);
+      case EK_SPLITK: return launch_cfg<BN, false, false, EK_SPLITK>(ctx, p, grid);
+      default: return launch_cfg<BN, false, false, EK_GENERIC>(ctx, p, grid);
+    }
+  }
+  if (a_mn && b_mn) {
+    switch (ek) {
+      case EK_PLAIN: return launch_cfg<BN, true, true, EK_PLAIN>(ctx, p, grid);
+      case EK_SPLITK: return launch_cfg<BN, true, true, EK_SPLITK>(ctx, p, grid);
+      default: return launch_cfg<BN, true, true, EK_GENERIC>(ctx, p, grid);
+    }
+  }
+  if (ek == EK_SPLITK) return launch_cfg<BN, true, false, EK_SPLITK>(ctx, p, grid);
+  return launch_cfg<BN, true, false, EK_GENERIC>(ctx, p, grid);
+}
+
+// the specialised kind whose flag set equals `flags` exactly, else EK_GENERIC
+static int pick_kind(uint32_t flags) {
+  if (flags & EPI_SPLITK) return EK_SPLITK;
+  for (int k = EK_PLAIN; k < EK_SPLITK; ++k)
+    if (epi_kind_flags(k) == flags) return k;
+  return EK_GENERIC;
 }
 
 static int pick_bn(int N, int m_tiles, int groups, int split_k, int ctas) {
@@ -279,6 +320,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   p.mask_out = d->mask_out; p.mask_in = d->mask_in; p.mask_ld = d->mask_ld;
   p.ws_ld = d->ws_ld;
   p.drop_p = d->drop_p; p.drop_seed = d->drop_seed;
+  { static const int krot = getenv("KFP16_KROT") ? atoi(getenv("KFP16_KROT")) : 1; p.k_rot = krot; }
   if ((flags & EPI_BIAS) && !p.bias) { set_error("kfp16_gemm_ex: EPI_BIAS without bias"); return -1; }
   if ((flags & EPI_BN) && (!p.bn_scale || !p.bn_shift)) { set_error("kfp16_gemm_ex: EPI_BN without scale/shift"); return -1; }
   if ((flags & EPI_MASK) && !p.mask_out) { set_error("kfp16_gemm_ex: EPI_MASK without mask_out"); return -1; }
@@ -309,11 +351,12 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     cudaEventRecord(ev0, ctx->stream);
   }
   bool ok = false;
+  const int ek = d->force_generic ? ((flags & EPI_SPLITK) ? EK_SPLITK : EK_GENERIC) : pick_kind(flags);
   switch (bn) {
-    case 64: ok = launch_bn<64>(ctx, p, grid, a_mn, b_mn); break;
-    case 128: ok = launch_bn<128>(ctx, p, grid, a_mn, b_mn); break;
-    case 160: ok = launch_bn<160>(ctx, p, grid, a_mn, b_mn); break;
-    case 256: ok = launch_bn<256>(ctx, p, grid, a_mn, b_mn); break;
+    case 64: ok = launch_bn<64>(ctx, p, grid, a_mn, b_mn, ek); break;
+    case 128: ok = launch_bn<128>(ctx, p, grid, a_mn, b_mn, ek); break;
+    case 160: ok = launch_bn<160>(ctx, p, grid, a_mn, b_mn, ek); break;
+    case 256: ok = launch_bn<256>(ctx, p, grid, a_mn, b_mn, ek); break;
   }
   if (ctx->profile) {
     cudaEventRecord(ev1, ctx->stream);
@@ -321,8 +364,8 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     ctx->prof_ev.push_back(ev1);
     ctx->prof_flops.push_back(2.0 * d->M * d->N * d->K * groups);
     char desc[160];
-    snprintf(desc, sizeof(desc), "M=%d N=%d K=%d g=%d slabs=%d split=%d bn=%d A%s B%s flags=0x%x grid=%d", d->M, d->N, d->K,
-             groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, grid);
+    snprintf(desc, sizeof(desc), "M=%d N=%d K=%d g=%d slabs=%d split=%d bn=%d A%s B%s flags=0x%x ek=%d grid=%d", d->M, d->N, d->K,
+             groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, ek, grid);
     ctx->prof_desc.push_back(desc);
   }
   return ok ? 0 : -1;

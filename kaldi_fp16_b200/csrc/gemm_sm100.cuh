@@ -4,13 +4,20 @@
 // (/root/reference/cpp/cuda/ops.cu:366-400), and the transposes + extra GEMMs its Go
 // layer builds around it (internal/gpu/backward_ops.go:162-253, ops.go:335-351).
 //
-// One persistent CTA per SM, warp-specialised:
+// One persistent CTA per SM, 12 warps, warp-specialised:
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      MMA issuer     (one elected thread, tcgen05.mma kind::f16, M=128 x N=BN x K=16)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       (tcgen05.ld -> fused epilogue -> swizzled smem -> TMA store,
-//                               or fp32 red.add for split-K)
+//   warp 3      residual / C-in prefetcher (TMA loads of the R tile, two 64-column chunks ahead)
+//   warps 4..11 epilogue       (tcgen05.ld -> fused epilogue -> swizzled smem -> TMA store,
+//                               or fp32 red.add for split-K).  Warp w owns TMEM lanes
+//                               32*(w%4)..+31 and the 32-column half (w-4)/4 of each 64-column chunk.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// The epilogue is specialised at compile time (EpiKind) for the flag combinations the network
+// executor issues, so the hot variants are short straight-line code; every other combination
+// (reference rounding mode, dropout, cuBLAS beta, ...) runs the EK_GENERIC body with run-time flags.
+// Per-column vectors (bias, batch-norm scale/shift) are staged in shared memory once per tile.
 //
 // Operands may be K-major or MN-major (no transpose kernels: the UMMA descriptors take
 // X^T / W^T directly) and the K dimension may be made of up to 2 "slabs" whose TMA
@@ -24,13 +31,16 @@ namespace kfp16 {
 
 constexpr int kBM = 128;          // UMMA M (cta_group::1)
 constexpr int kBK = 64;           // one 128-byte swizzle row of K per stage
-constexpr int kGemmThreads = 256; // 8 warps
+constexpr int kEpiThreads = 256;  // 8 epilogue warps
+constexpr int kGemmThreads = 128 + kEpiThreads;
+constexpr int kChunkBytes = kBM * 64 * 2;   // [128 x 64] fp16 staging chunk, SW128
+constexpr int kVecBytes = 256 * (2 + 4 + 4);
 constexpr int kMaxGroups = 2;
 constexpr int kMaxSlabs = 2;
 
 enum EpiFlags : uint32_t {
   EPI_BIAS = 1u << 0,       // + bias[n] (fp16 bias row, as gpu.AddBias)
-  EPI_RELU = 1u << 1,       // max(x,0) keeping NaN / -0 like kernel_relu
+  EPI_RELU = 1u << 1,       // max(x,0) keeping NaN like kernel_relu
   EPI_BN = 1u << 2,         // x*bn_scale[n] + bn_shift[n]   (inference batch-norm)
   EPI_RESID = 1u << 3,      // out = res_scale*R + x         (TDNN-F bypass, ops_add_scaled)
   EPI_BETA = 1u << 4,       // acc = alpha*acc + beta*R      (cuBLAS beta path)
@@ -40,6 +50,32 @@ enum EpiFlags : uint32_t {
   EPI_DROPOUT = 1u << 8,    // inverted dropout, counter-based mask (seed,row,col)
   EPI_GRADMASK = 1u << 9,   // x = mask_in bit ? x : 0      (relu backward fused in producer)
 };
+
+// compile-time epilogue variants
+enum EpiKind : int {
+  EK_GENERIC = 0,      // run-time flags
+  EK_PLAIN,            // D = h(alpha*acc)
+  EK_AFFINE,           // bias, relu, bn, mask            (prefinal affine, tdnnf affine without bypass)
+  EK_AFFINE_RES,       // bias, relu, bn, mask, residual  (tdnnf affine with bypass)
+  EK_RESID,            // residual only                   (tdnnf input gradient + bypass gradient)
+  EK_BN_GRADMASK,      // bn scale, relu-backward mask    (prefinal backward)
+  EK_BN,               // bn only                         (prefinal linear)
+  EK_BIAS,             // bias only                       (output layer)
+  EK_SPLITK,           // fp32 accumulate into the workspace (weight gradients)
+  EK_COUNT
+};
+
+__host__ __device__ constexpr uint32_t epi_kind_flags(int k) {
+  return k == EK_PLAIN ? 0u
+       : k == EK_AFFINE ? (EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK)
+       : k == EK_AFFINE_RES ? (EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK | EPI_RESID)
+       : k == EK_RESID ? (uint32_t)EPI_RESID
+       : k == EK_BN_GRADMASK ? (EPI_BN | EPI_GRADMASK)
+       : k == EK_BN ? (uint32_t)EPI_BN
+       : k == EK_BIAS ? (uint32_t)EPI_BIAS
+       : k == EK_SPLITK ? (uint32_t)EPI_SPLITK
+       : 0u;
+}
 
 struct GemmParams {
   CUtensorMap tmA, tmB;
@@ -52,7 +88,7 @@ struct GemmParams {
   int b_row_off[kMaxGroups][kMaxSlabs], b_col_off[kMaxGroups][kMaxSlabs];
   uint32_t flags;
   float alpha, beta, res_scale;
-  const __half* bias;           // [N]   (group g uses bias + g*bias_gstride)
+  const __half* bias;           // [N]   (group g uses bias + g*vec_gstride)
   const float* bn_scale;        // [N]
   const float* bn_shift;        // [N]
   int vec_gstride;              // per-group offset into bias/bn vectors
@@ -62,9 +98,10 @@ struct GemmParams {
   float* ws[kMaxGroups];        // split-K fp32 accumulation target [M x ws_ld]
   int ws_ld;
   float drop_p; uint32_t drop_seed;
+  int k_rot;                    // 1: each tile starts its K loop at a different k-block (spreads L2 requests for shared operands)
 };
 
-// counter-based uniform in [0,1): shared by the CUDA epilogue and the CPU oracle (oracle/kaldi_oracle.c)
+// counter-based uniform in [0,1): shared by the CUDA epilogue and the CPU oracle (oracle/kaldi_oracle.py)
 __host__ __device__ inline float dropout_uniform(uint32_t seed, uint32_t row, uint32_t col) {
   uint32_t x = seed ^ (row * 0x9E3779B1u) ^ (col * 0x85EBCA77u);
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
@@ -79,68 +116,87 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
+// max(x, 0) that lets NaN through, like the reference's `x < 0 ? 0 : x` (ops.cu:26-37)
+__device__ __forceinline__ float relu_nan(float x) {
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;\n" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EK>
 struct GemmCfg {
+  static constexpr bool kSplitK = EK == EK_SPLITK;
+  static constexpr uint32_t kFlags = epi_kind_flags(EK);
+  static constexpr bool kMayUseR = EK == EK_GENERIC || (kFlags & (EPI_RESID | EPI_BETA)) != 0;
+  static constexpr bool kUsesVec = EK == EK_GENERIC || (kFlags & (EPI_BIAS | EPI_BN)) != 0;
+  // staging ring: 4 chunks when a residual tile is prefetched into it (in-place epilogue), else 2
+  static constexpr int kRing = kSplitK ? 0 : (kMayUseR ? 4 : 2);
+  static constexpr int kStoreWait = kRing >= 3 ? 1 : 0;        // TMA stores allowed in flight
   static constexpr int kAChunks = A_MN ? 2 : 1;                // 64-wide M chunks (MN-major)
   static constexpr int kBChunks = B_MN ? (BN + 63) / 64 : 1;   // 64-wide N chunks (MN-major)
   static constexpr int kABytes = kBM * kBK * 2;                // 16 KB
   static constexpr int kBBytes = B_MN ? kBChunks * 64 * kBK * 2 : BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBufBytes = kBM * 64 * 2;            // [128 x 64] fp16 staging, SW128
-  static constexpr int kNumEpiBufs = 2;
-  static constexpr int kSmemBudget = 227 * 1024 - 2048;        // barriers + alignment slack
-  static constexpr int kStagesRaw = (kSmemBudget - kNumEpiBufs * kEpiBufBytes) / kStageBytes;
+  static constexpr int kEpiBytes = kRing * kChunkBytes + (kUsesVec ? kVecBytes : 0);
+  static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + kNumEpiBufs * kEpiBufBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
   static_assert(kStages >= 2, "tile too large for shared memory");
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=128; epilogue works on 32-column halves");
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EK>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_sm100(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, A_MN, B_MN, EK>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kRing = Cfg::kRing;
+  constexpr bool kGeneric = EK == EK_GENERIC;
+  constexpr bool kSplitK = Cfg::kSplitK;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kNumEpiBufs * Cfg::kEpiBufBytes);
+  uint8_t* smem_vec = smem_epi + kRing * kChunkBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
   uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]        epilogue -> MMA
-  uint64_t* rfull_bar = tempty_bar + 2;       // [2]        residual TMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;       // [4]        residual TMA -> epilogue
+  uint64_t* rempty_bar = rfull_bar + 4;       // [4]        output store drained -> residual TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t flags = kGeneric ? p.flags : Cfg::kFlags;
+  const bool use_r = Cfg::kMayUseR && (flags & (EPI_RESID | EPI_BETA)) != 0;
 
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles_per_split = m_tiles * n_tiles * p.groups;
   const int total_tiles = tiles_per_split * p.split_k;
-  const int kb_total = p.kslabs * ((p.kslab_len + kBK - 1) / kBK);   // k-blocks over all slabs
   const int kb_per_slab = (p.kslab_len + kBK - 1) / kBK;
+  const int kb_total = p.kslabs * kb_per_slab;   // k-blocks over all slabs
   const int kb_per_split = (kb_total + p.split_k - 1) / p.split_k;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    if (!(p.flags & EPI_SPLITK)) tma_prefetch_desc(&p.tmD[0]);
+    if (!kSplitK) tma_prefetch_desc(&p.tmD[0]);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
-      mbar_init(&rfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], kEpiThreads / 32);   // one arrive per epilogue warp
     }
+    for (int i = 0; i < 4; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 1); }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -161,7 +217,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         const int ks = id / p.groups;
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const int nkb = kb1 - kb0;
+        const int rot = p.k_rot ? (m_blk + n_blk) % nkb : 0;
+        for (int i = 0; i < nkb; ++i) {
+          const int kb = kb0 + (i + rot < nkb ? i + rot : i + rot - nkb);
           const int slab = kb / kb_per_slab;
           const int k_in = (kb - slab * kb_per_slab) * kBK;
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -208,10 +267,13 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         const int ks = tile / tiles_per_split;
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
+        const int nkb = kb1 - kb0;
+        const int rot = p.k_rot ? ((tile % n_tiles) + (tile / n_tiles) % m_tiles) % nkb : 0;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int i = 0; i < nkb; ++i) {
+          const int kb = kb0 + (i + rot < nkb ? i + rot : i + rot - nkb);
           const int slab = kb / kb_per_slab;
           const int k_in = (kb - slab * kb_per_slab) * kBK;
           const int k16s = min(kBK, p.kslab_len - k_in + 15) >> 4;   // partial last block (K % 64)
@@ -223,7 +285,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, kLayoutSW128);
           for (int k = 0; k < k16s; ++k) {
             umma_f16(d_tmem, adesc + ((uint64_t)(k * a_kstep) >> 4),
-                     bdesc + ((uint64_t)(k * b_kstep) >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                     bdesc + ((uint64_t)(k * b_kstep) >> 4), idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -232,18 +294,35 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // =========================================== residual / C-in prefetch
+    if (Cfg::kMayUseR && lane == 0 && use_r) {
+      int k = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int id = tile;
+        const int n_blk = id % n_tiles; id /= n_tiles;
+        const int m_blk = id % m_tiles; id /= m_tiles;
+        const int g = id % p.groups;
+        for (int c64 = 0; c64 < BN; c64 += 64, ++k) {
+          const int buf = k & 3;
+          if (k >= 4) mbar_wait(&rempty_bar[buf], ((k >> 2) + 1) & 1);
+          mbar_arrive_expect_tx(&rfull_bar[buf], kChunkBytes);
+          tma_load_2d(smem_epi + buf * kChunkBytes, &p.tmR[g], &rfull_bar[buf], n_blk * BN + c64, m_blk * kBM);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ========================================================= epilogue
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int hsel = (warp - 4) >> 2;       // which 32-column half of a 64-column chunk
     const int row_in_tile = q * 32 + lane;
     const int epi_tid = threadIdx.x - 128;
-    const uint32_t flags = p.flags;
-    const bool use_r = (flags & (EPI_RESID | EPI_BETA)) != 0;
-    const bool ref_round = (flags & EPI_REF_ROUND) != 0;
+    const bool ref_round = kGeneric && (flags & EPI_REF_ROUND) != 0;
+    __half* s_bias = reinterpret_cast<__half*>(smem_vec);
+    float* s_scale = reinterpret_cast<float*>(smem_vec + 512);
+    float* s_shift = reinterpret_cast<float*>(smem_vec + 512 + 1024);
     int acc = 0; uint32_t acc_phase = 0;
-    uint32_t rphase = 0;   // bit b = phase of rfull_bar[b]
-    const bool plain = (flags & ~(uint32_t)EPI_REF_ROUND) == 0;
-    int chunk_ctr = 0;
+    int k = 0;   // running 64-column chunk counter (staging ring position)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int id = tile;
       const int n_blk = id % n_tiles; id /= n_tiles;
@@ -251,14 +330,31 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       const int g = id % p.groups;
       const int row = m_blk * kBM + row_in_tile;
       const int n0 = n_blk * BN;
+
+      if (Cfg::kUsesVec && (flags & (EPI_BIAS | EPI_BN))) {
+        // per-column vectors of this tile -> shared memory (every reader of the previous tile's
+        // vectors has passed that tile's last chunk barrier before anyone gets here)
+        if (epi_tid < BN) {
+          const int col = n0 + epi_tid;
+          const bool ok = col < p.N;
+          const int vi = g * p.vec_gstride + col;
+          if (flags & EPI_BIAS) s_bias[epi_tid] = ok ? p.bias[vi] : __float2half(0.f);
+          if (flags & EPI_BN) {
+            s_scale[epi_tid] = ok ? __ldg(p.bn_scale + vi) : 0.f;
+            s_shift[epi_tid] = ok ? __ldg(p.bn_shift + vi) : 0.f;
+          }
+        }
+        named_bar_sync(2, kEpiThreads);
+      }
+
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
 
-      if (flags & EPI_SPLITK) {
+      if constexpr (kSplitK) {
         float* ws_row = p.ws[g] + (size_t)row * p.ws_ld;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = hsel * 32; c < BN; c += 64) {
           uint32_t v[32];
           tmem_ld_32x32(t_acc + c, v);
           tmem_ld_wait();
@@ -277,144 +373,109 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
-
-      const int voff = g * p.vec_gstride;
+      } else {
 #pragma unroll 1
-      for (int c64 = 0; c64 < BN; c64 += 64, ++chunk_ctr) {
-        const int buf = chunk_ctr & 1;
-        uint8_t* sbuf = smem_epi + buf * Cfg::kEpiBufBytes;
-        uint8_t* srow = sbuf + row_in_tile * 128;
-        // the TMA store that last read this buffer (2 chunks ago) must have drained
-        if (epi_tid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        if (plain) {
-          // ---- fast path: D = h(alpha * acc).  Kept separate so the common case is a short,
-          // fully unrolled instruction stream (the all-flags body below must stay a compact
-          // loop: unrolled it overflows the instruction cache and stalls the epilogue warps).
-          constexpr int kHalves = (BN % 64 == 0) ? 2 : 1;     // BN=160: last chunk is 32 wide
-          const int nh = (c64 + 64 <= BN) ? 2 : kHalves;
-          uint32_t v0[32], v1[32];
-          tmem_ld_32x32(t_acc + c64, v0);
-          if (nh == 2) tmem_ld_32x32(t_acc + c64 + 32, v1);
-          tmem_ld_wait();
+        for (int c64 = 0; c64 < BN; c64 += 64, ++k) {
+          const int buf = k & (kRing - 1);
+          uint8_t* sbuf = smem_epi + buf * kChunkBytes;
+          uint8_t* srow = sbuf + row_in_tile * 128;
+          const int c = c64 + hsel * 32;          // first tile column of this thread's 32
+          if (use_r) mbar_wait(&rfull_bar[buf], (k >> 2) & 1);
+          if (c < BN) {
+            uint32_t v32[32];
+            if (!kGeneric) {
+              tmem_ld_32x32(t_acc + c, v32);
+              tmem_ld_wait();
+            }
+            uint32_t maskword = 0, gm_word = 0xFFFFFFFFu;
+            if (flags & EPI_GRADMASK)
+              gm_word = (row < p.M && n0 + c < p.N) ? __ldg(p.mask_in + (size_t)row * p.mask_ld + ((n0 + c) >> 5)) : 0u;
+#pragma unroll(kGeneric ? 1 : 4)
+            for (int j = 0; j < 4; ++j) {          // 8 columns = one 16-byte smem unit
+              const int ct = c + j * 8;            // column inside the tile
+              uint4* sptr = reinterpret_cast<uint4*>(srow + (((hsel * 4 + j) ^ (row_in_tile & 7)) << 4));
+              uint32_t v8[8];
+              if (kGeneric) {
+                tmem_ld_32x32_x8(t_acc + ct, v8);
+                tmem_ld_wait();
+              } else {
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            uint4 ov;
-            ov.x = pack_f16x2(__uint_as_float(v0[j8 * 8 + 0]) * p.alpha, __uint_as_float(v0[j8 * 8 + 1]) * p.alpha);
-            ov.y = pack_f16x2(__uint_as_float(v0[j8 * 8 + 2]) * p.alpha, __uint_as_float(v0[j8 * 8 + 3]) * p.alpha);
-            ov.z = pack_f16x2(__uint_as_float(v0[j8 * 8 + 4]) * p.alpha, __uint_as_float(v0[j8 * 8 + 5]) * p.alpha);
-            ov.w = pack_f16x2(__uint_as_float(v0[j8 * 8 + 6]) * p.alpha, __uint_as_float(v0[j8 * 8 + 7]) * p.alpha);
-            *reinterpret_cast<uint4*>(srow + ((j8 ^ (row_in_tile & 7)) << 4)) = ov;
-          }
-          if (nh == 2) {
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              uint4 ov;
-              ov.x = pack_f16x2(__uint_as_float(v1[j8 * 8 + 0]) * p.alpha, __uint_as_float(v1[j8 * 8 + 1]) * p.alpha);
-              ov.y = pack_f16x2(__uint_as_float(v1[j8 * 8 + 2]) * p.alpha, __uint_as_float(v1[j8 * 8 + 3]) * p.alpha);
-              ov.z = pack_f16x2(__uint_as_float(v1[j8 * 8 + 4]) * p.alpha, __uint_as_float(v1[j8 * 8 + 5]) * p.alpha);
-              ov.w = pack_f16x2(__uint_as_float(v1[j8 * 8 + 6]) * p.alpha, __uint_as_float(v1[j8 * 8 + 7]) * p.alpha);
-              *reinterpret_cast<uint4*>(srow + (((4 + j8) ^ (row_in_tile & 7)) << 4)) = ov;
-            }
-          }
-        } else {
-          if (use_r) {
-            if (epi_tid == 0) {
-              mbar_arrive_expect_tx(&rfull_bar[buf], Cfg::kEpiBufBytes);
-              tma_load_2d(sbuf, &p.tmR[g], &rfull_bar[buf], n0 + c64, m_blk * kBM);
-            }
-            mbar_wait(&rfull_bar[buf], (rphase >> buf) & 1u);
-            rphase ^= (1u << buf);
-          }
-          uint32_t maskword = 0, gm_word = 0xFFFFFFFFu;
-#pragma unroll 1
-          for (int g8 = 0; g8 < 8; ++g8) {          // 8 columns = one 16-byte smem chunk
-            const int c = c64 + g8 * 8;
-            if (c >= BN) break;
-            const int col = n0 + c;
-            const bool col_ok = (col + 8 <= p.N);
-            uint32_t v[8];
-            tmem_ld_32x32_x8(t_acc + c, v);
-            if ((flags & EPI_GRADMASK) && (g8 & 3) == 0)
-              gm_word = (row < p.M && col < p.N) ? __ldg(p.mask_in + (size_t)row * p.mask_ld + (col >> 5)) : 0u;
-            uint4* sptr = reinterpret_cast<uint4*>(srow + ((g8 ^ (row_in_tile & 7)) << 4));
-            float r[8], bia[8], bsc[8], bsh[8];
-            if (use_r) {
-              const uint4 rv = *sptr;
-              float2 f;
-              f = unpack_f16x2(rv.x); r[0] = f.x; r[1] = f.y;
-              f = unpack_f16x2(rv.y); r[2] = f.x; r[3] = f.y;
-              f = unpack_f16x2(rv.z); r[4] = f.x; r[5] = f.y;
-              f = unpack_f16x2(rv.w); r[6] = f.x; r[7] = f.y;
-            }
-            if (flags & EPI_BIAS) {
-              const uint4 bv = col_ok ? __ldg(reinterpret_cast<const uint4*>(p.bias + voff + col)) : make_uint4(0, 0, 0, 0);
-              float2 f;
-              f = unpack_f16x2(bv.x); bia[0] = f.x; bia[1] = f.y;
-              f = unpack_f16x2(bv.y); bia[2] = f.x; bia[3] = f.y;
-              f = unpack_f16x2(bv.z); bia[4] = f.x; bia[5] = f.y;
-              f = unpack_f16x2(bv.w); bia[6] = f.x; bia[7] = f.y;
-            }
-            if (flags & EPI_BN) {
-#pragma unroll
-              for (int e = 0; e < 8; e += 4) {
-                const float4 s4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bn_scale + voff + col + e)) : make_float4(0, 0, 0, 0);
-                const float4 h4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.bn_shift + voff + col + e)) : make_float4(0, 0, 0, 0);
-                bsc[e] = s4.x; bsc[e + 1] = s4.y; bsc[e + 2] = s4.z; bsc[e + 3] = s4.w;
-                bsh[e] = h4.x; bsh[e + 1] = h4.y; bsh[e + 2] = h4.z; bsh[e + 3] = h4.w;
+                for (int e = 0; e < 8; ++e) v8[e] = v32[j * 8 + e];
               }
-            }
-            tmem_ld_wait();
-            float xo[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int j = (g8 & 3) * 8 + e;          // bit inside the 32-column mask word
-              float x = __uint_as_float(v[e]) * p.alpha;
-              if (flags & EPI_BETA) x = fmaf(p.beta, r[e], x);
-              if (ref_round) x = __half2float(__float2half_rn(x));
+              float r[8], bia[8], bsc[8], bsh[8];
+              if (use_r) {
+                const uint4 rv = *sptr;
+                float2 f;
+                f = unpack_f16x2(rv.x); r[0] = f.x; r[1] = f.y;
+                f = unpack_f16x2(rv.y); r[2] = f.x; r[3] = f.y;
+                f = unpack_f16x2(rv.z); r[4] = f.x; r[5] = f.y;
+                f = unpack_f16x2(rv.w); r[6] = f.x; r[7] = f.y;
+              }
               if (flags & EPI_BIAS) {
-                x += bia[e];
-                if (ref_round) x = __half2float(__float2half_rn(x));
-              }
-              if (flags & EPI_RELU) {
-                x = (x < 0.0f) ? 0.0f : x;            // NaN and -0 pass through (ops.cu:26-37)
-                if (x > 0.0f) maskword |= (1u << j);
-              }
-              if (flags & EPI_DROPOUT) {
-                const float u = dropout_uniform(p.drop_seed, (uint32_t)row, (uint32_t)(col + e));
-                x = (u > p.drop_p) ? x * (1.0f / (1.0f - p.drop_p)) : 0.0f;
-                if (ref_round) x = __half2float(__float2half_rn(x));
+                const uint4 bv = *reinterpret_cast<const uint4*>(s_bias + ct);
+                float2 f;
+                f = unpack_f16x2(bv.x); bia[0] = f.x; bia[1] = f.y;
+                f = unpack_f16x2(bv.y); bia[2] = f.x; bia[3] = f.y;
+                f = unpack_f16x2(bv.z); bia[4] = f.x; bia[5] = f.y;
+                f = unpack_f16x2(bv.w); bia[6] = f.x; bia[7] = f.y;
               }
               if (flags & EPI_BN) {
-                x = fmaf(x, bsc[e], bsh[e]);
-                if (ref_round) x = __half2float(__float2half_rn(x));
+#pragma unroll
+                for (int e = 0; e < 8; e += 4) {
+                  const float4 s4 = *reinterpret_cast<const float4*>(s_scale + ct + e);
+                  const float4 h4 = *reinterpret_cast<const float4*>(s_shift + ct + e);
+                  bsc[e] = s4.x; bsc[e + 1] = s4.y; bsc[e + 2] = s4.z; bsc[e + 3] = s4.w;
+                  bsh[e] = h4.x; bsh[e + 1] = h4.y; bsh[e + 2] = h4.z; bsh[e + 3] = h4.w;
+                }
               }
-              if (flags & EPI_RESID) x = fmaf(p.res_scale, r[e], x);
-              if (flags & EPI_GRADMASK) x = ((gm_word >> j) & 1u) ? x : 0.0f;
-              xo[e] = x;
+              float xo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int bit = j * 8 + e;           // bit inside the 32-column mask word
+                float x = __uint_as_float(v8[e]) * p.alpha;
+                if (flags & EPI_BETA) x = fmaf(p.beta, r[e], round_h(x));   // cuBLAS rounds alpha*acc to fp16 first (measured)
+                if (ref_round) x = round_h(x);
+                if (flags & EPI_BIAS) {
+                  x += bia[e];
+                  if (ref_round) x = round_h(x);
+                }
+                if (flags & EPI_RELU) {
+                  x = relu_nan(x);
+                  if (x > 0.0f) maskword |= (1u << bit);
+                }
+                if (flags & EPI_DROPOUT) {
+                  const float u = dropout_uniform(p.drop_seed, (uint32_t)row, (uint32_t)(n0 + ct + e));
+                  x = (u > p.drop_p) ? x * (1.0f / (1.0f - p.drop_p)) : 0.0f;
+                  if (ref_round) x = round_h(x);
+                }
+                if (flags & EPI_BN) {
+                  x = fmaf(x, bsc[e], bsh[e]);
+                  if (ref_round) x = round_h(x);
+                }
+                if (flags & EPI_RESID) x = fmaf(p.res_scale, r[e], x);
+                if (flags & EPI_GRADMASK) x = ((gm_word >> bit) & 1u) ? x : 0.0f;
+                xo[e] = x;
+              }
+              uint4 ov;
+              ov.x = pack_f16x2(xo[0], xo[1]); ov.y = pack_f16x2(xo[2], xo[3]);
+              ov.z = pack_f16x2(xo[4], xo[5]); ov.w = pack_f16x2(xo[6], xo[7]);
+              *sptr = ov;
             }
-            uint4 ov;
-            ov.x = pack_f16x2(xo[0], xo[1]); ov.y = pack_f16x2(xo[2], xo[3]);
-            ov.z = pack_f16x2(xo[4], xo[5]); ov.w = pack_f16x2(xo[6], xo[7]);
-            *sptr = ov;
-            if ((g8 & 3) == 3) {
-              if ((flags & EPI_MASK) && row < p.M && (col & ~31) < p.N)
-                p.mask_out[(size_t)row * p.mask_ld + (col >> 5)] = maskword;
-              maskword = 0;
-            }
+            if ((flags & EPI_MASK) && row < p.M && n0 + c < p.N)
+              p.mask_out[(size_t)row * p.mask_ld + ((n0 + c) >> 5)] = maskword;
           }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (epi_tid == 0) {
-          tma_store_2d(&p.tmD[g], sbuf, n0 + c64, m_blk * kBM);
-          tma_store_commit();
+          fence_proxy_async_smem();
+          if (epi_tid == 0) {
+            // stores older than the newest kStoreWait have drained their smem reads: the buffer
+            // two chunks back is free again (for the next residual prefetch / next write)
+            tma_store_wait_read<Cfg::kStoreWait>();
+            if (use_r && k >= 2) mbar_arrive(&rempty_bar[(k - 2) & 3]);
+          }
+          named_bar_sync(1, kEpiThreads);
+          if (epi_tid == 0) {
+            tma_store_2d(&p.tmD[g], sbuf, n0 + c64, m_blk * kBM);
+            tma_store_commit();
+          }
         }
       }
       // all tcgen05.ld of this accumulator stage are complete -> hand it back to the MMA warp
@@ -423,7 +484,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (epi_tid == 0) tma_store_wait_all<0>();
+    if (!kSplitK && epi_tid == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

@@ -1,0 +1,76 @@
+"""Data-parallel plumbing for the training step: one process per GPU, sequences of the
+egs minibatch sharded across ranks, ONE exchange step per minibatch -- a sum all-reduce of the flat
+FP32 weight-gradient bucket -- then the identical SGD update on every rank.
+
+The reference has no multi-GPU path (single process, device 0: cpp/cuda/bridge.cu:38-47); this is
+where nnet.TrainStep (internal/nnet/train_step.go:142-283) is split: shard before TransferBatch,
+all-reduce between Backward (212) and the optimizer updates (221).
+
+torch.distributed is plumbing only (NCCL over NVLink on the GPU box, gloo in the CPU tests); the
+buffer that is reduced is the library's own gradient bucket (kfp16_net_grads_f32), in place.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class Shard:
+    rank: int
+    world: int
+    first_seq: int   # first sequence of the global minibatch owned by this rank
+    n_seq: int       # sequences owned by this rank
+
+    def rows(self, seq_len: int) -> slice:
+        """rows of the dense [n_seq_global*seq_len x dim] minibatch matrix owned by this rank
+        (sequences are contiguous row blocks: internal/batch merges examples back to back)"""
+        return slice(self.first_seq * seq_len, (self.first_seq + self.n_seq) * seq_len)
+
+    def seqs(self) -> slice:
+        return slice(self.first_seq, self.first_seq + self.n_seq)
+
+
+def shard_sequences(n_seq_global: int, world: int, rank: int) -> Shard:
+    """Sequences [r*B/N, (r+1)*B/N) go to rank r; a remainder is spread over the first ranks."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} / world {world}")
+    if n_seq_global < world:
+        raise ValueError(f"cannot shard {n_seq_global} sequences over {world} ranks")
+    base, rem = divmod(n_seq_global, world)
+    first = rank * base + min(rank, rem)
+    return Shard(rank, world, first, base + (1 if rank < rem else 0))
+
+
+def env_rank_world() -> tuple[int, int, int]:
+    """(rank, world, local_rank) from the torchrun environment (1 process per GPU)"""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+class GradAllReducer:
+    """Sum all-reduce of the flat gradient bucket (and of the scalar objective).
+
+    `bucket` is a torch tensor aliasing the bucket memory (CUDA tensor over kfp16_net_grads_f32 on
+    the GPU box, a CPU tensor under gloo).  Sum semantics: the N-rank step equals the 1-rank step on
+    the concatenated minibatch up to FP32 summation order (the reference does not scale gradients
+    by 1/B: internal/nnet/chain_loss.go:289-293 divides only the reported objective)."""
+
+    def __init__(self, bucket, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.bucket = bucket
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def all_reduce(self, async_op: bool = False):
+        if self.world == 1:
+            return None
+        return self.dist.all_reduce(self.bucket, op=self.dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+
+    def all_reduce_scalars(self, t):
+        """objective / frame-count exchange (3 floats in the chain objective, 1 for 0.5*||out||^2)"""
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t

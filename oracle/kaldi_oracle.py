@@ -124,7 +124,10 @@ def gemm(A: np.ndarray, B: np.ndarray, alpha: float = 1.0, beta: float = 0.0, C:
     acc = a @ b  # fp32 accumulate (summation order differs from cuBLAS: covered by the tolerance)
     out = f32(alpha) * acc
     if beta != 0.0:
-        out = out + f32(beta) * np.asarray(C, dtype=f32)
+        # measured on the reference library itself (tests/golden/ref_ops.npz, gemm2): with beta != 0
+        # cublasGemmEx returns h(h(alpha*acc) + beta*C) -- the product is rounded to FP16 before C is
+        # added (99.95% of elements bit-identical to this form, 71% to the single-rounding form).
+        out = h(out) + f32(beta) * np.asarray(C, dtype=f32)
     return h(out)
 
 
@@ -155,8 +158,9 @@ def tanh_act(x):
 
 
 def clipped_relu(x, ceiling):
-    """kernel_clipped_relu (ops.cu:59-68)"""
-    return h(np.maximum(f32(0), np.minimum(np.asarray(x, dtype=f32), f32(ceiling))))
+    """kernel_clipped_relu (ops.cu:59-68): fmaxf(0, fminf(x, ceiling)) -- fminf/fmaxf drop NaN, so
+    NaN -> ceiling (pinned by tests/golden/ref_ops.npz)"""
+    return h(np.fmax(f32(0), np.fmin(np.asarray(x, dtype=f32), f32(ceiling))))
 
 
 def softmax(x):
@@ -245,9 +249,11 @@ def sigmoid_backward(out, grad):
 
 
 def tanh_backward(out, grad):
-    """bw_tanh_backward_kernel (backward_wrappers.cu:63-73)"""
+    """bw_tanh_backward_kernel (backward_wrappers.cu:63-73): __hmul(g, __hsub(1, __hmul(o,o))); the
+    compiled reference contracts 1 - o*o into one HFMA (single rounding) -- pinned bit-for-bit by
+    tests/golden/ref_ops.npz"""
     o, g = np.asarray(out, f32), np.asarray(grad, f32)
-    return h(g * h(f32(1) - h(o * o)))
+    return h(g * h(f32(1) - o * o))
 
 
 def transpose(x):

@@ -1,0 +1,118 @@
+"""CPU tests of the drop-in boundary: the C-ABI shared library builds for sm_100a, loads without a
+GPU, exports every symbol include/*.h declares (and every reference symbol SURVEY 8b lists for the
+path), the ctypes binding table matches the headers, and entry points fail loudly -- never fall
+back to a CPU path -- when there is no CUDA device."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+INC = ROOT / "include"
+
+
+def declared_functions() -> dict:
+    """name -> header, for every function prototype in include/*.h"""
+    out = {}
+    for hdr in sorted(INC.glob("*.h")):
+        text = re.sub(r"/\*.*?\*/", "", hdr.read_text(), flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        text = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
+        text = re.sub(r"enum\s*\{.*?\}\s*;", "", text, flags=re.S)
+        for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b((?:kfp16|ops|bridge|kaldi|launch)_\w+)\s*\(", text):
+            out[m.group(2)] = hdr.name
+    return out
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from kaldi_fp16_b200 import build
+
+    return build.build(verbose=False)
+
+
+def test_headers_declare_the_reference_surface():
+    fns = declared_functions()
+    # the symbols internal/gpu binds (cpp/include/ops.h:16-188, bridge.h:12-60)
+    for name in ["ops_cublas_create", "ops_cublas_destroy", "ops_gemm", "ops_gemm_strided", "ops_relu", "ops_sigmoid",
+                 "ops_tanh_act", "ops_clipped_relu", "ops_softmax", "ops_log_softmax", "ops_batchnorm_forward",
+                 "ops_batchnorm_forward_rms", "ops_add_scaled", "ops_add", "ops_copy", "ops_fill", "ops_concat_cols",
+                 "ops_slice_cols", "ops_combine_feature_maps", "ops_subsample_rows", "ops_relu_backward",
+                 "ops_sigmoid_backward", "ops_tanh_backward", "ops_transpose", "ops_batchnorm_backward", "ops_fp16_to_fp32",
+                 "ops_sgd_update", "ops_last_error", "ops_clear_error", "bridge_gpu_init", "bridge_gpu_get_free_memory",
+                 "bridge_gpu_sync", "bridge_gpu_malloc", "bridge_gpu_free", "bridge_host_alloc", "bridge_host_free",
+                 "bridge_transfer_fp16", "bridge_transfer_int32", "bridge_transfer_float32", "bridge_read_fp16",
+                 "bridge_batch_alloc", "bridge_batch_transfer", "bridge_batch_free", "bridge_gpu_memset",
+                 "bridge_fp16_to_fp32_gpu", "bridge_fp32_to_fp16_gpu", "bridge_last_error", "bridge_clear_error"]:
+        assert name in fns, f"{name} (reference C ABI) is not declared in include/*.h"
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    fns = declared_functions()
+    assert len(fns) > 100
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(built_lib)], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in nm.splitlines() if " T " in line}
+    missing = sorted(n for n in fns if n not in exported)
+    assert not missing, f"declared in include/*.h but not exported by {built_lib.name}: {missing}"
+
+
+def test_binding_table_matches_headers(built_lib):
+    from kaldi_fp16_b200 import _lib
+
+    fns = declared_functions()
+    assert sorted(set(fns) - set(_lib.SIGNATURES)) == [], "header functions without a ctypes signature"
+    assert sorted(set(_lib.SIGNATURES) - set(fns)) == [], "ctypes signatures without a header declaration"
+    _lib.load()     # resolves every symbol; raises ImportError otherwise
+
+
+def test_struct_layouts_match_the_headers(built_lib):
+    """sizeof() of the ctypes mirrors == sizeof() the C compiler sees (a probe compiled with gcc)"""
+    from kaldi_fp16_b200 import _lib
+
+    src = ('#include <stdio.h>\n#include "kaldi_fp16_nnet.h"\n#include "kaldi_fp16_bridge.h"\n'
+           'int main(){printf("%zu %zu %zu %zu\\n", sizeof(kfp16_gemm_desc), sizeof(kfp16_mat), sizeof(kfp16_net_opts), sizeof(GPUBatchPtrs));return 0;}\n')
+    exe = Path("/tmp/kfp16_sizeof_probe")
+    subprocess.run(["gcc", "-x", "c", "-", f"-I{INC}", "-o", str(exe)], input=src, text=True, check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(_lib.GemmDesc), C.sizeof(_lib.KMat), C.sizeof(_lib.NetOpts), C.sizeof(_lib.GPUBatchPtrs)]
+
+
+def test_compiled_for_sm100a_with_tcgen05_and_tma(built_lib):
+    """the product library carries sm_100a SASS with UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld) and UTMALDG/UTMASTG (TMA)"""
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "gemm_f16_sm100", str(built_lib)], capture_output=True, text=True)
+    text = sass.stdout
+    if "UTCHMMA" not in text:      # -fun needs the mangled name on some toolkits: fall back to a full dump
+        text = subprocess.run(["cuobjdump", "-sass", str(built_lib)], capture_output=True, text=True).stdout
+    assert "sm_100a" in text
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
+        assert mnemonic in text, f"{mnemonic} not found in the SASS"
+    assert "HMMA.16816" not in text    # no legacy mma.sync path
+
+
+def test_fails_loudly_without_a_gpu(built_lib):
+    from kaldi_fp16_b200 import _lib
+    from tests.conftest import _have_gpu
+
+    if _have_gpu():
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    lib.ops_clear_error()
+    assert not lib.ops_cublas_create()                       # NULL, with a message -- no CPU fallback
+    assert lib.kfp16_last_error()
+    assert lib.bridge_gpu_init(0) != 0
+    assert not lib.kfp16_ctx_create(0)
+    opts = _lib.NetOpts(n_seq=1, seq_len=8, train=0)
+    assert not lib.kfp16_net_create(None, b"input name=input dim=8\n", C.byref(opts))
+    x = np.zeros(8, np.uint16)
+    assert lib.ops_gemm(None, 1, 8, 8, 1.0, x.ctypes.data, 8, x.ctypes.data, 8, 0.0, x.ctypes.data, 8) == -1
+
+
+def test_product_package_never_imports_the_oracle():
+    for py in (ROOT / "kaldi_fp16_b200").rglob("*.py"):
+        text = py.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, f"{py} imports the oracle"
+    for src in (ROOT / "kaldi_fp16_b200" / "csrc").iterdir():
+        assert "#include \"../../oracle" not in src.read_text() and "gotorch_port" not in src.read_text(), src
