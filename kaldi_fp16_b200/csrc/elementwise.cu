@@ -475,12 +475,19 @@ __global__ void fold_edges_kernel(__half* __restrict__ G, int ld, int n_seq, int
     Half8 z;
 #pragma unroll
     for (int j = 0; j < 4; ++j) z.v[j] = __float2half2_rn(0.f);
-    for (int k = 0; k < halo; ++k) {
-      Half8 h = ld8(G + (h0 + k) * ld + c);
-      const __half* hh = reinterpret_cast<const __half*>(&h);
+    for (int k0 = 0; k0 < halo; k0 += 4) {     // 4 independent row loads in flight per pass
+      Half8 h[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += __half2float(hh[j]);
-      st8(G + (h0 + k) * ld + c, z);
+      for (int k = 0; k < 4; ++k)
+        if (k0 + k < halo) h[k] = ld8(G + (h0 + k0 + k) * ld + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k0 + k < halo) {
+          const __half* hh = reinterpret_cast<const __half*>(&h[k]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += __half2float(hh[j]);
+          st8(G + (h0 + k0 + k) * ld + c, z);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) eh[j] = __float2half_rn(acc[j]);

@@ -11,8 +11,7 @@
 
 #include "../../include/kaldi_fp16_fused.h"
 #include "../../include/kaldi_fp16_ops.h"
-#include "gemm_sm100.cuh"
-#include "host_common.h"
+#include "gemm_launch.cuh"
 
 namespace kfp16 {
 
@@ -83,62 +82,12 @@ static bool make_map_2d(CUtensorMap* m, const void* base, long long inner, long 
 }
 
 // ------------------------------------------------------------------ dispatch
-template <int BN, bool A_MN, bool B_MN, int EK>
-static bool launch_cfg(kfp16_ctx* ctx, const GemmParams& p, int grid) {
-  using Cfg = GemmCfg<BN, A_MN, B_MN, EK>;
-  static bool attr_done = false;   // per instantiation
-  if (!attr_done) {
-    if (!check_cuda(cudaFuncSetAttribute(gemm_f16_sm100<BN, A_MN, B_MN, EK>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
-                    "cudaFuncSetAttribute(gemm smem)"))
-      return false;
-    attr_done = true;
-  }
-  gemm_f16_sm100<BN, A_MN, B_MN, EK><<<grid, kGemmThreads, Cfg::kSmemBytes, ctx->stream>>>(p);
-  count_launch();
-  return check_launch("gemm_f16_sm100 launch");
-}
-
-// Which epilogue specialisations exist per operand-major combination (everything else runs the
-// run-time-flag EK_GENERIC body):
-//   A K-major,  B MN-major (forward NN)        : all kinds
-//   A K-major,  B K-major  (input gradients NT): plain, residual, bn+gradmask
-//   A MN-major, B MN-major (weight gradients)  : split-K, plain
-//   A MN-major, B K-major  (kaldi_gemm TT)     : generic only
-template <int BN>
-static bool launch_bn(kfp16_ctx* ctx, const GemmParams& p, int grid, bool a_mn, bool b_mn, int ek) {
-  if (!a_mn && b_mn) {
-    switch (ek) {
-      case EK_PLAIN: return launch_cfg<BN, false, true, EK_PLAIN>(ctx, p, grid);
-      case EK_AFFINE: return launch_cfg<BN, false, true, EK_AFFINE>(ctx, p, grid);
-      case EK_AFFINE_RES: return launch_cfg<BN, false, true, EK_AFFINE_RES>(ctx, p, grid);
-      case EK_RESID: return launch_cfg<BN, false, true, EK_RESID>(ctx, p, grid);
-      case EK_BN_GRADMASK: return launch_cfg<BN, false, true, EK_BN_GRADMASK>(ctx, p, grid);
-      case EK_BN: return launch_cfg<BN, false, true, EK_BN>(ctx, p, grid);
-      case EK_BIAS: return launch_cfg<BN, false, true, EK_BIAS>(ctx, p, grid);
-      case EK_SPLITK: return launch_cfg<BN, false, true, EK_SPLITK>(ctx, p, grid);
-      default: return launch_cfg<BN, false, true, EK_GENERIC>(ctx, p, grid);
-    }
-  }
-  if (!a_mn && !b_mn) {
-    switch (ek) {
-      case EK_PLAIN: return launch_cfg<BN, false, false, EK_PLAIN>(ctx, p, grid);
-      case EK_RESID: return launch_cfg<BN, false, false, EK_RESID>(ctx, p, grid);
-      case EK_BN_GRADMASK: return launch_cfg<BN, false, false, EK_BN_GRADMASK>(ctx, p, grid);
-      case EK_SPLITK: return launch_cfg<BN, false, false, EK_SPLITK>(ctx, p, grid);
-      default: return launch_cfg<BN, false, false, EK_GENERIC>(ctx, p, grid);
-    }
-  }
-  if (a_mn && b_mn) {
-    switch (ek) {
-      case EK_PLAIN: return launch_cfg<BN, true, true, EK_PLAIN>(ctx, p, grid);
-      case EK_SPLITK: return launch_cfg<BN, true, true, EK_SPLITK>(ctx, p, grid);
-      default: return launch_cfg<BN, true, true, EK_GENERIC>(ctx, p, grid);
-    }
-  }
-  if (ek == EK_SPLITK) return launch_cfg<BN, true, false, EK_SPLITK>(ctx, p, grid);
-  return launch_cfg<BN, true, false, EK_GENERIC>(ctx, p, grid);
-}
+// one translation unit per tile width (gemm_bn*.cu)
+template <int BN> bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L);
+extern template bool launch_gemm_bn<64>(kfp16_ctx*, const GemmParams&, const GemmLaunch&);
+extern template bool launch_gemm_bn<128>(kfp16_ctx*, const GemmParams&, const GemmLaunch&);
+extern template bool launch_gemm_bn<160>(kfp16_ctx*, const GemmParams&, const GemmLaunch&);
+extern template bool launch_gemm_bn<256>(kfp16_ctx*, const GemmParams&, const GemmLaunch&);
 
 // the specialised kind whose flag set equals `flags` exactly, else EK_GENERIC
 static int pick_kind(uint32_t flags) {
@@ -280,20 +229,46 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.groups = groups; p.kslabs = kslabs; p.kslab_len = kslab_len;
 
-  const int m_tiles = (d->M + kBM - 1) / kBM;
-  const int kb_total = kslabs * ((kslab_len + kBK - 1) / kBK);
+  if (d->split_k > 1) flags |= EPI_SPLITK;   // caller asked for fp32 accumulation into ws
+  const int ek = d->force_generic ? ((flags & EPI_SPLITK) ? EK_SPLITK : EK_GENERIC) : pick_kind(flags);
+  const kfp16_mat& A = d->A; const kfp16_mat& B = d->B;
+  if (!A.ptr || !B.ptr) { set_error("kfp16_gemm_ex: null operand"); return -1; }
+
+  // ---- kernel shape: CTA pairs (cta_group::2, 256-row tiles: each CTA stages half of B) whenever the
+  // problem has at least two 128-row tiles, and ONE shared A tile for both splice slabs when the slabs
+  // are row-shifted views of the same columns (time splicing).  force_cg / KFP16_CG override (tests).
+  static const int env_cg = getenv("KFP16_CG") ? atoi(getenv("KFP16_CG")) : 0;
+  static const int env_share = getenv("KFP16_SHARE") ? atoi(getenv("KFP16_SHARE")) : 1;
+  p.mma_rep = getenv("KFP16_MMAREP") ? atoi(getenv("KFP16_MMAREP")) : 1;
+  int cg = d->force_cg ? d->force_cg : (env_cg ? env_cg : 2);
+  if (cg != 1 && cg != 2) { set_error("kfp16_gemm_ex: force_cg must be 0, 1 or 2"); return -1; }
+  if (d->M <= kBM) cg = 1;
+  bool share = false;
+  int span = 0, min_off = 0;
+  if (cg == 2 && kslabs == 2 && groups == 1 && !a_mn && !(flags & EPI_SPLITK) && env_share && !d->no_share &&
+      d->a_col_off[0][0] == d->a_col_off[0][1]) {
+    min_off = d->a_row_off[0][0] < d->a_row_off[0][1] ? d->a_row_off[0][0] : d->a_row_off[0][1];
+    span = d->a_row_off[0][0] + d->a_row_off[0][1] - 2 * min_off;
+    share = span <= 8 && gemm_variant_exists(a_mn, b_mn, ek, 2, true);
+  }
+  if (cg == 2 && !share && !gemm_variant_exists(a_mn, b_mn, ek, 2, false)) cg = 1;
+
+  const int tile_m = kBM * cg;
+  const int m_tiles = (d->M + tile_m - 1) / tile_m;
+  const int kb_total = (share ? 1 : kslabs) * ((kslab_len + kBK - 1) / kBK);
   int split_k = d->split_k > 1 ? d->split_k : 1;
   if (split_k > kb_total) split_k = kb_total;
   if (split_k > 1) {   // make every split non-empty
     const int per = (kb_total + split_k - 1) / split_k;
     split_k = (kb_total + per - 1) / per;
   }
-  if (d->split_k > 1) flags |= EPI_SPLITK;   // caller asked for fp32 accumulation into ws
   p.split_k = split_k;
 
   int ctas = ctx->num_sms;
   if (ctx->max_ctas > 0 && ctx->max_ctas < ctas) ctas = ctx->max_ctas;
-  int bn = d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, groups, split_k, ctas);
+  int units = ctas / cg;                 // CTAs or CTA pairs that can be resident
+  if (units < 1) { units = 1; }
+  int bn = d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, groups, split_k, units);
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) { set_error("kfp16_gemm_ex: unsupported tile width %d", bn); return -1; }
   if (!(flags & EPI_SPLITK) && (bn % 64) != 0 && d->N > bn) {
     // the last 64-wide store chunk of a 160-wide tile would spill into the next tile
@@ -301,17 +276,22 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   }
 
   // operand maps (halo rows are part of the mapped tensor so spliced reads can address them)
-  const kfp16_mat& A = d->A; const kfp16_mat& B = d->B;
-  if (!A.ptr || !B.ptr) { set_error("kfp16_gemm_ex: null operand"); return -1; }
   const __half* a_base = (const __half*)A.ptr - (long long)A.halo * A.ld;
   const __half* b_base = (const __half*)B.ptr - (long long)B.halo * B.ld;
-  if (!make_map_2d(&p.tmA, a_base, A.cols, (long long)A.rows + 2 * A.halo, A.ld, 64, a_mn ? 64 : kBM, "A")) return -1;
-  if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? 64 : bn, "B")) return -1;
+  const int a_box_rows = a_mn ? 64 : (share ? kBM + span : kBM);
+  if (!make_map_2d(&p.tmA, a_base, A.cols, (long long)A.rows + 2 * A.halo, A.ld, 64, a_box_rows, "A")) return -1;
+  if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? 64 : bn / cg, "B")) return -1;
   for (int g = 0; g < groups; ++g)
     for (int s = 0; s < kslabs; ++s) {
       p.a_row_off[g][s] = d->a_row_off[g][s] + A.halo; p.a_col_off[g][s] = d->a_col_off[g][s];
       p.b_row_off[g][s] = d->b_row_off[g][s] + B.halo; p.b_col_off[g][s] = d->b_col_off[g][s];
     }
+  if (share) {
+    p.a_shift[0] = d->a_row_off[0][0] - min_off;
+    p.a_shift[1] = d->a_row_off[0][1] - min_off;
+    p.a_row_off[0][0] = min_off + A.halo;       // the one A box starts at the earlier slab's row
+    p.a_box_bytes = a_box_rows * kBK * 2;
+  }
 
   p.flags = flags;
   p.alpha = d->alpha; p.beta = d->beta; p.res_scale = d->res_scale;
@@ -320,7 +300,6 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   p.mask_out = d->mask_out; p.mask_in = d->mask_in; p.mask_ld = d->mask_ld;
   p.ws_ld = d->ws_ld;
   p.drop_p = d->drop_p; p.drop_seed = d->drop_seed;
-  { static const int krot = getenv("KFP16_KROT") ? atoi(getenv("KFP16_KROT")) : 1; p.k_rot = krot; }
   if ((flags & EPI_BIAS) && !p.bias) { set_error("kfp16_gemm_ex: EPI_BIAS without bias"); return -1; }
   if ((flags & EPI_BN) && (!p.bn_scale || !p.bn_shift)) { set_error("kfp16_gemm_ex: EPI_BN without scale/shift"); return -1; }
   if ((flags & EPI_MASK) && !p.mask_out) { set_error("kfp16_gemm_ex: EPI_MASK without mask_out"); return -1; }
@@ -343,7 +322,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   }
 
   const long long tiles = (long long)m_tiles * ((d->N + bn - 1) / bn) * groups * split_k;
-  const int grid = (int)(tiles < ctas ? tiles : ctas);
+  const int grid = cg * (int)(tiles < units ? tiles : units);
   if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ctx->profile) {
@@ -351,12 +330,13 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     cudaEventRecord(ev0, ctx->stream);
   }
   bool ok = false;
-  const int ek = d->force_generic ? ((flags & EPI_SPLITK) ? EK_SPLITK : EK_GENERIC) : pick_kind(flags);
+  GemmLaunch L;
+  L.bn = bn; L.a_mn = a_mn; L.b_mn = b_mn; L.ek = ek; L.cg = cg; L.share = share; L.grid = grid;
   switch (bn) {
-    case 64: ok = launch_bn<64>(ctx, p, grid, a_mn, b_mn, ek); break;
-    case 128: ok = launch_bn<128>(ctx, p, grid, a_mn, b_mn, ek); break;
-    case 160: ok = launch_bn<160>(ctx, p, grid, a_mn, b_mn, ek); break;
-    case 256: ok = launch_bn<256>(ctx, p, grid, a_mn, b_mn, ek); break;
+    case 64: ok = launch_gemm_bn<64>(ctx, p, L); break;
+    case 128: ok = launch_gemm_bn<128>(ctx, p, L); break;
+    case 160: ok = launch_gemm_bn<160>(ctx, p, L); break;
+    case 256: ok = launch_gemm_bn<256>(ctx, p, L); break;
   }
   if (ctx->profile) {
     cudaEventRecord(ev1, ctx->stream);
@@ -364,8 +344,8 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     ctx->prof_ev.push_back(ev1);
     ctx->prof_flops.push_back(2.0 * d->M * d->N * d->K * groups);
     char desc[160];
-    snprintf(desc, sizeof(desc), "M=%d N=%d K=%d g=%d slabs=%d split=%d bn=%d A%s B%s flags=0x%x ek=%d grid=%d", d->M, d->N, d->K,
-             groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, ek, grid);
+    snprintf(desc, sizeof(desc), "M=%d N=%d K=%d g=%d slabs=%d split=%d bn=%d A%s B%s flags=0x%x ek=%d cg=%d share=%d grid=%d", d->M, d->N, d->K,
+             groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, ek, cg, (int)share, grid);
     ctx->prof_desc.push_back(desc);
   }
   return ok ? 0 : -1;

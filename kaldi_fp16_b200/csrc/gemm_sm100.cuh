@@ -98,7 +98,10 @@ struct GemmParams {
   float* ws[kMaxGroups];        // split-K fp32 accumulation target [M x ws_ld]
   int ws_ld;
   float drop_p; uint32_t drop_seed;
-  int k_rot;                    // 1: each tile starts its K loop at a different k-block (spreads L2 requests for shared operands)
+  // shared splice tile (SHARE kernels): slab s reads the A tile from row a_shift[s] (0..8) on
+  int a_shift[kMaxSlabs];
+  int a_box_bytes;              // bytes of the A box (128 + span rows) x 128 B
+  int mma_rep;                  // experiment knob: issue every UMMA this many times (0/1 = once)
 };
 
 // counter-based uniform in [0,1): shared by the CUDA epilogue and the CPU oracle (oracle/kaldi_oracle.py)
@@ -124,8 +127,10 @@ __device__ __forceinline__ float relu_nan(float x) {
 }
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
-template <int BN, bool A_MN, bool B_MN, int EK>
+template <int BN, bool A_MN, bool B_MN, int EK, int CG, bool SHARE>
 struct GemmCfg {
+  static_assert(CG == 1 || CG == 2, "cta_group 1 or 2");
+  static_assert(!SHARE || !A_MN, "the shared splice tile is implemented for a K-major A");
   static constexpr bool kSplitK = EK == EK_SPLITK;
   static constexpr uint32_t kFlags = epi_kind_flags(EK);
   static constexpr bool kMayUseR = EK == EK_GENERIC || (kFlags & (EPI_RESID | EPI_BETA)) != 0;
@@ -133,11 +138,14 @@ struct GemmCfg {
   // staging ring: 4 chunks when a residual tile is prefetched into it (in-place epilogue), else 2
   static constexpr int kRing = kSplitK ? 0 : (kMayUseR ? 4 : 2);
   static constexpr int kStoreWait = kRing >= 3 ? 1 : 0;        // TMA stores allowed in flight
-  static constexpr int kAChunks = A_MN ? 2 : 1;                // 64-wide M chunks (MN-major)
-  static constexpr int kBChunks = B_MN ? (BN + 63) / 64 : 1;   // 64-wide N chunks (MN-major)
-  static constexpr int kABytes = kBM * kBK * 2;                // 16 KB
-  static constexpr int kBBytes = B_MN ? kBChunks * 64 * kBK * 2 : BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kUmmaM = kBM * CG;                      // 256 rows over a CTA pair
+  static constexpr int kBNLocal = BN / CG;                     // B rows / columns staged by this CTA
+  static constexpr int kBChunks = B_MN ? (kBNLocal + 63) / 64 : 1;   // 64-wide N chunks (MN-major)
+  // SHARE: one A tile of 128+8 rows serves both splice slabs (row-shifted UMMA descriptors)
+  static constexpr int kABytes = SHARE ? (kBM + 8) * kBK * 2 : kBM * kBK * 2;
+  static constexpr int kBTileBytes = B_MN ? kBChunks * 64 * kBK * 2 : kBNLocal * kBK * 2;
+  static constexpr int kNumBTiles = SHARE ? 2 : 1;
+  static constexpr int kStageBytes = kABytes + kNumBTiles * kBTileBytes;
   static constexpr int kEpiBytes = kRing * kChunkBytes + (kUsesVec ? kVecBytes : 0);
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
   static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes) / kStageBytes;
@@ -146,13 +154,38 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
   static_assert(kStages >= 2, "tile too large for shared memory");
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=128; epilogue works on 32-column halves");
+  static_assert(kStageBytes % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N; epilogue works on 32-column halves");
 };
 
-template <int BN, bool A_MN, bool B_MN, int EK>
+// Tile bookkeeping shared by all warp roles.  A "unit" is a CTA (CG = 1) or a CTA pair (CG = 2);
+// a tile is kBM*CG rows x BN columns and this CTA owns rows m_row0 .. m_row0+127 of it.
+template <int BN, int CG>
+struct TileIter {
+  int m_tiles, n_tiles, tiles_per_split, total_tiles, unit, nunits, rank;
+  __device__ __forceinline__ TileIter(const GemmParams& p) {
+    m_tiles = (p.M + kBM * CG - 1) / (kBM * CG);
+    n_tiles = (p.N + BN - 1) / BN;
+    tiles_per_split = m_tiles * n_tiles * p.groups;
+    total_tiles = tiles_per_split * p.split_k;
+    unit = blockIdx.x / CG;
+    nunits = gridDim.x / CG;
+    rank = CG == 2 ? (int)cluster_ctarank() : 0;
+    p_groups = p.groups;
+  }
+  __device__ __forceinline__ void decode(int tile, int& n_blk, int& m_row0, int& g, int& ks) const {
+    int id = tile;
+    n_blk = id % n_tiles; id /= n_tiles;
+    m_row0 = (id % m_tiles) * (kBM * CG) + rank * kBM; id /= m_tiles;
+    g = id % p_groups; ks = id / p_groups;
+  }
+  int p_groups;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EK, int CG, bool SHARE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_sm100(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, A_MN, B_MN, EK>;
+  using Cfg = GemmCfg<BN, A_MN, B_MN, EK, CG, SHARE>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kRing = Cfg::kRing;
   constexpr bool kGeneric = EK == EK_GENERIC;
@@ -164,10 +197,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
   uint8_t* smem_vec = smem_epi + kRing * kChunkBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
-  uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA
-  uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
-  uint64_t* tempty_bar = tfull_bar + 2;       // [2]        epilogue -> MMA
+  uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA          (CG=2: the leader's is used)
+  uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA          (CG=2: commit multicast to both CTAs)
+  uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue     (CG=2: commit multicast)
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]        epilogue -> MMA     (CG=2: the leader's, 16 arrivals)
   uint64_t* rfull_bar = tempty_bar + 2;       // [4]        residual TMA -> epilogue
   uint64_t* rempty_bar = rfull_bar + 4;       // [4]        output store drained -> residual TMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + 4);
@@ -177,12 +210,12 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   const uint32_t flags = kGeneric ? p.flags : Cfg::kFlags;
   const bool use_r = Cfg::kMayUseR && (flags & (EPI_RESID | EPI_BETA)) != 0;
 
-  const int m_tiles = (p.M + kBM - 1) / kBM;
-  const int n_tiles = (p.N + BN - 1) / BN;
-  const int tiles_per_split = m_tiles * n_tiles * p.groups;
-  const int total_tiles = tiles_per_split * p.split_k;
+  const TileIter<BN, CG> ti(p);
+  const int total_tiles = ti.total_tiles;
+  const int rank = ti.rank;
   const int kb_per_slab = (p.kslab_len + kBK - 1) / kBK;
-  const int kb_total = p.kslabs * kb_per_slab;   // k-blocks over all slabs
+  // SHARE: the slabs are consumed inside every k-block; otherwise they are laid end to end along K
+  const int kb_total = SHARE ? kb_per_slab : p.kslabs * kb_per_slab;
   const int kb_per_split = (kb_total + p.split_k - 1) / p.split_k;
 
   if (warp == 0 && lane == 0) {
@@ -191,123 +224,159 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     if (!kSplitK) tma_prefetch_desc(&p.tmD[0]);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiThreads / 32);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], CG * (kEpiThreads / 32));   // one arrive per epilogue warp (of both CTAs)
     }
     for (int i = 0; i < 4; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 1); }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The three single-issuer roles below run with the whole warp converged and elect ONE lane only around
+  // the TMA / tcgen05 instructions: every address and descriptor is then warp-uniform, so ptxas keeps them
+  // in uniform registers.  (Measured: with an `if (lane == 0)` body the issue loop cost ~100 cycles per
+  // tcgen05.mma -- R2UR moves on a divergent path -- and bounded every GEMM regardless of tile shape.)
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int id = tile;
-        const int n_blk = id % n_tiles; id /= n_tiles;
-        const int m_blk = id % m_tiles; id /= m_tiles;
-        const int g = id % p.groups;
-        const int ks = id / p.groups;
-        const int kb0 = ks * kb_per_split;
-        const int kb1 = min(kb0 + kb_per_split, kb_total);
-        const int nkb = kb1 - kb0;
-        const int rot = p.k_rot ? (m_blk + n_blk) % nkb : 0;
-        for (int i = 0; i < nkb; ++i) {
-          const int kb = kb0 + (i + rot < nkb ? i + rot : i + rot - nkb);
-          const int slab = kb / kb_per_slab;
-          const int k_in = (kb - slab * kb_per_slab) * kBK;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t stage_tx = SHARE ? (uint32_t)(p.a_box_bytes + p.kslabs * Cfg::kBTileBytes)
+                                    : (uint32_t)(Cfg::kABytes + Cfg::kBTileBytes);
+    for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+      int n_blk, m_row0, g, ks;
+      ti.decode(tile, n_blk, m_row0, g, ks);
+      const int kb0 = ks * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, kb_total);
+      const int n_loc = n_blk * BN + rank * Cfg::kBNLocal;     // first B row / column staged by this CTA
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int slab = SHARE ? 0 : kb / kb_per_slab;
+        const int k_in = (kb - slab * kb_per_slab) * kBK;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          // completion is signalled on this CTA's full barrier (CG=1) or the pair leader's (CG=2)
+          const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[stage]), 0) : 0;
+          if (CG == 2) mbar_arrive_expect_tx_cluster(fb, stage_tx);
+          else mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+          auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+            if (CG == 2) tma_load_2d_pair(dst, m, fb, c0, c1);
+            else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(sa, &p.tmA, &full_bar[stage], k_in + p.a_col_off[g][slab],
-                        m_blk * kBM + p.a_row_off[g][slab]);
+            load(sa, &p.tmA, k_in + p.a_col_off[g][slab], m_row0 + p.a_row_off[g][slab]);
           } else {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-              tma_load_2d(sa + c * (64 * kBK * 2), &p.tmA, &full_bar[stage],
-                          m_blk * kBM + c * 64 + p.a_col_off[g][slab],
-                          k_in + p.a_row_off[g][slab]);
+              load(sa + c * (64 * kBK * 2), &p.tmA, m_row0 + c * 64 + p.a_col_off[g][slab],
+                   k_in + p.a_row_off[g][slab]);
           }
-          if (!B_MN) {
-            tma_load_2d(sb, &p.tmB, &full_bar[stage], k_in + p.b_col_off[g][slab],
-                        n_blk * BN + p.b_row_off[g][slab]);
-          } else {
+          const int nb = SHARE ? p.kslabs : 1;
+          for (int t = 0; t < nb; ++t) {
+            const int bs = SHARE ? t : slab;
+            uint8_t* sbt = sb + t * Cfg::kBTileBytes;
+            if (!B_MN) {
+              load(sbt, &p.tmB, k_in + p.b_col_off[g][bs], n_loc + p.b_row_off[g][bs]);
+            } else {
 #pragma unroll
-            for (int c = 0; c < Cfg::kBChunks; ++c)
-              tma_load_2d(sb + c * (64 * kBK * 2), &p.tmB, &full_bar[stage],
-                          n_blk * BN + c * 64 + p.b_col_off[g][slab],
-                          k_in + p.b_row_off[g][slab]);
+              for (int c = 0; c < Cfg::kBChunks; ++c)
+                load(sbt + c * (64 * kBK * 2), &p.tmB, n_loc + c * 64 + p.b_col_off[g][bs],
+                     k_in + p.b_row_off[g][bs]);
+            }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ======================================================= MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kBM, BN, A_MN, B_MN);
+    // ======================================================= MMA issuer (CG=2: the pair leader only)
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(Cfg::kUmmaM, BN, A_MN, B_MN);
       // K-major: 8-row groups 1024 B apart (SBO); MN-major: 64-wide chunks 8 KB apart (LBO),
       // 8-k groups 1024 B apart (SBO).
       constexpr uint32_t a_lbo = A_MN ? 64 * kBK * 2 : 16, a_sbo = 1024;
       constexpr uint32_t b_lbo = B_MN ? 64 * kBK * 2 : 16, b_sbo = 1024;
-      constexpr uint32_t a_kstep = A_MN ? 2048 : 32;   // bytes per UMMA K=16
-      constexpr uint32_t b_kstep = B_MN ? 2048 : 32;
+      constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4;   // descriptor units (16 B) per UMMA K=16
+      constexpr uint32_t b_kstep = (B_MN ? 2048 : 32) >> 4;
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem), a_lbo, a_sbo, kLayoutSW128);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, b_lbo, b_sbo, kLayoutSW128);
+      auto mma = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t accum) {
+        if (CG == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum);
+        else umma_f16(d_tmem, ad, bd, idesc, accum);
+      };
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ks = tile / tiles_per_split;
+      for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+        const int ks = tile / ti.tiles_per_split;
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
-        const int nkb = kb1 - kb0;
-        const int rot = p.k_rot ? ((tile % n_tiles) + (tile / n_tiles) % m_tiles) % nkb : 0;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
-        for (int i = 0; i < nkb; ++i) {
-          const int kb = kb0 + (i + rot < nkb ? i + rot : i + rot - nkb);
-          const int slab = kb / kb_per_slab;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int slab = SHARE ? 0 : kb / kb_per_slab;
           const int k_in = (kb - slab * kb_per_slab) * kBK;
           const int k16s = min(kBK, p.kslab_len - k_in + 15) >> 4;   // partial last block (K % 64)
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, kLayoutSW128);
-          const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, kLayoutSW128);
-          for (int k = 0; k < k16s; ++k) {
-            umma_f16(d_tmem, adesc + ((uint64_t)(k * a_kstep) >> 4),
-                     bdesc + ((uint64_t)(k * b_kstep) >> 4), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if (elect_one()) {
+            const uint64_t so = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
+            const int nb = SHARE ? p.kslabs : 1;
+            for (int t = 0; t < nb; ++t) {
+              // SHARE: slab t reads the A tile from row a_shift[t] on: the descriptor start moves by whole
+              // 128-byte rows.  Measured on B200: the 128B swizzle is applied on the absolute shared-memory
+              // address bits, so the descriptor's base-offset field stays 0 (setting it to the row phase,
+              // as the CUTLASS comment on that field suggests for unaligned starts, gives wrong products).
+              const uint64_t ad = adesc0 + so + (SHARE ? (uint64_t)((uint32_t)p.a_shift[t] * 8u) : 0ull);
+              const uint64_t bd = bdesc0 + so + (uint64_t)((uint32_t)(t * Cfg::kBTileBytes) >> 4);
+              const uint32_t first = (kb > kb0 || t > 0) ? 1u : 0u;
+              if (k16s == 4 && p.mma_rep <= 1) {
+                mma(d_tmem, ad, bd, first);
+                mma(d_tmem, ad + a_kstep, bd + b_kstep, 1u);
+                mma(d_tmem, ad + 2 * a_kstep, bd + 2 * b_kstep, 1u);
+                mma(d_tmem, ad + 3 * a_kstep, bd + 3 * b_kstep, 1u);
+              } else {
+                for (int rep = (p.mma_rep > 1 ? p.mma_rep : 1); rep > 0; --rep)
+                  for (int k = 0; k < k16s; ++k)
+                    mma(d_tmem, ad + k * a_kstep, bd + k * b_kstep, (first || k > 0 || rep < p.mma_rep) ? 1u : 0u);
+              }
+            }
+            if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if (CG == 2) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp == 3) {
     // =========================================== residual / C-in prefetch
-    if (Cfg::kMayUseR && lane == 0 && use_r) {
+    if (Cfg::kMayUseR && use_r) {
       int k = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int id = tile;
-        const int n_blk = id % n_tiles; id /= n_tiles;
-        const int m_blk = id % m_tiles; id /= m_tiles;
-        const int g = id % p.groups;
+      for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+        int n_blk, m_row0, g, ks;
+        ti.decode(tile, n_blk, m_row0, g, ks);
         for (int c64 = 0; c64 < BN; c64 += 64, ++k) {
           const int buf = k & 3;
           if (k >= 4) mbar_wait(&rempty_bar[buf], ((k >> 2) + 1) & 1);
-          mbar_arrive_expect_tx(&rfull_bar[buf], kChunkBytes);
-          tma_load_2d(smem_epi + buf * kChunkBytes, &p.tmR[g], &rfull_bar[buf], n_blk * BN + c64, m_blk * kBM);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&rfull_bar[buf], kChunkBytes);
+            tma_load_2d(smem_epi + buf * kChunkBytes, &p.tmR[g], &rfull_bar[buf], n_blk * BN + c64, m_row0);
+          }
+          __syncwarp();
         }
       }
     }
@@ -323,12 +392,12 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     float* s_shift = reinterpret_cast<float*>(smem_vec + 512 + 1024);
     int acc = 0; uint32_t acc_phase = 0;
     int k = 0;   // running 64-column chunk counter (staging ring position)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int id = tile;
-      const int n_blk = id % n_tiles; id /= n_tiles;
-      const int m_blk = id % m_tiles; id /= m_tiles;
-      const int g = id % p.groups;
-      const int row = m_blk * kBM + row_in_tile;
+    const uint32_t tempty_leader[2] = {CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u,
+                                       CG == 2 ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
+    for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+      int n_blk, m_row0, g, ks;
+      ti.decode(tile, n_blk, m_row0, g, ks);
+      const int row = m_row0 + row_in_tile;
       const int n0 = n_blk * BN;
 
       if (Cfg::kUsesVec && (flags & (EPI_BIAS | EPI_BN))) {
@@ -473,7 +542,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           }
           named_bar_sync(1, kEpiThreads);
           if (epi_tid == 0) {
-            tma_store_2d(&p.tmD[g], sbuf, n0 + c64, m_blk * kBM);
+            tma_store_2d(&p.tmD[g], sbuf, n0 + c64, m_row0);
             tma_store_commit();
           }
         }
@@ -481,17 +550,20 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       // all tcgen05.ld of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_leader[acc]); else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (!kSplitK && epi_tid == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer may still arrive on the leader's barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CG == 2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 

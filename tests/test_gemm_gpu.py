@@ -54,6 +54,8 @@ def test_ops_gemm_matches_reference_library(handle, reflib, M, N, K):
         got = tC.ToFP32()
         want = O.gemm(A, B, alpha, beta, C0)
         tol = gemm_tol(A, B, want, alpha) + 2.0 ** -10 * np.abs(beta * C0)
+        if beta != 0.0:   # cuBLAS rounds alpha*acc to fp16 before adding beta*C (see oracle.gemm): one more rounding of the product
+            tol = tol + 2.0 ** -10 * np.abs(alpha * O.gemm_f64(A, B))
         assert_close(ref, want, tol, f"oracle vs reference cuBLAS a={alpha} b={beta}")   # pins the oracle
         assert_close(got, ref, tol, f"kernel vs reference cuBLAS a={alpha} b={beta}")
         for b in (rA, rB, rC):
@@ -204,3 +206,89 @@ def test_unaligned_shapes_take_the_simt_path(handle, lib):
         gpu.Sync()
         want = O.gemm(A, B, 1.0, 1.0, C0)
         assert_close(tC.ToFP32(), want, gemm_tol(A, B, want) + 2.0 ** -10 * np.abs(C0), f"simt {M}x{N}x{K}")
+
+
+# ------------------------------------------------------------------ CTA pairs (cta_group::2) and the shared splice tile
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,N,K,b_k_major", [(512, 160, 384, False), (1000, 256, 320, False), (384, 160, 1536, True),
+                                             (2000, 1536, 192, False), (777, 64, 200, True), (260, 128, 64, False)])
+def test_cta_pair_plain_gemm(handle, lib, cg, M, N, K, b_k_major):
+    """256-row tiles over a CTA pair (each CTA stages half of B) == one CTA per 128-row tile == oracle"""
+    rng = np.random.default_rng(M + N + K)
+    A, B = rand_f16(rng, (M, K)), rand_f16(rng, (K, N), 0.1)
+    want = O.gemm(A, B)
+    tA, tD = gpu.TensorFromFP16(A), gpu.ZeroTensor(M, N)
+    tB = gpu.TensorFromFP16(np.ascontiguousarray(B.T) if b_k_major else B)
+    d = make_desc(M, N, K, tA, tB, tD, b_major=K_MAJOR if b_k_major else MN_MAJOR, force_cg=cg)
+    lib.kfp16_ctx_set_max_ctas(handle.ptr, 6)          # several tiles per CTA / pair: exercises every ring
+    try:
+        run_desc(handle, d)
+    finally:
+        lib.kfp16_ctx_set_max_ctas(handle.ptr, 0)
+    assert_close(tD.ToFP32(), want, gemm_tol(A, B, want), f"cg={cg} {M}x{N}x{K}")
+    for t in (tA, tB, tD):
+        t.Free()
+
+
+@pytest.mark.parametrize("cg,no_share", [(1, 1), (2, 1), (2, 0)])
+@pytest.mark.parametrize("T,D,N,s0,s1,b_k_major", [(600, 192, 160, -3, 0, False), (600, 160, 256, 0, 3, False),
+                                                   (515, 256, 160, 0, -3, True), (900, 160, 1536, 3, 0, True),
+                                                   (300, 64, 64, -1, 0, False)])
+def test_spliced_gemm_shared_tile(handle, lib, cg, no_share, T, D, N, s0, s1, b_k_major):
+    """Y = X(t+s0)*W0 + X(t+s1)*W1 (forward.go:699-790 and its transposes): separate A tiles per slab vs ONE
+    A tile of 128+|s| rows read through row-shifted UMMA descriptors, on one CTA and on a CTA pair"""
+    halo = 3
+    rng = np.random.default_rng(T + D + N)
+    X = rand_f16(rng, (T, D))
+    W = rand_f16(rng, (2 * D, N), 0.08)
+    Xp = np.concatenate([np.repeat(X[:1], halo, 0), X, np.repeat(X[-1:], halo, 0)], 0)
+    i0, i1 = np.clip(np.arange(T) + s0, 0, T - 1), np.clip(np.arange(T) + s1, 0, T - 1)
+    S = np.concatenate([X[i0], X[i1]], 1)
+    want = O.gemm(S, W)
+    tXp, tD = gpu.TensorFromFP16(Xp), gpu.ZeroTensor(T, N)
+    # K-major B: stored [2N x D]: rows [0,N) = W0^T, rows [N,2N) = W1^T  (the layout dgrad sees: W stored [out x in])
+    Bst = np.concatenate([W[:D].T, W[D:].T], 0) if b_k_major else W
+    tW = gpu.TensorFromFP16(np.ascontiguousarray(Bst))
+    d = make_desc(T, N, 2 * D, tXp, tW, tD, b_major=K_MAJOR if b_k_major else MN_MAJOR, force_cg=cg, no_share=no_share)
+    d.A.ptr = tXp.Ptr + halo * D * 2
+    d.A.rows, d.A.halo = T, halo
+    d.kslabs, d.kslab_len = 2, D
+    d.a_row_off[0][0], d.a_row_off[0][1] = s0, s1
+    d.b_row_off[0][0], d.b_row_off[0][1] = 0, (N if b_k_major else D)
+    run_desc(handle, d)
+    assert_close(tD.ToFP32(), want, gemm_tol(S, W, want), f"spliced cg={cg} no_share={no_share}")
+    for t in (tXp, tW, tD):
+        t.Free()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_fused_epilogues_on_cta_pairs(handle, lib, cg):
+    """the specialised affine epilogue (bias, relu, bn, mask, bypass) on 128- and 256-row tiles vs the generic one"""
+    M, N, K = 700, 512, 192
+    rng = np.random.default_rng(17)
+    A, W, X = rand_f16(rng, (M, K)), rand_f16(rng, (K, N), 0.08), rand_f16(rng, (M, N))
+    bias = rand_f16(rng, (N,), 0.1)
+    scale, shift = (rng.random(N).astype(np.float32) + 0.5), rng.standard_normal(N).astype(np.float32) * 0.1
+    z = A.astype(np.float64) @ W.astype(np.float64) + bias
+    relu = np.maximum(z, 0)
+    want = relu * scale + shift + 0.66 * X
+    tA, tW, tX = gpu.TensorFromFP16(A), gpu.TensorFromFP16(W), gpu.TensorFromFP16(X)
+    tb = gpu.TensorFromFP16(bias.reshape(1, -1))
+    sc, sh = gpu.DeviceF32(scale), gpu.DeviceF32(shift)
+    mask_ld = (N + 31) // 32
+    outs = []
+    for generic in (0, 1):
+        tD, mask = gpu.ZeroTensor(M, N), gpu.DeviceF32(n=M * mask_ld)
+        d = make_desc(M, N, K, tA, tW, tD, flags=EPI_BIAS | EPI_RELU | EPI_BN | EPI_RESID | EPI_MASK, bias=tb.Ptr,
+                      bn_scale=sc.Ptr, bn_shift=sh.Ptr, res_scale=0.66, mask_out=mask.Ptr, mask_ld=mask_ld, ldr=N,
+                      force_cg=cg, force_generic=generic)
+        d.R[0] = tX.Ptr
+        run_desc(handle, d)
+        got = tD.ToFP32()
+        assert_close(got, want, 2.0 ** -10 * np.abs(want) * 1.01 + 2e-3, f"affine epilogue cg={cg} generic={generic}")
+        bits = mask.ToHost().view(np.uint32).reshape(M, mask_ld)
+        got_mask = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(M, -1)[:, :N].astype(bool)
+        assert ((got_mask == (z > 0)) | (np.abs(z) < 1e-3)).all()
+        outs.append(got)
+        tD.Free()
+    assert np.array_equal(outs[0], outs[1])       # specialised == generic, bit for bit
