@@ -98,6 +98,7 @@ typedef struct {
     int force_generic; /* 1 = run the run-time-flag epilogue even when a specialised one exists (tests) */
     int force_cg;      /* 0 = heuristic; 1 = one CTA per 128-row tile; 2 = CTA pairs (cta_group::2, 256-row tiles) */
     int no_share;      /* 1 = load each splice slab's A tile separately even when one shifted tile could serve both */
+    void *debug_clock_buf; /* profiling: device int64 [grid][3 roles][8 tiles][16] clock64 stamps per warp role; NULL = off */
 } kfp16_gemm_desc;
 
 /* returns 0 on success, -1 on error (message via kfp16_last_error / ops_last_error) */

@@ -39,7 +39,7 @@ class GemmDesc(C.Structure):
         ("mask_out", c_void_p), ("mask_in", c_void_p), ("mask_ld", c_int),
         ("split_k", c_int), ("ws", c_void_p * 2), ("ws_ld", c_int),
         ("drop_p", c_float), ("drop_seed", c_u32),
-        ("force_bn", c_int), ("force_generic", c_int), ("force_cg", c_int), ("no_share", c_int),
+        ("force_bn", c_int), ("force_generic", c_int), ("force_cg", c_int), ("no_share", c_int), ("debug_clock_buf", c_void_p),
     ]
 
 

@@ -239,6 +239,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   // are row-shifted views of the same columns (time splicing).  force_cg / KFP16_CG override (tests).
   static const int env_cg = getenv("KFP16_CG") ? atoi(getenv("KFP16_CG")) : 0;
   static const int env_share = getenv("KFP16_SHARE") ? atoi(getenv("KFP16_SHARE")) : 1;
+  p.dbg = (long long*)d->debug_clock_buf;
   p.mma_rep = getenv("KFP16_MMAREP") ? atoi(getenv("KFP16_MMAREP")) : 1;
   int cg = d->force_cg ? d->force_cg : (env_cg ? env_cg : 2);
   if (cg != 1 && cg != 2) { set_error("kfp16_gemm_ex: force_cg must be 0, 1 or 2"); return -1; }

@@ -102,6 +102,7 @@ struct GemmParams {
   int a_shift[kMaxSlabs];
   int a_box_bytes;              // bytes of the A box (128 + span rows) x 128 B
   int mma_rep;                  // experiment knob: issue every UMMA this many times (0/1 = once)
+  long long* dbg;               // profiling: per-CTA role timestamps [grid][3 roles][8 tiles][16] (nullptr = off)
 };
 
 // counter-based uniform in [0,1): shared by the CUDA epilogue and the CPU oracle (oracle/kaldi_oracle.py)
@@ -136,8 +137,11 @@ struct GemmCfg {
   static constexpr bool kMayUseR = EK == EK_GENERIC || (kFlags & (EPI_RESID | EPI_BETA)) != 0;
   static constexpr bool kUsesVec = EK == EK_GENERIC || (kFlags & (EPI_BIAS | EPI_BN)) != 0;
   // staging ring: 4 chunks when a residual tile is prefetched into it (in-place epilogue), else 2
-  static constexpr int kRing = kSplitK ? 0 : (kMayUseR ? 4 : 2);
-  static constexpr int kStoreWait = kRing >= 3 ? 1 : 0;        // TMA stores allowed in flight
+  // (6 when the tile is narrow enough to afford it: the residual prefetch then runs 4 chunks ahead)
+  static constexpr int kRing = kSplitK ? 0 : (kMayUseR ? (BN <= 160 ? 6 : 4) : 4);
+  // TMA stores left in flight when a chunk is handed over (a store's smem-read latency is ~1000 cycles:
+  // with none in flight every 64-column chunk paid it in full)
+  static constexpr int kStoreWait = kRing == 6 ? 3 : (kMayUseR ? 1 : 2);
   static constexpr int kUmmaM = kBM * CG;                      // 256 rows over a CTA pair
   static constexpr int kBNLocal = BN / CG;                     // B rows / columns staged by this CTA
   static constexpr int kBChunks = B_MN ? (kBNLocal + 63) / 64 : 1;   // 64-wide N chunks (MN-major)
@@ -146,7 +150,7 @@ struct GemmCfg {
   static constexpr int kBTileBytes = B_MN ? kBChunks * 64 * kBK * 2 : kBNLocal * kBK * 2;
   static constexpr int kNumBTiles = SHARE ? 2 : 1;
   static constexpr int kStageBytes = kABytes + kNumBTiles * kBTileBytes;
-  static constexpr int kEpiBytes = kRing * kChunkBytes + (kUsesVec ? kVecBytes : 0);
+  static constexpr int kEpiBytes = kRing * kChunkBytes + (kUsesVec ? 2 * kVecBytes : 0);   // vectors double-buffered
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
   static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -182,6 +186,12 @@ struct TileIter {
   int p_groups;
 };
 
+// profiling hook: role 0 = TMA producer, 1 = MMA issuer, 2 = epilogue (warp 4); slot < 16, tile index < 8
+__device__ __forceinline__ void dbg_stamp(const GemmParams& p, int role, int tile_i, int slot) {
+  if (p.dbg != nullptr && tile_i < 8 && (threadIdx.x & 31) == 0)
+    p.dbg[(((size_t)blockIdx.x * 3 + role) * 8 + tile_i) * 16 + slot] = clock64();
+}
+
 template <int BN, bool A_MN, bool B_MN, int EK, int CG, bool SHARE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_sm100(const __grid_constant__ GemmParams p) {
@@ -201,9 +211,9 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA          (CG=2: commit multicast to both CTAs)
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue     (CG=2: commit multicast)
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]        epilogue -> MMA     (CG=2: the leader's, 16 arrivals)
-  uint64_t* rfull_bar = tempty_bar + 2;       // [4]        residual TMA -> epilogue
-  uint64_t* rempty_bar = rfull_bar + 4;       // [4]        output store drained -> residual TMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + 4);
+  uint64_t* rfull_bar = tempty_bar + 2;       // [8]        residual TMA -> epilogue
+  uint64_t* rempty_bar = rfull_bar + 8;       // [8]        output store drained -> residual TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -229,7 +239,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], CG * (kEpiThreads / 32));   // one arrive per epilogue warp (of both CTAs)
     }
-    for (int i = 0; i < 4; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 1); }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -250,12 +260,14 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     int stage = 0; uint32_t phase = 0;
     const uint32_t stage_tx = SHARE ? (uint32_t)(p.a_box_bytes + p.kslabs * Cfg::kBTileBytes)
                                     : (uint32_t)(Cfg::kABytes + Cfg::kBTileBytes);
-    for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+    int tile_i = 0;
+    for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits, ++tile_i) {
       int n_blk, m_row0, g, ks;
       ti.decode(tile, n_blk, m_row0, g, ks);
       const int kb0 = ks * kb_per_split;
       const int kb1 = min(kb0 + kb_per_split, kb_total);
       const int n_loc = n_blk * BN + rank * Cfg::kBNLocal;     // first B row / column staged by this CTA
+      dbg_stamp(p, 0, tile_i, 0);
       for (int kb = kb0; kb < kb1; ++kb) {
         const int slab = SHARE ? 0 : kb / kb_per_slab;
         const int k_in = (kb - slab * kb_per_slab) * kBK;
@@ -294,8 +306,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           }
         }
         __syncwarp();
+        if (kb == kb0) dbg_stamp(p, 0, tile_i, 1);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      dbg_stamp(p, 0, tile_i, 2);
     }
   } else if (warp == 1) {
     // ======================================================= MMA issuer (CG=2: the pair leader only)
@@ -315,12 +329,15 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       };
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+      int tile_i = 0;
+      for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits, ++tile_i) {
         const int ks = tile / ti.tiles_per_split;
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
+        dbg_stamp(p, 1, tile_i, 0);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        dbg_stamp(p, 1, tile_i, 1);
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
         for (int kb = kb0; kb < kb1; ++kb) {
           const int slab = SHARE ? 0 : kb / kb_per_slab;
@@ -328,6 +345,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           const int k16s = min(kBK, p.kslab_len - k_in + 15) >> 4;   // partial last block (K % 64)
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == kb0) dbg_stamp(p, 1, tile_i, 2);
           if (elect_one()) {
             const uint64_t so = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
             const int nb = SHARE ? p.kslabs : 1;
@@ -359,24 +377,25 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           if (CG == 2) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
+        dbg_stamp(p, 1, tile_i, 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp == 3) {
     // =========================================== residual / C-in prefetch
     if (Cfg::kMayUseR && use_r) {
-      int k = 0;
+      int buf = 0; uint32_t round = 0;     // ring position of the running chunk counter
       for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
         int n_blk, m_row0, g, ks;
         ti.decode(tile, n_blk, m_row0, g, ks);
-        for (int c64 = 0; c64 < BN; c64 += 64, ++k) {
-          const int buf = k & 3;
-          if (k >= 4) mbar_wait(&rempty_bar[buf], ((k >> 2) + 1) & 1);
+        for (int c64 = 0; c64 < BN; c64 += 64) {
+          if (round > 0) mbar_wait(&rempty_bar[buf], (round + 1) & 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&rfull_bar[buf], kChunkBytes);
             tma_load_2d(smem_epi + buf * kChunkBytes, &p.tmR[g], &rfull_bar[buf], n_blk * BN + c64, m_row0);
           }
           __syncwarp();
+          if (++buf == kRing) { buf = 0; ++round; }
         }
       }
     }
@@ -387,37 +406,61 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     const int row_in_tile = q * 32 + lane;
     const int epi_tid = threadIdx.x - 128;
     const bool ref_round = kGeneric && (flags & EPI_REF_ROUND) != 0;
-    __half* s_bias = reinterpret_cast<__half*>(smem_vec);
-    float* s_scale = reinterpret_cast<float*>(smem_vec + 512);
-    float* s_shift = reinterpret_cast<float*>(smem_vec + 512 + 1024);
     int acc = 0; uint32_t acc_phase = 0;
-    int k = 0;   // running 64-column chunk counter (staging ring position)
+    int k = 0;   // running 64-column chunk counter
+    int buf = 0; uint32_t round = 0;   // its position in the staging ring
+    int fbuf = 0;                      // ring slot of chunk k-1-kStoreWait (the one a drained store frees)
+    // per-column vectors (bias, bn scale/shift): double-buffered in smem; the loads for the NEXT tile are
+    // issued at the start of the current one so their latency hides behind its chunks
+    const bool use_vec = Cfg::kUsesVec && (flags & (EPI_BIAS | EPI_BN)) != 0;
+    int vsel = 0;
+    __half nbias = __float2half(0.f); float nscale = 0.f, nshift = 0.f;
+    auto vec_fetch = [&](int tile) {
+      if (epi_tid < BN && tile < total_tiles) {
+        int n_blk, m_row0, g, ks;
+        ti.decode(tile, n_blk, m_row0, g, ks);
+        const int col = n_blk * BN + epi_tid;
+        const bool ok = col < p.N;
+        const int vi = g * p.vec_gstride + col;
+        if (flags & EPI_BIAS) nbias = ok ? p.bias[vi] : __float2half(0.f);
+        if (flags & EPI_BN) {
+          nscale = ok ? __ldg(p.bn_scale + vi) : 0.f;
+          nshift = ok ? __ldg(p.bn_shift + vi) : 0.f;
+        }
+      }
+    };
+    auto vec_store = [&](int sel) {
+      if (epi_tid < BN) {
+        uint8_t* vb = smem_vec + sel * kVecBytes;
+        if (flags & EPI_BIAS) reinterpret_cast<__half*>(vb)[epi_tid] = nbias;
+        if (flags & EPI_BN) {
+          reinterpret_cast<float*>(vb + 512)[epi_tid] = nscale;
+          reinterpret_cast<float*>(vb + 512 + 1024)[epi_tid] = nshift;
+        }
+      }
+    };
+    if (use_vec) { vec_fetch(ti.unit); vec_store(0); }
     const uint32_t tempty_leader[2] = {CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u,
                                        CG == 2 ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
-    for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+    int tile_i = 0;
+    for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits, ++tile_i) {
       int n_blk, m_row0, g, ks;
       ti.decode(tile, n_blk, m_row0, g, ks);
       const int row = m_row0 + row_in_tile;
       const int n0 = n_blk * BN;
+      if (warp == 4) dbg_stamp(p, 2, tile_i, 0);
 
-      if (Cfg::kUsesVec && (flags & (EPI_BIAS | EPI_BN))) {
-        // per-column vectors of this tile -> shared memory (every reader of the previous tile's
-        // vectors has passed that tile's last chunk barrier before anyone gets here)
-        if (epi_tid < BN) {
-          const int col = n0 + epi_tid;
-          const bool ok = col < p.N;
-          const int vi = g * p.vec_gstride + col;
-          if (flags & EPI_BIAS) s_bias[epi_tid] = ok ? p.bias[vi] : __float2half(0.f);
-          if (flags & EPI_BN) {
-            s_scale[epi_tid] = ok ? __ldg(p.bn_scale + vi) : 0.f;
-            s_shift[epi_tid] = ok ? __ldg(p.bn_shift + vi) : 0.f;
-          }
-        }
-        named_bar_sync(2, kEpiThreads);
+      const __half* s_bias = reinterpret_cast<const __half*>(smem_vec + vsel * kVecBytes);
+      const float* s_scale = reinterpret_cast<const float*>(smem_vec + vsel * kVecBytes + 512);
+      const float* s_shift = reinterpret_cast<const float*>(smem_vec + vsel * kVecBytes + 512 + 1024);
+      if (use_vec) {
+        named_bar_sync(2, kEpiThreads);      // this tile's vectors (stored at the end of the previous tile) are visible
+        vec_fetch(tile + ti.nunits);         // next tile's: in flight while this tile is processed
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (warp == 4) dbg_stamp(p, 2, tile_i, 1);
       const uint32_t t_acc = tmem_base + acc * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
 
       if constexpr (kSplitK) {
@@ -445,11 +488,11 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       } else {
 #pragma unroll 1
         for (int c64 = 0; c64 < BN; c64 += 64, ++k) {
-          const int buf = k & (kRing - 1);
           uint8_t* sbuf = smem_epi + buf * kChunkBytes;
           uint8_t* srow = sbuf + row_in_tile * 128;
           const int c = c64 + hsel * 32;          // first tile column of this thread's 32
-          if (use_r) mbar_wait(&rfull_bar[buf], (k >> 2) & 1);
+          if (use_r) mbar_wait(&rfull_bar[buf], round & 1);
+          if (warp == 4 && c64 < 256) dbg_stamp(p, 2, tile_i, 2 + 3 * (c64 >> 6));
           if (c < BN) {
             uint32_t v32[32];
             if (!kGeneric) {
@@ -534,17 +577,25 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
               p.mask_out[(size_t)row * p.mask_ld + ((n0 + c) >> 5)] = maskword;
           }
           fence_proxy_async_smem();
+          if (warp == 4 && c64 < 256) dbg_stamp(p, 2, tile_i, 3 + 3 * (c64 >> 6));
           if (epi_tid == 0) {
             // stores older than the newest kStoreWait have drained their smem reads: the buffer
             // two chunks back is free again (for the next residual prefetch / next write)
             tma_store_wait_read<Cfg::kStoreWait>();
-            if (use_r && k >= 2) mbar_arrive(&rempty_bar[(k - 2) & 3]);
+            if (use_r && k >= Cfg::kStoreWait + 1) mbar_arrive(&rempty_bar[fbuf]);
           }
           named_bar_sync(1, kEpiThreads);
+          if (warp == 4 && c64 < 256) dbg_stamp(p, 2, tile_i, 4 + 3 * (c64 >> 6));
           if (epi_tid == 0) {
             tma_store_2d(&p.tmD[g], sbuf, n0 + c64, m_row0);
             tma_store_commit();
           }
+          if (++buf == kRing) { buf = 0; ++round; }
+          if (k >= Cfg::kStoreWait + 1 && ++fbuf == kRing) fbuf = 0;
+        }
+        if (use_vec) {            // everyone is past this tile's last chunk barrier: the other buffer is free
+          vsel ^= 1;
+          vec_store(vsel);
         }
       }
       // all tcgen05.ld of this accumulator stage are complete -> hand it back to the MMA warp
@@ -553,6 +604,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(tempty_leader[acc]); else mbar_arrive(&tempty_bar[acc]);
       }
+      if (warp == 4) dbg_stamp(p, 2, tile_i, 15);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (!kSplitK && epi_tid == 0) tma_store_wait_all<0>();

@@ -80,7 +80,7 @@ elif name in ("F2", "F2p", "B4"):
         setB(Waff, 2 * Bt, H)
         d.a_row_off[0][0], d.a_row_off[0][1], d.b_row_off[0][0], d.b_row_off[0][1] = 0, s, 0, Bt
         if name == "F2":
-            d.flags = EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK | EPI_RESID
+            d.flags = int(kv["flags"], 0) if "flags" in kv else (EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK | EPI_RESID)
             d.bias, d.bn_scale, d.bn_shift, d.mask_out, d.mask_ld = bias.Ptr, sc.Ptr, sh.Ptr, mask.Ptr, H // 32
             d.res_scale, d.ldr = 0.66, H
             d.R[0] = X.Ptr + halo * H * 2
@@ -112,6 +112,11 @@ else:
 
 if ctas:
     lib.kfp16_ctx_set_max_ctas(h.ptr, ctas)
+dbg = None
+if int(kv.get("dbg", 0)):
+    dbg = gpu.DeviceF32(n=148 * 3 * 8 * 16 * 2)
+    cudart.memset(dbg.Ptr, 0, dbg.N * 4)
+    d.debug_clock_buf = dbg.Ptr
 fl = gpu.DeviceF32(n=64 * 1024 * 1024) if flush else None
 e0, e1 = cudart.Event(), cudart.Event()
 lib.kfp16_ctx_set_profile(h.ptr, 0)
@@ -126,6 +131,15 @@ for it in range(iters + 3):
     e1.synchronize()
     if it >= 3:
         ts.append(e0.elapsed_ms(e1) * 1e3)
+if dbg is not None:
+    st = dbg.ToHost().view(np.int64).reshape(148, 3, 8, 16)
+    for cta in [int(x) for x in kv.get("ctas_dbg", "0,1,77").split(",")]:
+        t0 = st[cta][st[cta] > 0].min() if (st[cta] > 0).any() else 0
+        for role, rn in enumerate(["tma", "mma", "epi"]):
+            for ti_ in range(8):
+                row = st[cta, role, ti_]
+                if (row > 0).any():
+                    print(f"cta {cta:3d} {rn} tile {ti_}: " + " ".join(f"{(v - t0) if v > 0 else -1:6d}" for v in row))
 flops = 2.0 * d.M * d.N * d.K * d.groups
 med = float(np.median(ts))
 print(f"{name:4s} {' '.join(sys.argv[2:]):40s} median {med:7.2f} us  min {min(ts):7.2f} us  {flops / med / 1e6:7.1f} TF")
