@@ -160,6 +160,17 @@ int kfp16_bn_relu_backward_bias(kfp16_ctx *ctx, const void *dY, int ldy, const f
 /* out_f32[n] += sum_t X[t,n]  (no memset: accumulates into the flat gradient bucket) */
 int kfp16_colsum_accum(kfp16_ctx *ctx, const void *X, int ld, int rows, int cols, float *out_f32);
 
+/* ---- CNN front-end: patch gather / scatter for conv-relu-batchnorm-layer
+ * (the reference builds the patch matrix in Go on the CPU between a D2H and an H2D copy,
+ *  internal/nnet/forward.go:429-455).  x: padded rows [n_seq*(seq_len+2*halo) x hin*fin], height-major;
+ * P: [rows*hout x Kp] with P[(r*hout+ho), tap*fin+f] = x[r+dt[tap], (ho*sub+dh[tap])*fin+f], zero outside the
+ * sequence's real frames / [0,hin) and in the K padding columns [ntaps*fin, Kp). */
+int kfp16_im2col(kfp16_ctx *ctx, const void *x, void *P, int Kp, int n_seq, int seq_len, int halo, int hin,
+                 int hout, int sub, int fin, int ntaps, const int *dt, const int *dh);
+/* adjoint of kfp16_im2col: dx[r, h*fin+f] = sum of the dP entries that read it (fp32 sum, one fp16 rounding) */
+int kfp16_col2im(kfp16_ctx *ctx, const void *dP, int Kp, void *dx, int n_seq, int seq_len, int halo, int hin,
+                 int hout, int sub, int fin, int ntaps, const int *dt, const int *dh);
+
 #ifdef __cplusplus
 }
 #endif

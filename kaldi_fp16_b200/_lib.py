@@ -102,6 +102,8 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_half_sq_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "kfp16_bn_relu_backward_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "kfp16_colsum_accum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kfp16_im2col": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [C.POINTER(c_int), C.POINTER(c_int)]),
+    "kfp16_col2im": (c_int, [c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 8 + [C.POINTER(c_int), C.POINTER(c_int)]),
     # ---- kaldi_fp16_nnet.h
     "kfp16_net_create": (c_void_p, [c_void_p, C.c_char_p, C.POINTER(NetOpts)]),
     "kfp16_net_destroy": (None, [c_void_p]),

@@ -1,0 +1,176 @@
+// CNN front-end support: patch gather / scatter for the conv-relu-batchnorm layer.
+//
+// The reference lowers its convolution to a GEMM through an im2col done in Go on the CPU, between a
+// D2H and an H2D copy (/root/reference/internal/nnet/forward.go:418-524: patches P[(t*Hout+ho),
+// off*Fin+f] = X[t+dt, (ho*sub+dh)*Fin+f], zero outside).  Here the same patch matrix is built on
+// the device (one HBM-bound pass) and fed to the tcgen05 GEMM with its bias/ReLU/batch-norm epilogue;
+// the backward pass scatters dP back with the adjoint gather (fp32 accumulate, one fp16 rounding).
+// Activations stay height-major [T x H*F] with batch-norm per filter (SURVEY Appendix A / oracle header).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/kaldi_fp16_fused.h"
+#include "host_common.h"
+
+using namespace kfp16;
+
+namespace {
+
+constexpr int kMaxTaps = 32;
+struct Taps {
+  int n;
+  int8_t dt[kMaxTaps], dh[kMaxTaps];
+};
+
+struct ConvGeom {
+  int n_seq, L, halo, blk;   // rows: n_seq blocks of blk = L + 2*halo
+  int hin, hout, sub, fin, Kp;
+};
+
+// one thread per (row m = r*hout + ho, tap, 8-wide filter group) -- or scalar when fin % 8 != 0
+template <int VEC>
+__global__ void im2col_kernel(const __half* __restrict__ x, __half* __restrict__ P, ConvGeom g, Taps taps) {
+  const int fv = (g.fin + VEC - 1) / VEC;
+  const size_t rows = (size_t)g.n_seq * g.blk * g.hout;
+  const size_t total = rows * taps.n * fv;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int ldx = g.hin * g.fin;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int f = (int)(i % fv) * VEC;
+    size_t rest = i / fv;
+    const int tap = (int)(rest % taps.n);
+    const size_t m = rest / taps.n;
+    const int ho = (int)(m % g.hout);
+    const size_t r = m / g.hout;               // padded row
+    const int local = (int)(r % g.blk) - g.halo;
+    const int ts = local + taps.dt[tap];
+    const int hs = ho * g.sub + taps.dh[tap];
+    const bool ok = local >= 0 && local < g.L && ts >= 0 && ts < g.L && hs >= 0 && hs < g.hin;
+    __half* dst = P + m * g.Kp + (size_t)tap * g.fin + f;
+    if (VEC == 8) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ok) v = *reinterpret_cast<const uint4*>(x + (r + taps.dt[tap]) * ldx + (size_t)hs * g.fin + f);
+      *reinterpret_cast<uint4*>(dst) = v;
+    } else {
+      *dst = ok ? x[(r + taps.dt[tap]) * ldx + (size_t)hs * g.fin + f] : __float2half(0.f);
+    }
+  }
+}
+
+// zero the K padding columns [K, Kp) once per call (K = taps*fin not a multiple of 16)
+__global__ void zero_pad_cols_kernel(__half* __restrict__ P, size_t rows, int K, int Kp) {
+  const int padw = Kp - K;
+  const size_t total = rows * padw;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    P[(i / padw) * Kp + K + (i % padw)] = __float2half(0.f);
+}
+
+// adjoint: dx[r, h, f] = sum over taps with ho*sub + dh == h of dP[((r-dt)*hout + ho), tap*fin + f]
+template <int VEC>
+__global__ void col2im_kernel(const __half* __restrict__ dP, __half* __restrict__ dx, ConvGeom g, Taps taps) {
+  const int fv = (g.fin + VEC - 1) / VEC;
+  const size_t total = (size_t)g.n_seq * g.blk * g.hin * fv;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int f = (int)(i % fv) * VEC;
+    size_t rest = i / fv;
+    const int hh = (int)(rest % g.hin);
+    const size_t r = rest / g.hin;
+    const int local = (int)(r % g.blk) - g.halo;
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+    if (local >= 0 && local < g.L) {
+      for (int tap = 0; tap < taps.n; ++tap) {
+        const int to = local - taps.dt[tap];     // output frame that read this input frame through `tap`
+        const int hs = hh - taps.dh[tap];
+        if (to < 0 || to >= g.L || hs < 0 || (hs % g.sub) != 0) continue;
+        const int ho = hs / g.sub;
+        if (ho >= g.hout) continue;
+        const __half* src = dP + ((r - taps.dt[tap]) * g.hout + ho) * g.Kp + (size_t)tap * g.fin + f;
+        if (VEC == 8) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h2[e]); acc[2 * e] += t.x; acc[2 * e + 1] += t.y; }
+        } else {
+          acc[0] += __half2float(*src);
+        }
+      }
+    }
+    __half* dst = dx + r * (size_t)(g.hin * g.fin) + (size_t)hh * g.fin + f;
+    if (VEC == 8) {
+      uint4 o;
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+      *reinterpret_cast<uint4*>(dst) = o;
+    } else {
+      *dst = __float2half_rn(acc[0]);
+    }
+  }
+}
+
+int grid_for_elems(size_t work) {
+  size_t blocks = (work + 255) / 256;
+  const size_t cap = 148 * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+bool fill_geom(ConvGeom& g, Taps& t, int n_seq, int seq_len, int halo, int hin, int hout, int sub, int fin, int Kp,
+               int ntaps, const int* dt, const int* dh, const char* who) {
+  if (ntaps < 1 || ntaps > kMaxTaps) { set_error("%s: 1..%d taps supported (got %d)", who, kMaxTaps, ntaps); return false; }
+  if (n_seq <= 0 || seq_len <= 0 || halo < 0 || hin <= 0 || hout <= 0 || sub <= 0 || fin <= 0 || Kp < ntaps * fin) {
+    set_error("%s: bad geometry", who); return false;
+  }
+  g.n_seq = n_seq; g.L = seq_len; g.halo = halo; g.blk = seq_len + 2 * halo;
+  g.hin = hin; g.hout = hout; g.sub = sub; g.fin = fin; g.Kp = Kp;
+  t.n = ntaps;
+  for (int i = 0; i < ntaps; ++i) {
+    if (dt[i] < -halo - 64 || dt[i] > 127 || dh[i] < -128 || dh[i] > 127) { set_error("%s: tap offset out of range", who); return false; }
+    t.dt[i] = (int8_t)dt[i]; t.dh[i] = (int8_t)dh[i];
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kfp16_im2col(kfp16_ctx* ctx, const void* x, void* P, int Kp, int n_seq, int seq_len, int halo, int hin, int hout,
+                 int sub, int fin, int ntaps, const int* dt, const int* dh) {
+  if (!x || !P) { set_error("kfp16_im2col: null pointer"); return -1; }
+  ConvGeom g; Taps t;
+  if (!fill_geom(g, t, n_seq, seq_len, halo, hin, hout, sub, fin, Kp, ntaps, dt, dh, "kfp16_im2col")) return -1;
+  cudaStream_t s = ctx ? ctx->stream : default_stream();
+  const size_t rows = (size_t)n_seq * g.blk * hout;
+  const int K = ntaps * fin;
+  if (Kp > K) {
+    zero_pad_cols_kernel<<<grid_for_elems(rows * (Kp - K)), 256, 0, s>>>((__half*)P, rows, K, Kp);
+    count_launch();
+  }
+  const bool vec = (fin % 8) == 0 && (Kp % 8) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)P & 15) == 0;
+  if (vec) im2col_kernel<8><<<grid_for_elems(rows * ntaps * (fin / 8)), 256, 0, s>>>((const __half*)x, (__half*)P, g, t);
+  else im2col_kernel<1><<<grid_for_elems(rows * ntaps * fin), 256, 0, s>>>((const __half*)x, (__half*)P, g, t);
+  count_launch();
+  return check_launch("kfp16_im2col") ? 0 : -1;
+}
+
+int kfp16_col2im(kfp16_ctx* ctx, const void* dP, int Kp, void* dx, int n_seq, int seq_len, int halo, int hin, int hout,
+                 int sub, int fin, int ntaps, const int* dt, const int* dh) {
+  if (!dP || !dx) { set_error("kfp16_col2im: null pointer"); return -1; }
+  ConvGeom g; Taps t;
+  if (!fill_geom(g, t, n_seq, seq_len, halo, hin, hout, sub, fin, Kp, ntaps, dt, dh, "kfp16_col2im")) return -1;
+  cudaStream_t s = ctx ? ctx->stream : default_stream();
+  const size_t elems = (size_t)n_seq * g.blk * hin;
+  const bool vec = (fin % 8) == 0 && (Kp % 8) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)dP & 15) == 0;
+  if (vec) col2im_kernel<8><<<grid_for_elems(elems * (fin / 8)), 256, 0, s>>>((const __half*)dP, (__half*)dx, g, t);
+  else col2im_kernel<1><<<grid_for_elems(elems * fin), 256, 0, s>>>((const __half*)dP, (__half*)dx, g, t);
+  count_launch();
+  return check_launch("kfp16_col2im") ? 0 : -1;
+}
+
+}  // extern "C"

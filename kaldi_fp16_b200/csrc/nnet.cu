@@ -88,6 +88,9 @@ struct Layer {
   bool log_softmax = false;
   // combine-feature-maps
   int height = 0, nf1 = 1, nf2 = 1;
+  // conv-relu-batchnorm
+  int hin = 0, hout = 0, hsub = 1, fin = 0, fout = 0, convK = 0, convKp = 0;
+  std::vector<int> tap_dt, tap_dh;
   int grads_seen = 0;
 };
 
@@ -104,6 +107,8 @@ struct kfp16_net {
   float *w32 = nullptr, *vel = nullptr, *g32 = nullptr;
   float* loss_dev = nullptr;
   std::vector<void*> allocs;
+  __half *conv_P = nullptr, *conv_dP = nullptr, *conv_dz = nullptr;   // shared conv scratch (patches, patch grads, dZ)
+  size_t conv_P_elems = 0, conv_dz_elems = 0;
   __half* stage_in = nullptr;   // dense staging for host uploads / downloads
   size_t stage_bytes = 0;
   double flops_fwd = 0;
@@ -396,9 +401,31 @@ bool resolve_dims(kfp16_net* n) {
           return false;
         }
         break;
-      case L_CONV:
-        set_error("conv-relu-batchnorm-layer %s: not wired into this executor build yet", l.name.c_str());
-        return false;
+      case L_CONV: {   // forward.go:418-524; dims as layers.go resolves them
+        l.hin = kv_int(l, "height-in", 0);
+        l.hout = kv_int(l, "height-out", l.hin);
+        l.hsub = kv_int(l, "height-subsample-out", 1);
+        l.fout = kv_int(l, "num-filters-out", 0);
+        if (l.hin <= 0 || l.hout <= 0 || l.hsub <= 0 || l.fout <= 0 || (l.in_dim % l.hin)) {
+          set_error("conv-relu-batchnorm-layer %s: needs height-in dividing the input dim (%d), height-out, num-filters-out", l.name.c_str(), l.in_dim);
+          return false;
+        }
+        l.fin = l.in_dim / l.hin;
+        std::vector<int> to = kv_ints(l, "time-offsets"), ho = kv_ints(l, "height-offsets");
+        if (to.empty()) to.push_back(0);
+        if (ho.empty()) ho.push_back(0);
+        if (n->opts.conv_cartesian) {     // Kaldi: time x height Cartesian product (quirk Q4 fixed)
+          for (int dt : to) for (int dh : ho) { l.tap_dt.push_back(dt); l.tap_dh.push_back(dh); }
+        } else {                          // the reference pairs them (forward.go:426-446)
+          for (size_t k = 0; k < to.size(); ++k) { l.tap_dt.push_back(to[k]); l.tap_dh.push_back(ho[k < ho.size() ? k : ho.size() - 1]); }
+        }
+        if (l.tap_dt.size() > 32) { set_error("conv-relu-batchnorm-layer %s: more than 32 taps", l.name.c_str()); return false; }
+        for (int dt : l.tap_dt) if (abs(dt) >= n->opts.seq_len) { set_error("conv layer %s: time offset %d exceeds the sequence length", l.name.c_str(), dt); return false; }
+        l.convK = (int)l.tap_dt.size() * l.fin;
+        l.convKp = (l.convK + 15) & ~15;
+        l.out_dim = l.hout * l.fout;
+        break;
+      }
       case L_TDNNF:
         l.out_dim = kv_int(l, "dim", 0);
         l.bott_dim = kv_int(l, "bottleneck-dim", 0);
@@ -494,6 +521,10 @@ bool build_plan(kfp16_net* n) {
         l.pW = add_param(n, l.name + ".W", l.in_dim, l.out_dim);
         l.pB = add_param(n, l.name + ".Bias", 1, l.out_dim, true);
         break;
+      case L_CONV:
+        l.pW = add_param(n, l.name + ".W", l.convK, l.fout);
+        l.pB = add_param(n, l.name + ".Bias", 1, l.fout, true);
+        break;
       default: break;
     }
   }
@@ -509,12 +540,23 @@ bool build_plan(kfp16_net* n) {
   size_t max_dense = 16;
   for (auto& l : n->layers) {
     const int rows = l.per_seq ? n->opts.n_seq : n->Tp;
-    if (!check_tma_dim(l, l.out_dim, "output dim")) return false;
+    // input layers may have any dim (the 100-dim ivector): their rows are stored 8-column aligned with zero
+    // padding and a linear consumer reads the padded width (the weight rows past in_dim are TMA-out-of-bounds zeros)
+    const int store_dim = l.type == L_INPUT ? ((l.out_dim + 7) & ~7) : l.out_dim;
+    if (l.type != L_INPUT && !check_tma_dim(l, l.out_dim, "output dim")) return false;
+    if (l.type == L_INPUT && store_dim != l.out_dim) {
+      for (auto& c : n->layers)
+        for (int src : c.in)
+          if (&n->layers[src] == &l && (c.in.size() != 1 || c.type != L_LINEAR)) {
+            set_error("input %s: dim %d is not a multiple of 8; only a direct linear-component consumer is supported", l.name.c_str(), l.out_dim);
+            return false;
+          }
+    }
     if (l.in.size() > 1) {
       if (!alloc_buf(n, l.in_cat, rows, l.in_dim)) return false;
       if (train && l.needs_grad && l.wants_dx && !alloc_buf(n, l.d_in_cat, rows, l.in_dim)) return false;
     }
-    if (!alloc_buf(n, l.out, rows, l.out_dim)) return false;
+    if (!alloc_buf(n, l.out, rows, store_dim)) return false;
     max_dense = std::max(max_dense, (size_t)n->T * l.out_dim * sizeof(__half));
     if (train && l.needs_grad) {
       if (!alloc_buf(n, l.dout, rows, l.out_dim)) return false;
@@ -538,7 +580,6 @@ bool build_plan(kfp16_net* n) {
         break;
       }
       case L_LINEAR:
-        if (!check_tma_dim(l, l.in_dim, "input dim")) return false;
         n->flops_fwd += 2.0 * M * l.in_dim * l.out_dim;
         break;
       case L_BATCHNORM: {
@@ -584,7 +625,26 @@ bool build_plan(kfp16_net* n) {
         if (!check_tma_dim(l, l.in_dim, "input dim")) return false;
         n->flops_fwd += 2.0 * M * l.in_dim * l.out_dim;
         break;
+      case L_CONV: {
+        if (l.per_seq) { set_error("conv layer %s on a per-sequence input", l.name.c_str()); return false; }
+        if (!check_tma_dim(l, l.fout, "num-filters-out")) return false;
+        if (!make_bn(n, l.bn, l.fout, 1.0f, false)) return false;   // per filter
+        const size_t mrows = (size_t)n->Tp * l.hout;
+        l.mask_ld = (l.fout + 31) / 32;
+        if (!dev_alloc(n, (void**)&l.mask, mrows * l.mask_ld * 4)) return false;
+        n->conv_P_elems = std::max(n->conv_P_elems, mrows * l.convKp);
+        n->conv_dz_elems = std::max(n->conv_dz_elems, mrows * l.fout);
+        n->flops_fwd += 2.0 * M * l.hout * l.convK * l.fout;
+        break;
+      }
       default: break;
+    }
+  }
+  if (n->conv_P_elems) {
+    if (!dev_alloc(n, (void**)&n->conv_P, n->conv_P_elems * 2, false)) return false;
+    if (train) {
+      if (!dev_alloc(n, (void**)&n->conv_dP, n->conv_P_elems * 2, false)) return false;
+      if (!dev_alloc(n, (void**)&n->conv_dz, n->conv_dz_elems * 2, false)) return false;
     }
   }
   n->stage_bytes = max_dense;
@@ -622,7 +682,7 @@ float* G32(kfp16_net* n, int p) { return n->g32 + n->params[p].off; }
 
 // dW[in x out] (+)= X^T * dY, fp32 into the gradient bucket.  Up to two row-shifted groups (splice).
 int wgrad(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int off0, int off1) {
-  const int in = X.cols, out = dY.cols;
+  const int in = n->params[param].rows / groups, out = dY.cols;   // <= X.cols (padded input storage)
   kfp16_gemm_desc d = mk_desc(in, out, X.rows);
   d.a_major = KFP16_MN_MAJOR;
   set_A(d, X.p, X.rows, X.cols);
@@ -713,8 +773,8 @@ int forward_layer(kfp16_net* n, Layer& l) {
       break;
     }
     case L_LINEAR: {   // Y = h(X*W)  forward.go:333-346
-      kfp16_gemm_desc d = mk_desc(rows, l.out_dim, l.in_dim);
-      set_A(d, X.p, rows, l.in_dim);
+      kfp16_gemm_desc d = mk_desc(rows, l.out_dim, X.cols);   // X.cols >= in_dim: zero-padded storage width
+      set_A(d, X.p, rows, X.cols);
       set_B(d, W16(n, l.pW), l.in_dim, l.out_dim);
       d.D[0] = l.out.p; d.ldd = l.out_dim;
       if (kfp16_gemm_ex(ctx, &d)) return -1;
@@ -775,6 +835,21 @@ int forward_layer(kfp16_net* n, Layer& l) {
       e.flags = KFP16_EPI_BN | rr;
       e.bn_scale = l.bn2.scale; e.bn_shift = l.bn2.shift;
       if (kfp16_gemm_ex(ctx, &e)) return -1;
+      break;
+    }
+    case L_CONV: {       // forward.go:418-524 with the im2col on the device; Z = BN(ReLU(P*W + b)) per filter
+      const int mrows = rows * l.hout;
+      if (kfp16_im2col(ctx, X.p, n->conv_P, l.convKp, n->opts.n_seq, n->opts.seq_len, n->halo, l.hin, l.hout, l.hsub, l.fin,
+                       (int)l.tap_dt.size(), l.tap_dt.data(), l.tap_dh.data())) return -1;
+      kfp16_gemm_desc d = mk_desc(mrows, l.fout, l.convKp);
+      set_A(d, n->conv_P, mrows, l.convKp);
+      set_B(d, W16(n, l.pW), l.convK, l.fout);          // rows [convK, convKp) read as zeros (TMA bounds)
+      d.D[0] = l.out.p; d.ldd = l.fout;
+      d.flags = KFP16_EPI_BIAS | KFP16_EPI_RELU | KFP16_EPI_BN | KFP16_EPI_MASK | rr;
+      d.bias = W16(n, l.pB);
+      d.bn_scale = l.bn.scale; d.bn_shift = l.bn.shift;
+      d.mask_out = l.mask; d.mask_ld = l.mask_ld;
+      if (kfp16_gemm_ex(ctx, &d)) return -1;
       break;
     }
     case L_OUTPUT: {     // forward.go:971-1001
@@ -890,6 +965,32 @@ int backward_layer(kfp16_net* n, Layer& l) {
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
       if (wgrad(n, X, l.dbig, l.pBig, 1, 0, 0)) return -1;
+      break;
+    }
+    case L_CONV: {     // transpose of the forward (the reference treats the conv as a dense affine: quirk Q2)
+      const int mrows = rows * l.hout;
+      if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.fout, l.bn.scale, l.mask, l.mask_ld, n->conv_dz, l.fout, mrows, l.fout, G32(n, l.pB))) return -1;
+      if (kfp16_im2col(ctx, X.p, n->conv_P, l.convKp, n->opts.n_seq, n->opts.seq_len, n->halo, l.hin, l.hout, l.hsub, l.fin,
+                       (int)l.tap_dt.size(), l.tap_dt.data(), l.tap_dh.data())) return -1;
+      {  // dW[K x fout] = P^T dZ
+        kfp16_gemm_desc d = mk_desc(l.convK, l.fout, mrows);
+        d.a_major = KFP16_MN_MAJOR;
+        set_A(d, n->conv_P, mrows, l.convKp);
+        set_B(d, n->conv_dz, mrows, l.fout);
+        d.split_k = pick_split_k(n, l.convK, l.fout, 1, mrows);
+        d.ws[0] = G32(n, l.pW); d.ws_ld = l.fout;
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+      }
+      if (l.wants_dx) {   // dP = dZ W^T, then the adjoint of the patch gather
+        kfp16_gemm_desc d = mk_desc(mrows, l.convKp, l.fout);
+        set_A(d, n->conv_dz, mrows, l.fout);
+        d.b_major = KFP16_K_MAJOR;
+        set_B(d, W16(n, l.pW), l.convK, l.fout);
+        d.D[0] = n->conv_dP; d.ldd = l.convKp;
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
+        if (kfp16_col2im(ctx, n->conv_dP, l.convKp, dx.p, n->opts.n_seq, n->opts.seq_len, n->halo, l.hin, l.hout, l.hsub, l.fin,
+                         (int)l.tap_dt.size(), l.tap_dt.data(), l.tap_dh.data())) return -1;
+      }
       break;
     }
     case L_OUTPUT: {   // log-softmax Jacobian is not applied (network_backward.go:243-244)
@@ -1058,9 +1159,10 @@ static int set_input_common(kfp16_net* n, const char* input_name, const void* de
     return -1;
   }
   if (l.per_seq)
-    return check_cuda(cudaMemcpyAsync(l.out.p, dense_dev, (size_t)rows * cols * 2, cudaMemcpyDeviceToDevice, n->ctx->stream), "input copy") ? 0 : -1;
+    return check_cuda(cudaMemcpy2DAsync(l.out.p, (size_t)l.out.cols * 2, dense_dev, (size_t)cols * 2, (size_t)cols * 2, rows,
+                                        cudaMemcpyDeviceToDevice, n->ctx->stream), "input copy") ? 0 : -1;
   // halo rows: replicate for spliced consumers, zero otherwise (finite values either way)
-  return kfp16_pack_rows(n->ctx, dense_dev, l.out.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, n->halo, cols, l.halo_mode == HALO_ZERO ? 0 : 1);
+  return kfp16_pack_rows(n->ctx, dense_dev, l.out.p, l.out.cols, n->opts.n_seq, n->opts.seq_len, n->halo, cols, l.halo_mode == HALO_ZERO ? 0 : 1);
 }
 int kfp16_net_set_input_device(kfp16_net* n, const char* input_name, const void* dev, int rows, int cols) {
   if (!n || !input_name || !dev) { set_error("kfp16_net_set_input_device: null argument"); return -1; }
@@ -1121,12 +1223,19 @@ int kfp16_net_get_mask(kfp16_net* n, const char* layer, uint8_t* host, int rows,
   const int prow = l.per_seq ? n->opts.n_seq : n->Tp;
   const int want_rows = l.per_seq ? n->opts.n_seq : n->T;
   if (rows != want_rows || cols != dim) { set_error("kfp16_net_get_mask: %s mask is [%d x %d]", layer, want_rows, dim); return -1; }
-  std::vector<uint32_t> words((size_t)prow * l.mask_ld);
+  // conv layers keep one mask row per (frame, height): [Tp*hout x fout] == [Tp x hout*fout] in memory
+  const int sub_rows = l.type == L_CONV ? l.hout : 1;
+  const int sub_cols = l.type == L_CONV ? l.fout : cols;
+  std::vector<uint32_t> words((size_t)prow * sub_rows * l.mask_ld);
   if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "sync")) return -1;
   if (!check_cuda(cudaMemcpy(words.data(), l.mask, words.size() * 4, cudaMemcpyDeviceToHost), "mask download")) return -1;
   for (int r = 0; r < rows; ++r) {
     const int pr = l.per_seq ? r : (r / n->opts.seq_len) * n->blk + n->halo + (r % n->opts.seq_len);
-    for (int c = 0; c < cols; ++c) host[(size_t)r * cols + c] = (words[(size_t)pr * l.mask_ld + (c >> 5)] >> (c & 31)) & 1u;
+    for (int c = 0; c < cols; ++c) {
+      const size_t mrow = (size_t)pr * sub_rows + c / sub_cols;
+      const int mc = c % sub_cols;
+      host[(size_t)r * cols + c] = (words[mrow * l.mask_ld + (mc >> 5)] >> (mc & 31)) & 1u;
+    }
   }
   return 0;
 }

@@ -264,3 +264,64 @@ def test_xconfig_errors(handle, lib):
         with pytest.raises(nnet.NNetError) as e:
             nnet.NewNetwork(nnet.BuildModelFromString(bad), handle, 1, 8)
         assert frag.decode() in str(e.value), str(e.value)
+
+
+# ------------------------------------------------------------------ CNN front-end (conv-relu-batchnorm-layer)
+CNN_SMALL = """
+input dim=24 name=ivector
+input dim=16 name=input
+idct-layer name=idct input=input dim=16 cepstral-lifter=22
+linear-component name=ivector-linear dim=32 input=ReplaceIndex(ivector, t, 0)
+batchnorm-component name=ivector-batchnorm target-rms=0.025
+batchnorm-component name=idct-batchnorm input=idct
+combine-feature-maps-layer name=combine_inputs input=Append(idct-batchnorm, ivector-batchnorm) num-filters1=1 num-filters2=2 height=16
+conv-relu-batchnorm-layer name=cnn1 height-in=16 height-out=16 time-offsets=-1,0,1 height-offsets=-1,0,1 num-filters-out=32
+conv-relu-batchnorm-layer name=cnn2 height-in=16 height-out=8 height-subsample-out=2 time-offsets=-1,0,1 height-offsets=-1,0,1 num-filters-out=64
+conv-relu-batchnorm-layer name=cnn3 height-in=8 height-out=8 time-offsets=-1,0,1 height-offsets=-1,0,1 num-filters-out=64
+tdnnf-layer name=tdnnf4 dim=256 bottleneck-dim=64 time-stride=0
+tdnnf-layer name=tdnnf5 dim=256 bottleneck-dim=64 time-stride=3
+output-layer name=output include-log-softmax=false dim=72
+"""
+
+
+def check_conv_net(handle, n_seq, L, seed):
+    on, net, rng = make_pair(handle, CNN_SMALL, n_seq, L, seed=seed)
+    x = O.to_f16_rne((rng.standard_normal((n_seq * L, 16)) * 2).astype(np.float32))
+    iv = O.to_f16_rne(np.clip(rng.standard_normal((n_seq, 24)), -3, 3).astype(np.float32))
+    inputs = {"input": x, "ivector": iv}
+    acts = on.forward(inputs)
+    net.MarkPerSequence("ivector", "ivector-linear", "ivector-batchnorm")
+    net.SetInput("input", x)
+    net.SetInput("ivector", iv)
+    assert net.lib.kfp16_net_forward(net.ptr) == 0
+    for l in on.layers:
+        if l.type == "input":
+            continue
+        err = rel_to_scale(net.Output(l.name), acts[l.name])
+        assert err <= 2e-3, f"forward {l.name}: err {err:.2e}"
+    masks = {}
+    for l in on.layers:
+        if l.type in ("tdnnf-layer", "conv-relu-batchnorm-layer"):
+            want = on.saved[l.name]["mask"]
+            got = net.Mask(l.name, l.out_dim).reshape(want.shape)
+            assert np.mean(got != want) < 5e-3, f"relu mask {l.name}: {np.mean(got != want):.2%} differ"
+            masks[l.name] = got
+    wg, dact = on.backward("output", acts["output"], masks)
+    net.ZeroGrads()
+    net.Backward(None)
+    got_wg = net.WeightGrads()
+    for k, g in wg.items():
+        err = rel_to_scale(got_wg[k], g)
+        tol = 1e-2 if k.endswith("Bias") else 5e-3
+        assert err <= tol, f"weight grad {k}: err {err:.2e} > {tol}"
+    for name in ("cnn3", "cnn1", "combine_inputs"):
+        err = rel_to_scale(net.Grad(name), dact[name])
+        assert err <= 5e-3, f"activation grad {name}: err {err:.2e}"
+    net.Free()
+
+
+@pytest.mark.parametrize("n_seq,L", [(2, 30), (3, 17)])
+def test_cnn_front_end_forward_backward(handle, n_seq, L):
+    """conv-relu-batchnorm layers (3x3 Cartesian taps, height subsampling, 3-filter input with K = 27 padded
+    to 32) lowered to im2col + tcgen05 GEMM, against the numpy oracle's explicit patch matrices"""
+    check_conv_net(handle, n_seq, L, seed=5 + n_seq)
