@@ -173,6 +173,26 @@ SIGNATURES: dict[str, tuple] = {
     "ops_sgd_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int]),
     "ops_last_error": (C.c_char_p, []),
     "ops_clear_error": (None, []),
+    # ---- kaldi_fp16_cnn.h (go/kaldibridge surface)
+    "kaldi_get_last_error": (C.c_char_p, []), "kaldi_clear_error": (None, []),
+    "kaldi_cublas_create": (c_void_p, []), "kaldi_cublas_destroy": (None, [c_void_p]),
+    "kaldi_cublas_enable_tensor_cores": (None, [c_void_p]),
+    "kaldi_tensor_create": (c_void_p, [c_int, c_int]), "kaldi_tensor_zeros": (c_void_p, [c_int, c_int]),
+    "kaldi_tensor_ones": (c_void_p, [c_int, c_int]), "kaldi_tensor_free": (None, [c_void_p]),
+    "kaldi_tensor_rows": (c_int, [c_void_p]), "kaldi_tensor_cols": (c_int, [c_void_p]), "kaldi_tensor_size": (c_size_t, [c_void_p]),
+    "kaldi_tensor_copy_from_host_fp32": (None, [c_void_p, c_void_p, c_size_t]),
+    "kaldi_tensor_copy_to_host_fp32": (None, [c_void_p, c_void_p, c_size_t]),
+    "kaldi_gemm": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int]),
+    "kaldi_relu": (None, [c_void_p]), "kaldi_sigmoid": (None, [c_void_p]), "kaldi_tanh": (None, [c_void_p]),
+    "kaldi_softmax": (None, [c_void_p]), "kaldi_add": (None, [c_void_p, c_void_p]), "kaldi_scale": (None, [c_void_p, c_float]),
+    "kaldi_loss_scaler_create": (c_void_p, [c_float]), "kaldi_loss_scaler_free": (None, [c_void_p]),
+    "kaldi_loss_scaler_get_scale": (c_float, [c_void_p]), "kaldi_loss_scaler_update": (None, [c_void_p, c_int]),
+    "launch_conv1d_forward_fp16": (None, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
+    "launch_conv1d_backward_fp16": (None, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
+    "launch_maxpool1d_forward_fp16": (None, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
+    "launch_maxpool1d_backward_fp16": (None, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
+    "launch_batchnorm1d_forward_fp16": (None, [c_void_p] * 8 + [c_int] * 3 + [c_float, c_float, C.c_bool, c_void_p]),
+    "launch_pointwise_conv1d_fp16": (None, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     # ---- kaldi_fp16_bridge.h
     "bridge_last_error": (C.c_char_p, []),
     "bridge_clear_error": (None, []),

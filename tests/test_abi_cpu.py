@@ -116,3 +116,29 @@ def test_product_package_never_imports_the_oracle():
         assert "import oracle" not in text and "from oracle" not in text, f"{py} imports the oracle"
     for src in (ROOT / "kaldi_fp16_b200" / "csrc").iterdir():
         assert "#include \"../../oracle" not in src.read_text() and "gotorch_port" not in src.read_text(), src
+
+
+def test_loss_scaler_host_logic(built_lib):
+    """kaldi_loss_scaler_* (cgo_interface.cu:405-449): x0.5 on overflow, x2 after 2000 clean steps, clamped to [1, 65536]"""
+    from kaldi_fp16_b200 import _lib
+
+    lib = _lib.load()
+    s = lib.kaldi_loss_scaler_create(1024.0)
+    assert lib.kaldi_loss_scaler_get_scale(s) == 1024.0
+    lib.kaldi_loss_scaler_update(s, 1)
+    assert lib.kaldi_loss_scaler_get_scale(s) == 512.0
+    for _ in range(1999):
+        lib.kaldi_loss_scaler_update(s, 0)
+    assert lib.kaldi_loss_scaler_get_scale(s) == 512.0
+    lib.kaldi_loss_scaler_update(s, 0)
+    assert lib.kaldi_loss_scaler_get_scale(s) == 1024.0
+    for _ in range(12):
+        lib.kaldi_loss_scaler_update(s, 1)
+    assert lib.kaldi_loss_scaler_get_scale(s) == 1.0
+    lib.kaldi_loss_scaler_free(s)
+    big = lib.kaldi_loss_scaler_create(65536.0)
+    for _ in range(2000):
+        lib.kaldi_loss_scaler_update(big, 0)
+    assert lib.kaldi_loss_scaler_get_scale(big) == 65536.0
+    lib.kaldi_loss_scaler_free(big)
+    assert lib.kaldi_loss_scaler_get_scale(None) == 1.0
