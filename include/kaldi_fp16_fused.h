@@ -92,6 +92,7 @@ typedef struct {
     int split_k;
     float *ws[2];
     int ws_ld;
+    int ws_transposed; /* 1: the split-K target is D^T, fp32 [N x M] with ld ws_ld >= M (weight gradients computed as dY^T * X) */
     float drop_p;
     uint32_t drop_seed;
     int force_bn; /* 0 = heuristic tile width; else 64/128/160/256 */

@@ -37,7 +37,7 @@ class GemmDesc(C.Structure):
         ("bias", c_void_p), ("bn_scale", c_void_p), ("bn_shift", c_void_p),
         ("vec_gstride", c_int),
         ("mask_out", c_void_p), ("mask_in", c_void_p), ("mask_ld", c_int),
-        ("split_k", c_int), ("ws", c_void_p * 2), ("ws_ld", c_int),
+        ("split_k", c_int), ("ws", c_void_p * 2), ("ws_ld", c_int), ("ws_transposed", c_int),
         ("drop_p", c_float), ("drop_seed", c_u32),
         ("force_bn", c_int), ("force_generic", c_int), ("force_cg", c_int), ("no_share", c_int), ("debug_clock_buf", c_void_p),
     ]

@@ -300,6 +300,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   p.vec_gstride = d->vec_gstride;
   p.mask_out = d->mask_out; p.mask_in = d->mask_in; p.mask_ld = d->mask_ld;
   p.ws_ld = d->ws_ld;
+  p.ws_transposed = d->ws_transposed;
   p.drop_p = d->drop_p; p.drop_seed = d->drop_seed;
   if ((flags & EPI_BIAS) && !p.bias) { set_error("kfp16_gemm_ex: EPI_BIAS without bias"); return -1; }
   if ((flags & EPI_BN) && (!p.bn_scale || !p.bn_shift)) { set_error("kfp16_gemm_ex: EPI_BN without scale/shift"); return -1; }
@@ -308,7 +309,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
 
   for (int g = 0; g < groups; ++g) {
     if (flags & EPI_SPLITK) {
-      if (!d->ws[g] || d->ws_ld < d->N || (d->ws_ld % 4) || !aligned16(d->ws[g])) {
+      if (d->ws_transposed ? (!d->ws[g] || d->ws_ld < d->M) : (!d->ws[g] || d->ws_ld < d->N || (d->ws_ld % 4) || !aligned16(d->ws[g]))) {
         set_error("kfp16_gemm_ex: split-K needs a 16B-aligned fp32 workspace with ws_ld >= N, ws_ld %% 4 == 0"); return -1;
       }
       p.ws[g] = d->ws[g];

@@ -97,6 +97,7 @@ struct GemmParams {
   int mask_ld;
   float* ws[kMaxGroups];        // split-K fp32 accumulation target [M x ws_ld]
   int ws_ld;
+  int ws_transposed;            // split-K target is stored [N x M] (ws[n*ws_ld + m]): warp lanes = consecutive m
   float drop_p; uint32_t drop_seed;
   // shared splice tile (SHARE kernels): slab s reads the A tile from row a_shift[s] (0..8) on
   int a_shift[kMaxSlabs];
@@ -470,7 +471,17 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           uint32_t v[32];
           tmem_ld_32x32(t_acc + c, v);
           tmem_ld_wait();
-          if (row < p.M) {
+          if (p.ws_transposed) {
+            // D^T accumulation: element (row, col) -> ws[col*ws_ld + row]; the 32 lanes of a warp hold 32
+            // consecutive rows, so each red is one coalesced 128-byte line
+            if (row < p.M) {
+              float* wcol = p.ws[g] + (size_t)(n0 + c) * p.ws_ld + row;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c + j < p.N)
+                  asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(wcol + (size_t)j * p.ws_ld), "f"(__uint_as_float(v[j]) * p.alpha) : "memory");
+            }
+          } else if (row < p.M) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const int col = n0 + c + j;

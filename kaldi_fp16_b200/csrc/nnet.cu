@@ -667,13 +667,18 @@ void set_A(kfp16_gemm_desc& d, const void* p, int rows, int cols) { d.A.ptr = p;
 void set_B(kfp16_gemm_desc& d, const void* p, int rows, int cols) { d.B.ptr = p; d.B.rows = rows; d.B.cols = cols; d.B.ld = cols; d.B.halo = 0; }
 
 int pick_split_k(const kfp16_net* n, int M, int N, int groups, int K) {
-  const int m_tiles = (M + 127) / 128;
+  // work items = tiles * splits should fill ONE wave of CTA pairs (256-row tiles) as evenly as possible:
+  // every extra split costs another fp32 red pass over the tile, every partial wave idles SMs
+  const int cg = M > 128 ? 2 : 1;
+  const int m_tiles = (M + 128 * cg - 1) / (128 * cg);
   const int bn = N <= 64 ? 64 : N <= 128 ? 128 : N <= 160 ? 160 : 256;
   const int n_tiles = (N + bn - 1) / bn;
   const int tiles = m_tiles * n_tiles * groups;
+  const int units = std::max(1, n->ctx->num_sms / cg);
   const int kb = (K + 63) / 64;
-  int split = (2 * n->ctx->num_sms + tiles - 1) / tiles;
-  split = std::min(split, std::max(1, kb / 4));
+  int split = units / tiles;                       // largest split that still fits one wave
+  if (split < 1) split = 1;
+  split = std::min(split, std::max(1, kb / 4));    // keep >= 4 k-blocks per item
   return std::max(split, 2);   // >= 2 selects the fp32 accumulate path into the gradient bucket
 }
 
@@ -683,14 +688,26 @@ float* G32(kfp16_net* n, int p) { return n->g32 + n->params[p].off; }
 // dW[in x out] (+)= X^T * dY, fp32 into the gradient bucket.  Up to two row-shifted groups (splice).
 int wgrad(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int off0, int off1) {
   const int in = n->params[param].rows / groups, out = dY.cols;   // <= X.cols (padded input storage)
-  kfp16_gemm_desc d = mk_desc(in, out, X.rows);
+  // Orientation: the UMMA M dimension should be the LONG side of dW.  For a narrow `in` (the 160-wide
+  // TDNN-F bottleneck, 256-wide prefinal) compute dW^T = dY^T * X instead -- M = out fills whole 256-row pair
+  // tiles, N = in is one tile wide -- and accumulate transposed into the same [in x out] bucket section.
+  const bool transposed = out > in && in <= 256 && (in % 8) == 0 && X.cols == in;
+  kfp16_gemm_desc d = transposed ? mk_desc(out, in, X.rows) : mk_desc(in, out, X.rows);
   d.a_major = KFP16_MN_MAJOR;
-  set_A(d, X.p, X.rows, X.cols);
-  set_B(d, dY.p, dY.rows, dY.cols);
   d.groups = groups;
-  d.a_row_off[0][0] = off0;
-  d.a_row_off[1][0] = off1;
-  d.split_k = pick_split_k(n, in, out, groups, X.rows);
+  if (transposed) {
+    set_A(d, dY.p, dY.rows, dY.cols);
+    set_B(d, X.p, X.rows, X.cols);
+    d.b_row_off[0][0] = off0;
+    d.b_row_off[1][0] = off1;
+    d.ws_transposed = 1;
+  } else {
+    set_A(d, X.p, X.rows, X.cols);
+    set_B(d, dY.p, dY.rows, dY.cols);
+    d.a_row_off[0][0] = off0;
+    d.a_row_off[1][0] = off1;
+  }
+  d.split_k = pick_split_k(n, d.M, d.N, groups, X.rows);
   d.ws[0] = G32(n, param);
   d.ws[1] = G32(n, param) + (size_t)in * out;
   d.ws_ld = out;
