@@ -7,7 +7,7 @@
 // One persistent CTA per SM, 12 warps, warp-specialised:
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      MMA issuer     (one elected thread, tcgen05.mma kind::f16, M=128 x N=BN x K=16)
-//   warp 2      TMEM allocator
+//   warp 2      TMEM allocator, then output store warp (TMA stores of finished 64-column chunks)
 //   warp 3      residual / C-in prefetcher (TMA loads of the R tile, two 64-column chunks ahead)
 //   warps 4..11 epilogue       (tcgen05.ld -> fused epilogue -> swizzled smem -> TMA store,
 //                               or fp32 red.add for split-K).  Warp w owns TMEM lanes
@@ -142,7 +142,7 @@ struct GemmCfg {
   static constexpr int kRing = kSplitK ? 0 : (kMayUseR ? (BN <= 160 ? 6 : 4) : 4);
   // TMA stores left in flight when a chunk is handed over (a store's smem-read latency is ~1000 cycles:
   // with none in flight every 64-column chunk paid it in full)
-  static constexpr int kStoreWait = kRing == 6 ? 3 : (kMayUseR ? 1 : 2);
+  static constexpr int kStoreWait = kRing == 6 ? 3 : (kMayUseR ? 1 : 2);   // < kRing
   static constexpr int kUmmaM = kBM * CG;                      // 256 rows over a CTA pair
   static constexpr int kBNLocal = BN / CG;                     // B rows / columns staged by this CTA
   static constexpr int kBChunks = B_MN ? (kBNLocal + 63) / 64 : 1;   // 64-wide N chunks (MN-major)
@@ -213,8 +213,9 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue     (CG=2: commit multicast)
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]        epilogue -> MMA     (CG=2: the leader's, 16 arrivals)
   uint64_t* rfull_bar = tempty_bar + 2;       // [8]        residual TMA -> epilogue
-  uint64_t* rempty_bar = rfull_bar + 8;       // [8]        output store drained -> residual TMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + 8);
+  uint64_t* rempty_bar = rfull_bar + 8;       // [8]        output store drained -> residual TMA / next writer
+  uint64_t* cfull_bar = rempty_bar + 8;       // [8]        epilogue warps wrote a chunk -> store warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -240,7 +241,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], CG * (kEpiThreads / 32));   // one arrive per epilogue warp (of both CTAs)
     }
-    for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 1); mbar_init(&cfull_bar[i], kEpiThreads / 32); }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -400,6 +401,32 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         }
       }
     }
+  } else if (warp == 2) {
+    // ================================================== output store warp
+    // Waits until the 8 epilogue warps have written a 64-column chunk, issues its TMA store and recycles
+    // staging buffers as earlier stores drain -- so the math warps never wait on a store or on each other
+    // (measured before: a 256-thread barrier + the store issue on the critical thread cost as much as the math).
+    if (!kSplitK) {
+      int buf = 0; uint32_t round = 0; int fbuf = 0; int k = 0;
+      for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+        int n_blk, m_row0, g, ks;
+        ti.decode(tile, n_blk, m_row0, g, ks);
+        for (int c64 = 0; c64 < BN; c64 += 64, ++k) {
+          mbar_wait(&cfull_bar[buf], round & 1);
+          if (elect_one()) {
+            tma_store_2d(&p.tmD[g], smem_epi + buf * kChunkBytes, n_blk * BN + c64, m_row0);
+            tma_store_commit();
+            tma_store_wait_read<Cfg::kStoreWait>();          // stores up to chunk k - kStoreWait have drained
+            if (k >= Cfg::kStoreWait) mbar_arrive(&rempty_bar[fbuf]);
+          }
+          __syncwarp();
+          if (++buf == kRing) { buf = 0; ++round; }
+          if (k >= Cfg::kStoreWait && ++fbuf == kRing) fbuf = 0;
+        }
+      }
+      if (elect_one()) tma_store_wait_all<0>();
+      __syncwarp();
+    }
   } else if (warp >= 4) {
     // ========================================================= epilogue
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -410,7 +437,6 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     int acc = 0; uint32_t acc_phase = 0;
     int k = 0;   // running 64-column chunk counter
     int buf = 0; uint32_t round = 0;   // its position in the staging ring
-    int fbuf = 0;                      // ring slot of chunk k-1-kStoreWait (the one a drained store frees)
     // per-column vectors (bias, bn scale/shift): double-buffered in smem; the loads for the NEXT tile are
     // issued at the start of the current one so their latency hides behind its chunks
     const bool use_vec = Cfg::kUsesVec && (flags & (EPI_BIAS | EPI_BN)) != 0;
@@ -451,9 +477,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       const int n0 = n_blk * BN;
       if (warp == 4) dbg_stamp(p, 2, tile_i, 0);
 
-      const __half* s_bias = reinterpret_cast<const __half*>(smem_vec + vsel * kVecBytes);
-      const float* s_scale = reinterpret_cast<const float*>(smem_vec + vsel * kVecBytes + 512);
-      const float* s_shift = reinterpret_cast<const float*>(smem_vec + vsel * kVecBytes + 512 + 1024);
+      const uint32_t s_bias = smem_u32(smem_vec + vsel * kVecBytes);            // fp16 [BN]
+      const uint32_t s_scale = s_bias + 512, s_shift = s_bias + 512 + 1024;     // fp32 [BN] each
       if (use_vec) {
         named_bar_sync(2, kEpiThreads);      // this tile's vectors (stored at the end of the previous tile) are visible
         vec_fetch(tile + ti.nunits);         // next tile's: in flight while this tile is processed
@@ -500,9 +525,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
 #pragma unroll 1
         for (int c64 = 0; c64 < BN; c64 += 64, ++k) {
           uint8_t* sbuf = smem_epi + buf * kChunkBytes;
-          uint8_t* srow = sbuf + row_in_tile * 128;
+          const uint32_t srow = smem_u32(sbuf) + row_in_tile * 128;
           const int c = c64 + hsel * 32;          // first tile column of this thread's 32
-          if (use_r) mbar_wait(&rfull_bar[buf], round & 1);
+          if (use_r) mbar_wait(&rfull_bar[buf], round & 1);                       // residual tile landed (buffer was free)
+          else if (round > 0) mbar_wait(&rempty_bar[buf], (round + 1) & 1);      // the store that last used it drained
           if (warp == 4 && c64 < 256) dbg_stamp(p, 2, tile_i, 2 + 3 * (c64 >> 6));
           if (c < BN) {
             uint32_t v32[32];
@@ -516,7 +542,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
 #pragma unroll(kGeneric ? 1 : 4)
             for (int j = 0; j < 4; ++j) {          // 8 columns = one 16-byte smem unit
               const int ct = c + j * 8;            // column inside the tile
-              uint4* sptr = reinterpret_cast<uint4*>(srow + (((hsel * 4 + j) ^ (row_in_tile & 7)) << 4));
+              const uint32_t sptr = srow + (((hsel * 4 + j) ^ (row_in_tile & 7)) << 4);
               uint32_t v8[8];
               if (kGeneric) {
                 tmem_ld_32x32_x8(t_acc + ct, v8);
@@ -527,7 +553,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
               }
               float r[8], bia[8], bsc[8], bsh[8];
               if (use_r) {
-                const uint4 rv = *sptr;
+                const uint4 rv = lds128(sptr);
                 float2 f;
                 f = unpack_f16x2(rv.x); r[0] = f.x; r[1] = f.y;
                 f = unpack_f16x2(rv.y); r[2] = f.x; r[3] = f.y;
@@ -535,7 +561,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
                 f = unpack_f16x2(rv.w); r[6] = f.x; r[7] = f.y;
               }
               if (flags & EPI_BIAS) {
-                const uint4 bv = *reinterpret_cast<const uint4*>(s_bias + ct);
+                const uint4 bv = lds128(s_bias + ct * 2);
                 float2 f;
                 f = unpack_f16x2(bv.x); bia[0] = f.x; bia[1] = f.y;
                 f = unpack_f16x2(bv.y); bia[2] = f.x; bia[3] = f.y;
@@ -545,8 +571,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
               if (flags & EPI_BN) {
 #pragma unroll
                 for (int e = 0; e < 8; e += 4) {
-                  const float4 s4 = *reinterpret_cast<const float4*>(s_scale + ct + e);
-                  const float4 h4 = *reinterpret_cast<const float4*>(s_shift + ct + e);
+                  const float4 s4 = lds128f(s_scale + (ct + e) * 4);
+                  const float4 h4 = lds128f(s_shift + (ct + e) * 4);
                   bsc[e] = s4.x; bsc[e + 1] = s4.y; bsc[e + 2] = s4.z; bsc[e + 3] = s4.w;
                   bsh[e] = h4.x; bsh[e + 1] = h4.y; bsh[e + 2] = h4.z; bsh[e + 3] = h4.w;
                 }
@@ -582,29 +608,18 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
               uint4 ov;
               ov.x = pack_f16x2(xo[0], xo[1]); ov.y = pack_f16x2(xo[2], xo[3]);
               ov.z = pack_f16x2(xo[4], xo[5]); ov.w = pack_f16x2(xo[6], xo[7]);
-              *sptr = ov;
+              sts128(sptr, ov);
             }
             if ((flags & EPI_MASK) && row < p.M && n0 + c < p.N)
               p.mask_out[(size_t)row * p.mask_ld + ((n0 + c) >> 5)] = maskword;
           }
           fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cfull_bar[buf]);      // this warp's part of the chunk is in smem
           if (warp == 4 && c64 < 256) dbg_stamp(p, 2, tile_i, 3 + 3 * (c64 >> 6));
-          if (epi_tid == 0) {
-            // stores older than the newest kStoreWait have drained their smem reads: the buffer
-            // two chunks back is free again (for the next residual prefetch / next write)
-            tma_store_wait_read<Cfg::kStoreWait>();
-            if (use_r && k >= Cfg::kStoreWait + 1) mbar_arrive(&rempty_bar[fbuf]);
-          }
-          named_bar_sync(1, kEpiThreads);
-          if (warp == 4 && c64 < 256) dbg_stamp(p, 2, tile_i, 4 + 3 * (c64 >> 6));
-          if (epi_tid == 0) {
-            tma_store_2d(&p.tmD[g], sbuf, n0 + c64, m_row0);
-            tma_store_commit();
-          }
           if (++buf == kRing) { buf = 0; ++round; }
-          if (k >= Cfg::kStoreWait + 1 && ++fbuf == kRing) fbuf = 0;
         }
-        if (use_vec) {            // everyone is past this tile's last chunk barrier: the other buffer is free
+        if (use_vec) {            // every warp passed this tile's vector barrier: the other buffer is free
           vsel ^= 1;
           vec_store(vsel);
         }
@@ -618,7 +633,6 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       if (warp == 4) dbg_stamp(p, 2, tile_i, 15);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (!kSplitK && epi_tid == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
