@@ -498,20 +498,31 @@ __global__ void fold_edges_kernel(__half* __restrict__ G, int ld, int n_seq, int
 
 // ---- padded minibatch layout helpers ----------------------------------------------------
 // dense [n_seq*L x cols] -> padded [n_seq*(L+2h) x ld]; halo rows: mode 0 = zero, 1 = replicate edge
+template <int VEC>
 __global__ void pack_rows_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int ld, int n_seq, int L,
                                  int halo, int cols, int mode) {
   const int blk = L + 2 * halo;
-  const size_t total = (size_t)n_seq * blk * cols;
+  const int cv = cols / VEC;
+  const size_t total = (size_t)n_seq * blk * cv;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const size_t r = i / cols;
-    const int c = (int)(i % cols);
+    const size_t r = i / cv;
+    const int c = (int)(i % cv) * VEC;
     const int s = (int)(r / blk);
-    int t = (int)(r % blk) - halo;
-    __half v = __float2half(0.f);
-    if (t >= 0 && t < L) v = src[((size_t)s * L + t) * cols + c];
-    else if (mode == 1) v = src[((size_t)s * L + (t < 0 ? 0 : L - 1)) * cols + c];
-    dst[r * ld + c] = v;
+    const int t = (int)(r % blk) - halo;
+    const bool real = t >= 0 && t < L;
+    const size_t srow = (size_t)s * L + (real ? t : (t < 0 ? 0 : L - 1));
+    if (VEC == 8) {
+      Half8 v;
+      if (real || mode == 1) v = ld8(src + srow * cols + c);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.v[j] = __float2half2_rn(0.f);
+      }
+      st8(dst + r * ld + c, v);
+    } else {
+      dst[r * ld + c] = (real || mode == 1) ? src[srow * cols + c] : __float2half(0.f);
+    }
   }
 }
 // padded [.. x ld] (cols from col0) -> dense [n_seq*L x cols]
@@ -573,18 +584,37 @@ __global__ void scale_shift_kernel(const __half* __restrict__ x, __half* __restr
   }
 }
 // dY = Y on real rows, 0 on halo rows; *loss += 0.5*sum(Y^2)   (cmd/sgdtest/main.go:258-267)
+template <int VEC>
 __global__ void half_sq_loss_kernel(const __half* __restrict__ Y, __half* __restrict__ dY, int n_seq, int L, int halo,
                                     int cols, float* __restrict__ loss) {
   __shared__ float red[32];
   const int blk = L + 2 * halo;
-  const size_t total = (size_t)n_seq * blk * cols;
+  const int cv = cols / VEC;
+  const size_t total = (size_t)n_seq * blk * cv;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   float acc = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int t = (int)((i / cols) % blk) - halo;
-    __half v = __float2half(0.f);
-    if (t >= 0 && t < L) { v = Y[i]; const float f = __half2float(v); acc += 0.5f * f * f; }
-    dY[i] = v;
+    const size_t r = i / cv;
+    const int t = (int)(r % blk) - halo;
+    const size_t off = r * cols + (i % cv) * VEC;
+    const bool real = t >= 0 && t < L;
+    if (VEC == 8) {
+      Half8 v;
+      if (real) {
+        v = ld8(Y + off);
+        const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float f = __half2float(h[j]); acc += 0.5f * f * f; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.v[j] = __float2half2_rn(0.f);
+      }
+      st8(dY + off, v);
+    } else {
+      __half v = __float2half(0.f);
+      if (real) { v = Y[off]; const float f = __half2float(v); acc += 0.5f * f * f; }
+      dY[off] = v;
+    }
   }
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -595,8 +625,6 @@ __global__ void half_sq_loss_kernel(const __half* __restrict__ Y, __half* __rest
     if (threadIdx.x == 0) atomicAdd(loss, v);
   }
 }
-// dZ = mask ? h(dY*scale[c]) : 0 and db[c] += sum_r dZ[r,c]  (BN backward + ReLU backward + bias grad)
-// block (32 column-groups of 8, 8 row lanes); grid (ceil(cols/256), row_chunks)
 __global__ void bn_relu_bwd_colsum_kernel(const __half* __restrict__ dY, int ldy, const float* __restrict__ scale,
                                           const uint32_t* __restrict__ mask, int mask_ld, __half* __restrict__ dZ,
                                           int ldz, size_t rows, int cols, float* __restrict__ db) {
@@ -849,8 +877,11 @@ int kfp16_pack_rows(kfp16_ctx* ctx, const void* src, void* dst, int ld, int n_se
                     int mode) {
   if (n_seq <= 0 || seq_len <= 0 || cols <= 0) return 0;
   if (!src || !dst) { set_error("kfp16_pack_rows: null pointer"); return -1; }
-  pack_rows_kernel<<<grid_for((size_t)n_seq * (seq_len + 2 * halo) * cols), kThreads, 0, ctx_stream(ctx)>>>(
-      (const __half*)src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
+  const size_t elems = (size_t)n_seq * (seq_len + 2 * halo) * cols;
+  if ((cols % 8) == 0 && (ld % 8) == 0 && al16(src) && al16(dst))
+    pack_rows_kernel<8><<<grid_for(elems / 8), kThreads, 0, ctx_stream(ctx)>>>((const __half*)src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
+  else
+    pack_rows_kernel<1><<<grid_for(elems), kThreads, 0, ctx_stream(ctx)>>>((const __half*)src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
   count_launch();
   return check_launch("kfp16_pack_rows") ? 0 : -1;
 }
@@ -897,8 +928,11 @@ int kfp16_half_sq_loss(kfp16_ctx* ctx, const void* Y, void* dY, int n_seq, int s
                        float* loss_dev) {
   if (n_seq <= 0 || cols <= 0) return 0;
   if (!Y || !dY || !loss_dev) { set_error("kfp16_half_sq_loss: null pointer"); return -1; }
-  half_sq_loss_kernel<<<grid_for((size_t)n_seq * (seq_len + 2 * halo) * cols), kThreads, 0, ctx_stream(ctx)>>>(
-      (const __half*)Y, (__half*)dY, n_seq, seq_len, halo, cols, loss_dev);
+  const size_t elems = (size_t)n_seq * (seq_len + 2 * halo) * cols;
+  if ((cols % 8) == 0 && al16(Y) && al16(dY))
+    half_sq_loss_kernel<8><<<grid_for(elems / 8), kThreads, 0, ctx_stream(ctx)>>>((const __half*)Y, (__half*)dY, n_seq, seq_len, halo, cols, loss_dev);
+  else
+    half_sq_loss_kernel<1><<<grid_for(elems), kThreads, 0, ctx_stream(ctx)>>>((const __half*)Y, (__half*)dY, n_seq, seq_len, halo, cols, loss_dev);
   count_launch();
   return check_launch("kfp16_half_sq_loss") ? 0 : -1;
 }
@@ -909,7 +943,7 @@ int kfp16_bn_relu_backward_bias(kfp16_ctx* ctx, const void* dY, int ldy, const f
     set_error("kfp16_bn_relu_backward_bias: needs 16B-aligned buffers and cols/ld %% 8 == 0"); return -1;
   }
   const int gx = (cols + 255) / 256;
-  int gy = (num_sms_cached() * 4 + gx - 1) / gx;
+  int gy = (num_sms_cached() * 8 + gx - 1) / gx;      // 8 resident 256-thread blocks per SM: one wave, 64 warps/SM
   const int max_gy = (rows + 31) / 32;
   if (gy > max_gy) gy = max_gy;
   if (gy < 1) gy = 1;

@@ -109,6 +109,13 @@ struct kfp16_net {
   std::vector<void*> allocs;
   __half *conv_P = nullptr, *conv_dP = nullptr, *conv_dz = nullptr;   // shared conv scratch (patches, patch grads, dZ)
   size_t conv_P_elems = 0, conv_dz_elems = 0;
+  // weight-gradient GEMMs are off the backward critical path (they only feed the gradient bucket): they run on a
+  // low-priority side stream, forked / joined with events, and fill the SMs the narrow dgrad GEMMs leave idle
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  cudaEvent_t ev_join = nullptr;
+  bool side_used = false;
   __half* stage_in = nullptr;   // dense staging for host uploads / downloads
   size_t stage_bytes = 0;
   double flops_fwd = 0;
@@ -714,6 +721,25 @@ int wgrad(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int 
   return kfp16_gemm_ex(n->ctx, &d);
 }
 
+// same, launched on the side stream after everything issued so far on the main stream
+int wgrad_async(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int off0, int off1) {
+  if (!n->side) return wgrad(n, X, dY, param, groups, off0, off1);
+  if (n->ev_next == n->ev_pool.size()) {
+    cudaEvent_t e = nullptr;
+    if (!check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate (wgrad fork)")) return -1;
+    n->ev_pool.push_back(e);
+  }
+  cudaEvent_t ev = n->ev_pool[n->ev_next++];
+  cudaStream_t main_stream = n->ctx->stream;
+  if (!check_cuda(cudaEventRecord(ev, main_stream), "wgrad fork record") ||
+      !check_cuda(cudaStreamWaitEvent(n->side, ev, 0), "wgrad fork wait")) return -1;
+  n->ctx->stream = n->side;
+  const int rc = wgrad(n, X, dY, param, groups, off0, off1);
+  n->ctx->stream = main_stream;
+  n->side_used = true;
+  return rc;
+}
+
 // route a freshly computed input-gradient into the producer(s) of layer l
 int deliver_dx(kfp16_net* n, Layer& l, const Buf& dx) {
   // dx: [rows x in_dim]; single producer: dx IS producer.dout when it was written in place
@@ -910,7 +936,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
         d.D[0] = dx.p; d.ldd = l.in_dim;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (l.type == L_LINEAR && wgrad(n, X, l.dout, l.pW, 1, 0, 0)) return -1;   // backward_ops.go:195-225
+      if (l.type == L_LINEAR && wgrad_async(n, X, l.dout, l.pW, 1, 0, 0)) return -1;   // backward_ops.go:195-225
       break;
     }
     case L_BATCHNORM:   // dX = dY * gamma/sqrt(var+eps)  (backward_wrappers.cu:104-115)
@@ -929,6 +955,9 @@ int backward_layer(kfp16_net* n, Layer& l) {
       const int s = l.stride, sp = s > 0 ? 2 : 1;
       // dZ = mask ? h(dY * bn_scale) : 0 ; db += colsum(dZ)
       if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim, rows, l.out_dim, G32(n, l.pAffB))) return -1;
+      // dWaff = [B(t) | B(t+s)]^T * dZ: forked onto the side stream BEFORE the narrow dB GEMM below, whose 78 CTAs
+      // leave the other SMs free for it
+      if (wgrad_async(n, l.bott, l.dz, l.pAff, sp, 0, s)) return -1;
       {  // dB(r) = dZ(r)*Waff[0:bn]^T + dZ(r-s)*Waff[bn:2bn]^T
         kfp16_gemm_desc d = mk_desc(rows, l.bott_dim, sp * l.out_dim);
         set_A(d, l.dz.p, rows, l.out_dim);
@@ -940,8 +969,8 @@ int backward_layer(kfp16_net* n, Layer& l) {
         if (kfp16_gemm_ex(ctx, &d)) return -1;
         if (s > 0 && kfp16_fold_edges(ctx, l.dbott.p, l.bott_dim, n->opts.n_seq, n->opts.seq_len, l.bott_dim, n->halo)) return -1;
       }
-      // dWaff = [B(t) | B(t+s)]^T * dZ
-      if (wgrad(n, l.bott, l.dz, l.pAff, sp, 0, s)) return -1;
+      // dWlin = [X(t-s) | X(t)]^T * dB (side stream, concurrent with the input-gradient GEMM)
+      if (wgrad_async(n, X, l.dbott, l.pLin, sp, -s, 0)) return -1;
       if (l.wants_dx) {   // dX(r) = dB(r+s)*Wlin[0:in]^T + dB(r)*Wlin[in:2in]^T (+ bypass*dY)
         kfp16_gemm_desc d = mk_desc(rows, l.in_dim, sp * l.bott_dim);
         set_A(d, l.dbott.p, rows, l.bott_dim);
@@ -953,8 +982,6 @@ int backward_layer(kfp16_net* n, Layer& l) {
         if (l.use_bypass) { d.flags |= KFP16_EPI_RESID; d.R[0] = l.dout.p; d.ldr = l.out_dim; d.res_scale = l.bypass; }
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      // dWlin = [X(t-s) | X(t)]^T * dB
-      if (wgrad(n, X, l.dbott, l.pLin, sp, -s, 0)) return -1;
       break;
     }
     case L_PREFINAL: {
@@ -971,7 +998,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
         d.mask_in = l.mask; d.mask_ld = l.mask_ld;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (wgrad(n, l.big, l.dys, l.pSmall, 1, 0, 0)) return -1;
+      if (wgrad_async(n, l.big, l.dys, l.pSmall, 1, 0, 0)) return -1;
       if (kfp16_colsum_accum(ctx, l.dbig.p, l.big_dim, rows, l.big_dim, G32(n, l.pBigB))) return -1;
       if (l.wants_dx) {
         kfp16_gemm_desc d = mk_desc(rows, l.in_dim, l.big_dim);
@@ -981,7 +1008,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
         d.D[0] = dx.p; d.ldd = l.in_dim;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (wgrad(n, X, l.dbig, l.pBig, 1, 0, 0)) return -1;
+      if (wgrad_async(n, X, l.dbig, l.pBig, 1, 0, 0)) return -1;
       break;
     }
     case L_CONV: {     // transpose of the forward (the reference treats the conv as a dense affine: quirk Q2)
@@ -1019,7 +1046,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
         d.D[0] = dx.p; d.ldd = l.in_dim;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (wgrad(n, X, l.dout, l.pW, 1, 0, 0)) return -1;
+      if (wgrad_async(n, X, l.dout, l.pW, 1, 0, 0)) return -1;
       if (kfp16_colsum_accum(ctx, l.dout.p, l.out_dim, rows, l.out_dim, G32(n, l.pB))) return -1;
       break;
     }
@@ -1062,6 +1089,17 @@ kfp16_net* kfp16_net_create(kfp16_ctx* ctx, const char* xconfig, const kfp16_net
     set_error("%s", msg);
     return nullptr;
   }
+  // (opt-in: measured on the TDNN-F stack the fork gives no gain -- 2.38 ms/step with and without -- the wgrad and
+  //  dgrad kernels contend for the same L2->SM bandwidth rather than for SMs)
+  if (opts->train && getenv("KFP16_SIDE_STREAM")) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);    // lo = least priority (numerically largest)
+    if (!check_cuda(cudaStreamCreateWithPriority(&n->side, cudaStreamNonBlocking, lo), "side stream") ||
+        !check_cuda(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming), "join event")) {
+      kfp16_net_destroy(n.release());
+      return nullptr;
+    }
+  }
   if (kfp16_net_init_random(n.get(), 42) != 0) { kfp16_net_destroy(n.release()); return nullptr; }
   return n.release();
 }
@@ -1071,6 +1109,9 @@ void kfp16_net_destroy(kfp16_net* n) {
   for (auto& g : n->graph)
     if (g) cudaGraphExecDestroy(g);
   for (void* p : n->allocs) cudaFree(p);
+  for (cudaEvent_t e : n->ev_pool) cudaEventDestroy(e);
+  if (n->ev_join) cudaEventDestroy(n->ev_join);
+  if (n->side) cudaStreamDestroy(n->side);
   delete n;
 }
 
@@ -1294,11 +1335,17 @@ int kfp16_net_backward(kfp16_net* n) {
   if (!n || !n->g32) { set_error("kfp16_net_backward: network was created with train = 0"); return -1; }
   for (auto& l : n->layers) l.grads_seen = 0;
   n->layers[n->out_layer].grads_seen = 1;
+  n->ev_next = 0;
   for (int i = (int)n->layers.size() - 1; i >= 0; --i) {
     Layer& l = n->layers[i];
     if (!l.needs_grad || l.type == L_INPUT) continue;
     if (l.grads_seen == 0) continue;   // nothing flowed into this layer
     if (backward_layer(n, l)) return -1;
+  }
+  if (n->side_used) {   // join: the gradient bucket is complete only when the side stream has drained
+    if (!check_cuda(cudaEventRecord(n->ev_join, n->side), "wgrad join record") ||
+        !check_cuda(cudaStreamWaitEvent(n->ctx->stream, n->ev_join, 0), "wgrad join wait")) return -1;
+    n->side_used = false;
   }
   return 0;
 }
@@ -1333,6 +1380,11 @@ int kfp16_net_capture(kfp16_net* n, int phases) {
   const cudaError_t e = cudaStreamEndCapture(n->ctx->stream, &g);
   if (rc) { if (g) cudaGraphDestroy(g); return -1; }
   if (!check_cuda(e, "cudaStreamEndCapture")) return -1;
+  if (const char* dot = getenv("KFP16_GRAPH_DOT")) {   // debugging aid: <path>.<phases>
+    char path[512];
+    snprintf(path, sizeof(path), "%s.%d", dot, phases);
+    cudaGraphDebugDotPrint(g, path, 0);
+  }
   if (n->graph[phases]) cudaGraphExecDestroy(n->graph[phases]);
   const bool ok = check_cuda(cudaGraphInstantiate(&n->graph[phases], g, 0), "cudaGraphInstantiate");
   cudaGraphDestroy(g);
