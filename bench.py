@@ -264,14 +264,15 @@ def main():
     set_inputs_device()
     net.Capture(1)
     net.Capture(2)
-    grads_t = None
+    reducer = None
     if world > 1:
-        grads_t = torch.as_tensor(net.grads_as_cuda_array(), device=f"cuda:{local}")
+        from kaldi_fp16_b200 import dp
+        reducer = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(), device=f"cuda:{local}"))
 
     def allreduce():
-        if world > 1:
+        if reducer is not None:
             with torch.cuda.stream(tstream):
-                dist.all_reduce(grads_t)     # sum: N-GPU step == 1-GPU step on the concatenated batch
+                reducer.all_reduce()         # sum: N-GPU step == 1-GPU step on the concatenated batch
 
     def step_device():
         set_inputs_device()
@@ -314,15 +315,31 @@ def main():
     frames_per_step = T * world
     value = frames_per_step * args.steps / (ms * 1e-3)
 
-    # ---- end-to-end leg: pinned host buffers in, loss out, every step
+    # ---- end-to-end leg: every step's inputs come from pinned host memory (H2D inside the timed region) and the
+    # step's loss is read back to the host.  The copy of step i+1's inputs is issued on the library's copy stream
+    # while step i computes (kfp16_net_prefetch_input / commit_input), as a training loop feeding egs would.
     e2e_steps = max(3, min(args.steps, 100))
+
+    def prefetch_host():
+        assert lib.kfp16_net_prefetch_input(net.ptr, b"input", h_feat_ptr, T, fd) == 0, _lib.last_error()
+        if ivd:
+            assert lib.kfp16_net_prefetch_input(net.ptr, b"ivector", h_ivec_ptr, N_SEQ, ivd) == 0, _lib.last_error()
+
+    def commit_host():
+        assert lib.kfp16_net_commit_input(net.ptr, b"input") == 0, _lib.last_error()
+        if ivd:
+            assert lib.kfp16_net_commit_input(net.ptr, b"ivector") == 0, _lib.last_error()
+
     net.ReadLoss()
     sync_all()
     t0 = time.perf_counter()
     e0.record(stream_ptr)
     last_loss = 0.0
-    for _ in range(e2e_steps):
-        set_inputs_host()
+    prefetch_host()
+    for i in range(e2e_steps):
+        commit_host()
+        if i + 1 < e2e_steps:
+            prefetch_host()
         net.Launch(1)
         allreduce()
         net.Launch(2)
@@ -356,13 +373,17 @@ def main():
     lib.kfp16_ctx_profile_read(handle.ptr, C.byref(n_l), C.byref(g_ms), C.byref(g_fl))
     lib.kfp16_ctx_set_profile(handle.ptr, 0)
     burst, sustained, hbm, src = peaks()
+    traffic = None
+    tp = ROOT / "profiles" / "r01_ncu_traffic.json"
+    if tp.exists() and args.workload == "tdnnf_stack":
+        traffic = json.loads(tp.read_text()).get("dram_bytes_per_gemm_launch")
     achieved = g_fl.value / max(g_ms.value, 1e-9) / 1e9   # TFLOP/s
     flops_fwd = lib.kfp16_net_flops_forward(net.ptr)
     step_flops_real = g_fl.value / max(args.profile_steps, 1)
 
     if rank == 0:
         out = {
-            "metric": "CNN-TDNN fwd+bwd frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "impl": "ours", "metric": "CNN-TDNN fwd+bwd frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": wl["desc"], "frames_per_gpu_step": T, "global_frames_per_step": frames_per_step,
@@ -375,7 +396,8 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "kfp16::gemm_f16_sm100 (all tile variants)",
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src}); burst {burst}",
-                         "frac_of_burst": achieved / burst, "traffic": None,
+                         "frac_of_burst": achieved / burst, "traffic": traffic,
+                         "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, dram read+write bytes averaged over the step's GEMM launches)" if traffic else None,
                          "launches_per_step": n_l.value // max(args.profile_steps, 1),
                          "gemm_ms_per_step": g_ms.value / max(args.profile_steps, 1),
                          "gemm_share_of_step": (g_ms.value / max(args.profile_steps, 1)) / (ms / args.steps),

@@ -78,6 +78,11 @@ int kfp16_net_init_random(kfp16_net *net, uint64_t seed);
 int kfp16_net_set_input(kfp16_net *net, const char *input_name, const uint16_t *host_f16, int rows, int cols);
 /* same from a device buffer already holding the dense fp16 rows (inputs resident in HBM) */
 int kfp16_net_set_input_device(kfp16_net *net, const char *input_name, const void *dev_f16, int rows, int cols);
+/* double-buffered asynchronous form: prefetch copies the NEXT minibatch's dense rows from PINNED host memory on a
+ * copy stream (overlapping the current step), commit scatters them into the padded layout on the step's stream.
+ * (the reference's TransferBatchPinned is a synchronous cudaMemcpy: internal/gpu/bridge.go:273-366, bridge.cu:257-267) */
+int kfp16_net_prefetch_input(kfp16_net *net, const char *input_name, const uint16_t *host_pinned_f16, int rows, int cols);
+int kfp16_net_commit_input(kfp16_net *net, const char *input_name);
 int kfp16_net_forward(kfp16_net *net);
 /* dense real rows of a layer's output -> host fp16 [n_seq*seq_len x dim] */
 int kfp16_net_get_output(kfp16_net *net, const char *layer, uint16_t *host_f16, int rows, int cols);

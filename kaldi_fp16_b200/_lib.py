@@ -129,6 +129,8 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_init_random": (c_int, [c_void_p, c_u64]),
     "kfp16_net_set_input": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
     "kfp16_net_set_input_device": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_prefetch_input": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_commit_input": (c_int, [c_void_p, C.c_char_p]),
     "kfp16_net_forward": (c_int, [c_void_p]),
     "kfp16_net_get_output": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
     "kfp16_net_get_mask": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),

@@ -88,6 +88,10 @@ struct Layer {
   bool log_softmax = false;
   // combine-feature-maps
   int height = 0, nf1 = 1, nf2 = 1;
+  // input prefetch (double-buffered async H2D): staged dense rows + events
+  __half* pf_buf[2] = {nullptr, nullptr};
+  cudaEvent_t pf_copied[2] = {nullptr, nullptr}, pf_packed[2] = {nullptr, nullptr};
+  int pf_rows = 0, pf_cols = 0, pf_slot = 0, pf_ready = -1;
   // conv-relu-batchnorm
   int hin = 0, hout = 0, hsub = 1, fin = 0, fout = 0, convK = 0, convKp = 0;
   std::vector<int> tap_dt, tap_dh;
@@ -112,6 +116,7 @@ struct kfp16_net {
   // weight-gradient GEMMs are off the backward critical path (they only feed the gradient bucket): they run on a
   // low-priority side stream, forked / joined with events, and fill the SMs the narrow dgrad GEMMs leave idle
   cudaStream_t side = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D prefetch of the next minibatch (kfp16_net_prefetch_input)
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   cudaEvent_t ev_join = nullptr;
@@ -1109,6 +1114,12 @@ void kfp16_net_destroy(kfp16_net* n) {
   for (auto& g : n->graph)
     if (g) cudaGraphExecDestroy(g);
   for (void* p : n->allocs) cudaFree(p);
+  for (auto& l : n->layers)
+    for (int b = 0; b < 2; ++b) {
+      if (l.pf_copied[b]) cudaEventDestroy(l.pf_copied[b]);
+      if (l.pf_packed[b]) cudaEventDestroy(l.pf_packed[b]);
+    }
+  if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
   for (cudaEvent_t e : n->ev_pool) cudaEventDestroy(e);
   if (n->ev_join) cudaEventDestroy(n->ev_join);
   if (n->side) cudaStreamDestroy(n->side);
@@ -1234,6 +1245,45 @@ int kfp16_net_set_input(kfp16_net* n, const char* input_name, const uint16_t* ho
   if (!check_cuda(cudaMemcpyAsync(n->stage_in, host, bytes, cudaMemcpyHostToDevice, n->ctx->stream), "input upload")) return -1;
   if (set_input_common(n, input_name, n->stage_in, rows, cols)) return -1;
   return check_cuda(cudaStreamSynchronize(n->ctx->stream), "input sync") ? 0 : -1;
+}
+
+// Asynchronous input path: the NEXT minibatch's rows travel host -> device on a copy stream while the current
+// step computes; kfp16_net_commit_input then scatters the staged rows into the padded layout on the main
+// stream.  `host_f16` must be pinned (bridge_host_alloc) and stay untouched until the matching commit.
+int kfp16_net_prefetch_input(kfp16_net* n, const char* input_name, const uint16_t* host, int rows, int cols) {
+  if (!n || !input_name || !host) { set_error("kfp16_net_prefetch_input: null argument"); return -1; }
+  const int i = find_layer(n, input_name);
+  if (i < 0 || n->layers[i].type != L_INPUT) { set_error("kfp16_net_prefetch_input: no input layer named %s", input_name); return -1; }
+  Layer& l = n->layers[i];
+  const int want_rows = l.per_seq ? n->opts.n_seq : n->T;
+  if (rows != want_rows || cols != l.out_dim) { set_error("kfp16_net_prefetch_input: %s expects [%d x %d], got [%d x %d]", input_name, want_rows, l.out_dim, rows, cols); return -1; }
+  if (!n->copy_stream && !check_cuda(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking), "copy stream")) return -1;
+  const size_t bytes = (size_t)rows * cols * 2;
+  const int b = l.pf_slot;
+  if (!l.pf_buf[b]) {
+    if (!dev_alloc(n, (void**)&l.pf_buf[b], bytes, false)) return -1;
+    if (!check_cuda(cudaEventCreateWithFlags(&l.pf_copied[b], cudaEventDisableTiming), "prefetch event") ||
+        !check_cuda(cudaEventCreateWithFlags(&l.pf_packed[b], cudaEventDisableTiming), "prefetch event")) return -1;
+  } else if (!check_cuda(cudaStreamWaitEvent(n->copy_stream, l.pf_packed[b], 0), "prefetch wait")) {
+    return -1;   // the scatter that last read this staging slot must have run
+  }
+  if (!check_cuda(cudaMemcpyAsync(l.pf_buf[b], host, bytes, cudaMemcpyHostToDevice, n->copy_stream), "prefetch copy") ||
+      !check_cuda(cudaEventRecord(l.pf_copied[b], n->copy_stream), "prefetch record")) return -1;
+  l.pf_rows = rows; l.pf_cols = cols;
+  l.pf_ready = b;
+  l.pf_slot = b ^ 1;
+  return 0;
+}
+int kfp16_net_commit_input(kfp16_net* n, const char* input_name) {
+  if (!n || !input_name) { set_error("kfp16_net_commit_input: null argument"); return -1; }
+  const int i = find_layer(n, input_name);
+  if (i < 0 || n->layers[i].type != L_INPUT || n->layers[i].pf_ready < 0) { set_error("kfp16_net_commit_input: nothing prefetched for %s", input_name ? input_name : "?"); return -1; }
+  Layer& l = n->layers[i];
+  const int b = l.pf_ready;
+  l.pf_ready = -1;
+  if (!check_cuda(cudaStreamWaitEvent(n->ctx->stream, l.pf_copied[b], 0), "commit wait")) return -1;
+  if (set_input_common(n, input_name, l.pf_buf[b], l.pf_rows, l.pf_cols)) return -1;
+  return check_cuda(cudaEventRecord(l.pf_packed[b], n->ctx->stream), "commit record") ? 0 : -1;
 }
 
 int kfp16_net_forward(kfp16_net* n) {

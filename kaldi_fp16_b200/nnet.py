@@ -140,6 +140,15 @@ class Network:
         if self.lib.kfp16_net_set_input(self.ptr, name.encode(), bits.ctypes.data, bits.shape[0], bits.shape[1]) != 0:
             raise _err("SetInput")
 
+    def PrefetchInput(self, name: str, host_ptr: int, rows: int, cols: int) -> None:
+        """async H2D of the NEXT minibatch from pinned host memory (gpu.TransferBatchPinned done asynchronously)"""
+        if self.lib.kfp16_net_prefetch_input(self.ptr, name.encode(), host_ptr, rows, cols) != 0:
+            raise _err("PrefetchInput")
+
+    def CommitInput(self, name: str) -> None:
+        if self.lib.kfp16_net_commit_input(self.ptr, name.encode()) != 0:
+            raise _err("CommitInput")
+
     def Forward(self, features: np.ndarray, ivectors: Optional[np.ndarray] = None, input_name: str = "input",
                 ivector_name: str = "ivector") -> np.ndarray:
         """forward.go:148: returns the activation of the layer named ``output`` (dense real rows, fp32)."""

@@ -325,3 +325,30 @@ def test_cnn_front_end_forward_backward(handle, n_seq, L):
     """conv-relu-batchnorm layers (3x3 Cartesian taps, height subsampling, 3-filter input with K = 27 padded
     to 32) lowered to im2col + tcgen05 GEMM, against the numpy oracle's explicit patch matrices"""
     check_conv_net(handle, n_seq, L, seed=5 + n_seq)
+
+
+def test_prefetched_input_equals_synchronous_input(handle, lib):
+    """kfp16_net_prefetch_input / commit_input (async H2D from pinned memory, double buffered) == kfp16_net_set_input"""
+    import ctypes as C
+
+    n_seq, L = 3, 25
+    on, net, rng = make_pair(handle, SPLICED, n_seq, L, seed=9)
+    outs = []
+    pinned = lib.bridge_host_alloc(n_seq * L * 64 * 2)
+    xs = [O.to_f16_rne(rng.standard_normal((n_seq * L, 64)).astype(np.float32)) for _ in range(3)]
+    for x in xs:                      # synchronous path
+        outs.append(net.Forward(x))
+    bits0 = nnet.rne_fp16_bits(xs[0])
+    C.memmove(pinned, bits0.ctypes.data, bits0.nbytes)
+    net.PrefetchInput("input", pinned, n_seq * L, 64)
+    for i, x in enumerate(xs):        # prefetch i+1 while i runs
+        net.CommitInput("input")
+        gpu.Sync()                    # (the test reuses ONE pinned buffer, so wait before overwriting it)
+        if i + 1 < len(xs):
+            nb = nnet.rne_fp16_bits(xs[i + 1])
+            C.memmove(pinned, nb.ctypes.data, nb.nbytes)
+            net.PrefetchInput("input", pinned, n_seq * L, 64)
+        assert lib.kfp16_net_forward(net.ptr) == 0
+        assert np.array_equal(net.Output(""), outs[i])
+    lib.bridge_host_free(pinned)
+    net.Free()
