@@ -365,6 +365,32 @@ int kfp16_gemm(kfp16_ctx* ctx, int M, int N, int K, float alpha, const void* A, 
     kfp16_gemm_desc d;
     memset(&d, 0, sizeof(d));
     d.M = M; d.N = N; d.K = K;
+    // long-reduction shapes with few output tiles (weight gradients through the plain API): split K over the
+    // idle SMs into the context's fp32 workspace, then round once to fp16
+    const int bn_est = N <= 64 ? 64 : N <= 128 ? 128 : N <= 160 ? 160 : 256;
+    const long long tiles = (long long)((M + 255) / 256) * ((N + bn_est - 1) / bn_est);
+    const int pairs = ctx->num_sms / 2;
+    int split = (int)(pairs / (tiles > 0 ? tiles : 1));
+    if (split > K / 256) split = K / 256;
+    if (beta == 0.0f && split >= 2 && (N % 4) == 0) {
+      const size_t need = (size_t)M * N * sizeof(float);
+      if (ctx->ws_bytes < need) {
+        if (ctx->ws) cudaFree(ctx->ws);
+        ctx->ws = nullptr; ctx->ws_bytes = 0;
+        if (!check_cuda(cudaMalloc(&ctx->ws, need), "cudaMalloc (split-K workspace)")) return -1;
+        ctx->ws_bytes = need;
+      }
+      if (!check_cuda(cudaMemsetAsync(ctx->ws, 0, need, ctx->stream), "split-K workspace memset")) return -1;
+      d.a_major = transA ? KFP16_MN_MAJOR : KFP16_K_MAJOR;
+      d.b_major = transB ? KFP16_K_MAJOR : KFP16_MN_MAJOR;
+      d.A.ptr = A; d.A.rows = transA ? K : M; d.A.cols = transA ? M : K; d.A.ld = lda;
+      d.B.ptr = B; d.B.rows = transB ? N : K; d.B.cols = transB ? K : N; d.B.ld = ldb;
+      d.groups = 1; d.kslabs = 1; d.kslab_len = K;
+      d.alpha = alpha;
+      d.split_k = split; d.ws[0] = ctx->ws; d.ws_ld = N;
+      if (kfp16_gemm_ex(ctx, &d) != 0) return -1;
+      return kfp16_f32_to_f16(ctx, ctx->ws, C, (size_t)M * N);
+    }
     d.a_major = transA ? KFP16_MN_MAJOR : KFP16_K_MAJOR;
     d.b_major = transB ? KFP16_K_MAJOR : KFP16_MN_MAJOR;
     d.A.ptr = A; d.A.rows = transA ? K : M; d.A.cols = transA ? M : K; d.A.ld = lda;

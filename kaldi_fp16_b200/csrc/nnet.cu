@@ -1099,7 +1099,8 @@ kfp16_net* kfp16_net_create(kfp16_ctx* ctx, const char* xconfig, const kfp16_net
   if (opts->train && getenv("KFP16_SIDE_STREAM")) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);    // lo = least priority (numerically largest)
-    if (!check_cuda(cudaStreamCreateWithPriority(&n->side, cudaStreamNonBlocking, lo), "side stream") ||
+    const int prio = atoi(getenv("KFP16_SIDE_STREAM")) == 2 ? hi : lo;   // 1: lowest priority, 2: highest
+    if (!check_cuda(cudaStreamCreateWithPriority(&n->side, cudaStreamNonBlocking, prio), "side stream") ||
         !check_cuda(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming), "join event")) {
       kfp16_net_destroy(n.release());
       return nullptr;

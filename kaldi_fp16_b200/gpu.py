@@ -475,3 +475,89 @@ class SGDOptimizer:
 
 def NewSGDOptimizer(lr: float, momentum: float) -> SGDOptimizer:
     return SGDOptimizer(lr, momentum)
+
+
+# --------------------------------------------------------------------------- batch transfer (bridge.go:68-221)
+@dataclass
+class TrainingBatch:
+    """The fields of loader.TrainingBatch that TransferBatch consumes (internal/loader/dataloader.go:15-38):
+    dense features [total_frames x feat_dim], optional ivectors [batch_size x ivec_dim], merged numerator FST in CSR."""
+
+    features: np.ndarray
+    batch_size: int
+    ivectors: Optional[np.ndarray] = None
+    csr_row_ptr: Optional[np.ndarray] = None     # int32 [num_states + 1]
+    csr_col_idx: Optional[np.ndarray] = None     # int32 [num_arcs]
+    csr_labels: Optional[np.ndarray] = None      # int32 [num_arcs]
+    csr_weights: Optional[np.ndarray] = None     # float32 [num_arcs]
+
+
+def _align256(n: int) -> int:
+    return (n + 255) & ~255
+
+
+def pack_batch(tb: TrainingBatch) -> tuple[np.ndarray, dict]:
+    """Host side of TransferBatch (bridge.go:123-221): features / ivectors go through the round-to-nearest-even
+    converter (internal/fp16/fp16.go:13-70 via bridge.go:141), then everything is packed into ONE buffer
+    [feat fp16 | ivec fp16 | row_ptr i32 | col_idx i32 | labels i32 | weights f32], each section 256-byte aligned."""
+    with np.errstate(over="ignore"):
+        feat = np.ascontiguousarray(tb.features, dtype=np.float32).astype(np.float16)
+        ivec = (np.ascontiguousarray(tb.ivectors, dtype=np.float32).astype(np.float16) if tb.ivectors is not None
+                else np.zeros((tb.batch_size, 0), np.float16))
+    rp = np.ascontiguousarray(tb.csr_row_ptr if tb.csr_row_ptr is not None else [0], dtype=np.int32)
+    ci = np.ascontiguousarray(tb.csr_col_idx if tb.csr_col_idx is not None else [], dtype=np.int32)
+    lb = np.ascontiguousarray(tb.csr_labels if tb.csr_labels is not None else [], dtype=np.int32)
+    wt = np.ascontiguousarray(tb.csr_weights if tb.csr_weights is not None else [], dtype=np.float32)
+    if not (ci.size == lb.size == wt.size):
+        raise ValueError("CSR col_idx / labels / weights must have one entry per arc")
+    sections = [("features", feat), ("ivectors", ivec), ("csr_row_ptr", rp), ("csr_col_idx", ci), ("csr_labels", lb),
+                ("csr_weights", wt)]
+    offsets, off = {}, 0
+    for name, a in sections:
+        offsets[name] = off
+        off += _align256(a.nbytes)
+    buf = np.zeros(off, dtype=np.uint8)
+    for name, a in sections:
+        buf[offsets[name]: offsets[name] + a.nbytes] = a.view(np.uint8).reshape(-1)
+    meta = dict(total_frames=feat.shape[0], feat_dim=feat.shape[1], batch_size=tb.batch_size, ivec_dim=ivec.shape[1],
+                num_states=rp.size - 1, num_arcs=ci.size, offsets=offsets, total_bytes=off)
+    return buf, meta
+
+
+class GPUBatch:
+    """bridge.go:68-112: one device allocation holding the whole minibatch"""
+
+    def __init__(self, ptrs, meta):
+        self.ptrs, self.meta = ptrs, meta
+        self.TotalFrames, self.FeatDim = meta["total_frames"], meta["feat_dim"]
+        self.BatchSize, self.IvecDim = meta["batch_size"], meta["ivec_dim"]
+        self.NumStates, self.NumArcs = meta["num_states"], meta["num_arcs"]
+
+    def Features(self) -> Tensor:
+        return Tensor(self.ptrs.d_features, self.TotalFrames, self.FeatDim, False)
+
+    def Ivectors(self) -> Tensor:
+        return Tensor(self.ptrs.d_ivectors, self.BatchSize, self.IvecDim, False)
+
+    def TotalBytes(self) -> int:
+        return int(self.ptrs.total_bytes)
+
+    def Free(self) -> None:
+        _lib.load().bridge_batch_free(C.byref(self.ptrs))
+
+
+def TransferBatch(tb: TrainingBatch) -> GPUBatch:
+    """bridge.go:123-221: convert, pack, ONE cudaMalloc + ONE cudaMemcpy (bridge.cu:206-267)"""
+    lib = _lib.load()
+    buf, meta = pack_batch(tb)
+    ptrs = _lib.GPUBatchPtrs()
+    if lib.bridge_batch_alloc(meta["total_frames"], meta["feat_dim"], meta["batch_size"], meta["ivec_dim"], meta["num_states"],
+                              meta["num_arcs"], C.byref(ptrs)) != 0:
+        raise _bridge_err("GPU alloc failed")
+    if int(ptrs.total_bytes) != meta["total_bytes"]:
+        lib.bridge_batch_free(C.byref(ptrs))
+        raise GPUError(f"batch layout mismatch: device {int(ptrs.total_bytes)} bytes, host {meta['total_bytes']}")
+    if lib.bridge_batch_transfer(C.byref(ptrs), buf.ctypes.data, buf.nbytes) != 0:
+        lib.bridge_batch_free(C.byref(ptrs))
+        raise _bridge_err("GPU transfer failed")
+    return GPUBatch(ptrs, meta)

@@ -142,3 +142,31 @@ def test_loss_scaler_host_logic(built_lib):
     assert lib.kaldi_loss_scaler_get_scale(big) == 65536.0
     lib.kaldi_loss_scaler_free(big)
     assert lib.kaldi_loss_scaler_get_scale(None) == 1.0
+
+
+def test_host_converters_and_batch_packing():
+    """gpu.float32_to_fp16_bits == the oracle's truncating converter (tensor.go:158-174); pack_batch lays the minibatch
+    out as bridge_batch_alloc does (bridge.cu:206-246): 256-byte aligned sections, RNE features"""
+    from kaldi_fp16_b200 import gpu
+    from oracle import kaldi_oracle as O
+
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(5000).astype(np.float32) * s for s in (1e-6, 1e-3, 1.0, 300.0, 1e5)])
+    assert np.array_equal(gpu.float32_to_fp16_bits(x), O.float32_to_fp16_bits_trunc(x))
+    assert np.array_equal(gpu.fp16_bits_to_float32(np.arange(0x7C00, dtype=np.uint16)),
+                          O.fp16_bits_to_float32(np.arange(0x7C00, dtype=np.uint16)))
+    feats = rng.standard_normal((30, 40)).astype(np.float32) * 20
+    ivec = rng.standard_normal((2, 100)).astype(np.float32)
+    tb = gpu.TrainingBatch(features=feats, batch_size=2, ivectors=ivec, csr_row_ptr=[0, 2, 3, 3], csr_col_idx=[1, 2, 2],
+                           csr_labels=[5, 6, 7], csr_weights=[-0.5, -0.25, 0.0])
+    buf, meta = gpu.pack_batch(tb)
+    off = meta["offsets"]
+    assert all(v % 256 == 0 for v in off.values()) and meta["total_bytes"] % 256 == 0
+    assert off["ivectors"] == 30 * 40 * 2 + (256 - (30 * 40 * 2) % 256) % 256
+    got_feat = buf[: 30 * 40 * 2].view(np.uint16)
+    assert np.array_equal(got_feat, O.fp16_from_float32_rne(feats).reshape(-1))          # RNE, not truncation
+    assert np.array_equal(buf[off["csr_row_ptr"]: off["csr_row_ptr"] + 16].view(np.int32), [0, 2, 3, 3])
+    assert np.array_equal(buf[off["csr_weights"]: off["csr_weights"] + 12].view(np.float32), np.float32([-0.5, -0.25, 0.0]))
+    assert (meta["num_states"], meta["num_arcs"]) == (3, 3)
+    with pytest.raises(ValueError):
+        gpu.pack_batch(gpu.TrainingBatch(features=feats, batch_size=2, csr_row_ptr=[0, 1], csr_col_idx=[0], csr_labels=[], csr_weights=[0.0]))

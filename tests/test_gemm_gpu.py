@@ -292,3 +292,28 @@ def test_fused_epilogues_on_cta_pairs(handle, lib, cg):
         outs.append(got)
         tD.Free()
     assert np.array_equal(outs[0], outs[1])       # specialised == generic, bit for bit
+
+
+@pytest.mark.parametrize("M,N,K,groups", [(1536, 160, 2000, 2), (512, 256, 900, 1), (304, 64, 700, 1)])
+def test_split_k_transposed_target(handle, lib, M, N, K, groups):
+    """weight gradient computed as dY^T * X (M = the long side) and accumulated TRANSPOSED into the [N x M] fp32
+    bucket section, the second group reading B shifted by s rows (the TDNN-F splice): dW_g[n, m] += sum_k A[k, m] B[k+off_g, n]"""
+    s = 3
+    rng = np.random.default_rng(M + N)
+    At = rand_f16(rng, (K, M))
+    Bfull = rand_f16(rng, (K + 2 * s, N), 0.05)
+    tA, tB = gpu.TensorFromFP16(At), gpu.TensorFromFP16(Bfull)
+    ws = gpu.DeviceF32(n=groups * N * M)
+    tD = gpu.ZeroTensor(8, 8)
+    d = make_desc(M, N, K, tA, tB, tD, a_major=MN_MAJOR, b_major=MN_MAJOR, split_k=6, ws_ld=M, ws_transposed=1)
+    d.groups = groups
+    d.B.ptr, d.B.rows, d.B.halo = tB.Ptr + s * N * 2, K, s
+    d.b_row_off[0][0], d.b_row_off[1][0] = 0, s
+    d.ws[0], d.ws[1] = ws.Ptr, ws.Ptr + N * M * 4
+    run_desc(handle, d)
+    got = ws.ToHost().reshape(groups, N, M)
+    for g, off in zip(range(groups), (0, s)):
+        Bg = Bfull[s + off: s + off + K].astype(np.float64)
+        want = Bg.T @ At.astype(np.float64)
+        absprod = np.abs(Bg).T @ np.abs(At).astype(np.float64)
+        assert_close(got[g], want, 2.0 ** -19 * absprod + 1e-6, f"transposed split-K group {g}")
