@@ -158,6 +158,11 @@ int kfp16_half_sq_loss(kfp16_ctx *ctx, const void *Y, void *dY, int n_seq, int s
 int kfp16_bn_relu_backward_bias(kfp16_ctx *ctx, const void *dY, int ldy, const float *scale,
                                 const uint32_t *mask, int mask_ld, void *dZ, int ldz, int rows, int cols,
                                 float *db_accum);
+/* same on a padded minibatch [n_seq x (seq_len + 2*halo)] rows, with the adjoint of kfp16_pad_edges applied to dY
+ * first and in place (edge row += its halo rows, halo rows = 0): one pass instead of fold + backward */
+int kfp16_bn_relu_backward_bias_fold(kfp16_ctx *ctx, void *dY, int ldy, const float *scale, const uint32_t *mask,
+                                     int mask_ld, void *dZ, int ldz, int n_seq, int seq_len, int halo, int cols,
+                                     float *db_accum);
 /* out_f32[n] += sum_t X[t,n]  (no memset: accumulates into the flat gradient bucket) */
 int kfp16_colsum_accum(kfp16_ctx *ctx, const void *X, int ld, int rows, int cols, float *out_f32);
 

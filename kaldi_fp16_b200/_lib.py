@@ -101,6 +101,7 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_scale_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "kfp16_half_sq_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "kfp16_bn_relu_backward_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kfp16_bn_relu_backward_bias_fold": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "kfp16_colsum_accum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "kfp16_im2col": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [C.POINTER(c_int), C.POINTER(c_int)]),
     "kfp16_col2im": (c_int, [c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 8 + [C.POINTER(c_int), C.POINTER(c_int)]),

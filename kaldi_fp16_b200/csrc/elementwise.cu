@@ -339,22 +339,67 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
 //   g = float(grad); v = m*v + g; w32 -= lr*v; w16 = half(w32)
 // One launch covers a whole flat parameter bucket (the reference launches once per tensor).
 template <bool GRAD_F32>
+__device__ __forceinline__ void sgd_one(float& w, float& v, float g, int round_grad, float grad_scale, float lr, float mom) {
+  g *= grad_scale;
+  if (GRAD_F32 && round_grad) g = __half2float(__float2half_rn(g));
+  v = mom * v + g;
+  w = w - lr * v;
+}
+template <bool GRAD_F32>
 __global__ void sgd_kernel(float* __restrict__ w32, __half* __restrict__ w16, const void* __restrict__ grad,
                            int round_grad, float grad_scale, float* __restrict__ vel, float lr, float mom, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float g;
-    if (GRAD_F32) {
-      g = reinterpret_cast<const float*>(grad)[i] * grad_scale;
-      if (round_grad) g = __half2float(__float2half_rn(g));
-    } else {
-      g = __half2float(reinterpret_cast<const __half*>(grad)[i]) * grad_scale;
-    }
-    const float v = mom * vel[i] + g;
+    const float g = GRAD_F32 ? reinterpret_cast<const float*>(grad)[i] : __half2float(reinterpret_cast<const __half*>(grad)[i]);
+    float v = vel[i], w = w32[i];
+    sgd_one<GRAD_F32>(w, v, g, round_grad, grad_scale, lr, mom);
     vel[i] = v;
-    const float w = w32[i] - lr * v;
     w32[i] = w;
     w16[i] = __float2half_rn(w);
+  }
+}
+// 4 parameters per thread and two such groups in flight: 16-byte loads/stores on the fp32 arrays (20 B/parameter total)
+template <bool GRAD_F32>
+__global__ void __launch_bounds__(256)
+sgd_kernel_v4(float* __restrict__ w32, __half* __restrict__ w16, const void* __restrict__ grad,
+              int round_grad, float grad_scale, float* __restrict__ vel, float lr, float mom, size_t n4) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+    float4 w[2], v[2], g[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t i = i0 + u * stride;
+      ok[u] = i < n4;
+      if (ok[u]) {
+        w[u] = reinterpret_cast<const float4*>(w32)[i];
+        v[u] = reinterpret_cast<const float4*>(vel)[i];
+        if (GRAD_F32) {
+          g[u] = reinterpret_cast<const float4*>(grad)[i];
+        } else {
+          const uint2 h = reinterpret_cast<const uint2*>(grad)[i];
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+          g[u] = make_float4(a.x, a.y, b.x, b.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      const size_t i = i0 + u * stride;
+      sgd_one<GRAD_F32>(w[u].x, v[u].x, g[u].x, round_grad, grad_scale, lr, mom);
+      sgd_one<GRAD_F32>(w[u].y, v[u].y, g[u].y, round_grad, grad_scale, lr, mom);
+      sgd_one<GRAD_F32>(w[u].z, v[u].z, g[u].z, round_grad, grad_scale, lr, mom);
+      sgd_one<GRAD_F32>(w[u].w, v[u].w, g[u].w, round_grad, grad_scale, lr, mom);
+      reinterpret_cast<float4*>(vel)[i] = v[u];
+      reinterpret_cast<float4*>(w32)[i] = w[u];
+      const __half2 lo = __floats2half2_rn(w[u].x, w[u].y), hi = __floats2half2_rn(w[u].z, w[u].w);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(w16)[i] = o;
+    }
   }
 }
 
@@ -465,8 +510,8 @@ __global__ void fold_edges_kernel(__half* __restrict__ G, int ld, int n_seq, int
     const int side = (int)((i / c8) & 1);
     const int c = (int)(i % c8) * 8;
     const size_t base = (size_t)s * blk;
+    if (seq_len == 1 && side == 1) continue;   // a one-frame sequence has both edges on one row: side 0 folds both halos
     const size_t edge = side == 0 ? base + halo : base + halo + seq_len - 1;
-    const size_t h0 = side == 0 ? base : base + halo + seq_len;
     Half8 e = ld8(G + edge * ld + c);
     __half* eh = reinterpret_cast<__half*>(&e);
     float acc[8];
@@ -475,19 +520,22 @@ __global__ void fold_edges_kernel(__half* __restrict__ G, int ld, int n_seq, int
     Half8 z;
 #pragma unroll
     for (int j = 0; j < 4; ++j) z.v[j] = __float2half2_rn(0.f);
-    for (int k0 = 0; k0 < halo; k0 += 4) {     // 4 independent row loads in flight per pass
-      Half8 h[4];
+    for (int pass = 0; pass < (seq_len == 1 ? 2 : 1); ++pass) {
+      const size_t h0 = (side == 0 && pass == 0) ? base : base + halo + seq_len;
+      for (int k0 = 0; k0 < halo; k0 += 4) {     // 4 independent row loads in flight per pass
+        Half8 h[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k0 + k < halo) h[k] = ld8(G + (h0 + k0 + k) * ld + c);
+        for (int k = 0; k < 4; ++k)
+          if (k0 + k < halo) h[k] = ld8(G + (h0 + k0 + k) * ld + c);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k0 + k < halo) {
-          const __half* hh = reinterpret_cast<const __half*>(&h[k]);
+        for (int k = 0; k < 4; ++k)
+          if (k0 + k < halo) {
+            const __half* hh = reinterpret_cast<const __half*>(&h[k]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += __half2float(hh[j]);
-          st8(G + (h0 + k0 + k) * ld + c, z);
-        }
+            for (int j = 0; j < 8; ++j) acc[j] += __half2float(hh[j]);
+            st8(G + (h0 + k0 + k) * ld + c, z);
+          }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) eh[j] = __float2half_rn(acc[j]);
@@ -625,9 +673,16 @@ __global__ void half_sq_loss_kernel(const __half* __restrict__ Y, __half* __rest
     if (threadIdx.x == 0) atomicAdd(loss, v);
   }
 }
-__global__ void bn_relu_bwd_colsum_kernel(const __half* __restrict__ dY, int ldy, const float* __restrict__ scale,
-                                          const uint32_t* __restrict__ mask, int mask_ld, __half* __restrict__ dZ,
-                                          int ldz, size_t rows, int cols, float* __restrict__ db) {
+// dZ = mask ? h(dY * scale) : 0 and db += colsum(dZ) in one pass (the reference: ops_batchnorm_backward +
+// ops_relu_backward + an M=1 GEMM, backward_wrappers.cu:41-115, backward_ops.go:228-253).
+// Optionally also applies the adjoint of pad_edges to dY first (blk > 0): halo rows of every sequence block are
+// added into their edge row and zeroed (dY is updated in place on those rows), so no separate fold launch is needed.
+// Each thread keeps kRowsInFlight independent 16-byte row loads in flight (one per 8-row step).
+constexpr int kBnBwdRows = 4;
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_colsum_kernel(__half* __restrict__ dY, int ldy, const float* __restrict__ scale,
+                          const uint32_t* __restrict__ mask, int mask_ld, __half* __restrict__ dZ,
+                          int ldz, size_t rows, int cols, float* __restrict__ db, int blk, int seq_len, int halo) {
   __shared__ float red[8][32][8];
   const int cg = threadIdx.x, ry = threadIdx.y;
   const int c = (blockIdx.x * 32 + cg) * 8;
@@ -641,18 +696,68 @@ __global__ void bn_relu_bwd_colsum_kernel(const __half* __restrict__ dY, int ldy
     const size_t rows_per = (rows + gridDim.y - 1) / gridDim.y;
     const size_t r0 = (size_t)blockIdx.y * rows_per;
     const size_t r1 = r0 + rows_per < rows ? r0 + rows_per : rows;
-    for (size_t r = r0 + ry; r < r1; r += 8) {
-      Half8 a = ld8(dY + r * ldy + c);
-      __half* h = reinterpret_cast<__half*>(&a);
-      uint32_t bits = 0xFFu;
-      if (mask) bits = (mask[r * mask_ld + (c >> 5)] >> (c & 31)) & 0xFFu;
+    for (size_t rb = r0 + ry; rb < r1; rb += 8 * kBnBwdRows) {
+      Half8 a[kBnBwdRows];
+      uint32_t bits[kBnBwdRows];
+      int kind[kBnBwdRows];     // 0 = interior row, 1 = left edge, 2 = right edge, 3 = halo row (blk > 0 only)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const __half o = ((bits >> j) & 1u) ? __float2half_rn(__half2float(h[j]) * sc[j]) : __float2half(0.f);
-        h[j] = o;
-        acc[j] += __half2float(o);
+      for (int k = 0; k < kBnBwdRows; ++k) {
+        const size_t r = rb + (size_t)k * 8;
+        kind[k] = 0;
+        bits[k] = 0;
+        if (r < r1) {
+          if (blk > 0) {
+            const int pos = (int)(r % (size_t)blk);
+            kind[k] = (pos < halo || pos >= halo + seq_len) ? 3 : pos == halo ? 1 : pos == halo + seq_len - 1 ? 2 : 0;
+          }
+          a[k] = ld8(dY + r * ldy + c);
+          bits[k] = mask ? (__ldg(mask + r * mask_ld + (c >> 5)) >> (c & 31)) & 0xFFu : 0xFFu;
+        }
       }
-      st8(dZ + r * ldz + c, a);
+#pragma unroll
+      for (int k = 0; k < kBnBwdRows; ++k) {
+        const size_t r = rb + (size_t)k * 8;
+        if (r >= r1) continue;
+        __half* h = reinterpret_cast<__half*>(&a[k]);
+        if (kind[k] == 3) {
+          // halo row: contributes nothing; its dY values are consumed (and zeroed) by the edge row's thread
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = __float2half(0.f);
+          st8(dZ + r * ldz + c, a[k]);
+          continue;
+        }
+        if (kind[k] != 0) {
+          // edge row += its halo rows (fp32), halo rows = 0  (a one-frame sequence has both edges on one row)
+          float e[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = __half2float(h[j]);
+          Half8 z;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z.v[j] = __float2half2_rn(0.f);
+          const bool left = kind[k] == 1 || seq_len == 1, right = kind[k] == 2 || seq_len == 1;
+          for (int side = 0; side < 2; ++side) {
+            if (side == 0 ? !left : !right) continue;
+            const size_t h0 = side == 0 ? r - halo : r + 1;
+            for (int q = 0; q < halo; ++q) {
+              const Half8 hv = ld8(dY + (h0 + q) * ldy + c);
+              const __half* hh = reinterpret_cast<const __half*>(&hv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) e[j] += __half2float(hh[j]);
+              st8(dY + (h0 + q) * ldy + c, z);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(e[j]);
+          st8(dY + r * ldy + c, a[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __half o = ((bits[k] >> j) & 1u) ? __float2half_rn(__half2float(h[j]) * sc[j]) : __float2half(0.f);
+          h[j] = o;
+          acc[j] += __half2float(o);
+        }
+        st8(dZ + r * ldz + c, a[k]);
+      }
     }
   }
   if (db) {
@@ -867,9 +972,21 @@ int kfp16_sgd_update_flat(kfp16_ctx* ctx, float* w32, void* w16, const void* gra
   if (n == 0) return 0;
   if (!w32 || !w16 || !grad || !velocity) { set_error("kfp16_sgd_update_flat: null pointer"); return -1; }
   cudaStream_t s = ctx_stream(ctx);
-  if (grad_is_f32) sgd_kernel<true><<<grid_for(n), kThreads, 0, s>>>(w32, (__half*)w16, grad, round_grad, grad_scale, velocity, lr, momentum, n);
-  else sgd_kernel<false><<<grid_for(n), kThreads, 0, s>>>(w32, (__half*)w16, grad, 0, grad_scale, velocity, lr, momentum, n);
-  count_launch();
+  const bool aligned = al16(w32) && al16(velocity) && ((uintptr_t)w16 % 8) == 0 && ((uintptr_t)grad % (grad_is_f32 ? 16 : 8)) == 0;
+  const size_t n4 = aligned ? n / 4 : 0;
+  if (n4 > 0) {
+    const int grid = grid_for((n4 + 1) / 2);
+    if (grad_is_f32) sgd_kernel_v4<true><<<grid, kThreads, 0, s>>>(w32, (__half*)w16, grad, round_grad, grad_scale, velocity, lr, momentum, n4);
+    else sgd_kernel_v4<false><<<grid, kThreads, 0, s>>>(w32, (__half*)w16, grad, 0, grad_scale, velocity, lr, momentum, n4);
+    count_launch();
+  }
+  const size_t done = n4 * 4, rest = n - done;
+  if (rest > 0) {
+    const char* gp = (const char*)grad + done * (grad_is_f32 ? 4 : 2);
+    if (grad_is_f32) sgd_kernel<true><<<grid_for(rest), kThreads, 0, s>>>(w32 + done, (__half*)w16 + done, gp, round_grad, grad_scale, velocity + done, lr, momentum, rest);
+    else sgd_kernel<false><<<grid_for(rest), kThreads, 0, s>>>(w32 + done, (__half*)w16 + done, gp, 0, grad_scale, velocity + done, lr, momentum, rest);
+    count_launch();
+  }
   return check_launch("kfp16_sgd_update_flat") ? 0 : -1;
 }
 
@@ -936,21 +1053,35 @@ int kfp16_half_sq_loss(kfp16_ctx* ctx, const void* Y, void* dY, int n_seq, int s
   count_launch();
   return check_launch("kfp16_half_sq_loss") ? 0 : -1;
 }
-int kfp16_bn_relu_backward_bias(kfp16_ctx* ctx, const void* dY, int ldy, const float* scale, const uint32_t* mask,
-                                int mask_ld, void* dZ, int ldz, int rows, int cols, float* db_accum) {
+static int bn_relu_bwd_launch(kfp16_ctx* ctx, void* dY, int ldy, const float* scale, const uint32_t* mask,
+                              int mask_ld, void* dZ, int ldz, int rows, int cols, float* db_accum, int blk, int seq_len,
+                              int halo) {
   if (rows <= 0 || cols <= 0) return 0;
   if (!dY || !dZ || (cols % 8) || (ldy % 8) || (ldz % 8) || !al16(dY) || !al16(dZ)) {
     set_error("kfp16_bn_relu_backward_bias: needs 16B-aligned buffers and cols/ld %% 8 == 0"); return -1;
   }
+  if (blk > 0 && (seq_len < 1 || halo < 1 || blk != seq_len + 2 * halo || rows % blk != 0 || dY == dZ)) {
+    set_error("kfp16_bn_relu_backward_bias_fold: rows must be whole sequence blocks of seq_len + 2*halo, out of place"); return -1;
+  }
   const int gx = (cols + 255) / 256;
-  int gy = (num_sms_cached() * 8 + gx - 1) / gx;      // 8 resident 256-thread blocks per SM: one wave, 64 warps/SM
-  const int max_gy = (rows + 31) / 32;
+  int gy = (num_sms_cached() * 4 + gx - 1) / gx;      // ~4 resident 256-thread blocks per SM, 4 row loads in flight per thread
+  const int max_gy = (rows + 8 * kBnBwdRows - 1) / (8 * kBnBwdRows);
   if (gy > max_gy) gy = max_gy;
   if (gy < 1) gy = 1;
   bn_relu_bwd_colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, ctx_stream(ctx)>>>(
-      (const __half*)dY, ldy, scale, mask, mask_ld, (__half*)dZ, ldz, (size_t)rows, cols, db_accum);
+      (__half*)dY, ldy, scale, mask, mask_ld, (__half*)dZ, ldz, (size_t)rows, cols, db_accum, blk, seq_len, halo);
   count_launch();
   return check_launch("kfp16_bn_relu_backward_bias") ? 0 : -1;
+}
+int kfp16_bn_relu_backward_bias(kfp16_ctx* ctx, const void* dY, int ldy, const float* scale, const uint32_t* mask,
+                                int mask_ld, void* dZ, int ldz, int rows, int cols, float* db_accum) {
+  return bn_relu_bwd_launch(ctx, const_cast<void*>(dY), ldy, scale, mask, mask_ld, dZ, ldz, rows, cols, db_accum, 0, 0, 0);
+}
+int kfp16_bn_relu_backward_bias_fold(kfp16_ctx* ctx, void* dY, int ldy, const float* scale, const uint32_t* mask,
+                                     int mask_ld, void* dZ, int ldz, int n_seq, int seq_len, int halo, int cols,
+                                     float* db_accum) {
+  return bn_relu_bwd_launch(ctx, dY, ldy, scale, mask, mask_ld, dZ, ldz, n_seq * (seq_len + 2 * halo), cols, db_accum,
+                            seq_len + 2 * halo, seq_len, halo);
 }
 int kfp16_colsum_accum(kfp16_ctx* ctx, const void* X, int ld, int rows, int cols, float* out_f32) {
   if (cols <= 0 || rows <= 0) return 0;

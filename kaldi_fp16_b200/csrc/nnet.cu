@@ -923,7 +923,8 @@ int backward_layer(kfp16_net* n, Layer& l) {
   if (!l.needs_grad || l.type == L_INPUT) return 0;
   const int rows = l.per_seq ? n->opts.n_seq : n->Tp;
   // adjoint of the halo fix-up applied to this layer's output in the forward pass
-  if (!l.per_seq && n->halo > 0) {
+  const bool fused_fold = l.type == L_TDNNF && !l.per_seq && n->halo > 0 && l.halo_mode == HALO_REPL;   // folded inside the dZ pass
+  if (!l.per_seq && n->halo > 0 && !fused_fold) {
     if (l.halo_mode == HALO_REPL && kfp16_fold_edges(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
     if (l.halo_mode == HALO_ZERO && kfp16_zero_halo(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
   }
@@ -959,7 +960,10 @@ int backward_layer(kfp16_net* n, Layer& l) {
     case L_TDNNF: {
       const int s = l.stride, sp = s > 0 ? 2 : 1;
       // dZ = mask ? h(dY * bn_scale) : 0 ; db += colsum(dZ)
-      if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim, rows, l.out_dim, G32(n, l.pAffB))) return -1;
+      if (fused_fold) {
+        if (kfp16_bn_relu_backward_bias_fold(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim,
+                                             n->opts.n_seq, n->opts.seq_len, n->halo, l.out_dim, G32(n, l.pAffB))) return -1;
+      } else if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim, rows, l.out_dim, G32(n, l.pAffB))) return -1;
       // dWaff = [B(t) | B(t+s)]^T * dZ: forked onto the side stream BEFORE the narrow dB GEMM below, whose 78 CTAs
       // leave the other SMs free for it
       if (wgrad_async(n, l.bott, l.dz, l.pAff, sp, 0, s)) return -1;
