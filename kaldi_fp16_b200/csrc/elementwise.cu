@@ -15,6 +15,9 @@
 namespace kfp16 {
 
 constexpr int kThreads = 256;
+// programmatic dependent launch (see sm100_ptx.cuh / host_common.h launch_pdl)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
 static int num_sms_cached() {
   static int n = 0;
@@ -39,8 +42,14 @@ struct alignas(16) Half8 {
   __half2 v[4];
 };
 
-__device__ __forceinline__ Half8 ld8(const __half* p) { return *reinterpret_cast<const Half8*>(p); }
-__device__ __forceinline__ void st8(__half* p, const Half8& x) { *reinterpret_cast<Half8*>(p) = x; }
+// one 16-byte access (a member-wise copy of the __half2 array compiles to four 4-byte accesses)
+__device__ __forceinline__ Half8 ld8(const __half* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  Half8 r;
+  *reinterpret_cast<uint4*>(&r) = u;
+  return r;
+}
+__device__ __forceinline__ void st8(__half* p, const Half8& x) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&x); }
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -348,6 +357,8 @@ __device__ __forceinline__ void sgd_one(float& w, float& v, float g, int round_g
 template <bool GRAD_F32>
 __global__ void sgd_kernel(float* __restrict__ w32, __half* __restrict__ w16, const void* __restrict__ grad,
                            int round_grad, float grad_scale, float* __restrict__ vel, float lr, float mom, size_t n) {
+  griddep_launch();
+  griddep_wait();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float g = GRAD_F32 ? reinterpret_cast<const float*>(grad)[i] : __half2float(reinterpret_cast<const __half*>(grad)[i]);
@@ -363,6 +374,8 @@ template <bool GRAD_F32>
 __global__ void __launch_bounds__(256)
 sgd_kernel_v4(float* __restrict__ w32, __half* __restrict__ w16, const void* __restrict__ grad,
               int round_grad, float grad_scale, float* __restrict__ vel, float lr, float mom, size_t n4) {
+  griddep_launch();
+  griddep_wait();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
     float4 w[2], v[2], g[2];
@@ -483,6 +496,8 @@ __global__ void colsum_kernel(const __half* __restrict__ X, int ld, size_t rows,
 // replicate row 0 / row rows-1 of every sequence block into its halo rows
 //   buffer rows: n_seq blocks of (seq_len + 2*halo) rows; X points at the first block's row -halo
 __global__ void pad_edges_kernel(__half* __restrict__ X, int ld, int n_seq, int seq_len, int cols, int halo) {
+  griddep_launch();
+  griddep_wait();
   const int c8 = cols >> 3;
   const size_t per_seq = (size_t)2 * halo * c8;
   const size_t total = per_seq * n_seq;
@@ -501,6 +516,8 @@ __global__ void pad_edges_kernel(__half* __restrict__ X, int ld, int n_seq, int 
 }
 // adjoint of pad_edges: edge row += sum of its halo rows (fp32), halo rows = 0
 __global__ void fold_edges_kernel(__half* __restrict__ G, int ld, int n_seq, int seq_len, int cols, int halo) {
+  griddep_launch();
+  griddep_wait();
   const int c8 = cols >> 3;
   const size_t total = (size_t)n_seq * 2 * c8;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -549,6 +566,8 @@ __global__ void fold_edges_kernel(__half* __restrict__ G, int ld, int n_seq, int
 template <int VEC>
 __global__ void pack_rows_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int ld, int n_seq, int L,
                                  int halo, int cols, int mode) {
+  griddep_launch();
+  griddep_wait();
   const int blk = L + 2 * halo;
   const int cv = cols / VEC;
   const size_t total = (size_t)n_seq * blk * cv;
@@ -635,6 +654,8 @@ __global__ void scale_shift_kernel(const __half* __restrict__ x, __half* __restr
 template <int VEC>
 __global__ void half_sq_loss_kernel(const __half* __restrict__ Y, __half* __restrict__ dY, int n_seq, int L, int halo,
                                     int cols, float* __restrict__ loss) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float red[32];
   const int blk = L + 2 * halo;
   const int cv = cols / VEC;
@@ -679,10 +700,12 @@ __global__ void half_sq_loss_kernel(const __half* __restrict__ Y, __half* __rest
 // added into their edge row and zeroed (dY is updated in place on those rows), so no separate fold launch is needed.
 // Each thread keeps kRowsInFlight independent 16-byte row loads in flight (one per 8-row step).
 constexpr int kBnBwdRows = 4;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_relu_bwd_colsum_kernel(__half* __restrict__ dY, int ldy, const float* __restrict__ scale,
                           const uint32_t* __restrict__ mask, int mask_ld, __half* __restrict__ dZ,
                           int ldz, size_t rows, int cols, float* __restrict__ db, int blk, int seq_len, int halo) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float red[8][32][8];
   const int cg = threadIdx.x, ry = threadIdx.y;
   const int c = (blockIdx.x * 32 + cg) * 8;
@@ -711,9 +734,11 @@ bn_relu_bwd_colsum_kernel(__half* __restrict__ dY, int ldy, const float* __restr
             kind[k] = (pos < halo || pos >= halo + seq_len) ? 3 : pos == halo ? 1 : pos == halo + seq_len - 1 ? 2 : 0;
           }
           a[k] = ld8(dY + r * ldy + c);
-          bits[k] = mask ? (__ldg(mask + r * mask_ld + (c >> 5)) >> (c & 31)) & 0xFFu : 0xFFu;
-        }
+          bits[k] = mask ? __ldg(mask + r * mask_ld + (c >> 5)) : 0xFFFFFFFFu;   // raw word: no use of a load result
+        }                                                                         // before every load of the group is issued
       }
+#pragma unroll
+      for (int k = 0; k < kBnBwdRows; ++k) bits[k] = (bits[k] >> (c & 31)) & 0xFFu;
 #pragma unroll
       for (int k = 0; k < kBnBwdRows; ++k) {
         const size_t r = rb + (size_t)k * 8;
@@ -765,12 +790,19 @@ bn_relu_bwd_colsum_kernel(__half* __restrict__ dY, int ldy, const float* __restr
     for (int j = 0; j < 8; ++j) red[ry][cg][j] = acc[j];
     __syncthreads();
     if (ry == 0 && c < cols) {
+      float s[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float s = 0.f;
+        s[j] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += red[k][cg][j];
-        atomicAdd(db + c + j, s);
+        for (int k = 0; k < 8; ++k) s[j] += red[k][cg][j];
+      }
+      if ((reinterpret_cast<uintptr_t>(db + c) & 15) == 0) {   // 4 floats per L2 reduction op
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(db + c), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(db + c + 4), "f"(s[4]), "f"(s[5]), "f"(s[6]), "f"(s[7]) : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(db + c + j, s[j]);
       }
     }
   }
@@ -956,14 +988,14 @@ int kfp16_f32_to_f16(kfp16_ctx* ctx, const float* src, void* dst, size_t n) {
 int kfp16_pad_edges(kfp16_ctx* ctx, void* X, int ld, int n_seq, int seq_len, int cols, int halo) {
   if (n_seq <= 0 || seq_len <= 0 || halo <= 0 || cols <= 0) return 0;
   if (!X || (cols % 8) || (ld % 8) || !al16(X)) { set_error("kfp16_pad_edges: needs a 16B-aligned buffer and cols/ld %% 8 == 0"); return -1; }
-  pad_edges_kernel<<<grid_for((size_t)n_seq * 2 * halo * (cols / 8)), kThreads, 0, ctx_stream(ctx)>>>((__half*)X, ld, n_seq, seq_len, cols, halo);
+  launch_pdl(pad_edges_kernel, grid_for((size_t)n_seq * 2 * halo * (cols / 8)), kThreads, 0, ctx_stream(ctx), (__half*)X, ld, n_seq, seq_len, cols, halo);
   count_launch();
   return check_launch("kfp16_pad_edges") ? 0 : -1;
 }
 int kfp16_fold_edges(kfp16_ctx* ctx, void* G, int ld, int n_seq, int seq_len, int cols, int halo) {
   if (n_seq <= 0 || seq_len <= 0 || halo <= 0 || cols <= 0) return 0;
   if (!G || (cols % 8) || (ld % 8) || !al16(G)) { set_error("kfp16_fold_edges: needs a 16B-aligned buffer and cols/ld %% 8 == 0"); return -1; }
-  fold_edges_kernel<<<grid_for((size_t)n_seq * 2 * (cols / 8)), kThreads, 0, ctx_stream(ctx)>>>((__half*)G, ld, n_seq, seq_len, cols, halo);
+  launch_pdl(fold_edges_kernel, grid_for((size_t)n_seq * 2 * (cols / 8)), kThreads, 0, ctx_stream(ctx), (__half*)G, ld, n_seq, seq_len, cols, halo);
   count_launch();
   return check_launch("kfp16_fold_edges") ? 0 : -1;
 }
@@ -996,9 +1028,9 @@ int kfp16_pack_rows(kfp16_ctx* ctx, const void* src, void* dst, int ld, int n_se
   if (!src || !dst) { set_error("kfp16_pack_rows: null pointer"); return -1; }
   const size_t elems = (size_t)n_seq * (seq_len + 2 * halo) * cols;
   if ((cols % 8) == 0 && (ld % 8) == 0 && al16(src) && al16(dst))
-    pack_rows_kernel<8><<<grid_for(elems / 8), kThreads, 0, ctx_stream(ctx)>>>((const __half*)src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
+    launch_pdl(pack_rows_kernel<8>, grid_for(elems / 8), kThreads, 0, ctx_stream(ctx), (const __half*)src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
   else
-    pack_rows_kernel<1><<<grid_for(elems), kThreads, 0, ctx_stream(ctx)>>>((const __half*)src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
+    launch_pdl(pack_rows_kernel<1>, grid_for(elems), kThreads, 0, ctx_stream(ctx), (const __half*)src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
   count_launch();
   return check_launch("kfp16_pack_rows") ? 0 : -1;
 }
@@ -1047,9 +1079,9 @@ int kfp16_half_sq_loss(kfp16_ctx* ctx, const void* Y, void* dY, int n_seq, int s
   if (!Y || !dY || !loss_dev) { set_error("kfp16_half_sq_loss: null pointer"); return -1; }
   const size_t elems = (size_t)n_seq * (seq_len + 2 * halo) * cols;
   if ((cols % 8) == 0 && al16(Y) && al16(dY))
-    half_sq_loss_kernel<8><<<grid_for(elems / 8), kThreads, 0, ctx_stream(ctx)>>>((const __half*)Y, (__half*)dY, n_seq, seq_len, halo, cols, loss_dev);
+    launch_pdl(half_sq_loss_kernel<8>, grid_for(elems / 8), kThreads, 0, ctx_stream(ctx), (const __half*)Y, (__half*)dY, n_seq, seq_len, halo, cols, loss_dev);
   else
-    half_sq_loss_kernel<1><<<grid_for(elems), kThreads, 0, ctx_stream(ctx)>>>((const __half*)Y, (__half*)dY, n_seq, seq_len, halo, cols, loss_dev);
+    launch_pdl(half_sq_loss_kernel<1>, grid_for(elems), kThreads, 0, ctx_stream(ctx), (const __half*)Y, (__half*)dY, n_seq, seq_len, halo, cols, loss_dev);
   count_launch();
   return check_launch("kfp16_half_sq_loss") ? 0 : -1;
 }
@@ -1064,12 +1096,20 @@ static int bn_relu_bwd_launch(kfp16_ctx* ctx, void* dY, int ldy, const float* sc
     set_error("kfp16_bn_relu_backward_bias_fold: rows must be whole sequence blocks of seq_len + 2*halo, out of place"); return -1;
   }
   const int gx = (cols + 255) / 256;
-  int gy = (num_sms_cached() * 4 + gx - 1) / gx;      // ~4 resident 256-thread blocks per SM, 4 row loads in flight per thread
+  // exactly ONE wave of resident blocks (a few blocks more than fit spill into a second, nearly empty wave that
+  // doubles the kernel time: measured 25 us -> 12 us on 9984 x 1536)
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bn_relu_bwd_colsum_kernel, 256, 0) != cudaSuccess || b < 1) b = 1;
+    blocks_per_sm = b;
+  }
+  int gy = (num_sms_cached() * blocks_per_sm) / gx;
   const int max_gy = (rows + 8 * kBnBwdRows - 1) / (8 * kBnBwdRows);
   if (gy > max_gy) gy = max_gy;
   if (gy < 1) gy = 1;
-  bn_relu_bwd_colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, ctx_stream(ctx)>>>(
-      (__half*)dY, ldy, scale, mask, mask_ld, (__half*)dZ, ldz, (size_t)rows, cols, db_accum, blk, seq_len, halo);
+  launch_pdl(bn_relu_bwd_colsum_kernel, dim3(gx, gy), dim3(32, 8), 0, ctx_stream(ctx),
+             (__half*)dY, ldy, scale, mask, mask_ld, (__half*)dZ, ldz, (size_t)rows, cols, db_accum, blk, seq_len, halo);
   count_launch();
   return check_launch("kfp16_bn_relu_backward_bias") ? 0 : -1;
 }

@@ -18,6 +18,10 @@ namespace kfp16 {
 // ------------------------------------------------------------------ errors / counters
 static thread_local char g_err[512] = {0};
 std::atomic<unsigned long long> g_launches{0};
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("KFP16_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 static cudaStream_t g_default_stream = nullptr;
 
 void set_error(const char* fmt, ...) {

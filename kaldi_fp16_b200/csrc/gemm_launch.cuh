@@ -35,13 +35,15 @@ static bool launch_cfg(kfp16_ctx* ctx, const GemmParams& p, int grid) {
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // the kernel calls griddep_wait() after its prologue
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   count_launch();
   return check_cuda(e, "gemm_f16_sm100 launch");

@@ -248,10 +248,15 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     if (CG == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
     else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
+  // programmatic dependent launch: the next kernel in the stream may be scheduled from here on (its CTAs start as
+  // ours exit); everything above touched only parameters / shared memory / TMEM, everything below may read what the
+  // previous kernel wrote, so wait for it here
+  griddep_launch();
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
 
   // The three single-issuer roles below run with the whole warp converged and elect ONE lane only around
   // the TMA / tcgen05 instructions: every address and descriptor is then warp-uniform, so ptxas keeps them

@@ -42,6 +42,25 @@ cudaStream_t default_stream();
 bool check_launch(const char* what);
 bool check_cuda(cudaError_t e, const char* what);
 
+// Programmatic dependent launch (KFP16_PDL=0 disables): kernels that call griddep_wait() before their first
+// global access are launched with the stream-serialization attribute, so consecutive launches overlap their
+// launch latency / prologue with the predecessor's tail (also inside captured graphs: programmatic edges).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // stream-explicit forms of a few reference ops, used by the network executor (elementwise.cu)
 int softmax_on_stream(cudaStream_t stream, void* data, int rows, int cols, bool log);
 int ops_concat_cols_on(cudaStream_t stream, void* dst, int T, int dst_cols, const void* src, int src_cols, int dst_col_offset);

@@ -298,6 +298,14 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// ------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
+// the stream is still running: it must not touch global memory before griddep_wait() (which returns once the
+// predecessor grid has completed and its writes are visible).  griddep_launch() lets the NEXT kernel's CTAs be
+// scheduled as soon as SM resources free up, so its launch latency and prologue overlap this kernel's tail.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // ------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128B/64B swizzle.
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
