@@ -250,7 +250,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if (d->M <= kBM) cg = 1;
   bool share = false;
   int span = 0, min_off = 0;
-  if (cg == 2 && kslabs == 2 && groups == 1 && !a_mn && !(flags & EPI_SPLITK) && env_share && !d->no_share &&
+  if (cg == 2 && kslabs == 2 && groups == 1 && !a_mn && !(flags & EPI_SPLITK) && env_share && d->no_share != 1 &&
       d->a_col_off[0][0] == d->a_col_off[0][1]) {
     min_off = d->a_row_off[0][0] < d->a_row_off[0][1] ? d->a_row_off[0][0] : d->a_row_off[0][1];
     span = d->a_row_off[0][0] + d->a_row_off[0][1] - 2 * min_off;
@@ -336,8 +336,14 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     cudaEventRecord(ev0, ctx->stream);
   }
   bool ok = false;
+  // small-K spliced GEMMs on 128-wide tiles may keep their A tile resident (SHARE mode 2: 6 B stages of look-ahead,
+  // a third less L2->SM traffic).  Measured on the TDNN-F affine / dX shapes it is NOT faster (24.1 vs 23.4 us,
+  // 22.0 vs 20.2 us in-graph: those kernels are bound by the per-SM TMA throughput of B + residual + output), so it
+  // is opt-in: d->no_share == 3 or KFP16_ASTAT=1.
+  static const int env_astat = getenv("KFP16_ASTAT") ? atoi(getenv("KFP16_ASTAT")) : 0;
+  const bool astat = share && bn == 128 && (kslab_len + kBK - 1) / kBK <= 3 && split_k == 1 && (env_astat || d->no_share == 3) && d->no_share != 2;
   GemmLaunch L;
-  L.bn = bn; L.a_mn = a_mn; L.b_mn = b_mn; L.ek = ek; L.cg = cg; L.share = share; L.grid = grid;
+  L.bn = bn; L.a_mn = a_mn; L.b_mn = b_mn; L.ek = ek; L.cg = cg; L.share = share ? (astat ? 2 : 1) : 0; L.grid = grid;
   switch (bn) {
     case 64: ok = launch_gemm_bn<64>(ctx, p, L); break;
     case 128: ok = launch_gemm_bn<128>(ctx, p, L); break;
@@ -351,7 +357,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     ctx->prof_flops.push_back(2.0 * d->M * d->N * d->K * groups);
     char desc[160];
     snprintf(desc, sizeof(desc), "M=%d N=%d K=%d g=%d slabs=%d split=%d bn=%d A%s B%s flags=0x%x ek=%d cg=%d share=%d grid=%d", d->M, d->N, d->K,
-             groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, ek, cg, (int)share, grid);
+             groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, ek, cg, L.share, grid);
     ctx->prof_desc.push_back(desc);
   }
   return ok ? 0 : -1;

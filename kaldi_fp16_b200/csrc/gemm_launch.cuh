@@ -15,11 +15,11 @@ struct GemmLaunch {
   bool a_mn, b_mn;   // operand majors
   int ek;            // EpiKind
   int cg;            // 1 = one CTA per tile, 2 = CTA pair (cta_group::2, 256-row tiles)
-  bool share;        // both splice slabs read one A tile
+  int share;         // 1: both splice slabs read one A tile; 2: and that tile stays resident (small K, BN 128)
   int grid;          // CTAs (even when cg == 2)
 };
 
-template <int BN, bool A_MN, bool B_MN, int EK, int CG, bool SHARE>
+template <int BN, bool A_MN, bool B_MN, int EK, int CG, int SHARE>
 static bool launch_cfg(kfp16_ctx* ctx, const GemmParams& p, int grid) {
   using Cfg = GemmCfg<BN, A_MN, B_MN, EK, CG, SHARE>;
   auto kern = gemm_f16_sm100<BN, A_MN, B_MN, EK, CG, SHARE>;
@@ -58,6 +58,26 @@ template <int BN>
 bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
   const int g = L.grid;
 #define KFP16_CASE(A, B, EK, CG, SH) return launch_cfg<BN, A, B, EK, CG, SH>(ctx, p, g)
+  if constexpr (BN == 128) {
+    if (L.share == 2 && !L.a_mn) {
+      if (L.b_mn) {
+        switch (L.ek) {
+          case EK_PLAIN: KFP16_CASE(false, true, EK_PLAIN, 2, 2);
+          case EK_AFFINE: KFP16_CASE(false, true, EK_AFFINE, 2, 2);
+          case EK_AFFINE_RES: KFP16_CASE(false, true, EK_AFFINE_RES, 2, 2);
+          default: break;
+        }
+      } else {
+        switch (L.ek) {
+          case EK_PLAIN: KFP16_CASE(false, false, EK_PLAIN, 2, 2);
+          case EK_RESID: KFP16_CASE(false, false, EK_RESID, 2, 2);
+          default: break;
+        }
+      }
+      set_error("internal: no A-stationary kernel for epilogue kind %d", L.ek);
+      return false;
+    }
+  }
   if (!L.a_mn && L.b_mn) {
     if (L.share) {
       switch (L.ek) {
@@ -141,7 +161,7 @@ bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
 }
 
 // true when launch_gemm_bn has a kernel for this combination
-inline bool gemm_variant_exists(bool a_mn, bool b_mn, int ek, int cg, bool share) {
+inline bool gemm_variant_exists(bool a_mn, bool b_mn, int ek, int cg, int share) {
   if (share) {
     if (a_mn || cg != 2) return false;   // the shared splice tile exists for CTA pairs only
     if (b_mn) return ek == EK_PLAIN || ek == EK_AFFINE || ek == EK_AFFINE_RES;

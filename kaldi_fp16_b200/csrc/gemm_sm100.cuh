@@ -129,17 +129,24 @@ __device__ __forceinline__ float relu_nan(float x) {
 }
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
-template <int BN, bool A_MN, bool B_MN, int EK, int CG, bool SHARE>
+template <int BN, bool A_MN, bool B_MN, int EK, int CG, int SHARE>   // SHARE: 0 none, 1 shared splice tile, 2 = 1 + resident A tile
 struct GemmCfg {
   static_assert(CG == 1 || CG == 2, "cta_group 1 or 2");
   static_assert(!SHARE || !A_MN, "the shared splice tile is implemented for a K-major A");
+  static_assert(SHARE >= 0 && SHARE <= 2, "SHARE mode");
   static constexpr bool kSplitK = EK == EK_SPLITK;
   static constexpr uint32_t kFlags = epi_kind_flags(EK);
   static constexpr bool kMayUseR = EK == EK_GENERIC || (kFlags & (EPI_RESID | EPI_BETA)) != 0;
   static constexpr bool kUsesVec = EK == EK_GENERIC || (kFlags & (EPI_BIAS | EPI_BN)) != 0;
   // staging ring: 4 chunks when a residual tile is prefetched into it (in-place epilogue), else 2
   // (6 when the tile is narrow enough to afford it: the residual prefetch then runs 4 chunks ahead)
-  static constexpr int kRing = kSplitK ? 0 : (kMayUseR ? (BN <= 160 ? 6 : 4) : 4);
+  // A-stationary (SHARE == 2, small K: the TDNN-F affine / input-gradient GEMMs with K = 2 x 160): the whole A tile
+  // (kAKb k-blocks) stays resident in shared memory while the unit walks the N tiles of one row block, and only B
+  // tiles stream through the ring -- 6 B stages = two tiles of look-ahead instead of one (the 3-stage A+B ring
+  // exposed the full load latency on every 5-k-block tile: ~3000 cycles per tile against 1280 of MMA).
+  static constexpr bool kAStat = SHARE == 2;
+  static constexpr int kAKb = 3;
+  static constexpr int kRing = kSplitK ? 0 : (kAStat ? 4 : (kMayUseR ? (BN <= 160 ? 6 : 4) : 4));
   // TMA stores left in flight when a chunk is handed over (a store's smem-read latency is ~1000 cycles:
   // with none in flight every 64-column chunk paid it in full)
   static constexpr int kStoreWait = kRing == 6 ? 3 : (kMayUseR ? 1 : 2);   // < kRing
@@ -150,14 +157,15 @@ struct GemmCfg {
   static constexpr int kABytes = SHARE ? (kBM + 8) * kBK * 2 : kBM * kBK * 2;
   static constexpr int kBTileBytes = B_MN ? kBChunks * 64 * kBK * 2 : kBNLocal * kBK * 2;
   static constexpr int kNumBTiles = SHARE ? 2 : 1;
-  static constexpr int kStageBytes = kABytes + kNumBTiles * kBTileBytes;
+  static constexpr int kStageBytes = (kAStat ? 0 : kABytes) + kNumBTiles * kBTileBytes;
+  static constexpr int kAResBytes = kAStat ? kAKb * kABytes : 0;
   static constexpr int kEpiBytes = kRing * kChunkBytes + (kUsesVec ? 2 * kVecBytes : 0);   // vectors double-buffered
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
-  static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes) / kStageBytes;
+  static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes - kAResBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kAResBytes + kStages * kStageBytes + kEpiBytes + 1024 + 512;
   static_assert(kStages >= 2, "tile too large for shared memory");
   static_assert(kStageBytes % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N; epilogue works on 32-column halves");
@@ -165,9 +173,10 @@ struct GemmCfg {
 
 // Tile bookkeeping shared by all warp roles.  A "unit" is a CTA (CG = 1) or a CTA pair (CG = 2);
 // a tile is kBM*CG rows x BN columns and this CTA owns rows m_row0 .. m_row0+127 of it.
-template <int BN, int CG>
+template <int BN, int CG, bool CONTIG = false>
 struct TileIter {
   int m_tiles, n_tiles, tiles_per_split, total_tiles, unit, nunits, rank;
+  int first, last, step;   // this unit's tiles: first, first + step, ... < last
   __device__ __forceinline__ TileIter(const GemmParams& p) {
     m_tiles = (p.M + kBM * CG - 1) / (kBM * CG);
     n_tiles = (p.N + BN - 1) / BN;
@@ -177,6 +186,13 @@ struct TileIter {
     nunits = gridDim.x / CG;
     rank = CG == 2 ? (int)cluster_ctarank() : 0;
     p_groups = p.groups;
+    if (CONTIG) {   // a contiguous run of tiles (N fastest): consecutive tiles of a unit share their A row block
+      first = (int)(((long long)unit * total_tiles) / nunits);
+      last = (int)(((long long)(unit + 1) * total_tiles) / nunits);
+      step = 1;
+    } else {        // round-robin
+      first = unit; last = total_tiles; step = nunits;
+    }
   }
   __device__ __forceinline__ void decode(int tile, int& n_blk, int& m_row0, int& g, int& ks) const {
     int id = tile;
@@ -193,7 +209,7 @@ __device__ __forceinline__ void dbg_stamp(const GemmParams& p, int role, int til
     p.dbg[(((size_t)blockIdx.x * 3 + role) * 8 + tile_i) * 16 + slot] = clock64();
 }
 
-template <int BN, bool A_MN, bool B_MN, int EK, int CG, bool SHARE>
+template <int BN, bool A_MN, bool B_MN, int EK, int CG, int SHARE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN, A_MN, B_MN, EK, CG, SHARE>;
@@ -205,9 +221,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
+  uint8_t* smem_ring = smem + Cfg::kAResBytes;     // operand stages (after the resident A tile, if any)
+  uint8_t* smem_epi = smem_ring + kStages * Cfg::kStageBytes;
   uint8_t* smem_vec = smem_epi + kRing * kChunkBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
   uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA          (CG=2: the leader's is used)
   uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA          (CG=2: commit multicast to both CTAs)
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue     (CG=2: commit multicast)
@@ -215,14 +232,16 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   uint64_t* rfull_bar = tempty_bar + 2;       // [8]        residual TMA -> epilogue
   uint64_t* rempty_bar = rfull_bar + 8;       // [8]        output store drained -> residual TMA / next writer
   uint64_t* cfull_bar = rempty_bar + 8;       // [8]        epilogue warps wrote a chunk -> store warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull_bar + 8);
+  uint64_t* afull_bar = cfull_bar + 8;        // [1]        resident A tile landed (CG=2: the leader's is used)
+  uint64_t* aempty_bar = afull_bar + 1;       // [1]        MMAs on the resident A tile done (commit multicast)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t flags = kGeneric ? p.flags : Cfg::kFlags;
   const bool use_r = Cfg::kMayUseR && (flags & (EPI_RESID | EPI_BETA)) != 0;
 
-  const TileIter<BN, CG> ti(p);
+  const TileIter<BN, CG, Cfg::kAStat> ti(p);
   const int total_tiles = ti.total_tiles;
   const int rank = ti.rank;
   const int kb_per_slab = (p.kslab_len + kBK - 1) / kBK;
@@ -242,6 +261,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       mbar_init(&tempty_bar[i], CG * (kEpiThreads / 32));   // one arrive per epilogue warp (of both CTAs)
     }
     for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 1); mbar_init(&cfull_bar[i], kEpiThreads / 32); }
+    mbar_init(afull_bar, CG); mbar_init(aempty_bar, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -265,23 +285,42 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   if (warp == 0) {
     // ===================================================== TMA producer
     int stage = 0; uint32_t phase = 0;
-    const uint32_t stage_tx = SHARE ? (uint32_t)(p.a_box_bytes + p.kslabs * Cfg::kBTileBytes)
-                                    : (uint32_t)(Cfg::kABytes + Cfg::kBTileBytes);
+    const uint32_t stage_tx = Cfg::kAStat ? (uint32_t)(p.kslabs * Cfg::kBTileBytes)
+                              : SHARE ? (uint32_t)(p.a_box_bytes + p.kslabs * Cfg::kBTileBytes)
+                                      : (uint32_t)(Cfg::kABytes + Cfg::kBTileBytes);
+    int a_m = -1; uint32_t a_phase = 0;   // resident A tile: row block it holds, load count parity
     int tile_i = 0;
-    for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits, ++tile_i) {
+    for (int tile = ti.first; tile < ti.last; tile += ti.step, ++tile_i) {
       int n_blk, m_row0, g, ks;
       ti.decode(tile, n_blk, m_row0, g, ks);
       const int kb0 = ks * kb_per_split;
       const int kb1 = min(kb0 + kb_per_split, kb_total);
       const int n_loc = n_blk * BN + rank * Cfg::kBNLocal;     // first B row / column staged by this CTA
       dbg_stamp(p, 0, tile_i, 0);
+      if (Cfg::kAStat && m_row0 != a_m) {
+        // new row block: once the MMAs on the previous resident tile are complete, load all its k-blocks
+        a_m = m_row0;
+        mbar_wait(aempty_bar, a_phase ^ 1);
+        a_phase ^= 1;
+        if (elect_one()) {
+          const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(afull_bar), 0) : 0;
+          const uint32_t tx = (uint32_t)(kb_per_slab * p.a_box_bytes);
+          if (CG == 2) mbar_arrive_expect_tx_cluster(fb, tx);
+          else mbar_arrive_expect_tx(afull_bar, tx);
+          for (int kb = 0; kb < kb_per_slab; ++kb) {
+            if (CG == 2) tma_load_2d_pair(smem + kb * Cfg::kABytes, &p.tmA, fb, kb * kBK + p.a_col_off[g][0], m_row0 + p.a_row_off[g][0]);
+            else tma_load_2d(smem + kb * Cfg::kABytes, &p.tmA, afull_bar, kb * kBK + p.a_col_off[g][0], m_row0 + p.a_row_off[g][0]);
+          }
+        }
+        __syncwarp();
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         const int slab = SHARE ? 0 : kb / kb_per_slab;
         const int k_in = (kb - slab * kb_per_slab) * kBK;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
+          uint8_t* sa = smem_ring + stage * Cfg::kStageBytes;
+          uint8_t* sb = Cfg::kAStat ? sa : sa + Cfg::kABytes;
           // completion is signalled on this CTA's full barrier (CG=1) or the pair leader's (CG=2)
           const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[stage]), 0) : 0;
           if (CG == 2) mbar_arrive_expect_tx_cluster(fb, stage_tx);
@@ -290,7 +329,9 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             if (CG == 2) tma_load_2d_pair(dst, m, fb, c0, c1);
             else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
           };
-          if (!A_MN) {
+          if (Cfg::kAStat) {
+            // A is resident
+          } else if (!A_MN) {
             load(sa, &p.tmA, k_in + p.a_col_off[g][slab], m_row0 + p.a_row_off[g][slab]);
           } else {
 #pragma unroll
@@ -328,8 +369,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       constexpr uint32_t b_lbo = B_MN ? 64 * kBK * 2 : 16, b_sbo = 1024;
       constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4;   // descriptor units (16 B) per UMMA K=16
       constexpr uint32_t b_kstep = (B_MN ? 2048 : 32) >> 4;
-      const uint64_t adesc0 = make_smem_desc(smem_u32(smem), a_lbo, a_sbo, kLayoutSW128);
-      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, b_lbo, b_sbo, kLayoutSW128);
+      // A-stationary: A descriptors address the resident tile (k-block kb at kb * kABytes), B the ring stages
+      const uint64_t adesc0 = make_smem_desc(smem_u32(Cfg::kAStat ? smem : smem_ring), a_lbo, a_sbo, kLayoutSW128);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_ring) + (Cfg::kAStat ? 0 : Cfg::kABytes), b_lbo, b_sbo, kLayoutSW128);
+      int a_m = -1; uint32_t a_phase = 0;
       auto mma = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t accum) {
         if (CG == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum);
         else umma_f16(d_tmem, ad, bd, idesc, accum);
@@ -337,7 +380,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int tile_i = 0;
-      for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits, ++tile_i) {
+      for (int tile = ti.first; tile < ti.last; tile += ti.step, ++tile_i) {
         const int ks = tile / ti.tiles_per_split;
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
@@ -346,6 +389,17 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         tc_fence_after();
         dbg_stamp(p, 1, tile_i, 1);
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
+        bool a_last = false;     // last tile of this unit on the resident A tile -> release it after the MMAs
+        if (Cfg::kAStat) {
+          const int m_cur = (tile / ti.n_tiles) % ti.m_tiles;
+          if (m_cur != a_m) {
+            a_m = m_cur;
+            mbar_wait(afull_bar, a_phase);
+            a_phase ^= 1;
+            tc_fence_after();
+          }
+          a_last = tile + 1 >= ti.last || ((tile + 1) / ti.n_tiles) % ti.m_tiles != m_cur;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const int slab = SHARE ? 0 : kb / kb_per_slab;
           const int k_in = (kb - slab * kb_per_slab) * kBK;
@@ -361,7 +415,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
               // 128-byte rows.  Measured on B200: the 128B swizzle is applied on the absolute shared-memory
               // address bits, so the descriptor's base-offset field stays 0 (setting it to the row phase,
               // as the CUTLASS comment on that field suggests for unaligned starts, gives wrong products).
-              const uint64_t ad = adesc0 + so + (SHARE ? (uint64_t)((uint32_t)p.a_shift[t] * 8u) : 0ull);
+              const uint64_t ad = adesc0 + (Cfg::kAStat ? (uint64_t)((uint32_t)(kb * Cfg::kABytes) >> 4) : so) +
+                                  (SHARE ? (uint64_t)((uint32_t)p.a_shift[t] * 8u) : 0ull);
               const uint64_t bd = bdesc0 + so + (uint64_t)((uint32_t)(t * Cfg::kBTileBytes) >> 4);
               const uint32_t first = (kb > kb0 || t > 0) ? 1u : 0u;
               if (k16s == 4 && p.mma_rep <= 1) {
@@ -382,6 +437,9 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         }
         if (elect_one()) {
           if (CG == 2) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+          if (Cfg::kAStat && a_last) {
+            if (CG == 2) umma_commit_pair(aempty_bar); else umma_commit(aempty_bar);
+          }
         }
         __syncwarp();
         dbg_stamp(p, 1, tile_i, 3);
@@ -392,7 +450,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     // =========================================== residual / C-in prefetch
     if (Cfg::kMayUseR && use_r) {
       int buf = 0; uint32_t round = 0;     // ring position of the running chunk counter
-      for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+      for (int tile = ti.first; tile < ti.last; tile += ti.step) {
         int n_blk, m_row0, g, ks;
         ti.decode(tile, n_blk, m_row0, g, ks);
         for (int c64 = 0; c64 < BN; c64 += 64) {
@@ -413,7 +471,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     // (measured before: a 256-thread barrier + the store issue on the critical thread cost as much as the math).
     if (!kSplitK) {
       int buf = 0; uint32_t round = 0; int fbuf = 0; int k = 0;
-      for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits) {
+      for (int tile = ti.first; tile < ti.last; tile += ti.step) {
         int n_blk, m_row0, g, ks;
         ti.decode(tile, n_blk, m_row0, g, ks);
         for (int c64 = 0; c64 < BN; c64 += 64, ++k) {
@@ -448,7 +506,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     int vsel = 0;
     __half nbias = __float2half(0.f); float nscale = 0.f, nshift = 0.f;
     auto vec_fetch = [&](int tile) {
-      if (epi_tid < BN && tile < total_tiles) {
+      if (epi_tid < BN && tile < ti.last) {
         int n_blk, m_row0, g, ks;
         ti.decode(tile, n_blk, m_row0, g, ks);
         const int col = n_blk * BN + epi_tid;
@@ -471,11 +529,11 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         }
       }
     };
-    if (use_vec) { vec_fetch(ti.unit); vec_store(0); }
+    if (use_vec) { vec_fetch(ti.first); vec_store(0); }
     const uint32_t tempty_leader[2] = {CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u,
                                        CG == 2 ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
     int tile_i = 0;
-    for (int tile = ti.unit; tile < total_tiles; tile += ti.nunits, ++tile_i) {
+    for (int tile = ti.first; tile < ti.last; tile += ti.step, ++tile_i) {
       int n_blk, m_row0, g, ks;
       ti.decode(tile, n_blk, m_row0, g, ks);
       const int row = m_row0 + row_in_tile;
@@ -486,7 +544,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       const uint32_t s_scale = s_bias + 512, s_shift = s_bias + 512 + 1024;     // fp32 [BN] each
       if (use_vec) {
         named_bar_sync(2, kEpiThreads);      // this tile's vectors (stored at the end of the previous tile) are visible
-        vec_fetch(tile + ti.nunits);         // next tile's: in flight while this tile is processed
+        vec_fetch(tile + ti.step);           // next tile's: in flight while this tile is processed
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);

@@ -317,3 +317,48 @@ def test_split_k_transposed_target(handle, lib, M, N, K, groups):
         want = Bg.T @ At.astype(np.float64)
         absprod = np.abs(Bg).T @ np.abs(At).astype(np.float64)
         assert_close(got[g], want, 2.0 ** -19 * absprod + 1e-6, f"transposed split-K group {g}")
+
+
+@pytest.mark.parametrize("max_ctas", [0, 6, 10])
+@pytest.mark.parametrize("T,D,N,s0,s1,b_k_major,resid", [(900, 160, 512, 0, 3, False, True), (2100, 160, 1536, 3, 0, True, True),
+                                                         (1300, 128, 384, -3, 0, False, False), (9984, 160, 1536, 0, 3, False, True)])
+def test_a_stationary_spliced_gemm(handle, lib, max_ctas, T, D, N, s0, s1, b_k_major, resid):
+    """small-K spliced GEMMs (the TDNN-F affine / input-gradient shapes, K = 2 x 160) keep their A tile resident in
+    shared memory while a CTA pair walks a contiguous run of N tiles: same result as the streaming shared-tile kernel
+    (no_share = 2) and the oracle, also when a unit's run crosses row blocks (few CTAs) and with the bypass epilogue"""
+    halo = 3
+    rng = np.random.default_rng(T + D + N)
+    X = rand_f16(rng, (T, D))
+    W = rand_f16(rng, (2 * D, N), 0.08)
+    R = rand_f16(rng, (T, N))
+    Xp = np.concatenate([np.repeat(X[:1], halo, 0), X, np.repeat(X[-1:], halo, 0)], 0)
+    i0, i1 = np.clip(np.arange(T) + s0, 0, T - 1), np.clip(np.arange(T) + s1, 0, T - 1)
+    S = np.concatenate([X[i0], X[i1]], 1)
+    acc = S.astype(np.float64) @ W.astype(np.float64)
+    want = acc + (0.66 * R if resid else 0.0)
+    tXp, tR = gpu.TensorFromFP16(Xp), gpu.TensorFromFP16(R)
+    Bst = np.concatenate([W[:D].T, W[D:].T], 0) if b_k_major else W
+    tW = gpu.TensorFromFP16(np.ascontiguousarray(Bst))
+    lib.kfp16_ctx_set_max_ctas(handle.ptr, max_ctas)
+    outs = []
+    try:
+        for no_share in (3, 2):
+            tD = gpu.ZeroTensor(T, N)
+            d = make_desc(T, N, 2 * D, tXp, tW, tD, b_major=K_MAJOR if b_k_major else MN_MAJOR, force_cg=2, force_bn=128,
+                          no_share=no_share, flags=EPI_RESID if resid else 0, res_scale=0.66, ldr=N)
+            d.R[0] = tR.Ptr
+            d.A.ptr = tXp.Ptr + halo * D * 2
+            d.A.rows, d.A.halo = T, halo
+            d.kslabs, d.kslab_len = 2, D
+            d.a_row_off[0][0], d.a_row_off[0][1] = s0, s1
+            d.b_row_off[0][0], d.b_row_off[0][1] = 0, (N if b_k_major else D)
+            run_desc(handle, d)
+            outs.append(tD.ToFP32())
+            tD.Free()
+    finally:
+        lib.kfp16_ctx_set_max_ctas(handle.ptr, 0)
+    tol = gemm_tol(S, W, want) + (2.0 ** -10 * np.abs(0.66 * R) if resid else 0.0)
+    assert_close(outs[0], want, tol, f"A-stationary T={T} N={N} ctas={max_ctas}")
+    assert np.array_equal(outs[0], outs[1])      # same k-block / slab order -> same fp32 accumulation order
+    for t in (tXp, tW, tR):
+        t.Free()
