@@ -100,7 +100,8 @@ typedef struct {
     int force_cg;      /* 0 = heuristic; 1 = one CTA per 128-row tile; 2 = CTA pairs (cta_group::2, 256-row tiles) */
     int no_share;      /* 1 = load each splice slab's A tile separately even when one shifted tile could serve both;
                           2 = share the tile, never keep it resident across N tiles; 3 = share it and keep it resident
-                          (A-stationary mode, small K on 128-wide tiles; default off, see gemm_api.cu) */
+                          (A-stationary mode, small K on 128-wide tiles; default off, see gemm_api.cu);
+                          4 = merge the two row-shifted groups of a split-K weight gradient into one tile pass (default off) */
     void *debug_clock_buf; /* profiling: device int64 [grid][3 roles][8 tiles][16] clock64 stamps per warp role; NULL = off */
 } kfp16_gemm_desc;
 

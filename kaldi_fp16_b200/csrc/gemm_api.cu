@@ -245,6 +245,8 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   static const int env_share = getenv("KFP16_SHARE") ? atoi(getenv("KFP16_SHARE")) : 1;
   p.dbg = (long long*)d->debug_clock_buf;
   p.mma_rep = getenv("KFP16_MMAREP") ? atoi(getenv("KFP16_MMAREP")) : 1;
+  static const int env_norot = getenv("KFP16_NOROT") ? atoi(getenv("KFP16_NOROT")) : 0;
+  p.no_rotate = env_norot;
   int cg = d->force_cg ? d->force_cg : (env_cg ? env_cg : 2);
   if (cg != 1 && cg != 2) { set_error("kfp16_gemm_ex: force_cg must be 0, 1 or 2"); return -1; }
   if (d->M <= kBM) cg = 1;
@@ -257,11 +259,31 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     share = span <= 8 && gemm_variant_exists(a_mn, b_mn, ek, 2, true);
   }
   if (cg == 2 && !share && !gemm_variant_exists(a_mn, b_mn, ek, 2, false)) cg = 1;
+  // merged groups: the two groups of a spliced weight gradient (dW_g = sum_k A[k + a_off_g]^T B[k + b_off_g]) differ
+  // only by row shifts of <= 8 -> ONE A and ONE B tile of 64+span k-rows per k-block, read through row-shifted
+  // descriptors into the two TMEM accumulator stages: half the L2->SM traffic of two separate groups
+  // Measured on the TDNN-F shapes it halves the main loop's load traffic (7.0 -> 5.2 us) but doubles the fp32
+  // reductions per unit (the L2 atomic throughput, ~3.5 TB/s, is the wall: 3.3 -> 6.7 us), so it is opt-in:
+  // d->no_share == 4 or KFP16_MERGE=1.
+  static const int env_merge = getenv("KFP16_MERGE") ? atoi(getenv("KFP16_MERGE")) : 0;
+  bool merge = false;
+  int ma_min = 0, mb_min = 0, ma_span = 0, mb_span = 0;
+  if (cg == 2 && groups == 2 && kslabs == 1 && a_mn && b_mn && (flags & EPI_SPLITK) && (env_merge || d->no_share == 4) && d->no_share != 1 &&
+      d->N > 128 && d->N <= 160 && !d->force_bn &&
+      d->a_col_off[0][0] == d->a_col_off[1][0] && d->b_col_off[0][0] == d->b_col_off[1][0]) {
+    ma_min = d->a_row_off[0][0] < d->a_row_off[1][0] ? d->a_row_off[0][0] : d->a_row_off[1][0];
+    mb_min = d->b_row_off[0][0] < d->b_row_off[1][0] ? d->b_row_off[0][0] : d->b_row_off[1][0];
+    ma_span = d->a_row_off[0][0] + d->a_row_off[1][0] - 2 * ma_min;
+    mb_span = d->b_row_off[0][0] + d->b_row_off[1][0] - 2 * mb_min;
+    merge = ma_span <= 8 && mb_span <= 8;
+  }
+  const int tile_groups = merge ? 1 : groups;     // groups that multiply the tile count
 
   const int tile_m = kBM * cg;
   const int m_tiles = (d->M + tile_m - 1) / tile_m;
   const int kb_total = (share ? 1 : kslabs) * ((kslab_len + kBK - 1) / kBK);
   int split_k = d->split_k > 1 ? d->split_k : 1;
+  if (merge) split_k *= 2;     // same number of work items as the two separate groups had
   if (split_k > kb_total) split_k = kb_total;
   if (split_k > 1) {   // make every split non-empty
     const int per = (kb_total + split_k - 1) / split_k;
@@ -273,7 +295,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if (ctx->max_ctas > 0 && ctx->max_ctas < ctas) ctas = ctx->max_ctas;
   int units = ctas / cg;                 // CTAs or CTA pairs that can be resident
   if (units < 1) { units = 1; }
-  int bn = d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, groups, split_k, units);
+  int bn = merge ? 160 : (d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, groups, split_k, units));
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) { set_error("kfp16_gemm_ex: unsupported tile width %d", bn); return -1; }
   if (!(flags & EPI_SPLITK) && (bn % 64) != 0 && d->N > bn) {
     // the last 64-wide store chunk of a 160-wide tile would spill into the next tile
@@ -283,14 +305,23 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   // operand maps (halo rows are part of the mapped tensor so spliced reads can address them)
   const __half* a_base = (const __half*)A.ptr - (long long)A.halo * A.ld;
   const __half* b_base = (const __half*)B.ptr - (long long)B.halo * B.ld;
-  const int a_box_rows = a_mn ? 64 : (share ? kBM + span : kBM);
+  const int a_box_rows = a_mn ? (merge ? 64 + ma_span : 64) : (share ? kBM + span : kBM);
   if (!make_map_2d(&p.tmA, a_base, A.cols, (long long)A.rows + 2 * A.halo, A.ld, 64, a_box_rows, "A")) return -1;
-  if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? 64 : bn / cg, "B")) return -1;
+  if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? (merge ? 64 + mb_span : 64) : bn / cg, "B")) return -1;
   for (int g = 0; g < groups; ++g)
     for (int s = 0; s < kslabs; ++s) {
       p.a_row_off[g][s] = d->a_row_off[g][s] + A.halo; p.a_col_off[g][s] = d->a_col_off[g][s];
       p.b_row_off[g][s] = d->b_row_off[g][s] + B.halo; p.b_col_off[g][s] = d->b_col_off[g][s];
     }
+  if (merge) {
+    p.groups = 1;
+    p.a_shift[0] = d->a_row_off[0][0] - ma_min; p.a_shift[1] = d->a_row_off[1][0] - ma_min;
+    p.b_shift[0] = d->b_row_off[0][0] - mb_min; p.b_shift[1] = d->b_row_off[1][0] - mb_min;
+    p.a_row_off[0][0] = ma_min + A.halo;
+    p.b_row_off[0][0] = mb_min + B.halo;
+    const int b_chunks = (bn / cg + 63) / 64;
+    p.merge_tx = 2 * (64 + ma_span) * 128 + b_chunks * (64 + mb_span) * 128;
+  }
   if (share) {
     p.a_shift[0] = d->a_row_off[0][0] - min_off;
     p.a_shift[1] = d->a_row_off[0][1] - min_off;
@@ -327,7 +358,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     }
   }
 
-  const long long tiles = (long long)m_tiles * ((d->N + bn - 1) / bn) * groups * split_k;
+  const long long tiles = (long long)m_tiles * ((d->N + bn - 1) / bn) * tile_groups * split_k;
   const int grid = cg * (int)(tiles < units ? tiles : units);
   if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -343,7 +374,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   static const int env_astat = getenv("KFP16_ASTAT") ? atoi(getenv("KFP16_ASTAT")) : 0;
   const bool astat = share && bn == 128 && (kslab_len + kBK - 1) / kBK <= 3 && split_k == 1 && (env_astat || d->no_share == 3) && d->no_share != 2;
   GemmLaunch L;
-  L.bn = bn; L.a_mn = a_mn; L.b_mn = b_mn; L.ek = ek; L.cg = cg; L.share = share ? (astat ? 2 : 1) : 0; L.grid = grid;
+  L.bn = bn; L.a_mn = a_mn; L.b_mn = b_mn; L.ek = ek; L.cg = cg; L.share = merge ? 3 : (share ? (astat ? 2 : 1) : 0); L.grid = grid;
   switch (bn) {
     case 64: ok = launch_gemm_bn<64>(ctx, p, L); break;
     case 128: ok = launch_gemm_bn<128>(ctx, p, L); break;

@@ -15,7 +15,8 @@ struct GemmLaunch {
   bool a_mn, b_mn;   // operand majors
   int ek;            // EpiKind
   int cg;            // 1 = one CTA per tile, 2 = CTA pair (cta_group::2, 256-row tiles)
-  int share;         // 1: both splice slabs read one A tile; 2: and that tile stays resident (small K, BN 128)
+  int share;         // kernel MODE: 1 both splice slabs read one A tile; 2 and that tile stays resident (small K, BN 128);
+                     // 3 merged groups (spliced weight gradients, BN 160)
   int grid;          // CTAs (even when cg == 2)
 };
 
@@ -58,6 +59,13 @@ template <int BN>
 bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
   const int g = L.grid;
 #define KFP16_CASE(A, B, EK, CG, SH) return launch_cfg<BN, A, B, EK, CG, SH>(ctx, p, g)
+  if constexpr (BN == 160) {
+    if (L.share == 3) {
+      if (L.a_mn && L.b_mn && L.ek == EK_SPLITK && L.cg == 2) KFP16_CASE(true, true, EK_SPLITK, 2, 3);
+      set_error("internal: merged-group kernel needs MN-major operands, split-K and CTA pairs");
+      return false;
+    }
+  }
   if constexpr (BN == 128) {
     if (L.share == 2 && !L.a_mn) {
       if (L.b_mn) {

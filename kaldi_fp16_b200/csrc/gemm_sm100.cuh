@@ -102,6 +102,11 @@ struct GemmParams {
   // shared splice tile (SHARE kernels): slab s reads the A tile from row a_shift[s] (0..8) on
   int a_shift[kMaxSlabs];
   int a_box_bytes;              // bytes of the A box (128 + span rows) x 128 B
+  // merged groups (MODE 3): group g reads the A / B tile from k-row a_shift[g] / b_shift[g] (0..8) on; the tiles are
+  // loaded from row offsets a_row_off[0][0] / b_row_off[0][0]; merge_tx = bytes one CTA's loads deliver per k-block
+  int b_shift[kMaxSlabs];
+  int merge_tx;
+  int no_rotate;                // experiment knob: 1 = every split-K item walks its columns in the same order
   int mma_rep;                  // experiment knob: issue every UMMA this many times (0/1 = once)
   long long* dbg;               // profiling: per-CTA role timestamps [grid][3 roles][8 tiles][16] (nullptr = off)
 };
@@ -129,11 +134,17 @@ __device__ __forceinline__ float relu_nan(float x) {
 }
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
-template <int BN, bool A_MN, bool B_MN, int EK, int CG, int SHARE>   // SHARE: 0 none, 1 shared splice tile, 2 = 1 + resident A tile
+// MODE: 0 plain; 1 shared splice tile (one A tile of 128+8 rows serves both K slabs); 2 = 1 + resident A tile;
+//       3 merged groups (weight gradients of a spliced layer: both row-shifted groups read ONE A and ONE B tile of 64+8
+//         k-rows through shifted descriptors and accumulate into the two TMEM accumulator stages)
+template <int BN, bool A_MN, bool B_MN, int EK, int CG, int MODE>
 struct GemmCfg {
+  static constexpr bool SHARE = MODE == 1 || MODE == 2;
+  static constexpr bool kMerge = MODE == 3;
   static_assert(CG == 1 || CG == 2, "cta_group 1 or 2");
   static_assert(!SHARE || !A_MN, "the shared splice tile is implemented for a K-major A");
-  static_assert(SHARE >= 0 && SHARE <= 2, "SHARE mode");
+  static_assert(MODE >= 0 && MODE <= 3, "kernel mode");
+  static_assert(!kMerge || (A_MN && B_MN && EK == EK_SPLITK && CG == 2), "merged groups: MN-major operands, split-K, CTA pairs");
   static constexpr bool kSplitK = EK == EK_SPLITK;
   static constexpr uint32_t kFlags = epi_kind_flags(EK);
   static constexpr bool kMayUseR = EK == EK_GENERIC || (kFlags & (EPI_RESID | EPI_BETA)) != 0;
@@ -144,7 +155,7 @@ struct GemmCfg {
   // (kAKb k-blocks) stays resident in shared memory while the unit walks the N tiles of one row block, and only B
   // tiles stream through the ring -- 6 B stages = two tiles of look-ahead instead of one (the 3-stage A+B ring
   // exposed the full load latency on every 5-k-block tile: ~3000 cycles per tile against 1280 of MMA).
-  static constexpr bool kAStat = SHARE == 2;
+  static constexpr bool kAStat = MODE == 2;
   static constexpr int kAKb = 3;
   static constexpr int kRing = kSplitK ? 0 : (kAStat ? 4 : (kMayUseR ? (BN <= 160 ? 6 : 4) : 4));
   // TMA stores left in flight when a chunk is handed over (a store's smem-read latency is ~1000 cycles:
@@ -154,8 +165,10 @@ struct GemmCfg {
   static constexpr int kBNLocal = BN / CG;                     // B rows / columns staged by this CTA
   static constexpr int kBChunks = B_MN ? (kBNLocal + 63) / 64 : 1;   // 64-wide N chunks (MN-major)
   // SHARE: one A tile of 128+8 rows serves both splice slabs (row-shifted UMMA descriptors)
-  static constexpr int kABytes = SHARE ? (kBM + 8) * kBK * 2 : kBM * kBK * 2;
-  static constexpr int kBTileBytes = B_MN ? kBChunks * 64 * kBK * 2 : kBNLocal * kBK * 2;
+  // MN-major chunk = [k rows][64 M/N elements]: 64 k-rows, or 64+8 when the groups are merged (row-shifted reads)
+  static constexpr int kMnChunkBytes = (kMerge ? kBK + 8 : kBK) * 64 * 2;
+  static constexpr int kABytes = SHARE ? (kBM + 8) * kBK * 2 : (A_MN ? 2 * kMnChunkBytes : kBM * kBK * 2);
+  static constexpr int kBTileBytes = B_MN ? kBChunks * kMnChunkBytes : kBNLocal * kBK * 2;
   static constexpr int kNumBTiles = SHARE ? 2 : 1;
   static constexpr int kStageBytes = (kAStat ? 0 : kABytes) + kNumBTiles * kBTileBytes;
   static constexpr int kAResBytes = kAStat ? kAKb * kABytes : 0;
@@ -209,10 +222,12 @@ __device__ __forceinline__ void dbg_stamp(const GemmParams& p, int role, int til
     p.dbg[(((size_t)blockIdx.x * 3 + role) * 8 + tile_i) * 16 + slot] = clock64();
 }
 
-template <int BN, bool A_MN, bool B_MN, int EK, int CG, int SHARE>
+template <int BN, bool A_MN, bool B_MN, int EK, int CG, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_sm100(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, A_MN, B_MN, EK, CG, SHARE>;
+  using Cfg = GemmCfg<BN, A_MN, B_MN, EK, CG, MODE>;
+  constexpr bool SHARE = Cfg::SHARE;
+  constexpr bool kMerge = Cfg::kMerge;
   constexpr int kStages = Cfg::kStages;
   constexpr int kRing = Cfg::kRing;
   constexpr bool kGeneric = EK == EK_GENERIC;
@@ -285,7 +300,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   if (warp == 0) {
     // ===================================================== TMA producer
     int stage = 0; uint32_t phase = 0;
-    const uint32_t stage_tx = Cfg::kAStat ? (uint32_t)(p.kslabs * Cfg::kBTileBytes)
+    const uint32_t stage_tx = kMerge ? (uint32_t)p.merge_tx
+                              : Cfg::kAStat ? (uint32_t)(p.kslabs * Cfg::kBTileBytes)
                               : SHARE ? (uint32_t)(p.a_box_bytes + p.kslabs * Cfg::kBTileBytes)
                                       : (uint32_t)(Cfg::kABytes + Cfg::kBTileBytes);
     int a_m = -1; uint32_t a_phase = 0;   // resident A tile: row block it holds, load count parity
@@ -336,7 +352,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           } else {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-              load(sa + c * (64 * kBK * 2), &p.tmA, m_row0 + c * 64 + p.a_col_off[g][slab],
+              load(sa + c * Cfg::kMnChunkBytes, &p.tmA, m_row0 + c * 64 + p.a_col_off[g][slab],
                    k_in + p.a_row_off[g][slab]);
           }
           const int nb = SHARE ? p.kslabs : 1;
@@ -348,7 +364,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             } else {
 #pragma unroll
               for (int c = 0; c < Cfg::kBChunks; ++c)
-                load(sbt + c * (64 * kBK * 2), &p.tmB, n_loc + c * 64 + p.b_col_off[g][bs],
+                load(sbt + c * Cfg::kMnChunkBytes, &p.tmB, n_loc + c * 64 + p.b_col_off[g][bs],
                      k_in + p.b_row_off[g][bs]);
             }
           }
@@ -365,8 +381,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       constexpr uint32_t idesc = make_idesc_f16(Cfg::kUmmaM, BN, A_MN, B_MN);
       // K-major: 8-row groups 1024 B apart (SBO); MN-major: 64-wide chunks 8 KB apart (LBO),
       // 8-k groups 1024 B apart (SBO).
-      constexpr uint32_t a_lbo = A_MN ? 64 * kBK * 2 : 16, a_sbo = 1024;
-      constexpr uint32_t b_lbo = B_MN ? 64 * kBK * 2 : 16, b_sbo = 1024;
+      constexpr uint32_t a_lbo = A_MN ? Cfg::kMnChunkBytes : 16, a_sbo = 1024;
+      constexpr uint32_t b_lbo = B_MN ? Cfg::kMnChunkBytes : 16, b_sbo = 1024;
       constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4;   // descriptor units (16 B) per UMMA K=16
       constexpr uint32_t b_kstep = (B_MN ? 2048 : 32) >> 4;
       // A-stationary: A descriptors address the resident tile (k-block kb at kb * kABytes), B the ring stages
@@ -385,7 +401,12 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
         dbg_stamp(p, 1, tile_i, 0);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (kMerge) {      // a merged tile owns BOTH accumulator stages (one per group)
+          mbar_wait(&tempty_bar[0], acc_phase ^ 1);
+          mbar_wait(&tempty_bar[1], acc_phase ^ 1);
+        } else {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        }
         tc_fence_after();
         dbg_stamp(p, 1, tile_i, 1);
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
@@ -407,7 +428,20 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (kb == kb0) dbg_stamp(p, 1, tile_i, 2);
-          if (elect_one()) {
+          if (kMerge) {
+            if (elect_one()) {
+              const uint64_t so = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
+#pragma unroll
+              for (int gq = 0; gq < 2; ++gq) {
+                // group gq: both operands start a_shift / b_shift whole 128-byte k-rows into their tiles
+                const uint64_t ad = adesc0 + so + (uint64_t)((uint32_t)p.a_shift[gq] * 8u);
+                const uint64_t bd = bdesc0 + so + (uint64_t)((uint32_t)p.b_shift[gq] * 8u);
+                const uint32_t dt = tmem_base + gq * Cfg::kAccCols;
+                for (int k = 0; k < k16s; ++k) mma(dt, ad + k * a_kstep, bd + k * b_kstep, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit_pair(&empty_bar[stage]);
+            }
+          } else if (elect_one()) {
             const uint64_t so = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
             const int nb = SHARE ? p.kslabs : 1;
             for (int t = 0; t < nb; ++t) {
@@ -435,7 +469,11 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) {
+        if (kMerge) {
+          if (elect_one()) { umma_commit_pair(&tfull_bar[0]); umma_commit_pair(&tfull_bar[1]); }
+          __syncwarp();
+          acc = 1;      // the bookkeeping below then flips the phase once per merged tile
+        } else if (elect_one()) {
           if (CG == 2) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
           if (Cfg::kAStat && a_last) {
             if (CG == 2) umma_commit_pair(aempty_bar); else umma_commit(aempty_bar);
@@ -533,9 +571,12 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     const uint32_t tempty_leader[2] = {CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u,
                                        CG == 2 ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
     int tile_i = 0;
-    for (int tile = ti.first; tile < ti.last; tile += ti.step, ++tile_i) {
+    // merged groups: a tile is visited twice, group g's partial product sits in accumulator stage g
+    for (int tile = ti.first; tile < ti.last; tile += ti.step, ++tile_i)
+    for (int gg = 0; gg < (kMerge ? 2 : 1); ++gg) {
       int n_blk, m_row0, g, ks;
       ti.decode(tile, n_blk, m_row0, g, ks);
+      if (kMerge) g = gg;
       const int row = m_row0 + row_in_tile;
       const int n0 = n_blk * BN;
       if (warp == 4) dbg_stamp(p, 2, tile_i, 0);
@@ -554,8 +595,14 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
 
       if constexpr (kSplitK) {
         float* ws_row = p.ws[g] + (size_t)row * p.ws_ld;
+        // The split_k work items of one output tile finish together and accumulate into the SAME addresses: each
+        // starts its walk over the 32-column groups at a different group (rotated by its split index) so that they
+        // hit different L2 lines at any one time.
+        const int my_groups = hsel == 0 ? (BN / 32 + 1) / 2 : (BN / 32) / 2;
+        const int rot = p.no_rotate ? 0 : ks + (kMerge ? g : 0);
 #pragma unroll 1
-        for (int c = hsel * 32; c < BN; c += 64) {
+        for (int ci = 0; ci < my_groups; ++ci) {
+          const int c = (hsel + 2 * ((ci + rot) % my_groups)) * 32;
           uint32_t v[32];
           tmem_ld_32x32(t_acc + c, v);
           tmem_ld_wait();

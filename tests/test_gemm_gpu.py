@@ -362,3 +362,41 @@ def test_a_stationary_spliced_gemm(handle, lib, max_ctas, T, D, N, s0, s1, b_k_m
     assert np.array_equal(outs[0], outs[1])      # same k-block / slab order -> same fp32 accumulation order
     for t in (tXp, tW, tR):
         t.Free()
+
+
+@pytest.mark.parametrize("K", [2000, 9984])
+@pytest.mark.parametrize("shift_a,transposed,N", [(False, True, 160), (True, False, 160), (True, False, 144)])
+@pytest.mark.parametrize("merge", [True, False])
+def test_spliced_weight_gradient_merged_groups(handle, lib, K, shift_a, transposed, N, merge):
+    """the two groups of a spliced weight gradient, dW_g = sum_k A[k + a_off_g]^T B[k + b_off_g], share ONE A and ONE B
+    tile per k-block (row-shifted UMMA descriptors on MN-major operands, one TMEM accumulator stage per group):
+    shift on the B side (dWaff = dZ^T [B(t) | B(t+s)], transposed target) or on the A side (dWlin = [X(t-s) | X(t)]^T dB);
+    merge=False runs the two groups as separate tiles (no_share = 1) for comparison"""
+    s, M = 3, 1536
+    rng = np.random.default_rng(K + N + int(shift_a))
+    Afull = rand_f16(rng, (K + 2 * s, M))
+    Bfull = rand_f16(rng, (K + 2 * s, N), 0.05)
+    tA, tB = gpu.TensorFromFP16(Afull), gpu.TensorFromFP16(Bfull)
+    ws = gpu.DeviceF32(n=2 * N * M)
+    tD = gpu.ZeroTensor(8, 8)
+    d = make_desc(M, N, K, tA, tB, tD, a_major=MN_MAJOR, b_major=MN_MAJOR, split_k=6, ws_ld=M if transposed else N,
+                  ws_transposed=int(transposed), no_share=4 if merge else 1)
+    d.groups = 2
+    d.A.ptr, d.A.rows, d.A.halo = tA.Ptr + s * M * 2, K, s
+    d.B.ptr, d.B.rows, d.B.halo = tB.Ptr + s * N * 2, K, s
+    a_off, b_off = ((-s, 0), (0, 0)) if shift_a else ((0, 0), (0, s))
+    d.a_row_off[0][0], d.a_row_off[1][0] = a_off
+    d.b_row_off[0][0], d.b_row_off[1][0] = b_off
+    d.ws[0], d.ws[1] = ws.Ptr, ws.Ptr + N * M * 4
+    run_desc(handle, d)
+    got = ws.ToHost().reshape((2, N, M) if transposed else (2, M, N))
+    for g in range(2):
+        Ag = Afull[s + a_off[g]: s + a_off[g] + K].astype(np.float64)
+        Bg = Bfull[s + b_off[g]: s + b_off[g] + K].astype(np.float64)
+        want = Ag.T @ Bg
+        absprod = np.abs(Ag).T @ np.abs(Bg)
+        if transposed:
+            want, absprod = want.T, absprod.T
+        assert_close(got[g], want, 2.0 ** -19 * absprod + 1e-6, f"merged={merge} group {g}")
+    for t in (tA, tB, tD, ws):
+        t.Free()
