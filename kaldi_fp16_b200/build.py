@@ -20,7 +20,7 @@ LIB = PKG / "libkaldi_fp16.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo", "-O3", "-std=c++17",
+    "-lineinfo", "-O3", "-std=c++17", *os.environ.get("KFP16_NVCC_EXTRA", "").split(),
     "-Xcompiler", "-fPIC,-fvisibility=default",
 ]
 

@@ -18,6 +18,17 @@ namespace kfp16 {
 // ------------------------------------------------------------------ errors / counters
 static thread_local char g_err[512] = {0};
 std::atomic<unsigned long long> g_launches{0};
+void prefer_max_smem_carveout(const void* kern) {
+  static const bool on = [] { const char* e = getenv("KFP16_CARVEOUT"); return !(e && e[0] == '0'); }();
+  if (!on) return;
+  static std::mutex mu;
+  static std::unordered_map<const void*, bool> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(kern)) return;
+  done[kern] = true;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();   // a kernel that cannot take the hint keeps its default
+}
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("KFP16_PDL"); return !(e && e[0] == '0'); }();
   return on;

@@ -157,10 +157,13 @@ struct GemmCfg {
   // exposed the full load latency on every 5-k-block tile: ~3000 cycles per tile against 1280 of MMA).
   static constexpr bool kAStat = MODE == 2;
   static constexpr int kAKb = 3;
-  static constexpr int kRing = kSplitK ? 0 : (kAStat ? 4 : (kMayUseR ? (BN <= 160 ? 6 : 4) : 4));
+#ifndef KFP16_RING128
+#define KFP16_RING128 6
+#endif
+  static constexpr int kRing = kSplitK ? 0 : (kAStat ? 4 : (kMayUseR ? (BN <= 160 ? (BN == 128 && SHARE ? KFP16_RING128 : 6) : 4) : 4));
   // TMA stores left in flight when a chunk is handed over (a store's smem-read latency is ~1000 cycles:
   // with none in flight every 64-column chunk paid it in full)
-  static constexpr int kStoreWait = kRing == 6 ? 3 : (kMayUseR ? 1 : 2);   // < kRing
+  static constexpr int kStoreWait = kRing >= 5 ? kRing - 3 : (kMayUseR ? 1 : 2);   // < kRing
   static constexpr int kUmmaM = kBM * CG;                      // 256 rows over a CTA pair
   static constexpr int kBNLocal = BN / CG;                     // B rows / columns staged by this CTA
   static constexpr int kBChunks = B_MN ? (kBNLocal + 63) / 64 : 1;   // 64-wide N chunks (MN-major)
@@ -253,6 +256,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (warp == 2) dbg_stamp(p, 0, 7, 0);      // kernel entry (profiling row: role 0, tile slot 7)
   const uint32_t flags = kGeneric ? p.flags : Cfg::kFlags;
   const bool use_r = Cfg::kMayUseR && (flags & (EPI_RESID | EPI_BETA)) != 0;
 
@@ -291,7 +295,9 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 2) dbg_stamp(p, 0, 7, 1);      // prologue done (barriers, TMEM, cluster sync)
   griddep_wait();
+  if (warp == 2) dbg_stamp(p, 0, 7, 2);      // predecessor grid complete
 
   // The three single-issuer roles below run with the whole warp converged and elect ONE lane only around
   // the TMA / tcgen05 instructions: every address and descriptor is then warp-uniform, so ptxas keeps them
@@ -525,8 +531,12 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           if (k >= Cfg::kStoreWait && ++fbuf == kRing) fbuf = 0;
         }
       }
-      if (elect_one()) tma_store_wait_all<0>();
+      dbg_stamp(p, 0, 7, 3);                 // last store issued
+      // the staging buffers only have to be READ before the CTA exits; the writes complete asynchronously and are
+      // ordered before the next kernel by the grid boundary (waiting for full completion cost ~1 us per launch)
+      if (elect_one()) tma_store_wait_read<0>();
       __syncwarp();
+      dbg_stamp(p, 0, 7, 4);                 // stores drained
     }
   } else if (warp >= 4) {
     // ========================================================= epilogue
@@ -748,9 +758,11 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer may still arrive on the leader's barriers
   if (warp == 2) {
+    dbg_stamp(p, 0, 7, 5);                   // all roles done
     tc_fence_after();
     if (CG == 2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
     else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    dbg_stamp(p, 0, 7, 6);                   // TMEM released
   }
 }
 

@@ -46,8 +46,12 @@ bool check_cuda(cudaError_t e, const char* what);
 // global access are launched with the stream-serialization attribute, so consecutive launches overlap their
 // launch latency / prologue with the predecessor's tail (also inside captured graphs: programmatic edges).
 bool pdl_enabled();
+// once per kernel: ask for the maximum shared-memory carve-out, the configuration the GEMM kernels need, so that the
+// SMs are not re-partitioned (L1 <-> shared) every time a small helper kernel runs between two GEMMs
+void prefer_max_smem_carveout(const void* kern);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  prefer_max_smem_carveout(reinterpret_cast<const void*>(kern));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;

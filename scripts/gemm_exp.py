@@ -120,6 +120,20 @@ if int(kv.get("dbg", 0)):
 fl = gpu.DeviceF32(n=64 * 1024 * 1024) if flush else None
 e0, e1 = cudart.Event(), cudart.Event()
 lib.kfp16_ctx_set_profile(h.ptr, 0)
+if int(kv.get("prof", 0)):     # device-side kernel durations from CUPTI (no host launch overhead in the number)
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.init()
+    for _ in range(3):
+        assert lib.kfp16_gemm_ex(h.ptr, C.byref(d)) == 0, _lib.last_error()
+    cudart.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(iters):
+            assert lib.kfp16_gemm_ex(h.ptr, C.byref(d)) == 0, _lib.last_error()
+        cudart.synchronize()
+    durs = sorted(e.time_range.end - e.time_range.start for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA)
+    print(f"{name:4s} {' '.join(sys.argv[2:]):40s} CUPTI kernel duration median {durs[len(durs) // 2]:.2f} us  min {durs[0]:.2f} us  (n={len(durs)})")
+    raise SystemExit(0)
 ts = []
 for it in range(iters + 3):
     if fl is not None:
