@@ -322,6 +322,73 @@ __global__ void softmax_kernel(__half* __restrict__ data, int rows, int cols) {
   }
 }
 
+// Same arithmetic with the row held in registers: one 16-byte read and one 16-byte write per 8 elements (rows of up
+// to 8192 columns; the output layer has 6016).  256 threads x up to 4 chunks of 8 halves.
+template <bool LOG>
+__global__ void __launch_bounds__(256)
+softmax_row_regs_kernel(__half* __restrict__ data, int rows, int cols) {
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunks = cols >> 3;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    uint4* row = reinterpret_cast<uint4*>(data + (size_t)r * cols);
+    uint4 v[4];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = threadIdx.x + k * 256;
+      if (j < chunks) v[k] = row[j];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (threadIdx.x + k * 256 < chunks) {
+        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = unpack_h2(w[e]); m = fmaxf(m, fmaxf(f.x, f.y)); }
+      }
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffff, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (threadIdx.x + k * 256 < chunks) {
+        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = unpack_h2(w[e]); s += expf(f.x - m) + expf(f.y - m); }
+      }
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    __syncthreads();
+    const float lse = m + logf(s), inv = 1.0f / s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = threadIdx.x + k * 256;
+      if (j < chunks) {
+        uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_h2(w[e]);
+          if (LOG) w[e] = pack_h2(f.x - lse, f.y - lse);
+          else     // the reference rounds exp(x-max) to fp16 before normalising (ops.cu:96-110)
+            w[e] = pack_h2(__half2float(__float2half(expf(f.x - m))) * inv, __half2float(__float2half(expf(f.y - m))) * inv);
+        }
+        row[j] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+}
+
 // ---- transpose dst[c*rows + r] = src[r*cols + c]  (backward_wrappers.cu:75-85), 32x32 smem tiles
 __global__ void transpose_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
   __shared__ __half tile[32][34];
@@ -851,7 +918,11 @@ int kfp16::softmax_on_stream(cudaStream_t stream, void* data, int rows, int cols
   if (rows <= 0 || cols <= 0) return 0;
   if (!data) { set_error("softmax: null pointer"); return -1; }
   const int grid = rows < num_sms_cached() * 16 ? rows : num_sms_cached() * 16;
-  if (log) softmax_kernel<true><<<grid, 128, 0, stream>>>((__half*)data, rows, cols);
+  if ((cols % 8) == 0 && cols <= 8192 && al16(data)) {
+    const int g2 = rows < num_sms_cached() * 8 ? rows : num_sms_cached() * 8;
+    if (log) softmax_row_regs_kernel<true><<<g2, 256, 0, stream>>>((__half*)data, rows, cols);
+    else softmax_row_regs_kernel<false><<<g2, 256, 0, stream>>>((__half*)data, rows, cols);
+  } else if (log) softmax_kernel<true><<<grid, 128, 0, stream>>>((__half*)data, rows, cols);
   else softmax_kernel<false><<<grid, 128, 0, stream>>>((__half*)data, rows, cols);
   count_launch();
   return check_launch(log ? "log_softmax kernel" : "softmax kernel") ? 0 : -1;

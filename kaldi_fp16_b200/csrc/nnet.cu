@@ -94,6 +94,7 @@ struct Layer {
   int pf_rows = 0, pf_cols = 0, pf_slot = 0, pf_ready = -1;
   // conv-relu-batchnorm
   int hin = 0, hout = 0, hsub = 1, fin = 0, fout = 0, convK = 0, convKp = 0;
+  __half* convP = nullptr;   // this layer's patch matrix: kept from the forward pass for the weight gradient (train mode)
   std::vector<int> tap_dt, tap_dh;
   int grads_seen = 0;
 };
@@ -644,6 +645,9 @@ bool build_plan(kfp16_net* n) {
         const size_t mrows = (size_t)n->Tp * l.hout;
         l.mask_ld = (l.fout + 31) / 32;
         if (!dev_alloc(n, (void**)&l.mask, mrows * l.mask_ld * 4)) return false;
+        // training keeps every layer's patch matrix resident between forward and backward (1.8 GB for the cnn_tdnn_1a
+        // front end: HBM is 180 GB) instead of gathering it a second time; inference shares one scratch buffer
+        if (train) { if (!dev_alloc(n, (void**)&l.convP, mrows * l.convKp * 2, false)) return false; }
         n->conv_P_elems = std::max(n->conv_P_elems, mrows * l.convKp);
         n->conv_dz_elems = std::max(n->conv_dz_elems, mrows * l.fout);
         n->flops_fwd += 2.0 * M * l.hout * l.convK * l.fout;
@@ -653,7 +657,7 @@ bool build_plan(kfp16_net* n) {
     }
   }
   if (n->conv_P_elems) {
-    if (!dev_alloc(n, (void**)&n->conv_P, n->conv_P_elems * 2, false)) return false;
+    if (!train && !dev_alloc(n, (void**)&n->conv_P, n->conv_P_elems * 2, false)) return false;
     if (train) {
       if (!dev_alloc(n, (void**)&n->conv_dP, n->conv_P_elems * 2, false)) return false;
       if (!dev_alloc(n, (void**)&n->conv_dz, n->conv_dz_elems * 2, false)) return false;
@@ -887,10 +891,11 @@ int forward_layer(kfp16_net* n, Layer& l) {
     }
     case L_CONV: {       // forward.go:418-524 with the im2col on the device; Z = BN(ReLU(P*W + b)) per filter
       const int mrows = rows * l.hout;
-      if (kfp16_im2col(ctx, X.p, n->conv_P, l.convKp, n->opts.n_seq, n->opts.seq_len, n->halo, l.hin, l.hout, l.hsub, l.fin,
+      __half* P = l.convP ? l.convP : n->conv_P;
+      if (kfp16_im2col(ctx, X.p, P, l.convKp, n->opts.n_seq, n->opts.seq_len, n->halo, l.hin, l.hout, l.hsub, l.fin,
                        (int)l.tap_dt.size(), l.tap_dt.data(), l.tap_dh.data())) return -1;
       kfp16_gemm_desc d = mk_desc(mrows, l.fout, l.convKp);
-      set_A(d, n->conv_P, mrows, l.convKp);
+      set_A(d, P, mrows, l.convKp);
       set_B(d, W16(n, l.pW), l.convK, l.fout);          // rows [convK, convKp) read as zeros (TMA bounds)
       d.D[0] = l.out.p; d.ldd = l.fout;
       d.flags = KFP16_EPI_BIAS | KFP16_EPI_RELU | KFP16_EPI_BN | KFP16_EPI_MASK | rr;
@@ -1026,12 +1031,11 @@ int backward_layer(kfp16_net* n, Layer& l) {
     case L_CONV: {     // transpose of the forward (the reference treats the conv as a dense affine: quirk Q2)
       const int mrows = rows * l.hout;
       if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.fout, l.bn.scale, l.mask, l.mask_ld, n->conv_dz, l.fout, mrows, l.fout, G32(n, l.pB))) return -1;
-      if (kfp16_im2col(ctx, X.p, n->conv_P, l.convKp, n->opts.n_seq, n->opts.seq_len, n->halo, l.hin, l.hout, l.hsub, l.fin,
-                       (int)l.tap_dt.size(), l.tap_dt.data(), l.tap_dh.data())) return -1;
+      // the patch matrix of the forward pass is still resident (l.convP)
       {  // dW[K x fout] = P^T dZ
         kfp16_gemm_desc d = mk_desc(l.convK, l.fout, mrows);
         d.a_major = KFP16_MN_MAJOR;
-        set_A(d, n->conv_P, mrows, l.convKp);
+        set_A(d, l.convP, mrows, l.convKp);
         set_B(d, n->conv_dz, mrows, l.fout);
         d.split_k = pick_split_k(n, l.convK, l.fout, 1, mrows);
         d.ws[0] = G32(n, l.pW); d.ws_ld = l.fout;
