@@ -345,7 +345,12 @@ def main():
         net.Launch(1)
         allreduce()
         net.Launch(2)
-        last_loss = net.ReadLoss()
+        # every step's loss is read back to the host; the read of step i is queued behind step i and collected after
+        # step i+1 has been queued, so the stream never drains between minibatches
+        net.ReadLossAsync(i & 1)
+        if i > 0:
+            last_loss = net.WaitLoss((i - 1) & 1)
+    last_loss = net.WaitLoss((e2e_steps - 1) & 1)
     e1.record(stream_ptr)
     e1.synchronize()
     sync_all()

@@ -105,6 +105,10 @@ int kfp16_net_sgd_step(kfp16_net *net, float grad_scale, int round_grad);
 int kfp16_net_set_lr(kfp16_net *net, float lr);
 /* accumulated loss since the last call (device->host sync) */
 int kfp16_net_read_loss(kfp16_net *net, float *loss);
+/* pipelined form: queue the download (+ reset) of the loss accumulated so far into pinned slot 0/1 behind the work
+ * already in the stream; kfp16_net_wait_loss blocks on that copy only (the host can queue the next minibatch first) */
+int kfp16_net_read_loss_async(kfp16_net *net, int slot);
+int kfp16_net_wait_loss(kfp16_net *net, int slot, float *loss);
 
 /* ---- CUDA graph of the step: phases bitmask 1 = zero_grads+forward+loss+backward, 2 = SGD.
  * Capture once (buffers are fixed), then launch per minibatch after kfp16_net_set_input*. */

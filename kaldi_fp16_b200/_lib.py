@@ -143,6 +143,8 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_sgd_step": (c_int, [c_void_p, c_float, c_int]),
     "kfp16_net_set_lr": (c_int, [c_void_p, c_float]),
     "kfp16_net_read_loss": (c_int, [c_void_p, C.POINTER(c_float)]),
+    "kfp16_net_read_loss_async": (c_int, [c_void_p, c_int]),
+    "kfp16_net_wait_loss": (c_int, [c_void_p, c_int, C.POINTER(c_float)]),
     "kfp16_net_capture": (c_int, [c_void_p, c_int]),
     "kfp16_net_launch": (c_int, [c_void_p, c_int]),
     "kfp16_net_launches_per_step": (c_int, [c_void_p, c_int]),

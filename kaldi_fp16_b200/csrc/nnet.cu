@@ -111,6 +111,8 @@ struct kfp16_net {
   __half* w16 = nullptr;
   float *w32 = nullptr, *vel = nullptr, *g32 = nullptr;
   float* loss_dev = nullptr;
+  float* loss_pinned = nullptr;            // 2 pinned slots for kfp16_net_read_loss_async / kfp16_net_wait_loss
+  cudaEvent_t loss_ev[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
   __half *conv_P = nullptr, *conv_dP = nullptr, *conv_dz = nullptr;   // shared conv scratch (patches, patch grads, dZ)
   size_t conv_P_elems = 0, conv_dz_elems = 0;
@@ -1132,6 +1134,8 @@ void kfp16_net_destroy(kfp16_net* n) {
       if (l.pf_packed[b]) cudaEventDestroy(l.pf_packed[b]);
     }
   if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
+  if (n->loss_pinned) cudaFreeHost(n->loss_pinned);
+  for (cudaEvent_t e : n->loss_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : n->ev_pool) cudaEventDestroy(e);
   if (n->ev_join) cudaEventDestroy(n->ev_join);
   if (n->side) cudaStreamDestroy(n->side);
@@ -1427,6 +1431,28 @@ int kfp16_net_read_loss(kfp16_net* n, float* loss) {
   if (!check_cuda(cudaMemcpyAsync(loss, n->loss_dev, 4, cudaMemcpyDeviceToHost, n->ctx->stream), "loss download")) return -1;
   if (!check_cuda(cudaMemsetAsync(n->loss_dev, 0, 4, n->ctx->stream), "loss reset")) return -1;
   return check_cuda(cudaStreamSynchronize(n->ctx->stream), "loss sync") ? 0 : -1;
+}
+
+// Pipelined form of kfp16_net_read_loss: the copy of the loss accumulated so far (and its reset) is queued behind the
+// work already in the stream and lands in pinned slot `slot` (0/1); kfp16_net_wait_loss blocks on that copy only, so a
+// training loop can queue minibatch i+1 before it looks at the loss of minibatch i and the GPU never drains.
+int kfp16_net_read_loss_async(kfp16_net* n, int slot) {
+  if (!n || slot < 0 || slot > 1) { set_error("kfp16_net_read_loss_async: slot must be 0 or 1"); return -1; }
+  if (!n->loss_pinned) {
+    if (!check_cuda(cudaMallocHost((void**)&n->loss_pinned, 2 * sizeof(float)), "cudaMallocHost (loss slots)")) return -1;
+    n->loss_pinned[0] = n->loss_pinned[1] = 0.f;
+    for (int i = 0; i < 2; ++i)
+      if (!check_cuda(cudaEventCreateWithFlags(&n->loss_ev[i], cudaEventDisableTiming), "loss event")) return -1;
+  }
+  if (!check_cuda(cudaMemcpyAsync(n->loss_pinned + slot, n->loss_dev, 4, cudaMemcpyDeviceToHost, n->ctx->stream), "loss download")) return -1;
+  if (!check_cuda(cudaMemsetAsync(n->loss_dev, 0, 4, n->ctx->stream), "loss reset")) return -1;
+  return check_cuda(cudaEventRecord(n->loss_ev[slot], n->ctx->stream), "loss event record") ? 0 : -1;
+}
+int kfp16_net_wait_loss(kfp16_net* n, int slot, float* loss) {
+  if (!n || !loss || slot < 0 || slot > 1 || !n->loss_pinned) { set_error("kfp16_net_wait_loss: no read queued for this slot"); return -1; }
+  if (!check_cuda(cudaEventSynchronize(n->loss_ev[slot]), "loss event sync")) return -1;
+  *loss = n->loss_pinned[slot];
+  return 0;
 }
 
 int kfp16_net_capture(kfp16_net* n, int phases) {

@@ -222,6 +222,17 @@ class Network:
             raise _err("ReadLoss")
         return v.value
 
+    def ReadLossAsync(self, slot: int) -> None:
+        """queue the loss download behind the work already in the stream (pinned slot 0/1)"""
+        if self.lib.kfp16_net_read_loss_async(self.ptr, slot) != 0:
+            raise _err("ReadLossAsync")
+
+    def WaitLoss(self, slot: int) -> float:
+        v = C.c_float(0)
+        if self.lib.kfp16_net_wait_loss(self.ptr, slot, C.byref(v)) != 0:
+            raise _err("WaitLoss")
+        return v.value
+
     def SGDStep(self, grad_scale: float = 1.0, round_grad: bool = True) -> None:
         if self.lib.kfp16_net_sgd_step(self.ptr, grad_scale, int(round_grad)) != 0:
             raise _err("SGDStep")

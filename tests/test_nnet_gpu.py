@@ -352,3 +352,28 @@ def test_prefetched_input_equals_synchronous_input(handle, lib):
         assert np.array_equal(net.Output(""), outs[i])
     lib.bridge_host_free(pinned)
     net.Free()
+
+
+def test_pipelined_loss_read_equals_synchronous_read(handle, lib):
+    """kfp16_net_read_loss_async / kfp16_net_wait_loss (download queued behind the step, collected one step later)
+    return the same per-step objective as the synchronous kfp16_net_read_loss"""
+    n_seq, L = 3, 25
+    on, net, rng = make_pair(handle, SPLICED, n_seq, L, seed=11)
+    xs = [O.to_f16_rne(rng.standard_normal((n_seq * L, 64)).astype(np.float32)) for _ in range(4)]
+    sync_losses = []
+    net.ReadLoss()
+    for x in xs:
+        net.Forward(x)
+        net.Backward(None)
+        sync_losses.append(net.ReadLoss())
+    got = []
+    for i, x in enumerate(xs):
+        net.Forward(x)
+        net.Backward(None)
+        net.ReadLossAsync(i & 1)
+        if i > 0:
+            got.append(net.WaitLoss((i - 1) & 1))
+    got.append(net.WaitLoss((len(xs) - 1) & 1))
+    assert got == sync_losses and all(v > 0 for v in got)
+    assert lib.kfp16_net_read_loss_async(net.ptr, 2) == -1
+    net.Free()
