@@ -27,32 +27,42 @@ struct ConvGeom {
   int hin, hout, sub, fin, Kp;
 };
 
-// one thread per (row m = r*hout + ho, tap, 8-wide filter group) -- or scalar when fin % 8 != 0
+// one thread per (row m = r*hout + ho, VEC-wide filter group), looping over the taps: the index arithmetic (32-bit) is
+// paid once per row and the taps' loads are independent (9 x 16 bytes in flight per thread).  Consecutive threads
+// cover the fin filters of one row, i.e. one contiguous fin*2-byte run per tap on both sides.
 template <int VEC>
 __global__ void im2col_kernel(const __half* __restrict__ x, __half* __restrict__ P, ConvGeom g, Taps taps) {
-  const int fv = (g.fin + VEC - 1) / VEC;
-  const size_t rows = (size_t)g.n_seq * g.blk * g.hout;
-  const size_t total = rows * taps.n * fv;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const int ldx = g.hin * g.fin;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int f = (int)(i % fv) * VEC;
-    size_t rest = i / fv;
-    const int tap = (int)(rest % taps.n);
-    const size_t m = rest / taps.n;
-    const int ho = (int)(m % g.hout);
-    const size_t r = m / g.hout;               // padded row
-    const int local = (int)(r % g.blk) - g.halo;
-    const int ts = local + taps.dt[tap];
-    const int hs = ho * g.sub + taps.dh[tap];
-    const bool ok = local >= 0 && local < g.L && ts >= 0 && ts < g.L && hs >= 0 && hs < g.hin;
-    __half* dst = P + m * g.Kp + (size_t)tap * g.fin + f;
+  const uint32_t fv = (uint32_t)(g.fin + VEC - 1) / VEC;
+  const uint32_t rows = (uint32_t)g.n_seq * g.blk * g.hout;
+  const uint32_t total = rows * fv;                       // < 2^32: checked by the launcher
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const size_t ldx = (size_t)g.hin * g.fin;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const uint32_t f = (i % fv) * VEC;
+    const uint32_t m = i / fv;
+    const int ho = (int)(m % (uint32_t)g.hout);
+    const uint32_t r = m / (uint32_t)g.hout;              // padded row
+    const int local = (int)(r % (uint32_t)g.blk) - g.halo;
+    const bool row_ok = local >= 0 && local < g.L;
+    __half* dst = P + (size_t)m * g.Kp + f;
+    const __half* src = x + (size_t)r * ldx + f;
     if (VEC == 8) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (ok) v = *reinterpret_cast<const uint4*>(x + (r + taps.dt[tap]) * ldx + (size_t)hs * g.fin + f);
-      *reinterpret_cast<uint4*>(dst) = v;
+#pragma unroll 3
+      for (int tap = 0; tap < taps.n; ++tap) {
+        const int ts = local + taps.dt[tap];
+        const int hs = ho * g.sub + taps.dh[tap];
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row_ok && ts >= 0 && ts < g.L && hs >= 0 && hs < g.hin)
+          v = *reinterpret_cast<const uint4*>(src + (ptrdiff_t)taps.dt[tap] * (ptrdiff_t)ldx + (size_t)hs * g.fin);
+        *reinterpret_cast<uint4*>(dst + (size_t)tap * g.fin) = v;
+      }
     } else {
-      *dst = ok ? x[(r + taps.dt[tap]) * ldx + (size_t)hs * g.fin + f] : __float2half(0.f);
+      for (int tap = 0; tap < taps.n; ++tap) {
+        const int ts = local + taps.dt[tap];
+        const int hs = ho * g.sub + taps.dh[tap];
+        const bool ok = row_ok && ts >= 0 && ts < g.L && hs >= 0 && hs < g.hin && (int)f < g.fin;
+        if ((int)f < g.fin) dst[(size_t)tap * g.fin] = ok ? src[(ptrdiff_t)taps.dt[tap] * (ptrdiff_t)ldx + (size_t)hs * g.fin] : __float2half(0.f);
+      }
     }
   }
 }
@@ -69,33 +79,53 @@ __global__ void zero_pad_cols_kernel(__half* __restrict__ P, size_t rows, int K,
 // adjoint: dx[r, h, f] = sum over taps with ho*sub + dh == h of dP[((r-dt)*hout + ho), tap*fin + f]
 template <int VEC>
 __global__ void col2im_kernel(const __half* __restrict__ dP, __half* __restrict__ dx, ConvGeom g, Taps taps) {
-  const int fv = (g.fin + VEC - 1) / VEC;
-  const size_t total = (size_t)g.n_seq * g.blk * g.hin * fv;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+  const uint32_t fv = (uint32_t)(g.fin + VEC - 1) / VEC;
+  const uint32_t total = (uint32_t)g.n_seq * g.blk * g.hin * fv;    // < 2^32: checked by the launcher
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int f = (int)(i % fv) * VEC;
-    size_t rest = i / fv;
-    const int hh = (int)(rest % g.hin);
-    const size_t r = rest / g.hin;
-    const int local = (int)(r % g.blk) - g.halo;
+    const uint32_t rest = i / fv;
+    const int hh = (int)(rest % (uint32_t)g.hin);
+    const size_t r = rest / (uint32_t)g.hin;
+    const int local = (int)((uint32_t)r % (uint32_t)g.blk) - g.halo;
     float acc[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
     if (local >= 0 && local < g.L) {
-      for (int tap = 0; tap < taps.n; ++tap) {
-        const int to = local - taps.dt[tap];     // output frame that read this input frame through `tap`
-        const int hs = hh - taps.dh[tap];
-        if (to < 0 || to >= g.L || hs < 0 || (hs % g.sub) != 0) continue;
-        const int ho = hs / g.sub;
-        if (ho >= g.hout) continue;
-        const __half* src = dP + ((r - taps.dt[tap]) * g.hout + ho) * g.Kp + (size_t)tap * g.fin + f;
-        if (VEC == 8) {
-          const uint4 v = *reinterpret_cast<const uint4*>(src);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+      // taps in groups of 3: the (up to) three 16-byte loads of a group are issued before any of them is used
+      for (int tap0 = 0; tap0 < taps.n; tap0 += 3) {
+        uint4 v[3];
+        bool ok[3];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h2[e]); acc[2 * e] += t.x; acc[2 * e + 1] += t.y; }
-        } else {
-          acc[0] += __half2float(*src);
+        for (int q = 0; q < 3; ++q) {
+          const int tap = tap0 + q;
+          ok[q] = false;
+          v[q] = make_uint4(0, 0, 0, 0);
+          if (tap < taps.n) {
+            const int to = local - taps.dt[tap];     // output frame that read this input frame through `tap`
+            const int hs = hh - taps.dh[tap];
+            int ho = hs;
+            bool hit = to >= 0 && to < g.L && hs >= 0;
+            if (g.sub != 1) { hit = hit && (hs % g.sub) == 0; ho = hs / g.sub; }
+            hit = hit && ho < g.hout;
+            if (hit) {
+              const __half* src = dP + ((r - taps.dt[tap]) * g.hout + ho) * g.Kp + (size_t)tap * g.fin + f;
+              if (VEC == 8) v[q] = *reinterpret_cast<const uint4*>(src);
+              else v[q].x = *reinterpret_cast<const unsigned short*>(src);
+              ok[q] = true;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (!ok[q]) continue;
+          if (VEC == 8) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h2[e]); acc[2 * e] += t.x; acc[2 * e + 1] += t.y; }
+          } else {
+            acc[0] += __half2float(__ushort_as_half((unsigned short)v[q].x));
+          }
         }
       }
     }
@@ -153,8 +183,9 @@ int kfp16_im2col(kfp16_ctx* ctx, const void* x, void* P, int Kp, int n_seq, int 
     count_launch();
   }
   const bool vec = (fin % 8) == 0 && (Kp % 8) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)P & 15) == 0;
-  if (vec) im2col_kernel<8><<<grid_for_elems(rows * ntaps * (fin / 8)), 256, 0, s>>>((const __half*)x, (__half*)P, g, t);
-  else im2col_kernel<1><<<grid_for_elems(rows * ntaps * fin), 256, 0, s>>>((const __half*)x, (__half*)P, g, t);
+  if (rows * (size_t)fin >= 0xFFFFFFFFull) { set_error("kfp16_im2col: more than 2^32 patch rows x filters"); return -1; }
+  if (vec) im2col_kernel<8><<<grid_for_elems(rows * (fin / 8)), 256, 0, s>>>((const __half*)x, (__half*)P, g, t);
+  else im2col_kernel<1><<<grid_for_elems(rows * fin), 256, 0, s>>>((const __half*)x, (__half*)P, g, t);
   count_launch();
   return check_launch("kfp16_im2col") ? 0 : -1;
 }
@@ -166,6 +197,7 @@ int kfp16_col2im(kfp16_ctx* ctx, const void* dP, int Kp, void* dx, int n_seq, in
   if (!fill_geom(g, t, n_seq, seq_len, halo, hin, hout, sub, fin, Kp, ntaps, dt, dh, "kfp16_col2im")) return -1;
   cudaStream_t s = ctx ? ctx->stream : default_stream();
   const size_t elems = (size_t)n_seq * g.blk * hin;
+  if (elems * (size_t)fin >= 0xFFFFFFFFull) { set_error("kfp16_col2im: more than 2^32 input elements"); return -1; }
   const bool vec = (fin % 8) == 0 && (Kp % 8) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)dP & 15) == 0;
   if (vec) col2im_kernel<8><<<grid_for_elems(elems * (fin / 8)), 256, 0, s>>>((const __half*)dP, (__half*)dx, g, t);
   else col2im_kernel<1><<<grid_for_elems(elems * fin), 256, 0, s>>>((const __half*)dP, (__half*)dx, g, t);
