@@ -160,7 +160,10 @@ struct GemmCfg {
 #ifndef KFP16_RING128
 #define KFP16_RING128 6
 #endif
-  static constexpr int kRing = kSplitK ? 0 : (kAStat ? 4 : (kMayUseR ? (BN <= 160 ? (BN == 128 && SHARE ? KFP16_RING128 : 6) : 4) : 4));
+#ifndef KFP16_ASTAT_RING
+#define KFP16_ASTAT_RING 4
+#endif
+  static constexpr int kRing = kSplitK ? 0 : (kAStat ? KFP16_ASTAT_RING : (kMayUseR ? (BN <= 160 ? (BN == 128 && SHARE ? KFP16_RING128 : 6) : 4) : 4));
   // TMA stores left in flight when a chunk is handed over (a store's smem-read latency is ~1000 cycles:
   // with none in flight every 64-column chunk paid it in full)
   static constexpr int kStoreWait = kRing >= 5 ? kRing - 3 : (kMayUseR ? 1 : 2);   // < kRing
