@@ -210,9 +210,19 @@ def main():
     from kaldi_fp16_b200 import _lib, cudart, gpu, nnet
     lib = _lib.load()          # raises if the CUDA library is missing: there is no fallback
     dist = torch = None
+    # Bucketed all-reduce beside the backward pass (kfp16_net_capture_segments): measured at N = 8 it gains 0.7-1.5 %
+    # (2.287 / 2.266 ms with 8 / 16 SMs left to NCCL against 2.302 ms), because the compute kernels lose those SMs for the
+    # whole step -- opt-in until the GEMMs have a dynamic tile scheduler.
+    overlap = world > 1 and os.environ.get("KFP16_DP_OVERLAP", "0") != "0"
+    nccl_sms = int(os.environ.get("KFP16_NCCL_SMS", "8"))
     if world > 1:
         # NCCL's own banner / debug lines go to stderr so that stdout carries the one JSON line only
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if overlap:
+            # the bucketed all-reduce runs beside the backward pass: NCCL gets nccl_sms SMs (one CTA per channel), the
+            # compute kernels size their grids for the other 148 - nccl_sms
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nccl_sms))
+            os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -264,22 +274,40 @@ def main():
             assert lib.kfp16_net_set_input(net.ptr, b"ivector", h_ivec_ptr, N_SEQ, ivd) == 0, _lib.last_error()
 
     set_inputs_device()
-    net.Capture(1)
+    n_seg, seg_ranges = 0, []
+    if overlap:
+        assert lib.kfp16_ctx_set_max_ctas(handle.ptr, 148 - nccl_sms) == 0
+        n_seg = net.CaptureSegments(int(os.environ.get("KFP16_DP_SEGMENTS", "6")))
+        seg_ranges = [net.SegmentGrads(k) for k in range(n_seg)]
+    else:
+        net.Capture(1)
     net.Capture(2)
     reducer = None
     if world > 1:
         from kaldi_fp16_b200 import dp
         reducer = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(), device=f"cuda:{local}"))
 
-    def allreduce():
-        if reducer is not None:
-            with torch.cuda.stream(tstream):
-                reducer.all_reduce()         # sum: N-GPU step == 1-GPU step on the concatenated batch
+    def step_compute_and_reduce():
+        """graph 1 (or its segments) + the sum all-reduce of the gradient bucket: N-GPU step == 1-GPU step on the
+        concatenated batch"""
+        if not overlap:
+            net.Launch(1)
+            if reducer is not None:
+                with torch.cuda.stream(tstream):
+                    reducer.all_reduce()
+            return
+        works = []
+        with torch.cuda.stream(tstream):
+            for k in range(n_seg):
+                net.LaunchSegment(k)                       # backward of one layer group ...
+                works.append(reducer.all_reduce_range(*seg_ranges[k], async_op=True))   # ... its gradients reduce beside the next
+            for w in works:
+                if w is not None:
+                    w.wait()                               # device-side: the SGD graph waits for the reduced bucket
 
     def step_device():
         set_inputs_device()
-        net.Launch(1)
-        allreduce()
+        step_compute_and_reduce()
         net.Launch(2)
 
     def sync_all():
@@ -342,8 +370,7 @@ def main():
         commit_host()
         if i + 1 < e2e_steps:
             prefetch_host()
-        net.Launch(1)
-        allreduce()
+        step_compute_and_reduce()
         net.Launch(2)
         # every step's loss is read back to the host; the read of step i is queued behind step i and collected after
         # step i+1 has been queued, so the stream never drains between minibatches
@@ -372,7 +399,9 @@ def main():
         net.ZeroGrads()
         assert lib.kfp16_net_forward(net.ptr) == 0
         net.Backward(None)
-        allreduce()
+        if reducer is not None:
+            with torch.cuda.stream(tstream):
+                reducer.all_reduce()
         net.SGDStep(grad_scale)
     ev1.record(stream_ptr)
     ev1.synchronize()
@@ -395,7 +424,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": wl["desc"], "frames_per_gpu_step": T, "global_frames_per_step": frames_per_step,
-                       "parallelism": f"dp{world}", "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush",
+                       "parallelism": f"dp{world}" + (f", gradient all-reduce in {n_seg} buckets overlapped with the backward pass ({nccl_sms} SMs for NCCL)" if overlap else ""), "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush",
                        "loss": "0.5*||out||^2, dY=Y", "optimizer": f"momentum SGD on FP32 masters, lr {LR}, m 0.9, grads scaled by 1/(frames*out_dim)",
                        "launch": "CUDA graphs (step, SGD) with programmatic dependent launch between kernels" + ("" if os.environ.get("KFP16_PDL", "1") != "0" else " OFF")},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -114,6 +114,13 @@ int kfp16_net_wait_loss(kfp16_net *net, int slot, float *loss);
  * Capture once (buffers are fixed), then launch per minibatch after kfp16_net_set_input*. */
 int kfp16_net_capture(kfp16_net *net, int phases);
 int kfp16_net_launch(kfp16_net *net, int phases);
+/* The step graph (phases = 1) cut into up to nseg graphs along the backward pass: segment 0 = zero grads + forward +
+ * objective + backward of the top layers, segment k = backward of the next layer group.  After segment k the gradient
+ * bucket elements [first_elem, first_elem + count) of kfp16_net_segment_grads(k) are final, so a data-parallel loop
+ * all-reduces them while segment k+1 computes.  Returns the number of segments captured, -1 on error. */
+int kfp16_net_capture_segments(kfp16_net *net, int nseg);
+int kfp16_net_launch_segment(kfp16_net *net, int seg);
+int kfp16_net_segment_grads(const kfp16_net *net, int seg, size_t *first_elem, size_t *count);
 /* kernels launched by one forward+loss+backward(+sgd) pass of this network */
 int kfp16_net_launches_per_step(const kfp16_net *net, int phases);
 

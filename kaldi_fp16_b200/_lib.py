@@ -143,6 +143,9 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_sgd_step": (c_int, [c_void_p, c_float, c_int]),
     "kfp16_net_set_lr": (c_int, [c_void_p, c_float]),
     "kfp16_net_read_loss": (c_int, [c_void_p, C.POINTER(c_float)]),
+    "kfp16_net_capture_segments": (c_int, [c_void_p, c_int]),
+    "kfp16_net_launch_segment": (c_int, [c_void_p, c_int]),
+    "kfp16_net_segment_grads": (c_int, [c_void_p, c_int, C.POINTER(c_size_t), C.POINTER(c_size_t)]),
     "kfp16_net_read_loss_async": (c_int, [c_void_p, c_int]),
     "kfp16_net_wait_loss": (c_int, [c_void_p, c_int, C.POINTER(c_float)]),
     "kfp16_net_capture": (c_int, [c_void_p, c_int]),

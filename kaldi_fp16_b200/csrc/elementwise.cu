@@ -1191,7 +1191,10 @@ static int bn_relu_bwd_launch(kfp16_ctx* ctx, void* dY, int ldy, const float* sc
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, bn_relu_bwd_colsum_kernel<true>, 256, 0) != cudaSuccess || b1 < 1) b1 = 1;
     blocks_per_sm = b0 < b1 ? b0 : b1;
   }
-  int gy = (num_sms_cached() * blocks_per_sm) / gx;
+  // SMs this context may use (kfp16_ctx_set_max_ctas leaves the rest to a concurrent NCCL kernel)
+  int sms = num_sms_cached();
+  if (ctx && ctx->max_ctas > 0 && ctx->max_ctas < sms) sms = ctx->max_ctas;
+  int gy = (sms * blocks_per_sm) / gx;
   const int max_gy = (rows + 8 * kBnBwdRows - 1) / (8 * kBnBwdRows);
   if (gy > max_gy) gy = max_gy;
   if (gy < 1) gy = 1;

@@ -128,6 +128,10 @@ struct kfp16_net {
   size_t stage_bytes = 0;
   double flops_fwd = 0;
   cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  // the step graph cut into segments along the backward pass (gradient all-reduce overlapped bucket by bucket)
+  std::vector<cudaGraphExec_t> seg_graph;
+  std::vector<int> seg_launches, seg_lo;            // per segment: kernels, first layer index it back-propagates
+  std::vector<size_t> seg_off, seg_cnt;              // gradient-bucket range completed by the segment (elements)
   int graph_launches[4] = {0, 0, 0, 0};
   int out_layer = -1;
 };
@@ -692,7 +696,9 @@ int pick_split_k(const kfp16_net* n, int M, int N, int groups, int K) {
   const int bn = N <= 64 ? 64 : N <= 128 ? 128 : N <= 160 ? 160 : 256;
   const int n_tiles = (N + bn - 1) / bn;
   const int tiles = m_tiles * n_tiles * groups;
-  const int units = std::max(1, n->ctx->num_sms / cg);
+  int sms = n->ctx->num_sms;
+  if (n->ctx->max_ctas > 0 && n->ctx->max_ctas < sms) sms = n->ctx->max_ctas;   // SMs left to the compute kernels
+  const int units = std::max(1, sms / cg);
   const int kb = (K + 63) / 64;
   int split = units / tiles;                       // largest split that still fits one wave
   if (split < 1) split = 1;
@@ -1134,6 +1140,7 @@ void kfp16_net_destroy(kfp16_net* n) {
       if (l.pf_packed[b]) cudaEventDestroy(l.pf_packed[b]);
     }
   if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
+  for (cudaGraphExec_t g : n->seg_graph) if (g) cudaGraphExecDestroy(g);
   if (n->loss_pinned) cudaFreeHost(n->loss_pinned);
   for (cudaEvent_t e : n->loss_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : n->ev_pool) cudaEventDestroy(e);
@@ -1397,17 +1404,25 @@ int kfp16_net_set_output_grad(kfp16_net* n, const char* layer, const uint16_t* h
   return check_cuda(cudaStreamSynchronize(n->ctx->stream), "grad sync") ? 0 : -1;
 }
 
-int kfp16_net_backward(kfp16_net* n) {
-  if (!n || !n->g32) { set_error("kfp16_net_backward: network was created with train = 0"); return -1; }
-  for (auto& l : n->layers) l.grads_seen = 0;
-  n->layers[n->out_layer].grads_seen = 1;
-  n->ev_next = 0;
-  for (int i = (int)n->layers.size() - 1; i >= 0; --i) {
+// back-propagate through layers [lo, hi) in reverse order; `begin` starts a new backward pass
+static int backward_range(kfp16_net* n, int hi, int lo, bool begin) {
+  if (begin) {
+    for (auto& l : n->layers) l.grads_seen = 0;
+    n->layers[n->out_layer].grads_seen = 1;
+    n->ev_next = 0;
+  }
+  for (int i = hi - 1; i >= lo; --i) {
     Layer& l = n->layers[i];
     if (!l.needs_grad || l.type == L_INPUT) continue;
     if (l.grads_seen == 0) continue;   // nothing flowed into this layer
     if (backward_layer(n, l)) return -1;
   }
+  return 0;
+}
+
+int kfp16_net_backward(kfp16_net* n) {
+  if (!n || !n->g32) { set_error("kfp16_net_backward: network was created with train = 0"); return -1; }
+  if (backward_range(n, (int)n->layers.size(), 0, true)) return -1;
   if (n->side_used) {   // join: the gradient bucket is complete only when the side stream has drained
     if (!check_cuda(cudaEventRecord(n->ev_join, n->side), "wgrad join record") ||
         !check_cuda(cudaStreamWaitEvent(n->ctx->stream, n->ev_join, 0), "wgrad join wait")) return -1;
@@ -1479,6 +1494,94 @@ int kfp16_net_capture(kfp16_net* n, int phases) {
   n->graph_launches[phases] = (int)(kfp16_launch_count() - before);
   return ok ? 0 : -1;
 }
+// ---- segmented step: segment 0 = zero grads + forward + objective + backward of the top layers, segment k > 0 =
+// backward of the next group of layers.  When segment k has run, the gradient-bucket range kfp16_net_segment_grads(k)
+// is final, so a data-parallel loop can all-reduce it while segment k+1 computes (parameters sit in the bucket in
+// layer order and the backward pass walks the layers in reverse).
+static int first_param_of_layer(const Layer& l) {
+  int m = -1;
+  for (int p : {l.pW, l.pB, l.pLin, l.pAff, l.pAffB, l.pBig, l.pBigB, l.pSmall})
+    if (p >= 0 && (m < 0 || p < m)) m = p;
+  return m;
+}
+static int run_segment(kfp16_net* n, int seg) {
+  const int hi = seg == 0 ? (int)n->layers.size() : n->seg_lo[seg - 1];
+  if (seg == 0) {
+    if (kfp16_net_zero_grads(n) || kfp16_net_forward(n) || kfp16_net_loss_half_sq(n, "")) return -1;
+  }
+  return backward_range(n, hi, n->seg_lo[seg], seg == 0);
+}
+int kfp16_net_capture_segments(kfp16_net* n, int nseg) {
+  if (!n || !n->g32 || nseg < 1) { set_error("kfp16_net_capture_segments: needs a training network and nseg >= 1"); return -1; }
+  if (!n->ctx->stream) { set_error("kfp16_net_capture_segments: graph capture needs a non-default stream"); return -1; }
+  if (n->side) { set_error("kfp16_net_capture_segments: not available with the weight-gradient side stream"); return -1; }
+  // cut points: equal shares of the parameter count, counted from the top of the network
+  const int L = (int)n->layers.size();
+  std::vector<size_t> first(L + 1, n->bucket);
+  for (int i = L - 1; i >= 0; --i) {
+    const int p = first_param_of_layer(n->layers[i]);
+    first[i] = p >= 0 ? n->params[p].off : first[i + 1];
+  }
+  for (cudaGraphExec_t g : n->seg_graph) if (g) cudaGraphExecDestroy(g);
+  n->seg_graph.clear(); n->seg_launches.clear(); n->seg_lo.clear(); n->seg_off.clear(); n->seg_cnt.clear();
+  int hi = L;
+  for (int k = 0; k < nseg && hi > 0; ++k) {
+    int lo = 0;
+    if (k + 1 < nseg) {
+      const size_t target = (size_t)((double)n->bucket * (nseg - 1 - k) / nseg);   // bucket offset where this segment should start
+      lo = hi - 1;
+      while (lo > 0 && first[lo] > target) --lo;
+    }
+    if (first[lo] == first[hi]) {          // no parameters in [lo, hi)
+      if (lo > 0) continue;                 // try again with the next (lower) target
+      break;                                // only parameter-free layers are left: the last segment takes them (below)
+    }
+    n->seg_lo.push_back(lo);
+    n->seg_off.push_back(first[lo]);
+    n->seg_cnt.push_back(first[hi] - first[lo]);
+    hi = lo;
+  }
+  if (n->seg_lo.empty()) {
+    n->seg_lo.push_back(0); n->seg_off.push_back(first[0]); n->seg_cnt.push_back(first[L] - first[0]);
+  } else if (n->seg_lo.back() != 0) {       // the last segment back-propagates down to the first layer
+    n->seg_cnt.back() += n->seg_off.back() - first[0];
+    n->seg_off.back() = first[0];
+    n->seg_lo.back() = 0;
+  }
+  const int S = (int)n->seg_lo.size();
+  for (int k = 0; k < S; ++k)                           // eager pass: kernel attributes are set outside the capture
+    if (run_segment(n, k)) return -1;
+  if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "pre-capture sync")) return -1;
+  for (int k = 0; k < S; ++k) {
+    const unsigned long long before = kfp16_launch_count();
+    if (!check_cuda(cudaStreamBeginCapture(n->ctx->stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) return -1;
+    const int rc = run_segment(n, k);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(n->ctx->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return -1; }
+    if (!check_cuda(e, "cudaStreamEndCapture")) return -1;
+    cudaGraphExec_t ge = nullptr;
+    const bool ok = check_cuda(cudaGraphInstantiate(&ge, g, 0), "cudaGraphInstantiate");
+    cudaGraphDestroy(g);
+    if (!ok) return -1;
+    n->seg_graph.push_back(ge);
+    n->seg_launches.push_back((int)(kfp16_launch_count() - before));
+  }
+  return S;
+}
+int kfp16_net_launch_segment(kfp16_net* n, int seg) {
+  if (!n || seg < 0 || seg >= (int)n->seg_graph.size()) { set_error("kfp16_net_launch_segment: segment %d not captured", seg); return -1; }
+  if (!check_cuda(cudaGraphLaunch(n->seg_graph[seg], n->ctx->stream), "cudaGraphLaunch")) return -1;
+  count_launch(n->seg_launches[seg]);
+  return 0;
+}
+int kfp16_net_segment_grads(const kfp16_net* n, int seg, size_t* first_elem, size_t* count) {
+  if (!n || seg < 0 || seg >= (int)n->seg_off.size() || !first_elem || !count) { set_error("kfp16_net_segment_grads: bad argument"); return -1; }
+  *first_elem = n->seg_off[seg];
+  *count = n->seg_cnt[seg];
+  return 0;
+}
+
 int kfp16_net_launch(kfp16_net* n, int phases) {
   if (!n || phases < 1 || phases > 3 || !n->graph[phases]) { set_error("kfp16_net_launch: phases %d not captured", phases); return -1; }
   if (!check_cuda(cudaGraphLaunch(n->graph[phases], n->ctx->stream), "cudaGraphLaunch")) return -1;

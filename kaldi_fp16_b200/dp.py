@@ -69,6 +69,14 @@ class GradAllReducer:
             return None
         return self.dist.all_reduce(self.bucket, op=self.dist.ReduceOp.SUM, group=self.group, async_op=async_op)
 
+    def all_reduce_range(self, first: int, count: int, async_op: bool = True):
+        """all-reduce bucket[first : first + count] only (the part of the gradient a finished segment of the backward
+        pass has completed: kfp16_net_segment_grads), by default asynchronously so that it overlaps the next segment"""
+        if self.world == 1 or count <= 0:
+            return None
+        return self.dist.all_reduce(self.bucket[first:first + count], op=self.dist.ReduceOp.SUM, group=self.group,
+                                    async_op=async_op)
+
     def all_reduce_scalars(self, t):
         """objective / frame-count exchange (3 floats in the chain objective, 1 for 0.5*||out||^2)"""
         if self.world > 1:

@@ -222,6 +222,24 @@ class Network:
             raise _err("ReadLoss")
         return v.value
 
+    def CaptureSegments(self, nseg: int) -> int:
+        """cut the step graph along the backward pass (bucketed gradient all-reduce); returns the segment count"""
+        k = self.lib.kfp16_net_capture_segments(self.ptr, nseg)
+        if k < 0:
+            raise _err("CaptureSegments")
+        return k
+
+    def LaunchSegment(self, seg: int) -> None:
+        if self.lib.kfp16_net_launch_segment(self.ptr, seg) != 0:
+            raise _err("LaunchSegment")
+
+    def SegmentGrads(self, seg: int) -> tuple[int, int]:
+        """(first element, count) of the gradient bucket that is final once segment `seg` has run"""
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        if self.lib.kfp16_net_segment_grads(self.ptr, seg, C.byref(a), C.byref(b)) != 0:
+            raise _err("SegmentGrads")
+        return a.value, b.value
+
     def ReadLossAsync(self, slot: int) -> None:
         """queue the loss download behind the work already in the stream (pinned slot 0/1)"""
         if self.lib.kfp16_net_read_loss_async(self.ptr, slot) != 0:

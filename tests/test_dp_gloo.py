@@ -53,7 +53,15 @@ def worker(rank, world, port, q):
         names = sorted(wg)
         bucket = torch.from_numpy(flat(wg, names).copy())
         red = dp.GradAllReducer(bucket)
-        red.all_reduce()
+        # bucketed exchange as the overlapped loop issues it: ranges from the top of the bucket down, asynchronously
+        whole = bucket.clone()
+        n = bucket.numel()
+        cuts = [n, (2 * n) // 3, n // 4, 0]
+        works = [red.all_reduce_range(lo, hi - lo, async_op=True) for hi, lo in zip(cuts, cuts[1:])]
+        for w in works:
+            w.wait()
+        dist.all_reduce(whole, op=dist.ReduceOp.SUM)
+        assert torch.equal(whole, bucket), "range-wise all-reduce differs from the whole-bucket all-reduce"
         obj = red.all_reduce_scalars(torch.tensor([loss], dtype=torch.float64))
         if rank == 0:
             q.put((bucket.numpy().copy(), float(obj[0])))

@@ -377,3 +377,42 @@ def test_pipelined_loss_read_equals_synchronous_read(handle, lib):
     assert got == sync_losses and all(v > 0 for v in got)
     assert lib.kfp16_net_read_loss_async(net.ptr, 2) == -1
     net.Free()
+
+
+@pytest.mark.parametrize("nseg", [1, 3, 8])
+def test_segmented_step_graphs_equal_the_single_graph(handle, lib, nseg):
+    """kfp16_net_capture_segments cuts the step along the backward pass for a bucketed gradient all-reduce: the
+    segments' gradient ranges tile the bucket in reverse layer order, and launching them in turn gives the same
+    objective and gradients as the eager step"""
+    from kaldi_fp16_b200 import cudart
+    st = cudart.Stream()
+    lib.kfp16_ctx_set_stream(handle.ptr, st.ptr)
+    try:
+        on, net, rng = make_pair(handle, SPLICED, 2, 40, seed=6)
+        x = O.to_f16_rne(rng.standard_normal((80, 64)).astype(np.float32))
+        net.SetInput("input", x)
+        net.ZeroGrads()
+        assert lib.kfp16_net_forward(net.ptr) == 0
+        net.Backward(None)
+        st.synchronize()
+        l_eager, g_eager = net.ReadLoss(), net.WeightGrads()
+        k = net.CaptureSegments(nseg)
+        assert 1 <= k <= nseg
+        ranges = [net.SegmentGrads(i) for i in range(k)]
+        bucket = lib.kfp16_net_bucket_size(net.ptr)
+        assert ranges[0][0] + ranges[0][1] == bucket and ranges[-1][0] == 0
+        for (a0, c0), (a1, c1) in zip(ranges, ranges[1:]):
+            assert a1 + c1 == a0 and c1 > 0          # contiguous, walking down the bucket
+        net.ReadLoss()
+        for i in range(k):
+            net.LaunchSegment(i)
+        st.synchronize()
+        assert abs(net.ReadLoss() - l_eager) <= 1e-5 * abs(l_eager)
+        g = net.WeightGrads()
+        for name in g_eager:
+            assert rel_to_scale(g[name], g_eager[name]) <= 1e-5, name     # fp32 reduction order only
+        assert lib.kfp16_net_launch_segment(net.ptr, k) == -1
+        net.Free()
+    finally:
+        lib.kfp16_ctx_set_stream(handle.ptr, None)
+        st.destroy()
