@@ -34,7 +34,7 @@ constexpr int kBK = 64;           // one 128-byte swizzle row of K per stage
 constexpr int kEpiThreads = 256;  // 8 epilogue warps
 constexpr int kGemmThreads = 128 + kEpiThreads;
 constexpr int kChunkBytes = kBM * 64 * 2;   // [128 x 64] fp16 staging chunk, SW128
-constexpr int kVecBytes = 256 * (2 + 4 + 4);
+constexpr int kVecBytes = 256 * (4 + 4 + 4);   // per-column bias, bn scale, bn shift as fp32 [256] each
 constexpr int kMaxGroups = 2;
 constexpr int kMaxSlabs = 2;
 
@@ -133,6 +133,19 @@ __device__ __forceinline__ float relu_nan(float x) {
   return r;
 }
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
+// packed fp32 arithmetic (sm_100: one FFMA2 / FMUL2 per two values)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
 
 // MODE: 0 plain; 1 shared splice tile (one A tile of 128+8 rows serves both K slabs); 2 = 1 + resident A tile;
 //       3 merged groups (weight gradients of a spliced layer: both row-shifted groups read ONE A and ONE B tile of 64+8
@@ -573,10 +586,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     auto vec_store = [&](int sel) {
       if (epi_tid < BN) {
         uint8_t* vb = smem_vec + sel * kVecBytes;
-        if (flags & EPI_BIAS) reinterpret_cast<__half*>(vb)[epi_tid] = nbias;
+        if (flags & EPI_BIAS) reinterpret_cast<float*>(vb)[epi_tid] = __half2float(nbias);   // converted once per tile
         if (flags & EPI_BN) {
-          reinterpret_cast<float*>(vb + 512)[epi_tid] = nscale;
-          reinterpret_cast<float*>(vb + 512 + 1024)[epi_tid] = nshift;
+          reinterpret_cast<float*>(vb + 1024)[epi_tid] = nscale;
+          reinterpret_cast<float*>(vb + 2048)[epi_tid] = nshift;
         }
       }
     };
@@ -594,8 +607,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       const int n0 = n_blk * BN;
       if (warp == 4) dbg_stamp(p, 2, tile_i, 0);
 
-      const uint32_t s_bias = smem_u32(smem_vec + vsel * kVecBytes);            // fp16 [BN]
-      const uint32_t s_scale = s_bias + 512, s_shift = s_bias + 512 + 1024;     // fp32 [BN] each
+      const uint32_t s_bias = smem_u32(smem_vec + vsel * kVecBytes);            // fp32 [BN] each
+      const uint32_t s_scale = s_bias + 1024, s_shift = s_bias + 2048;
       if (use_vec) {
         named_bar_sync(2, kEpiThreads);      // this tile's vectors (stored at the end of the previous tile) are visible
         vec_fetch(tile + ti.step);           // next tile's: in flight while this tile is processed
@@ -684,12 +697,11 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
                 f = unpack_f16x2(rv.w); r[6] = f.x; r[7] = f.y;
               }
               if (flags & EPI_BIAS) {
-                const uint4 bv = lds128(s_bias + ct * 2);
-                float2 f;
-                f = unpack_f16x2(bv.x); bia[0] = f.x; bia[1] = f.y;
-                f = unpack_f16x2(bv.y); bia[2] = f.x; bia[3] = f.y;
-                f = unpack_f16x2(bv.z); bia[4] = f.x; bia[5] = f.y;
-                f = unpack_f16x2(bv.w); bia[6] = f.x; bia[7] = f.y;
+#pragma unroll
+                for (int e = 0; e < 8; e += 4) {
+                  const float4 b4 = lds128f(s_bias + (ct + e) * 4);
+                  bia[e] = b4.x; bia[e + 1] = b4.y; bia[e + 2] = b4.z; bia[e + 3] = b4.w;
+                }
               }
               if (flags & EPI_BN) {
 #pragma unroll
@@ -701,6 +713,30 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
                 }
               }
               float xo[8];
+              if constexpr (!kGeneric) {
+                // specialised kinds: two columns per instruction with the packed fp32 FMA of sm_100 (FFMA2); each half
+                // is the same fused multiply-add the scalar form compiles to, so the results are bit-identical
+                const float2 alpha2 = make_float2(p.alpha, p.alpha), res2 = make_float2(p.res_scale, p.res_scale);
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  const int bit = j * 8 + e;
+                  float2 x = make_float2(__uint_as_float(v8[e]), __uint_as_float(v8[e + 1]));
+                  if (flags & EPI_BIAS) x = ffma2(x, alpha2, make_float2(bia[e], bia[e + 1]));
+                  else x = fmul2(x, alpha2);
+                  if (flags & EPI_RELU) {
+                    x.x = relu_nan(x.x); x.y = relu_nan(x.y);
+                    if (x.x > 0.0f) maskword |= (1u << bit);
+                    if (x.y > 0.0f) maskword |= (2u << bit);
+                  }
+                  if (flags & EPI_BN) x = ffma2(x, make_float2(bsc[e], bsc[e + 1]), make_float2(bsh[e], bsh[e + 1]));
+                  if (flags & EPI_RESID) x = ffma2(res2, make_float2(r[e], r[e + 1]), x);
+                  if (flags & EPI_GRADMASK) {
+                    x.x = ((gm_word >> bit) & 1u) ? x.x : 0.0f;
+                    x.y = ((gm_word >> bit) & 2u) ? x.y : 0.0f;
+                  }
+                  xo[e] = x.x; xo[e + 1] = x.y;
+                }
+              } else
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int bit = j * 8 + e;           // bit inside the 32-column mask word
