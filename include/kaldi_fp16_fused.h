@@ -103,6 +103,13 @@ typedef struct {
                           (A-stationary mode, small K on 128-wide tiles; default off, see gemm_api.cu);
                           4 = merge the two row-shifted groups of a split-K weight gradient into one tile pass (default off) */
     void *debug_clock_buf; /* profiling: device int64 [grid][3 roles][8 tiles][16] clock64 stamps per warp role; NULL = off */
+    /* A second split-K problem of the same shape (M, N, K, majors, groups) sharing the launch -- the two weight
+     * gradients of one TDNN-F layer: tile groups [groups, 2*groups) compute A2^T * B2 into ws2[].  One launch and half
+     * the split count (= half the fp32 reduction traffic) of two separate calls.  A2.ptr == NULL: none. */
+    kfp16_mat A2, B2;
+    int a2_row_off[2], b2_row_off[2]; /* row offsets per group of the second problem */
+    float *ws2[2];
+    int ws2_ld, ws2_transposed;
 } kfp16_gemm_desc;
 
 /* returns 0 on success, -1 on error (message via kfp16_last_error / ops_last_error) */

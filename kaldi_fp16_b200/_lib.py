@@ -40,6 +40,8 @@ class GemmDesc(C.Structure):
         ("split_k", c_int), ("ws", c_void_p * 2), ("ws_ld", c_int), ("ws_transposed", c_int),
         ("drop_p", c_float), ("drop_seed", c_u32),
         ("force_bn", c_int), ("force_generic", c_int), ("force_cg", c_int), ("no_share", c_int), ("debug_clock_buf", c_void_p),
+        ("A2", KMat), ("B2", KMat), ("a2_row_off", c_int * 2), ("b2_row_off", c_int * 2),
+        ("ws2", c_void_p * 2), ("ws2_ld", c_int), ("ws2_transposed", c_int),
     ]
 
 

@@ -227,7 +227,8 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   const int groups = d->groups < 1 ? 1 : d->groups;
   const int kslabs = d->kslabs < 1 ? 1 : d->kslabs;
   const int kslab_len = d->kslab_len > 0 ? d->kslab_len : d->K;
-  if (groups > kMaxGroups || kslabs > kMaxSlabs) { set_error("kfp16_gemm_ex: at most 2 groups / 2 K-slabs"); return -1; }
+  if (groups > 2 || kslabs > kMaxSlabs) { set_error("kfp16_gemm_ex: at most 2 groups / 2 K-slabs"); return -1; }
+  const bool two = d->A2.ptr != nullptr;    // a second split-K problem of the same shape in this launch
   if (kslabs * kslab_len != d->K) { set_error("kfp16_gemm_ex: K (%d) != kslabs*kslab_len (%d*%d)", d->K, kslabs, kslab_len); return -1; }
   // N is the contiguous dimension of D (and of an MN-major B); K only has to be 16-byte aligned
   // where it is some operand's contiguous dimension, which the tensor-map builder checks (ld % 8)
@@ -242,7 +243,13 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = d->M; p.N = d->N; p.K = d->K;
-  p.groups = groups; p.kslabs = kslabs; p.kslab_len = kslab_len;
+  p.groups = two ? 2 * groups : groups; p.kslabs = kslabs; p.kslab_len = kslab_len;
+  if (two) {
+    if (!(d->split_k > 1) || kslabs != 1 || d->a_major != KFP16_MN_MAJOR || d->b_major != KFP16_MN_MAJOR || !d->B2.ptr) {
+      set_error("kfp16_gemm_ex: a second problem (A2/B2) needs split_k > 1, one K slab and MN-major operands"); return -1;
+    }
+    p.groups2_from = groups;
+  }
 
   if (d->split_k > 1) flags |= EPI_SPLITK;   // caller asked for fp32 accumulation into ws
   const int ek = d->force_generic ? ((flags & EPI_SPLITK) ? EK_SPLITK : EK_GENERIC) : pick_kind(flags);
@@ -279,7 +286,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   static const int env_merge = getenv("KFP16_MERGE") ? atoi(getenv("KFP16_MERGE")) : 0;
   bool merge = false;
   int ma_min = 0, mb_min = 0, ma_span = 0, mb_span = 0;
-  if (cg == 2 && groups == 2 && kslabs == 1 && a_mn && b_mn && (flags & EPI_SPLITK) && (env_merge || d->no_share == 4) && d->no_share != 1 &&
+  if (!two && cg == 2 && groups == 2 && kslabs == 1 && a_mn && b_mn && (flags & EPI_SPLITK) && (env_merge || d->no_share == 4) && d->no_share != 1 &&
       d->N > 128 && d->N <= 160 && !d->force_bn &&
       d->a_col_off[0][0] == d->a_col_off[1][0] && d->b_col_off[0][0] == d->b_col_off[1][0]) {
     ma_min = d->a_row_off[0][0] < d->a_row_off[1][0] ? d->a_row_off[0][0] : d->a_row_off[1][0];
@@ -288,7 +295,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     mb_span = d->b_row_off[0][0] + d->b_row_off[1][0] - 2 * mb_min;
     merge = ma_span <= 8 && mb_span <= 8;
   }
-  const int tile_groups = merge ? 1 : groups;     // groups that multiply the tile count
+  const int tile_groups = merge ? 1 : (two ? 2 * groups : groups);     // groups that multiply the tile count
 
   const int tile_m = kBM * cg;
   const int m_tiles = (d->M + tile_m - 1) / tile_m;
@@ -306,7 +313,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if (ctx->max_ctas > 0 && ctx->max_ctas < ctas) ctas = ctx->max_ctas;
   int units = ctas / cg;                 // CTAs or CTA pairs that can be resident
   if (units < 1) { units = 1; }
-  int bn = merge ? 160 : (d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, groups, split_k, units));
+  int bn = merge ? 160 : (d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, tile_groups, split_k, units));
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) { set_error("kfp16_gemm_ex: unsupported tile width %d", bn); return -1; }
   if (!(flags & EPI_SPLITK) && (bn % 64) != 0 && d->N > bn) {
     // the last 64-wide store chunk of a 160-wide tile would spill into the next tile
@@ -324,6 +331,19 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
       p.a_row_off[g][s] = d->a_row_off[g][s] + A.halo; p.a_col_off[g][s] = d->a_col_off[g][s];
       p.b_row_off[g][s] = d->b_row_off[g][s] + B.halo; p.b_col_off[g][s] = d->b_col_off[g][s];
     }
+  if (two) {
+    const kfp16_mat& A2 = d->A2; const kfp16_mat& B2 = d->B2;
+    const __half* a2_base = (const __half*)A2.ptr - (long long)A2.halo * A2.ld;
+    const __half* b2_base = (const __half*)B2.ptr - (long long)B2.halo * B2.ld;
+    if (!make_map_2d(&p.tmA2, a2_base, A2.cols, (long long)A2.rows + 2 * A2.halo, A2.ld, 64, 64, "A2")) return -1;
+    if (!make_map_2d(&p.tmB2, b2_base, B2.cols, (long long)B2.rows + 2 * B2.halo, B2.ld, 64, 64, "B2")) return -1;
+    for (int g = 0; g < groups; ++g) {
+      p.a_row_off[groups + g][0] = d->a2_row_off[g] + A2.halo;
+      p.b_row_off[groups + g][0] = d->b2_row_off[g] + B2.halo;
+    }
+    p.ws_ld2 = d->ws2_ld;
+    p.ws_transposed2 = d->ws2_transposed;
+  }
   if (merge) {
     p.groups = 1;
     p.a_shift[0] = d->a_row_off[0][0] - ma_min; p.a_shift[1] = d->a_row_off[1][0] - ma_min;
@@ -353,6 +373,14 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if ((flags & EPI_MASK) && !p.mask_out) { set_error("kfp16_gemm_ex: EPI_MASK without mask_out"); return -1; }
   if ((flags & EPI_GRADMASK) && !p.mask_in) { set_error("kfp16_gemm_ex: EPI_GRADMASK without mask_in"); return -1; }
 
+  if (two) {
+    for (int g = 0; g < groups; ++g) {
+      if (d->ws2_transposed ? (!d->ws2[g] || d->ws2_ld < d->M) : (!d->ws2[g] || d->ws2_ld < d->N || (d->ws2_ld % 4) || !aligned16(d->ws2[g]))) {
+        set_error("kfp16_gemm_ex: the second problem needs a 16B-aligned fp32 workspace with ws2_ld >= N, ws2_ld %% 4 == 0"); return -1;
+      }
+      p.ws[groups + g] = d->ws2[g];
+    }
+  }
   for (int g = 0; g < groups; ++g) {
     if (flags & EPI_SPLITK) {
       if (d->ws_transposed ? (!d->ws[g] || d->ws_ld < d->M) : (!d->ws[g] || d->ws_ld < d->N || (d->ws_ld % 4) || !aligned16(d->ws[g]))) {
@@ -396,7 +424,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     cudaEventRecord(ev1, ctx->stream);
     ctx->prof_ev.push_back(ev0);
     ctx->prof_ev.push_back(ev1);
-    ctx->prof_flops.push_back(2.0 * d->M * d->N * d->K * groups);
+    ctx->prof_flops.push_back(2.0 * d->M * d->N * d->K * groups * (two ? 2 : 1));
     char desc[160];
     snprintf(desc, sizeof(desc), "M=%d N=%d K=%d g=%d slabs=%d split=%d bn=%d A%s B%s flags=0x%x ek=%d cg=%d share=%d grid=%d", d->M, d->N, d->K,
              groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, ek, cg, L.share, grid);

@@ -35,7 +35,7 @@ constexpr int kEpiThreads = 256;  // 8 epilogue warps
 constexpr int kGemmThreads = 128 + kEpiThreads;
 constexpr int kChunkBytes = kBM * 64 * 2;   // [128 x 64] fp16 staging chunk, SW128
 constexpr int kVecBytes = 256 * (4 + 4 + 4);   // per-column bias, bn scale, bn shift as fp32 [256] each
-constexpr int kMaxGroups = 2;
+constexpr int kMaxGroups = 4;    // 2 per problem, up to two problems per launch (split-K only)
 constexpr int kMaxSlabs = 2;
 
 enum EpiFlags : uint32_t {
@@ -79,6 +79,9 @@ __host__ __device__ constexpr uint32_t epi_kind_flags(int k) {
 
 struct GemmParams {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmA2, tmB2;       // second split-K problem of the launch: tile groups >= groups2_from read these
+  int groups2_from;             // first group index of the second problem (0 = none)
+  int ws_ld2, ws_transposed2;   // its accumulation target layout
   CUtensorMap tmD[kMaxGroups];  // per-group output view  (TMA store clips to the view)
   CUtensorMap tmR[kMaxGroups];  // per-group residual / C-in view (TMA load)
   int M, N, K;                  // per-group problem size; K = kslabs * kslab_len
@@ -287,6 +290,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    if (kSplitK && p.groups2_from > 0) { tma_prefetch_desc(&p.tmA2); tma_prefetch_desc(&p.tmB2); }
     if (!kSplitK) tma_prefetch_desc(&p.tmD[0]);
   }
   if (warp == 1 && lane == 0) {
@@ -334,6 +338,9 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       const int kb0 = ks * kb_per_split;
       const int kb1 = min(kb0 + kb_per_split, kb_total);
       const int n_loc = n_blk * BN + rank * Cfg::kBNLocal;     // first B row / column staged by this CTA
+      const bool second = kSplitK && p.groups2_from > 0 && g >= p.groups2_from;
+      const CUtensorMap* mapA = second ? &p.tmA2 : &p.tmA;
+      const CUtensorMap* mapB = second ? &p.tmB2 : &p.tmB;
       dbg_stamp(p, 0, tile_i, 0);
       if (Cfg::kAStat && m_row0 != a_m) {
         // new row block: once the MMAs on the previous resident tile are complete, load all its k-blocks
@@ -370,11 +377,11 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           if (Cfg::kAStat) {
             // A is resident
           } else if (!A_MN) {
-            load(sa, &p.tmA, k_in + p.a_col_off[g][slab], m_row0 + p.a_row_off[g][slab]);
+            load(sa, mapA, k_in + p.a_col_off[g][slab], m_row0 + p.a_row_off[g][slab]);
           } else {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-              load(sa + c * Cfg::kMnChunkBytes, &p.tmA, m_row0 + c * 64 + p.a_col_off[g][slab],
+              load(sa + c * Cfg::kMnChunkBytes, mapA, m_row0 + c * 64 + p.a_col_off[g][slab],
                    k_in + p.a_row_off[g][slab]);
           }
           const int nb = SHARE ? p.kslabs : 1;
@@ -382,11 +389,11 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             const int bs = SHARE ? t : slab;
             uint8_t* sbt = sb + t * Cfg::kBTileBytes;
             if (!B_MN) {
-              load(sbt, &p.tmB, k_in + p.b_col_off[g][bs], n_loc + p.b_row_off[g][bs]);
+              load(sbt, mapB, k_in + p.b_col_off[g][bs], n_loc + p.b_row_off[g][bs]);
             } else {
 #pragma unroll
               for (int c = 0; c < Cfg::kBChunks; ++c)
-                load(sbt + c * Cfg::kMnChunkBytes, &p.tmB, n_loc + c * 64 + p.b_col_off[g][bs],
+                load(sbt + c * Cfg::kMnChunkBytes, mapB, n_loc + c * 64 + p.b_col_off[g][bs],
                      k_in + p.b_row_off[g][bs]);
             }
           }
@@ -620,7 +627,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       const uint32_t t_acc = tmem_base + acc * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
 
       if constexpr (kSplitK) {
-        float* ws_row = p.ws[g] + (size_t)row * p.ws_ld;
+        const bool second = p.groups2_from > 0 && g >= p.groups2_from;
+        const int ws_ld = second ? p.ws_ld2 : p.ws_ld;
+        const int ws_tr = second ? p.ws_transposed2 : p.ws_transposed;
+        float* ws_row = p.ws[g] + (size_t)row * ws_ld;
         // The split_k work items of one output tile finish together and accumulate into the SAME addresses: each
         // starts its walk over the 32-column groups at a different group (rotated by its split index) so that they
         // hit different L2 lines at any one time.
@@ -632,15 +642,15 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           uint32_t v[32];
           tmem_ld_32x32(t_acc + c, v);
           tmem_ld_wait();
-          if (p.ws_transposed) {
+          if (ws_tr) {
             // D^T accumulation: element (row, col) -> ws[col*ws_ld + row]; the 32 lanes of a warp hold 32
             // consecutive rows, so each red is one coalesced 128-byte line
             if (row < p.M) {
-              float* wcol = p.ws[g] + (size_t)(n0 + c) * p.ws_ld + row;
+              float* wcol = p.ws[g] + (size_t)(n0 + c) * ws_ld + row;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (n0 + c + j < p.N)
-                  asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(wcol + (size_t)j * p.ws_ld), "f"(__uint_as_float(v[j]) * p.alpha) : "memory");
+                  asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(wcol + (size_t)j * ws_ld), "f"(__uint_as_float(v[j]) * p.alpha) : "memory");
             }
           } else if (row < p.M) {
 #pragma unroll

@@ -738,6 +738,52 @@ int wgrad(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int 
   return kfp16_gemm_ex(n->ctx, &d);
 }
 
+// Two weight gradients of the same shape in ONE launch (the affine and the linear half of a TDNN-F layer: both are
+// [1536 x 160] x 2 groups reduced over the frames): half the split count, so half the fp32 reduction traffic, and one
+// launch less.  Falls back to two calls when the shapes / orientations do not allow it.
+struct WgradArgs { const Buf* X; const Buf* dY; int param, groups, off0, off1; };
+static bool wgrad_fill(kfp16_net* n, const WgradArgs& a, kfp16_mat& A, kfp16_mat& B, int a_off[2], int b_off[2], float* ws[2],
+                       int& ws_ld, int& transposed, int& M, int& N) {
+  const int in = n->params[a.param].rows / a.groups, out = a.dY->cols;
+  const bool tr = out > in && in <= 256 && (in % 8) == 0 && a.X->cols == in;
+  M = tr ? out : in; N = tr ? in : out;
+  const Buf& am = tr ? *a.dY : *a.X;
+  const Buf& bm = tr ? *a.X : *a.dY;
+  A.ptr = am.p; A.rows = am.rows; A.cols = am.cols; A.ld = am.cols; A.halo = 0;
+  B.ptr = bm.p; B.rows = bm.rows; B.cols = bm.cols; B.ld = bm.cols; B.halo = 0;
+  a_off[0] = tr ? 0 : a.off0; a_off[1] = tr ? 0 : a.off1;
+  b_off[0] = tr ? a.off0 : 0; b_off[1] = tr ? a.off1 : 0;
+  ws[0] = G32(n, a.param); ws[1] = G32(n, a.param) + (size_t)in * out;
+  ws_ld = out; transposed = tr ? 1 : 0;
+  return true;
+}
+int wgrad2(kfp16_net* n, const WgradArgs& w1, const WgradArgs& w2) {
+  static const bool fuse = !(getenv("KFP16_WGRAD2") && atoi(getenv("KFP16_WGRAD2")) == 0);
+  kfp16_gemm_desc d;
+  int M1, N1, M2, N2, a1[2], b1[2], a2[2], b2[2], ld1, ld2, t1, t2;
+  float *ws1[2], *ws2[2];
+  memset(&d, 0, sizeof(d));
+  wgrad_fill(n, w1, d.A, d.B, a1, b1, ws1, ld1, t1, M1, N1);
+  wgrad_fill(n, w2, d.A2, d.B2, a2, b2, ws2, ld2, t2, M2, N2);
+  if (!fuse || n->side || M1 != M2 || N1 != N2 || w1.X->rows != w2.X->rows || w1.groups != 2 || w2.groups != 2) {
+    if (wgrad(n, *w1.X, *w1.dY, w1.param, w1.groups, w1.off0, w1.off1)) return -1;
+    return wgrad(n, *w2.X, *w2.dY, w2.param, w2.groups, w2.off0, w2.off1);
+  }
+  d.M = M1; d.N = N1; d.K = w1.X->rows;
+  d.groups = 2; d.kslabs = 1; d.kslab_len = d.K;
+  d.alpha = 1.0f;
+  d.a_major = KFP16_MN_MAJOR; d.b_major = KFP16_MN_MAJOR;
+  for (int g = 0; g < 2; ++g) {
+    d.a_row_off[g][0] = a1[g]; d.b_row_off[g][0] = b1[g];
+    d.a2_row_off[g] = a2[g]; d.b2_row_off[g] = b2[g];
+    d.ws[g] = ws1[g]; d.ws2[g] = ws2[g];
+  }
+  d.ws_ld = ld1; d.ws_transposed = t1;
+  d.ws2_ld = ld2; d.ws2_transposed = t2;
+  d.split_k = pick_split_k(n, d.M, d.N, 4, d.K);
+  return kfp16_gemm_ex(n->ctx, &d);
+}
+
 // same, launched on the side stream after everything issued so far on the main stream
 int wgrad_async(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int off0, int off1) {
   if (!n->side) return wgrad(n, X, dY, param, groups, off0, off1);
@@ -982,7 +1028,9 @@ int backward_layer(kfp16_net* n, Layer& l) {
       } else if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim, rows, l.out_dim, G32(n, l.pAffB))) return -1;
       // dWaff = [B(t) | B(t+s)]^T * dZ: forked onto the side stream BEFORE the narrow dB GEMM below, whose 78 CTAs
       // leave the other SMs free for it
-      if (wgrad_async(n, l.bott, l.dz, l.pAff, sp, 0, s)) return -1;
+      // with a splice both weight gradients of the layer share one launch after dB is known (wgrad2 below)
+      const bool both = sp == 2 && !n->side;
+      if (!both && wgrad_async(n, l.bott, l.dz, l.pAff, sp, 0, s)) return -1;
       {  // dB(r) = dZ(r)*Waff[0:bn]^T + dZ(r-s)*Waff[bn:2bn]^T
         kfp16_gemm_desc d = mk_desc(rows, l.bott_dim, sp * l.out_dim);
         set_A(d, l.dz.p, rows, l.out_dim);
@@ -995,7 +1043,10 @@ int backward_layer(kfp16_net* n, Layer& l) {
         if (s > 0 && kfp16_fold_edges(ctx, l.dbott.p, l.bott_dim, n->opts.n_seq, n->opts.seq_len, l.bott_dim, n->halo)) return -1;
       }
       // dWlin = [X(t-s) | X(t)]^T * dB (side stream, concurrent with the input-gradient GEMM)
-      if (wgrad_async(n, X, l.dbott, l.pLin, sp, -s, 0)) return -1;
+      if (both) {
+        const WgradArgs wa{&l.bott, &l.dz, l.pAff, sp, 0, s}, wl{&X, &l.dbott, l.pLin, sp, -s, 0};
+        if (wgrad2(n, wa, wl)) return -1;
+      } else if (wgrad_async(n, X, l.dbott, l.pLin, sp, -s, 0)) return -1;
       if (l.wants_dx) {   // dX(r) = dB(r+s)*Wlin[0:in]^T + dB(r)*Wlin[in:2in]^T (+ bypass*dY)
         kfp16_gemm_desc d = mk_desc(rows, l.in_dim, sp * l.bott_dim);
         set_A(d, l.dbott.p, rows, l.bott_dim);
