@@ -112,6 +112,22 @@ typedef struct {
     int ws2_ld, ws2_transposed;
 } kfp16_gemm_desc;
 
+/* ---- grouped weight gradients: `count` split-K problems of the SAME shape (dW = A^T B with MN-major operands, two
+ * row-shifted groups each -- the spliced weight gradients of many TDNN-F layers) in ONE persistent launch.  The
+ * problem table (tensor maps, offsets, targets) is built once in device memory; the launch itself takes no per-call
+ * host work, so it can be captured in a CUDA graph.  Against one launch per layer: no per-launch fixed cost, 2-3x
+ * fewer partial-tile reductions (split_k is chosen for the whole set). */
+typedef struct {
+    kfp16_mat A, B;                   /* stored [K x M] and [K x N] */
+    int a_row_off[2], b_row_off[2];   /* per group */
+    float *ws[2];                     /* fp32 targets (accumulated into) */
+    int ws_ld, ws_transposed;
+} kfp16_wgrad_prob;
+typedef struct kfp16_wgrad_group kfp16_wgrad_group;
+kfp16_wgrad_group *kfp16_wgrad_group_create(kfp16_ctx *ctx, int M, int N, int K, const kfp16_wgrad_prob *probs, int count);
+int kfp16_wgrad_group_launch(kfp16_ctx *ctx, kfp16_wgrad_group *grp);
+void kfp16_wgrad_group_destroy(kfp16_wgrad_group *grp);
+
 /* returns 0 on success, -1 on error (message via kfp16_last_error / ops_last_error) */
 int kfp16_gemm_ex(kfp16_ctx *ctx, const kfp16_gemm_desc *d);
 

@@ -45,6 +45,13 @@ class GemmDesc(C.Structure):
     ]
 
 
+class WgradProb(C.Structure):
+    """struct kfp16_wgrad_prob (include/kaldi_fp16_fused.h)."""
+
+    _fields_ = [("A", KMat), ("B", KMat), ("a_row_off", c_int * 2), ("b_row_off", c_int * 2),
+                ("ws", c_void_p * 2), ("ws_ld", c_int), ("ws_transposed", c_int)]
+
+
 class NetOpts(C.Structure):
     """struct kfp16_net_opts (include/kaldi_fp16_nnet.h)."""
 
@@ -145,6 +152,9 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_sgd_step": (c_int, [c_void_p, c_float, c_int]),
     "kfp16_net_set_lr": (c_int, [c_void_p, c_float]),
     "kfp16_net_read_loss": (c_int, [c_void_p, C.POINTER(c_float)]),
+    "kfp16_wgrad_group_create": (c_void_p, [c_void_p, c_int, c_int, c_int, C.POINTER(WgradProb), c_int]),
+    "kfp16_wgrad_group_launch": (c_int, [c_void_p, c_void_p]),
+    "kfp16_wgrad_group_destroy": (None, [c_void_p]),
     "kfp16_net_capture_segments": (c_int, [c_void_p, c_int]),
     "kfp16_net_launch_segment": (c_int, [c_void_p, c_int]),
     "kfp16_net_segment_grads": (c_int, [c_void_p, c_int, C.POINTER(c_size_t), C.POINTER(c_size_t)]),

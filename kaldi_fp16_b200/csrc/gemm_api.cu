@@ -433,6 +433,107 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   return ok ? 0 : -1;
 }
 
+// ------------------------------------------------------------------ grouped weight gradients
+struct kfp16_wgrad_group {
+  int M, N, K, count, split_k, bn, grid;
+  GroupProb* dev = nullptr;
+};
+
+kfp16_wgrad_group* kfp16_wgrad_group_create(kfp16_ctx* ctx, int M, int N, int K, const kfp16_wgrad_prob* probs, int count) {
+  if (!ctx || !probs || count < 1 || M <= 0 || N <= 0 || K <= 0 || (N % 8)) { set_error("kfp16_wgrad_group_create: bad argument"); return nullptr; }
+  if (M <= kBM) { set_error("kfp16_wgrad_group_create: needs M > 128 (CTA-pair tiles)"); return nullptr; }
+  std::vector<GroupProb> host(count);
+  for (int i = 0; i < count; ++i) {
+    const kfp16_wgrad_prob& q = probs[i];
+    GroupProb& g = host[i];
+    memset(&g, 0, sizeof(g));
+    if (!q.A.ptr || !q.B.ptr) { set_error("kfp16_wgrad_group_create: null operand in problem %d", i); return nullptr; }
+    const __half* a_base = (const __half*)q.A.ptr - (long long)q.A.halo * q.A.ld;
+    const __half* b_base = (const __half*)q.B.ptr - (long long)q.B.halo * q.B.ld;
+    if (!make_map_2d(&g.tmA, a_base, q.A.cols, (long long)q.A.rows + 2 * q.A.halo, q.A.ld, 64, 64, "A (grouped)")) return nullptr;
+    if (!make_map_2d(&g.tmB, b_base, q.B.cols, (long long)q.B.rows + 2 * q.B.halo, q.B.ld, 64, 64, "B (grouped)")) return nullptr;
+    for (int k = 0; k < 2; ++k) {
+      g.a_row_off[k] = q.a_row_off[k] + q.A.halo;
+      g.b_row_off[k] = q.b_row_off[k] + q.B.halo;
+      if (q.ws_transposed ? (!q.ws[k] || q.ws_ld < M) : (!q.ws[k] || q.ws_ld < N || (q.ws_ld % 4) || !aligned16(q.ws[k]))) {
+        set_error("kfp16_wgrad_group_create: problem %d needs 16B-aligned fp32 targets with ws_ld >= N, ws_ld %% 4 == 0", i); return nullptr;
+      }
+      g.ws[k] = q.ws[k];
+    }
+    g.ws_ld = q.ws_ld; g.ws_transposed = q.ws_transposed;
+  }
+  kfp16_wgrad_group* grp = new kfp16_wgrad_group();
+  grp->M = M; grp->N = N; grp->K = K; grp->count = count;
+  grp->bn = N <= 64 ? 64 : N <= 128 ? 128 : N <= 160 ? 160 : 256;
+  int sms = ctx->num_sms;
+  if (ctx->max_ctas > 0 && ctx->max_ctas < sms) sms = ctx->max_ctas;
+  const int units = std::max(1, sms / 2);
+  const long long tiles = (long long)((M + 255) / 256) * ((N + grp->bn - 1) / grp->bn) * 2 * count;
+  const int kb = (K + kBK - 1) / kBK;
+  // split so that the rounds of work items waste little of the last round; every extra split costs another fp32
+  // reduction pass over the tiles (L2 atomics at ~3.5 TB/s), weighed as 8 k-blocks
+  int best = 1; double best_cost = 1e30;
+  for (int sp = 1; sp <= 8 && sp <= kb / 4; ++sp) {
+    const long long rounds = (tiles * sp + units - 1) / units;
+    const double cost = (double)rounds * ((kb + sp - 1) / sp + 8.0);
+    if (cost < best_cost * 0.99) { best_cost = cost; best = sp; }
+  }
+  grp->split_k = best < 2 && tiles < units ? 2 : best;
+  { const int per = (kb + grp->split_k - 1) / grp->split_k; grp->split_k = (kb + per - 1) / per; }
+  const long long items = tiles * grp->split_k;
+  grp->grid = 2 * (int)(items < units ? items : units);
+  if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice") ||
+      !check_cuda(cudaMalloc((void**)&grp->dev, sizeof(GroupProb) * count), "cudaMalloc (grouped problem table)") ||
+      !check_cuda(cudaMemcpy(grp->dev, host.data(), sizeof(GroupProb) * count, cudaMemcpyHostToDevice), "grouped problem table upload")) {
+    if (grp->dev) cudaFree(grp->dev);
+    delete grp;
+    return nullptr;
+  }
+  return grp;
+}
+int kfp16_wgrad_group_launch(kfp16_ctx* ctx, kfp16_wgrad_group* grp) {
+  if (!ctx || !grp) { set_error("kfp16_wgrad_group_launch: null argument"); return -1; }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.probs = grp->dev;
+  p.M = grp->M; p.N = grp->N; p.K = grp->K;
+  p.groups = 2 * grp->count; p.kslabs = 1; p.kslab_len = grp->K;
+  p.split_k = grp->split_k;
+  p.flags = EPI_SPLITK;
+  p.alpha = 1.0f;
+  p.mma_rep = 1;
+  if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ctx->profile) {
+    if (!check_cuda(cudaEventCreate(&ev0), "cudaEventCreate") || !check_cuda(cudaEventCreate(&ev1), "cudaEventCreate")) return -1;
+    cudaEventRecord(ev0, ctx->stream);
+  }
+  GemmLaunch L;
+  L.bn = grp->bn; L.a_mn = true; L.b_mn = true; L.ek = EK_SPLITK; L.cg = 2; L.share = 0; L.grid = grp->grid;
+  bool ok = false;
+  switch (grp->bn) {
+    case 64: ok = launch_gemm_bn<64>(ctx, p, L); break;
+    case 128: ok = launch_gemm_bn<128>(ctx, p, L); break;
+    case 160: ok = launch_gemm_bn<160>(ctx, p, L); break;
+    case 256: ok = launch_gemm_bn<256>(ctx, p, L); break;
+  }
+  if (ctx->profile) {
+    cudaEventRecord(ev1, ctx->stream);
+    ctx->prof_ev.push_back(ev0);
+    ctx->prof_ev.push_back(ev1);
+    ctx->prof_flops.push_back(2.0 * grp->M * grp->N * grp->K * 2 * grp->count);
+    char desc[160];
+    snprintf(desc, sizeof(desc), "grouped wgrad x%d M=%d N=%d K=%d split=%d bn=%d grid=%d", grp->count, grp->M, grp->N, grp->K, grp->split_k, grp->bn, grp->grid);
+    ctx->prof_desc.push_back(desc);
+  }
+  return ok ? 0 : -1;
+}
+void kfp16_wgrad_group_destroy(kfp16_wgrad_group* grp) {
+  if (!grp) return;
+  if (grp->dev) cudaFree(grp->dev);
+  delete grp;
+}
+
 int kfp16_gemm(kfp16_ctx* ctx, int M, int N, int K, float alpha, const void* A, int transA,
                const void* B, int transB, float beta, void* C) {
   if (!ctx) { set_error("kfp16_gemm: null context (create one with ops_cublas_create / kfp16_ctx_create)"); return -1; }

@@ -77,7 +77,17 @@ __host__ __device__ constexpr uint32_t epi_kind_flags(int k) {
        : 0u;
 }
 
+// One problem of a grouped split-K launch (weight gradients of many layers in one persistent kernel): the table lives
+// in device memory (a launch can carry more problems than kernel parameters could hold tensor maps for).
+struct alignas(64) GroupProb {
+  CUtensorMap tmA, tmB;
+  int a_row_off[2], b_row_off[2];   // per row-shifted group of the problem
+  float* ws[2];                     // fp32 accumulation targets
+  int ws_ld, ws_transposed;
+};
+
 struct GemmParams {
+  const GroupProb* probs;       // grouped launch: tile group g belongs to problem g / 2 (nullptr = single problem)
   CUtensorMap tmA, tmB;
   CUtensorMap tmA2, tmB2;       // second split-K problem of the launch: tile groups >= groups2_from read these
   int groups2_from;             // first group index of the second problem (0 = none)
@@ -341,6 +351,16 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       const bool second = kSplitK && p.groups2_from > 0 && g >= p.groups2_from;
       const CUtensorMap* mapA = second ? &p.tmA2 : &p.tmA;
       const CUtensorMap* mapB = second ? &p.tmB2 : &p.tmB;
+      int grp_a_row = 0, grp_b_row = 0;
+      const bool grouped = kSplitK && p.probs != nullptr;
+      const int gi = grouped ? 0 : g;     // index into the per-group parameter arrays (unused, zero, in a grouped launch)
+      if (grouped) {
+        const GroupProb& pr = p.probs[g >> 1];
+        mapA = &pr.tmA; mapB = &pr.tmB;
+        grp_a_row = pr.a_row_off[g & 1]; grp_b_row = pr.b_row_off[g & 1];
+        if (elect_one()) { tma_prefetch_desc(mapA); tma_prefetch_desc(mapB); }
+        __syncwarp();
+      }
       dbg_stamp(p, 0, tile_i, 0);
       if (Cfg::kAStat && m_row0 != a_m) {
         // new row block: once the MMAs on the previous resident tile are complete, load all its k-blocks
@@ -381,8 +401,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           } else {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-              load(sa + c * Cfg::kMnChunkBytes, mapA, m_row0 + c * 64 + p.a_col_off[g][slab],
-                   k_in + p.a_row_off[g][slab]);
+              load(sa + c * Cfg::kMnChunkBytes, mapA, m_row0 + c * 64 + p.a_col_off[gi][slab],
+                   k_in + (grouped ? grp_a_row : p.a_row_off[gi][slab]));
           }
           const int nb = SHARE ? p.kslabs : 1;
           for (int t = 0; t < nb; ++t) {
@@ -393,8 +413,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             } else {
 #pragma unroll
               for (int c = 0; c < Cfg::kBChunks; ++c)
-                load(sbt + c * Cfg::kMnChunkBytes, mapB, n_loc + c * 64 + p.b_col_off[g][bs],
-                     k_in + p.b_row_off[g][bs]);
+                load(sbt + c * Cfg::kMnChunkBytes, mapB, n_loc + c * 64 + p.b_col_off[gi][bs],
+                     k_in + (grouped ? grp_b_row : p.b_row_off[gi][bs]));
             }
           }
         }
@@ -628,9 +648,14 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
 
       if constexpr (kSplitK) {
         const bool second = p.groups2_from > 0 && g >= p.groups2_from;
-        const int ws_ld = second ? p.ws_ld2 : p.ws_ld;
-        const int ws_tr = second ? p.ws_transposed2 : p.ws_transposed;
-        float* ws_row = p.ws[g] + (size_t)row * ws_ld;
+        int ws_ld = second ? p.ws_ld2 : p.ws_ld;
+        int ws_tr = second ? p.ws_transposed2 : p.ws_transposed;
+        float* ws_base = p.probs ? nullptr : p.ws[g < kMaxGroups ? g : 0];
+        if (p.probs) {
+          const GroupProb& pr = p.probs[g >> 1];
+          ws_base = pr.ws[g & 1]; ws_ld = pr.ws_ld; ws_tr = pr.ws_transposed;
+        }
+        float* ws_row = ws_base + (size_t)row * ws_ld;
         // The split_k work items of one output tile finish together and accumulate into the SAME addresses: each
         // starts its walk over the 32-column groups at a different group (rotated by its split index) so that they
         // hit different L2 lines at any one time.
@@ -646,7 +671,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             // D^T accumulation: element (row, col) -> ws[col*ws_ld + row]; the 32 lanes of a warp hold 32
             // consecutive rows, so each red is one coalesced 128-byte line
             if (row < p.M) {
-              float* wcol = p.ws[g] + (size_t)(n0 + c) * ws_ld + row;
+              float* wcol = ws_base + (size_t)(n0 + c) * ws_ld + row;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (n0 + c + j < p.N)

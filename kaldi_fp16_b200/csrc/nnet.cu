@@ -101,6 +101,8 @@ struct Layer {
 
 }  // namespace
 
+struct WgradArgs { const Buf* X; const Buf* dY; int param, groups, off0, off1; };
+
 struct kfp16_net {
   kfp16_ctx* ctx = nullptr;
   kfp16_net_opts opts{};
@@ -129,6 +131,9 @@ struct kfp16_net {
   double flops_fwd = 0;
   cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
   // the step graph cut into segments along the backward pass (gradient all-reduce overlapped bucket by bucket)
+  // spliced weight gradients deferred to one grouped launch per backward pass / segment (kfp16_wgrad_group)
+  std::vector<WgradArgs> deferred;
+  std::map<std::vector<int>, kfp16_wgrad_group*> wg_groups;
   std::vector<cudaGraphExec_t> seg_graph;
   std::vector<int> seg_launches, seg_lo;            // per segment: kernels, first layer index it back-propagates
   std::vector<size_t> seg_off, seg_cnt;              // gradient-bucket range completed by the segment (elements)
@@ -741,7 +746,6 @@ int wgrad(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int 
 // Two weight gradients of the same shape in ONE launch (the affine and the linear half of a TDNN-F layer: both are
 // [1536 x 160] x 2 groups reduced over the frames): half the split count, so half the fp32 reduction traffic, and one
 // launch less.  Falls back to two calls when the shapes / orientations do not allow it.
-struct WgradArgs { const Buf* X; const Buf* dY; int param, groups, off0, off1; };
 static bool wgrad_fill(kfp16_net* n, const WgradArgs& a, kfp16_mat& A, kfp16_mat& B, int a_off[2], int b_off[2], float* ws[2],
                        int& ws_ld, int& transposed, int& M, int& N) {
   const int in = n->params[a.param].rows / a.groups, out = a.dY->cols;
@@ -782,6 +786,50 @@ int wgrad2(kfp16_net* n, const WgradArgs& w1, const WgradArgs& w2) {
   d.ws2_ld = ld2; d.ws2_transposed = t2;
   d.split_k = pick_split_k(n, d.M, d.N, 4, d.K);
   return kfp16_gemm_ex(n->ctx, &d);
+}
+
+// Defer a layer's pair of spliced weight gradients to the grouped launch at the end of the backward pass (or of the
+// current graph segment): all TDNN-F layers of a stack have the same gradient shape, so the whole set runs as ONE
+// persistent split-K kernel (kfp16_wgrad_group_*).  Falls back to the per-layer launch when shapes differ.
+int defer_wgrads(kfp16_net* n, const WgradArgs& w1, const WgradArgs& w2) {
+  static const bool grouping = !(getenv("KFP16_WGRAD_GROUP") && atoi(getenv("KFP16_WGRAD_GROUP")) == 0);
+  auto dims = [&](const WgradArgs& a, int& M, int& N) {
+    kfp16_mat A, B; int ao[2], bo[2], ld, tr; float* ws[2];
+    wgrad_fill(n, a, A, B, ao, bo, ws, ld, tr, M, N);
+  };
+  int M1, N1, M2, N2;
+  dims(w1, M1, N1); dims(w2, M2, N2);
+  bool ok = grouping && !n->side && M1 == M2 && N1 == N2 && M1 > 128 && w1.groups == 2 && w2.groups == 2 && w1.X->rows == w2.X->rows;
+  if (ok && !n->deferred.empty()) {
+    int M0, N0;
+    dims(n->deferred[0], M0, N0);
+    ok = M0 == M1 && N0 == N1 && n->deferred[0].X->rows == w1.X->rows;
+  }
+  if (!ok) return wgrad2(n, w1, w2);
+  n->deferred.push_back(w1);
+  n->deferred.push_back(w2);
+  return 0;
+}
+int flush_wgrads(kfp16_net* n) {
+  if (n->deferred.empty()) return 0;
+  std::vector<WgradArgs> list;
+  list.swap(n->deferred);
+  if (list.size() == 2) return wgrad2(n, list[0], list[1]);
+  std::vector<int> key;
+  for (const WgradArgs& a : list) key.push_back(a.param);
+  auto it = n->wg_groups.find(key);
+  if (it == n->wg_groups.end()) {
+    std::vector<kfp16_wgrad_prob> probs(list.size());
+    int M = 0, N = 0;
+    for (size_t i = 0; i < list.size(); ++i) {
+      kfp16_wgrad_prob& q = probs[i];
+      wgrad_fill(n, list[i], q.A, q.B, q.a_row_off, q.b_row_off, q.ws, q.ws_ld, q.ws_transposed, M, N);
+    }
+    kfp16_wgrad_group* g = kfp16_wgrad_group_create(n->ctx, M, N, list[0].X->rows, probs.data(), (int)probs.size());
+    if (!g) return -1;
+    it = n->wg_groups.emplace(key, g).first;
+  }
+  return kfp16_wgrad_group_launch(n->ctx, it->second);
 }
 
 // same, launched on the side stream after everything issued so far on the main stream
@@ -1045,7 +1093,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
       // dWlin = [X(t-s) | X(t)]^T * dB (side stream, concurrent with the input-gradient GEMM)
       if (both) {
         const WgradArgs wa{&l.bott, &l.dz, l.pAff, sp, 0, s}, wl{&X, &l.dbott, l.pLin, sp, -s, 0};
-        if (wgrad2(n, wa, wl)) return -1;
+        if (defer_wgrads(n, wa, wl)) return -1;
       } else if (wgrad_async(n, X, l.dbott, l.pLin, sp, -s, 0)) return -1;
       if (l.wants_dx) {   // dX(r) = dB(r+s)*Wlin[0:in]^T + dB(r)*Wlin[in:2in]^T (+ bypass*dY)
         kfp16_gemm_desc d = mk_desc(rows, l.in_dim, sp * l.bott_dim);
@@ -1191,6 +1239,7 @@ void kfp16_net_destroy(kfp16_net* n) {
       if (l.pf_packed[b]) cudaEventDestroy(l.pf_packed[b]);
     }
   if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
+  for (auto& kv : n->wg_groups) kfp16_wgrad_group_destroy(kv.second);
   for (cudaGraphExec_t g : n->seg_graph) if (g) cudaGraphExecDestroy(g);
   if (n->loss_pinned) cudaFreeHost(n->loss_pinned);
   for (cudaEvent_t e : n->loss_ev) if (e) cudaEventDestroy(e);
@@ -1474,6 +1523,7 @@ static int backward_range(kfp16_net* n, int hi, int lo, bool begin) {
 int kfp16_net_backward(kfp16_net* n) {
   if (!n || !n->g32) { set_error("kfp16_net_backward: network was created with train = 0"); return -1; }
   if (backward_range(n, (int)n->layers.size(), 0, true)) return -1;
+  if (flush_wgrads(n)) return -1;
   if (n->side_used) {   // join: the gradient bucket is complete only when the side stream has drained
     if (!check_cuda(cudaEventRecord(n->ev_join, n->side), "wgrad join record") ||
         !check_cuda(cudaStreamWaitEvent(n->ctx->stream, n->ev_join, 0), "wgrad join wait")) return -1;
@@ -1560,7 +1610,8 @@ static int run_segment(kfp16_net* n, int seg) {
   if (seg == 0) {
     if (kfp16_net_zero_grads(n) || kfp16_net_forward(n) || kfp16_net_loss_half_sq(n, "")) return -1;
   }
-  return backward_range(n, hi, n->seg_lo[seg], seg == 0);
+  if (backward_range(n, hi, n->seg_lo[seg], seg == 0)) return -1;
+  return flush_wgrads(n);      // the segment's gradient range must be complete when it ends
 }
 int kfp16_net_capture_segments(kfp16_net* n, int nseg) {
   if (!n || !n->g32 || nseg < 1) { set_error("kfp16_net_capture_segments: needs a training network and nseg >= 1"); return -1; }

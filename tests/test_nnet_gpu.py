@@ -374,7 +374,8 @@ def test_pipelined_loss_read_equals_synchronous_read(handle, lib):
         if i > 0:
             got.append(net.WaitLoss((i - 1) & 1))
     got.append(net.WaitLoss((len(xs) - 1) & 1))
-    assert got == sync_losses and all(v > 0 for v in got)
+    # the objective is an atomic fp32 sum: equal up to summation order
+    assert all(abs(a - b) <= 1e-5 * abs(b) for a, b in zip(got, sync_losses)) and all(v > 0 for v in got)
     assert lib.kfp16_net_read_loss_async(net.ptr, 2) == -1
     net.Free()
 
