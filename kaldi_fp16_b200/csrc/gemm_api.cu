@@ -436,12 +436,22 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
 // ------------------------------------------------------------------ grouped weight gradients
 struct kfp16_wgrad_group {
   int M, N, K, count, split_k, bn, grid;
+  bool merged = false;      // MODE 3 kernels: one tile pass per problem serves both row-shifted groups
   GroupProb* dev = nullptr;
 };
 
 kfp16_wgrad_group* kfp16_wgrad_group_create(kfp16_ctx* ctx, int M, int N, int K, const kfp16_wgrad_prob* probs, int count) {
   if (!ctx || !probs || count < 1 || M <= 0 || N <= 0 || K <= 0 || (N % 8)) { set_error("kfp16_wgrad_group_create: bad argument"); return nullptr; }
   if (M <= kBM) { set_error("kfp16_wgrad_group_create: needs M > 128 (CTA-pair tiles)"); return nullptr; }
+  // merged groups (one A and one B tile of 64 + span k-rows per k-block for both groups of a problem): in a grouped
+  // launch the main loop is bound by the L2->SM fabric (~6.3 KB/cycle), which the merge nearly halves; it needs the
+  // 160-wide kernel and row shifts of at most 8.  KFP16_WGRAD_MERGE=0 opts out.
+  static const bool env_wmerge = !(getenv("KFP16_WGRAD_MERGE") && atoi(getenv("KFP16_WGRAD_MERGE")) == 0);
+  bool merged = env_wmerge && N > 128 && N <= 160;
+  for (int i = 0; i < count && merged; ++i) {
+    const int sa = abs(probs[i].a_row_off[0] - probs[i].a_row_off[1]), sb = abs(probs[i].b_row_off[0] - probs[i].b_row_off[1]);
+    if (sa > 8 || sb > 8) merged = false;
+  }
   std::vector<GroupProb> host(count);
   for (int i = 0; i < count; ++i) {
     const kfp16_wgrad_prob& q = probs[i];
@@ -450,11 +460,19 @@ kfp16_wgrad_group* kfp16_wgrad_group_create(kfp16_ctx* ctx, int M, int N, int K,
     if (!q.A.ptr || !q.B.ptr) { set_error("kfp16_wgrad_group_create: null operand in problem %d", i); return nullptr; }
     const __half* a_base = (const __half*)q.A.ptr - (long long)q.A.halo * q.A.ld;
     const __half* b_base = (const __half*)q.B.ptr - (long long)q.B.halo * q.B.ld;
-    if (!make_map_2d(&g.tmA, a_base, q.A.cols, (long long)q.A.rows + 2 * q.A.halo, q.A.ld, 64, 64, "A (grouped)")) return nullptr;
-    if (!make_map_2d(&g.tmB, b_base, q.B.cols, (long long)q.B.rows + 2 * q.B.halo, q.B.ld, 64, 64, "B (grouped)")) return nullptr;
+    const int a_min = std::min(q.a_row_off[0], q.a_row_off[1]), b_min = std::min(q.b_row_off[0], q.b_row_off[1]);
+    const int a_span = merged ? abs(q.a_row_off[0] - q.a_row_off[1]) : 0, b_span = merged ? abs(q.b_row_off[0] - q.b_row_off[1]) : 0;
+    if (!make_map_2d(&g.tmA, a_base, q.A.cols, (long long)q.A.rows + 2 * q.A.halo, q.A.ld, 64, 64 + a_span, "A (grouped)")) return nullptr;
+    if (!make_map_2d(&g.tmB, b_base, q.B.cols, (long long)q.B.rows + 2 * q.B.halo, q.B.ld, 64, 64 + b_span, "B (grouped)")) return nullptr;
+    if (merged) {
+      const int b_chunks = (160 / 2 + 63) / 64;
+      g.merge_tx = 2 * (64 + a_span) * 128 + b_chunks * (64 + b_span) * 128;
+    }
     for (int k = 0; k < 2; ++k) {
-      g.a_row_off[k] = q.a_row_off[k] + q.A.halo;
-      g.b_row_off[k] = q.b_row_off[k] + q.B.halo;
+      g.a_shift[k] = q.a_row_off[k] - a_min;
+      g.b_shift[k] = q.b_row_off[k] - b_min;
+      g.a_row_off[k] = (merged ? a_min : q.a_row_off[k]) + q.A.halo;
+      g.b_row_off[k] = (merged ? b_min : q.b_row_off[k]) + q.B.halo;
       if (q.ws_transposed ? (!q.ws[k] || q.ws_ld < M) : (!q.ws[k] || q.ws_ld < N || (q.ws_ld % 4) || !aligned16(q.ws[k]))) {
         set_error("kfp16_wgrad_group_create: problem %d needs 16B-aligned fp32 targets with ws_ld >= N, ws_ld %% 4 == 0", i); return nullptr;
       }
@@ -468,17 +486,21 @@ kfp16_wgrad_group* kfp16_wgrad_group_create(kfp16_ctx* ctx, int M, int N, int K,
   int sms = ctx->num_sms;
   if (ctx->max_ctas > 0 && ctx->max_ctas < sms) sms = ctx->max_ctas;
   const int units = std::max(1, sms / 2);
-  const long long tiles = (long long)((M + 255) / 256) * ((N + grp->bn - 1) / grp->bn) * 2 * count;
+  grp->merged = merged;
+  const long long tiles = (long long)((M + 255) / 256) * ((N + grp->bn - 1) / grp->bn) * (merged ? 1 : 2) * count;
   const int kb = (K + kBK - 1) / kBK;
   // split so that the rounds of work items waste little of the last round; every extra split costs another fp32
   // reduction pass over the tiles (L2 atomics at ~3.5 TB/s), weighed as 8 k-blocks
   int best = 1; double best_cost = 1e30;
   for (int sp = 1; sp <= 8 && sp <= kb / 4; ++sp) {
     const long long rounds = (tiles * sp + units - 1) / units;
-    const double cost = (double)rounds * ((kb + sp - 1) / sp + 8.0);
+    // (merged tiles: the epilogue covers both accumulator stages and does not overlap the next tile's main loop --
+    // measured on 32 problems of 1536 x 160 x 9984: split 1 / 2 / 3 / 4 = 271 / 298 / 290 / 321 us)
+    const double cost = (double)rounds * ((kb + sp - 1) / sp + (merged ? 24.0 : 8.0));
     if (cost < best_cost * 0.99) { best_cost = cost; best = sp; }
   }
   grp->split_k = best < 2 && tiles < units ? 2 : best;
+  if (const char* e = getenv("KFP16_WGRAD_SPLIT")) { if (atoi(e) > 0) grp->split_k = atoi(e); }   // experiments
   { const int per = (kb + grp->split_k - 1) / grp->split_k; grp->split_k = (kb + per - 1) / per; }
   const long long items = tiles * grp->split_k;
   grp->grid = 2 * (int)(items < units ? items : units);
@@ -497,7 +519,7 @@ int kfp16_wgrad_group_launch(kfp16_ctx* ctx, kfp16_wgrad_group* grp) {
   memset(&p, 0, sizeof(p));
   p.probs = grp->dev;
   p.M = grp->M; p.N = grp->N; p.K = grp->K;
-  p.groups = 2 * grp->count; p.kslabs = 1; p.kslab_len = grp->K;
+  p.groups = (grp->merged ? 1 : 2) * grp->count; p.kslabs = 1; p.kslab_len = grp->K;
   p.split_k = grp->split_k;
   p.flags = EPI_SPLITK;
   p.alpha = 1.0f;
@@ -509,7 +531,7 @@ int kfp16_wgrad_group_launch(kfp16_ctx* ctx, kfp16_wgrad_group* grp) {
     cudaEventRecord(ev0, ctx->stream);
   }
   GemmLaunch L;
-  L.bn = grp->bn; L.a_mn = true; L.b_mn = true; L.ek = EK_SPLITK; L.cg = 2; L.share = 0; L.grid = grp->grid;
+  L.bn = grp->bn; L.a_mn = true; L.b_mn = true; L.ek = EK_SPLITK; L.cg = 2; L.share = grp->merged ? 3 : 0; L.grid = grp->grid;
   bool ok = false;
   switch (grp->bn) {
     case 64: ok = launch_gemm_bn<64>(ctx, p, L); break;
@@ -523,7 +545,7 @@ int kfp16_wgrad_group_launch(kfp16_ctx* ctx, kfp16_wgrad_group* grp) {
     ctx->prof_ev.push_back(ev1);
     ctx->prof_flops.push_back(2.0 * grp->M * grp->N * grp->K * 2 * grp->count);
     char desc[160];
-    snprintf(desc, sizeof(desc), "grouped wgrad x%d M=%d N=%d K=%d split=%d bn=%d grid=%d", grp->count, grp->M, grp->N, grp->K, grp->split_k, grp->bn, grp->grid);
+    snprintf(desc, sizeof(desc), "grouped wgrad x%d M=%d N=%d K=%d split=%d bn=%d merged=%d grid=%d", grp->count, grp->M, grp->N, grp->K, grp->split_k, grp->bn, (int)grp->merged, grp->grid);
     ctx->prof_desc.push_back(desc);
   }
   return ok ? 0 : -1;

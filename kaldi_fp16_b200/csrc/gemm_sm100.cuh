@@ -84,6 +84,10 @@ struct alignas(64) GroupProb {
   int a_row_off[2], b_row_off[2];   // per row-shifted group of the problem
   float* ws[2];                     // fp32 accumulation targets
   int ws_ld, ws_transposed;
+  // merged-group kernels (MODE 3): one tile per problem; tmA / tmB boxes are 64 + span k-rows starting at
+  // a_row_off[0] / b_row_off[0], group g reads them from k-row a_shift[g] / b_shift[g]; merge_tx = bytes per k-block per CTA
+  int a_shift[2], b_shift[2];
+  int merge_tx;
 };
 
 struct GemmParams {
@@ -354,10 +358,12 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       int grp_a_row = 0, grp_b_row = 0;
       const bool grouped = kSplitK && p.probs != nullptr;
       const int gi = grouped ? 0 : g;     // index into the per-group parameter arrays (unused, zero, in a grouped launch)
+      uint32_t tile_tx = stage_tx;
       if (grouped) {
-        const GroupProb& pr = p.probs[g >> 1];
+        const GroupProb& pr = p.probs[kMerge ? g : g >> 1];
         mapA = &pr.tmA; mapB = &pr.tmB;
-        grp_a_row = pr.a_row_off[g & 1]; grp_b_row = pr.b_row_off[g & 1];
+        grp_a_row = pr.a_row_off[kMerge ? 0 : g & 1]; grp_b_row = pr.b_row_off[kMerge ? 0 : g & 1];
+        if (kMerge) tile_tx = (uint32_t)pr.merge_tx;
         if (elect_one()) { tma_prefetch_desc(mapA); tma_prefetch_desc(mapB); }
         __syncwarp();
       }
@@ -388,8 +394,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           uint8_t* sb = Cfg::kAStat ? sa : sa + Cfg::kABytes;
           // completion is signalled on this CTA's full barrier (CG=1) or the pair leader's (CG=2)
           const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[stage]), 0) : 0;
-          if (CG == 2) mbar_arrive_expect_tx_cluster(fb, stage_tx);
-          else mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+          if (CG == 2) mbar_arrive_expect_tx_cluster(fb, tile_tx);
+          else mbar_arrive_expect_tx(&full_bar[stage], tile_tx);
           auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
             if (CG == 2) tma_load_2d_pair(dst, m, fb, c0, c1);
             else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
@@ -450,6 +456,11 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
         dbg_stamp(p, 1, tile_i, 0);
+        int sh_a[2] = {p.a_shift[0], p.a_shift[1]}, sh_b[2] = {p.b_shift[0], p.b_shift[1]};
+        if (kMerge && p.probs != nullptr) {      // grouped launch: this tile's problem carries its own shifts
+          const GroupProb& pr = p.probs[(tile % ti.tiles_per_split) / (ti.m_tiles * ti.n_tiles)];
+          sh_a[0] = pr.a_shift[0]; sh_a[1] = pr.a_shift[1]; sh_b[0] = pr.b_shift[0]; sh_b[1] = pr.b_shift[1];
+        }
         if (kMerge) {      // a merged tile owns BOTH accumulator stages (one per group)
           mbar_wait(&tempty_bar[0], acc_phase ^ 1);
           mbar_wait(&tempty_bar[1], acc_phase ^ 1);
@@ -483,8 +494,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
 #pragma unroll
               for (int gq = 0; gq < 2; ++gq) {
                 // group gq: both operands start a_shift / b_shift whole 128-byte k-rows into their tiles
-                const uint64_t ad = adesc0 + so + (uint64_t)((uint32_t)p.a_shift[gq] * 8u);
-                const uint64_t bd = bdesc0 + so + (uint64_t)((uint32_t)p.b_shift[gq] * 8u);
+                const uint64_t ad = adesc0 + so + (uint64_t)((uint32_t)sh_a[gq] * 8u);
+                const uint64_t bd = bdesc0 + so + (uint64_t)((uint32_t)sh_b[gq] * 8u);
                 const uint32_t dt = tmem_base + gq * Cfg::kAccCols;
                 for (int k = 0; k < k16s; ++k) mma(dt, ad + k * a_kstep, bd + k * b_kstep, (kb > kb0 || k > 0) ? 1u : 0u);
               }
@@ -629,6 +640,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     for (int gg = 0; gg < (kMerge ? 2 : 1); ++gg) {
       int n_blk, m_row0, g, ks;
       ti.decode(tile, n_blk, m_row0, g, ks);
+      const int prob = kMerge ? g : g >> 1;      // grouped launches: index into the problem table
       if (kMerge) g = gg;
       const int row = m_row0 + row_in_tile;
       const int n0 = n_blk * BN;
@@ -652,7 +664,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         int ws_tr = second ? p.ws_transposed2 : p.ws_transposed;
         float* ws_base = p.probs ? nullptr : p.ws[g < kMaxGroups ? g : 0];
         if (p.probs) {
-          const GroupProb& pr = p.probs[g >> 1];
+          const GroupProb& pr = p.probs[prob];
           ws_base = pr.ws[g & 1]; ws_ld = pr.ws_ld; ws_tr = pr.ws_transposed;
         }
         float* ws_row = ws_base + (size_t)row * ws_ld;
