@@ -400,3 +400,58 @@ def test_spliced_weight_gradient_merged_groups(handle, lib, K, shift_a, transpos
         assert_close(got[g], want, 2.0 ** -19 * absprod + 1e-6, f"merged={merge} group {g}")
     for t in (tA, tB, tD, ws):
         t.Free()
+
+
+@pytest.mark.parametrize("N,count,K", [(160, 3, 2000), (64, 2, 912), (160, 5, 9984)])
+def test_grouped_weight_gradients_equal_the_oracle(handle, lib, N, count, K):
+    """kfp16_wgrad_group_*: `count` spliced weight-gradient problems (two row-shifted groups each, shift on the A or
+    on the B side, plain or transposed target) in ONE persistent split-K launch with a device-resident problem table;
+    N = 160 takes the merged-tile kernel (one A/B tile per k-block for both groups), N = 64 the two-tiles-per-problem one.
+    Launched twice: the targets accumulate.  (K is a multiple of 16: a partial UMMA K step relies on TMA zero-fill past
+    the matrix edge, and here the operands carry readable halo rows beyond K.)"""
+    import ctypes as C
+    from kaldi_fp16_b200._lib import WgradProb
+    s, M = 3, 512
+    rng = np.random.default_rng(N + count + K)
+    probs = (WgradProb * count)()
+    keep, want = [], []
+    for i in range(count):
+        transposed = i % 2 == 0                      # shift on the B side + transposed target, or shift on the A side
+        Af = rand_f16(rng, (K + 2 * s, M))
+        Bf = rand_f16(rng, (K + 2 * s, N), 0.05)
+        tA, tB = gpu.TensorFromFP16(Af), gpu.TensorFromFP16(Bf)
+        ws = gpu.DeviceF32(n=2 * N * M)
+        keep += [tA, tB, ws]
+        a_off, b_off = ((0, 0), (0, s)) if transposed else ((-s, 0), (0, 0))
+        q = probs[i]
+        q.A.ptr, q.A.rows, q.A.cols, q.A.ld, q.A.halo = tA.Ptr + s * M * 2, K, M, M, s
+        q.B.ptr, q.B.rows, q.B.cols, q.B.ld, q.B.halo = tB.Ptr + s * N * 2, K, N, N, s
+        q.a_row_off[0], q.a_row_off[1] = a_off
+        q.b_row_off[0], q.b_row_off[1] = b_off
+        q.ws[0], q.ws[1] = ws.Ptr, ws.Ptr + N * M * 4
+        q.ws_ld, q.ws_transposed = (M if transposed else N), int(transposed)
+        w = []
+        for g in range(2):
+            Ag = Af[s + a_off[g]: s + a_off[g] + K].astype(np.float64)
+            Bg = Bf[s + b_off[g]: s + b_off[g] + K].astype(np.float64)
+            d, ap = Ag.T @ Bg, np.abs(Ag).T @ np.abs(Bg)
+            w.append((d.T, ap.T) if transposed else (d, ap))
+        want.append((ws, transposed, w))
+    grp = lib.kfp16_wgrad_group_create(handle.ptr, M, N, K, probs, count)
+    assert grp, _lib_err()
+    for _ in range(2):
+        assert lib.kfp16_wgrad_group_launch(handle.ptr, grp) == 0, _lib_err()
+    gpu.Sync()
+    for i, (ws, transposed, w) in enumerate(want):
+        got = ws.ToHost().reshape((2, N, M) if transposed else (2, M, N))
+        for g in range(2):
+            assert_close(got[g], 2.0 * w[g][0], 2.0 * (2.0 ** -19 * w[g][1] + 1e-6), f"problem {i} group {g}")
+    lib.kfp16_wgrad_group_destroy(grp)
+    assert not lib.kfp16_wgrad_group_create(handle.ptr, 64, N, K, probs, count)      # needs CTA-pair tiles
+    for t in keep:
+        t.Free()
+
+
+def _lib_err():
+    from kaldi_fp16_b200 import _lib
+    return _lib.last_error()
