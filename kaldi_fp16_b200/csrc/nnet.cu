@@ -122,6 +122,8 @@ struct kfp16_net {
   // low-priority side stream, forked / joined with events, and fill the SMs the narrow dgrad GEMMs leave idle
   cudaStream_t side = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D prefetch of the next minibatch (kfp16_net_prefetch_input)
+  cudaStream_t copy_extra[3] = {nullptr, nullptr, nullptr};   // large inputs are copied in 4 parts on 4 streams (one DMA
+  cudaEvent_t copy_part[3] = {nullptr, nullptr, nullptr};      // engine each: a single stream does not saturate the host link)
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   cudaEvent_t ev_join = nullptr;
@@ -1239,6 +1241,7 @@ void kfp16_net_destroy(kfp16_net* n) {
       if (l.pf_packed[b]) cudaEventDestroy(l.pf_packed[b]);
     }
   if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
+  for (int k = 0; k < 3; ++k) { if (n->copy_extra[k]) cudaStreamDestroy(n->copy_extra[k]); if (n->copy_part[k]) cudaEventDestroy(n->copy_part[k]); }
   for (auto& kv : n->wg_groups) kfp16_wgrad_group_destroy(kv.second);
   for (cudaGraphExec_t g : n->seg_graph) if (g) cudaGraphExecDestroy(g);
   if (n->loss_pinned) cudaFreeHost(n->loss_pinned);
@@ -1390,8 +1393,25 @@ int kfp16_net_prefetch_input(kfp16_net* n, const char* input_name, const uint16_
   } else if (!check_cuda(cudaStreamWaitEvent(n->copy_stream, l.pf_packed[b], 0), "prefetch wait")) {
     return -1;   // the scatter that last read this staging slot must have run
   }
-  if (!check_cuda(cudaMemcpyAsync(l.pf_buf[b], host, bytes, cudaMemcpyHostToDevice, n->copy_stream), "prefetch copy") ||
-      !check_cuda(cudaEventRecord(l.pf_copied[b], n->copy_stream), "prefetch record")) return -1;
+  static const int parts_env = getenv("KFP16_H2D_SPLIT") ? atoi(getenv("KFP16_H2D_SPLIT")) : 4;
+  const int parts = bytes >= ((size_t)4 << 20) ? std::max(1, std::min(4, parts_env)) : 1;
+  const size_t chunk = ((bytes / parts) + 255) & ~(size_t)255;
+  if (!check_cuda(cudaMemcpyAsync(l.pf_buf[b], host, parts > 1 ? std::min(chunk, bytes) : bytes, cudaMemcpyHostToDevice, n->copy_stream), "prefetch copy")) return -1;
+  for (int k = 1; k < parts; ++k) {       // parts 1.. on their own streams (joined into the copy stream), part 0 above
+    if (!n->copy_extra[k - 1]) {
+      if (!check_cuda(cudaStreamCreateWithFlags(&n->copy_extra[k - 1], cudaStreamNonBlocking), "copy stream") ||
+          !check_cuda(cudaEventCreateWithFlags(&n->copy_part[k - 1], cudaEventDisableTiming), "copy event")) return -1;
+    }
+    const size_t off = chunk * k;
+    if (off >= bytes) break;
+    const size_t len = std::min(chunk, bytes - off);
+    cudaStream_t cs = n->copy_extra[k - 1];
+    if (l.pf_packed[b] && !check_cuda(cudaStreamWaitEvent(cs, l.pf_packed[b], 0), "prefetch wait")) return -1;
+    if (!check_cuda(cudaMemcpyAsync((char*)l.pf_buf[b] + off, (const char*)host + off, len, cudaMemcpyHostToDevice, cs), "prefetch copy") ||
+        !check_cuda(cudaEventRecord(n->copy_part[k - 1], cs), "prefetch part record") ||
+        !check_cuda(cudaStreamWaitEvent(n->copy_stream, n->copy_part[k - 1], 0), "prefetch part join")) return -1;
+  }
+  if (!check_cuda(cudaEventRecord(l.pf_copied[b], n->copy_stream), "prefetch record")) return -1;
   l.pf_rows = rows; l.pf_cols = cols;
   l.pf_ready = b;
   l.pf_slot = b ^ 1;
