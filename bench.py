@@ -4,11 +4,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one minibatch (64 sequences x 150 frames per GPU) through zero-grads, forward,
-0.5*||out||^2 objective (dY = Y, cmd/sgdtest/main.go:258-267), backward, gradient all-reduce
-(N > 1) and the momentum-SGD update.  `value` is whole-job frames/s with the inputs resident in
-HBM; `e2e` is the same step through the public host-buffer API (pinned host features -> H2D every
-step, loss read back every step).  One JSON line is printed by rank 0.
+Default workload: the full CNN-TDNN (BASELINE configs[2], the config the metric is quoted on);
+--workload tdnnf_stack runs BASELINE configs[1].  A "step" is one minibatch (64 sequences x 150
+frames per GPU) through zero-grads, forward, 0.5*||out||^2 objective (dY = Y,
+cmd/sgdtest/main.go:258-267), backward, gradient all-reduce (N > 1: the FP16 gradient bucket) and
+the momentum-SGD update.  `value` is whole-job frames/s with the inputs resident in HBM; `e2e` is
+the same step through the public host-buffer API (pinned host FP32 features -> H2D every step,
+FP32 -> FP16 on the device, loss read back every step).  One JSON line is printed by rank 0.
 
 --impl reference times the reference's own CPU engine (go/gotorch restated in C, oracle/
 gotorch_port.c -- there is no Go toolchain here) on a bounded sample of the same workload.
@@ -68,7 +70,7 @@ def cnn_tdnn_xconfig(pdfs=6016):
 WORKLOADS = {
     "tdnnf_stack": dict(xconfig=tdnnf_stack_xconfig, feat_dim=1536, ivec_dim=0,
                         desc="TDNN-F stack 16 x (1536 hidden, 160 bottleneck, stride 3, bypass 0.66) fwd+bwd+SGD, 64 seqs x 150 frames per GPU (BASELINE configs[1])"),
-    "cnn_tdnn": dict(xconfig=cnn_tdnn_xconfig, feat_dim=40, ivec_dim=100,
+    "cnn_tdnn": dict(xconfig=cnn_tdnn_xconfig, feat_dim=40, ivec_dim=100, dp_cut="tdnnf7",
                      desc="full CNN-TDNN (6 conv + 12 TDNN-F + prefinal + 6016-pdf output) fwd+bwd+SGD, 64 seqs x 150 frames per GPU (BASELINE configs[2])"),
 }
 
@@ -142,23 +144,49 @@ def load_port():
     lib = C.CDLL(str(so))
     lib.gt_bench_tdnnf_stack.restype = C.c_double
     lib.gt_bench_tdnnf_stack.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_double)]
+    lib.gt_bench_cnn_tdnn.restype = C.c_double
+    lib.gt_bench_cnn_tdnn.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_double)]
     return lib
 
 
-def cpu_sample(lib, frames: int) -> float:
-    """one fwd+bwd of the 16-layer TDNN-F stack on `frames` frames of one sequence; returns seconds"""
+def cpu_threads() -> int:
+    return max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+
+
+def cpu_sample(lib, workload: str, frames: int) -> float:
+    """one fwd+bwd of the workload's network on `frames` frames of one sequence; returns seconds"""
     cs = C.c_double()
+    if workload == "cnn_tdnn":
+        return lib.gt_bench_cnn_tdnn(frames, 6016, 1, cpu_threads(), C.byref(cs))
     return lib.gt_bench_tdnnf_stack(16, 1536, 160, 3, 1, frames, 1, C.byref(cs))
 
 
-def cpu_baseline(budget_s: float = 12.0):
+def cpu_sample_desc(workload: str, frames: int) -> str:
+    if workload == "cnn_tdnn":
+        return (f"full CNN-TDNN fwd+bwd on 1 sequence x {frames} frames, float64: gotorch Conv1DLayer loop nest "
+                f"(go/gotorch/cnn_tdnn.go:85-172, extended over height with the 3x3 taps of forward.go:429-455), TDNNLayer "
+                f"(layers.go:444-524) and AffineLayer (layers.go:57-110) restated in C; as in the reference only MatMul "
+                f"(the affine layers) is multi-threaded ({cpu_threads()} threads), conv / TDNN / every Backward are "
+                f"single-goroutine loops; host has {os.cpu_count()} cores")
+    return (f"TDNN-F stack (16 layers) fwd+bwd on 1 sequence x {frames} frames, float64, gotorch TDNNLayer loops "
+            f"(go/gotorch/layers.go:444-524, single goroutine in the reference; host has {os.cpu_count()} cores)")
+
+
+def cpu_frames_for(lib, workload: str, budget_s: float) -> int:
+    t_small = cpu_sample(lib, workload, 4)
+    return int(max(4, min(SEQ_LEN, 4 * budget_s / max(t_small, 1e-3))))
+
+
+def cpu_baseline(workload: str, budget_s: float = 12.0):
     lib = load_port()
-    t_small = cpu_sample(lib, 4)
-    frames = int(max(4, min(SEQ_LEN, 4 * budget_s / max(t_small, 1e-3))))
-    t = cpu_sample(lib, frames)
-    return {"value": frames / t, "unit": "frames/s", "cores": 1, "kind": "port",
-            "sample": f"TDNN-F stack (16 layers) fwd+bwd on 1 sequence x {frames} frames, float64, gotorch TDNNLayer loops "
-                      f"(single goroutine in the reference; host has {os.cpu_count()} cores), {t:.1f} s"}
+    frames = cpu_frames_for(lib, workload, budget_s)
+    t = cpu_sample(lib, workload, frames)
+    return {"value": frames / t, "unit": "frames/s", "cores": cpu_threads() if workload == "cnn_tdnn" else 1, "kind": "port",
+            "sample": cpu_sample_desc(workload, frames) + f", {t:.1f} s"}
+
+
+def metric_name(workload: str) -> str:
+    return {"cnn_tdnn": "CNN-TDNN fwd+bwd frames/sec", "tdnnf_stack": "TDNN-F stack fwd+bwd frames/sec"}[workload]
 
 
 def run_reference(args, rank):
@@ -166,24 +194,21 @@ def run_reference(args, rank):
         return
     lib = load_port()
     per_step = max(1.0, min(6.0, 150.0 / max(1, args.steps + args.warmup)))
-    t_small = cpu_sample(lib, 4)
-    frames = int(max(4, min(SEQ_LEN, 4 * per_step / max(t_small, 1e-3))))
+    frames = cpu_frames_for(lib, args.workload, per_step)
     for _ in range(args.warmup):
-        cpu_sample(lib, frames)
+        cpu_sample(lib, args.workload, frames)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_sample(lib, frames)
+        cpu_sample(lib, args.workload, frames)
     dt = time.perf_counter() - t0
     val = frames * args.steps / dt
-    sample = (f"TDNN-F stack (16 layers) fwd+bwd, 1 sequence x {frames} frames per step, float64 gotorch TDNNLayer loops; "
-              f"reference CPU engine restated in C (no Go toolchain), single goroutine as in go/gotorch/layers.go:444-524; "
-              f"host has {os.cpu_count()} cores")
+    sample = cpu_sample_desc(args.workload, frames) + " per step; reference CPU engine restated in C (no Go toolchain)"
     print(json.dumps({
-        "impl": "reference", "metric": "CNN-TDNN fwd+bwd frames/sec", "value": val, "unit": "frames/s",
+        "impl": "reference", "metric": metric_name(args.workload), "value": val, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload]["desc"], "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cpu_threads() if args.workload == "cnn_tdnn" else 1, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
@@ -192,12 +217,12 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("KFP16_WORKLOAD", "tdnnf_stack"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("KFP16_WORKLOAD", "cnn_tdnn"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--profile-steps", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -210,19 +235,17 @@ def main():
     from kaldi_fp16_b200 import _lib, cudart, gpu, nnet
     lib = _lib.load()          # raises if the CUDA library is missing: there is no fallback
     dist = torch = None
-    # Bucketed all-reduce beside the backward pass (kfp16_net_capture_segments): measured at N = 8 it gains 0.7-1.5 %
-    # (2.287 / 2.266 ms with 8 / 16 SMs left to NCCL against 2.302 ms), because the compute kernels lose those SMs for the
-    # whole step -- opt-in until the GEMMs have a dynamic tile scheduler.
-    overlap = world > 1 and os.environ.get("KFP16_DP_OVERLAP", "0") != "0"
-    nccl_sms = int(os.environ.get("KFP16_NCCL_SMS", "8"))
+    # N > 1: the FP16 gradient bucket is all-reduced (the reference keeps FP16 gradient tensors: backward_ops.go:195-225).
+    # KFP16_DP_OVERLAP=1 (default on for the CNN-TDNN): the step graph is cut once, where the backward pass leaves the
+    # TDNN-F / output layers -- from there on their gradients (97 % of the bucket) are final and reduce on a second stream
+    # while the convolutional front end back-propagates.
+    overlap = world > 1 and os.environ.get("KFP16_DP_OVERLAP", "1" if args.workload == "cnn_tdnn" else "0") != "0"
+    nccl_sms = int(os.environ.get("KFP16_NCCL_SMS", "16"))
     if world > 1:
         # NCCL's own banner / debug lines go to stderr so that stdout carries the one JSON line only
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if overlap:
-            # the bucketed all-reduce runs beside the backward pass: NCCL gets nccl_sms SMs (one CTA per channel), the
-            # compute kernels size their grids for the other 148 - nccl_sms
             os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nccl_sms))
-            os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -250,65 +273,74 @@ def main():
         feats[:, 0] = np.clip(60 + 20 * rng.standard_normal(T), -20, 105)
     else:
         feats = rng.standard_normal((T, fd)).astype(np.float32)
+    feats = np.ascontiguousarray(feats, dtype=np.float32)
+    ivecs = np.ascontiguousarray(np.clip(rng.standard_normal((N_SEQ, max(ivd, 1))), -3, 3), dtype=np.float32) if ivd else None
     feat_bits = nnet.rne_fp16_bits(feats)
-    ivec_bits = nnet.rne_fp16_bits(np.clip(rng.standard_normal((N_SEQ, max(ivd, 1))), -3, 3).astype(np.float32)) if ivd else None
+    ivec_bits = nnet.rne_fp16_bits(ivecs) if ivd else None
 
-    # inputs resident in HBM (device-timed leg) and in pinned host memory (e2e leg)
+    # inputs resident in HBM as FP16 (device-timed leg) and in pinned host memory as FP32 (e2e leg: the features are
+    # FP32 in the egs; the reference converts them on the CPU, internal/gpu/bridge.go:141 -- here on the device)
     d_feat = gpu.TensorFromBits(feat_bits)
     d_ivec = gpu.TensorFromBits(ivec_bits) if ivd else None
-    h_feat_ptr = lib.bridge_host_alloc(feat_bits.nbytes)
-    C.memmove(h_feat_ptr, feat_bits.ctypes.data, feat_bits.nbytes)
+    h_feat_ptr = lib.bridge_host_alloc(feats.nbytes)
+    C.memmove(h_feat_ptr, feats.ctypes.data, feats.nbytes)
     h_ivec_ptr = None
     if ivd:
-        h_ivec_ptr = lib.bridge_host_alloc(ivec_bits.nbytes)
-        C.memmove(h_ivec_ptr, ivec_bits.ctypes.data, ivec_bits.nbytes)
+        h_ivec_ptr = lib.bridge_host_alloc(ivecs.nbytes)
+        C.memmove(h_ivec_ptr, ivecs.ctypes.data, ivecs.nbytes)
 
     def set_inputs_device():
         assert lib.kfp16_net_set_input_device(net.ptr, b"input", d_feat.Ptr, T, fd) == 0, _lib.last_error()
         if ivd:
             assert lib.kfp16_net_set_input_device(net.ptr, b"ivector", d_ivec.Ptr, N_SEQ, ivd) == 0, _lib.last_error()
 
-    def set_inputs_host():
-        assert lib.kfp16_net_set_input(net.ptr, b"input", h_feat_ptr, T, fd) == 0, _lib.last_error()
-        if ivd:
-            assert lib.kfp16_net_set_input(net.ptr, b"ivector", h_ivec_ptr, N_SEQ, ivd) == 0, _lib.last_error()
-
     set_inputs_device()
+    # graphs: N = 1: [step] [SGD on the FP32 bucket, gradients rounded to FP16 as the reference's are]
+    #         N > 1: [step + FP16 gradient export] all-reduce(g16) [SGD on the reduced FP16 bucket]
     n_seg, seg_ranges = 0, []
-    if overlap:
-        assert lib.kfp16_ctx_set_max_ctas(handle.ptr, 148 - nccl_sms) == 0
-        n_seg = net.CaptureSegments(int(os.environ.get("KFP16_DP_SEGMENTS", "6")))
-        seg_ranges = [net.SegmentGrads(k) for k in range(n_seg)]
-    else:
-        net.Capture(1)
-    net.Capture(2)
     reducer = None
     if world > 1:
         from kaldi_fp16_b200 import dp
-        reducer = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(), device=f"cuda:{local}"))
+        if overlap:
+            n_seg = net.CaptureSegments(2, cut_layers=wl.get("dp_cut"), export_f16=True,
+                                        tail_max_ctas=(148 - nccl_sms) if nccl_sms > 0 else 0)
+            seg_ranges = [net.SegmentGrads(k) for k in range(n_seg)]
+        else:
+            net.Capture(1 | 4)
+        net.Capture(8)
+        reducer = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(f16=True), device=f"cuda:{local}"))
+        comm_stream = torch.cuda.Stream(device=local, priority=-1)
+    else:
+        net.Capture(1)
+        net.Capture(2)
 
     def step_compute_and_reduce():
-        """graph 1 (or its segments) + the sum all-reduce of the gradient bucket: N-GPU step == 1-GPU step on the
-        concatenated batch"""
-        if not overlap:
+        """graph(s) of the step + the sum all-reduce of the gradient bucket: N-GPU step == 1-GPU step on the
+        concatenated batch (up to FP16 rounding of the per-rank gradients)"""
+        if world == 1:
             net.Launch(1)
-            if reducer is not None:
-                with torch.cuda.stream(tstream):
-                    reducer.all_reduce()
             return
-        works = []
+        if not overlap:
+            net.Launch(1 | 4)
+            with torch.cuda.stream(tstream):
+                reducer.all_reduce()
+            return
         with torch.cuda.stream(tstream):
             for k in range(n_seg):
-                net.LaunchSegment(k)                       # backward of one layer group ...
-                works.append(reducer.all_reduce_range(*seg_ranges[k], async_op=True))   # ... its gradients reduce beside the next
-            for w in works:
-                if w is not None:
-                    w.wait()                               # device-side: the SGD graph waits for the reduced bucket
+                net.LaunchSegment(k)                       # backward of one layer group (+ its FP16 export) ...
+                ev = torch.cuda.Event()
+                ev.record(tstream)
+                comm_stream.wait_event(ev)
+                with torch.cuda.stream(comm_stream):       # ... its gradients reduce beside the next segment
+                    reducer.all_reduce_range(*seg_ranges[k], async_op=False)
+            ev = torch.cuda.Event()
+            ev.record(comm_stream)
+            tstream.wait_event(ev)                         # the SGD graph waits for the reduced bucket
 
     def step_device():
         set_inputs_device()
         step_compute_and_reduce()
-        net.Launch(2)
+        net.Launch(2 if world == 1 else 8)
 
     def sync_all():
         cudart.synchronize()
@@ -345,52 +377,70 @@ def main():
     frames_per_step = T * world
     value = frames_per_step * args.steps / (ms * 1e-3)
 
-    # ---- end-to-end leg: every step's inputs come from pinned host memory (H2D inside the timed region) and the
-    # step's loss is read back to the host.  The copy of step i+1's inputs is issued on the library's copy stream
-    # while step i computes (kfp16_net_prefetch_input / commit_input), as a training loop feeding egs would.
+    # ---- end-to-end leg: every step's inputs come from pinned host memory as FP32 (H2D inside the timed region, the
+    # FP32 -> FP16 conversion on the device) and the step's loss is read back to the host.  The copy of step i+1's
+    # inputs is issued on the library's copy stream while step i computes (kfp16_net_prefetch_input_f32 / commit_input),
+    # as a training loop feeding egs would.  Timed by CUDA events AND by the host clock; the larger one counts.
     e2e_steps = max(3, min(args.steps, 100))
 
     def prefetch_host():
-        assert lib.kfp16_net_prefetch_input(net.ptr, b"input", h_feat_ptr, T, fd) == 0, _lib.last_error()
+        assert lib.kfp16_net_prefetch_input_f32(net.ptr, b"input", h_feat_ptr, T, fd) == 0, _lib.last_error()
         if ivd:
-            assert lib.kfp16_net_prefetch_input(net.ptr, b"ivector", h_ivec_ptr, N_SEQ, ivd) == 0, _lib.last_error()
+            assert lib.kfp16_net_prefetch_input_f32(net.ptr, b"ivector", h_ivec_ptr, N_SEQ, ivd) == 0, _lib.last_error()
 
     def commit_host():
         assert lib.kfp16_net_commit_input(net.ptr, b"input") == 0, _lib.last_error()
         if ivd:
             assert lib.kfp16_net_commit_input(net.ptr, b"ivector") == 0, _lib.last_error()
 
+    def e2e_loop(nsteps):
+        last = 0.0
+        prefetch_host()
+        for i in range(nsteps):
+            commit_host()
+            if i + 1 < nsteps:
+                prefetch_host()
+            step_compute_and_reduce()
+            net.Launch(2 if world == 1 else 8)
+            # every step's loss is read back to the host; the read of step i is queued behind step i and collected
+            # after step i+1 has been queued, so the stream never drains between minibatches
+            net.ReadLossAsync(i & 1)
+            if i > 0:
+                last = net.WaitLoss((i - 1) & 1)
+        return net.WaitLoss((nsteps - 1) & 1)
+
     net.ReadLoss()
+    e2e_loop(3)                 # warm-up of the host-fed path (staging buffers, copy streams)
     sync_all()
     t0 = time.perf_counter()
     e0.record(stream_ptr)
-    last_loss = 0.0
-    prefetch_host()
-    for i in range(e2e_steps):
-        commit_host()
-        if i + 1 < e2e_steps:
-            prefetch_host()
-        step_compute_and_reduce()
-        net.Launch(2)
-        # every step's loss is read back to the host; the read of step i is queued behind step i and collected after
-        # step i+1 has been queued, so the stream never drains between minibatches
-        net.ReadLossAsync(i & 1)
-        if i > 0:
-            last_loss = net.WaitLoss((i - 1) & 1)
-    last_loss = net.WaitLoss((e2e_steps - 1) & 1)
+    last_loss = e2e_loop(e2e_steps)
     e1.record(stream_ptr)
     e1.synchronize()
+    cudart.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
     sync_all()
-    e2e_ms = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    e2e_event_ms = e0.elapsed_ms(e1)
+    e2e_ms = max(e2e_event_ms, wall_ms)
     if world > 1:
         t_ms = torch.tensor([e2e_ms], device=f"cuda:{local}")
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         e2e_ms = float(t_ms.item())
     e2e_value = frames_per_step * e2e_steps / (e2e_ms * 1e-3)
-    h2d = feat_bits.nbytes + (ivec_bits.nbytes if ivd else 0)
+    h2d = feats.nbytes + (ivecs.nbytes if ivd else 0)
     clocks = sampler.stop() if sampler else None
 
-    # ---- roofline leg: CUDA-event pair around every GEMM launch, eager replay of the same step
+    # ---- data-parallel invariant: every rank holds the same master weights after the timed loops
+    ranks_identical = None
+    if world > 1:
+        w = torch.as_tensor(net.params_as_cuda_array(), device=f"cuda:{local}")
+        wmax, wmin = w.clone(), w.clone()
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(wmin, op=dist.ReduceOp.MIN)
+        ranks_identical = bool(torch.equal(wmax, wmin))
+        assert ranks_identical, "master weights differ between ranks after the timed loop"
+
+    # ---- side table: CUDA-event pair around every GEMM launch in an eager replay of the same step (per-kernel rates)
     lib.kfp16_ctx_set_profile(handle.ptr, 1)
     ev0, ev1 = cudart.Event(), cudart.Event()
     ev0.record(stream_ptr)
@@ -399,56 +449,62 @@ def main():
         net.ZeroGrads()
         assert lib.kfp16_net_forward(net.ptr) == 0
         net.Backward(None)
-        if reducer is not None:
-            with torch.cuda.stream(tstream):
-                reducer.all_reduce()
         net.SGDStep(grad_scale)
     ev1.record(stream_ptr)
     ev1.synchronize()
-    profile_ms = ev0.elapsed_ms(ev1) / max(args.profile_steps, 1)     # eager, event-bracketed replay of the same step
+    profile_ms = ev0.elapsed_ms(ev1) / max(args.profile_steps, 1)
     n_l, g_ms, g_fl = C.c_int(), C.c_double(), C.c_double()
     lib.kfp16_ctx_profile_read(handle.ptr, C.byref(n_l), C.byref(g_ms), C.byref(g_fl))
     lib.kfp16_ctx_set_profile(handle.ptr, 0)
     burst, sustained, hbm, src = peaks()
-    traffic = None
-    tp = ROOT / "profiles" / "r01_ncu_traffic.json"
-    if tp.exists() and args.workload == "tdnnf_stack":
-        traffic = json.loads(tp.read_text()).get("dram_bytes_per_gemm_launch")
-    achieved = g_fl.value / max(g_ms.value, 1e-9) / 1e9   # TFLOP/s
+    traffic = traffic_src = None
+    tp = ROOT / "profiles" / f"r02_ncu_traffic_{args.workload}.json"
+    if tp.exists():
+        tj = json.loads(tp.read_text())
+        traffic, traffic_src = tj.get("dram_bytes_per_step"), f"profiles/{tp.name}: {tj.get('how', '')}"
+    # ALGORITHMIC work of the step as executed (real rows only): forward GEMMs of every layer (the xent
+    # branch included) + weight- and input-gradient GEMMs of the layers on the gradient path
     flops_fwd = lib.kfp16_net_flops_forward(net.ptr)
-    step_flops_real = g_fl.value / max(args.profile_steps, 1)
+    flops_bwd = lib.kfp16_net_flops_backward(net.ptr)
+    step_flops = flops_fwd + flops_bwd
+    ms_step = ms / args.steps
+    achieved = step_flops / ms_step / 1e9        # TFLOP/s over the WHOLE timed step (GEMMs, epilogues, elementwise, SGD)
+    gemm_ms = g_ms.value / max(args.profile_steps, 1)
 
     if rank == 0:
         out = {
-            "impl": "ours", "metric": "CNN-TDNN fwd+bwd frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "impl": "ours", "metric": metric_name(args.workload), "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": wl["desc"], "frames_per_gpu_step": T, "global_frames_per_step": frames_per_step,
-                       "parallelism": f"dp{world}" + (f", gradient all-reduce in {n_seg} buckets overlapped with the backward pass ({nccl_sms} SMs for NCCL)" if overlap else ""), "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush",
+                       "parallelism": f"dp{world}" + (f", FP16 gradient all-reduce in {n_seg} buckets, the first overlapped with the conv front end's backward pass ({nccl_sms} SMs left to NCCL there)" if overlap else (", FP16 gradient all-reduce" if world > 1 else "")),
+                       "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush",
                        "loss": "0.5*||out||^2, dY=Y", "optimizer": f"momentum SGD on FP32 masters, lr {LR}, m 0.9, grads scaled by 1/(frames*out_dim)",
                        "launch": "CUDA graphs (step, SGD) with programmatic dependent launch between kernels" + ("" if os.environ.get("KFP16_PDL", "1") != "0" else " OFF")},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps, "first_loss": first_loss, "last_loss": last_loss},
+                    "steps": e2e_steps, "event_ms": e2e_event_ms, "wall_ms": wall_ms, "input": "FP32 features in pinned host memory, converted to FP16 on the device",
+                    "first_loss": first_loss, "last_loss": last_loss},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "kfp16::gemm_f16_sm100 (all tile variants)",
-                         "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src}); burst {burst}",
-                         "frac_of_burst": achieved / burst, "traffic": traffic,
-                         "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, dram read+write bytes averaged over the step's GEMM launches)" if traffic else None,
-                         "launches_per_step": n_l.value // max(args.profile_steps, 1),
-                         "gemm_ms_per_step": g_ms.value / max(args.profile_steps, 1),
-                         # share inside the eager replay the GEMM times were taken in (the timed graph step overlaps
-                         # consecutive launches through programmatic dependent launch and is shorter than their sum)
-                         "gemm_share_of_step": (g_ms.value / max(args.profile_steps, 1)) / profile_ms,
-                         "eager_replay_ms_per_step": profile_ms,
-                         "flops_per_step_launched": step_flops_real, "flops_forward_real_rows": flops_fwd},
-            "step_tflops": step_flops_real / (ms / args.steps) / 1e9,
-            "step_frac_of_sustained_peak": step_flops_real / (ms / args.steps) / 1e9 / sustained,
+            "roofline": {"bound": "tensor", "kernel": "kfp16::gemm_f16_sm100 (all tile variants; whole step timed)",
+                         "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+                         "how": "algorithmic 2*M*N*K of the step's GEMMs on real rows (forward incl. xent branch + executed backward) / ms_per_step of the timed region",
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({src}); sustained {sustained}",
+                         "frac_of_sustained": achieved / sustained, "frac_of_nominal_2250": achieved / 2250.0,
+                         "flops_per_step": step_flops, "flops_forward": flops_fwd, "flops_backward": flops_bwd,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         # side table from an eager, event-bracketed replay (each GEMM launch timed alone; their sum can
+                         # exceed the graph step, which overlaps consecutive launches through programmatic dependent launch)
+                         "gemm_launches_per_step": n_l.value // max(args.profile_steps, 1),
+                         "gemm_ms_per_step_eager": gemm_ms,
+                         "gemm_tflops_eager": g_fl.value / max(g_ms.value, 1e-9) / 1e9,
+                         "eager_replay_ms_per_step": profile_ms},
         }
+        if ranks_identical is not None:
+            out["ranks_identical_weights"] = ranks_identical
         if world == 1 and not args.no_cpu_baseline:
             try:
-                out["cpu_baseline"] = cpu_baseline()
+                out["cpu_baseline"] = cpu_baseline(args.workload)
             except Exception as e:  # noqa: BLE001 - the GPU number must still be reported
                 out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(out), flush=True)

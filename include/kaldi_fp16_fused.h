@@ -38,6 +38,9 @@ int kfp16_ctx_profile_read(kfp16_ctx *ctx, int *launches, double *total_ms, doub
 void kfp16_set_default_stream(void *cuda_stream);
 /* number of kernels this library has launched in the calling process (bench "gpu_launches") */
 unsigned long long kfp16_launch_count(void);
+/* GEMM launches so far whose kernel was compiled for epilogue kind `kind` (0 generic run-time flags, 1 plain, 2 bias+relu+bn+mask,
+ * 3 same + residual, 4 residual, 5 bn+relu-backward mask, 6 bn, 7 bias, 8 split-K): lets tests assert WHICH epilogue body ran */
+unsigned long long kfp16_gemm_kind_launches(int kind);
 const char *kfp16_last_error(void);
 
 enum {
@@ -162,10 +165,22 @@ int kfp16_sgd_update_flat(kfp16_ctx *ctx, float *w32, void *w16, const void *gra
                           int round_grad, float grad_scale, float *velocity, float lr,
                           float momentum, size_t n);
 
+/* same update with {lr, momentum, grad_scale} read from a 3-float DEVICE block when the kernel runs: a captured CUDA
+ * graph of the update follows SGDOptimizer.SetLR (internal/gpu/optimize.go:123) without re-capture */
+int kfp16_sgd_update_flat_hp(kfp16_ctx *ctx, float *w32, void *w16, const void *grad, int grad_is_f32,
+                             int round_grad, float *velocity, const float *hyper_dev, size_t n);
+/* dst_f16[i] = half(src[i] * *scale_dev)  (scale_dev NULL = 1): FP32 gradient bucket -> the FP16 gradient tensors of
+ * the reference (AffineBackwardWeights output, backward_ops.go:195-225) */
+int kfp16_scale_f32_to_f16(kfp16_ctx *ctx, const float *src, void *dst_f16, size_t n, const float *scale_dev);
+
 /* ---- padded minibatch layout: dense [n_seq*seq_len x cols] <-> padded [n_seq*(seq_len+2*halo) x ld] */
 /* mode 0: halo rows = 0 (conv zero padding, forward.go:449)   1: replicate the edge row (splice clamp) */
 int kfp16_pack_rows(kfp16_ctx *ctx, const void *src, void *dst, int ld, int n_seq, int seq_len, int halo,
                     int cols, int mode);
+/* same from dense FP32 rows, converting FP32 -> FP16 round-to-nearest-even on the device (what
+ * fp16.ConvertFloat32ToFloat16 does on the CPU for the features: internal/gpu/bridge.go:141, internal/fp16/fp16.go:13-70) */
+int kfp16_pack_rows_f32(kfp16_ctx *ctx, const float *src, void *dst, int ld, int n_seq, int seq_len, int halo,
+                        int cols, int mode);
 int kfp16_unpack_rows(kfp16_ctx *ctx, const void *src, int ld, int col0, void *dst, int n_seq, int seq_len,
                       int halo, int cols);
 /* dst[r, col0 + c] = src[r / blk, c]: per-sequence vector (ivector) appended to every frame of its block */

@@ -51,6 +51,9 @@ int kfp16_net_layer_dim(const kfp16_net *net, int i); /* output dim */
 int kfp16_net_padded_rows(const kfp16_net *net);      /* n_seq*(seq_len+2*halo) */
 int kfp16_net_halo(const kfp16_net *net);
 double kfp16_net_flops_forward(const kfp16_net *net); /* 2*M*N*K over the GEMMs, real rows only */
+/* same for the backward pass as executed: weight-gradient GEMMs of every layer on the gradient path plus the
+ * input-gradient GEMMs that feed a layer with parameters (the xent branch gets no gradient, network_backward.go:104-107) */
+double kfp16_net_flops_backward(const kfp16_net *net);
 
 /* ---- parameters: flat buckets.  name = "<layer>.<param>" as SGDOptimizer.RegisterParam keys
  * (optimize.go:52): W, LinearW, AffineW, AffineBias, BigW, BigBias, SmallW, Bias */
@@ -83,6 +86,11 @@ int kfp16_net_set_input_device(kfp16_net *net, const char *input_name, const voi
  * (the reference's TransferBatchPinned is a synchronous cudaMemcpy: internal/gpu/bridge.go:273-366, bridge.cu:257-267) */
 int kfp16_net_prefetch_input(kfp16_net *net, const char *input_name, const uint16_t *host_pinned_f16, int rows, int cols);
 int kfp16_net_commit_input(kfp16_net *net, const char *input_name);
+/* FP32 forms: the features arrive as FP32 (as the egs hold them) and are converted FP32 -> FP16 round-to-nearest-even
+ * ON THE DEVICE while they are scattered into the padded layout -- the conversion internal/gpu/bridge.go:141 does on
+ * the CPU through fp16.ConvertFloat32ToFloat16 (internal/fp16/fp16.go:13-70).  commit_input handles either kind. */
+int kfp16_net_set_input_f32(kfp16_net *net, const char *input_name, const float *host_f32, int rows, int cols);
+int kfp16_net_prefetch_input_f32(kfp16_net *net, const char *input_name, const float *host_pinned_f32, int rows, int cols);
 int kfp16_net_forward(kfp16_net *net);
 /* dense real rows of a layer's output -> host fp16 [n_seq*seq_len x dim] */
 int kfp16_net_get_output(kfp16_net *net, const char *layer, uint16_t *host_f16, int rows, int cols);
@@ -102,7 +110,17 @@ int kfp16_net_get_grad(kfp16_net *net, const char *layer, uint16_t *host_f16, in
 /* v = m*v + g*grad_scale; w32 -= lr*v; w16 = half(w32) over the whole bucket (one launch);
  * round_grad = 1 rounds g to fp16 first, as the reference's FP16 gradient tensors do */
 int kfp16_net_sgd_step(kfp16_net *net, float grad_scale, int round_grad);
+/* SGDOptimizer.SetLR (internal/gpu/optimize.go:123).  lr / momentum / grad_scale live in a small device block the
+ * update kernel reads when it runs, so this also takes effect for already captured graphs (stream-ordered). */
 int kfp16_net_set_lr(kfp16_net *net, float lr);
+int kfp16_net_set_momentum(kfp16_net *net, float momentum);
+float kfp16_net_get_lr(const kfp16_net *net);
+/* FP16 gradient bucket: g16 = half(g32 * grad_scale), the FP16 gradient tensors of the reference
+ * (backward_ops.go:195-225) as one flat buffer.  A data-parallel loop all-reduces THIS buffer (half the bytes of the
+ * FP32 bucket) and applies kfp16_net_sgd_step_f16 (ops_sgd_update arithmetic on FP16 gradients, scale 1). */
+int kfp16_net_grads_to_f16(kfp16_net *net);
+void *kfp16_net_grads_f16(kfp16_net *net);
+int kfp16_net_sgd_step_f16(kfp16_net *net);
 /* accumulated loss since the last call (device->host sync) */
 int kfp16_net_read_loss(kfp16_net *net, float *loss);
 /* pipelined form: queue the download (+ reset) of the loss accumulated so far into pinned slot 0/1 behind the work
@@ -110,8 +128,12 @@ int kfp16_net_read_loss(kfp16_net *net, float *loss);
 int kfp16_net_read_loss_async(kfp16_net *net, int slot);
 int kfp16_net_wait_loss(kfp16_net *net, int slot, float *loss);
 
-/* ---- CUDA graph of the step: phases bitmask 1 = zero_grads+forward+loss+backward, 2 = SGD.
- * Capture once (buffers are fixed), then launch per minibatch after kfp16_net_set_input*. */
+/* ---- CUDA graph of the step: phases bitmask 1 = zero_grads+forward+loss+backward, 2 = SGD (FP32 bucket),
+ * 4 = kfp16_net_grads_to_f16, 8 = kfp16_net_sgd_step_f16; any combination is one graph.
+ * Capture once (buffers are fixed), then launch per minibatch after kfp16_net_set_input*.
+ * Capturing runs the phases once eagerly first (kernel attributes, grouped weight-gradient tables); weights,
+ * velocities, both gradient buckets and the loss accumulator are saved before and restored after that pass, so a
+ * capture does NOT take an optimiser step or change the training state (activations are recomputed scratch). */
 int kfp16_net_capture(kfp16_net *net, int phases);
 int kfp16_net_launch(kfp16_net *net, int phases);
 /* The step graph (phases = 1) cut into up to nseg graphs along the backward pass: segment 0 = zero grads + forward +
@@ -119,6 +141,12 @@ int kfp16_net_launch(kfp16_net *net, int phases);
  * bucket elements [first_elem, first_elem + count) of kfp16_net_segment_grads(k) are final, so a data-parallel loop
  * all-reduces them while segment k+1 computes.  Returns the number of segments captured, -1 on error. */
 int kfp16_net_capture_segments(kfp16_net *net, int nseg);
+/* extended form: cut_layers = NULL (equal parameter shares) or a comma-separated list of layer names, top of the network
+ * first -- segment k back-propagates down to and including the k-th named layer, one more segment takes the rest;
+ * export_f16 = 1: every segment ends by exporting its gradient range to the FP16 bucket (kfp16_net_grads_f16);
+ * tail_max_ctas > 0: segments 1.. size their persistent grids for that many CTAs (SMs left to the collective that
+ * reduces the previous segment's gradients beside them). */
+int kfp16_net_capture_segments_ex(kfp16_net *net, int nseg, const char *cut_layers, int export_f16, int tail_max_ctas);
 int kfp16_net_launch_segment(kfp16_net *net, int seg);
 int kfp16_net_segment_grads(const kfp16_net *net, int seg, size_t *first_elem, size_t *count);
 /* kernels launched by one forward+loss+backward(+sgd) pass of this network */

@@ -91,6 +91,7 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_ctx_profile_read": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "kfp16_set_default_stream": (None, [c_void_p]),
     "kfp16_launch_count": (c_u64, []),
+    "kfp16_gemm_kind_launches": (c_u64, [c_int]),
     "kfp16_last_error": (C.c_char_p, []),
     "kfp16_gemm_ex": (c_int, [c_void_p, C.POINTER(GemmDesc)]),
     "kfp16_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p]),
@@ -103,6 +104,9 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_fold_edges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "kfp16_sgd_update_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_float, c_float, c_size_t]),
     "kfp16_pack_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "kfp16_pack_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "kfp16_sgd_update_flat_hp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t]),
+    "kfp16_scale_f32_to_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kfp16_unpack_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int]),
     "kfp16_bcast_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int]),
     "kfp16_seq_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int]),
@@ -124,6 +128,7 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_padded_rows": (c_int, [c_void_p]),
     "kfp16_net_halo": (c_int, [c_void_p]),
     "kfp16_net_flops_forward": (C.c_double, [c_void_p]),
+    "kfp16_net_flops_backward": (C.c_double, [c_void_p]),
     "kfp16_net_num_params": (c_int, [c_void_p]),
     "kfp16_net_param_name": (C.c_char_p, [c_void_p, c_int]),
     "kfp16_net_param_shape": (c_int, [c_void_p, c_int, C.POINTER(c_int), C.POINTER(c_int)]),
@@ -141,6 +146,8 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_set_input_device": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
     "kfp16_net_prefetch_input": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
     "kfp16_net_commit_input": (c_int, [c_void_p, C.c_char_p]),
+    "kfp16_net_set_input_f32": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
+    "kfp16_net_prefetch_input_f32": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
     "kfp16_net_forward": (c_int, [c_void_p]),
     "kfp16_net_get_output": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
     "kfp16_net_get_mask": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
@@ -151,11 +158,17 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_get_grad": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int]),
     "kfp16_net_sgd_step": (c_int, [c_void_p, c_float, c_int]),
     "kfp16_net_set_lr": (c_int, [c_void_p, c_float]),
+    "kfp16_net_set_momentum": (c_int, [c_void_p, c_float]),
+    "kfp16_net_get_lr": (c_float, [c_void_p]),
+    "kfp16_net_grads_to_f16": (c_int, [c_void_p]),
+    "kfp16_net_grads_f16": (c_void_p, [c_void_p]),
+    "kfp16_net_sgd_step_f16": (c_int, [c_void_p]),
     "kfp16_net_read_loss": (c_int, [c_void_p, C.POINTER(c_float)]),
     "kfp16_wgrad_group_create": (c_void_p, [c_void_p, c_int, c_int, c_int, C.POINTER(WgradProb), c_int]),
     "kfp16_wgrad_group_launch": (c_int, [c_void_p, c_void_p]),
     "kfp16_wgrad_group_destroy": (None, [c_void_p]),
     "kfp16_net_capture_segments": (c_int, [c_void_p, c_int]),
+    "kfp16_net_capture_segments_ex": (c_int, [c_void_p, c_int, C.c_char_p, c_int, c_int]),
     "kfp16_net_launch_segment": (c_int, [c_void_p, c_int]),
     "kfp16_net_segment_grads": (c_int, [c_void_p, c_int, C.POINTER(c_size_t), C.POINTER(c_size_t)]),
     "kfp16_net_read_loss_async": (c_int, [c_void_p, c_int]),

@@ -417,6 +417,26 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
 }
 
+// dst = half(src * *scale_dev): the flat FP32 gradient bucket -> the FP16 gradient tensors the reference keeps
+// (16-byte loads, 8-byte stores; 6 B per element against the measured HBM copy rate)
+__global__ void __launch_bounds__(256)
+scale_f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n4, size_t n, const float* __restrict__ scale_dev) {
+  griddep_launch();
+  griddep_wait();
+  const float sc = scale_dev ? *scale_dev : 1.0f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = tid; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const __half2 lo = __floats2half2_rn(v.x * sc, v.y * sc), hi = __floats2half2_rn(v.z * sc, v.w * sc);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += stride) dst[i] = __float2half_rn(src[i] * sc);
+}
+
 // ---- SGD with momentum on FP32 master weights (backward_wrappers.cu:129-142):
 //   g = float(grad); v = m*v + g; w32 -= lr*v; w16 = half(w32)
 // One launch covers a whole flat parameter bucket (the reference launches once per tensor).
@@ -429,9 +449,11 @@ __device__ __forceinline__ void sgd_one(float& w, float& v, float g, int round_g
 }
 template <bool GRAD_F32>
 __global__ void sgd_kernel(float* __restrict__ w32, __half* __restrict__ w16, const void* __restrict__ grad,
-                           int round_grad, float grad_scale, float* __restrict__ vel, float lr, float mom, size_t n) {
+                           int round_grad, float grad_scale, float* __restrict__ vel, float lr, float mom, size_t n,
+                           const float* __restrict__ hp) {
   griddep_launch();
   griddep_wait();
+  if (hp) { lr = hp[0]; mom = hp[1]; grad_scale = hp[2]; }   // hyper-parameters live in device memory (graph replays see updates)
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float g = GRAD_F32 ? reinterpret_cast<const float*>(grad)[i] : __half2float(reinterpret_cast<const __half*>(grad)[i]);
@@ -446,9 +468,11 @@ __global__ void sgd_kernel(float* __restrict__ w32, __half* __restrict__ w16, co
 template <bool GRAD_F32>
 __global__ void __launch_bounds__(256)
 sgd_kernel_v4(float* __restrict__ w32, __half* __restrict__ w16, const void* __restrict__ grad,
-              int round_grad, float grad_scale, float* __restrict__ vel, float lr, float mom, size_t n4) {
+              int round_grad, float grad_scale, float* __restrict__ vel, float lr, float mom, size_t n4,
+              const float* __restrict__ hp) {
   griddep_launch();
   griddep_wait();
+  if (hp) { lr = hp[0]; mom = hp[1]; grad_scale = hp[2]; }
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
     float4 w[2], v[2], g[2];
@@ -663,6 +687,25 @@ __global__ void pack_rows_kernel(const __half* __restrict__ src, __half* __restr
     } else {
       dst[r * ld + c] = (real || mode == 1) ? src[srow * cols + c] : __float2half(0.f);
     }
+  }
+}
+// same from FP32 rows: the RNE FP32 -> FP16 conversion of the features (internal/gpu/bridge.go:141, internal/fp16/fp16.go:13-70:
+// round-to-nearest-even, overflow to Inf) done on the device while scattering into the padded layout
+__global__ void pack_rows_f32_kernel(const float* __restrict__ src, __half* __restrict__ dst, int ld, int n_seq, int L,
+                                     int halo, int cols, int mode) {
+  griddep_launch();
+  griddep_wait();
+  const int blk = L + 2 * halo;
+  const size_t total = (size_t)n_seq * blk * cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / cols;
+    const int c = (int)(i % cols);
+    const int s = (int)(r / blk);
+    const int t = (int)(r % blk) - halo;
+    const bool real = t >= 0 && t < L;
+    const size_t srow = (size_t)s * L + (real ? t : (t < 0 ? 0 : L - 1));
+    dst[r * ld + c] = (real || mode == 1) ? __float2half_rn(src[srow * cols + c]) : __float2half(0.f);
   }
 }
 // padded [.. x ld] (cols from col0) -> dense [n_seq*L x cols]
@@ -1012,7 +1055,7 @@ int ops_sgd_update(float* w_fp32, void* w_fp16, const void* grad_fp16, float* ve
                    int count) {
   if (count <= 0) return 0;
   if (!w_fp32 || !w_fp16 || !grad_fp16 || !velocity) { set_error("sgd_update: null pointer"); return -1; }
-  sgd_kernel<false><<<grid_for((size_t)count), kThreads, 0, default_stream()>>>(w_fp32, (__half*)w_fp16, grad_fp16, 0, 1.0f, velocity, lr, momentum, (size_t)count);
+  sgd_kernel<false><<<grid_for((size_t)count), kThreads, 0, default_stream()>>>(w_fp32, (__half*)w_fp16, grad_fp16, 0, 1.0f, velocity, lr, momentum, (size_t)count, nullptr);
   count_launch();
   return check_launch("sgd_update") ? 0 : -1;
 }
@@ -1071,6 +1114,14 @@ int kfp16_f32_to_f16(kfp16_ctx* ctx, const float* src, void* dst, size_t n) {
   count_launch();
   return check_launch("kfp16_f32_to_f16") ? 0 : -1;
 }
+int kfp16_scale_f32_to_f16(kfp16_ctx* ctx, const float* src, void* dst, size_t n, const float* scale_dev) {
+  if (n == 0) return 0;
+  if (!src || !dst) { set_error("kfp16_scale_f32_to_f16: null pointer"); return -1; }
+  const size_t n4 = (al16(src) && ((uintptr_t)dst % 8) == 0) ? n / 4 : 0;
+  launch_pdl(scale_f32_to_f16_kernel, grid_for(n4 ? n4 : n), kThreads, 0, ctx_stream(ctx), src, (__half*)dst, n4, n, scale_dev);
+  count_launch();
+  return check_launch("kfp16_scale_f32_to_f16") ? 0 : -1;
+}
 int kfp16_pad_edges(kfp16_ctx* ctx, void* X, int ld, int n_seq, int seq_len, int cols, int halo) {
   if (n_seq <= 0 || seq_len <= 0 || halo <= 0 || cols <= 0) return 0;
   if (!X || (cols % 8) || (ld % 8) || !al16(X)) { set_error("kfp16_pad_edges: needs a 16B-aligned buffer and cols/ld %% 8 == 0"); return -1; }
@@ -1085,27 +1136,38 @@ int kfp16_fold_edges(kfp16_ctx* ctx, void* G, int ld, int n_seq, int seq_len, in
   count_launch();
   return check_launch("kfp16_fold_edges") ? 0 : -1;
 }
-int kfp16_sgd_update_flat(kfp16_ctx* ctx, float* w32, void* w16, const void* grad, int grad_is_f32, int round_grad,
-                          float grad_scale, float* velocity, float lr, float momentum, size_t n) {
+static int sgd_flat(kfp16_ctx* ctx, float* w32, void* w16, const void* grad, int grad_is_f32, int round_grad,
+                    float grad_scale, float* velocity, float lr, float momentum, size_t n, const float* hp, const char* who) {
   if (n == 0) return 0;
-  if (!w32 || !w16 || !grad || !velocity) { set_error("kfp16_sgd_update_flat: null pointer"); return -1; }
+  if (!w32 || !w16 || !grad || !velocity) { set_error("%s: null pointer", who); return -1; }
   cudaStream_t s = ctx_stream(ctx);
   const bool aligned = al16(w32) && al16(velocity) && ((uintptr_t)w16 % 8) == 0 && ((uintptr_t)grad % (grad_is_f32 ? 16 : 8)) == 0;
   const size_t n4 = aligned ? n / 4 : 0;
   if (n4 > 0) {
     const int grid = grid_for((n4 + 1) / 2);
-    if (grad_is_f32) sgd_kernel_v4<true><<<grid, kThreads, 0, s>>>(w32, (__half*)w16, grad, round_grad, grad_scale, velocity, lr, momentum, n4);
-    else sgd_kernel_v4<false><<<grid, kThreads, 0, s>>>(w32, (__half*)w16, grad, 0, grad_scale, velocity, lr, momentum, n4);
+    if (grad_is_f32) sgd_kernel_v4<true><<<grid, kThreads, 0, s>>>(w32, (__half*)w16, grad, round_grad, grad_scale, velocity, lr, momentum, n4, hp);
+    else sgd_kernel_v4<false><<<grid, kThreads, 0, s>>>(w32, (__half*)w16, grad, 0, grad_scale, velocity, lr, momentum, n4, hp);
     count_launch();
   }
   const size_t done = n4 * 4, rest = n - done;
   if (rest > 0) {
     const char* gp = (const char*)grad + done * (grad_is_f32 ? 4 : 2);
-    if (grad_is_f32) sgd_kernel<true><<<grid_for(rest), kThreads, 0, s>>>(w32 + done, (__half*)w16 + done, gp, round_grad, grad_scale, velocity + done, lr, momentum, rest);
-    else sgd_kernel<false><<<grid_for(rest), kThreads, 0, s>>>(w32 + done, (__half*)w16 + done, gp, 0, grad_scale, velocity + done, lr, momentum, rest);
+    if (grad_is_f32) sgd_kernel<true><<<grid_for(rest), kThreads, 0, s>>>(w32 + done, (__half*)w16 + done, gp, round_grad, grad_scale, velocity + done, lr, momentum, rest, hp);
+    else sgd_kernel<false><<<grid_for(rest), kThreads, 0, s>>>(w32 + done, (__half*)w16 + done, gp, 0, grad_scale, velocity + done, lr, momentum, rest, hp);
     count_launch();
   }
-  return check_launch("kfp16_sgd_update_flat") ? 0 : -1;
+  return check_launch(who) ? 0 : -1;
+}
+int kfp16_sgd_update_flat(kfp16_ctx* ctx, float* w32, void* w16, const void* grad, int grad_is_f32, int round_grad,
+                          float grad_scale, float* velocity, float lr, float momentum, size_t n) {
+  return sgd_flat(ctx, w32, w16, grad, grad_is_f32, round_grad, grad_scale, velocity, lr, momentum, n, nullptr, "kfp16_sgd_update_flat");
+}
+// same update with {lr, momentum, grad_scale} read from a 3-float device block at kernel start: a captured CUDA graph of
+// the update then follows SGDOptimizer.SetLR (internal/gpu/optimize.go:123) without re-capture
+int kfp16_sgd_update_flat_hp(kfp16_ctx* ctx, float* w32, void* w16, const void* grad, int grad_is_f32, int round_grad,
+                             float* velocity, const float* hyper_dev, size_t n) {
+  if (!hyper_dev) { set_error("kfp16_sgd_update_flat_hp: null hyper-parameter block"); return -1; }
+  return sgd_flat(ctx, w32, w16, grad, grad_is_f32, round_grad, 1.0f, velocity, 0.f, 0.f, n, hyper_dev, "kfp16_sgd_update_flat_hp");
 }
 
 int kfp16_pack_rows(kfp16_ctx* ctx, const void* src, void* dst, int ld, int n_seq, int seq_len, int halo, int cols,
@@ -1119,6 +1181,15 @@ int kfp16_pack_rows(kfp16_ctx* ctx, const void* src, void* dst, int ld, int n_se
     launch_pdl(pack_rows_kernel<1>, grid_for(elems), kThreads, 0, ctx_stream(ctx), (const __half*)src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
   count_launch();
   return check_launch("kfp16_pack_rows") ? 0 : -1;
+}
+int kfp16_pack_rows_f32(kfp16_ctx* ctx, const float* src, void* dst, int ld, int n_seq, int seq_len, int halo, int cols,
+                        int mode) {
+  if (n_seq <= 0 || seq_len <= 0 || cols <= 0) return 0;
+  if (!src || !dst) { set_error("kfp16_pack_rows_f32: null pointer"); return -1; }
+  const size_t elems = (size_t)n_seq * (seq_len + 2 * halo) * cols;
+  launch_pdl(pack_rows_f32_kernel, grid_for(elems), kThreads, 0, ctx_stream(ctx), src, (__half*)dst, ld, n_seq, seq_len, halo, cols, mode);
+  count_launch();
+  return check_launch("kfp16_pack_rows_f32") ? 0 : -1;
 }
 int kfp16_unpack_rows(kfp16_ctx* ctx, const void* src, int ld, int col0, void* dst, int n_seq, int seq_len, int halo,
                       int cols) {

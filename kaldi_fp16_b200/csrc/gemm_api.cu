@@ -18,6 +18,8 @@ namespace kfp16 {
 // ------------------------------------------------------------------ errors / counters
 static thread_local char g_err[512] = {0};
 std::atomic<unsigned long long> g_launches{0};
+static std::atomic<unsigned long long> g_kind_launches[EK_COUNT];   // GEMM launches per epilogue kind (tests: which bodies ran)
+void count_gemm_kind(int ek) { if (ek >= 0 && ek < EK_COUNT) g_kind_launches[ek].fetch_add(1, std::memory_order_relaxed); }
 void prefer_max_smem_carveout(const void* kern) {
   static const bool on = [] { const char* e = getenv("KFP16_CARVEOUT"); return !(e && e[0] == '0'); }();
   if (!on) return;
@@ -218,6 +220,7 @@ int kfp16_ctx_profile_read(kfp16_ctx* ctx, int* launches, double* total_ms, doub
 }
 void kfp16_set_default_stream(void* s) { g_default_stream = (cudaStream_t)s; }
 unsigned long long kfp16_launch_count(void) { return g_launches.load(); }
+unsigned long long kfp16_gemm_kind_launches(int kind) { return (kind >= 0 && kind < EK_COUNT) ? g_kind_launches[kind].load() : 0ull; }
 const char* kfp16_last_error(void) { return get_error(); }
 
 // ------------------------------------------------------------------ fused GEMM

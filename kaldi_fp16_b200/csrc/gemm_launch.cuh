@@ -47,6 +47,7 @@ static bool launch_cfg(kfp16_ctx* ctx, const GemmParams& p, int grid) {
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   count_launch();
+  count_gemm_kind(EK);            // the epilogue body that actually ran (template argument, not the requested flags)
   return check_cuda(e, "gemm_f16_sm100 launch");
 }
 

@@ -37,6 +37,7 @@ extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 cudaStream_t default_stream();
+void count_gemm_kind(int ek);   // per-EpiKind launch counter (kfp16_gemm_kind_launches)
 
 // returns false (and sets the error) when a launch / runtime call failed
 bool check_launch(const char* what);

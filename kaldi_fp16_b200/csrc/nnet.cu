@@ -92,6 +92,8 @@ struct Layer {
   __half* pf_buf[2] = {nullptr, nullptr};
   cudaEvent_t pf_copied[2] = {nullptr, nullptr}, pf_packed[2] = {nullptr, nullptr};
   int pf_rows = 0, pf_cols = 0, pf_slot = 0, pf_ready = -1;
+  bool pf_f32[2] = {false, false};
+  size_t pf_cap[2] = {0, 0};
   // conv-relu-batchnorm
   int hin = 0, hout = 0, hsub = 1, fin = 0, fout = 0, convK = 0, convKp = 0;
   __half* convP = nullptr;   // this layer's patch matrix: kept from the forward pass for the weight gradient (train mode)
@@ -112,6 +114,10 @@ struct kfp16_net {
   size_t bucket = 0;
   __half* w16 = nullptr;
   float *w32 = nullptr, *vel = nullptr, *g32 = nullptr;
+  __half* g16 = nullptr;                   // FP16 copy of the (scaled) gradient bucket: what the data-parallel exchange carries
+  float* hp_dev = nullptr;                 // {lr, momentum, grad_scale}: read by the SGD kernel at run time (graph-safe SetLR)
+  float hp_host[3] = {0.f, 0.f, 1.f};
+  double flops_bwd = 0;
   float* loss_dev = nullptr;
   float* loss_pinned = nullptr;            // 2 pinned slots for kfp16_net_read_loss_async / kfp16_net_wait_loss
   cudaEvent_t loss_ev[2] = {nullptr, nullptr};
@@ -131,7 +137,7 @@ struct kfp16_net {
   __half* stage_in = nullptr;   // dense staging for host uploads / downloads
   size_t stage_bytes = 0;
   double flops_fwd = 0;
-  cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::map<int, cudaGraphExec_t> graph;     // keyed by the phases bitmask
   // the step graph cut into segments along the backward pass (gradient all-reduce overlapped bucket by bucket)
   // spliced weight gradients deferred to one grouped launch per backward pass / segment (kfp16_wgrad_group)
   std::vector<WgradArgs> deferred;
@@ -139,7 +145,8 @@ struct kfp16_net {
   std::vector<cudaGraphExec_t> seg_graph;
   std::vector<int> seg_launches, seg_lo;            // per segment: kernels, first layer index it back-propagates
   std::vector<size_t> seg_off, seg_cnt;              // gradient-bucket range completed by the segment (elements)
-  int graph_launches[4] = {0, 0, 0, 0};
+  bool seg_export_f16 = false;                       // each segment ends by exporting its gradient range to the FP16 bucket
+  std::map<int, int> graph_launches;
   int out_layer = -1;
 };
 
@@ -559,6 +566,15 @@ bool build_plan(kfp16_net* n) {
     if (!dev_alloc(n, (void**)&n->w32, std::max<size_t>(n->bucket, 8) * sizeof(float))) return false;
     if (!dev_alloc(n, (void**)&n->vel, std::max<size_t>(n->bucket, 8) * sizeof(float))) return false;
     if (!dev_alloc(n, (void**)&n->g32, std::max<size_t>(n->bucket, 8) * sizeof(float))) return false;
+    if (!dev_alloc(n, (void**)&n->g16, std::max<size_t>(n->bucket, 8) * sizeof(__half))) return false;
+    if (!dev_alloc(n, (void**)&n->hp_dev, 64)) return false;
+    n->hp_host[0] = n->opts.lr; n->hp_host[1] = n->opts.momentum;
+    n->hp_host[2] = n->opts.grad_scale != 0.f ? n->opts.grad_scale : 1.0f;
+    {
+      float h[8] = {n->hp_host[0], n->hp_host[1], n->hp_host[2], 0.f, n->hp_host[0], n->hp_host[1], 1.0f, 0.f};
+      if (!check_cuda(cudaMemcpyAsync(n->hp_dev, h, sizeof(h), cudaMemcpyHostToDevice, n->ctx->stream), "hyper-parameter upload") ||
+          !check_cuda(cudaStreamSynchronize(n->ctx->stream), "hyper-parameter upload sync")) return false;
+    }
   }
   if (!dev_alloc(n, (void**)&n->loss_dev, 256)) return false;
 
@@ -583,7 +599,7 @@ bool build_plan(kfp16_net* n) {
       if (train && l.needs_grad && l.wants_dx && !alloc_buf(n, l.d_in_cat, rows, l.in_dim)) return false;
     }
     if (!alloc_buf(n, l.out, rows, store_dim)) return false;
-    max_dense = std::max(max_dense, (size_t)n->T * l.out_dim * sizeof(__half));
+    max_dense = std::max(max_dense, (size_t)n->T * l.out_dim * (l.type == L_INPUT ? sizeof(float) : sizeof(__half)));   // FP32 feature uploads
     if (train && l.needs_grad) {
       if (!alloc_buf(n, l.dout, rows, l.out_dim)) return false;
       if (l.wants_dx && !alloc_buf(n, l.tmp_dx, rows, l.in_dim)) return false;
@@ -603,10 +619,12 @@ bool build_plan(kfp16_net* n) {
         if (!dev_alloc(n, (void**)&l.idct_mat, h.size() * 2)) return false;
         if (!check_cuda(cudaMemcpy(l.idct_mat, h.data(), h.size() * 2, cudaMemcpyHostToDevice), "idct upload")) return false;
         n->flops_fwd += 2.0 * M * D * D;
+        if ((train && l.needs_grad) && l.wants_dx) n->flops_bwd += 2.0 * M * D * D;
         break;
       }
       case L_LINEAR:
         n->flops_fwd += 2.0 * M * l.in_dim * l.out_dim;
+        if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.out_dim;
         break;
       case L_BATCHNORM: {
         const float rms = (float)kv_float(l, "target-rms", 1.0);
@@ -630,6 +648,7 @@ bool build_plan(kfp16_net* n) {
           if (!alloc_buf(n, l.dz, n->Tp, l.out_dim)) return false;
         }
         n->flops_fwd += 2.0 * M * (sp * l.in_dim) * l.bott_dim + 2.0 * M * (sp * l.bott_dim) * l.out_dim;
+        if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * (sp * l.in_dim) * l.bott_dim + 2 * 2.0 * M * (sp * l.bott_dim) * l.out_dim;
         break;
       }
       case L_PREFINAL: {
@@ -645,11 +664,13 @@ bool build_plan(kfp16_net* n) {
           if (!alloc_buf(n, l.dys, rows2, l.small_dim)) return false;
         }
         n->flops_fwd += 2.0 * M * l.in_dim * l.big_dim + 2.0 * M * l.big_dim * l.small_dim;
+        if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.big_dim + 2 * 2.0 * M * l.big_dim * l.small_dim;
         break;
       }
       case L_OUTPUT:
         if (!check_tma_dim(l, l.in_dim, "input dim")) return false;
         n->flops_fwd += 2.0 * M * l.in_dim * l.out_dim;
+        if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.out_dim;
         break;
       case L_CONV: {
         if (l.per_seq) { set_error("conv layer %s on a per-sequence input", l.name.c_str()); return false; }
@@ -664,6 +685,7 @@ bool build_plan(kfp16_net* n) {
         n->conv_P_elems = std::max(n->conv_P_elems, mrows * l.convKp);
         n->conv_dz_elems = std::max(n->conv_dz_elems, mrows * l.fout);
         n->flops_fwd += 2.0 * M * l.hout * l.convK * l.fout;
+        if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * l.hout * l.convK * l.fout;
         break;
       }
       default: break;
@@ -1188,8 +1210,14 @@ int run_phases(kfp16_net* n, int phases) {
     if (kfp16_net_loss_half_sq(n, "")) return -1;
     if (kfp16_net_backward(n)) return -1;
   }
+  if (phases & 4) {
+    if (kfp16_net_grads_to_f16(n)) return -1;
+  }
   if (phases & 2) {
-    if (kfp16_net_sgd_step(n, n->opts.grad_scale != 0.f ? n->opts.grad_scale : 1.0f, n->opts.round_grad)) return -1;
+    if (kfp16_net_sgd_step(n, n->hp_host[2], n->opts.round_grad)) return -1;
+  }
+  if (phases & 8) {
+    if (kfp16_net_sgd_step_f16(n)) return -1;
   }
   return 0;
 }
@@ -1233,7 +1261,7 @@ kfp16_net* kfp16_net_create(kfp16_ctx* ctx, const char* xconfig, const kfp16_net
 void kfp16_net_destroy(kfp16_net* n) {
   if (!n) return;
   for (auto& g : n->graph)
-    if (g) cudaGraphExecDestroy(g);
+    if (g.second) cudaGraphExecDestroy(g.second);
   for (void* p : n->allocs) cudaFree(p);
   for (auto& l : n->layers)
     for (int b = 0; b < 2; ++b) {
@@ -1259,6 +1287,7 @@ int kfp16_net_layer_dim(const kfp16_net* n, int i) { return (n && i >= 0 && i < 
 int kfp16_net_padded_rows(const kfp16_net* n) { return n ? n->Tp : 0; }
 int kfp16_net_halo(const kfp16_net* n) { return n ? n->halo : 0; }
 double kfp16_net_flops_forward(const kfp16_net* n) { return n ? n->flops_fwd : 0.0; }
+double kfp16_net_flops_backward(const kfp16_net* n) { return n ? n->flops_bwd : 0.0; }
 
 int kfp16_net_num_params(const kfp16_net* n) { return n ? (int)n->params.size() : 0; }
 const char* kfp16_net_param_name(const kfp16_net* n, int i) { return (n && i >= 0 && i < (int)n->params.size()) ? n->params[i].name.c_str() : nullptr; }
@@ -1344,7 +1373,7 @@ int kfp16_net_init_random(kfp16_net* n, uint64_t seed) {
   return 0;
 }
 
-static int set_input_common(kfp16_net* n, const char* input_name, const void* dense_dev, int rows, int cols) {
+static int set_input_common(kfp16_net* n, const char* input_name, const void* dense_dev, int rows, int cols, bool f32 = false) {
   const int i = find_layer(n, input_name);
   if (i < 0 || n->layers[i].type != L_INPUT) { set_error("kfp16_net_set_input: no input layer named %s", input_name); return -1; }
   Layer& l = n->layers[i];
@@ -1353,30 +1382,42 @@ static int set_input_common(kfp16_net* n, const char* input_name, const void* de
     set_error("kfp16_net_set_input: %s expects [%d x %d], got [%d x %d]", input_name, want_rows, l.out_dim, rows, cols);
     return -1;
   }
+  // halo rows: replicate for spliced consumers, zero otherwise (finite values either way)
+  const int mode = l.halo_mode == HALO_ZERO ? 0 : 1;
+  if (f32) {   // FP32 rows: RNE conversion on the device while scattering (bridge.go:141 does it on the CPU)
+    if (l.per_seq) return kfp16_pack_rows_f32(n->ctx, (const float*)dense_dev, l.out.p, l.out.cols, rows, 1, 0, cols, 0);
+    return kfp16_pack_rows_f32(n->ctx, (const float*)dense_dev, l.out.p, l.out.cols, n->opts.n_seq, n->opts.seq_len, n->halo, cols, mode);
+  }
   if (l.per_seq)
     return check_cuda(cudaMemcpy2DAsync(l.out.p, (size_t)l.out.cols * 2, dense_dev, (size_t)cols * 2, (size_t)cols * 2, rows,
                                         cudaMemcpyDeviceToDevice, n->ctx->stream), "input copy") ? 0 : -1;
-  // halo rows: replicate for spliced consumers, zero otherwise (finite values either way)
-  return kfp16_pack_rows(n->ctx, dense_dev, l.out.p, l.out.cols, n->opts.n_seq, n->opts.seq_len, n->halo, cols, l.halo_mode == HALO_ZERO ? 0 : 1);
+  return kfp16_pack_rows(n->ctx, dense_dev, l.out.p, l.out.cols, n->opts.n_seq, n->opts.seq_len, n->halo, cols, mode);
 }
 int kfp16_net_set_input_device(kfp16_net* n, const char* input_name, const void* dev, int rows, int cols) {
   if (!n || !input_name || !dev) { set_error("kfp16_net_set_input_device: null argument"); return -1; }
   return set_input_common(n, input_name, dev, rows, cols);
 }
-int kfp16_net_set_input(kfp16_net* n, const char* input_name, const uint16_t* host, int rows, int cols) {
+static int set_input_host(kfp16_net* n, const char* input_name, const void* host, int rows, int cols, bool f32) {
   if (!n || !input_name || !host) { set_error("kfp16_net_set_input: null argument"); return -1; }
-  const size_t bytes = (size_t)rows * cols * 2;
+  const size_t bytes = (size_t)rows * cols * (f32 ? 4 : 2);
   if (bytes > n->stage_bytes) { set_error("kfp16_net_set_input: [%d x %d] exceeds the staging buffer", rows, cols); return -1; }
   // the staging buffer is reused by the next call: keep the copy and the scatter ordered on the stream
   if (!check_cuda(cudaMemcpyAsync(n->stage_in, host, bytes, cudaMemcpyHostToDevice, n->ctx->stream), "input upload")) return -1;
-  if (set_input_common(n, input_name, n->stage_in, rows, cols)) return -1;
+  if (set_input_common(n, input_name, n->stage_in, rows, cols, f32)) return -1;
   return check_cuda(cudaStreamSynchronize(n->ctx->stream), "input sync") ? 0 : -1;
+}
+int kfp16_net_set_input(kfp16_net* n, const char* input_name, const uint16_t* host, int rows, int cols) {
+  return set_input_host(n, input_name, host, rows, cols, false);
+}
+int kfp16_net_set_input_f32(kfp16_net* n, const char* input_name, const float* host, int rows, int cols) {
+  return set_input_host(n, input_name, host, rows, cols, true);
 }
 
 // Asynchronous input path: the NEXT minibatch's rows travel host -> device on a copy stream while the current
 // step computes; kfp16_net_commit_input then scatters the staged rows into the padded layout on the main
-// stream.  `host_f16` must be pinned (bridge_host_alloc) and stay untouched until the matching commit.
-int kfp16_net_prefetch_input(kfp16_net* n, const char* input_name, const uint16_t* host, int rows, int cols) {
+// stream (converting FP32 -> FP16 there when the rows were FP32).  `host` must be pinned (bridge_host_alloc) and stay
+// untouched until the matching commit.
+static int prefetch_common(kfp16_net* n, const char* input_name, const void* host, int rows, int cols, bool f32) {
   if (!n || !input_name || !host) { set_error("kfp16_net_prefetch_input: null argument"); return -1; }
   const int i = find_layer(n, input_name);
   if (i < 0 || n->layers[i].type != L_INPUT) { set_error("kfp16_net_prefetch_input: no input layer named %s", input_name); return -1; }
@@ -1384,17 +1425,19 @@ int kfp16_net_prefetch_input(kfp16_net* n, const char* input_name, const uint16_
   const int want_rows = l.per_seq ? n->opts.n_seq : n->T;
   if (rows != want_rows || cols != l.out_dim) { set_error("kfp16_net_prefetch_input: %s expects [%d x %d], got [%d x %d]", input_name, want_rows, l.out_dim, rows, cols); return -1; }
   if (!n->copy_stream && !check_cuda(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking), "copy stream")) return -1;
-  const size_t bytes = (size_t)rows * cols * 2;
+  const size_t bytes = (size_t)rows * cols * (f32 ? 4 : 2);
   const int b = l.pf_slot;
-  if (!l.pf_buf[b]) {
-    if (!dev_alloc(n, (void**)&l.pf_buf[b], bytes, false)) return -1;
-    if (!check_cuda(cudaEventCreateWithFlags(&l.pf_copied[b], cudaEventDisableTiming), "prefetch event") ||
-        !check_cuda(cudaEventCreateWithFlags(&l.pf_packed[b], cudaEventDisableTiming), "prefetch event")) return -1;
+  if (l.pf_cap[b] < bytes) {      // first use of this slot (or a wider element type than before): FP32-sized from then on
+    const size_t cap = (size_t)rows * cols * 4;
+    if (l.pf_buf[b] && !check_cuda(cudaStreamSynchronize(n->ctx->stream), "prefetch regrow sync")) return -1;
+    if (!dev_alloc(n, (void**)&l.pf_buf[b], cap, false)) return -1;
+    l.pf_cap[b] = cap;
+    if (!l.pf_copied[b] && (!check_cuda(cudaEventCreateWithFlags(&l.pf_copied[b], cudaEventDisableTiming), "prefetch event") ||
+                            !check_cuda(cudaEventCreateWithFlags(&l.pf_packed[b], cudaEventDisableTiming), "prefetch event"))) return -1;
   } else if (!check_cuda(cudaStreamWaitEvent(n->copy_stream, l.pf_packed[b], 0), "prefetch wait")) {
     return -1;   // the scatter that last read this staging slot must have run
   }
-  static const int parts_env = getenv("KFP16_H2D_SPLIT") ? atoi(getenv("KFP16_H2D_SPLIT")) : 4;
-  const int parts = bytes >= ((size_t)4 << 20) ? std::max(1, std::min(4, parts_env)) : 1;
+  const int parts = bytes >= ((size_t)4 << 20) ? 4 : 1;
   const size_t chunk = ((bytes / parts) + 255) & ~(size_t)255;
   if (!check_cuda(cudaMemcpyAsync(l.pf_buf[b], host, parts > 1 ? std::min(chunk, bytes) : bytes, cudaMemcpyHostToDevice, n->copy_stream), "prefetch copy")) return -1;
   for (int k = 1; k < parts; ++k) {       // parts 1.. on their own streams (joined into the copy stream), part 0 above
@@ -1413,9 +1456,16 @@ int kfp16_net_prefetch_input(kfp16_net* n, const char* input_name, const uint16_
   }
   if (!check_cuda(cudaEventRecord(l.pf_copied[b], n->copy_stream), "prefetch record")) return -1;
   l.pf_rows = rows; l.pf_cols = cols;
+  l.pf_f32[b] = f32;
   l.pf_ready = b;
   l.pf_slot = b ^ 1;
   return 0;
+}
+int kfp16_net_prefetch_input(kfp16_net* n, const char* input_name, const uint16_t* host, int rows, int cols) {
+  return prefetch_common(n, input_name, host, rows, cols, false);
+}
+int kfp16_net_prefetch_input_f32(kfp16_net* n, const char* input_name, const float* host, int rows, int cols) {
+  return prefetch_common(n, input_name, host, rows, cols, true);
 }
 int kfp16_net_commit_input(kfp16_net* n, const char* input_name) {
   if (!n || !input_name) { set_error("kfp16_net_commit_input: null argument"); return -1; }
@@ -1425,7 +1475,7 @@ int kfp16_net_commit_input(kfp16_net* n, const char* input_name) {
   const int b = l.pf_ready;
   l.pf_ready = -1;
   if (!check_cuda(cudaStreamWaitEvent(n->ctx->stream, l.pf_copied[b], 0), "commit wait")) return -1;
-  if (set_input_common(n, input_name, l.pf_buf[b], l.pf_rows, l.pf_cols)) return -1;
+  if (set_input_common(n, input_name, l.pf_buf[b], l.pf_rows, l.pf_cols, l.pf_f32[b])) return -1;
   return check_cuda(cudaEventRecord(l.pf_packed[b], n->ctx->stream), "commit record") ? 0 : -1;
 }
 
@@ -1554,14 +1604,46 @@ int kfp16_net_backward(kfp16_net* n) {
 
 int kfp16_net_sgd_step(kfp16_net* n, float grad_scale, int round_grad) {
   if (!n || !n->g32) { set_error("kfp16_net_sgd_step: network was created with train = 0"); return -1; }
-  return kfp16_sgd_update_flat(n->ctx, n->w32, n->w16, n->g32, 1, round_grad, grad_scale, n->vel, n->opts.lr, n->opts.momentum, n->bucket);
+  // the usual case (the scale the network was created with): every hyper-parameter is read from the device block, so a
+  // captured graph of this launch follows kfp16_net_set_lr / set_momentum; any other scale is passed by value
+  if (grad_scale == n->hp_host[2])
+    return kfp16_sgd_update_flat_hp(n->ctx, n->w32, n->w16, n->g32, 1, round_grad, n->vel, n->hp_dev, n->bucket);
+  return kfp16_sgd_update_flat(n->ctx, n->w32, n->w16, n->g32, 1, round_grad, grad_scale, n->vel, n->hp_host[0], n->hp_host[1], n->bucket);
+}
+// g16 = half(g32 * grad_scale): the FP16 gradient tensors of the reference (AffineBackwardWeights returns FP16,
+// internal/gpu/backward_ops.go:195-225) as ONE flat bucket -- what the data-parallel exchange all-reduces (half the bytes
+// of the FP32 bucket).  kfp16_net_sgd_step_f16 then applies ops_sgd_update's arithmetic to it (scale 1).
+int kfp16_net_grads_to_f16(kfp16_net* n) {
+  if (!n || !n->g32) { set_error("kfp16_net_grads_to_f16: network was created with train = 0"); return -1; }
+  return kfp16_scale_f32_to_f16(n->ctx, n->g32, n->g16, n->bucket, n->hp_dev + 2);
+}
+void* kfp16_net_grads_f16(kfp16_net* n) { return n ? (void*)n->g16 : nullptr; }
+int kfp16_net_sgd_step_f16(kfp16_net* n) {
+  if (!n || !n->g16) { set_error("kfp16_net_sgd_step_f16: network was created with train = 0"); return -1; }
+  return kfp16_sgd_update_flat_hp(n->ctx, n->w32, n->w16, n->g16, 0, 0, n->vel, n->hp_dev + 4, n->bucket);
+}
+static int upload_hp(kfp16_net* n) {
+  // hp_dev[0..2] = {lr, momentum, grad_scale}; hp_dev[4..6] = {lr, momentum, 1} for the FP16-gradient update
+  float h[8] = {n->hp_host[0], n->hp_host[1], n->hp_host[2], 0.f, n->hp_host[0], n->hp_host[1], 1.0f, 0.f};
+  // stream-ordered: takes effect for every update queued after this call, captured graphs included
+  return check_cuda(cudaMemcpyAsync(n->hp_dev, h, sizeof(h), cudaMemcpyHostToDevice, n->ctx->stream), "hyper-parameter upload") &&
+         check_cuda(cudaStreamSynchronize(n->ctx->stream), "hyper-parameter upload sync") ? 0 : -1;
 }
 int kfp16_net_set_lr(kfp16_net* n, float lr) {
-  if (!n) return -1;
-  if (n->graph[2] || n->graph[3]) { set_error("kfp16_net_set_lr: the SGD step is captured in a CUDA graph; re-capture after changing lr"); return -1; }
+  if (!n) { set_error("kfp16_net_set_lr: null network"); return -1; }
   n->opts.lr = lr;
-  return 0;
+  if (!n->hp_dev) return 0;
+  n->hp_host[0] = lr;
+  return upload_hp(n);
 }
+int kfp16_net_set_momentum(kfp16_net* n, float momentum) {
+  if (!n) { set_error("kfp16_net_set_momentum: null network"); return -1; }
+  n->opts.momentum = momentum;
+  if (!n->hp_dev) return 0;
+  n->hp_host[1] = momentum;
+  return upload_hp(n);
+}
+float kfp16_net_get_lr(const kfp16_net* n) { return n ? n->opts.lr : 0.f; }
 int kfp16_net_read_loss(kfp16_net* n, float* loss) {
   if (!n || !loss) { set_error("kfp16_net_read_loss: null argument"); return -1; }
   if (!check_cuda(cudaMemcpyAsync(loss, n->loss_dev, 4, cudaMemcpyDeviceToHost, n->ctx->stream), "loss download")) return -1;
@@ -1592,16 +1674,38 @@ int kfp16_net_wait_loss(kfp16_net* n, int slot, float* loss) {
 }
 
 int kfp16_net_capture(kfp16_net* n, int phases) {
-  if (!n || phases < 1 || phases > 3) { set_error("kfp16_net_capture: phases must be 1, 2 or 3"); return -1; }
+  if (!n || phases < 1 || phases > 15) { set_error("kfp16_net_capture: phases is a bitmask of 1 (step), 2 (SGD), 4 (FP16 gradient export), 8 (SGD from FP16 gradients)"); return -1; }
   if (!n->ctx->stream) { set_error("kfp16_net_capture: graph capture needs a non-default stream (kfp16_ctx_set_stream)"); return -1; }
-  // one eager pass first: sets kernel attributes (dynamic smem opt-in) outside the capture
-  if (run_phases(n, phases)) return -1;
-  if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "pre-capture sync")) return -1;
+  if ((phases & ~1) && !n->g32) { set_error("kfp16_net_capture: network was created with train = 0"); return -1; }
+  cudaStream_t st = n->ctx->stream;
+  // One eager pass first: kernel attributes (dynamic shared memory opt-in) and the grouped weight-gradient tables are
+  // set up outside the capture.  Its side effects on the training state are undone: master / FP16 weights, velocities,
+  // both gradient buckets and the loss accumulator are snapshotted before and restored after, so capturing neither
+  // takes an optimiser step nor disturbs a pending loss read (activations are scratch and simply recomputed).
+  struct Snap { void* dst; const void* src; size_t bytes; };
+  std::vector<Snap> snaps;
+  char* save = nullptr;
+  if (n->g32) {
+    const size_t b = n->bucket;
+    const size_t total = b * (4 + 4 + 4 + 2 + 2) + 256;
+    if (!check_cuda(cudaMalloc((void**)&save, total), "cudaMalloc (capture snapshot)")) return -1;
+    char* q = save;
+    auto add = [&](void* live, size_t bytes) { snaps.push_back({live, q, bytes}); q += bytes; };
+    add(n->w32, b * 4); add(n->vel, b * 4); add(n->g32, b * 4); add(n->w16, b * 2); add(n->g16, b * 2); add(n->loss_dev, 4);
+    for (const Snap& sn : snaps)
+      if (!check_cuda(cudaMemcpyAsync(const_cast<void*>(sn.src), sn.dst, sn.bytes, cudaMemcpyDeviceToDevice, st), "capture snapshot")) { cudaFree(save); return -1; }
+  }
+  int rc = run_phases(n, phases);
+  for (const Snap& sn : snaps)
+    if (!check_cuda(cudaMemcpyAsync(sn.dst, sn.src, sn.bytes, cudaMemcpyDeviceToDevice, st), "capture restore")) rc = -1;
+  const bool synced = check_cuda(cudaStreamSynchronize(st), "pre-capture sync");
+  if (save) cudaFree(save);
+  if (rc || !synced) return -1;
   const unsigned long long before = kfp16_launch_count();
-  if (!check_cuda(cudaStreamBeginCapture(n->ctx->stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) return -1;
-  const int rc = run_phases(n, phases);
+  if (!check_cuda(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) return -1;
+  rc = run_phases(n, phases);
   cudaGraph_t g = nullptr;
-  const cudaError_t e = cudaStreamEndCapture(n->ctx->stream, &g);
+  const cudaError_t e = cudaStreamEndCapture(st, &g);
   if (rc) { if (g) cudaGraphDestroy(g); return -1; }
   if (!check_cuda(e, "cudaStreamEndCapture")) return -1;
   if (const char* dot = getenv("KFP16_GRAPH_DOT")) {   // debugging aid: <path>.<phases>
@@ -1609,9 +1713,11 @@ int kfp16_net_capture(kfp16_net* n, int phases) {
     snprintf(path, sizeof(path), "%s.%d", dot, phases);
     cudaGraphDebugDotPrint(g, path, 0);
   }
-  if (n->graph[phases]) cudaGraphExecDestroy(n->graph[phases]);
-  const bool ok = check_cuda(cudaGraphInstantiate(&n->graph[phases], g, 0), "cudaGraphInstantiate");
+  if (n->graph.count(phases) && n->graph[phases]) cudaGraphExecDestroy(n->graph[phases]);
+  cudaGraphExec_t ge = nullptr;
+  const bool ok = check_cuda(cudaGraphInstantiate(&ge, g, 0), "cudaGraphInstantiate");
   cudaGraphDestroy(g);
+  n->graph[phases] = ge;
   n->graph_launches[phases] = (int)(kfp16_launch_count() - before);
   return ok ? 0 : -1;
 }
@@ -1631,13 +1737,19 @@ static int run_segment(kfp16_net* n, int seg) {
     if (kfp16_net_zero_grads(n) || kfp16_net_forward(n) || kfp16_net_loss_half_sq(n, "")) return -1;
   }
   if (backward_range(n, hi, n->seg_lo[seg], seg == 0)) return -1;
-  return flush_wgrads(n);      // the segment's gradient range must be complete when it ends
+  if (flush_wgrads(n)) return -1;      // the segment's gradient range must be complete when it ends
+  if (n->seg_export_f16 && n->seg_cnt[seg] > 0)
+    return kfp16_scale_f32_to_f16(n->ctx, n->g32 + n->seg_off[seg], n->g16 + n->seg_off[seg], n->seg_cnt[seg], n->hp_dev + 2);
+  return 0;
 }
-int kfp16_net_capture_segments(kfp16_net* n, int nseg) {
+// cut_layers: NULL = cut at equal shares of the parameter count; else a comma-separated list of layer names, top of the
+// network first: segment k back-propagates down to (and including) the k-th named layer, the last segment takes the rest.
+// tail_max_ctas > 0: segments 1.. are captured with their persistent grids limited to that many CTAs (the all-reduce
+// of the previous segment's gradients runs beside them and needs SMs of its own).
+int kfp16_net_capture_segments_ex(kfp16_net* n, int nseg, const char* cut_layers, int export_f16, int tail_max_ctas) {
   if (!n || !n->g32 || nseg < 1) { set_error("kfp16_net_capture_segments: needs a training network and nseg >= 1"); return -1; }
   if (!n->ctx->stream) { set_error("kfp16_net_capture_segments: graph capture needs a non-default stream"); return -1; }
   if (n->side) { set_error("kfp16_net_capture_segments: not available with the weight-gradient side stream"); return -1; }
-  // cut points: equal shares of the parameter count, counted from the top of the network
   const int L = (int)n->layers.size();
   std::vector<size_t> first(L + 1, n->bucket);
   for (int i = L - 1; i >= 0; --i) {
@@ -1646,17 +1758,35 @@ int kfp16_net_capture_segments(kfp16_net* n, int nseg) {
   }
   for (cudaGraphExec_t g : n->seg_graph) if (g) cudaGraphExecDestroy(g);
   n->seg_graph.clear(); n->seg_launches.clear(); n->seg_lo.clear(); n->seg_off.clear(); n->seg_cnt.clear();
+  n->seg_export_f16 = export_f16 != 0;
+  std::vector<int> cuts;     // explicit lower bounds (layer indices), top first
+  if (cut_layers && cut_layers[0]) {
+    std::stringstream ss(cut_layers);
+    std::string nm;
+    while (std::getline(ss, nm, ',')) {
+      nm = trim(nm);
+      if (nm.empty()) continue;
+      const int li = find_layer(n, nm);
+      if (li < 0) { set_error("kfp16_net_capture_segments: no layer named %s", nm.c_str()); return -1; }
+      if (!cuts.empty() && li >= cuts.back()) { set_error("kfp16_net_capture_segments: cut layers must be listed top of the network first"); return -1; }
+      cuts.push_back(li);
+    }
+    nseg = (int)cuts.size() + 1;
+  }
   int hi = L;
   for (int k = 0; k < nseg && hi > 0; ++k) {
     int lo = 0;
-    if (k + 1 < nseg) {
+    if (!cuts.empty()) {
+      lo = k < (int)cuts.size() ? cuts[k] : 0;
+    } else if (k + 1 < nseg) {
+      // cut points: equal shares of the parameter count, counted from the top of the network
       const size_t target = (size_t)((double)n->bucket * (nseg - 1 - k) / nseg);   // bucket offset where this segment should start
       lo = hi - 1;
       while (lo > 0 && first[lo] > target) --lo;
     }
     if (first[lo] == first[hi]) {          // no parameters in [lo, hi)
-      if (lo > 0) continue;                 // try again with the next (lower) target
-      break;                                // only parameter-free layers are left: the last segment takes them (below)
+      if (lo > 0 && cuts.empty()) continue; // try again with the next (lower) target
+      if (cuts.empty()) break;              // only parameter-free layers are left: the last segment takes them (below)
     }
     n->seg_lo.push_back(lo);
     n->seg_off.push_back(first[lo]);
@@ -1671,13 +1801,22 @@ int kfp16_net_capture_segments(kfp16_net* n, int nseg) {
     n->seg_lo.back() = 0;
   }
   const int S = (int)n->seg_lo.size();
-  for (int k = 0; k < S; ++k)                           // eager pass: kernel attributes are set outside the capture
-    if (run_segment(n, k)) return -1;
+  const int saved_max = n->ctx->max_ctas;
+  auto limit = [&](int k) { n->ctx->max_ctas = (k > 0 && tail_max_ctas > 0) ? tail_max_ctas : saved_max; };
+  // eager pass: kernel attributes are set outside the capture (this pass leaves a gradient in the buckets and adds to
+  // the loss accumulator; weights are untouched)
+  for (int k = 0; k < S; ++k) {
+    limit(k);
+    if (run_segment(n, k)) { n->ctx->max_ctas = saved_max; return -1; }
+  }
+  n->ctx->max_ctas = saved_max;
   if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "pre-capture sync")) return -1;
   for (int k = 0; k < S; ++k) {
     const unsigned long long before = kfp16_launch_count();
-    if (!check_cuda(cudaStreamBeginCapture(n->ctx->stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) return -1;
+    limit(k);
+    if (!check_cuda(cudaStreamBeginCapture(n->ctx->stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) { n->ctx->max_ctas = saved_max; return -1; }
     const int rc = run_segment(n, k);
+    n->ctx->max_ctas = saved_max;
     cudaGraph_t g = nullptr;
     const cudaError_t e = cudaStreamEndCapture(n->ctx->stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return -1; }
@@ -1691,6 +1830,7 @@ int kfp16_net_capture_segments(kfp16_net* n, int nseg) {
   }
   return S;
 }
+int kfp16_net_capture_segments(kfp16_net* n, int nseg) { return kfp16_net_capture_segments_ex(n, nseg, nullptr, 0, 0); }
 int kfp16_net_launch_segment(kfp16_net* n, int seg) {
   if (!n || seg < 0 || seg >= (int)n->seg_graph.size()) { set_error("kfp16_net_launch_segment: segment %d not captured", seg); return -1; }
   if (!check_cuda(cudaGraphLaunch(n->seg_graph[seg], n->ctx->stream), "cudaGraphLaunch")) return -1;
@@ -1705,13 +1845,15 @@ int kfp16_net_segment_grads(const kfp16_net* n, int seg, size_t* first_elem, siz
 }
 
 int kfp16_net_launch(kfp16_net* n, int phases) {
-  if (!n || phases < 1 || phases > 3 || !n->graph[phases]) { set_error("kfp16_net_launch: phases %d not captured", phases); return -1; }
+  if (!n || !n->graph.count(phases) || !n->graph[phases]) { set_error("kfp16_net_launch: phases %d not captured", phases); return -1; }
   if (!check_cuda(cudaGraphLaunch(n->graph[phases], n->ctx->stream), "cudaGraphLaunch")) return -1;
   count_launch(n->graph_launches[phases]);
   return 0;
 }
 int kfp16_net_launches_per_step(const kfp16_net* n, int phases) {
-  return (n && phases >= 1 && phases <= 3) ? n->graph_launches[phases] : 0;
+  if (!n) return 0;
+  auto it = n->graph_launches.find(phases);
+  return it == n->graph_launches.end() ? 0 : it->second;
 }
 
 }  // extern "C"

@@ -140,6 +140,17 @@ class Network:
         if self.lib.kfp16_net_set_input(self.ptr, name.encode(), bits.ctypes.data, bits.shape[0], bits.shape[1]) != 0:
             raise _err("SetInput")
 
+    def SetInputF32(self, name: str, x: np.ndarray) -> None:
+        """FP32 rows uploaded as they are; the RNE FP32 -> FP16 conversion (bridge.go:141) runs on the device"""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if self.lib.kfp16_net_set_input_f32(self.ptr, name.encode(), x.ctypes.data, x.shape[0], x.shape[1]) != 0:
+            raise _err("SetInputF32")
+
+    def PrefetchInputF32(self, name: str, host_ptr: int, rows: int, cols: int) -> None:
+        """async H2D of the next minibatch's FP32 rows from pinned host memory; CommitInput converts on the device"""
+        if self.lib.kfp16_net_prefetch_input_f32(self.ptr, name.encode(), host_ptr, rows, cols) != 0:
+            raise _err("PrefetchInputF32")
+
     def PrefetchInput(self, name: str, host_ptr: int, rows: int, cols: int) -> None:
         """async H2D of the NEXT minibatch from pinned host memory (gpu.TransferBatchPinned done asynchronously)"""
         if self.lib.kfp16_net_prefetch_input(self.ptr, name.encode(), host_ptr, rows, cols) != 0:
@@ -222,9 +233,11 @@ class Network:
             raise _err("ReadLoss")
         return v.value
 
-    def CaptureSegments(self, nseg: int) -> int:
+    def CaptureSegments(self, nseg: int, cut_layers: Optional[str] = None, export_f16: bool = False,
+                        tail_max_ctas: int = 0) -> int:
         """cut the step graph along the backward pass (bucketed gradient all-reduce); returns the segment count"""
-        k = self.lib.kfp16_net_capture_segments(self.ptr, nseg)
+        k = self.lib.kfp16_net_capture_segments_ex(self.ptr, nseg, cut_layers.encode() if cut_layers else None,
+                                                   int(export_f16), tail_max_ctas)
         if k < 0:
             raise _err("CaptureSegments")
         return k
@@ -255,6 +268,24 @@ class Network:
         if self.lib.kfp16_net_sgd_step(self.ptr, grad_scale, int(round_grad)) != 0:
             raise _err("SGDStep")
 
+    def GradsToF16(self) -> None:
+        """g16 = half(g32 * grad_scale): the reference's FP16 gradient tensors as one flat bucket"""
+        if self.lib.kfp16_net_grads_to_f16(self.ptr) != 0:
+            raise _err("GradsToF16")
+
+    def SGDStepF16(self) -> None:
+        if self.lib.kfp16_net_sgd_step_f16(self.ptr) != 0:
+            raise _err("SGDStepF16")
+
+    def SetLR(self, lr: float) -> None:
+        """SGDOptimizer.SetLR (optimize.go:123); also takes effect for captured graphs"""
+        if self.lib.kfp16_net_set_lr(self.ptr, lr) != 0:
+            raise _err("SetLR")
+
+    def SetMomentum(self, momentum: float) -> None:
+        if self.lib.kfp16_net_set_momentum(self.ptr, momentum) != 0:
+            raise _err("SetMomentum")
+
     def Capture(self, phases: int = 3) -> None:
         if self.lib.kfp16_net_capture(self.ptr, phases) != 0:
             raise _err("Capture")
@@ -263,10 +294,20 @@ class Network:
         if self.lib.kfp16_net_launch(self.ptr, phases) != 0:
             raise _err("Launch")
 
-    def grads_as_cuda_array(self):
-        """flat FP32 gradient bucket as a __cuda_array_interface__ object (for torch.distributed)."""
+    def grads_as_cuda_array(self, f16: bool = False):
+        """flat gradient bucket (FP32, or the FP16 export) as a __cuda_array_interface__ object (for torch.distributed)."""
         n = self.lib.kfp16_net_bucket_size(self.ptr)
-        ptr = self.lib.kfp16_net_grads_f32(self.ptr)
+        ptr = self.lib.kfp16_net_grads_f16(self.ptr) if f16 else self.lib.kfp16_net_grads_f32(self.ptr)
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f2" if f16 else "<f4", "data": (ptr, False),
+                                        "version": 3, "strides": None}
+        return _Arr()
+
+    def params_as_cuda_array(self):
+        """flat FP32 master weights (cross-rank equality checks in the data-parallel loop)"""
+        n = self.lib.kfp16_net_bucket_size(self.ptr)
+        ptr = self.lib.kfp16_net_params_f32(self.ptr)
 
         class _Arr:
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3,
@@ -294,5 +335,4 @@ class Trainer:
         return loss
 
     def SetLR(self, lr: float) -> None:
-        if self.net.lib.kfp16_net_set_lr(self.net.ptr, lr) != 0:
-            raise _err("SetLR")
+        self.net.SetLR(lr)

@@ -1,0 +1,130 @@
+"""Data-parallel step ON THE GPUs: 2 ranks (one process per GPU, NCCL) each run the native executor on
+their shard of the minibatch's sequences, exchange gradients with one sum all-reduce and apply the same SGD update.
+
+  * FP32 bucket exchange: the all-reduced gradient equals the 1-rank gradient on the concatenated minibatch to FP32
+    summation order (<= 1e-5 of the tensor scale);
+  * FP16 bucket exchange (what bench.py --gpus N runs; the reference keeps FP16 gradient tensors,
+    internal/gpu/backward_ops.go:195-225): equal to <= 3 FP16 ulps of the tensor scale;
+  * after 3 steps the master weights are bit-identical on both ranks and match the 1-rank run.
+
+Skipped when fewer than 2 GPUs are visible (run with `gpurun --gpus 2`)."""
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import kaldi_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+XCONFIG = """
+input name=input dim=64
+linear-component name=lin0 dim=256
+tdnnf-layer name=tdnnf1 dim=256 bottleneck-dim=64 time-stride=3 bypass-scale=0.66
+tdnnf-layer name=tdnnf2 dim=256 bottleneck-dim=64 time-stride=3 bypass-scale=0.66
+prefinal-layer name=prefinal small-dim=64 big-dim=256
+output-layer name=output dim=104 include-log-softmax=false
+"""
+N_SEQ, L, STEPS = 8, 40, 3
+SCALE = 1.0 / (N_SEQ * L)
+
+
+def n_gpus() -> int:
+    try:
+        import ctypes
+        n = ctypes.c_int(0)
+        return n.value if ctypes.CDLL("libcudart.so").cudaGetDeviceCount(ctypes.byref(n)) == 0 and n.value > 0 else 0
+    except OSError:
+        return 0
+
+
+def make_data():
+    rng = np.random.default_rng(5)
+    return [O.to_f16_rne(rng.standard_normal((N_SEQ * L, 64)).astype(np.float32)) for _ in range(STEPS)]
+
+
+def run_rank(rank, world, port, f16, q):
+    import torch
+    import torch.distributed as dist
+
+    from kaldi_fp16_b200 import _lib, cudart, dp, gpu, nnet
+    torch.cuda.set_device(rank)
+    if world > 1:
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device(f"cuda:{rank}"))
+    lib = _lib.load()
+    gpu.Init(rank)
+    h = gpu.NewHandle()
+    ts = torch.cuda.Stream(device=rank)
+    lib.kfp16_ctx_set_stream(h.ptr, ts.cuda_stream)
+    sh = dp.shard_sequences(N_SEQ, world, rank)
+    net = nnet.NewNetwork(nnet.BuildModelFromString(XCONFIG), h, sh.n_seq, L, train=True, lr=1e-2, momentum=0.9,
+                          ref_round=False, seed=42, grad_scale=SCALE)
+    red = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(f16=f16), device=f"cuda:{rank}")) if world > 1 else None
+    first_grad = None
+    for step, x in enumerate(make_data()):
+        net.SetInput("input", x[sh.rows(L)])
+        net.ZeroGrads()
+        assert lib.kfp16_net_forward(net.ptr) == 0
+        net.Backward(None)
+        if f16:
+            net.GradsToF16()
+        if red is not None:
+            with torch.cuda.stream(ts):
+                red.all_reduce()
+        cudart.synchronize()
+        if step == 0:
+            if f16:
+                g = np.empty(lib.kfp16_net_bucket_size(net.ptr), np.uint16)
+                assert lib.bridge_read_fp16(g.ctypes.data, lib.kfp16_net_grads_f16(net.ptr), g.size) == 0
+                first_grad = g.view(np.float16).astype(np.float32)
+            else:
+                first_grad = net._bucket_f32(lib.kfp16_net_grads_f32) * np.float32(SCALE)
+        if f16:
+            net.SGDStepF16()
+        else:
+            net.SGDStep(SCALE, False)
+    cudart.synchronize()
+    w = net._bucket_f32(lib.kfp16_net_params_f32)
+    q.put((rank, first_grad, w))
+    net.Free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def launch(world, f16):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [ctx.Process(target=run_rank, args=(r, world, port, f16, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, g, w = q.get(timeout=600)
+        res[r] = (g, w)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return res
+
+
+@pytest.mark.parametrize("f16", [False, True], ids=["fp32_bucket", "fp16_bucket"])
+def test_two_rank_step_equals_one_rank_step(f16):
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    one = launch(1, f16)[0]
+    two = launch(2, f16)
+    g1, w1 = one
+    scale = np.abs(g1).max()
+    assert scale > 0
+    for r in (0, 1):
+        g2, w2 = two[r]
+        err = np.abs(g2 - g1).max() / scale
+        assert err <= (3 * 2.0 ** -10 if f16 else 1e-5), f"rank {r}: all-reduced gradient vs 1-rank gradient: {err:.2e}"
+    assert np.array_equal(two[0][1], two[1][1]), "master weights differ between the ranks after 3 steps"
+    werr = np.abs(two[0][1] - w1).max() / np.abs(w1).max()
+    assert werr <= (2e-3 if f16 else 1e-5), f"weights after {STEPS} steps vs the 1-rank run: {werr:.2e}"

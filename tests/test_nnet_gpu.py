@@ -137,17 +137,26 @@ def check_forward_backward(on, net, inputs, per_seq=(), act_tol=2e-3, grad_tol=5
     return acts, wg, dact
 
 
+# ref_round = True keeps the reference's FP16 store between fused stages (generic run-time-flag epilogue);
+# ref_round = False is what bench.py runs: the compile-time specialised epilogues (EK_AFFINE, EK_AFFINE_RES, EK_BN,
+# EK_BN_GRADMASK, EK_BIAS, EK_RESID, EK_PLAIN), which skip those intermediate roundings.  Both must meet the same bounds.
+REF_ROUND = pytest.mark.parametrize("ref_round", [True, False], ids=["ref_round", "specialised"])
+SEEDS = {"sgdtest": 11, "traintest": 23}
+
+
+@REF_ROUND
 @pytest.mark.parametrize("xconfig,name", [(SGDTEST, "sgdtest"), (TRAINTEST, "traintest")])
-def test_acceptance_nets_forward_backward(handle, xconfig, name):
-    on, net, rng = make_pair(handle, xconfig, 1, 32, seed=hash(name) % 1000)
+def test_acceptance_nets_forward_backward(handle, xconfig, name, ref_round):
+    on, net, rng = make_pair(handle, xconfig, 1, 32, seed=SEEDS[name], ref_round=ref_round)
     x = O.to_f16_rne((rng.random((32, 40)) * 2 - 1).astype(np.float32))     # rand.Float32()*2-1
     check_forward_backward(on, net, {"input": x})
     net.Free()
 
 
-def test_backtest_net_with_append(handle):
+@REF_ROUND
+def test_backtest_net_with_append(handle, ref_round):
     """cmd/backtest/main.go:217-293: Append(idct, ivector) with a [T x 32] ivector; every layer gets gradients"""
-    on, net, rng = make_pair(handle, BACKTEST, 1, 32, seed=5)
+    on, net, rng = make_pair(handle, BACKTEST, 1, 32, seed=5, ref_round=ref_round)
     x = O.to_f16_rne((rng.random((32, 40)) * 2 - 1).astype(np.float32))
     iv = O.to_f16_rne((rng.random((32, 32)) * 2 - 1).astype(np.float32))
     acts, wg, dact = check_forward_backward(on, net, {"input": x, "ivector": iv})
@@ -156,24 +165,35 @@ def test_backtest_net_with_append(handle):
     net.Free()
 
 
+@REF_ROUND
 @pytest.mark.parametrize("n_seq,L", [(1, 96), (4, 50), (3, 41)])
-def test_spliced_tdnnf_stack(handle, n_seq, L):
+def test_spliced_tdnnf_stack(handle, lib, n_seq, L, ref_round):
     """time-stride > 0: splice as TMA row offsets over the padded layout, per-sequence clamp
     (n_seq=1 is the reference's whole-minibatch clamp, forward.go:714-722,760-770)"""
-    on, net, rng = make_pair(handle, SPLICED, n_seq, L, seed=n_seq * 100 + L)
+    kinds0 = [lib.kfp16_gemm_kind_launches(k) for k in range(9)]
+    on, net, rng = make_pair(handle, SPLICED, n_seq, L, seed=n_seq * 100 + L, ref_round=ref_round)
     x = O.to_f16_rne(rng.standard_normal((n_seq * L, 64)).astype(np.float32))
     acts, wg, dact = check_forward_backward(on, net, {"input": x})
     # activation gradients too
     for lname in ("tdnnf2", "tdnnf1", "lin0"):
         err = rel_to_scale(net.Grad(lname), dact[lname])
         assert err <= 5e-3, f"dact {lname}: {err:.2e}"
+    # which epilogue bodies ran: kind 0 = generic run-time flags, 2 affine, 3 affine+bypass, 4 residual, 5 bn+gradmask,
+    # 6 bn, 7 bias (include/kaldi_fp16_fused.h kfp16_gemm_kind_launches)
+    ran = [lib.kfp16_gemm_kind_launches(k) - kinds0[k] for k in range(9)]
+    if ref_round:
+        assert ran[0] > 0 and ran[2] == 0 and ran[3] == 0
+    else:
+        assert ran[0] == 0, f"specialised run used the generic epilogue: {ran}"
+        assert all(ran[k] > 0 for k in (1, 2, 3, 4, 5, 6, 7, 8)), f"expected every specialised kind to run: {ran}"
     net.Free()
 
 
-def test_ivector_branch_and_combine(handle):
+@REF_ROUND
+def test_ivector_branch_and_combine(handle, ref_round):
     """ReplaceIndex(ivector,t,0) -> per-sequence branch broadcast into Append + combine-feature-maps"""
     n_seq, L = 3, 20
-    on, net, rng = make_pair(handle, IVECTOR, n_seq, L, seed=77)
+    on, net, rng = make_pair(handle, IVECTOR, n_seq, L, seed=77, ref_round=ref_round)
     x = O.to_f16_rne((rng.standard_normal((n_seq * L, 40)) * 3).astype(np.float32))
     iv = O.to_f16_rne(rng.standard_normal((n_seq, 16)).astype(np.float32))
     check_forward_backward(on, net, {"input": x, "ivector": iv}, per_seq=("ivector", "ivector-linear", "ivector-batchnorm"))
@@ -238,9 +258,12 @@ def test_graph_replay_equals_eager(handle, lib):
         w_eager = {k: net.GetParam(k) for k in net.params}
         for k, w in w0.items():
             net.SetParam(k, w)
-        net.Capture(3)           # runs one eager pass + the capture pass: reset weights again
-        for k, w in w0.items():
-            net.SetParam(k, w)
+        m0 = net.MasterWeights()
+        net.Capture(3)           # its eager warm-up pass is undone: capturing takes no optimiser step
+        m1 = net.MasterWeights()
+        for k in m0:
+            assert np.array_equal(m0[k], m1[k]), f"capture changed master weights of {k}"
+        assert not np.any(net._bucket_f32(lib.kfp16_net_velocity)), "capture left a velocity behind"
         net.ReadLoss()
         net.Launch(3)
         st.synchronize()
@@ -284,8 +307,8 @@ output-layer name=output include-log-softmax=false dim=72
 """
 
 
-def check_conv_net(handle, n_seq, L, seed):
-    on, net, rng = make_pair(handle, CNN_SMALL, n_seq, L, seed=seed)
+def check_conv_net(handle, n_seq, L, seed, ref_round=True):
+    on, net, rng = make_pair(handle, CNN_SMALL, n_seq, L, seed=seed, ref_round=ref_round)
     x = O.to_f16_rne((rng.standard_normal((n_seq * L, 16)) * 2).astype(np.float32))
     iv = O.to_f16_rne(np.clip(rng.standard_normal((n_seq, 24)), -3, 3).astype(np.float32))
     inputs = {"input": x, "ivector": iv}
@@ -320,11 +343,105 @@ def check_conv_net(handle, n_seq, L, seed):
     net.Free()
 
 
-@pytest.mark.parametrize("n_seq,L", [(2, 30), (3, 17)])
-def test_cnn_front_end_forward_backward(handle, n_seq, L):
-    """conv-relu-batchnorm layers (3x3 Cartesian taps, height subsampling, 3-filter input with K = 27 padded
-    to 32) lowered to im2col + tcgen05 GEMM, against the numpy oracle's explicit patch matrices"""
-    check_conv_net(handle, n_seq, L, seed=5 + n_seq)
+@REF_ROUND
+@pytest.mark.parametrize("n_seq,L", [(2, 30), (3, 17), (5, 64)])
+def test_cnn_front_end_forward_backward(handle, n_seq, L, ref_round):
+    """conv-relu-batchnorm layers (3x3 Cartesian taps, height subsampling, 3-filter input with K = 27) lowered to
+    tcgen05 GEMMs (implicit GEMM over 4-D TMA boxes; the 3-filter first layer through a patch matrix), against the
+    numpy oracle's explicit patch matrices"""
+    check_conv_net(handle, n_seq, L, seed=5 + n_seq, ref_round=ref_round)
+
+
+def test_set_lr_reaches_a_captured_sgd_graph(handle, lib):
+    """SGDOptimizer.SetLR (optimize.go:123) on the graph path: lr / momentum live in a device block the captured update
+    kernel reads at run time, so kfp16_net_set_lr changes the step size of an already captured graph"""
+    from kaldi_fp16_b200 import cudart
+    st = cudart.Stream()
+    lib.kfp16_ctx_set_stream(handle.ptr, st.ptr)
+    try:
+        on, net, rng = make_pair(handle, TRAINTEST, 1, 32, seed=3, randomize_bn=False, lr=1e-3, momentum=0.0)
+        x = O.to_f16_rne((rng.random((32, 40)) * 2 - 1).astype(np.float32))
+        net.SetInput("input", x)
+        net.Capture(1)
+        net.Capture(2)
+        w0 = net.MasterWeights()
+
+        def delta():
+            before = net.MasterWeights()
+            net.Launch(1)
+            net.Launch(2)
+            st.synchronize()
+            after = net.MasterWeights()
+            return {k: after[k] - before[k] for k in before}
+
+        d1 = delta()
+        for k, w in w0.items():          # same weights again -> same gradient
+            net.SetParam(k, w)
+        net.SetLR(2.5e-4)
+        assert abs(lib.kfp16_net_get_lr(net.ptr) - 2.5e-4) < 1e-9
+        d2 = delta()
+        for k in d1:
+            if k.endswith("Bias") or not np.abs(d1[k]).max() > 0:
+                continue
+            ratio = np.abs(d2[k]).sum() / np.abs(d1[k]).sum()
+            assert abs(ratio - 0.25) < 2e-3, f"{k}: update ratio {ratio} after lr 1e-3 -> 2.5e-4"
+        net.Free()
+    finally:
+        lib.kfp16_ctx_set_stream(handle.ptr, None)
+        st.destroy()
+
+
+def test_fp32_input_is_converted_on_the_device(handle, lib):
+    """kfp16_net_set_input_f32 / prefetch_input_f32: FP32 rows -> RNE FP16 on the device == the host-side conversion
+    (internal/gpu/bridge.go:141, fp16.ConvertFloat32ToFloat16), including overflow to Inf and subnormals"""
+    import ctypes as C
+    n_seq, L = 3, 25
+    on, net, rng = make_pair(handle, SPLICED, n_seq, L, seed=21)
+    x = (rng.standard_normal((n_seq * L, 64)) * 3).astype(np.float32)
+    x[0, :6] = [65504.0, 65519.9, 65520.0, 1e-7, 6.1e-5, -2.0 ** -25]
+    net.SetInput("input", x)                  # host RNE conversion
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    want_in, want = net.Output("input"), net.Output("lin0")
+    net.SetInputF32("input", x)               # device conversion
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    assert np.array_equal(net.Output("input"), want_in, equal_nan=True)
+    assert np.array_equal(net.Output("lin0"), want, equal_nan=True)
+    pinned = lib.bridge_host_alloc(x.nbytes)
+    C.memmove(pinned, x.ctypes.data, x.nbytes)
+    net.SetInput("input", np.zeros_like(x))
+    net.PrefetchInputF32("input", pinned, n_seq * L, 64)
+    net.CommitInput("input")
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    assert np.array_equal(net.Output("input"), want_in, equal_nan=True)
+    lib.bridge_host_free(pinned)
+    net.Free()
+
+
+def test_fp16_gradient_bucket_and_update(handle, lib):
+    """kfp16_net_grads_to_f16 + kfp16_net_sgd_step_f16 (the data-parallel path: FP16 gradient bucket, as the reference's
+    FP16 gradient tensors) == kfp16_net_sgd_step with round_grad = 1 on the FP32 bucket, bit for bit"""
+    on, net, rng = make_pair(handle, SPLICED, 2, 40, seed=8, lr=1e-3, momentum=0.9, grad_scale=1.0 / 64)
+    x = O.to_f16_rne(rng.standard_normal((80, 64)).astype(np.float32))
+    w0 = {k: net.GetParam(k) for k in net.params}
+    net.SetInput("input", x)
+    net.ZeroGrads()
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    net.Backward(None)
+    net.SGDStep(1.0 / 64, True)
+    a = net.MasterWeights()
+    for k, w in w0.items():
+        net.SetParam(k, w)
+    net.GradsToF16()
+    g16 = np.empty(lib.kfp16_net_bucket_size(net.ptr), np.uint16)
+    gpu.Sync()
+    assert lib.bridge_read_fp16(g16.ctypes.data, lib.kfp16_net_grads_f16(net.ptr), g16.size) == 0
+    g32 = net._bucket_f32(lib.kfp16_net_grads_f32)
+    assert np.array_equal(g16.view(np.float16), (g32 * np.float32(1.0 / 64)).astype(np.float16))
+    net.SGDStepF16()
+    b = net.MasterWeights()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    net.Free()
 
 
 def test_prefetched_input_equals_synchronous_input(handle, lib):
