@@ -66,6 +66,24 @@ typedef struct {
     int halo;        /* rows readable before row 0 and after row rows-1 */
 } kfp16_mat;
 
+/* Implicit-GEMM convolution addressing (the conv-relu-batchnorm layer, internal/nnet/forward.go:418-524, without the
+ * patch matrix): one operand of the GEMM is the 4-D activation tensor x[T][H][P][C] (frames, heights, parity planes,
+ * channels; C innermost, C % 64 == 0) and the GEMM's K (mode 1) or M (mode 2) index runs over (tap, channel): tap s reads
+ * x[t + dt[s]][h + hq[s]][par[s]][:], zeros outside [0,T) x [0,H) -- TMA out-of-bounds fill is the zero padding.
+ *   mode 1 (forward, input gradient): A rows m = t*rows_h + h, K = ntaps*C; B as usual with brow[s] = where tap s's
+ *           weights start (MN-major B: first k row; K-major B: first n row).  M = T*rows_h.
+ *   mode 2 (weight gradient): dW[(s, c), n] = sum over (t, h) of x[t+dt[s]][h+hq[s]][par[s]][c] * B[(t*rows_h + h), n];
+ *           A and B MN-major, fp32 accumulation into ws[0] (split_k >= 1).  M = ntaps*C, K = T*rows_h.
+ * Height subsampling by 2 is a parity plane: x viewed as [T][H/2][2][C], tap dh -> par = dh & 1, hq = (dh - par) / 2. */
+typedef struct {
+    int mode;
+    const void *x;
+    int T, H, P, C;
+    int rows_h;   /* heights per frame in the GEMM index (<= H; <= 128 in mode 1) */
+    int ntaps;    /* 1..16 */
+    int dt[16], hq[16], par[16], brow[16];
+} kfp16_conv_addr;
+
 typedef struct {
     int M, N, K; /* per-group problem; K = kslabs*kslab_len */
     /* A: K-major = stored [M x K]; MN-major = stored [K x M] (i.e. A^T, used by weight gradients)
@@ -102,9 +120,8 @@ typedef struct {
     int force_generic; /* 1 = run the run-time-flag epilogue even when a specialised one exists (tests) */
     int force_cg;      /* 0 = heuristic; 1 = one CTA per 128-row tile; 2 = CTA pairs (cta_group::2, 256-row tiles) */
     int no_share;      /* 1 = load each splice slab's A tile separately even when one shifted tile could serve both;
-                          2 = share the tile, never keep it resident across N tiles; 3 = share it and keep it resident
-                          (A-stationary mode, small K on 128-wide tiles; default off, see gemm_api.cu);
-                          4 = merge the two row-shifted groups of a split-K weight gradient into one tile pass (default off) */
+                          4 = merge the two row-shifted groups of a split-K weight gradient into one tile pass (what the
+                          grouped launch does; for a single problem only on request) */
     void *debug_clock_buf; /* profiling: device int64 [grid][3 roles][8 tiles][16] clock64 stamps per warp role; NULL = off */
     /* A second split-K problem of the same shape (M, N, K, majors, groups) sharing the launch -- the two weight
      * gradients of one TDNN-F layer: tile groups [groups, 2*groups) compute A2^T * B2 into ws2[].  One launch and half
@@ -113,6 +130,7 @@ typedef struct {
     int a2_row_off[2], b2_row_off[2]; /* row offsets per group of the second problem */
     float *ws2[2];
     int ws2_ld, ws2_transposed;
+    kfp16_conv_addr conv; /* conv.mode != 0: the A operand is addressed as a convolution input (A.ptr unused) */
 } kfp16_gemm_desc;
 
 /* ---- grouped weight gradients: `count` split-K problems of the SAME shape (dW = A^T B with MN-major operands, two

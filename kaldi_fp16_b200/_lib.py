@@ -20,6 +20,14 @@ class KMat(C.Structure):
     _fields_ = [("ptr", c_void_p), ("rows", c_int), ("cols", c_int), ("ld", c_int), ("halo", c_int)]
 
 
+class ConvAddr(C.Structure):
+    """struct kfp16_conv_addr (include/kaldi_fp16_fused.h)."""
+
+    _fields_ = [("mode", c_int), ("x", c_void_p), ("T", c_int), ("H", c_int), ("P", c_int), ("C", c_int),
+                ("rows_h", c_int), ("ntaps", c_int), ("dt", c_int * 16), ("hq", c_int * 16), ("par", c_int * 16),
+                ("brow", c_int * 16)]
+
+
 class GemmDesc(C.Structure):
     """struct kfp16_gemm_desc (include/kaldi_fp16_fused.h)."""
 
@@ -42,6 +50,7 @@ class GemmDesc(C.Structure):
         ("force_bn", c_int), ("force_generic", c_int), ("force_cg", c_int), ("no_share", c_int), ("debug_clock_buf", c_void_p),
         ("A2", KMat), ("B2", KMat), ("a2_row_off", c_int * 2), ("b2_row_off", c_int * 2),
         ("ws2", c_void_p * 2), ("ws2_ld", c_int), ("ws2_transposed", c_int),
+        ("conv", ConvAddr),
     ]
 
 

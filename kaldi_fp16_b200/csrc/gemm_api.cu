@@ -21,8 +21,6 @@ std::atomic<unsigned long long> g_launches{0};
 static std::atomic<unsigned long long> g_kind_launches[EK_COUNT];   // GEMM launches per epilogue kind (tests: which bodies ran)
 void count_gemm_kind(int ek) { if (ek >= 0 && ek < EK_COUNT) g_kind_launches[ek].fetch_add(1, std::memory_order_relaxed); }
 void prefer_max_smem_carveout(const void* kern) {
-  static const bool on = [] { const char* e = getenv("KFP16_CARVEOUT"); return !(e && e[0] == '0'); }();
-  if (!on) return;
   static std::mutex mu;
   static std::unordered_map<const void*, bool> done;
   std::lock_guard<std::mutex> lk(mu);
@@ -224,15 +222,37 @@ unsigned long long kfp16_gemm_kind_launches(int kind) { return (kind >= 0 && kin
 const char* kfp16_last_error(void) { return get_error(); }
 
 // ------------------------------------------------------------------ fused GEMM
+// 4-D fp16 tensor [T][H][P][C] (C innermost), box [tbox][rows_h][1][64], 128B swizzle: the operand of an implicit-GEMM
+// convolution.  Out-of-bounds box elements (negative / past-the-end coordinates) are zero-filled = zero padding.
+static bool make_map_conv(CUtensorMap* m, const void* base, int C, int P, int H, long long T, int rows_h, int tbox, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return false; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (C % 64) != 0 || P < 1 || H < 1 || T < 1 || rows_h < 1 || rows_h > 256 || tbox < 1 || tbox > 256) {
+    set_error("%s: convolution operand needs a 16-byte aligned base, channels %% 64 == 0 (C=%d P=%d H=%d T=%lld rows_h=%d tbox=%d)", what, C, P, H, T, rows_h, tbox);
+    return false;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)H, (cuuint64_t)T};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)P * C * 2, (cuuint64_t)H * P * C * 2};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)rows_h, (cuuint32_t)tbox};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled (4-D) failed (%d)", what, (int)r); return false; }
+  return true;
+}
+
 int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if (!ctx || !d) { set_error("kfp16_gemm_ex: null argument"); return -1; }
   if (d->M <= 0 || d->N <= 0 || d->K <= 0) return 0;   // empty problem: nothing to do
+  const int conv = d->conv.mode;
+  if (conv < 0 || conv > 2) { set_error("kfp16_gemm_ex: conv.mode must be 0, 1 or 2"); return -1; }
   const int groups = d->groups < 1 ? 1 : d->groups;
-  const int kslabs = d->kslabs < 1 ? 1 : d->kslabs;
-  const int kslab_len = d->kslab_len > 0 ? d->kslab_len : d->K;
+  const int kslabs = conv ? 1 : (d->kslabs < 1 ? 1 : d->kslabs);
+  const int kslab_len = conv == 1 ? d->conv.C : (d->kslab_len > 0 && !conv ? d->kslab_len : d->K);
   if (groups > 2 || kslabs > kMaxSlabs) { set_error("kfp16_gemm_ex: at most 2 groups / 2 K-slabs"); return -1; }
   const bool two = d->A2.ptr != nullptr;    // a second split-K problem of the same shape in this launch
-  if (kslabs * kslab_len != d->K) { set_error("kfp16_gemm_ex: K (%d) != kslabs*kslab_len (%d*%d)", d->K, kslabs, kslab_len); return -1; }
+  if (!conv && kslabs * kslab_len != d->K) { set_error("kfp16_gemm_ex: K (%d) != kslabs*kslab_len (%d*%d)", d->K, kslabs, kslab_len); return -1; }
   // N is the contiguous dimension of D (and of an MN-major B); K only has to be 16-byte aligned
   // where it is some operand's contiguous dimension, which the tensor-map builder checks (ld % 8)
   if (d->N % 8) { set_error("kfp16_gemm_ex: N must be a multiple of 8 (N=%d)", d->N); return -1; }
@@ -247,33 +267,61 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   memset(&p, 0, sizeof(p));
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.groups = two ? 2 * groups : groups; p.kslabs = kslabs; p.kslab_len = kslab_len;
+  p.tile_rows = kBM;
   if (two) {
-    if (!(d->split_k > 1) || kslabs != 1 || d->a_major != KFP16_MN_MAJOR || d->b_major != KFP16_MN_MAJOR || !d->B2.ptr) {
+    if (!(d->split_k > 1) || kslabs != 1 || d->a_major != KFP16_MN_MAJOR || d->b_major != KFP16_MN_MAJOR || !d->B2.ptr || conv) {
       set_error("kfp16_gemm_ex: a second problem (A2/B2) needs split_k > 1, one K slab and MN-major operands"); return -1;
     }
     p.groups2_from = groups;
   }
 
-  if (d->split_k > 1) flags |= EPI_SPLITK;   // caller asked for fp32 accumulation into ws
+  // ---- implicit-GEMM convolution: geometry checks and the tile shape it imposes
+  int conv_tbox = 0, conv_krows = 0;
+  if (conv) {
+    const kfp16_conv_addr& c = d->conv;
+    if (!c.x || c.ntaps < 1 || c.ntaps > kMaxTaps || groups != 1 || two || c.rows_h < 1 || c.rows_h > c.H) {
+      set_error("kfp16_gemm_ex: convolution needs x, 1..%d taps, one group, 1 <= rows_h <= H", kMaxTaps); return -1;
+    }
+    for (int t = 0; t < c.ntaps; ++t)
+      if (c.dt[t] < -127 || c.dt[t] > 127 || c.hq[t] < -127 || c.hq[t] > 127 || c.par[t] < 0 || c.par[t] >= c.P) {
+        set_error("kfp16_gemm_ex: convolution tap %d out of range (dt %d hq %d par %d)", t, c.dt[t], c.hq[t], c.par[t]); return -1;
+      }
+    if (conv == 1) {
+      if (a_mn || d->M != c.T * c.rows_h || d->K != c.ntaps * c.C || d->split_k > 1 || c.rows_h > kBM) {
+        set_error("kfp16_gemm_ex: conv.mode 1 needs a K-major A, M = T*rows_h, K = ntaps*C, rows_h <= 128, no split-K"); return -1;
+      }
+      conv_tbox = kBM / c.rows_h;
+      p.tile_rows = conv_tbox * c.rows_h;
+    } else {
+      if (!a_mn || !b_mn || d->M != c.ntaps * c.C || d->K != c.T * c.rows_h || !(d->split_k >= 1)) {
+        set_error("kfp16_gemm_ex: conv.mode 2 needs MN-major operands, M = ntaps*C, K = T*rows_h"); return -1;
+      }
+      for (int tb = 80 / c.rows_h; tb >= 1; --tb)
+        if ((tb * c.rows_h) % 16 == 0) { conv_tbox = tb; break; }
+      if (!conv_tbox) { set_error("kfp16_gemm_ex: conv.mode 2: no k-block of <= 80 rows that is a multiple of 16 for %d heights", c.rows_h); return -1; }
+      conv_krows = conv_tbox * c.rows_h;
+    }
+    p.conv = conv; p.conv_h = c.rows_h; p.conv_c = c.C; p.conv_taps = c.ntaps; p.conv_tbox = conv_tbox; p.conv_k16 = conv_krows / 16;
+    for (int t = 0; t < c.ntaps; ++t) {
+      p.conv_dt[t] = (int8_t)c.dt[t]; p.conv_hq[t] = (int8_t)c.hq[t]; p.conv_par[t] = (int8_t)c.par[t]; p.conv_brow[t] = c.brow[t];
+    }
+  }
+
+  if (d->split_k > 1 || conv == 2) flags |= EPI_SPLITK;   // caller asked for fp32 accumulation into ws
   const int ek = d->force_generic ? ((flags & EPI_SPLITK) ? EK_SPLITK : EK_GENERIC) : pick_kind(flags);
   const kfp16_mat& A = d->A; const kfp16_mat& B = d->B;
-  if (!A.ptr || !B.ptr) { set_error("kfp16_gemm_ex: null operand"); return -1; }
+  if ((!conv && !A.ptr) || !B.ptr) { set_error("kfp16_gemm_ex: null operand"); return -1; }
 
   // ---- kernel shape: CTA pairs (cta_group::2, 256-row tiles: each CTA stages half of B) whenever the
-  // problem has at least two 128-row tiles, and ONE shared A tile for both splice slabs when the slabs
-  // are row-shifted views of the same columns (time splicing).  force_cg / KFP16_CG override (tests).
-  static const int env_cg = getenv("KFP16_CG") ? atoi(getenv("KFP16_CG")) : 0;
-  static const int env_share = getenv("KFP16_SHARE") ? atoi(getenv("KFP16_SHARE")) : 1;
+  // problem has at least two row tiles, and ONE shared A tile for both splice slabs when the slabs
+  // are row-shifted views of the same columns (time splicing).  force_cg overrides (tests).
   p.dbg = (long long*)d->debug_clock_buf;
-  p.mma_rep = getenv("KFP16_MMAREP") ? atoi(getenv("KFP16_MMAREP")) : 1;
-  static const int env_norot = getenv("KFP16_NOROT") ? atoi(getenv("KFP16_NOROT")) : 0;
-  p.no_rotate = env_norot;
-  int cg = d->force_cg ? d->force_cg : (env_cg ? env_cg : 2);
+  int cg = d->force_cg ? d->force_cg : 2;
   if (cg != 1 && cg != 2) { set_error("kfp16_gemm_ex: force_cg must be 0, 1 or 2"); return -1; }
-  if (d->M <= kBM) cg = 1;
+  if (d->M <= p.tile_rows) cg = 1;
   bool share = false;
   int span = 0, min_off = 0;
-  if (cg == 2 && kslabs == 2 && groups == 1 && !a_mn && !(flags & EPI_SPLITK) && env_share && d->no_share != 1 &&
+  if (!conv && cg == 2 && kslabs == 2 && groups == 1 && !a_mn && !(flags & EPI_SPLITK) && d->no_share != 1 &&
       d->a_col_off[0][0] == d->a_col_off[0][1]) {
     min_off = d->a_row_off[0][0] < d->a_row_off[0][1] ? d->a_row_off[0][0] : d->a_row_off[0][1];
     span = d->a_row_off[0][0] + d->a_row_off[0][1] - 2 * min_off;
@@ -282,14 +330,12 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if (cg == 2 && !share && !gemm_variant_exists(a_mn, b_mn, ek, 2, false)) cg = 1;
   // merged groups: the two groups of a spliced weight gradient (dW_g = sum_k A[k + a_off_g]^T B[k + b_off_g]) differ
   // only by row shifts of <= 8 -> ONE A and ONE B tile of 64+span k-rows per k-block, read through row-shifted
-  // descriptors into the two TMEM accumulator stages: half the L2->SM traffic of two separate groups
-  // Measured on the TDNN-F shapes it halves the main loop's load traffic (7.0 -> 5.2 us) but doubles the fp32
-  // reductions per unit (the L2 atomic throughput, ~3.5 TB/s, is the wall: 3.3 -> 6.7 us), so it is opt-in:
-  // d->no_share == 4 or KFP16_MERGE=1.
-  static const int env_merge = getenv("KFP16_MERGE") ? atoi(getenv("KFP16_MERGE")) : 0;
+  // descriptors into the two TMEM accumulator stages.  It pays in the grouped launch (kfp16_wgrad_group_*: one partial
+  // per element); for a single layer's gradient the doubled fp32 reductions per unit cost more than the loads saved, so
+  // here it is only taken on request (no_share == 4: the kernel's stand-alone test).
   bool merge = false;
   int ma_min = 0, mb_min = 0, ma_span = 0, mb_span = 0;
-  if (!two && cg == 2 && groups == 2 && kslabs == 1 && a_mn && b_mn && (flags & EPI_SPLITK) && (env_merge || d->no_share == 4) && d->no_share != 1 &&
+  if (!conv && !two && cg == 2 && groups == 2 && kslabs == 1 && a_mn && b_mn && (flags & EPI_SPLITK) && d->no_share == 4 &&
       d->N > 128 && d->N <= 160 && !d->force_bn &&
       d->a_col_off[0][0] == d->a_col_off[1][0] && d->b_col_off[0][0] == d->b_col_off[1][0]) {
     ma_min = d->a_row_off[0][0] < d->a_row_off[1][0] ? d->a_row_off[0][0] : d->a_row_off[1][0];
@@ -300,9 +346,10 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   }
   const int tile_groups = merge ? 1 : (two ? 2 * groups : groups);     // groups that multiply the tile count
 
-  const int tile_m = kBM * cg;
+  const int tile_m = p.tile_rows * cg;
   const int m_tiles = (d->M + tile_m - 1) / tile_m;
-  const int kb_total = (share ? 1 : kslabs) * ((kslab_len + kBK - 1) / kBK);
+  const int kb_total = conv == 2 ? (d->conv.T + conv_tbox - 1) / conv_tbox
+                                 : (conv == 1 ? d->conv.ntaps : (share ? 1 : kslabs)) * ((kslab_len + kBK - 1) / kBK);
   int split_k = d->split_k > 1 ? d->split_k : 1;
   if (merge) split_k *= 2;     // same number of work items as the two separate groups had
   if (split_k > kb_total) split_k = kb_total;
@@ -311,6 +358,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     split_k = (kb_total + per - 1) / per;
   }
   p.split_k = split_k;
+  if (conv == 1) p.kslabs = d->conv.ntaps;     // the kernel walks taps as K slabs (offsets come from the conv arrays)
 
   int ctas = ctx->num_sms;
   if (ctx->max_ctas > 0 && ctx->max_ctas < ctas) ctas = ctx->max_ctas;
@@ -318,22 +366,37 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if (units < 1) { units = 1; }
   int bn = merge ? 160 : (d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, tile_groups, split_k, units));
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) { set_error("kfp16_gemm_ex: unsupported tile width %d", bn); return -1; }
+  if (conv == 2 && bn == 160) bn = 256;
   if (!(flags & EPI_SPLITK) && (bn % 64) != 0 && d->N > bn) {
     // the last 64-wide store chunk of a 160-wide tile would spill into the next tile
     set_error("kfp16_gemm_ex: tile width %d needs N <= %d unless split-K", bn, bn); return -1;
   }
 
   // operand maps (halo rows are part of the mapped tensor so spliced reads can address them)
-  const __half* a_base = (const __half*)A.ptr - (long long)A.halo * A.ld;
   const __half* b_base = (const __half*)B.ptr - (long long)B.halo * B.ld;
-  const int a_box_rows = a_mn ? (merge ? 64 + ma_span : 64) : (share ? kBM + span : kBM);
-  if (!make_map_2d(&p.tmA, a_base, A.cols, (long long)A.rows + 2 * A.halo, A.ld, 64, a_box_rows, "A")) return -1;
-  if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? (merge ? 64 + mb_span : 64) : bn / cg, "B")) return -1;
-  for (int g = 0; g < groups; ++g)
-    for (int s = 0; s < kslabs; ++s) {
-      p.a_row_off[g][s] = d->a_row_off[g][s] + A.halo; p.a_col_off[g][s] = d->a_col_off[g][s];
-      p.b_row_off[g][s] = d->b_row_off[g][s] + B.halo; p.b_col_off[g][s] = d->b_col_off[g][s];
+  const int b_chunks = (bn / cg + 63) / 64;
+  if (conv) {
+    const kfp16_conv_addr& c = d->conv;
+    if (!make_map_conv(&p.tmA, c.x, c.C, c.P, c.H, c.T, c.rows_h, conv_tbox, "A (convolution)")) return -1;
+    if (conv == 1) {
+      if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? 64 : bn / cg, "B")) return -1;
+      p.conv_tx = p.tile_rows * 128 + (b_mn ? b_chunks * 8192 : (bn / cg) * 128);
+    } else {
+      if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, conv_krows, "B")) return -1;
+      p.conv_tx = (2 + b_chunks) * conv_krows * 128;
     }
+  } else {
+    const __half* a_base = (const __half*)A.ptr - (long long)A.halo * A.ld;
+    const int a_box_rows = a_mn ? (merge ? 64 + ma_span : 64) : (share ? kBM + span : kBM);
+    if (!make_map_2d(&p.tmA, a_base, A.cols, (long long)A.rows + 2 * A.halo, A.ld, 64, a_box_rows, "A")) return -1;
+    if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? (merge ? 64 + mb_span : 64) : bn / cg, "B")) return -1;
+    for (int g = 0; g < groups; ++g)
+      for (int s = 0; s < kslabs; ++s) {
+        p.a_row_off[g][s] = d->a_row_off[g][s] + A.halo; p.a_col_off[g][s] = d->a_col_off[g][s];
+        p.b_row_off[g][s] = d->b_row_off[g][s] + B.halo; p.b_col_off[g][s] = d->b_col_off[g][s];
+      }
+    if (share) p.a_box_bytes = a_box_rows * kBK * 2;
+  }
   if (two) {
     const kfp16_mat& A2 = d->A2; const kfp16_mat& B2 = d->B2;
     const __half* a2_base = (const __half*)A2.ptr - (long long)A2.halo * A2.ld;
@@ -353,14 +416,12 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     p.b_shift[0] = d->b_row_off[0][0] - mb_min; p.b_shift[1] = d->b_row_off[1][0] - mb_min;
     p.a_row_off[0][0] = ma_min + A.halo;
     p.b_row_off[0][0] = mb_min + B.halo;
-    const int b_chunks = (bn / cg + 63) / 64;
     p.merge_tx = 2 * (64 + ma_span) * 128 + b_chunks * (64 + mb_span) * 128;
   }
   if (share) {
     p.a_shift[0] = d->a_row_off[0][0] - min_off;
     p.a_shift[1] = d->a_row_off[0][1] - min_off;
     p.a_row_off[0][0] = min_off + A.halo;       // the one A box starts at the earlier slab's row
-    p.a_box_bytes = a_box_rows * kBK * 2;
   }
 
   p.flags = flags;
@@ -375,6 +436,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if ((flags & EPI_BN) && (!p.bn_scale || !p.bn_shift)) { set_error("kfp16_gemm_ex: EPI_BN without scale/shift"); return -1; }
   if ((flags & EPI_MASK) && !p.mask_out) { set_error("kfp16_gemm_ex: EPI_MASK without mask_out"); return -1; }
   if ((flags & EPI_GRADMASK) && !p.mask_in) { set_error("kfp16_gemm_ex: EPI_GRADMASK without mask_in"); return -1; }
+  if (conv && (flags & (EPI_RESID | EPI_BETA))) { set_error("kfp16_gemm_ex: residual / beta epilogues are not available on convolution tiles"); return -1; }
 
   if (two) {
     for (int g = 0; g < groups; ++g) {
@@ -392,7 +454,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
       p.ws[g] = d->ws[g];
     } else {
       if (!d->D[g]) { set_error("kfp16_gemm_ex: null output"); return -1; }
-      if (!make_map_2d(&p.tmD[g], d->D[g], d->N, d->M, d->ldd, 64, kBM, "D")) return -1;
+      if (!make_map_2d(&p.tmD[g], d->D[g], d->N, d->M, d->ldd, 64, p.tile_rows, "D")) return -1;
       if (flags & (EPI_RESID | EPI_BETA)) {
         if (!d->R[g]) { set_error("kfp16_gemm_ex: residual / beta requested without R"); return -1; }
         if (!make_map_2d(&p.tmR[g], d->R[g], d->N, d->M, d->ldr, 64, kBM, "R")) return -1;
@@ -409,14 +471,8 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     cudaEventRecord(ev0, ctx->stream);
   }
   bool ok = false;
-  // small-K spliced GEMMs on 128-wide tiles may keep their A tile resident (SHARE mode 2: 6 B stages of look-ahead,
-  // a third less L2->SM traffic).  Measured on the TDNN-F affine / dX shapes it is NOT faster (24.1 vs 23.4 us,
-  // 22.0 vs 20.2 us in-graph: those kernels are bound by the per-SM TMA throughput of B + residual + output), so it
-  // is opt-in: d->no_share == 3 or KFP16_ASTAT=1.
-  static const int env_astat = getenv("KFP16_ASTAT") ? atoi(getenv("KFP16_ASTAT")) : 0;
-  const bool astat = share && bn == 128 && (kslab_len + kBK - 1) / kBK <= 3 && split_k == 1 && (env_astat || d->no_share == 3) && d->no_share != 2;
   GemmLaunch L;
-  L.bn = bn; L.a_mn = a_mn; L.b_mn = b_mn; L.ek = ek; L.cg = cg; L.share = merge ? 3 : (share ? (astat ? 2 : 1) : 0); L.grid = grid;
+  L.bn = bn; L.a_mn = a_mn; L.b_mn = b_mn; L.ek = ek; L.cg = cg; L.share = conv == 2 ? 4 : (merge ? 3 : (share ? 1 : 0)); L.grid = grid;
   switch (bn) {
     case 64: ok = launch_gemm_bn<64>(ctx, p, L); break;
     case 128: ok = launch_gemm_bn<128>(ctx, p, L); break;
@@ -428,9 +484,9 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     ctx->prof_ev.push_back(ev0);
     ctx->prof_ev.push_back(ev1);
     ctx->prof_flops.push_back(2.0 * d->M * d->N * d->K * groups * (two ? 2 : 1));
-    char desc[160];
-    snprintf(desc, sizeof(desc), "M=%d N=%d K=%d g=%d slabs=%d split=%d bn=%d A%s B%s flags=0x%x ek=%d cg=%d share=%d grid=%d", d->M, d->N, d->K,
-             groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, ek, cg, L.share, grid);
+    char desc[192];
+    snprintf(desc, sizeof(desc), "M=%d N=%d K=%d g=%d slabs=%d split=%d bn=%d A%s B%s flags=0x%x ek=%d cg=%d mode=%d conv=%d grid=%d", d->M, d->N, d->K,
+             groups, kslabs, split_k, bn, a_mn ? "mn" : "k", b_mn ? "mn" : "k", flags, ek, cg, L.share, conv, grid);
     ctx->prof_desc.push_back(desc);
   }
   return ok ? 0 : -1;
@@ -448,9 +504,8 @@ kfp16_wgrad_group* kfp16_wgrad_group_create(kfp16_ctx* ctx, int M, int N, int K,
   if (M <= kBM) { set_error("kfp16_wgrad_group_create: needs M > 128 (CTA-pair tiles)"); return nullptr; }
   // merged groups (one A and one B tile of 64 + span k-rows per k-block for both groups of a problem): in a grouped
   // launch the main loop is bound by the L2->SM fabric (~6.3 KB/cycle), which the merge nearly halves; it needs the
-  // 160-wide kernel and row shifts of at most 8.  KFP16_WGRAD_MERGE=0 opts out.
-  static const bool env_wmerge = !(getenv("KFP16_WGRAD_MERGE") && atoi(getenv("KFP16_WGRAD_MERGE")) == 0);
-  bool merged = env_wmerge && N > 128 && N <= 160;
+  // 160-wide kernel and row shifts of at most 8.
+  bool merged = N > 128 && N <= 160;
   for (int i = 0; i < count && merged; ++i) {
     const int sa = abs(probs[i].a_row_off[0] - probs[i].a_row_off[1]), sb = abs(probs[i].b_row_off[0] - probs[i].b_row_off[1]);
     if (sa > 8 || sb > 8) merged = false;
@@ -503,7 +558,6 @@ kfp16_wgrad_group* kfp16_wgrad_group_create(kfp16_ctx* ctx, int M, int N, int K,
     if (cost < best_cost * 0.99) { best_cost = cost; best = sp; }
   }
   grp->split_k = best < 2 && tiles < units ? 2 : best;
-  if (const char* e = getenv("KFP16_WGRAD_SPLIT")) { if (atoi(e) > 0) grp->split_k = atoi(e); }   // experiments
   { const int per = (kb + grp->split_k - 1) / grp->split_k; grp->split_k = (kb + per - 1) / per; }
   const long long items = tiles * grp->split_k;
   grp->grid = 2 * (int)(items < units ? items : units);
@@ -526,7 +580,7 @@ int kfp16_wgrad_group_launch(kfp16_ctx* ctx, kfp16_wgrad_group* grp) {
   p.split_k = grp->split_k;
   p.flags = EPI_SPLITK;
   p.alpha = 1.0f;
-  p.mma_rep = 1;
+  p.tile_rows = kBM;
   if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ctx->profile) {

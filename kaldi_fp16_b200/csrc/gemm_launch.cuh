@@ -15,8 +15,8 @@ struct GemmLaunch {
   bool a_mn, b_mn;   // operand majors
   int ek;            // EpiKind
   int cg;            // 1 = one CTA per tile, 2 = CTA pair (cta_group::2, 256-row tiles)
-  int share;         // kernel MODE: 1 both splice slabs read one A tile; 2 and that tile stays resident (small K, BN 128);
-                     // 3 merged groups (spliced weight gradients, BN 160)
+  int share;         // kernel MODE: 1 both splice slabs read one A tile; 3 merged groups (spliced weight gradients, BN 160);
+                     // 4 convolution weight gradient
   int grid;          // CTAs (even when cg == 2)
 };
 
@@ -67,25 +67,15 @@ bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
       return false;
     }
   }
-  if constexpr (BN == 128) {
-    if (L.share == 2 && !L.a_mn) {
-      if (L.b_mn) {
-        switch (L.ek) {
-          case EK_PLAIN: KFP16_CASE(false, true, EK_PLAIN, 2, 2);
-          case EK_AFFINE: KFP16_CASE(false, true, EK_AFFINE, 2, 2);
-          case EK_AFFINE_RES: KFP16_CASE(false, true, EK_AFFINE_RES, 2, 2);
-          default: break;
-        }
-      } else {
-        switch (L.ek) {
-          case EK_PLAIN: KFP16_CASE(false, false, EK_PLAIN, 2, 2);
-          case EK_RESID: KFP16_CASE(false, false, EK_RESID, 2, 2);
-          default: break;
-        }
+  if (L.share == 4) {     // convolution weight gradient (80-row k-blocks of (time, height), 4-D boxes for A)
+    if constexpr (BN != 160) {
+      if (L.a_mn && L.b_mn && L.ek == EK_SPLITK) {
+        if (L.cg == 2) KFP16_CASE(true, true, EK_SPLITK, 2, 4);
+        KFP16_CASE(true, true, EK_SPLITK, 1, 4);
       }
-      set_error("internal: no A-stationary kernel for epilogue kind %d", L.ek);
-      return false;
     }
+    set_error("internal: the convolution weight-gradient kernel needs MN-major operands, split-K and a 64 / 128 / 256 tile");
+    return false;
   }
   if (!L.a_mn && L.b_mn) {
     if (L.share) {

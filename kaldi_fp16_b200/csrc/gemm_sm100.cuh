@@ -37,6 +37,7 @@ constexpr int kChunkBytes = kBM * 64 * 2;   // [128 x 64] fp16 staging chunk, SW
 constexpr int kVecBytes = 256 * (4 + 4 + 4);   // per-column bias, bn scale, bn shift as fp32 [256] each
 constexpr int kMaxGroups = 4;    // 2 per problem, up to two problems per launch (split-K only)
 constexpr int kMaxSlabs = 2;
+constexpr int kMaxTaps = 16;      // implicit-GEMM convolution: taps addressed by one launch
 
 enum EpiFlags : uint32_t {
   EPI_BIAS = 1u << 0,       // + bias[n] (fp16 bias row, as gpu.AddBias)
@@ -123,8 +124,17 @@ struct GemmParams {
   // loaded from row offsets a_row_off[0][0] / b_row_off[0][0]; merge_tx = bytes one CTA's loads deliver per k-block
   int b_shift[kMaxSlabs];
   int merge_tx;
-  int no_rotate;                // experiment knob: 1 = every split-K item walks its columns in the same order
-  int mma_rep;                  // experiment knob: issue every UMMA this many times (0/1 = once)
+  int tile_rows;                // rows of M one CTA tile advances by (128; a convolution tile is tbox x height <= 128 rows)
+  // ---- implicit-GEMM convolution (conv != 0): the A operand is a 4-D tensor [time][height][parity][channel] and K (conv 1)
+  // or M (conv 2) runs over (tap, channel): tap s reads the box shifted by (dt, hq) in (time, height) at parity `par`;
+  // out-of-bounds box elements are zero-filled by the TMA unit = the convolution's zero padding.  No patch matrix.
+  //   conv 1: A K-major (forward / input gradient).  M row = t * conv_h + h; k-block kb -> tap kb / (conv_c/64)
+  //   conv 2: A MN-major (weight gradient).  M row = tap * conv_c + channel; k-block = conv_tbox time steps x conv_h heights
+  int conv;
+  int conv_h, conv_c, conv_taps, conv_tbox, conv_k16;   // heights per time step, channels per tap, taps, box time steps, UMMA K steps per k-block (conv 2)
+  int conv_tx;                  // bytes one CTA's loads deliver per k-block
+  int8_t conv_dt[kMaxTaps], conv_hq[kMaxTaps], conv_par[kMaxTaps];
+  int conv_brow[kMaxTaps];      // conv 1: B row offset of tap s (MN-major B: added to the k row; K-major B: to the n row)
   long long* dbg;               // profiling: per-CTA role timestamps [grid][3 roles][8 tiles][16] (nullptr = off)
 };
 
@@ -164,36 +174,28 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&d);
 }
 
-// MODE: 0 plain; 1 shared splice tile (one A tile of 128+8 rows serves both K slabs); 2 = 1 + resident A tile;
+// MODE: 0 plain; 1 shared splice tile (one A tile of 128+8 rows serves both K slabs);
 //       3 merged groups (weight gradients of a spliced layer: both row-shifted groups read ONE A and ONE B tile of 64+8
 //         k-rows through shifted descriptors and accumulate into the two TMEM accumulator stages)
+//       4 convolution weight gradient: MN-major operands in k-blocks of up to 80 (time, height) rows, the A chunks loaded
+//         as 4-D boxes of the layer input shifted per tap
 template <int BN, bool A_MN, bool B_MN, int EK, int CG, int MODE>
 struct GemmCfg {
-  static constexpr bool SHARE = MODE == 1 || MODE == 2;
+  static constexpr bool SHARE = MODE == 1;
+  static constexpr bool kConvW = MODE == 4;
   static constexpr bool kMerge = MODE == 3;
   static_assert(CG == 1 || CG == 2, "cta_group 1 or 2");
   static_assert(!SHARE || !A_MN, "the shared splice tile is implemented for a K-major A");
-  static_assert(MODE >= 0 && MODE <= 3, "kernel mode");
+  static_assert(MODE == 0 || MODE == 1 || MODE == 3 || MODE == 4, "kernel mode");
+  static_assert(!kConvW || (A_MN && B_MN && EK == EK_SPLITK), "convolution weight gradient: MN-major operands, split-K");
   static_assert(!kMerge || (A_MN && B_MN && EK == EK_SPLITK && CG == 2), "merged groups: MN-major operands, split-K, CTA pairs");
   static constexpr bool kSplitK = EK == EK_SPLITK;
   static constexpr uint32_t kFlags = epi_kind_flags(EK);
   static constexpr bool kMayUseR = EK == EK_GENERIC || (kFlags & (EPI_RESID | EPI_BETA)) != 0;
   static constexpr bool kUsesVec = EK == EK_GENERIC || (kFlags & (EPI_BIAS | EPI_BN)) != 0;
-  // staging ring: 4 chunks when a residual tile is prefetched into it (in-place epilogue), else 2
-  // (6 when the tile is narrow enough to afford it: the residual prefetch then runs 4 chunks ahead)
-  // A-stationary (SHARE == 2, small K: the TDNN-F affine / input-gradient GEMMs with K = 2 x 160): the whole A tile
-  // (kAKb k-blocks) stays resident in shared memory while the unit walks the N tiles of one row block, and only B
-  // tiles stream through the ring -- 6 B stages = two tiles of look-ahead instead of one (the 3-stage A+B ring
-  // exposed the full load latency on every 5-k-block tile: ~3000 cycles per tile against 1280 of MMA).
-  static constexpr bool kAStat = MODE == 2;
-  static constexpr int kAKb = 3;
-#ifndef KFP16_RING128
-#define KFP16_RING128 6
-#endif
-#ifndef KFP16_ASTAT_RING
-#define KFP16_ASTAT_RING 4
-#endif
-  static constexpr int kRing = kSplitK ? 0 : (kAStat ? KFP16_ASTAT_RING : (kMayUseR ? (BN <= 160 ? (BN == 128 && SHARE ? KFP16_RING128 : 6) : 4) : 4));
+  // staging ring: 4 chunks; 6 when a residual tile is prefetched into it (in-place epilogue) and the tile is narrow enough
+  // to afford it (the residual prefetch then runs 4 chunks ahead)
+  static constexpr int kRing = kSplitK ? 0 : (kMayUseR ? (BN <= 160 ? 6 : 4) : 4);
   // TMA stores left in flight when a chunk is handed over (a store's smem-read latency is ~1000 cycles:
   // with none in flight every 64-column chunk paid it in full)
   static constexpr int kStoreWait = kRing >= 5 ? kRing - 3 : (kMayUseR ? 1 : 2);   // < kRing
@@ -202,19 +204,19 @@ struct GemmCfg {
   static constexpr int kBChunks = B_MN ? (kBNLocal + 63) / 64 : 1;   // 64-wide N chunks (MN-major)
   // SHARE: one A tile of 128+8 rows serves both splice slabs (row-shifted UMMA descriptors)
   // MN-major chunk = [k rows][64 M/N elements]: 64 k-rows, or 64+8 when the groups are merged (row-shifted reads)
-  static constexpr int kMnChunkBytes = (kMerge ? kBK + 8 : kBK) * 64 * 2;
+  static constexpr int kMnRows = kConvW ? 80 : (kMerge ? kBK + 8 : kBK);
+  static constexpr int kMnChunkBytes = kMnRows * 64 * 2;
   static constexpr int kABytes = SHARE ? (kBM + 8) * kBK * 2 : (A_MN ? 2 * kMnChunkBytes : kBM * kBK * 2);
   static constexpr int kBTileBytes = B_MN ? kBChunks * kMnChunkBytes : kBNLocal * kBK * 2;
   static constexpr int kNumBTiles = SHARE ? 2 : 1;
-  static constexpr int kStageBytes = (kAStat ? 0 : kABytes) + kNumBTiles * kBTileBytes;
-  static constexpr int kAResBytes = kAStat ? kAKb * kABytes : 0;
+  static constexpr int kStageBytes = kABytes + kNumBTiles * kBTileBytes;
   static constexpr int kEpiBytes = kRing * kChunkBytes + (kUsesVec ? 2 * kVecBytes : 0);   // vectors double-buffered
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
-  static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes - kAResBytes) / kStageBytes;
+  static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two
-  static constexpr int kSmemBytes = kAResBytes + kStages * kStageBytes + kEpiBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
   static_assert(kStages >= 2, "tile too large for shared memory");
   static_assert(kStageBytes % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N; epilogue works on 32-column halves");
@@ -222,12 +224,13 @@ struct GemmCfg {
 
 // Tile bookkeeping shared by all warp roles.  A "unit" is a CTA (CG = 1) or a CTA pair (CG = 2);
 // a tile is kBM*CG rows x BN columns and this CTA owns rows m_row0 .. m_row0+127 of it.
-template <int BN, int CG, bool CONTIG = false>
+template <int BN, int CG>
 struct TileIter {
-  int m_tiles, n_tiles, tiles_per_split, total_tiles, unit, nunits, rank;
+  int m_tiles, n_tiles, tiles_per_split, total_tiles, unit, nunits, rank, tile_rows;
   int first, last, step;   // this unit's tiles: first, first + step, ... < last
   __device__ __forceinline__ TileIter(const GemmParams& p) {
-    m_tiles = (p.M + kBM * CG - 1) / (kBM * CG);
+    tile_rows = p.tile_rows;
+    m_tiles = (p.M + tile_rows * CG - 1) / (tile_rows * CG);
     n_tiles = (p.N + BN - 1) / BN;
     tiles_per_split = m_tiles * n_tiles * p.groups;
     total_tiles = tiles_per_split * p.split_k;
@@ -235,18 +238,12 @@ struct TileIter {
     nunits = gridDim.x / CG;
     rank = CG == 2 ? (int)cluster_ctarank() : 0;
     p_groups = p.groups;
-    if (CONTIG) {   // a contiguous run of tiles (N fastest): consecutive tiles of a unit share their A row block
-      first = (int)(((long long)unit * total_tiles) / nunits);
-      last = (int)(((long long)(unit + 1) * total_tiles) / nunits);
-      step = 1;
-    } else {        // round-robin
-      first = unit; last = total_tiles; step = nunits;
-    }
+    first = unit; last = total_tiles; step = nunits;     // round-robin
   }
   __device__ __forceinline__ void decode(int tile, int& n_blk, int& m_row0, int& g, int& ks) const {
     int id = tile;
     n_blk = id % n_tiles; id /= n_tiles;
-    m_row0 = (id % m_tiles) * (kBM * CG) + rank * kBM; id /= m_tiles;
+    m_row0 = (id % m_tiles) * (tile_rows * CG) + rank * tile_rows; id /= m_tiles;
     g = id % p_groups; ks = id / p_groups;
   }
   int p_groups;
@@ -272,7 +269,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_ring = smem + Cfg::kAResBytes;     // operand stages (after the resident A tile, if any)
+  uint8_t* smem_ring = smem;                       // operand stages
   uint8_t* smem_epi = smem_ring + kStages * Cfg::kStageBytes;
   uint8_t* smem_vec = smem_epi + kRing * kChunkBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
@@ -283,9 +280,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   uint64_t* rfull_bar = tempty_bar + 2;       // [8]        residual TMA -> epilogue
   uint64_t* rempty_bar = rfull_bar + 8;       // [8]        output store drained -> residual TMA / next writer
   uint64_t* cfull_bar = rempty_bar + 8;       // [8]        epilogue warps wrote a chunk -> store warp
-  uint64_t* afull_bar = cfull_bar + 8;        // [1]        resident A tile landed (CG=2: the leader's is used)
-  uint64_t* aempty_bar = afull_bar + 1;       // [1]        MMAs on the resident A tile done (commit multicast)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -293,12 +288,14 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   const uint32_t flags = kGeneric ? p.flags : Cfg::kFlags;
   const bool use_r = Cfg::kMayUseR && (flags & (EPI_RESID | EPI_BETA)) != 0;
 
-  const TileIter<BN, CG, Cfg::kAStat> ti(p);
+  const TileIter<BN, CG> ti(p);
   const int total_tiles = ti.total_tiles;
   const int rank = ti.rank;
   const int kb_per_slab = (p.kslab_len + kBK - 1) / kBK;
   // SHARE: the slabs are consumed inside every k-block; otherwise they are laid end to end along K
-  const int kb_total = SHARE ? kb_per_slab : p.kslabs * kb_per_slab;
+  // (implicit-GEMM convolution: conv 1 has one slab of kslab_len = channels per tap; conv 2 walks the time axis in
+  //  k-blocks of conv_tbox frames, K = frames x heights)
+  const int kb_total = Cfg::kConvW ? (p.K / p.conv_h + p.conv_tbox - 1) / p.conv_tbox : (SHARE ? kb_per_slab : p.kslabs * kb_per_slab);
   const int kb_per_split = (kb_total + p.split_k - 1) / p.split_k;
 
   if (warp == 0 && lane == 0) {
@@ -314,7 +311,6 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       mbar_init(&tempty_bar[i], CG * (kEpiThreads / 32));   // one arrive per epilogue warp (of both CTAs)
     }
     for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 1); mbar_init(&cfull_bar[i], kEpiThreads / 32); }
-    mbar_init(afull_bar, CG); mbar_init(aempty_bar, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -341,10 +337,9 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     // ===================================================== TMA producer
     int stage = 0; uint32_t phase = 0;
     const uint32_t stage_tx = kMerge ? (uint32_t)p.merge_tx
-                              : Cfg::kAStat ? (uint32_t)(p.kslabs * Cfg::kBTileBytes)
+                              : p.conv ? (uint32_t)p.conv_tx
                               : SHARE ? (uint32_t)(p.a_box_bytes + p.kslabs * Cfg::kBTileBytes)
                                       : (uint32_t)(Cfg::kABytes + Cfg::kBTileBytes);
-    int a_m = -1; uint32_t a_phase = 0;   // resident A tile: row block it holds, load count parity
     int tile_i = 0;
     for (int tile = ti.first; tile < ti.last; tile += ti.step, ++tile_i) {
       int n_blk, m_row0, g, ks;
@@ -368,22 +363,15 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         __syncwarp();
       }
       dbg_stamp(p, 0, tile_i, 0);
-      if (Cfg::kAStat && m_row0 != a_m) {
-        // new row block: once the MMAs on the previous resident tile are complete, load all its k-blocks
-        a_m = m_row0;
-        mbar_wait(aempty_bar, a_phase ^ 1);
-        a_phase ^= 1;
-        if (elect_one()) {
-          const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(afull_bar), 0) : 0;
-          const uint32_t tx = (uint32_t)(kb_per_slab * p.a_box_bytes);
-          if (CG == 2) mbar_arrive_expect_tx_cluster(fb, tx);
-          else mbar_arrive_expect_tx(afull_bar, tx);
-          for (int kb = 0; kb < kb_per_slab; ++kb) {
-            if (CG == 2) tma_load_2d_pair(smem + kb * Cfg::kABytes, &p.tmA, fb, kb * kBK + p.a_col_off[g][0], m_row0 + p.a_row_off[g][0]);
-            else tma_load_2d(smem + kb * Cfg::kABytes, &p.tmA, afull_bar, kb * kBK + p.a_col_off[g][0], m_row0 + p.a_row_off[g][0]);
-          }
+      // convolution: the tile's first time step (conv 1) / the two 64-wide M chunks' (tap, first channel) (conv 2)
+      const int conv_t0 = p.conv == 1 ? m_row0 / p.conv_h : 0;
+      int cw_tap[2] = {0, 0}, cw_c0[2] = {0, 0};
+      if (Cfg::kConvW) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int m = m_row0 + c * 64;
+          cw_tap[c] = m / p.conv_c; cw_c0[c] = m - cw_tap[c] * p.conv_c;
         }
-        __syncwarp();
       }
       for (int kb = kb0; kb < kb1; ++kb) {
         const int slab = SHARE ? 0 : kb / kb_per_slab;
@@ -391,7 +379,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem_ring + stage * Cfg::kStageBytes;
-          uint8_t* sb = Cfg::kAStat ? sa : sa + Cfg::kABytes;
+          uint8_t* sb = sa + Cfg::kABytes;
           // completion is signalled on this CTA's full barrier (CG=1) or the pair leader's (CG=2)
           const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[stage]), 0) : 0;
           if (CG == 2) mbar_arrive_expect_tx_cluster(fb, tile_tx);
@@ -400,27 +388,55 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             if (CG == 2) tma_load_2d_pair(dst, m, fb, c0, c1);
             else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
           };
-          if (Cfg::kAStat) {
-            // A is resident
-          } else if (!A_MN) {
-            load(sa, mapA, k_in + p.a_col_off[g][slab], m_row0 + p.a_row_off[g][slab]);
-          } else {
+          auto load4 = [&](void* dst, const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+            if (CG == 2) tma_load_4d_pair(dst, m, fb, c0, c1, c2, c3);
+            else tma_load_4d(dst, m, &full_bar[stage], c0, c1, c2, c3);
+          };
+          if (Cfg::kConvW) {
+            // weight gradient: k-block kb = frames [kb*tbox, +tbox) x all heights; chunk c = 64 channels of tap cw_tap[c]
+            // read from the layer input shifted by that tap (a tap index past the last one addresses nothing: zeros)
+            const int t_k = kb * p.conv_tbox;
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-              load(sa + c * Cfg::kMnChunkBytes, mapA, m_row0 + c * 64 + p.a_col_off[gi][slab],
-                   k_in + (grouped ? grp_a_row : p.a_row_off[gi][slab]));
-          }
-          const int nb = SHARE ? p.kslabs : 1;
-          for (int t = 0; t < nb; ++t) {
-            const int bs = SHARE ? t : slab;
-            uint8_t* sbt = sb + t * Cfg::kBTileBytes;
-            if (!B_MN) {
-              load(sbt, mapB, k_in + p.b_col_off[g][bs], n_loc + p.b_row_off[g][bs]);
-            } else {
+            for (int c = 0; c < 2; ++c) {
+              const int tp = cw_tap[c];
+              const bool ok = tp < p.conv_taps;
+              load4(sa + c * Cfg::kMnChunkBytes, mapA, cw_c0[c], ok ? p.conv_par[tp] : 0, ok ? p.conv_hq[tp] : 0,
+                    ok ? t_k + p.conv_dt[tp] : 0x3FFFFFFF);
+            }
+#pragma unroll
+            for (int c = 0; c < Cfg::kBChunks; ++c)
+              load(sb + c * Cfg::kMnChunkBytes, mapB, n_loc + c * 64, kb * p.conv_tbox * p.conv_h);
+          } else if (!A_MN && p.conv == 1) {
+            // forward / input gradient: slab = tap; the A box [tbox frames][conv_h heights][64 channels] starts at the
+            // tile's first frame shifted by the tap; B rows (tap, channel) are contiguous
+            load4(sa, mapA, k_in, p.conv_par[slab], p.conv_hq[slab], conv_t0 + p.conv_dt[slab]);
+            if (!B_MN) load(sb, mapB, k_in, n_loc + p.conv_brow[slab]);
+            else {
 #pragma unroll
               for (int c = 0; c < Cfg::kBChunks; ++c)
-                load(sbt + c * Cfg::kMnChunkBytes, mapB, n_loc + c * 64 + p.b_col_off[gi][bs],
-                     k_in + (grouped ? grp_b_row : p.b_row_off[gi][bs]));
+                load(sb + c * Cfg::kMnChunkBytes, mapB, n_loc + c * 64, k_in + p.conv_brow[slab]);
+            }
+          } else {
+            if (!A_MN) {
+              load(sa, mapA, k_in + p.a_col_off[g][slab], m_row0 + p.a_row_off[g][slab]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+                load(sa + c * Cfg::kMnChunkBytes, mapA, m_row0 + c * 64 + p.a_col_off[gi][slab],
+                     k_in + (grouped ? grp_a_row : p.a_row_off[gi][slab]));
+            }
+            const int nb = SHARE ? p.kslabs : 1;
+            for (int t = 0; t < nb; ++t) {
+              const int bs = SHARE ? t : slab;
+              uint8_t* sbt = sb + t * Cfg::kBTileBytes;
+              if (!B_MN) {
+                load(sbt, mapB, k_in + p.b_col_off[g][bs], n_loc + p.b_row_off[g][bs]);
+              } else {
+#pragma unroll
+                for (int c = 0; c < Cfg::kBChunks; ++c)
+                  load(sbt + c * Cfg::kMnChunkBytes, mapB, n_loc + c * 64 + p.b_col_off[gi][bs],
+                       k_in + (grouped ? grp_b_row : p.b_row_off[gi][bs]));
+              }
             }
           }
         }
@@ -440,10 +456,8 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       constexpr uint32_t b_lbo = B_MN ? Cfg::kMnChunkBytes : 16, b_sbo = 1024;
       constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4;   // descriptor units (16 B) per UMMA K=16
       constexpr uint32_t b_kstep = (B_MN ? 2048 : 32) >> 4;
-      // A-stationary: A descriptors address the resident tile (k-block kb at kb * kABytes), B the ring stages
-      const uint64_t adesc0 = make_smem_desc(smem_u32(Cfg::kAStat ? smem : smem_ring), a_lbo, a_sbo, kLayoutSW128);
-      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_ring) + (Cfg::kAStat ? 0 : Cfg::kABytes), b_lbo, b_sbo, kLayoutSW128);
-      int a_m = -1; uint32_t a_phase = 0;
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem_ring), a_lbo, a_sbo, kLayoutSW128);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_ring) + Cfg::kABytes, b_lbo, b_sbo, kLayoutSW128);
       auto mma = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t accum) {
         if (CG == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum);
         else umma_f16(d_tmem, ad, bd, idesc, accum);
@@ -470,21 +484,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         tc_fence_after();
         dbg_stamp(p, 1, tile_i, 1);
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
-        bool a_last = false;     // last tile of this unit on the resident A tile -> release it after the MMAs
-        if (Cfg::kAStat) {
-          const int m_cur = (tile / ti.n_tiles) % ti.m_tiles;
-          if (m_cur != a_m) {
-            a_m = m_cur;
-            mbar_wait(afull_bar, a_phase);
-            a_phase ^= 1;
-            tc_fence_after();
-          }
-          a_last = tile + 1 >= ti.last || ((tile + 1) / ti.n_tiles) % ti.m_tiles != m_cur;
-        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const int slab = SHARE ? 0 : kb / kb_per_slab;
           const int k_in = (kb - slab * kb_per_slab) * kBK;
-          const int k16s = min(kBK, p.kslab_len - k_in + 15) >> 4;   // partial last block (K % 64)
+          const int k16s = Cfg::kConvW ? p.conv_k16 : (min(kBK, p.kslab_len - k_in + 15) >> 4);   // partial last block (K % 64)
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (kb == kb0) dbg_stamp(p, 1, tile_i, 2);
@@ -509,19 +512,17 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
               // 128-byte rows.  Measured on B200: the 128B swizzle is applied on the absolute shared-memory
               // address bits, so the descriptor's base-offset field stays 0 (setting it to the row phase,
               // as the CUTLASS comment on that field suggests for unaligned starts, gives wrong products).
-              const uint64_t ad = adesc0 + (Cfg::kAStat ? (uint64_t)((uint32_t)(kb * Cfg::kABytes) >> 4) : so) +
-                                  (SHARE ? (uint64_t)((uint32_t)p.a_shift[t] * 8u) : 0ull);
+              const uint64_t ad = adesc0 + so + (SHARE ? (uint64_t)((uint32_t)p.a_shift[t] * 8u) : 0ull);
               const uint64_t bd = bdesc0 + so + (uint64_t)((uint32_t)(t * Cfg::kBTileBytes) >> 4);
               const uint32_t first = (kb > kb0 || t > 0) ? 1u : 0u;
-              if (k16s == 4 && p.mma_rep <= 1) {
+              if (k16s == 4) {
                 mma(d_tmem, ad, bd, first);
                 mma(d_tmem, ad + a_kstep, bd + b_kstep, 1u);
                 mma(d_tmem, ad + 2 * a_kstep, bd + 2 * b_kstep, 1u);
                 mma(d_tmem, ad + 3 * a_kstep, bd + 3 * b_kstep, 1u);
               } else {
-                for (int rep = (p.mma_rep > 1 ? p.mma_rep : 1); rep > 0; --rep)
-                  for (int k = 0; k < k16s; ++k)
-                    mma(d_tmem, ad + k * a_kstep, bd + k * b_kstep, (first || k > 0 || rep < p.mma_rep) ? 1u : 0u);
+                for (int k = 0; k < k16s; ++k)
+                  mma(d_tmem, ad + k * a_kstep, bd + k * b_kstep, (first || k > 0) ? 1u : 0u);
               }
             }
             if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -535,9 +536,6 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           acc = 1;      // the bookkeeping below then flips the phase once per merged tile
         } else if (elect_one()) {
           if (CG == 2) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
-          if (Cfg::kAStat && a_last) {
-            if (CG == 2) umma_commit_pair(aempty_bar); else umma_commit(aempty_bar);
-          }
         }
         __syncwarp();
         dbg_stamp(p, 1, tile_i, 3);
@@ -672,7 +670,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         // starts its walk over the 32-column groups at a different group (rotated by its split index) so that they
         // hit different L2 lines at any one time.
         const int my_groups = hsel == 0 ? (BN / 32 + 1) / 2 : (BN / 32) / 2;
-        const int rot = p.no_rotate ? 0 : ks + (kMerge ? g : 0);
+        const int rot = ks + (kMerge ? g : 0);
 #pragma unroll 1
         for (int ci = 0; ci < my_groups; ++ci) {
           const int c = (hsel + 2 * ((ci + rot) % my_groups)) * 32;
@@ -816,7 +814,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
               ov.z = pack_f16x2(xo[4], xo[5]); ov.w = pack_f16x2(xo[6], xo[7]);
               sts128(sptr, ov);
             }
-            if ((flags & EPI_MASK) && row < p.M && n0 + c < p.N)
+            if ((flags & EPI_MASK) && row < p.M && row_in_tile < ti.tile_rows && n0 + c < p.N)
               p.mask_out[(size_t)row * p.mask_ld + ((n0 + c) >> 5)] = maskword;
           }
           fence_proxy_async_smem();

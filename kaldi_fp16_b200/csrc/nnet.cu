@@ -98,6 +98,7 @@ struct Layer {
   int hin = 0, hout = 0, hsub = 1, fin = 0, fout = 0, convK = 0, convKp = 0;
   __half* convP = nullptr;   // this layer's patch matrix: kept from the forward pass for the weight gradient (train mode)
   std::vector<int> tap_dt, tap_dh;
+  bool conv_implicit = false;   // implicit GEMM over 4-D TMA boxes (no patch matrix); else im2col + GEMM + col2im
   int grads_seen = 0;
 };
 
@@ -124,16 +125,9 @@ struct kfp16_net {
   std::vector<void*> allocs;
   __half *conv_P = nullptr, *conv_dP = nullptr, *conv_dz = nullptr;   // shared conv scratch (patches, patch grads, dZ)
   size_t conv_P_elems = 0, conv_dz_elems = 0;
-  // weight-gradient GEMMs are off the backward critical path (they only feed the gradient bucket): they run on a
-  // low-priority side stream, forked / joined with events, and fill the SMs the narrow dgrad GEMMs leave idle
-  cudaStream_t side = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D prefetch of the next minibatch (kfp16_net_prefetch_input)
   cudaStream_t copy_extra[3] = {nullptr, nullptr, nullptr};   // large inputs are copied in 4 parts on 4 streams (one DMA
   cudaEvent_t copy_part[3] = {nullptr, nullptr, nullptr};      // engine each: a single stream does not saturate the host link)
-  std::vector<cudaEvent_t> ev_pool;
-  size_t ev_next = 0;
-  cudaEvent_t ev_join = nullptr;
-  bool side_used = false;
   __half* stage_in = nullptr;   // dense staging for host uploads / downloads
   size_t stage_bytes = 0;
   double flops_fwd = 0;
@@ -454,6 +448,7 @@ bool resolve_dims(kfp16_net* n) {
         }
         if (l.tap_dt.size() > 32) { set_error("conv-relu-batchnorm-layer %s: more than 32 taps", l.name.c_str()); return false; }
         for (int dt : l.tap_dt) if (abs(dt) >= n->opts.seq_len) { set_error("conv layer %s: time offset %d exceeds the sequence length", l.name.c_str(), dt); return false; }
+        for (int dt : l.tap_dt) max_halo = std::max(max_halo, abs(dt));   // zero-padded halo rows keep the sequences apart
         l.convK = (int)l.tap_dt.size() * l.fin;
         l.convKp = (l.convK + 15) & ~15;
         l.out_dim = l.hout * l.fout;
@@ -491,6 +486,21 @@ bool resolve_dims(kfp16_net* n) {
   for (auto& c : n->layers) {
     if (c.type == L_TDNNF && c.stride > 0)
       for (int src : c.in) n->layers[src].halo_mode = HALO_REPL;
+  }
+  // Convolutions run as implicit GEMMs (taps = shifted 4-D TMA boxes of the layer input, zero-filled outside it) when the
+  // geometry allows: 64-channel multiples on both sides, height subsampling 1 or 2, <= 16 taps, and a producer whose halo
+  // rows can be kept at zero (the per-sequence zero padding in time).  Anything else (the first layer's 6 input filters)
+  // gathers a patch matrix on the device and runs the same GEMM on it.
+  static const bool force_im2col = getenv("KFP16_CONV_IM2COL") && atoi(getenv("KFP16_CONV_IM2COL")) != 0;   // A/B measurements
+  for (auto& c : n->layers) {
+    if (c.type != L_CONV) continue;
+    bool kblock = false;
+    for (int tb = 80 / std::max(1, c.hout); tb >= 1; --tb) kblock = kblock || (tb * c.hout) % 16 == 0;
+    const bool geom = (c.hsub == 1 ? c.hin == c.hout : (c.hsub == 2 && c.hin == 2 * c.hout));
+    Layer& src = n->layers[c.in[0]];
+    c.conv_implicit = !force_im2col && c.in.size() == 1 && (c.fin % 64) == 0 && (c.fout % 64) == 0 && geom && c.hout <= 128 && kblock &&
+                      c.tap_dt.size() <= 16 && src.halo_mode != HALO_REPL && !src.per_seq;
+    if (c.conv_implicit) src.halo_mode = HALO_ZERO;
   }
   // output layer + gradient reachability (Backward seeds only the chain output, network_backward.go:104-107)
   n->out_layer = find_layer(n, "output");
@@ -681,8 +691,10 @@ bool build_plan(kfp16_net* n) {
         if (!dev_alloc(n, (void**)&l.mask, mrows * l.mask_ld * 4)) return false;
         // training keeps every layer's patch matrix resident between forward and backward (1.8 GB for the cnn_tdnn_1a
         // front end: HBM is 180 GB) instead of gathering it a second time; inference shares one scratch buffer
-        if (train) { if (!dev_alloc(n, (void**)&l.convP, mrows * l.convKp * 2, false)) return false; }
-        n->conv_P_elems = std::max(n->conv_P_elems, mrows * l.convKp);
+        if (!l.conv_implicit) {
+          if (train) { if (!dev_alloc(n, (void**)&l.convP, mrows * l.convKp * 2, false)) return false; }
+          n->conv_P_elems = std::max(n->conv_P_elems, mrows * l.convKp);
+        }
         n->conv_dz_elems = std::max(n->conv_dz_elems, mrows * l.fout);
         n->flops_fwd += 2.0 * M * l.hout * l.convK * l.fout;
         if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * l.hout * l.convK * l.fout;
@@ -693,11 +705,9 @@ bool build_plan(kfp16_net* n) {
   }
   if (n->conv_P_elems) {
     if (!train && !dev_alloc(n, (void**)&n->conv_P, n->conv_P_elems * 2, false)) return false;
-    if (train) {
-      if (!dev_alloc(n, (void**)&n->conv_dP, n->conv_P_elems * 2, false)) return false;
-      if (!dev_alloc(n, (void**)&n->conv_dz, n->conv_dz_elems * 2, false)) return false;
-    }
+    if (train && !dev_alloc(n, (void**)&n->conv_dP, n->conv_P_elems * 2, false)) return false;
   }
+  if (train && n->conv_dz_elems && !dev_alloc(n, (void**)&n->conv_dz, n->conv_dz_elems * 2, false)) return false;
   n->stage_bytes = max_dense;
   if (!dev_alloc(n, (void**)&n->stage_in, n->stage_bytes)) return false;
   return check_cuda(cudaStreamSynchronize(n->ctx->stream), "plan sync");
@@ -716,6 +726,23 @@ kfp16_gemm_desc mk_desc(int M, int N, int K) {
 }
 void set_A(kfp16_gemm_desc& d, const void* p, int rows, int cols) { d.A.ptr = p; d.A.rows = rows; d.A.cols = cols; d.A.ld = cols; d.A.halo = 0; }
 void set_B(kfp16_gemm_desc& d, const void* p, int rows, int cols) { d.B.ptr = p; d.B.rows = rows; d.B.cols = cols; d.B.ld = cols; d.B.halo = 0; }
+
+// tap list of a conv layer as implicit-GEMM addressing of its input x[Tp][hin][fin] (height subsampling 2 = parity planes)
+void conv_fwd_addr(const kfp16_net* n, const Layer& l, const void* x, int mode, kfp16_conv_addr& c) {
+  memset(&c, 0, sizeof(c));
+  c.mode = mode; c.x = x;
+  c.T = n->Tp; c.P = l.hsub; c.H = l.hin / l.hsub; c.C = l.fin;
+  c.rows_h = l.hout;
+  c.ntaps = (int)l.tap_dt.size();
+  for (int t = 0; t < c.ntaps; ++t) {
+    const int dh = l.tap_dh[t];
+    const int par = l.hsub == 2 ? ((dh % 2) + 2) % 2 : 0;
+    c.dt[t] = l.tap_dt[t];
+    c.par[t] = par;
+    c.hq[t] = l.hsub == 2 ? (dh - par) / 2 : dh;
+    c.brow[t] = t * l.fin;
+  }
+}
 
 int pick_split_k(const kfp16_net* n, int M, int N, int groups, int K) {
   // work items = tiles * splits should fill ONE wave of CTA pairs (256-row tiles) as evenly as possible:
@@ -786,14 +813,13 @@ static bool wgrad_fill(kfp16_net* n, const WgradArgs& a, kfp16_mat& A, kfp16_mat
   return true;
 }
 int wgrad2(kfp16_net* n, const WgradArgs& w1, const WgradArgs& w2) {
-  static const bool fuse = !(getenv("KFP16_WGRAD2") && atoi(getenv("KFP16_WGRAD2")) == 0);
   kfp16_gemm_desc d;
   int M1, N1, M2, N2, a1[2], b1[2], a2[2], b2[2], ld1, ld2, t1, t2;
   float *ws1[2], *ws2[2];
   memset(&d, 0, sizeof(d));
   wgrad_fill(n, w1, d.A, d.B, a1, b1, ws1, ld1, t1, M1, N1);
   wgrad_fill(n, w2, d.A2, d.B2, a2, b2, ws2, ld2, t2, M2, N2);
-  if (!fuse || n->side || M1 != M2 || N1 != N2 || w1.X->rows != w2.X->rows || w1.groups != 2 || w2.groups != 2) {
+  if (M1 != M2 || N1 != N2 || w1.X->rows != w2.X->rows || w1.groups != 2 || w2.groups != 2) {
     if (wgrad(n, *w1.X, *w1.dY, w1.param, w1.groups, w1.off0, w1.off1)) return -1;
     return wgrad(n, *w2.X, *w2.dY, w2.param, w2.groups, w2.off0, w2.off1);
   }
@@ -816,14 +842,13 @@ int wgrad2(kfp16_net* n, const WgradArgs& w1, const WgradArgs& w2) {
 // current graph segment): all TDNN-F layers of a stack have the same gradient shape, so the whole set runs as ONE
 // persistent split-K kernel (kfp16_wgrad_group_*).  Falls back to the per-layer launch when shapes differ.
 int defer_wgrads(kfp16_net* n, const WgradArgs& w1, const WgradArgs& w2) {
-  static const bool grouping = !(getenv("KFP16_WGRAD_GROUP") && atoi(getenv("KFP16_WGRAD_GROUP")) == 0);
   auto dims = [&](const WgradArgs& a, int& M, int& N) {
     kfp16_mat A, B; int ao[2], bo[2], ld, tr; float* ws[2];
     wgrad_fill(n, a, A, B, ao, bo, ws, ld, tr, M, N);
   };
   int M1, N1, M2, N2;
   dims(w1, M1, N1); dims(w2, M2, N2);
-  bool ok = grouping && !n->side && M1 == M2 && N1 == N2 && M1 > 128 && w1.groups == 2 && w2.groups == 2 && w1.X->rows == w2.X->rows;
+  bool ok = M1 == M2 && N1 == N2 && M1 > 128 && w1.groups == 2 && w2.groups == 2 && w1.X->rows == w2.X->rows;
   if (ok && !n->deferred.empty()) {
     int M0, N0;
     dims(n->deferred[0], M0, N0);
@@ -854,25 +879,6 @@ int flush_wgrads(kfp16_net* n) {
     it = n->wg_groups.emplace(key, g).first;
   }
   return kfp16_wgrad_group_launch(n->ctx, it->second);
-}
-
-// same, launched on the side stream after everything issued so far on the main stream
-int wgrad_async(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int off0, int off1) {
-  if (!n->side) return wgrad(n, X, dY, param, groups, off0, off1);
-  if (n->ev_next == n->ev_pool.size()) {
-    cudaEvent_t e = nullptr;
-    if (!check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate (wgrad fork)")) return -1;
-    n->ev_pool.push_back(e);
-  }
-  cudaEvent_t ev = n->ev_pool[n->ev_next++];
-  cudaStream_t main_stream = n->ctx->stream;
-  if (!check_cuda(cudaEventRecord(ev, main_stream), "wgrad fork record") ||
-      !check_cuda(cudaStreamWaitEvent(n->side, ev, 0), "wgrad fork wait")) return -1;
-  n->ctx->stream = n->side;
-  const int rc = wgrad(n, X, dY, param, groups, off0, off1);
-  n->ctx->stream = main_stream;
-  n->side_used = true;
-  return rc;
 }
 
 // route a freshly computed input-gradient into the producer(s) of layer l
@@ -1017,11 +1023,15 @@ int forward_layer(kfp16_net* n, Layer& l) {
     }
     case L_CONV: {       // forward.go:418-524 with the im2col on the device; Z = BN(ReLU(P*W + b)) per filter
       const int mrows = rows * l.hout;
-      __half* P = l.convP ? l.convP : n->conv_P;
-      if (kfp16_im2col(ctx, X.p, P, l.convKp, n->opts.n_seq, n->opts.seq_len, n->halo, l.hin, l.hout, l.hsub, l.fin,
-                       (int)l.tap_dt.size(), l.tap_dt.data(), l.tap_dh.data())) return -1;
-      kfp16_gemm_desc d = mk_desc(mrows, l.fout, l.convKp);
-      set_A(d, P, mrows, l.convKp);
+      kfp16_gemm_desc d = mk_desc(mrows, l.fout, l.conv_implicit ? l.convK : l.convKp);
+      if (l.conv_implicit) {   // taps = shifted 4-D boxes of X (its halo rows are zero: per-sequence zero padding)
+        conv_fwd_addr(n, l, X.p, 1, d.conv);
+      } else {
+        __half* P = l.convP ? l.convP : n->conv_P;
+        if (kfp16_im2col(ctx, X.p, P, l.convKp, n->opts.n_seq, n->opts.seq_len, n->halo, l.hin, l.hout, l.hsub, l.fin,
+                         (int)l.tap_dt.size(), l.tap_dt.data(), l.tap_dh.data())) return -1;
+        set_A(d, P, mrows, l.convKp);
+      }
       set_B(d, W16(n, l.pW), l.convK, l.fout);          // rows [convK, convKp) read as zeros (TMA bounds)
       d.D[0] = l.out.p; d.ldd = l.fout;
       d.flags = KFP16_EPI_BIAS | KFP16_EPI_RELU | KFP16_EPI_BN | KFP16_EPI_MASK | rr;
@@ -1054,11 +1064,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
   if (!l.needs_grad || l.type == L_INPUT) return 0;
   const int rows = l.per_seq ? n->opts.n_seq : n->Tp;
   // adjoint of the halo fix-up applied to this layer's output in the forward pass
-  // the dZ pass can fold the halo rows itself (kfp16_bn_relu_backward_bias_fold); measured, the separate 2.5 us fold
-  // launch + the plain pass (copy speed) is faster than the fused pass (its edge rows serialise a block): opt-in
-  static const bool env_fused_fold = getenv("KFP16_FUSED_FOLD") && atoi(getenv("KFP16_FUSED_FOLD")) != 0;
-  const bool fused_fold = env_fused_fold && l.type == L_TDNNF && !l.per_seq && n->halo > 0 && l.halo_mode == HALO_REPL;
-  if (!l.per_seq && n->halo > 0 && !fused_fold) {
+  if (!l.per_seq && n->halo > 0) {
     if (l.halo_mode == HALO_REPL && kfp16_fold_edges(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
     if (l.halo_mode == HALO_ZERO && kfp16_zero_halo(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
   }
@@ -1076,7 +1082,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
         d.D[0] = dx.p; d.ldd = l.in_dim;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (l.type == L_LINEAR && wgrad_async(n, X, l.dout, l.pW, 1, 0, 0)) return -1;   // backward_ops.go:195-225
+      if (l.type == L_LINEAR && wgrad(n, X, l.dout, l.pW, 1, 0, 0)) return -1;   // backward_ops.go:195-225
       break;
     }
     case L_BATCHNORM:   // dX = dY * gamma/sqrt(var+eps)  (backward_wrappers.cu:104-115)
@@ -1094,15 +1100,10 @@ int backward_layer(kfp16_net* n, Layer& l) {
     case L_TDNNF: {
       const int s = l.stride, sp = s > 0 ? 2 : 1;
       // dZ = mask ? h(dY * bn_scale) : 0 ; db += colsum(dZ)
-      if (fused_fold) {
-        if (kfp16_bn_relu_backward_bias_fold(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim,
-                                             n->opts.n_seq, n->opts.seq_len, n->halo, l.out_dim, G32(n, l.pAffB))) return -1;
-      } else if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim, rows, l.out_dim, G32(n, l.pAffB))) return -1;
-      // dWaff = [B(t) | B(t+s)]^T * dZ: forked onto the side stream BEFORE the narrow dB GEMM below, whose 78 CTAs
-      // leave the other SMs free for it
-      // with a splice both weight gradients of the layer share one launch after dB is known (wgrad2 below)
-      const bool both = sp == 2 && !n->side;
-      if (!both && wgrad_async(n, l.bott, l.dz, l.pAff, sp, 0, s)) return -1;
+      if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim, rows, l.out_dim, G32(n, l.pAffB))) return -1;
+      // with a splice both weight gradients of the layer are deferred to the grouped launch at the end of the pass
+      const bool both = sp == 2;
+      if (!both && wgrad(n, l.bott, l.dz, l.pAff, sp, 0, s)) return -1;
       {  // dB(r) = dZ(r)*Waff[0:bn]^T + dZ(r-s)*Waff[bn:2bn]^T
         kfp16_gemm_desc d = mk_desc(rows, l.bott_dim, sp * l.out_dim);
         set_A(d, l.dz.p, rows, l.out_dim);
@@ -1114,11 +1115,11 @@ int backward_layer(kfp16_net* n, Layer& l) {
         if (kfp16_gemm_ex(ctx, &d)) return -1;
         if (s > 0 && kfp16_fold_edges(ctx, l.dbott.p, l.bott_dim, n->opts.n_seq, n->opts.seq_len, l.bott_dim, n->halo)) return -1;
       }
-      // dWlin = [X(t-s) | X(t)]^T * dB (side stream, concurrent with the input-gradient GEMM)
+      // dWlin = [X(t-s) | X(t)]^T * dB
       if (both) {
         const WgradArgs wa{&l.bott, &l.dz, l.pAff, sp, 0, s}, wl{&X, &l.dbott, l.pLin, sp, -s, 0};
         if (defer_wgrads(n, wa, wl)) return -1;
-      } else if (wgrad_async(n, X, l.dbott, l.pLin, sp, -s, 0)) return -1;
+      } else if (wgrad(n, X, l.dbott, l.pLin, sp, -s, 0)) return -1;
       if (l.wants_dx) {   // dX(r) = dB(r+s)*Wlin[0:in]^T + dB(r)*Wlin[in:2in]^T (+ bypass*dY)
         kfp16_gemm_desc d = mk_desc(rows, l.in_dim, sp * l.bott_dim);
         set_A(d, l.dbott.p, rows, l.bott_dim);
@@ -1146,7 +1147,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
         d.mask_in = l.mask; d.mask_ld = l.mask_ld;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (wgrad_async(n, l.big, l.dys, l.pSmall, 1, 0, 0)) return -1;
+      if (wgrad(n, l.big, l.dys, l.pSmall, 1, 0, 0)) return -1;
       if (kfp16_colsum_accum(ctx, l.dbig.p, l.big_dim, rows, l.big_dim, G32(n, l.pBigB))) return -1;
       if (l.wants_dx) {
         kfp16_gemm_desc d = mk_desc(rows, l.in_dim, l.big_dim);
@@ -1156,13 +1157,59 @@ int backward_layer(kfp16_net* n, Layer& l) {
         d.D[0] = dx.p; d.ldd = l.in_dim;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (wgrad_async(n, X, l.dbig, l.pBig, 1, 0, 0)) return -1;
+      if (wgrad(n, X, l.dbig, l.pBig, 1, 0, 0)) return -1;
       break;
     }
     case L_CONV: {     // transpose of the forward (the reference treats the conv as a dense affine: quirk Q2)
       const int mrows = rows * l.hout;
+      // gradients on halo rows are not part of the minibatch: zero them so that neither the weight gradient (a sum over
+      // ALL padded rows) nor the input gradient of neighbouring real frames sees them
+      if (n->halo > 0 && l.halo_mode == HALO_NONE && kfp16_zero_halo(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
       if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.fout, l.bn.scale, l.mask, l.mask_ld, n->conv_dz, l.fout, mrows, l.fout, G32(n, l.pB))) return -1;
-      // the patch matrix of the forward pass is still resident (l.convP)
+      if (l.conv_implicit) {
+        {  // dW[(tap, f), fo] = sum over (t, h) of X[t+dt, h*sub+dh, f] * dZ[(t, h), fo]
+          kfp16_gemm_desc d = mk_desc(l.convK, l.fout, mrows);
+          d.a_major = KFP16_MN_MAJOR;
+          conv_fwd_addr(n, l, X.p, 2, d.conv);
+          set_B(d, n->conv_dz, mrows, l.fout);
+          d.split_k = pick_split_k(n, l.convK, l.fout, 1, mrows);
+          d.ws[0] = G32(n, l.pW); d.ws_ld = l.fout;
+          if (kfp16_gemm_ex(ctx, &d)) return -1;
+        }
+        if (l.wants_dx) {
+          // dX[t, hi, f] = sum over taps of dZ[t-dt, (hi-dh)/sub, :] * W[(tap, f), :]^T: again a convolution, of dZ with the
+          // mirrored taps; with height subsampling 2 the even and the odd input heights take different tap subsets and are
+          // written as two interleaved row sets of dX
+          for (int par = 0; par < l.hsub; ++par) {
+            kfp16_gemm_desc d = mk_desc(rows * l.hout, l.fin, 0);
+            kfp16_conv_addr& c = d.conv;
+            c.mode = 1; c.x = n->conv_dz;
+            c.T = rows; c.H = l.hout; c.P = 1; c.C = l.fout; c.rows_h = l.hout;
+            for (size_t t = 0; t < l.tap_dt.size(); ++t) {
+              const int dh = l.tap_dh[t];
+              if (((par - dh) % l.hsub) != 0) continue;
+              c.dt[c.ntaps] = -l.tap_dt[t];
+              c.hq[c.ntaps] = (par - dh) / l.hsub;
+              c.par[c.ntaps] = 0;
+              c.brow[c.ntaps] = (int)t * l.fin;
+              ++c.ntaps;
+            }
+            __half* dst = dx.p + (size_t)par * l.fin;
+            const int ldd = l.hsub * l.fin;
+            if (c.ntaps == 0) {   // no tap reaches this height parity
+              if (!check_cuda(cudaMemset2DAsync(dst, (size_t)ldd * 2, 0, (size_t)l.fin * 2, (size_t)rows * l.hout, ctx->stream), "conv input-gradient clear")) return -1;
+              continue;
+            }
+            d.K = c.ntaps * l.fout; d.kslab_len = d.K;
+            d.b_major = KFP16_K_MAJOR;
+            set_B(d, W16(n, l.pW), l.convK, l.fout);
+            d.D[0] = dst; d.ldd = ldd;
+            if (kfp16_gemm_ex(ctx, &d)) return -1;
+          }
+        }
+        break;
+      }
+      // patch-matrix path: the patch matrix of the forward pass is still resident (l.convP)
       {  // dW[K x fout] = P^T dZ
         kfp16_gemm_desc d = mk_desc(l.convK, l.fout, mrows);
         d.a_major = KFP16_MN_MAJOR;
@@ -1193,7 +1240,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
         d.D[0] = dx.p; d.ldd = l.in_dim;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (wgrad_async(n, X, l.dout, l.pW, 1, 0, 0)) return -1;
+      if (wgrad(n, X, l.dout, l.pW, 1, 0, 0)) return -1;
       if (kfp16_colsum_accum(ctx, l.dout.p, l.out_dim, rows, l.out_dim, G32(n, l.pB))) return -1;
       break;
     }
@@ -1242,18 +1289,6 @@ kfp16_net* kfp16_net_create(kfp16_ctx* ctx, const char* xconfig, const kfp16_net
     set_error("%s", msg);
     return nullptr;
   }
-  // (opt-in: measured on the TDNN-F stack the fork gives no gain -- 2.38 ms/step with and without -- the wgrad and
-  //  dgrad kernels contend for the same L2->SM bandwidth rather than for SMs)
-  if (opts->train && getenv("KFP16_SIDE_STREAM")) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);    // lo = least priority (numerically largest)
-    const int prio = atoi(getenv("KFP16_SIDE_STREAM")) == 2 ? hi : lo;   // 1: lowest priority, 2: highest
-    if (!check_cuda(cudaStreamCreateWithPriority(&n->side, cudaStreamNonBlocking, prio), "side stream") ||
-        !check_cuda(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming), "join event")) {
-      kfp16_net_destroy(n.release());
-      return nullptr;
-    }
-  }
   if (kfp16_net_init_random(n.get(), 42) != 0) { kfp16_net_destroy(n.release()); return nullptr; }
   return n.release();
 }
@@ -1274,9 +1309,6 @@ void kfp16_net_destroy(kfp16_net* n) {
   for (cudaGraphExec_t g : n->seg_graph) if (g) cudaGraphExecDestroy(g);
   if (n->loss_pinned) cudaFreeHost(n->loss_pinned);
   for (cudaEvent_t e : n->loss_ev) if (e) cudaEventDestroy(e);
-  for (cudaEvent_t e : n->ev_pool) cudaEventDestroy(e);
-  if (n->ev_join) cudaEventDestroy(n->ev_join);
-  if (n->side) cudaStreamDestroy(n->side);
   delete n;
 }
 
@@ -1579,7 +1611,6 @@ static int backward_range(kfp16_net* n, int hi, int lo, bool begin) {
   if (begin) {
     for (auto& l : n->layers) l.grads_seen = 0;
     n->layers[n->out_layer].grads_seen = 1;
-    n->ev_next = 0;
   }
   for (int i = hi - 1; i >= lo; --i) {
     Layer& l = n->layers[i];
@@ -1594,11 +1625,6 @@ int kfp16_net_backward(kfp16_net* n) {
   if (!n || !n->g32) { set_error("kfp16_net_backward: network was created with train = 0"); return -1; }
   if (backward_range(n, (int)n->layers.size(), 0, true)) return -1;
   if (flush_wgrads(n)) return -1;
-  if (n->side_used) {   // join: the gradient bucket is complete only when the side stream has drained
-    if (!check_cuda(cudaEventRecord(n->ev_join, n->side), "wgrad join record") ||
-        !check_cuda(cudaStreamWaitEvent(n->ctx->stream, n->ev_join, 0), "wgrad join wait")) return -1;
-    n->side_used = false;
-  }
   return 0;
 }
 
@@ -1749,7 +1775,6 @@ static int run_segment(kfp16_net* n, int seg) {
 int kfp16_net_capture_segments_ex(kfp16_net* n, int nseg, const char* cut_layers, int export_f16, int tail_max_ctas) {
   if (!n || !n->g32 || nseg < 1) { set_error("kfp16_net_capture_segments: needs a training network and nseg >= 1"); return -1; }
   if (!n->ctx->stream) { set_error("kfp16_net_capture_segments: graph capture needs a non-default stream"); return -1; }
-  if (n->side) { set_error("kfp16_net_capture_segments: not available with the weight-gradient side stream"); return -1; }
   const int L = (int)n->layers.size();
   std::vector<size_t> first(L + 1, n->bucket);
   for (int i = L - 1; i >= 0; --i) {

@@ -319,48 +319,155 @@ def test_split_k_transposed_target(handle, lib, M, N, K, groups):
         assert_close(got[g], want, 2.0 ** -19 * absprod + 1e-6, f"transposed split-K group {g}")
 
 
-@pytest.mark.parametrize("max_ctas", [0, 6, 10])
-@pytest.mark.parametrize("T,D,N,s0,s1,b_k_major,resid", [(900, 160, 512, 0, 3, False, True), (2100, 160, 1536, 3, 0, True, True),
-                                                         (1300, 128, 384, -3, 0, False, False), (9984, 160, 1536, 0, 3, False, True)])
-def test_a_stationary_spliced_gemm(handle, lib, max_ctas, T, D, N, s0, s1, b_k_major, resid):
-    """small-K spliced GEMMs (the TDNN-F affine / input-gradient shapes, K = 2 x 160) keep their A tile resident in
-    shared memory while a CTA pair walks a contiguous run of N tiles: same result as the streaming shared-tile kernel
-    (no_share = 2) and the oracle, also when a unit's run crosses row blocks (few CTAs) and with the bypass epilogue"""
-    halo = 3
-    rng = np.random.default_rng(T + D + N)
-    X = rand_f16(rng, (T, D))
-    W = rand_f16(rng, (2 * D, N), 0.08)
-    R = rand_f16(rng, (T, N))
-    Xp = np.concatenate([np.repeat(X[:1], halo, 0), X, np.repeat(X[-1:], halo, 0)], 0)
-    i0, i1 = np.clip(np.arange(T) + s0, 0, T - 1), np.clip(np.arange(T) + s1, 0, T - 1)
-    S = np.concatenate([X[i0], X[i1]], 1)
-    acc = S.astype(np.float64) @ W.astype(np.float64)
-    want = acc + (0.66 * R if resid else 0.0)
-    tXp, tR = gpu.TensorFromFP16(Xp), gpu.TensorFromFP16(R)
-    Bst = np.concatenate([W[:D].T, W[D:].T], 0) if b_k_major else W
-    tW = gpu.TensorFromFP16(np.ascontiguousarray(Bst))
+# ---------------------------------------------------------------- implicit-GEMM convolution (kfp16_conv_addr)
+def conv_ref_patches(x4, hout, sub, taps):
+    """P[(t*hout+ho), tap*C+c] = x[t+dt, ho*sub+dh, c], zero outside (internal/nnet/forward.go:429-455) -- float64"""
+    T, H, C = x4.shape
+    P = np.zeros((T, hout, len(taps), C), np.float64)
+    for k, (dt, dh) in enumerate(taps):
+        for ho in range(hout):
+            hs = ho * sub + dh
+            if hs < 0 or hs >= H:
+                continue
+            t0, t1 = max(0, -dt), min(T, T - dt)
+            P[t0:t1, ho, k, :] = x4[t0 + dt:t1 + dt, hs, :]
+    return P.reshape(T * hout, len(taps) * C)
+
+
+def conv_addr(d, mode, x_t, T, H, P, C, rows_h, taps_addr):
+    c = d.conv
+    c.mode, c.x, c.T, c.H, c.P, c.C, c.rows_h, c.ntaps = mode, x_t.Ptr, T, H, P, C, rows_h, len(taps_addr)
+    for i, (dt, hq, par, brow) in enumerate(taps_addr):
+        c.dt[i], c.hq[i], c.par[i], c.brow[i] = dt, hq, par, brow
+
+
+TAPS9 = [(dt, dh) for dt in (-1, 0, 1) for dh in (-1, 0, 1)]
+
+
+@pytest.mark.parametrize("max_ctas", [0, 6])
+@pytest.mark.parametrize("T,hin,sub,C,N,taps", [
+    (300, 40, 1, 64, 64, TAPS9),        # 3 frames x 40 heights = 120-row tiles (the benchmark's cnn2 geometry)
+    (190, 40, 2, 64, 128, TAPS9),       # height subsampling: parity planes of the input (cnn3)
+    (156, 10, 1, 256, 256, TAPS9),      # 12 x 10 rows, 4 k-blocks per tap (cnn6)
+    (97, 8, 1, 128, 64, [(-2, 0), (0, 1), (3, -1)]),   # 16 x 8 = full 128-row tiles, ragged T, irregular taps
+    (40, 16, 2, 64, 72, [(0, 0), (1, 1)]),             # N not a tile multiple; the odd parity plane only via dh = 1
+])
+def test_implicit_conv_forward_gemm(handle, lib, max_ctas, T, hin, sub, C, N, taps):
+    """conv.mode 1: Y[(t,h), n] = sum_taps x[t+dt, h*sub+dh, :] W[tap] with bias+ReLU+BN+mask epilogue, no patch matrix"""
+    hout = hin // sub
+    rng = np.random.default_rng(T * hin + C + N)
+    x = rand_f16(rng, (T, hin, C))
+    W = rand_f16(rng, (len(taps) * C, N), 0.05)
+    bias = rand_f16(rng, (1, N), 0.1)
+    scale = (rng.random(N) + 0.5).astype(np.float32)
+    shift = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    Pm = conv_ref_patches(x.astype(np.float64), hout, sub, taps)
+    z = np.maximum(Pm @ W.astype(np.float64) + bias, 0.0)
+    want = z * scale + shift
+    tx, tW, tb = gpu.TensorFromFP16(x.reshape(T, hin * C)), gpu.TensorFromFP16(W), gpu.TensorFromFP16(bias)
+    tD = gpu.ZeroTensor(T * hout, N)
+    tsc, tsh = gpu.DeviceF32(scale), gpu.DeviceF32(shift)
+    mask_ld = (N + 31) // 32
+    tmask = gpu.DeviceF32(n=T * hout * mask_ld)
+    d = make_desc(T * hout, N, len(taps) * C, tx, tW, tD, flags=EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK)
+    d.A.ptr = None
+    d.bias, d.bn_scale, d.bn_shift = tb.Ptr, tsc.Ptr, tsh.Ptr
+    d.mask_out, d.mask_ld = tmask.Ptr, mask_ld
+    addr = []
+    for k, (dt, dh) in enumerate(taps):
+        par = dh % 2 if sub == 2 else 0
+        addr.append((dt, (dh - par) // 2 if sub == 2 else dh, par, k * C))
+    conv_addr(d, 1, tx, T, hin // sub, sub, C, hout, addr)
     lib.kfp16_ctx_set_max_ctas(handle.ptr, max_ctas)
-    outs = []
     try:
-        for no_share in (3, 2):
-            tD = gpu.ZeroTensor(T, N)
-            d = make_desc(T, N, 2 * D, tXp, tW, tD, b_major=K_MAJOR if b_k_major else MN_MAJOR, force_cg=2, force_bn=128,
-                          no_share=no_share, flags=EPI_RESID if resid else 0, res_scale=0.66, ldr=N)
-            d.R[0] = tR.Ptr
-            d.A.ptr = tXp.Ptr + halo * D * 2
-            d.A.rows, d.A.halo = T, halo
-            d.kslabs, d.kslab_len = 2, D
-            d.a_row_off[0][0], d.a_row_off[0][1] = s0, s1
-            d.b_row_off[0][0], d.b_row_off[0][1] = 0, (N if b_k_major else D)
-            run_desc(handle, d)
-            outs.append(tD.ToFP32())
-            tD.Free()
+        run_desc(handle, d)
     finally:
         lib.kfp16_ctx_set_max_ctas(handle.ptr, 0)
-    tol = gemm_tol(S, W, want) + (2.0 ** -10 * np.abs(0.66 * R) if resid else 0.0)
-    assert_close(outs[0], want, tol, f"A-stationary T={T} N={N} ctas={max_ctas}")
-    assert np.array_equal(outs[0], outs[1])      # same k-block / slab order -> same fp32 accumulation order
-    for t in (tXp, tW, tR):
+    tol = gemm_tol(Pm, W, want) * float(scale.max()) + 2.0 ** -10 * np.abs(want) + 1e-3
+    assert_close(tD.ToFP32(), want, tol, f"implicit conv forward T={T} hin={hin} sub={sub} C={C} N={N}")
+    bits = tmask.ToHost().view(np.uint32).reshape(T * hout, mask_ld)
+    got_mask = ((bits[:, np.arange(N) >> 5] >> (np.arange(N) & 31)) & 1).astype(bool)
+    zf = Pm @ W.astype(np.float64) + bias
+    sure = np.abs(zf) > 1e-2
+    assert np.array_equal(got_mask[sure], (zf > 0)[sure])
+    for t in (tx, tW, tb, tD):
+        t.Free()
+
+
+@pytest.mark.parametrize("T,hin,sub,Cin,Cout,taps", [(300, 40, 1, 64, 64, TAPS9), (190, 40, 2, 64, 128, TAPS9),
+                                                     (156, 10, 1, 256, 128, TAPS9), (60, 16, 2, 64, 64, [(0, 0), (1, 1)])])
+def test_implicit_conv_input_gradient_gemm(handle, lib, T, hin, sub, Cin, Cout, taps):
+    """the adjoint: dX[t, hi, :] = sum_taps dZ[t-dt, (hi-dh)/sub, :] W[tap]^T as conv.mode 1 over dZ with mirrored taps
+    (one launch per input-height parity when the layer subsamples by 2), K-major B = the forward's weight matrix"""
+    hout = hin // sub
+    rng = np.random.default_rng(T + hin + Cin + Cout)
+    dZ = rand_f16(rng, (T, hout, Cout))
+    W = rand_f16(rng, (len(taps) * Cin, Cout), 0.05)
+    # oracle: dP = dZ W^T scattered back (transpose of conv_ref_patches)
+    dP = (dZ.reshape(T * hout, Cout).astype(np.float64) @ W.astype(np.float64).T).reshape(T, hout, len(taps), Cin)
+    want = np.zeros((T, hin, Cin), np.float64)
+    absw = np.zeros_like(want)
+    adP = (np.abs(dZ).reshape(T * hout, Cout).astype(np.float64) @ np.abs(W).astype(np.float64).T).reshape(T, hout, len(taps), Cin)
+    for k, (dt, dh) in enumerate(taps):
+        for ho in range(hout):
+            hs = ho * sub + dh
+            if hs < 0 or hs >= hin:
+                continue
+            t0, t1 = max(0, -dt), min(T, T - dt)
+            want[t0 + dt:t1 + dt, hs, :] += dP[t0:t1, ho, k, :]
+            absw[t0 + dt:t1 + dt, hs, :] += adP[t0:t1, ho, k, :]
+    tz, tW = gpu.TensorFromFP16(dZ.reshape(T, hout * Cout)), gpu.TensorFromFP16(W)
+    tD = gpu.TensorFromFP16(np.full((T, hin * Cin), 7.0, np.float32))      # every element must be overwritten
+    for par in range(sub):
+        addr = [(-dt, (par - dh) // sub, 0, k * Cin) for k, (dt, dh) in enumerate(taps) if (par - dh) % sub == 0]
+        if not addr:
+            continue
+        d = make_desc(T * hout, Cin, len(addr) * Cout, tz, tW, tD, b_major=K_MAJOR)
+        d.A.ptr = None
+        d.D[0] = tD.Ptr + par * Cin * 2
+        d.ldd = sub * Cin
+        conv_addr(d, 1, tz, T, hout, 1, Cout, hout, addr)
+        run_desc(handle, d)
+    got = tD.ToFP32().reshape(T, hin, Cin)
+    covered = np.zeros(hin, bool)
+    for par in range(sub):
+        if any((par - dh) % sub == 0 for _, dh in taps):
+            covered[par::sub] = True
+    tol = 2.0 ** -10 * np.abs(want) * 1.01 + 2.0 ** -19 * absw + 1e-6
+    assert_close(got[:, covered], want[:, covered], tol[:, covered], f"implicit conv input gradient T={T} hin={hin} sub={sub}")
+    for t in (tz, tW, tD):
+        t.Free()
+
+
+@pytest.mark.parametrize("split_k", [1, 5, 24])
+@pytest.mark.parametrize("T,hin,sub,Cin,Cout,taps", [(312, 40, 1, 64, 64, TAPS9), (200, 40, 2, 64, 128, TAPS9),
+                                                     (157, 10, 1, 256, 256, TAPS9), (90, 16, 1, 64, 136, [(-2, 0), (0, 1), (3, -1)])])
+def test_implicit_conv_weight_gradient_gemm(handle, lib, split_k, T, hin, sub, Cin, Cout, taps):
+    """conv.mode 2: dW[(tap, c), n] = sum over (t, h) of x[t+dt, h*sub+dh, c] dZ[(t,h), n]: MN-major operands, k-blocks of up to
+    80 (frame, height) rows, the A chunks loaded as shifted 4-D boxes of the layer input; fp32 split-K accumulation"""
+    hout = hin // sub
+    rng = np.random.default_rng(T + hin + Cin + Cout + split_k)
+    x = rand_f16(rng, (T, hin, Cin))
+    dZ = rand_f16(rng, (T * hout, Cout), 0.05)
+    Pm = conv_ref_patches(x.astype(np.float64), hout, sub, taps)
+    want = Pm.T @ dZ.astype(np.float64)
+    absprod = np.abs(Pm).T @ np.abs(dZ).astype(np.float64)
+    tx, tz = gpu.TensorFromFP16(x.reshape(T, hin * Cin)), gpu.TensorFromFP16(dZ)
+    M = len(taps) * Cin
+    ws = gpu.DeviceF32(n=M * Cout)
+    tD = gpu.ZeroTensor(8, 8)
+    d = make_desc(M, Cout, T * hout, tx, tz, tD, a_major=MN_MAJOR, b_major=MN_MAJOR, split_k=split_k, ws_ld=Cout)
+    d.A.ptr = None
+    d.ws[0] = ws.Ptr
+    addr = []
+    for k, (dt, dh) in enumerate(taps):
+        par = dh % 2 if sub == 2 else 0
+        addr.append((dt, (dh - par) // 2 if sub == 2 else dh, par, k * Cin))
+    conv_addr(d, 2, tx, T, hin // sub, sub, Cin, hout, addr)
+    run_desc(handle, d)
+    got = ws.ToHost().reshape(M, Cout)
+    assert_close(got, want, 2.0 ** -19 * absprod + 1e-5, f"implicit conv weight gradient split={split_k}")
+    for t in (tx, tz):
         t.Free()
 
 

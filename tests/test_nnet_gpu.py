@@ -298,17 +298,19 @@ linear-component name=ivector-linear dim=32 input=ReplaceIndex(ivector, t, 0)
 batchnorm-component name=ivector-batchnorm target-rms=0.025
 batchnorm-component name=idct-batchnorm input=idct
 combine-feature-maps-layer name=combine_inputs input=Append(idct-batchnorm, ivector-batchnorm) num-filters1=1 num-filters2=2 height=16
-conv-relu-batchnorm-layer name=cnn1 height-in=16 height-out=16 time-offsets=-1,0,1 height-offsets=-1,0,1 num-filters-out=32
+conv-relu-batchnorm-layer name=cnn1 height-in=16 height-out=16 time-offsets=-1,0,1 height-offsets=-1,0,1 num-filters-out=F1
 conv-relu-batchnorm-layer name=cnn2 height-in=16 height-out=8 height-subsample-out=2 time-offsets=-1,0,1 height-offsets=-1,0,1 num-filters-out=64
 conv-relu-batchnorm-layer name=cnn3 height-in=8 height-out=8 time-offsets=-1,0,1 height-offsets=-1,0,1 num-filters-out=64
 tdnnf-layer name=tdnnf4 dim=256 bottleneck-dim=64 time-stride=0
 tdnnf-layer name=tdnnf5 dim=256 bottleneck-dim=64 time-stride=3
 output-layer name=output include-log-softmax=false dim=72
 """
+# F1 = 64: cnn2 (height subsampling 2) and cnn3 run as implicit GEMMs (64-channel inputs), cnn1 (3 input filters) through a
+# patch matrix; F1 = 32: cnn2 has a 32-channel input and takes the patch-matrix path too
 
 
-def check_conv_net(handle, n_seq, L, seed, ref_round=True):
-    on, net, rng = make_pair(handle, CNN_SMALL, n_seq, L, seed=seed, ref_round=ref_round)
+def check_conv_net(handle, n_seq, L, seed, ref_round=True, f1=64):
+    on, net, rng = make_pair(handle, CNN_SMALL.replace("F1", str(f1)), n_seq, L, seed=seed, ref_round=ref_round)
     x = O.to_f16_rne((rng.standard_normal((n_seq * L, 16)) * 2).astype(np.float32))
     iv = O.to_f16_rne(np.clip(rng.standard_normal((n_seq, 24)), -3, 3).astype(np.float32))
     inputs = {"input": x, "ivector": iv}
@@ -350,6 +352,11 @@ def test_cnn_front_end_forward_backward(handle, n_seq, L, ref_round):
     tcgen05 GEMMs (implicit GEMM over 4-D TMA boxes; the 3-filter first layer through a patch matrix), against the
     numpy oracle's explicit patch matrices"""
     check_conv_net(handle, n_seq, L, seed=5 + n_seq, ref_round=ref_round)
+
+
+def test_cnn_front_end_patch_matrix_path(handle):
+    """a 32-channel conv input cannot be addressed by 64-wide TMA boxes: im2col + GEMM + col2im, same results"""
+    check_conv_net(handle, 2, 30, seed=3, ref_round=False, f1=32)
 
 
 def test_set_lr_reaches_a_captured_sgd_graph(handle, lib):
