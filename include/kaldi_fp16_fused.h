@@ -131,7 +131,14 @@ typedef struct {
     float *ws2[2];
     int ws2_ld, ws2_transposed;
     kfp16_conv_addr conv; /* conv.mode != 0: the A operand is addressed as a convolution input (A.ptr unused) */
+    /* KFP16_EPI_DROPOUT: element (row, col) is kept iff u(seed, row, col) > drop_p, kept values scaled by 1/(1-drop_p)
+     * (inverted dropout, go/gotorch/layers.go:365-399), applied after the batch-norm and before the bypass; the emitted
+     * mask bit is (ReLU active AND kept).  u is a counter-based hash (kfp16_dropout_uniform); seed = drop_seed XOR
+     * *drop_seed_dev when that device word is given (a per-step counter, so CUDA-graph replays draw new masks). */
+    const uint32_t *drop_seed_dev;
 } kfp16_gemm_desc;
+/* the dropout hash, for callers that need the mask on the host: uniform in [0,1) */
+float kfp16_dropout_uniform(uint32_t seed, uint32_t row, uint32_t col);
 
 /* ---- grouped weight gradients: `count` split-K problems of the SAME shape (dW = A^T B with MN-major operands, two
  * row-shifted groups each -- the spliced weight gradients of many TDNN-F layers) in ONE persistent launch.  The
@@ -169,6 +176,10 @@ int kfp16_add_bias(kfp16_ctx *ctx, void *x, int ld, const void *bias, int rows, 
 /* out[n] = sum_t X[t,n]  (AffineBackwardBias, backward_ops.go:228-253), fp32 accumulate */
 int kfp16_colsum(kfp16_ctx *ctx, const void *X, int ld, int rows, int cols, float *out_f32,
                  void *out_f16);
+/* dst[i] = src[i] * c  (fp32 vectors: per-layer copies of batch-norm scales with a dropout factor folded in) */
+int kfp16_scale_f32(kfp16_ctx *ctx, const float *src, float *dst, int n, float c);
+/* *counter += 1 on the stream (the per-step dropout seed word) */
+int kfp16_bump_counter(kfp16_ctx *ctx, uint32_t *counter_dev);
 /* fp32 -> fp16 (round to nearest even), n elements */
 int kfp16_f32_to_f16(kfp16_ctx *ctx, const float *src, void *dst, size_t n);
 /* Padded activation layout: n_seq blocks of (seq_len + 2*halo) rows; X points at the very first

@@ -115,6 +115,12 @@ int kfp16_net_sgd_step(kfp16_net *net, float grad_scale, int round_grad);
 int kfp16_net_set_lr(kfp16_net *net, float lr);
 int kfp16_net_set_momentum(kfp16_net *net, float momentum);
 float kfp16_net_get_lr(const kfp16_net *net);
+/* Dropout (tdnnf-layer dropout-proportion=p, training networks only; the reference has it on the CPU only,
+ * go/gotorch/layers.go:348-399): inverted dropout after the layer's batch-norm, fused into the GEMM epilogue.  The mask
+ * of layer index i at (padded row, column) is kfp16_dropout_uniform(seed ^ i*0x9E3779B9, row, col) > p; the seed word
+ * lives on the device and is incremented at the start of every captured / phase-1 step. */
+int kfp16_net_set_dropout_seed(kfp16_net *net, uint32_t seed);
+int kfp16_net_get_dropout_seed(kfp16_net *net, uint32_t *seed);
 /* FP16 gradient bucket: g16 = half(g32 * grad_scale), the FP16 gradient tensors of the reference
  * (backward_ops.go:195-225) as one flat buffer.  A data-parallel loop all-reduces THIS buffer (half the bytes of the
  * FP32 bucket) and applies kfp16_net_sgd_step_f16 (ops_sgd_update arithmetic on FP16 gradients, scale 1). */

@@ -51,6 +51,7 @@ class GemmDesc(C.Structure):
         ("A2", KMat), ("B2", KMat), ("a2_row_off", c_int * 2), ("b2_row_off", c_int * 2),
         ("ws2", c_void_p * 2), ("ws2_ld", c_int), ("ws2_transposed", c_int),
         ("conv", ConvAddr),
+        ("drop_seed_dev", c_void_p),
     ]
 
 
@@ -101,6 +102,9 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_set_default_stream": (None, [c_void_p]),
     "kfp16_launch_count": (c_u64, []),
     "kfp16_gemm_kind_launches": (c_u64, [c_int]),
+    "kfp16_dropout_uniform": (c_float, [c_u32, c_u32, c_u32]),
+    "kfp16_scale_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float]),
+    "kfp16_bump_counter": (c_int, [c_void_p, c_void_p]),
     "kfp16_last_error": (C.c_char_p, []),
     "kfp16_gemm_ex": (c_int, [c_void_p, C.POINTER(GemmDesc)]),
     "kfp16_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p]),
@@ -169,6 +173,8 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_set_lr": (c_int, [c_void_p, c_float]),
     "kfp16_net_set_momentum": (c_int, [c_void_p, c_float]),
     "kfp16_net_get_lr": (c_float, [c_void_p]),
+    "kfp16_net_set_dropout_seed": (c_int, [c_void_p, c_u32]),
+    "kfp16_net_get_dropout_seed": (c_int, [c_void_p, C.POINTER(c_u32)]),
     "kfp16_net_grads_to_f16": (c_int, [c_void_p]),
     "kfp16_net_grads_f16": (c_void_p, [c_void_p]),
     "kfp16_net_sgd_step_f16": (c_int, [c_void_p]),

@@ -437,6 +437,12 @@ scale_f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst,
   for (size_t i = n4 * 4 + tid; i < n; i += stride) dst[i] = __float2half_rn(src[i] * sc);
 }
 
+__global__ void scale_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, float c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * c;
+}
+__global__ void bump_counter_kernel(uint32_t* c) { *c += 1u; }
+
 // ---- SGD with momentum on FP32 master weights (backward_wrappers.cu:129-142):
 //   g = float(grad); v = m*v + g; w32 -= lr*v; w16 = half(w32)
 // One launch covers a whole flat parameter bucket (the reference launches once per tensor).
@@ -1113,6 +1119,19 @@ int kfp16_f32_to_f16(kfp16_ctx* ctx, const float* src, void* dst, size_t n) {
   f32_to_f16_kernel<<<grid_for(n), kThreads, 0, ctx_stream(ctx)>>>(src, (__half*)dst, n);
   count_launch();
   return check_launch("kfp16_f32_to_f16") ? 0 : -1;
+}
+int kfp16_scale_f32(kfp16_ctx* ctx, const float* src, float* dst, int n, float c) {
+  if (n <= 0) return 0;
+  if (!src || !dst) { set_error("kfp16_scale_f32: null pointer"); return -1; }
+  scale_f32_kernel<<<(n + 255) / 256, 256, 0, ctx_stream(ctx)>>>(src, dst, n, c);
+  count_launch();
+  return check_launch("kfp16_scale_f32") ? 0 : -1;
+}
+int kfp16_bump_counter(kfp16_ctx* ctx, uint32_t* counter_dev) {
+  if (!counter_dev) { set_error("kfp16_bump_counter: null pointer"); return -1; }
+  bump_counter_kernel<<<1, 1, 0, ctx_stream(ctx)>>>(counter_dev);
+  count_launch();
+  return check_launch("kfp16_bump_counter") ? 0 : -1;
 }
 int kfp16_scale_f32_to_f16(kfp16_ctx* ctx, const float* src, void* dst, size_t n, const float* scale_dev) {
   if (n == 0) return 0;

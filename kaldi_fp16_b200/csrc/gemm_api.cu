@@ -107,8 +107,8 @@ extern template bool launch_gemm_bn<256>(kfp16_ctx*, const GemmParams&, const Ge
 // the specialised kind whose flag set equals `flags` exactly, else EK_GENERIC
 static int pick_kind(uint32_t flags) {
   if (flags & EPI_SPLITK) return EK_SPLITK;
-  for (int k = EK_PLAIN; k < EK_SPLITK; ++k)
-    if (epi_kind_flags(k) == flags) return k;
+  for (int k = EK_PLAIN; k < EK_COUNT; ++k)
+    if (k != EK_SPLITK && epi_kind_flags(k) == flags) return k;
   return EK_GENERIC;
 }
 
@@ -220,6 +220,7 @@ void kfp16_set_default_stream(void* s) { g_default_stream = (cudaStream_t)s; }
 unsigned long long kfp16_launch_count(void) { return g_launches.load(); }
 unsigned long long kfp16_gemm_kind_launches(int kind) { return (kind >= 0 && kind < EK_COUNT) ? g_kind_launches[kind].load() : 0ull; }
 const char* kfp16_last_error(void) { return get_error(); }
+float kfp16_dropout_uniform(uint32_t seed, uint32_t row, uint32_t col) { return dropout_uniform(seed, row, col); }
 
 // ------------------------------------------------------------------ fused GEMM
 // 4-D fp16 tensor [T][H][P][C] (C innermost), box [tbox][rows_h][1][64], 128B swizzle: the operand of an implicit-GEMM
@@ -431,7 +432,8 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   p.mask_out = d->mask_out; p.mask_in = d->mask_in; p.mask_ld = d->mask_ld;
   p.ws_ld = d->ws_ld;
   p.ws_transposed = d->ws_transposed;
-  p.drop_p = d->drop_p; p.drop_seed = d->drop_seed;
+  p.drop_p = d->drop_p; p.drop_seed = d->drop_seed; p.drop_seed_dev = d->drop_seed_dev;
+  if ((flags & EPI_DROPOUT) && !(d->drop_p >= 0.0f && d->drop_p < 1.0f)) { set_error("kfp16_gemm_ex: dropout probability must be in [0, 1)"); return -1; }
   if ((flags & EPI_BIAS) && !p.bias) { set_error("kfp16_gemm_ex: EPI_BIAS without bias"); return -1; }
   if ((flags & EPI_BN) && (!p.bn_scale || !p.bn_shift)) { set_error("kfp16_gemm_ex: EPI_BN without scale/shift"); return -1; }
   if ((flags & EPI_MASK) && !p.mask_out) { set_error("kfp16_gemm_ex: EPI_MASK without mask_out"); return -1; }

@@ -83,6 +83,8 @@ bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
         case EK_PLAIN: KFP16_CASE(false, true, EK_PLAIN, 2, true);
         case EK_AFFINE: KFP16_CASE(false, true, EK_AFFINE, 2, true);
         case EK_AFFINE_RES: KFP16_CASE(false, true, EK_AFFINE_RES, 2, true);
+        case EK_AFFINE_DROP: KFP16_CASE(false, true, EK_AFFINE_DROP, 2, true);
+        case EK_AFFINE_RES_DROP: KFP16_CASE(false, true, EK_AFFINE_RES_DROP, 2, true);
         default: break;
       }
       set_error("internal: no shared-tile kernel for epilogue kind %d", L.ek);
@@ -97,6 +99,8 @@ bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
         case EK_BN_GRADMASK: KFP16_CASE(false, true, EK_BN_GRADMASK, 2, false);
         case EK_BN: KFP16_CASE(false, true, EK_BN, 2, false);
         case EK_BIAS: KFP16_CASE(false, true, EK_BIAS, 2, false);
+        case EK_AFFINE_DROP: KFP16_CASE(false, true, EK_AFFINE_DROP, 2, false);
+        case EK_AFFINE_RES_DROP: KFP16_CASE(false, true, EK_AFFINE_RES_DROP, 2, false);
         default: break;
       }
       set_error("internal: no CTA-pair kernel for epilogue kind %d", L.ek);
@@ -111,6 +115,8 @@ bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
       case EK_BN: KFP16_CASE(false, true, EK_BN, 1, false);
       case EK_BIAS: KFP16_CASE(false, true, EK_BIAS, 1, false);
       case EK_SPLITK: KFP16_CASE(false, true, EK_SPLITK, 1, false);
+      case EK_AFFINE_DROP: KFP16_CASE(false, true, EK_AFFINE_DROP, 1, false);
+      case EK_AFFINE_RES_DROP: KFP16_CASE(false, true, EK_AFFINE_RES_DROP, 1, false);
       default: KFP16_CASE(false, true, EK_GENERIC, 1, false);
     }
   }
@@ -163,7 +169,7 @@ bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
 inline bool gemm_variant_exists(bool a_mn, bool b_mn, int ek, int cg, int share) {
   if (share) {
     if (a_mn || cg != 2) return false;   // the shared splice tile exists for CTA pairs only
-    if (b_mn) return ek == EK_PLAIN || ek == EK_AFFINE || ek == EK_AFFINE_RES;
+    if (b_mn) return ek == EK_PLAIN || ek == EK_AFFINE || ek == EK_AFFINE_RES || ek == EK_AFFINE_DROP || ek == EK_AFFINE_RES_DROP;
     return ek == EK_PLAIN || ek == EK_RESID;
   }
   if (cg == 2) {

@@ -48,7 +48,7 @@ enum EpiFlags : uint32_t {
   EPI_REF_ROUND = 1u << 5,  // round to fp16 between fused stages exactly where the reference stores fp16
   EPI_MASK = 1u << 6,       // emit relu bit-mask (x > 0), 1 bit / element
   EPI_SPLITK = 1u << 7,     // fp32 red.add of the partial tile into ws (no fp16 store)
-  EPI_DROPOUT = 1u << 8,    // inverted dropout, counter-based mask (seed,row,col)
+  EPI_DROPOUT = 1u << 8,    // inverted dropout after the batch-norm: keep if u(seed,row,col) > p, scale 1/(1-p) (go/gotorch/layers.go:365-399)
   EPI_GRADMASK = 1u << 9,   // x = mask_in bit ? x : 0      (relu backward fused in producer)
 };
 
@@ -63,6 +63,8 @@ enum EpiKind : int {
   EK_BN,               // bn only                         (prefinal linear)
   EK_BIAS,             // bias only                       (output layer)
   EK_SPLITK,           // fp32 accumulate into the workspace (weight gradients)
+  EK_AFFINE_DROP,      // bias, relu, bn, dropout, mask            (tdnnf affine in training with dropout-proportion > 0)
+  EK_AFFINE_RES_DROP,  // bias, relu, bn, dropout, mask, residual
   EK_COUNT
 };
 
@@ -75,6 +77,8 @@ __host__ __device__ constexpr uint32_t epi_kind_flags(int k) {
        : k == EK_BN ? (uint32_t)EPI_BN
        : k == EK_BIAS ? (uint32_t)EPI_BIAS
        : k == EK_SPLITK ? (uint32_t)EPI_SPLITK
+       : k == EK_AFFINE_DROP ? (EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK | EPI_DROPOUT)
+       : k == EK_AFFINE_RES_DROP ? (EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK | EPI_DROPOUT | EPI_RESID)
        : 0u;
 }
 
@@ -117,6 +121,7 @@ struct GemmParams {
   int ws_ld;
   int ws_transposed;            // split-K target is stored [N x M] (ws[n*ws_ld + m]): warp lanes = consecutive m
   float drop_p; uint32_t drop_seed;
+  const uint32_t* drop_seed_dev;   // optional device word XOR-ed into drop_seed when the kernel runs (a per-step counter: graph replays draw new masks)
   // shared splice tile (SHARE kernels): slab s reads the A tile from row a_shift[s] (0..8) on
   int a_shift[kMaxSlabs];
   int a_box_bytes;              // bytes of the A box (128 + span rows) x 128 B
@@ -138,7 +143,7 @@ struct GemmParams {
   long long* dbg;               // profiling: per-CTA role timestamps [grid][3 roles][8 tiles][16] (nullptr = off)
 };
 
-// counter-based uniform in [0,1): shared by the CUDA epilogue and the CPU oracle (oracle/kaldi_oracle.py)
+// counter-based uniform in [0,1): the same integer hash is restated in the CPU oracle (oracle/kaldi_oracle.py::dropout_uniform)
 __host__ __device__ inline float dropout_uniform(uint32_t seed, uint32_t row, uint32_t col) {
   uint32_t x = seed ^ (row * 0x9E3779B1u) ^ (col * 0x85EBCA77u);
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
@@ -597,6 +602,11 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
     const int row_in_tile = q * 32 + lane;
     const int epi_tid = threadIdx.x - 128;
     const bool ref_round = kGeneric && (flags & EPI_REF_ROUND) != 0;
+    uint32_t drop_seed = 0; float drop_inv = 1.0f;
+    if ((kGeneric || (Cfg::kFlags & EPI_DROPOUT)) && (flags & EPI_DROPOUT)) {
+      drop_seed = p.drop_seed ^ (p.drop_seed_dev ? __ldg(p.drop_seed_dev) : 0u);
+      drop_inv = 1.0f / (1.0f - p.drop_p);
+    }
     int acc = 0; uint32_t acc_phase = 0;
     int k = 0;   // running 64-column chunk counter
     int buf = 0; uint32_t round = 0;   // its position in the staging ring
@@ -768,12 +778,21 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
                   float2 x = make_float2(__uint_as_float(v8[e]), __uint_as_float(v8[e + 1]));
                   if (flags & EPI_BIAS) x = ffma2(x, alpha2, make_float2(bia[e], bia[e + 1]));
                   else x = fmul2(x, alpha2);
+                  bool keep0 = true, keep1 = true;
+                  if (flags & EPI_DROPOUT) {
+                    keep0 = dropout_uniform(drop_seed, (uint32_t)row, (uint32_t)(n0 + ct + e)) > p.drop_p;
+                    keep1 = dropout_uniform(drop_seed, (uint32_t)row, (uint32_t)(n0 + ct + e + 1)) > p.drop_p;
+                  }
                   if (flags & EPI_RELU) {
                     x.x = relu_nan(x.x); x.y = relu_nan(x.y);
-                    if (x.x > 0.0f) maskword |= (1u << bit);
-                    if (x.y > 0.0f) maskword |= (2u << bit);
+                    if (x.x > 0.0f && keep0) maskword |= (1u << bit);      // gradient gate: ReLU active AND kept by dropout
+                    if (x.y > 0.0f && keep1) maskword |= (2u << bit);
                   }
                   if (flags & EPI_BN) x = ffma2(x, make_float2(bsc[e], bsc[e + 1]), make_float2(bsh[e], bsh[e + 1]));
+                  if (flags & EPI_DROPOUT) {
+                    x.x = keep0 ? x.x * drop_inv : 0.0f;
+                    x.y = keep1 ? x.y * drop_inv : 0.0f;
+                  }
                   if (flags & EPI_RESID) x = ffma2(res2, make_float2(r[e], r[e + 1]), x);
                   if (flags & EPI_GRADMASK) {
                     x.x = ((gm_word >> bit) & 1u) ? x.x : 0.0f;
@@ -792,17 +811,17 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
                   x += bia[e];
                   if (ref_round) x = round_h(x);
                 }
+                const bool keep = !(flags & EPI_DROPOUT) || dropout_uniform(drop_seed, (uint32_t)row, (uint32_t)(n0 + ct + e)) > p.drop_p;
                 if (flags & EPI_RELU) {
                   x = relu_nan(x);
-                  if (x > 0.0f) maskword |= (1u << bit);
-                }
-                if (flags & EPI_DROPOUT) {
-                  const float u = dropout_uniform(p.drop_seed, (uint32_t)row, (uint32_t)(n0 + ct + e));
-                  x = (u > p.drop_p) ? x * (1.0f / (1.0f - p.drop_p)) : 0.0f;
-                  if (ref_round) x = round_h(x);
+                  if (x > 0.0f && keep) maskword |= (1u << bit);
                 }
                 if (flags & EPI_BN) {
                   x = fmaf(x, bsc[e], bsh[e]);
+                  if (ref_round) x = round_h(x);
+                }
+                if (flags & EPI_DROPOUT) {
+                  x = keep ? x * drop_inv : 0.0f;
                   if (ref_round) x = round_h(x);
                 }
                 if (flags & EPI_RESID) x = fmaf(p.res_scale, r[e], x);

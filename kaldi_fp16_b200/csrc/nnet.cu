@@ -44,6 +44,8 @@ struct BNorm {
   bool rms_only = false;       // batchnorm-component with target-rms != 1 (forward.go:349-374)
   float *mean = nullptr, *var = nullptr, *gamma = nullptr, *beta = nullptr;   // fp32 [dim]
   float *scale = nullptr, *shift = nullptr, *zero = nullptr;                  // folded; zero = [dim] of 0
+  float *scale_bwd = nullptr;   // scale * bwd_mul: the backward pass's factor (dropout folds 1/(1-p) in here)
+  float bwd_mul = 1.0f;
 };
 
 struct Param {
@@ -73,6 +75,7 @@ struct Layer {
   BNorm bn, bn2;
   // tdnnf
   int stride = 0, bott_dim = 0;
+  float dropout_p = 0.f;        // dropout-proportion (training only): inverted dropout after the batch-norm
   float bypass = 0.f;
   bool use_bypass = false;
   Buf bott, dbott, dz;
@@ -116,6 +119,7 @@ struct kfp16_net {
   __half* w16 = nullptr;
   float *w32 = nullptr, *vel = nullptr, *g32 = nullptr;
   __half* g16 = nullptr;                   // FP16 copy of the (scaled) gradient bucket: what the data-parallel exchange carries
+  uint32_t* seed_dev = nullptr;            // per-step dropout seed word (bumped at the start of every training step)
   float* hp_dev = nullptr;                 // {lr, momentum, grad_scale}: read by the SGD kernel at run time (graph-safe SetLR)
   float hp_host[3] = {0.f, 0.f, 1.f};
   double flops_bwd = 0;
@@ -271,7 +275,7 @@ bool make_bn(kfp16_net* n, BNorm& bn, int dim, float target_rms, bool rms_only) 
   bn.target_rms = target_rms;
   bn.rms_only = rms_only;
   float* base = nullptr;
-  if (!dev_alloc(n, (void**)&base, (size_t)dim * 7 * sizeof(float))) return false;
+  if (!dev_alloc(n, (void**)&base, (size_t)dim * 8 * sizeof(float))) return false;
   bn.mean = base;
   bn.var = base + dim;
   bn.gamma = base + 2 * dim;
@@ -279,12 +283,14 @@ bool make_bn(kfp16_net* n, BNorm& bn, int dim, float target_rms, bool rms_only) 
   bn.scale = base + 4 * dim;
   bn.shift = base + 5 * dim;
   bn.zero = base + 6 * dim;
+  bn.scale_bwd = base + 7 * dim;
   std::vector<float> h((size_t)dim * 4, 0.f);   // identity: mean 0, var 1, gamma 1, beta 0
   for (int i = 0; i < dim; ++i) { h[dim + i] = 1.f; h[2 * dim + i] = 1.f; }
   if (!check_cuda(cudaMemcpyAsync(base, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, n->ctx->stream), "bn upload")) return false;
   if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "bn upload sync")) return false;
   return kfp16_bn_fold(n->ctx, bn.mean, bn.var, rms_only ? nullptr : bn.gamma, rms_only ? nullptr : bn.beta, bn.eps,
-                       target_rms, dim, bn.scale, bn.shift) == 0;
+                       target_rms, dim, bn.scale, bn.shift) == 0 &&
+         kfp16_scale_f32(n->ctx, bn.scale, bn.scale_bwd, dim, bn.bwd_mul) == 0;
 }
 
 // ------------------------------------------------------------------------------ xconfig
@@ -461,6 +467,8 @@ bool resolve_dims(kfp16_net* n) {
         l.stride = kv_int(l, "time-stride", 3);
         l.bypass = (float)kv_float(l, "bypass-scale", 0.66);
         l.use_bypass = l.bypass > 0 && l.in_dim == l.out_dim;   // forward.go:688
+        l.dropout_p = n->opts.train ? (float)kv_float(l, "dropout-proportion", 0.0) : 0.f;
+        if (!(l.dropout_p >= 0.f && l.dropout_p < 1.f)) { set_error("tdnnf-layer %s: dropout-proportion must be in [0, 1)", l.name.c_str()); return false; }
         if (l.stride < 0) { set_error("tdnnf-layer %s: negative time-stride", l.name.c_str()); return false; }
         max_halo = std::max(max_halo, l.stride);
         break;
@@ -578,6 +586,7 @@ bool build_plan(kfp16_net* n) {
     if (!dev_alloc(n, (void**)&n->g32, std::max<size_t>(n->bucket, 8) * sizeof(float))) return false;
     if (!dev_alloc(n, (void**)&n->g16, std::max<size_t>(n->bucket, 8) * sizeof(__half))) return false;
     if (!dev_alloc(n, (void**)&n->hp_dev, 64)) return false;
+    if (!dev_alloc(n, (void**)&n->seed_dev, 64)) return false;
     n->hp_host[0] = n->opts.lr; n->hp_host[1] = n->opts.momentum;
     n->hp_host[2] = n->opts.grad_scale != 0.f ? n->opts.grad_scale : 1.0f;
     {
@@ -650,6 +659,7 @@ bool build_plan(kfp16_net* n) {
         if (l.per_seq) { set_error("tdnnf-layer %s on a per-sequence input", l.name.c_str()); return false; }
         const int sp = l.stride > 0 ? 2 : 1;
         if (!alloc_buf(n, l.bott, n->Tp, l.bott_dim)) return false;
+        l.bn.bwd_mul = l.dropout_p > 0.f ? 1.0f / (1.0f - l.dropout_p) : 1.0f;
         if (!make_bn(n, l.bn, l.out_dim, 1.0f, false)) return false;
         l.mask_ld = (l.out_dim + 31) / 32;
         if (!dev_alloc(n, (void**)&l.mask, (size_t)n->Tp * l.mask_ld * 4)) return false;
@@ -998,6 +1008,12 @@ int forward_layer(kfp16_net* n, Layer& l) {
         d.bn_scale = l.bn.scale; d.bn_shift = l.bn.shift;
         d.mask_out = l.mask; d.mask_ld = l.mask_ld;
         if (l.use_bypass) { d.flags |= KFP16_EPI_RESID; d.R[0] = X.p; d.ldr = l.in_dim; d.res_scale = l.bypass; }
+        if (l.dropout_p > 0.f) {   // training: inverted dropout after the batch-norm (go/gotorch/layers.go:365-399), per-step seed word
+          d.flags |= KFP16_EPI_DROPOUT;
+          d.drop_p = l.dropout_p;
+          d.drop_seed = (uint32_t)(&l - n->layers.data()) * 0x9E3779B9u;
+          d.drop_seed_dev = n->seed_dev;
+        }
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
       break;
@@ -1100,7 +1116,8 @@ int backward_layer(kfp16_net* n, Layer& l) {
     case L_TDNNF: {
       const int s = l.stride, sp = s > 0 ? 2 : 1;
       // dZ = mask ? h(dY * bn_scale) : 0 ; db += colsum(dZ)
-      if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.out_dim, l.bn.scale, l.mask, l.mask_ld, l.dz.p, l.out_dim, rows, l.out_dim, G32(n, l.pAffB))) return -1;
+      // (with dropout the mask bit is ReLU-active AND kept, and the factor 1/(1-p) is folded into scale_bwd)
+      if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.out_dim, l.bn.scale_bwd, l.mask, l.mask_ld, l.dz.p, l.out_dim, rows, l.out_dim, G32(n, l.pAffB))) return -1;
       // with a splice both weight gradients of the layer are deferred to the grouped launch at the end of the pass
       const bool both = sp == 2;
       if (!both && wgrad(n, l.bott, l.dz, l.pAff, sp, 0, s)) return -1;
@@ -1252,6 +1269,7 @@ int backward_layer(kfp16_net* n, Layer& l) {
 
 int run_phases(kfp16_net* n, int phases) {
   if (phases & 1) {
+    if (kfp16_bump_counter(n->ctx, n->seed_dev)) return -1;     // a new dropout mask per step, graph replays included
     if (kfp16_net_zero_grads(n)) return -1;
     if (kfp16_net_forward(n)) return -1;
     if (kfp16_net_loss_half_sq(n, "")) return -1;
@@ -1382,6 +1400,7 @@ int kfp16_net_set_bn(kfp16_net* n, const char* layer, const char* which, const f
     return -1;
   const bool rms = bn->rms_only;
   if (kfp16_bn_fold(n->ctx, bn->mean, bn->var, rms ? nullptr : bn->gamma, rms ? nullptr : bn->beta, eps, bn->target_rms, dim, bn->scale, bn->shift)) return -1;
+  if (kfp16_scale_f32(n->ctx, bn->scale, bn->scale_bwd, dim, bn->bwd_mul)) return -1;
   return check_cuda(cudaStreamSynchronize(n->ctx->stream), "bn fold sync") ? 0 : -1;
 }
 
@@ -1670,6 +1689,17 @@ int kfp16_net_set_momentum(kfp16_net* n, float momentum) {
   return upload_hp(n);
 }
 float kfp16_net_get_lr(const kfp16_net* n) { return n ? n->opts.lr : 0.f; }
+// dropout: the mask of layer i at element (padded row, col) is kfp16_dropout_uniform(seed ^ i*0x9E3779B9, row, col) > p
+int kfp16_net_set_dropout_seed(kfp16_net* n, uint32_t seed) {
+  if (!n || !n->seed_dev) { set_error("kfp16_net_set_dropout_seed: network was created with train = 0"); return -1; }
+  return check_cuda(cudaMemcpyAsync(n->seed_dev, &seed, 4, cudaMemcpyHostToDevice, n->ctx->stream), "seed upload") &&
+         check_cuda(cudaStreamSynchronize(n->ctx->stream), "seed upload sync") ? 0 : -1;
+}
+int kfp16_net_get_dropout_seed(kfp16_net* n, uint32_t* seed) {
+  if (!n || !n->seed_dev || !seed) { set_error("kfp16_net_get_dropout_seed: bad argument"); return -1; }
+  if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "sync")) return -1;
+  return check_cuda(cudaMemcpy(seed, n->seed_dev, 4, cudaMemcpyDeviceToHost), "seed download") ? 0 : -1;
+}
 int kfp16_net_read_loss(kfp16_net* n, float* loss) {
   if (!n || !loss) { set_error("kfp16_net_read_loss: null argument"); return -1; }
   if (!check_cuda(cudaMemcpyAsync(loss, n->loss_dev, 4, cudaMemcpyDeviceToHost, n->ctx->stream), "loss download")) return -1;

@@ -237,6 +237,33 @@ def subsample_rows(x, stride, row_offset):
 
 
 # ----------------------------------------------------------------------------- backward ops
+def dropout_uniform(seed: int, rows: np.ndarray, cols: np.ndarray) -> np.ndarray:
+    """counter-based uniform in [0,1) per element (row, col): the integer hash the fused dropout epilogue uses
+    (kaldi_fp16_b200/csrc/gemm_sm100.cuh::dropout_uniform), restated with uint32 wrap-around arithmetic.  The reference
+    draws rand.Float64() per element (go/gotorch/layers.go:378); a counter-based generator gives the same distribution
+    and makes the mask a pure function of (seed, row, col)."""
+    with np.errstate(over="ignore"):
+        r = np.asarray(rows, np.uint32)[:, None]
+        c = np.asarray(cols, np.uint32)[None, :]
+        x = np.uint32(seed & 0xFFFFFFFF) ^ (r * np.uint32(0x9E3779B1)) ^ (c * np.uint32(0x85EBCA77))
+        x = x ^ (x >> np.uint32(16))
+        x = x * np.uint32(0x7FEB352D)
+        x = x ^ (x >> np.uint32(15))
+        x = x * np.uint32(0x846CA68B)
+        x = x ^ (x >> np.uint32(16))
+    return (x >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def dropout_forward(x: np.ndarray, keep: np.ndarray, p: float) -> np.ndarray:
+    """DropoutLayer.Forward (go/gotorch/layers.go:365-383): inverted dropout, kept values scaled by 1/(1-p); FP16 store"""
+    return h(np.where(keep, x.astype(np.float32) * np.float32(1.0 / (1.0 - p)), np.float32(0)))
+
+
+def dropout_backward(grad: np.ndarray, keep: np.ndarray, p: float) -> np.ndarray:
+    """DropoutLayer.Backward (go/gotorch/layers.go:385-399)"""
+    return h(np.where(keep, grad.astype(np.float32) * np.float32(1.0 / (1.0 - p)), np.float32(0)))
+
+
 def relu_backward(x, grad):
     """bw_relu_backward_kernel (backward_wrappers.cu:41-49): grad if x>0 else 0"""
     return np.where(np.asarray(x, f32) > 0, np.asarray(grad, f32), f32(0))

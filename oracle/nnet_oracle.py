@@ -135,7 +135,11 @@ def identity_bn(dim):
 
 
 class OracleNet:
-    def __init__(self, xconfig: str, n_seq: int, seq_len: int, cartesian: bool = True):
+    def __init__(self, xconfig: str, n_seq: int, seq_len: int, cartesian: bool = True, train: bool = False,
+                 dropout_seed: int = 0):
+        # train = True enables the tdnnf-layer dropout-proportion (inverted dropout after the batch-norm,
+        # go/gotorch/layers.go:348-399); the mask of layer index i is dropout_uniform(seed ^ i*0x9E3779B9, padded row, col) > p
+        self.train, self.dropout_seed = train, dropout_seed
         self.layers = parse_xconfig(xconfig)
         self.by_name = {l.name: l for l in self.layers}
         self.n_seq, self.L = n_seq, seq_len
@@ -191,6 +195,25 @@ class OracleNet:
             self.params[k] = O.to_f16_trunc((rng.standard_normal((r, c)) * math.sqrt(2.0 / (r + c))).astype(f32))
 
     # ------------------------------------------------------------------ helpers
+    def halo(self) -> int:
+        """halo rows per sequence side in the executor's padded layout: the largest time-stride / conv time offset"""
+        hmax = 0
+        for l in self.layers:
+            if l.type == "tdnnf-layer":
+                hmax = max(hmax, int(l.kv.get("time-stride", 3)))
+            elif l.type == "conv-relu-batchnorm-layer":
+                hmax = max([hmax] + [abs(int(v)) for v in l.kv.get("time-offsets", "0").split(",")])
+        return hmax
+
+    def dropout_keep(self, l, p: float) -> np.ndarray:
+        """keep mask [T x out_dim] of layer l: rows are numbered as the executor stores them (padded layout)"""
+        idx = self.layers.index(l)
+        hl = self.halo()
+        blk = self.L + 2 * hl
+        rows = (np.arange(self.n_seq)[:, None] * blk + hl + np.arange(self.L)[None, :]).reshape(-1)
+        seed = (self.dropout_seed ^ ((idx * 0x9E3779B9) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        return O.dropout_uniform(seed, rows, np.arange(l.out_dim)) > f32(p)
+
     def _shift(self, x, s):
         """rows t -> t+s inside each sequence, clamped at the sequence edges (forward.go:699-790)"""
         D = x.shape[1]
@@ -289,9 +312,15 @@ class OracleNet:
                 z = O.relu(z)
                 relu_out = z
                 z = self._bn_fwd(z, self.bn[(l.name, "AffBN")])
+                mask = relu_out > 0
+                pdrop = float(l.kv.get("dropout-proportion", 0.0)) if self.train else 0.0
+                if pdrop > 0:
+                    keep = self.dropout_keep(l, pdrop)
+                    z = O.dropout_forward(z, keep, pdrop)
+                    mask = mask & keep                      # gradient gate: ReLU active AND kept
                 bypass = float(l.kv.get("bypass-scale", 0.66))
                 y = O.add_scaled(z, x, bypass, 1.0) if (bypass > 0 and l.in_dim == l.out_dim) else z
-                saved[l.name].update(s1=s1, s2=s2, mask=relu_out > 0)
+                saved[l.name].update(s1=s1, s2=s2, mask=mask, pdrop=pdrop)
             elif t == "prefinal-layer":
                 g = O.gemm(x, P[f"{l.name}.BigW"])
                 g = O.add_bias(g, P[f"{l.name}.BigBias"])
@@ -359,7 +388,10 @@ class OracleNet:
             elif t == "tdnnf-layer":
                 s = int(l.kv.get("time-stride", 3))
                 bnd = int(l.kv["bottleneck-dim"])
-                dz = np.where(sv["mask"], h(dy * self._bn_scale(self.bn[(l.name, "AffBN")])), f32(0))
+                bscale = self._bn_scale(self.bn[(l.name, "AffBN")])
+                if sv.get("pdrop", 0.0) > 0:               # DropoutLayer.Backward folded into the batch-norm factor
+                    bscale = (bscale * f32(1.0 / (1.0 - sv["pdrop"]))).astype(f32)
+                dz = np.where(sv["mask"], h(dy * bscale), f32(0))
                 wg[f"{l.name}.AffineBias"] = dz.sum(0, dtype=f32).reshape(1, -1)
                 wg[f"{l.name}.AffineW"] = sv["s2"].T.astype(f32) @ dz
                 Wa, Wl = P[f"{l.name}.AffineW"], P[f"{l.name}.LinearW"]

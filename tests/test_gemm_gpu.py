@@ -8,8 +8,8 @@ import numpy as np
 import pytest
 
 from kaldi_fp16_b200 import _lib, gpu
-from kaldi_fp16_b200._lib import (EPI_BETA, EPI_BIAS, EPI_BN, EPI_MASK, EPI_REF_ROUND, EPI_RELU, EPI_RESID, K_MAJOR,
-                                  MN_MAJOR)
+from kaldi_fp16_b200._lib import (EPI_BETA, EPI_BIAS, EPI_BN, EPI_DROPOUT, EPI_MASK, EPI_REF_ROUND, EPI_RELU, EPI_RESID,
+                                  K_MAJOR, MN_MAJOR)
 from oracle import kaldi_oracle as O
 from tests.util import assert_close, gemm_tol, make_desc, rand_f16, run_desc
 
@@ -562,3 +562,55 @@ def test_grouped_weight_gradients_equal_the_oracle(handle, lib, N, count, K):
 def _lib_err():
     from kaldi_fp16_b200 import _lib
     return _lib.last_error()
+
+
+# ---------------------------------------------------------------- fused dropout epilogue
+@pytest.mark.parametrize("generic,resid", [(0, False), (0, True), (1, True)])
+@pytest.mark.parametrize("M,N,K,p", [(900, 512, 320, 0.1), (300, 1536, 128, 0.5), (129, 72, 88, 0.25)])
+def test_fused_dropout_epilogue(handle, lib, generic, resid, M, N, K, p):
+    """KFP16_EPI_DROPOUT (north_star: fused dropout epilogue; semantics go/gotorch/layers.go:365-399): after
+    bias + ReLU + batch-norm the element (row, col) is kept iff u(seed, row, col) > p and scaled by 1/(1-p), then the bypass is
+    added; the emitted mask bit is ReLU-active AND kept.  Checked against the numpy oracle (same counter hash), for the
+    specialised kinds (EK_AFFINE_DROP / EK_AFFINE_RES_DROP) and the generic run-time-flag body, with the seed taken from
+    a device word as the training step does."""
+    rng = np.random.default_rng(M + N + int(p * 100))
+    A, W = rand_f16(rng, (M, K)), rand_f16(rng, (K, N), 0.08)
+    bias = rand_f16(rng, (1, N), 0.1)
+    R = rand_f16(rng, (M, N))
+    scale = (rng.random(N) + 0.5).astype(np.float32)
+    shift = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    seed_host, seed_word = 0x1234ABCD, 77
+    u = O.dropout_uniform(seed_host ^ seed_word, np.arange(M), np.arange(N))
+    assert abs(lib.kfp16_dropout_uniform(seed_host ^ seed_word, 5, 9) - u[5, 9]) == 0.0
+    keep = u > np.float32(p)
+    assert abs(keep.mean() - (1 - p)) < 0.02
+    pre = A.astype(np.float64) @ W.astype(np.float64) + bias
+    z = np.maximum(pre, 0.0) * scale + shift
+    want = np.where(keep, z / (1.0 - p), 0.0) + (0.66 * R if resid else 0.0)
+    tA, tW, tb, tR = gpu.TensorFromFP16(A), gpu.TensorFromFP16(W), gpu.TensorFromFP16(bias), gpu.TensorFromFP16(R)
+    tD = gpu.ZeroTensor(M, N)
+    tsc, tsh = gpu.DeviceF32(scale), gpu.DeviceF32(shift)
+    mask_ld = (N + 31) // 32
+    tmask = gpu.DeviceF32(n=M * mask_ld)
+    tseed = gpu.DeviceF32(np.array([seed_word], np.uint32).view(np.float32))
+    d = make_desc(M, N, K, tA, tW, tD, flags=EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK | EPI_DROPOUT | (EPI_RESID if resid else 0),
+                  force_generic=generic, res_scale=0.66, ldr=N, drop_p=p, drop_seed=seed_host)
+    d.R[0] = tR.Ptr
+    d.bias, d.bn_scale, d.bn_shift = tb.Ptr, tsc.Ptr, tsh.Ptr
+    d.mask_out, d.mask_ld = tmask.Ptr, mask_ld
+    d.drop_seed_dev = tseed.Ptr
+    kinds0 = [lib.kfp16_gemm_kind_launches(k) for k in range(11)]
+    run_desc(handle, d)
+    ran = [lib.kfp16_gemm_kind_launches(k) - kinds0[k] for k in range(11)]
+    assert ran[0 if generic else (10 if resid else 9)] == 1, ran
+    got = tD.ToFP32()
+    tol = (gemm_tol(A, W, want) * float(scale.max()) + 2.0 ** -10 * np.abs(z)) / (1.0 - p) + 2.0 ** -10 * np.abs(want) + 1e-3
+    assert_close(got, want, tol, f"dropout p={p} generic={generic} resid={resid}")
+    if not resid:
+        assert np.array_equal(got[~keep], np.zeros_like(got[~keep]))
+    bits = tmask.ToHost().view(np.uint32).reshape(M, mask_ld)
+    got_mask = ((bits[:, np.arange(N) >> 5] >> (np.arange(N) & 31)) & 1).astype(bool)
+    sure = np.abs(pre) > 1e-2
+    assert np.array_equal(got_mask[sure], ((pre > 0) & keep)[sure])
+    for t in (tA, tW, tb, tR, tD):
+        t.Free()

@@ -541,3 +541,83 @@ def test_segmented_step_graphs_equal_the_single_graph(handle, lib, nseg):
     finally:
         lib.kfp16_ctx_set_stream(handle.ptr, None)
         st.destroy()
+
+
+DROPNET = """
+input name=input dim=64
+linear-component name=lin0 dim=256
+tdnnf-layer name=tdnnf1 dim=256 bottleneck-dim=64 time-stride=3 bypass-scale=0.66 dropout-proportion=0.2
+tdnnf-layer name=tdnnf2 dim=256 bottleneck-dim=64 time-stride=0 bypass-scale=0.66 dropout-proportion=0.35
+tdnnf-layer name=tdnnf3 dim=384 bottleneck-dim=64 time-stride=1 dropout-proportion=0.1
+output-layer name=output include-log-softmax=false dim=104
+"""
+
+
+@REF_ROUND
+def test_dropout_in_the_training_step(handle, lib, ref_round):
+    """tdnnf-layer dropout-proportion (training networks): the fused dropout epilogue + its backward (mask bit = ReLU active
+    AND kept, 1/(1-p) folded into the batch-norm factor) against the oracle's op-by-op dropout with the same mask; a
+    phase-1 step draws a new mask, an inference network ignores the option"""
+    n_seq, L, seed = 3, 41, 0xC0FFEE
+    rng = np.random.default_rng(17)
+    on = OracleNet(DROPNET, n_seq, L, train=True, dropout_seed=seed)
+    on.init_random(rng)
+    for k in on.params:
+        if k.endswith("Bias"):
+            on.params[k] = O.to_f16_trunc((rng.standard_normal(on.params[k].shape) * 0.1).astype(np.float32))
+    net = nnet.NewNetwork(nnet.BuildModelFromString(DROPNET), handle, n_seq, L, ref_round=ref_round)
+    for k, w in on.params.items():
+        net.SetParam(k, w)
+    assert lib.kfp16_net_set_dropout_seed(net.ptr, seed) == 0
+    x = O.to_f16_rne(rng.standard_normal((n_seq * L, 64)).astype(np.float32))
+    acts = on.forward({"input": x})
+    net.SetInput("input", x)
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    for name in ("tdnnf1", "tdnnf2", "tdnnf3", "output"):
+        err = rel_to_scale(net.Output(name), acts[name])
+        assert err <= 2e-3, f"forward {name} with dropout: {err:.2e}"
+    dropped = np.mean(net.Output("tdnnf3") == 0)
+    assert 0.05 < dropped < 0.6          # tdnnf3 has no bypass: dropped elements are exact zeros
+    masks = {}
+    for name in ("tdnnf1", "tdnnf2", "tdnnf3"):
+        want = on.saved[name]["mask"]
+        got = net.Mask(name, want.shape[1])
+        assert np.mean(got != want) < 5e-3, f"gradient gate {name}: {np.mean(got != want):.2%} differ"
+        masks[name] = got
+    wg, dact = on.backward("output", acts["output"], masks)
+    net.ZeroGrads()
+    net.Backward(None)
+    got_wg = net.WeightGrads()
+    for k, g in wg.items():
+        err = rel_to_scale(got_wg[k], g)
+        assert err <= (1e-2 if k.endswith("Bias") else 5e-3), f"weight grad {k} with dropout: {err:.2e}"
+    # a phase-1 step (what the captured graph replays) bumps the device seed word -> a different mask
+    import ctypes as C
+    s0, s1 = C.c_uint32(0), C.c_uint32(0)
+    assert lib.kfp16_net_get_dropout_seed(net.ptr, C.byref(s0)) == 0 and s0.value == seed
+    y0 = net.Output("tdnnf3")
+    from kaldi_fp16_b200 import cudart
+    st = cudart.Stream()
+    lib.kfp16_ctx_set_stream(handle.ptr, st.ptr)
+    try:
+        net.Capture(1)
+        assert lib.kfp16_net_get_dropout_seed(net.ptr, C.byref(s1)) == 0
+        base = s1.value
+        net.Launch(1)
+        st.synchronize()
+        assert lib.kfp16_net_get_dropout_seed(net.ptr, C.byref(s1)) == 0 and s1.value == base + 1
+        y1 = net.Output("tdnnf3")
+        assert np.mean((y0 == 0) != (y1 == 0)) > 0.05
+    finally:
+        lib.kfp16_ctx_set_stream(handle.ptr, None)
+        st.destroy()
+    net.Free()
+    # inference network: dropout off
+    inf = nnet.NewNetwork(nnet.BuildModelFromString(DROPNET), handle, n_seq, L, train=False)
+    for k, w in on.params.items():
+        inf.SetParam(k, w)
+    on_inf = OracleNet(DROPNET, n_seq, L, train=False)
+    on_inf.params = on.params
+    want = on_inf.forward({"input": x})["output"]
+    assert rel_to_scale(inf.Forward(x), want) <= 2e-3
+    inf.Free()

@@ -182,3 +182,24 @@ def test_affine_backward_vs_float64():
     X = O.to_f16_trunc(rng.uniform(-1, 1, (T, M)).astype(np.float32))
     assert O.max_err_vs_scale(O.affine_backward_weights(X, go), X.astype(np.float64).T @ go.astype(np.float64)) < 2e-3
     assert O.max_err_vs_scale(O.affine_backward_bias(go), go.astype(np.float64).sum(0, keepdims=True)) < 2e-3
+
+
+def test_dropout_hash_matches_the_library_host_function():
+    """oracle dropout_uniform == the integer hash compiled into the library (kfp16_dropout_uniform is a host function:
+    no GPU needed); inverted-dropout forward / backward follow go/gotorch/layers.go:365-399"""
+    from kaldi_fp16_b200 import _lib
+    lib = _lib.load()
+    rows, cols = np.arange(0, 4000, 37), np.arange(0, 1536, 11)
+    for seed in (0, 0xC0FFEE, 0xFFFFFFFF):
+        u = O.dropout_uniform(seed, rows, cols)
+        assert u.min() >= 0.0 and u.max() < 1.0
+        for i in (0, 5, len(rows) - 1):
+            for j in (0, 3, len(cols) - 1):
+                assert lib.kfp16_dropout_uniform(seed, int(rows[i]), int(cols[j])) == u[i, j]
+    u = O.dropout_uniform(123, np.arange(512), np.arange(512))
+    assert abs(u.mean() - 0.5) < 5e-3 and abs((u > 0.2).mean() - 0.8) < 5e-3
+    x = np.arange(12, dtype=np.float32).reshape(3, 4)
+    keep = np.array([[1, 0, 1, 1], [0, 0, 1, 1], [1, 1, 1, 0]], bool)
+    y = O.dropout_forward(x, keep, 0.5)
+    assert np.array_equal(y, np.where(keep, 2 * x, 0))
+    assert np.array_equal(O.dropout_backward(np.ones_like(x), keep, 0.5), np.where(keep, 2.0, 0.0).astype(np.float32))
