@@ -19,6 +19,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "kaldi_fp16_chain.h"
 #include "kaldi_fp16_fused.h"
 
 #ifdef __cplusplus
@@ -104,6 +105,16 @@ int kfp16_net_zero_grads(kfp16_net *net);
 /* loss = 0.5*||out||^2 over real rows of `layer` ("" = the layer named "output"), dOut = out */
 int kfp16_net_loss_half_sq(kfp16_net *net, const char *layer);
 int kfp16_net_set_output_grad(kfp16_net *net, const char *layer, const uint16_t *host_f16, int rows, int cols);
+/* chain LF-MMI objective on `layer` ("" = "output"): ComputeChainLossBatch (internal/nnet/chain_loss.go:221-294) in one
+ * launch.  Output frame t of every sequence is the layer's frame left_context + t*subsampling; the gradient is written on
+ * those rows of the layer's gradient buffer (zero elsewhere) and the accumulated loss (kfp16_net_read_loss) grows by the
+ * sum over sequences of -(num_logprob - den_logprob).  The chain object must have been created for this network's
+ * n_seq and hold the minibatch's numerator FSTs. */
+int kfp16_net_loss_chain(kfp16_net *net, const char *layer, kfp16_chain *chain, int subsampling, int left_context,
+                         float supervision_weight);
+/* make the chain objective the one the captured step graph (phase 1) computes instead of 0.5*||out||^2; chain = NULL
+ * switches back.  Call before kfp16_net_capture. */
+int kfp16_net_set_chain(kfp16_net *net, kfp16_chain *chain, int subsampling, int left_context, float supervision_weight);
 int kfp16_net_backward(kfp16_net *net);
 /* gradient wrt a layer's output, dense real rows (tests) */
 int kfp16_net_get_grad(kfp16_net *net, const char *layer, uint16_t *host_f16, int rows, int cols);

@@ -62,6 +62,14 @@ class WgradProb(C.Structure):
                 ("ws", c_void_p * 2), ("ws_ld", c_int), ("ws_transposed", c_int)]
 
 
+class ChainFst(C.Structure):
+    """struct kfp16_chain_fst (include/kaldi_fp16_chain.h): host CSR"""
+
+    _fields_ = [("row_ptr", c_void_p), ("col_idx", c_void_p), ("labels", c_void_p), ("weights", c_void_p),
+                ("final_states", c_void_p), ("final_weights", c_void_p),
+                ("num_states", c_int), ("num_arcs", c_int), ("num_final", c_int), ("start_state", c_int)]
+
+
 class NetOpts(C.Structure):
     """struct kfp16_net_opts (include/kaldi_fp16_nnet.h)."""
 
@@ -191,6 +199,16 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_capture": (c_int, [c_void_p, c_int]),
     "kfp16_net_launch": (c_int, [c_void_p, c_int]),
     "kfp16_net_launches_per_step": (c_int, [c_void_p, c_int]),
+    # ---- kaldi_fp16_chain.h
+    "kfp16_chain_create": (c_void_p, [c_void_p, c_int, c_int, c_int, C.POINTER(ChainFst)]),
+    "kfp16_chain_destroy": (None, [c_void_p]),
+    "kfp16_chain_set_numerators": (c_int, [c_void_p, C.POINTER(ChainFst), c_int]),
+    "kfp16_chain_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "kfp16_chain_read_results": (c_int, [c_void_p, c_void_p, c_int]),
+    "kfp16_chain_num_sequences": (c_int, [c_void_p]),
+    "kfp16_chain_frames": (c_int, [c_void_p]),
+    "kfp16_net_loss_chain": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int, c_float]),
+    "kfp16_net_set_chain": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float]),
     # ---- kaldi_fp16_ops.h
     "ops_cublas_create": (c_void_p, []),
     "ops_cublas_destroy": (None, [c_void_p]),

@@ -1,0 +1,346 @@
+// Chain LF-MMI objective, batched over the sequences of a minibatch (include/kaldi_fp16_chain.h).
+//
+// Replaces the reference's per-sequence chain_compute_loss (/root/reference/cpp/cuda/chain.cu:80-352,475: one kernel launch
+// per arc set per frame, a binary search per arc, atomic log-adds, cudaMalloc / cudaMemcpy / host sync per sequence) and
+// the Go loop around it (internal/nnet/chain_loss.go:221-294: ops_subsample_rows + an FST upload per sequence).  Same
+// arithmetic: log-semiring forward-backward over the numerator and the denominator FST,
+//   loss = -(num_logprob - den_logprob),  grad = clamp((den_post - num_post) * weight, +-30) as FP16.
+//
+// ONE launch for the whole minibatch: a CTA per sequence walks the frames itself (block barriers between frames, no host
+// involvement), the network-output row of the current frame is staged in shared memory as FP32, states are spread over
+// the threads, each state reduces its incoming (forward) / outgoing (backward) arcs in a fixed order -- no atomics on
+// alpha / beta, deterministic -- and the posteriors of a frame are accumulated in shared memory during the backward step
+// of that frame, so the gradient row is written once.  The x3 output-row subsampling (ops_subsample_rows, ops.cu:290-304)
+// is a row stride of the read; the gradient lands on the same rows.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/kaldi_fp16_chain.h"
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+using namespace kfp16;
+
+namespace {
+
+constexpr float kLogZero = -1.0e+30f;   // chain.cu:20
+constexpr int kChainThreads = 1024;
+
+struct DevFst {
+  // outgoing arcs (CSR by source, as given) and incoming arcs (CSR by destination, built at upload)
+  int *out_ptr = nullptr, *out_dst = nullptr, *out_pdf = nullptr;
+  float* out_w = nullptr;
+  int *in_ptr = nullptr, *in_src = nullptr, *in_pdf = nullptr;
+  float* in_w = nullptr;
+  int *final_state = nullptr;
+  float* final_w = nullptr;
+  int S = 0, A = 0, F = 0, start = 0;
+};
+
+// one sequence's view of an FST inside a concatenated batch (numerators) or the shared denominator graph
+struct FstRef {
+  const int *out_ptr, *out_dst, *out_pdf;
+  const float* out_w;
+  const int *in_ptr, *in_src, *in_pdf;
+  const float* in_w;
+  const int* final_state;
+  const float* final_w;
+  int S, F, start;
+};
+
+struct ChainArgs {
+  const __half* nnet;      // row of (sequence s, output frame t) = nnet + ((size_t)s * seq_rows + row0 + t * row_step) * ld
+  __half* grad;            // same addressing (may be null)
+  int ld, seq_rows, row0, row_step;
+  int T, P;
+  float weight;
+  float* alpha_num; float* alpha_den;   // [n_seq][(T + 1) * Smax]
+  float* beta;                          // [n_seq][2 * (Snum_max + Sden)]
+  int snum_max, sden;
+  float* result;                        // [n_seq][4]: num_logprob, den_logprob, loss, 0
+  float* loss_accum;                    // += loss of every sequence (may be null)
+};
+
+__device__ __forceinline__ float log_add(float a, float b) {   // chain.cu:44-66 without the CAS loop
+  if (b <= kLogZero) return a;
+  if (a <= kLogZero) return b;
+  const float mx = fmaxf(a, b), mn = fminf(a, b);
+  return mx + log1pf(expf(mn - mx));
+}
+
+// forward pass of one FST over all frames; alpha: [(T + 1) x S]
+__device__ void chain_forward(const FstRef& f, const ChainArgs& a, const __half* nnet_seq, float* alpha, float* row) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int s = tid; s < f.S; s += nt) alpha[s] = s == f.start ? 0.0f : kLogZero;
+  for (int t = 0; t < a.T; ++t) {
+    const __half* src_row = nnet_seq + (size_t)t * a.row_step * a.ld;
+    __syncthreads();                                   // alpha[t] complete, previous row no longer read
+    for (int p = tid; p < a.P; p += nt) row[p] = __half2float(src_row[p]);
+    __syncthreads();
+    const float* at = alpha + (size_t)t * f.S;
+    float* an = alpha + (size_t)(t + 1) * f.S;
+    for (int d = tid; d < f.S; d += nt) {
+      float acc = kLogZero;
+      for (int e = f.in_ptr[d]; e < f.in_ptr[d + 1]; ++e) {
+        const int pdf = f.in_pdf[e];
+        if (pdf <= 0 || pdf > a.P) continue;           // epsilon arcs are skipped (chain.cu:118-121)
+        const float sa = at[f.in_src[e]];
+        if (sa <= kLogZero) continue;
+        acc = log_add(acc, sa + row[pdf - 1] + f.in_w[e]);
+      }
+      an[d] = acc;
+    }
+  }
+  __syncthreads();
+}
+
+// total = log-sum over the final states of alpha[T][s] + final weight (chain.cu kernel_total_logprob, same order)
+__device__ float chain_total(const FstRef& f, const float* alphaT) {
+  float total = kLogZero;
+  for (int i = 0; i < f.F; ++i) {
+    const float v = alphaT[f.final_state[i]] + f.final_w[i];
+    if (total <= kLogZero) total = v;
+    else if (v > kLogZero) {
+      const float mx = fmaxf(total, v), mn = fminf(total, v);
+      total = mx + log1pf(expf(mn - mx));
+    }
+  }
+  return total;
+}
+
+// one backward step of one FST at frame t: beta_t[s] from beta_n (= beta[t+1]); posteriors added into post[] with `sign`
+__device__ void chain_backward_step(const FstRef& f, const ChainArgs& a, const float* alpha_t, const float* beta_n,
+                                    float* beta_t, const float* row, float* post, float total, float sign) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int s = tid; s < f.S; s += nt) {
+    float acc = kLogZero;
+    const float as = alpha_t[s];
+    for (int e = f.out_ptr[s]; e < f.out_ptr[s + 1]; ++e) {
+      const int pdf = f.out_pdf[e];
+      if (pdf <= 0 || pdf > a.P) continue;
+      const float b = beta_n[f.out_dst[e]];
+      if (b <= kLogZero) continue;
+      const float v = b + row[pdf - 1] + f.out_w[e];
+      acc = log_add(acc, v);
+      if (post != nullptr && as > kLogZero) {           // chain.cu kernel_chain_posteriors
+        float lp = as + v - total;
+        if (lp > 0.0f) lp = 0.0f;
+        atomicAdd(&post[pdf - 1], sign * expf(lp));
+      }
+    }
+    beta_t[s] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kChainThreads)
+chain_loss_kernel(ChainArgs a, const FstRef* __restrict__ nums, FstRef den) {
+  extern __shared__ float smem_f[];
+  float* row = smem_f;              // [P] network output of the current frame, FP32
+  float* post = smem_f + a.P;       // [P] den_post - num_post of the current frame
+  __shared__ float totals[2];
+  const int seq = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const FstRef num = nums[seq];
+  const __half* nnet_seq = a.nnet + ((size_t)seq * a.seq_rows + a.row0) * a.ld;
+  float* alpha_num = a.alpha_num + (size_t)seq * (a.T + 1) * a.snum_max;
+  float* alpha_den = a.alpha_den + (size_t)seq * (a.T + 1) * a.sden;
+  float* beta = a.beta + (size_t)seq * 2 * (a.snum_max + a.sden);
+  float* bnum[2] = {beta, beta + a.snum_max};
+  float* bden[2] = {beta + 2 * a.snum_max, beta + 2 * a.snum_max + a.sden};
+
+  chain_forward(num, a, nnet_seq, alpha_num, row);
+  chain_forward(den, a, nnet_seq, alpha_den, row);
+  if (tid == 0) totals[0] = chain_total(num, alpha_num + (size_t)a.T * num.S);
+  if (tid == 32) totals[1] = chain_total(den, alpha_den + (size_t)a.T * den.S);
+  // beta[T]: final weights, log-zero elsewhere (chain.cu kernel_set_finals)
+  for (int s = tid; s < num.S; s += nt) bnum[a.T & 1][s] = kLogZero;
+  for (int s = tid; s < den.S; s += nt) bden[a.T & 1][s] = kLogZero;
+  __syncthreads();
+  if (tid == 0) for (int i = 0; i < num.F; ++i) bnum[a.T & 1][num.final_state[i]] = num.final_w[i];
+  if (tid == 32) for (int i = 0; i < den.F; ++i) bden[a.T & 1][den.final_state[i]] = den.final_w[i];
+  const float tot_num = totals[0], tot_den = totals[1];
+  if (tid == 0) {
+    float* r = a.result + (size_t)seq * 4;
+    r[0] = tot_num; r[1] = tot_den; r[2] = -(tot_num - tot_den); r[3] = 0.f;
+    if (a.loss_accum) atomicAdd(a.loss_accum, -(tot_num - tot_den));
+  }
+  if (a.grad == nullptr) return;
+  __half* grad_seq = a.grad + ((size_t)seq * a.seq_rows + a.row0) * a.ld;
+  for (int t = a.T - 1; t >= 0; --t) {
+    const __half* src_row = nnet_seq + (size_t)t * a.row_step * a.ld;
+    __syncthreads();                                   // beta[t+1] complete; previous frame's gradient row written
+    for (int p = tid; p < a.P; p += nt) { row[p] = __half2float(src_row[p]); post[p] = 0.f; }
+    __syncthreads();
+    chain_backward_step(num, a, alpha_num + (size_t)t * num.S, bnum[(t + 1) & 1], bnum[t & 1], row, post, tot_num, -1.0f);
+    chain_backward_step(den, a, alpha_den + (size_t)t * den.S, bden[(t + 1) & 1], bden[t & 1], row, post, tot_den, 1.0f);
+    __syncthreads();
+    __half* dst_row = grad_seq + (size_t)t * a.row_step * a.ld;
+    for (int p = tid; p < a.P; p += nt) {              // chain.cu kernel_chain_gradient
+      float g = post[p] * a.weight;
+      g = fmaxf(-30.0f, fminf(30.0f, g));
+      dst_row[p] = __float2half(g);
+    }
+  }
+}
+
+bool upload(void** dev, const void* host, size_t bytes) {
+  if (bytes == 0) bytes = 4;
+  if (!check_cuda(cudaMalloc(dev, bytes), "cudaMalloc (chain)")) return false;
+  return host == nullptr || check_cuda(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice), "chain upload");
+}
+
+// CSR by source -> also CSR by destination; validates indices
+bool build_fst(DevFst& f, const kfp16_chain_fst& h, const char* what) {
+  if (h.num_states < 1 || h.num_arcs < 0 || !h.row_ptr || (h.num_arcs && (!h.col_idx || !h.labels || !h.weights)) ||
+      h.start_state < 0 || h.start_state >= h.num_states || h.num_final < 0 || (h.num_final && (!h.final_states || !h.final_weights))) {
+    set_error("%s: malformed FST (states %d arcs %d finals %d start %d)", what, h.num_states, h.num_arcs, h.num_final, h.start_state);
+    return false;
+  }
+  const int S = h.num_states, A = h.num_arcs;
+  if (h.row_ptr[0] != 0 || h.row_ptr[S] != A) { set_error("%s: row_ptr must run from 0 to num_arcs", what); return false; }
+  std::vector<int> in_ptr(S + 1, 0), in_src(A), in_pdf(A);
+  std::vector<float> in_w(A);
+  for (int s = 0; s < S; ++s) {
+    if (h.row_ptr[s + 1] < h.row_ptr[s]) { set_error("%s: row_ptr not monotone", what); return false; }
+    for (int e = h.row_ptr[s]; e < h.row_ptr[s + 1]; ++e) {
+      if (h.col_idx[e] < 0 || h.col_idx[e] >= S) { set_error("%s: arc %d points to state %d of %d", what, e, h.col_idx[e], S); return false; }
+      in_ptr[h.col_idx[e] + 1]++;
+    }
+  }
+  for (int s = 0; s < S; ++s) in_ptr[s + 1] += in_ptr[s];
+  std::vector<int> fill(in_ptr.begin(), in_ptr.end() - 1);
+  for (int s = 0; s < S; ++s)
+    for (int e = h.row_ptr[s]; e < h.row_ptr[s + 1]; ++e) {
+      const int k = fill[h.col_idx[e]]++;
+      in_src[k] = s; in_pdf[k] = h.labels[e]; in_w[k] = h.weights[e];
+    }
+  for (int i = 0; i < h.num_final; ++i)
+    if (h.final_states[i] < 0 || h.final_states[i] >= S) { set_error("%s: final state out of range", what); return false; }
+  f.S = S; f.A = A; f.F = h.num_final; f.start = h.start_state;
+  return upload((void**)&f.out_ptr, h.row_ptr, (S + 1) * 4) && upload((void**)&f.out_dst, h.col_idx, (size_t)A * 4) &&
+         upload((void**)&f.out_pdf, h.labels, (size_t)A * 4) && upload((void**)&f.out_w, h.weights, (size_t)A * 4) &&
+         upload((void**)&f.in_ptr, in_ptr.data(), (S + 1) * 4) && upload((void**)&f.in_src, in_src.data(), (size_t)A * 4) &&
+         upload((void**)&f.in_pdf, in_pdf.data(), (size_t)A * 4) && upload((void**)&f.in_w, in_w.data(), (size_t)A * 4) &&
+         upload((void**)&f.final_state, h.final_states, (size_t)h.num_final * 4) && upload((void**)&f.final_w, h.final_weights, (size_t)h.num_final * 4);
+}
+void free_fst(DevFst& f) {
+  for (void* p : {(void*)f.out_ptr, (void*)f.out_dst, (void*)f.out_pdf, (void*)f.out_w, (void*)f.in_ptr, (void*)f.in_src,
+                  (void*)f.in_pdf, (void*)f.in_w, (void*)f.final_state, (void*)f.final_w})
+    if (p) cudaFree(p);
+  f = DevFst();
+}
+FstRef ref_of(const DevFst& f) {
+  return FstRef{f.out_ptr, f.out_dst, f.out_pdf, f.out_w, f.in_ptr, f.in_src, f.in_pdf, f.in_w, f.final_state, f.final_w, f.S, f.F, f.start};
+}
+
+}  // namespace
+
+struct kfp16_chain {
+  kfp16_ctx* ctx = nullptr;
+  int num_pdfs = 0, n_seq = 0, frames = 0;
+  DevFst den;
+  std::vector<DevFst> nums;
+  FstRef* nums_dev = nullptr;
+  int snum_max = 0;
+  float *alpha_num = nullptr, *alpha_den = nullptr, *beta = nullptr, *result = nullptr;
+  size_t alpha_num_elems = 0;
+};
+
+extern "C" {
+
+kfp16_chain* kfp16_chain_create(kfp16_ctx* ctx, int num_pdfs, int n_seq, int frames_per_seq, const kfp16_chain_fst* den) {
+  if (!ctx || !den || num_pdfs < 1 || n_seq < 1 || frames_per_seq < 1) { set_error("kfp16_chain_create: bad argument"); return nullptr; }
+  if ((size_t)num_pdfs * 8 > 200 * 1024) { set_error("kfp16_chain_create: %d pdfs exceed the shared-memory row buffers", num_pdfs); return nullptr; }
+  if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return nullptr;
+  kfp16_chain* c = new kfp16_chain();
+  c->ctx = ctx; c->num_pdfs = num_pdfs; c->n_seq = n_seq; c->frames = frames_per_seq;
+  if (!build_fst(c->den, *den, "kfp16_chain_create (denominator)") ||
+      !upload((void**)&c->alpha_den, nullptr, (size_t)n_seq * (frames_per_seq + 1) * c->den.S * 4) ||
+      !upload((void**)&c->result, nullptr, (size_t)n_seq * 4 * 4) ||
+      !upload((void**)&c->nums_dev, nullptr, (size_t)n_seq * sizeof(FstRef))) {
+    kfp16_chain_destroy(c);
+    return nullptr;
+  }
+  c->nums.resize(n_seq);
+  return c;
+}
+
+void kfp16_chain_destroy(kfp16_chain* c) {
+  if (!c) return;
+  free_fst(c->den);
+  for (DevFst& f : c->nums) free_fst(f);
+  for (void* p : {(void*)c->nums_dev, (void*)c->alpha_num, (void*)c->alpha_den, (void*)c->beta, (void*)c->result})
+    if (p) cudaFree(p);
+  delete c;
+}
+
+// numerator FSTs of the current minibatch (per-sequence supervision, batch.PerSeqCSRs in train_step.go:183-193)
+int kfp16_chain_set_numerators(kfp16_chain* c, const kfp16_chain_fst* nums, int n_seq) {
+  if (!c || !nums || n_seq != c->n_seq) { set_error("kfp16_chain_set_numerators: expected %d numerator FSTs", c ? c->n_seq : 0); return -1; }
+  if (!check_cuda(cudaSetDevice(c->ctx->device), "cudaSetDevice") || !check_cuda(cudaStreamSynchronize(c->ctx->stream), "sync")) return -1;
+  std::vector<FstRef> refs(n_seq);
+  int smax = 1;
+  for (int i = 0; i < n_seq; ++i) {
+    free_fst(c->nums[i]);
+    if (!build_fst(c->nums[i], nums[i], "kfp16_chain_set_numerators")) return -1;
+    refs[i] = ref_of(c->nums[i]);
+    smax = std::max(smax, c->nums[i].S);
+  }
+  if (!check_cuda(cudaMemcpy(c->nums_dev, refs.data(), sizeof(FstRef) * n_seq, cudaMemcpyHostToDevice), "numerator table upload")) return -1;
+  const size_t need = (size_t)n_seq * (c->frames + 1) * smax;
+  if (need > c->alpha_num_elems || smax != c->snum_max) {
+    if (c->alpha_num) cudaFree(c->alpha_num);
+    if (c->beta) cudaFree(c->beta);
+    c->alpha_num = c->beta = nullptr;
+    if (!upload((void**)&c->alpha_num, nullptr, need * 4) ||
+        !upload((void**)&c->beta, nullptr, (size_t)n_seq * 2 * (smax + c->den.S) * 4)) return -1;
+    c->alpha_num_elems = need;
+    c->snum_max = smax;
+  }
+  return 0;
+}
+
+int kfp16_chain_loss(kfp16_chain* c, const void* nnet_out, void* grad_out, int ld, int seq_rows, int row0, int row_step,
+                     float supervision_weight, float* loss_accum_dev) {
+  if (!c || !nnet_out) { set_error("kfp16_chain_loss: null argument"); return -1; }
+  if (!c->alpha_num) { set_error("kfp16_chain_loss: no numerator FSTs set (kfp16_chain_set_numerators)"); return -1; }
+  if (ld < c->num_pdfs || row_step < 1 || row0 < 0 || row0 + (c->frames - 1) * row_step >= seq_rows) {
+    set_error("kfp16_chain_loss: %d output frames at rows %d + k*%d do not fit a sequence block of %d rows (ld %d, %d pdfs)",
+              c->frames, row0, row_step, seq_rows, ld, c->num_pdfs);
+    return -1;
+  }
+  if (!check_cuda(cudaSetDevice(c->ctx->device), "cudaSetDevice")) return -1;
+  ChainArgs a;
+  a.nnet = (const __half*)nnet_out; a.grad = (__half*)grad_out;
+  a.ld = ld; a.seq_rows = seq_rows; a.row0 = row0; a.row_step = row_step;
+  a.T = c->frames; a.P = c->num_pdfs; a.weight = supervision_weight;
+  a.alpha_num = c->alpha_num; a.alpha_den = c->alpha_den; a.beta = c->beta;
+  a.snum_max = c->snum_max; a.sden = c->den.S;
+  a.result = c->result; a.loss_accum = loss_accum_dev;
+  const size_t smem = (size_t)c->num_pdfs * 2 * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (!check_cuda(cudaFuncSetAttribute(chain_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute(chain)")) return -1;
+    attr_done = true;
+  }
+  chain_loss_kernel<<<c->n_seq, kChainThreads, smem, c->ctx->stream>>>(a, c->nums_dev, ref_of(c->den));
+  count_launch();
+  return check_launch("kfp16_chain_loss") ? 0 : -1;
+}
+
+int kfp16_chain_read_results(kfp16_chain* c, float* host, int n_seq) {
+  if (!c || !host || n_seq != c->n_seq) { set_error("kfp16_chain_read_results: bad argument"); return -1; }
+  if (!check_cuda(cudaStreamSynchronize(c->ctx->stream), "sync")) return -1;
+  return check_cuda(cudaMemcpy(host, c->result, (size_t)n_seq * 4 * sizeof(float), cudaMemcpyDeviceToHost), "chain results download") ? 0 : -1;
+}
+
+int kfp16_chain_num_sequences(const kfp16_chain* c) { return c ? c->n_seq : 0; }
+int kfp16_chain_frames(const kfp16_chain* c) { return c ? c->frames : 0; }
+
+}  // extern "C"

@@ -146,6 +146,10 @@ struct kfp16_net {
   bool seg_export_f16 = false;                       // each segment ends by exporting its gradient range to the FP16 bucket
   std::map<int, int> graph_launches;
   int out_layer = -1;
+  // objective of the captured step: the chain LF-MMI loss when set, else 0.5*||out||^2
+  kfp16_chain* chain = nullptr;
+  int chain_sub = 3, chain_left = 0;
+  float chain_weight = 1.0f;
 };
 
 namespace {
@@ -1272,7 +1276,7 @@ int run_phases(kfp16_net* n, int phases) {
     if (kfp16_bump_counter(n->ctx, n->seed_dev)) return -1;     // a new dropout mask per step, graph replays included
     if (kfp16_net_zero_grads(n)) return -1;
     if (kfp16_net_forward(n)) return -1;
-    if (kfp16_net_loss_half_sq(n, "")) return -1;
+    if (n->chain ? kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight) : kfp16_net_loss_half_sq(n, "")) return -1;
     if (kfp16_net_backward(n)) return -1;
   }
   if (phases & 4) {
@@ -1607,6 +1611,27 @@ int kfp16_net_loss_half_sq(kfp16_net* n, const char* layer) {
   return kfp16_half_sq_loss(n->ctx, l.out.p, l.dout.p, n->opts.n_seq, n->opts.seq_len, n->halo, l.out_dim, n->loss_dev);
 }
 
+int kfp16_net_loss_chain(kfp16_net* n, const char* layer, kfp16_chain* chain, int subsampling, int left_context, float weight) {
+  if (!n || !chain) { set_error("kfp16_net_loss_chain: null argument"); return -1; }
+  const int i = (!layer || layer[0] == 0) ? n->out_layer : find_layer(n, layer);
+  if (i < 0) { set_error("kfp16_net_loss_chain: no such layer"); return -1; }
+  Layer& l = n->layers[i];
+  if (!l.dout.p || l.per_seq) { set_error("kfp16_net_loss_chain: layer %s has no per-frame gradient buffer (train = 0?)", l.name.c_str()); return -1; }
+  if (kfp16_chain_num_sequences(chain) != n->opts.n_seq) { set_error("kfp16_net_loss_chain: the chain object is for %d sequences, the network for %d", kfp16_chain_num_sequences(chain), n->opts.n_seq); return -1; }
+  if (subsampling < 1 || left_context < 0 || left_context + (kfp16_chain_frames(chain) - 1) * subsampling >= n->opts.seq_len) {
+    set_error("kfp16_net_loss_chain: %d output frames at %d + t*%d exceed the %d frames of a sequence", kfp16_chain_frames(chain), left_context, subsampling, n->opts.seq_len);
+    return -1;
+  }
+  // the gradient is zero on every row that is not an output frame (and on the halo rows)
+  if (!check_cuda(cudaMemsetAsync(l.dout.p, 0, l.dout.bytes(), n->ctx->stream), "chain gradient clear")) return -1;
+  return kfp16_chain_loss(chain, l.out.p, l.dout.p, l.out_dim, n->blk, n->halo + left_context, subsampling, weight, n->loss_dev);
+}
+int kfp16_net_set_chain(kfp16_net* n, kfp16_chain* chain, int subsampling, int left_context, float weight) {
+  if (!n) { set_error("kfp16_net_set_chain: null network"); return -1; }
+  n->chain = chain; n->chain_sub = subsampling; n->chain_left = left_context; n->chain_weight = weight;
+  return 0;
+}
+
 int kfp16_net_set_output_grad(kfp16_net* n, const char* layer, const uint16_t* host, int rows, int cols) {
   if (!n || !host) { set_error("kfp16_net_set_output_grad: null argument"); return -1; }
   const int i = (!layer || layer[0] == 0) ? n->out_layer : find_layer(n, layer);
@@ -1790,7 +1815,8 @@ static int first_param_of_layer(const Layer& l) {
 static int run_segment(kfp16_net* n, int seg) {
   const int hi = seg == 0 ? (int)n->layers.size() : n->seg_lo[seg - 1];
   if (seg == 0) {
-    if (kfp16_net_zero_grads(n) || kfp16_net_forward(n) || kfp16_net_loss_half_sq(n, "")) return -1;
+    if (kfp16_net_zero_grads(n) || kfp16_net_forward(n)) return -1;
+    if (n->chain ? kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight) : kfp16_net_loss_half_sq(n, "")) return -1;
   }
   if (backward_range(n, hi, n->seg_lo[seg], seg == 0)) return -1;
   if (flush_wgrads(n)) return -1;      // the segment's gradient range must be complete when it ends

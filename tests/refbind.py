@@ -49,8 +49,16 @@ def load_ref():
         "launch_pointwise_conv1d_fp16": (None, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
         "launch_batchnorm1d_forward_fp16": (None, [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, cf, cf, C.c_bool, vp]),
     }
+    sig.update({
+        "bridge_transfer_int32": (ci, [vp, vp, C.c_size_t]),
+        "chain_compute_loss": (ci, [vp, vp, vp, ci, ci, vp, vp]),
+        "chain_last_error": (C.c_char_p, []),
+    })
     for name, (res, args) in sig.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:          # an older build of the reference library without the chain objects
+            continue
         fn.restype, fn.argtypes = res, args
     _ref = lib
     return lib
@@ -91,3 +99,39 @@ class RefBuf:
 def ref_half(lib, x_f32: np.ndarray) -> RefBuf:
     """upload fp16-representable float32 values as fp16"""
     return RefBuf(lib, np.ascontiguousarray(x_f32, dtype=np.float32).astype(np.float16).view(np.uint16))
+
+
+class RefChainFst(C.Structure):
+    """struct ChainFstGPU (reference cpp/include/chain.h:24-36): CSR with DEVICE pointers"""
+    _fields_ = [("row_ptr", C.c_void_p), ("col_idx", C.c_void_p), ("labels", C.c_void_p), ("weights", C.c_void_p),
+                ("final_states", C.c_void_p), ("final_weights", C.c_void_p),
+                ("num_states", C.c_int), ("num_arcs", C.c_int), ("num_final", C.c_int), ("start_state", C.c_int)]
+
+
+class RefChainResult(C.Structure):
+    _fields_ = [("num_logprob", C.c_float), ("den_logprob", C.c_float), ("loss", C.c_float)]
+
+
+def ref_chain_fst(lib, fst) -> tuple:
+    """upload an oracle.chain_oracle.Fst through the reference's own bridge; returns (struct, buffers to free)"""
+    bufs = []
+
+    def up_i32(a):
+        a = np.ascontiguousarray(a, np.int32)
+        p = lib.bridge_gpu_malloc(max(a.nbytes, 16))
+        assert p and (a.size == 0 or lib.bridge_transfer_int32(p, a.ctypes.data, a.size) == 0)
+        bufs.append(p)
+        return p
+
+    def up_f32(a):
+        a = np.ascontiguousarray(a, np.float32)
+        p = lib.bridge_gpu_malloc(max(a.nbytes, 16))
+        assert p and (a.size == 0 or lib.bridge_transfer_float32(p, a.ctypes.data, a.size) == 0)
+        bufs.append(p)
+        return p
+
+    f = RefChainFst()
+    f.row_ptr, f.col_idx, f.labels, f.weights = up_i32(fst.row_ptr), up_i32(fst.col_idx), up_i32(fst.labels), up_f32(fst.weights)
+    f.final_states, f.final_weights = up_i32(fst.final_states), up_f32(fst.final_weights)
+    f.num_states, f.num_arcs, f.num_final, f.start_state = fst.num_states, fst.num_arcs, len(fst.final_states), fst.start_state
+    return f, bufs

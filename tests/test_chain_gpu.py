@@ -1,0 +1,161 @@
+"""Chain LF-MMI objective on the GPU (kfp16_chain_*, one launch per minibatch) against
+  (a) the numpy oracle (oracle/chain_oracle.py, restating cpp/cuda/chain.cu), and
+  (b) the REFERENCE'S OWN chain.cu compiled unmodified into oracle/_ref, called per sequence on materialised
+      subsampled rows the way internal/nnet/chain_loss.go:221-294 does.
+Tolerances: objective per frame |delta| <= 1e-3; gradient (FP16 posteriors in [-1, 1]) |delta| <= 2e-3."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from kaldi_fp16_b200 import chain as KC
+from kaldi_fp16_b200 import gpu, nnet
+from oracle import chain_oracle as CO
+from oracle import kaldi_oracle as O
+from oracle.nnet_oracle import OracleNet
+from tests.refbind import RefBuf, RefChainResult, ref_chain_fst
+
+pytestmark = pytest.mark.gpu
+
+
+def to_kc(f: CO.Fst) -> KC.ChainFst:
+    return KC.ChainFst(f.row_ptr, f.col_idx, f.labels, f.weights, f.final_states, f.final_weights, f.start_state)
+
+
+def make_case(rng, n_seq, frames, P, den_states, arcs, branching_num=False):
+    den = CO.random_ergodic_fst(rng, den_states, arcs, P)
+    nums = []
+    for s in range(n_seq):
+        f = CO.linear_chain_fst(frames, P, offset=int(rng.integers(P)))
+        if branching_num:      # alternative pronunciation: a second arc on some frames (two paths through the numerator)
+            extra_src = np.arange(0, frames, 3, dtype=np.int32)
+            order = np.argsort(np.concatenate([np.arange(frames), extra_src]), kind="stable")
+            src = np.concatenate([np.arange(frames), extra_src])[order]
+            dst = np.concatenate([np.arange(1, frames + 1), extra_src + 1])[order].astype(np.int32)
+            lab = np.concatenate([f.labels, ((extra_src * 7 + s) % P + 1)])[order].astype(np.int32)
+            w = np.concatenate([np.full(frames, -0.3), np.full(len(extra_src), -1.2)])[order].astype(np.float32)
+            row_ptr = np.searchsorted(src, np.arange(frames + 2)).astype(np.int32)
+            f = CO.Fst(row_ptr, dst, lab, w, f.final_states, f.final_weights, 0)
+        nums.append(f)
+    return den, nums
+
+
+@pytest.mark.parametrize("n_seq,seq_rows,frames,sub,left,P,S,arcs,branch", [
+    (4, 40, 12, 3, 1, 48, 16, 3, False),
+    (6, 31, 10, 3, 0, 104, 64, 4, True),
+    (3, 20, 20, 1, 0, 3080, 40, 5, True),        # ragged pdf count, no subsampling
+    (64, 156, 50, 3, 3, 6016, 256, 4, False),    # the benchmark's shape: 64 sequences x 50 output frames, 6016 pdfs
+])
+def test_batched_chain_objective_matches_oracle_and_reference(handle, lib, reflib, n_seq, seq_rows, frames, sub, left, P, S, arcs, branch):
+    rng = np.random.default_rng(n_seq * 1000 + P)
+    den, nums = make_case(rng, n_seq, frames, P, S, arcs, branch)
+    out = O.to_f16_rne((rng.standard_normal((n_seq * seq_rows, P)) * 0.7).astype(np.float32))
+    t_out = gpu.TensorFromFP16(out)
+    t_grad = gpu.TensorFromFP16(np.full_like(out, 3.0))
+    obj = KC.ChainObjective(handle, P, n_seq, frames, to_kc(den))
+    obj.SetNumerators([to_kc(f) for f in nums])
+    weight = 0.75
+    loss_acc = gpu.DeviceF32(n=4)
+    assert lib.kfp16_chain_loss(obj.ptr, t_out.Ptr, t_grad.Ptr, P, seq_rows, left, sub, weight, loss_acc.Ptr) == 0, lib.kfp16_last_error()
+    gpu.Sync()
+    res = obj.Results()
+    got_grad = t_grad.ToFP32()
+    # ---- (a) numpy oracle
+    want_res, want_grad = CO.chain_loss_batch(out, nums, den, n_seq, seq_rows, frames, sub, left, weight)
+    assert np.abs(res.PerSeq[:, 0] - want_res[:, 0]).max() / frames <= 1e-3
+    assert np.abs(res.PerSeq[:, 1] - want_res[:, 1]).max() / frames <= 1e-3
+    assert np.abs(res.PerSeq[:, 2] - want_res[:, 2]).max() / frames <= 1e-3
+    assert abs(loss_acc.ToHost()[0] - want_res[:, 2].sum()) <= 1e-3 * frames * n_seq
+    used = np.zeros(n_seq * seq_rows, bool)
+    for s in range(n_seq):
+        used[s * seq_rows + left + np.arange(frames) * sub] = True
+    assert np.abs(got_grad[used] - want_grad[used]).max() <= 2e-3
+    assert np.all(got_grad[~used] == 3.0)            # rows off the subsampling grid are not touched
+    # ---- (b) the reference's chain_compute_loss, per sequence on materialised subsampled rows (a few sequences)
+    den_ref, den_bufs = ref_chain_fst(reflib, den)
+    for s in list(range(n_seq))[:4]:
+        rows = s * seq_rows + left + np.arange(frames) * sub
+        sub_out = RefBuf(reflib, np.ascontiguousarray(out[rows]).astype(np.float16).view(np.uint16))
+        g = RefBuf(reflib, np.zeros((frames, P), np.uint16))
+        num_ref, num_bufs = ref_chain_fst(reflib, nums[s])
+        r = RefChainResult()
+        assert reflib.chain_compute_loss(sub_out.ptr, C.byref(num_ref), C.byref(den_ref), frames, P, g.ptr, C.byref(r)) == 0, reflib.chain_last_error()
+        assert abs(res.PerSeq[s, 0] - r.num_logprob) / frames <= 1e-3, (s, res.PerSeq[s], r.num_logprob)
+        assert abs(res.PerSeq[s, 1] - r.den_logprob) / frames <= 1e-3, (s, res.PerSeq[s], r.den_logprob)
+        # the reference's gradient is unweighted here? no: chain_compute_loss applies supervision weight 1.0
+        ref_grad = g.f32() * np.float32(weight)
+        assert np.abs(got_grad[rows] - ref_grad).max() <= 2e-3 + 2.0 ** -10, s
+        for p in num_bufs:
+            reflib.bridge_gpu_free(p)
+        sub_out.free()
+        g.free()
+    for p in den_bufs:
+        reflib.bridge_gpu_free(p)
+    obj.Free()
+    t_out.Free()
+    t_grad.Free()
+
+
+CHAIN_NET = """
+input name=input dim=64
+linear-component name=lin0 dim=256
+tdnnf-layer name=tdnnf1 dim=256 bottleneck-dim=64 time-stride=3 bypass-scale=0.66
+tdnnf-layer name=tdnnf2 dim=256 bottleneck-dim=64 time-stride=3 bypass-scale=0.66
+linear-component name=prefinal-l dim=64
+prefinal-layer name=prefinal-chain input=prefinal-l big-dim=256 small-dim=64
+output-layer name=output include-log-softmax=false dim=104
+"""
+
+
+def test_chain_training_step(handle, lib):
+    """forward -> ComputeChainLossBatch -> Backward on a TDNN-F net: the parameter gradients equal the oracle's backward of
+    the oracle's chain gradient; a captured step graph with the chain objective reproduces it; SGD on it lowers the loss"""
+    n_seq, L, frames, sub, left, P = 4, 45, 14, 3, 1, 104
+    rng = np.random.default_rng(99)
+    on = OracleNet(CHAIN_NET, n_seq, L)
+    on.init_random(rng)
+    net = nnet.NewNetwork(nnet.BuildModelFromString(CHAIN_NET), handle, n_seq, L, ref_round=True, lr=5e-4, momentum=0.0)
+    for k, w in on.params.items():
+        net.SetParam(k, w)
+    den, nums = make_case(rng, n_seq, frames, P, 24, 4)
+    obj = KC.ChainObjective(handle, P, n_seq, frames, to_kc(den))
+    obj.SetNumerators([to_kc(f) for f in nums])
+    x = O.to_f16_rne(rng.standard_normal((n_seq * L, 64)).astype(np.float32))
+    acts = on.forward({"input": x})
+    want_res, dy = CO.chain_loss_batch(acts["output"], nums, den, n_seq, L, frames, sub, left)
+    net.SetInput("input", x)
+    net.ZeroGrads()
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    net.ReadLoss()
+    r = KC.ComputeChainLossBatch(net, obj, sub, left)
+    assert abs(r.Loss - want_res[:, 2].mean()) / frames <= 1e-3
+    assert np.abs(net.Grad("output") - dy).max() <= 3e-3
+    assert lib.kfp16_net_backward(net.ptr) == 0
+    assert abs(net.ReadLoss() - want_res[:, 2].sum()) <= 1e-3 * frames * n_seq
+    masks = {l.name: net.Mask(l.name, on.saved[l.name]["mask"].shape[1]) for l in on.layers if l.type in ("tdnnf-layer", "prefinal-layer")}
+    wg, _ = on.backward("output", dy, masks)
+    got = net.WeightGrads()
+    for k, g in wg.items():
+        err = O.max_err_vs_scale(got[k], g)
+        assert err <= (2e-2 if k.endswith("Bias") else 1e-2), f"{k}: {err:.2e}"     # FP16 posterior gradients: coarser than dY = Y
+    # captured step with the chain objective + SGD: the loss goes down
+    from kaldi_fp16_b200 import cudart
+    st = cudart.Stream()
+    lib.kfp16_ctx_set_stream(handle.ptr, st.ptr)
+    try:
+        assert lib.kfp16_net_set_chain(net.ptr, obj.ptr, sub, left, 1.0) == 0
+        net.Capture(3)
+        losses = []
+        net.ReadLoss()
+        for _ in range(4):      # (a random denominator graph does not bound the objective: a few steps only)
+            net.Launch(3)
+            st.synchronize()
+            losses.append(net.ReadLoss())
+        assert abs(losses[0] - want_res[:, 2].sum()) <= 1e-3 * frames * n_seq
+        assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    finally:
+        lib.kfp16_net_set_chain(net.ptr, None, 3, 0, 1.0)
+        lib.kfp16_ctx_set_stream(handle.ptr, None)
+        st.destroy()
+    obj.Free()
+    net.Free()
