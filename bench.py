@@ -33,7 +33,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_SEQ, SEQ_LEN = 64, 150
+CHAIN_FRAMES = 50   # output frames per sequence: frame-subsampling factor 3 (internal/nnet/chain_loss.go:221-294)
 LR = 1e-4   # with gradients scaled to the mean over frames x output dims (keeps the 0.5*||out||^2 objective stable)
+LR_CHAIN = 1e-6   # the synthetic denominator graph does not bound the LF-MMI objective: a small step keeps 300 updates finite
 
 
 def tdnnf_stack_xconfig(layers=16, dim=1536, bott=160, stride=3):
@@ -73,6 +75,23 @@ WORKLOADS = {
     "cnn_tdnn": dict(xconfig=cnn_tdnn_xconfig, feat_dim=40, ivec_dim=100, dp_cut="tdnnf7",
                      desc="full CNN-TDNN (6 conv + 12 TDNN-F + prefinal + 6016-pdf output) fwd+bwd+SGD, 64 seqs x 150 frames per GPU (BASELINE configs[2])"),
 }
+
+
+def build_synthetic_chain(handle, out_dim, rank=0):
+    """synthetic supervision: per sequence a linear-chain numerator over the 50 output frames (pdf = (i + seq) mod P,
+    weight 0: internal/nnet/backward_test.go:42-58), one small random ergodic HMM as the shared denominator graph"""
+    from kaldi_fp16_b200 import chain as KC
+    crng = np.random.default_rng(7)
+    S, K = 256, 4
+    w = crng.random((S, K)) + 0.1
+    den = KC.ChainFst((np.arange(S + 1) * K), crng.integers(0, S, size=S * K), crng.integers(0, out_dim, size=S * K) + 1,
+                      np.log(w / w.sum(1, keepdims=True)).reshape(-1), np.arange(S), np.zeros(S), 0)
+    nums = [KC.ChainFst(np.concatenate([np.arange(CHAIN_FRAMES), [CHAIN_FRAMES, CHAIN_FRAMES]]), np.arange(1, CHAIN_FRAMES + 1),
+                        (np.arange(CHAIN_FRAMES) + q + rank * N_SEQ) % out_dim + 1, np.zeros(CHAIN_FRAMES), [CHAIN_FRAMES], [0.0], 0)
+            for q in range(N_SEQ)]
+    obj = KC.ChainObjective(handle, out_dim, N_SEQ, CHAIN_FRAMES, den)
+    obj.SetNumerators(nums)
+    return obj
 
 
 def peaks():
@@ -221,6 +240,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("KFP16_WORKLOAD", "cnn_tdnn"), choices=sorted(WORKLOADS))
+    ap.add_argument("--objective", default=None, choices=["chain", "half_sq"],
+                    help="chain = LF-MMI on 50 output frames per sequence (default for cnn_tdnn: BASELINE configs[2] is a "
+                         "chain-model SGD step); half_sq = 0.5*||out||^2, dY = Y (cmd/sgdtest/main.go:258-267)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
     args = ap.parse_args()
@@ -263,8 +285,11 @@ def main():
 
     wl = WORKLOADS[args.workload]
     out_dim = {"tdnnf_stack": 1536, "cnn_tdnn": 6016}[args.workload]
-    grad_scale = 1.0 / (N_SEQ * SEQ_LEN * out_dim)
-    net = nnet.NewNetwork(nnet.BuildModelFromString(wl["xconfig"]()), handle, N_SEQ, SEQ_LEN, train=True, lr=LR,
+    objective = args.objective or ("chain" if args.workload == "cnn_tdnn" else "half_sq")
+    # chain: posterior gradients in [-1, 1] on the output frames, averaged over them; half_sq: mean over frames x dims
+    grad_scale = 1.0 / (N_SEQ * CHAIN_FRAMES) if objective == "chain" else 1.0 / (N_SEQ * SEQ_LEN * out_dim)
+    lr = LR_CHAIN if objective == "chain" else LR
+    net = nnet.NewNetwork(nnet.BuildModelFromString(wl["xconfig"]()), handle, N_SEQ, SEQ_LEN, train=True, lr=lr,
                           momentum=0.9, ref_round=False, seed=42, grad_scale=grad_scale)
     T, fd, ivd = N_SEQ * SEQ_LEN, wl["feat_dim"], wl["ivec_dim"]
     rng = np.random.default_rng(1234 + rank)
@@ -294,6 +319,10 @@ def main():
         if ivd:
             assert lib.kfp16_net_set_input_device(net.ptr, b"ivector", d_ivec.Ptr, N_SEQ, ivd) == 0, _lib.last_error()
 
+    chain_obj = None
+    if objective == "chain":
+        chain_obj = build_synthetic_chain(handle, out_dim, rank)
+        assert lib.kfp16_net_set_chain(net.ptr, chain_obj.ptr, 3, 0, 1.0) == 0, _lib.last_error()
     set_inputs_device()
     # graphs: N = 1: [step] [SGD on the FP32 bucket, gradients rounded to FP16 as the reference's are]
     #         N > 1: [step + FP16 gradient export] all-reduce(g16) [SGD on the reduced FP16 bucket]
@@ -448,7 +477,11 @@ def main():
         set_inputs_device()
         net.ZeroGrads()
         assert lib.kfp16_net_forward(net.ptr) == 0
-        net.Backward(None)
+        if chain_obj is not None:
+            assert lib.kfp16_net_loss_chain(net.ptr, b"", chain_obj.ptr, 3, 0, 1.0) == 0, _lib.last_error()
+            assert lib.kfp16_net_backward(net.ptr) == 0, _lib.last_error()
+        else:
+            net.Backward(None)
         net.SGDStep(grad_scale)
     ev1.record(stream_ptr)
     ev1.synchronize()
@@ -479,7 +512,9 @@ def main():
             "config": {"workload": wl["desc"], "frames_per_gpu_step": T, "global_frames_per_step": frames_per_step,
                        "parallelism": f"dp{world}" + (f", FP16 gradient all-reduce in {n_seg} buckets, the first overlapped with the conv front end's backward pass ({nccl_sms} SMs left to NCCL there)" if overlap else (", FP16 gradient all-reduce" if world > 1 else "")),
                        "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush",
-                       "loss": "0.5*||out||^2, dY=Y", "optimizer": f"momentum SGD on FP32 masters, lr {LR}, m 0.9, grads scaled by 1/(frames*out_dim)",
+                       "loss": ("chain LF-MMI (log-semiring numerator / denominator forward-backward, 50 output frames per sequence, one batched launch)"
+                                if objective == "chain" else "0.5*||out||^2, dY=Y"),
+                       "optimizer": f"momentum SGD on FP32 masters, lr {lr}, m 0.9, grads scaled by {grad_scale:.3g}",
                        "launch": "CUDA graphs (step, SGD) with programmatic dependent launch between kernels" + ("" if os.environ.get("KFP16_PDL", "1") != "0" else " OFF")},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "event_ms": e2e_event_ms, "wall_ms": wall_ms, "input": "FP32 features in pinned host memory, converted to FP16 on the device",

@@ -52,6 +52,9 @@ int kfp16_chain_loss(kfp16_chain *chain, const void *nnet_out, void *grad_out, i
                      float supervision_weight, float *loss_accum_dev);
 /* per sequence {num_logprob, den_logprob, loss, 0} of the last kfp16_chain_loss (ChainLossResult, chain.h:39-45) */
 int kfp16_chain_read_results(kfp16_chain *chain, float *host, int n_seq);
+/* two kernels compute the same thing: one keeps both graphs and the running alpha / beta vectors in shared memory (taken
+ * whenever they fit), one works from global memory (any size).  on = 1 forces the second (tests). */
+int kfp16_chain_force_general(kfp16_chain *chain, int on);
 int kfp16_chain_num_sequences(const kfp16_chain *chain);
 int kfp16_chain_frames(const kfp16_chain *chain);
 

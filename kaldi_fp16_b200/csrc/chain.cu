@@ -7,8 +7,7 @@
 //   loss = -(num_logprob - den_logprob),  grad = clamp((den_post - num_post) * weight, +-30) as FP16.
 //
 // ONE launch for the whole minibatch: a CTA per sequence walks the frames itself (block barriers between frames, no host
-// involvement), the network-output row of the current frame is staged in shared memory as FP32, states are spread over
-// the threads, each state reduces its incoming (forward) / outgoing (backward) arcs in a fixed order -- no atomics on
+// involvement; numerator and denominator advance in the same frame loop), states are spread over the threads, each state reduces its incoming (forward) / outgoing (backward) arcs in a fixed order -- no atomics on
 // alpha / beta, deterministic -- and the posteriors of a frame are accumulated in shared memory during the backward step
 // of that frame, so the gradient row is written once.  The x3 output-row subsampling (ops_subsample_rows, ops.cu:290-304)
 // is a row stride of the read; the gradient lands on the same rows.
@@ -36,7 +35,7 @@ struct DevFst {
   // outgoing arcs (CSR by source, as given) and incoming arcs (CSR by destination, built at upload)
   int *out_ptr = nullptr, *out_dst = nullptr, *out_pdf = nullptr;
   float* out_w = nullptr;
-  int *in_ptr = nullptr, *in_src = nullptr, *in_pdf = nullptr;
+  int *in_ptr = nullptr, *in_src = nullptr, *in_pdf = nullptr, *in_id = nullptr;   // in_id: index of the arc in outgoing order
   float* in_w = nullptr;
   int *final_state = nullptr;
   float* final_w = nullptr;
@@ -47,7 +46,7 @@ struct DevFst {
 struct FstRef {
   const int *out_ptr, *out_dst, *out_pdf;
   const float* out_w;
-  const int *in_ptr, *in_src, *in_pdf;
+  const int *in_ptr, *in_src, *in_pdf, *in_id;
   const float* in_w;
   const int* final_state;
   const float* final_w;
@@ -74,30 +73,22 @@ __device__ __forceinline__ float log_add(float a, float b) {   // chain.cu:44-66
   return mx + log1pf(expf(mn - mx));
 }
 
-// forward pass of one FST over all frames; alpha: [(T + 1) x S]
-__device__ void chain_forward(const FstRef& f, const ChainArgs& a, const __half* nnet_seq, float* alpha, float* row) {
+// one forward step of one FST: alpha[t+1] from alpha[t]; the frame's network outputs are read straight from global
+// memory (a few arcs per state: no staging needed in this direction)
+__device__ __forceinline__ void chain_forward_step(const FstRef& f, const ChainArgs& a, const __half* __restrict__ nrow,
+                                                   const float* at, float* an) {   // (alpha is written by this kernel: no read-only path)
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int s = tid; s < f.S; s += nt) alpha[s] = s == f.start ? 0.0f : kLogZero;
-  for (int t = 0; t < a.T; ++t) {
-    const __half* src_row = nnet_seq + (size_t)t * a.row_step * a.ld;
-    __syncthreads();                                   // alpha[t] complete, previous row no longer read
-    for (int p = tid; p < a.P; p += nt) row[p] = __half2float(src_row[p]);
-    __syncthreads();
-    const float* at = alpha + (size_t)t * f.S;
-    float* an = alpha + (size_t)(t + 1) * f.S;
-    for (int d = tid; d < f.S; d += nt) {
-      float acc = kLogZero;
-      for (int e = f.in_ptr[d]; e < f.in_ptr[d + 1]; ++e) {
-        const int pdf = f.in_pdf[e];
-        if (pdf <= 0 || pdf > a.P) continue;           // epsilon arcs are skipped (chain.cu:118-121)
-        const float sa = at[f.in_src[e]];
-        if (sa <= kLogZero) continue;
-        acc = log_add(acc, sa + row[pdf - 1] + f.in_w[e]);
-      }
-      an[d] = acc;
+  for (int d = tid; d < f.S; d += nt) {
+    float acc = kLogZero;
+    for (int e = f.in_ptr[d]; e < f.in_ptr[d + 1]; ++e) {
+      const int pdf = f.in_pdf[e];
+      if (pdf <= 0 || pdf > a.P) continue;           // epsilon arcs are skipped (chain.cu:118-121)
+      const float sa = at[f.in_src[e]];
+      if (sa <= kLogZero) continue;
+      acc = log_add(acc, sa + __half2float(nrow[pdf - 1]) + f.in_w[e]);
     }
+    an[d] = acc;
   }
-  __syncthreads();
 }
 
 // total = log-sum over the final states of alpha[T][s] + final weight (chain.cu kernel_total_logprob, same order)
@@ -154,8 +145,16 @@ chain_loss_kernel(ChainArgs a, const FstRef* __restrict__ nums, FstRef den) {
   float* bnum[2] = {beta, beta + a.snum_max};
   float* bden[2] = {beta + 2 * a.snum_max, beta + 2 * a.snum_max + a.sden};
 
-  chain_forward(num, a, nnet_seq, alpha_num, row);
-  chain_forward(den, a, nnet_seq, alpha_den, row);
+  // forward: numerator and denominator advance together, one block barrier per frame
+  for (int q = tid; q < num.S; q += nt) alpha_num[q] = q == num.start ? 0.0f : kLogZero;
+  for (int q = tid; q < den.S; q += nt) alpha_den[q] = q == den.start ? 0.0f : kLogZero;
+  for (int t = 0; t < a.T; ++t) {
+    __syncthreads();                                   // alpha[t] complete
+    const __half* nrow = nnet_seq + (size_t)t * a.row_step * a.ld;
+    chain_forward_step(num, a, nrow, alpha_num + (size_t)t * num.S, alpha_num + (size_t)(t + 1) * num.S);
+    chain_forward_step(den, a, nrow, alpha_den + (size_t)t * den.S, alpha_den + (size_t)(t + 1) * den.S);
+  }
+  __syncthreads();
   if (tid == 0) totals[0] = chain_total(num, alpha_num + (size_t)a.T * num.S);
   if (tid == 32) totals[1] = chain_total(den, alpha_den + (size_t)a.T * den.S);
   // beta[T]: final weights, log-zero elsewhere (chain.cu kernel_set_finals)
@@ -189,6 +188,209 @@ chain_loss_kernel(ChainArgs a, const FstRef* __restrict__ nums, FstRef den) {
   }
 }
 
+// ---- fast path: both FSTs (arcs, pointers) and the running alpha / beta vectors live in shared memory, the next frame's
+// network-output row and alpha values are prefetched while the current frame is processed -- a frame step then costs one
+// or two block barriers plus shared-memory work instead of three dependent global round trips (measured on the
+// benchmark's shape, 64 x 50 frames x 6016 pdfs, 256-state denominator: 490 us -> see profiles/).
+// Used when everything fits: (num + den) states <= kFastStates per thread budget, arcs + rows within the smem budget.
+constexpr int kFastQ = 4;                       // combined states per thread
+constexpr int kFastStates = kFastQ * kChainThreads;
+
+constexpr size_t kChainSmemMax = 220 * 1024;     // of the 227 KB a CTA may take
+struct FastSmem {
+  int p_pad, stot_max, atot_max, gathered;
+  size_t rowh, post, ab, ptr, arc_st, arc_pdf, arc_w, arc_id, total;
+};
+// gathered: the network outputs every arc needs, for ALL frames ([T][arcs] FP16), are collected into shared memory by one
+// fully parallel pass before the frame loops, which then never wait for global memory; otherwise the frame's row is
+// double-buffered and prefetched one frame ahead
+__host__ __device__ inline FastSmem fast_layout(int P, int stot_max, int atot_max, int T) {
+  FastSmem L;
+  L.p_pad = (P + 7) & ~7; L.stot_max = stot_max; L.atot_max = atot_max;
+  const size_t fixed = (size_t)L.p_pad * sizeof(float) + (size_t)2 * stot_max * sizeof(float) + (size_t)(stot_max + 1) * sizeof(int) +
+                       (size_t)atot_max * 16 + 64;
+  const size_t vals = (((size_t)T * atot_max * sizeof(__half)) + 15) & ~(size_t)15;
+  L.gathered = fixed + vals <= kChainSmemMax ? 1 : 0;
+  size_t o = 0;
+  L.rowh = o; o += L.gathered ? vals : (size_t)2 * L.p_pad * sizeof(__half);
+  L.post = o; o += (size_t)L.p_pad * sizeof(float);
+  L.ab = o; o += (size_t)2 * stot_max * sizeof(float);
+  L.ptr = o; o += (size_t)(stot_max + 1) * sizeof(int);
+  L.arc_st = o; o += (size_t)atot_max * sizeof(int);
+  L.arc_pdf = o; o += (size_t)atot_max * sizeof(int);
+  L.arc_w = o; o += (size_t)atot_max * sizeof(float);
+  L.arc_id = o; o += (size_t)atot_max * sizeof(int);
+  L.total = (o + 15) & ~(size_t)15;
+  return L;
+}
+
+__global__ void __launch_bounds__(kChainThreads)
+chain_loss_fast_kernel(ChainArgs a, const FstRef* __restrict__ nums, FstRef den, int stot_max, int atot_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const FastSmem L = fast_layout(a.P, stot_max, atot_max, a.T);
+  const bool gathered = L.gathered != 0;
+  __half* rowh = reinterpret_cast<__half*>(smem_raw + L.rowh);
+  float* post = reinterpret_cast<float*>(smem_raw + L.post);
+  float* ab = reinterpret_cast<float*>(smem_raw + L.ab);
+  int* ptr = reinterpret_cast<int*>(smem_raw + L.ptr);
+  int* arc_st = reinterpret_cast<int*>(smem_raw + L.arc_st);
+  int* arc_pdf = reinterpret_cast<int*>(smem_raw + L.arc_pdf);
+  float* arc_w = reinterpret_cast<float*>(smem_raw + L.arc_w);
+  int* arc_id = reinterpret_cast<int*>(smem_raw + L.arc_id);
+  __shared__ float totals[2];
+  const int seq = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const FstRef num = nums[seq];
+  const int nS = num.S, dS = den.S, stot = nS + dS;
+  const __half* nnet_seq = a.nnet + ((size_t)seq * a.seq_rows + a.row0) * a.ld;
+  float* alpha_num = a.alpha_num + (size_t)seq * (a.T + 1) * a.snum_max;
+  float* alpha_den = a.alpha_den + (size_t)seq * (a.T + 1) * a.sden;
+  const int pv = L.p_pad / 8;                     // 16-byte chunks per row (P % 8 == 0 on this path)
+  const size_t row_stride = (size_t)a.row_step * a.ld;
+  auto alpha_at = [&](int t, int q) -> float* { return q < nS ? alpha_num + (size_t)t * nS + q : alpha_den + (size_t)t * dS + (q - nS); };
+
+  // combined CSR (numerator states first): incoming arcs for the forward pass, outgoing for the backward pass
+  auto load_fst = [&](bool incoming) {
+    const int* np = incoming ? num.in_ptr : num.out_ptr;   const int* dp = incoming ? den.in_ptr : den.out_ptr;
+    const int* ns = incoming ? num.in_src : num.out_dst;   const int* ds = incoming ? den.in_src : den.out_dst;
+    const int* npdf = incoming ? num.in_pdf : num.out_pdf; const int* dpdf = incoming ? den.in_pdf : den.out_pdf;
+    const float* nw = incoming ? num.in_w : num.out_w;     const float* dw = incoming ? den.in_w : den.out_w;
+    const int nA = __ldg(np + nS), dA = __ldg(dp + dS);
+    for (int q = tid; q <= stot; q += nt) ptr[q] = q < nS ? __ldg(np + q) : nA + __ldg(dp + (q - nS));
+    for (int e = tid; e < nA; e += nt) {
+      arc_st[e] = __ldg(ns + e); arc_pdf[e] = __ldg(npdf + e); arc_w[e] = __ldg(nw + e);
+      arc_id[e] = incoming ? __ldg(num.in_id + e) : e;
+    }
+    for (int e = tid; e < dA; e += nt) {
+      arc_st[nA + e] = nS + __ldg(ds + e); arc_pdf[nA + e] = __ldg(dpdf + e); arc_w[nA + e] = __ldg(dw + e);
+      arc_id[nA + e] = nA + (incoming ? __ldg(den.in_id + e) : e);
+    }
+  };
+  // network output an arc reads at frame t: from the gathered table or from the staged row
+  const int atot = __ldg(num.out_ptr + nS) + __ldg(den.out_ptr + dS);
+  auto arc_val = [&](int t, int e, int pdf) -> float {
+    return __half2float(gathered ? rowh[(size_t)t * atot + arc_id[e]] : rowh[(t & 1) * L.p_pad + pdf - 1]);
+  };
+  if (gathered) {   // vals[t][arc in outgoing order] = nnet[t][pdf(arc) - 1]: all loads independent
+    const int nA = __ldg(num.out_ptr + nS);
+    for (int i = tid; i < a.T * atot; i += nt) {
+      const int t = i / atot, e = i - t * atot;
+      const int pdf = e < nA ? __ldg(num.out_pdf + e) : __ldg(den.out_pdf + (e - nA));
+      rowh[i] = (pdf > 0 && pdf <= a.P) ? nnet_seq[(size_t)t * row_stride + pdf - 1] : __float2half(0.f);
+    }
+  }
+
+  // ------------------------------------------------------------------ forward
+  load_fst(true);
+  for (int q = tid; q < stot; q += nt) {
+    const float v = (q < nS ? q == num.start : (q - nS) == den.start) ? 0.0f : kLogZero;
+    ab[q] = v;
+    *alpha_at(0, q) = v;
+  }
+  if (!gathered && tid < pv) reinterpret_cast<uint4*>(rowh)[tid] = __ldg(reinterpret_cast<const uint4*>(nnet_seq) + tid);
+  __syncthreads();
+  for (int t = 0; t < a.T; ++t) {
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (!gathered && t + 1 < a.T && tid < pv) nxt = __ldg(reinterpret_cast<const uint4*>(nnet_seq + (size_t)(t + 1) * row_stride) + tid);
+    const float* cur = ab + (t & 1) * stot_max;
+    float* nx = ab + ((t + 1) & 1) * stot_max;
+    for (int q = tid; q < stot; q += nt) {
+      float acc = kLogZero;
+      for (int e = ptr[q]; e < ptr[q + 1]; ++e) {
+        const int pdf = arc_pdf[e];
+        if (pdf <= 0 || pdf > a.P) continue;
+        const float sa = cur[arc_st[e]];
+        if (sa <= kLogZero) continue;
+        acc = log_add(acc, sa + arc_val(t, e, pdf) + arc_w[e]);
+      }
+      nx[q] = acc;
+      *alpha_at(t + 1, q) = acc;
+    }
+    if (!gathered && tid < pv) reinterpret_cast<uint4*>(rowh + ((t + 1) & 1) * L.p_pad)[tid] = nxt;
+    __syncthreads();
+  }
+  {
+    const float* aT = ab + (a.T & 1) * stot_max;
+    if (tid == 0) totals[0] = chain_total(num, aT);
+    if (tid == 32) totals[1] = chain_total(den, aT + nS);
+  }
+  __syncthreads();
+  const float tot_num = totals[0], tot_den = totals[1];
+  if (tid == 0) {
+    float* r = a.result + (size_t)seq * 4;
+    r[0] = tot_num; r[1] = tot_den; r[2] = -(tot_num - tot_den); r[3] = 0.f;
+    if (a.loss_accum) atomicAdd(a.loss_accum, -(tot_num - tot_den));
+  }
+  if (a.grad == nullptr) return;
+
+  // ------------------------------------------------------------------ backward + posteriors + gradient rows
+  __half* grad_seq = a.grad + ((size_t)seq * a.seq_rows + a.row0) * a.ld;
+  load_fst(false);
+  for (int q = tid; q < stot; q += nt) ab[(a.T & 1) * stot_max + q] = kLogZero;
+  for (int p = tid; p < L.p_pad; p += nt) post[p] = 0.f;
+  __syncthreads();
+  if (tid == 0) for (int i = 0; i < num.F; ++i) ab[(a.T & 1) * stot_max + num.final_state[i]] = num.final_w[i];
+  if (tid == 32) for (int i = 0; i < den.F; ++i) ab[(a.T & 1) * stot_max + nS + den.final_state[i]] = den.final_w[i];
+  // alpha[t][q] of this thread's states: fetched two frames ahead (registers), so the loop never waits for them
+  float a_cur[kFastQ], a_n1[kFastQ], a_n2[kFastQ];
+#pragma unroll
+  for (int k = 0; k < kFastQ; ++k) {
+    const int q = tid + k * nt;
+    a_cur[k] = q < stot ? *alpha_at(a.T - 1, q) : kLogZero;
+    a_n1[k] = (q < stot && a.T >= 2) ? *alpha_at(a.T - 2, q) : kLogZero;
+    a_n2[k] = kLogZero;
+  }
+  if (!gathered && tid < pv) reinterpret_cast<uint4*>(rowh + ((a.T - 1) & 1) * L.p_pad)[tid] = __ldg(reinterpret_cast<const uint4*>(nnet_seq + (size_t)(a.T - 1) * row_stride) + tid);
+  __syncthreads();
+  for (int t = a.T - 1; t >= 0; --t) {
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (!gathered && t > 0 && tid < pv) nxt = __ldg(reinterpret_cast<const uint4*>(nnet_seq + (size_t)(t - 1) * row_stride) + tid);
+    if (t > 1) {
+#pragma unroll
+      for (int k = 0; k < kFastQ; ++k) { const int q = tid + k * nt; if (q < stot) a_n2[k] = *alpha_at(t - 2, q); }
+    }
+    const float* bn = ab + ((t + 1) & 1) * stot_max;
+    float* bt = ab + (t & 1) * stot_max;
+#pragma unroll
+    for (int k = 0; k < kFastQ; ++k) {
+      const int q = tid + k * nt;
+      if (q >= stot) break;
+      const float as = a_cur[k];
+      const float total = q < nS ? tot_num : tot_den, sign = q < nS ? -1.0f : 1.0f;
+      float acc = kLogZero;
+      for (int e = ptr[q]; e < ptr[q + 1]; ++e) {
+        const int pdf = arc_pdf[e];
+        if (pdf <= 0 || pdf > a.P) continue;
+        const float b = bn[arc_st[e]];
+        if (b <= kLogZero) continue;
+        const float v = b + arc_val(t, e, pdf) + arc_w[e];
+        acc = log_add(acc, v);
+        if (as > kLogZero) {
+          float lp = as + v - total;
+          if (lp > 0.0f) lp = 0.0f;
+          atomicAdd(&post[pdf - 1], sign * expf(lp));
+        }
+      }
+      bt[q] = acc;
+    }
+    __syncthreads();                                   // posteriors of frame t and beta[t] complete
+    if (tid < pv) {                                    // gradient row t: 8 pdfs per thread, one 16-byte store (kernel_chain_gradient)
+      __half2 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g0 = fmaxf(-30.0f, fminf(30.0f, post[tid * 8 + 2 * j] * a.weight));
+        const float g1 = fmaxf(-30.0f, fminf(30.0f, post[tid * 8 + 2 * j + 1] * a.weight));
+        h[j] = __floats2half2_rn(g0, g1);
+        post[tid * 8 + 2 * j] = 0.f; post[tid * 8 + 2 * j + 1] = 0.f;
+      }
+      *reinterpret_cast<uint4*>(grad_seq + (size_t)t * row_stride + tid * 8) = *reinterpret_cast<const uint4*>(h);
+      if (!gathered && t > 0) reinterpret_cast<uint4*>(rowh + ((t - 1) & 1) * L.p_pad)[tid] = nxt;
+    }
+#pragma unroll
+    for (int k = 0; k < kFastQ; ++k) { a_cur[k] = a_n1[k]; a_n1[k] = a_n2[k]; }
+    __syncthreads();                                   // post cleared, next row staged
+  }
+}
+
 bool upload(void** dev, const void* host, size_t bytes) {
   if (bytes == 0) bytes = 4;
   if (!check_cuda(cudaMalloc(dev, bytes), "cudaMalloc (chain)")) return false;
@@ -204,7 +406,7 @@ bool build_fst(DevFst& f, const kfp16_chain_fst& h, const char* what) {
   }
   const int S = h.num_states, A = h.num_arcs;
   if (h.row_ptr[0] != 0 || h.row_ptr[S] != A) { set_error("%s: row_ptr must run from 0 to num_arcs", what); return false; }
-  std::vector<int> in_ptr(S + 1, 0), in_src(A), in_pdf(A);
+  std::vector<int> in_ptr(S + 1, 0), in_src(A), in_pdf(A), in_id(A);
   std::vector<float> in_w(A);
   for (int s = 0; s < S; ++s) {
     if (h.row_ptr[s + 1] < h.row_ptr[s]) { set_error("%s: row_ptr not monotone", what); return false; }
@@ -218,7 +420,7 @@ bool build_fst(DevFst& f, const kfp16_chain_fst& h, const char* what) {
   for (int s = 0; s < S; ++s)
     for (int e = h.row_ptr[s]; e < h.row_ptr[s + 1]; ++e) {
       const int k = fill[h.col_idx[e]]++;
-      in_src[k] = s; in_pdf[k] = h.labels[e]; in_w[k] = h.weights[e];
+      in_src[k] = s; in_pdf[k] = h.labels[e]; in_w[k] = h.weights[e]; in_id[k] = e;
     }
   for (int i = 0; i < h.num_final; ++i)
     if (h.final_states[i] < 0 || h.final_states[i] >= S) { set_error("%s: final state out of range", what); return false; }
@@ -227,16 +429,17 @@ bool build_fst(DevFst& f, const kfp16_chain_fst& h, const char* what) {
          upload((void**)&f.out_pdf, h.labels, (size_t)A * 4) && upload((void**)&f.out_w, h.weights, (size_t)A * 4) &&
          upload((void**)&f.in_ptr, in_ptr.data(), (S + 1) * 4) && upload((void**)&f.in_src, in_src.data(), (size_t)A * 4) &&
          upload((void**)&f.in_pdf, in_pdf.data(), (size_t)A * 4) && upload((void**)&f.in_w, in_w.data(), (size_t)A * 4) &&
+         upload((void**)&f.in_id, in_id.data(), (size_t)A * 4) &&
          upload((void**)&f.final_state, h.final_states, (size_t)h.num_final * 4) && upload((void**)&f.final_w, h.final_weights, (size_t)h.num_final * 4);
 }
 void free_fst(DevFst& f) {
   for (void* p : {(void*)f.out_ptr, (void*)f.out_dst, (void*)f.out_pdf, (void*)f.out_w, (void*)f.in_ptr, (void*)f.in_src,
-                  (void*)f.in_pdf, (void*)f.in_w, (void*)f.final_state, (void*)f.final_w})
+                  (void*)f.in_pdf, (void*)f.in_id, (void*)f.in_w, (void*)f.final_state, (void*)f.final_w})
     if (p) cudaFree(p);
   f = DevFst();
 }
 FstRef ref_of(const DevFst& f) {
-  return FstRef{f.out_ptr, f.out_dst, f.out_pdf, f.out_w, f.in_ptr, f.in_src, f.in_pdf, f.in_w, f.final_state, f.final_w, f.S, f.F, f.start};
+  return FstRef{f.out_ptr, f.out_dst, f.out_pdf, f.out_w, f.in_ptr, f.in_src, f.in_pdf, f.in_id, f.in_w, f.final_state, f.final_w, f.S, f.F, f.start};
 }
 
 }  // namespace
@@ -247,7 +450,8 @@ struct kfp16_chain {
   DevFst den;
   std::vector<DevFst> nums;
   FstRef* nums_dev = nullptr;
-  int snum_max = 0;
+  int snum_max = 0, anum_max = 0;
+  bool force_general = false;   // tests: run the global-memory kernel even when the shared-memory one would fit
   float *alpha_num = nullptr, *alpha_den = nullptr, *beta = nullptr, *result = nullptr;
   size_t alpha_num_elems = 0;
 };
@@ -285,13 +489,15 @@ int kfp16_chain_set_numerators(kfp16_chain* c, const kfp16_chain_fst* nums, int 
   if (!c || !nums || n_seq != c->n_seq) { set_error("kfp16_chain_set_numerators: expected %d numerator FSTs", c ? c->n_seq : 0); return -1; }
   if (!check_cuda(cudaSetDevice(c->ctx->device), "cudaSetDevice") || !check_cuda(cudaStreamSynchronize(c->ctx->stream), "sync")) return -1;
   std::vector<FstRef> refs(n_seq);
-  int smax = 1;
+  int smax = 1, amax = 0;
   for (int i = 0; i < n_seq; ++i) {
     free_fst(c->nums[i]);
     if (!build_fst(c->nums[i], nums[i], "kfp16_chain_set_numerators")) return -1;
     refs[i] = ref_of(c->nums[i]);
     smax = std::max(smax, c->nums[i].S);
+    amax = std::max(amax, c->nums[i].A);
   }
+  c->anum_max = amax;
   if (!check_cuda(cudaMemcpy(c->nums_dev, refs.data(), sizeof(FstRef) * n_seq, cudaMemcpyHostToDevice), "numerator table upload")) return -1;
   const size_t need = (size_t)n_seq * (c->frames + 1) * smax;
   if (need > c->alpha_num_elems || smax != c->snum_max) {
@@ -323,13 +529,22 @@ int kfp16_chain_loss(kfp16_chain* c, const void* nnet_out, void* grad_out, int l
   a.alpha_num = c->alpha_num; a.alpha_den = c->alpha_den; a.beta = c->beta;
   a.snum_max = c->snum_max; a.sden = c->den.S;
   a.result = c->result; a.loss_accum = loss_accum_dev;
-  const size_t smem = (size_t)c->num_pdfs * 2 * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    if (!check_cuda(cudaFuncSetAttribute(chain_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute(chain)")) return -1;
+    if (!check_cuda(cudaFuncSetAttribute(chain_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute(chain)") ||
+        !check_cuda(cudaFuncSetAttribute(chain_loss_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax), "cudaFuncSetAttribute(chain fast)")) return -1;
     attr_done = true;
   }
-  chain_loss_kernel<<<c->n_seq, kChainThreads, smem, c->ctx->stream>>>(a, c->nums_dev, ref_of(c->den));
+  // everything in shared memory when it fits (small graphs: the usual numerator, a compact denominator)
+  const int stot_max = c->snum_max + c->den.S, atot_max = c->anum_max + c->den.A;
+  const FastSmem L = fast_layout(c->num_pdfs, stot_max, atot_max, c->frames);
+  const bool aligned = (c->num_pdfs % 8) == 0 && (ld % 8) == 0 && ((uintptr_t)nnet_out & 15) == 0 && (!grad_out || ((uintptr_t)grad_out & 15) == 0);
+  if (aligned && stot_max <= kFastStates && L.total <= kChainSmemMax && !c->force_general) {
+    chain_loss_fast_kernel<<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, ref_of(c->den), stot_max, atot_max);
+  } else {
+    const size_t smem = (size_t)c->num_pdfs * 2 * sizeof(float);
+    chain_loss_kernel<<<c->n_seq, kChainThreads, smem, c->ctx->stream>>>(a, c->nums_dev, ref_of(c->den));
+  }
   count_launch();
   return check_launch("kfp16_chain_loss") ? 0 : -1;
 }
@@ -340,6 +555,7 @@ int kfp16_chain_read_results(kfp16_chain* c, float* host, int n_seq) {
   return check_cuda(cudaMemcpy(host, c->result, (size_t)n_seq * 4 * sizeof(float), cudaMemcpyDeviceToHost), "chain results download") ? 0 : -1;
 }
 
+int kfp16_chain_force_general(kfp16_chain* c, int on) { if (!c) return -1; c->force_general = on != 0; return 0; }
 int kfp16_chain_num_sequences(const kfp16_chain* c) { return c ? c->n_seq : 0; }
 int kfp16_chain_frames(const kfp16_chain* c) { return c ? c->frames : 0; }
 

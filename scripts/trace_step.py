@@ -1,6 +1,6 @@
 """In-graph kernel timeline of the bench step (CUPTI through torch.profiler; no ncu, no serialisation).
 
-    python scripts/trace_step.py [layers=16] [out=gpurun_out/trace_step.txt] [workload=tdnnf_stack]
+    python scripts/trace_step.py [layers=16] [out=gpurun_out/trace_step.txt] [workload=tdnnf_stack|cnn_tdnn] [chain]
 
 Replays the captured step graph a few times under the profiler and writes, for ONE step, every kernel in
 launch order with its start offset, duration and the idle gap before it, plus totals per kernel name.
@@ -48,6 +48,9 @@ def set_in():
 
 
 set_in()
+if workload != "tdnnf_stack" and len(sys.argv) > 4 and sys.argv[4] == "chain":     # the bench's default objective for the CNN-TDNN
+    chain_obj = bench.build_synthetic_chain(h, od)
+    assert lib.kfp16_net_set_chain(net.ptr, chain_obj.ptr, 3, 0, 1.0) == 0, _lib.last_error()
 net.Capture(1)
 net.Capture(2)
 

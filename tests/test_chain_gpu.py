@@ -40,13 +40,15 @@ def make_case(rng, n_seq, frames, P, den_states, arcs, branching_num=False):
     return den, nums
 
 
+@pytest.mark.parametrize("general", [0, 1], ids=["smem_kernel", "global_kernel"])
 @pytest.mark.parametrize("n_seq,seq_rows,frames,sub,left,P,S,arcs,branch", [
     (4, 40, 12, 3, 1, 48, 16, 3, False),
     (6, 31, 10, 3, 0, 104, 64, 4, True),
     (3, 20, 20, 1, 0, 3080, 40, 5, True),        # ragged pdf count, no subsampling
     (64, 156, 50, 3, 3, 6016, 256, 4, False),    # the benchmark's shape: 64 sequences x 50 output frames, 6016 pdfs
+    (8, 156, 50, 3, 0, 1024, 512, 8, True),      # 4096 denominator arcs: too many to gather all frames' values up front
 ])
-def test_batched_chain_objective_matches_oracle_and_reference(handle, lib, reflib, n_seq, seq_rows, frames, sub, left, P, S, arcs, branch):
+def test_batched_chain_objective_matches_oracle_and_reference(handle, lib, reflib, general, n_seq, seq_rows, frames, sub, left, P, S, arcs, branch):
     rng = np.random.default_rng(n_seq * 1000 + P)
     den, nums = make_case(rng, n_seq, frames, P, S, arcs, branch)
     out = O.to_f16_rne((rng.standard_normal((n_seq * seq_rows, P)) * 0.7).astype(np.float32))
@@ -54,6 +56,7 @@ def test_batched_chain_objective_matches_oracle_and_reference(handle, lib, refli
     t_grad = gpu.TensorFromFP16(np.full_like(out, 3.0))
     obj = KC.ChainObjective(handle, P, n_seq, frames, to_kc(den))
     obj.SetNumerators([to_kc(f) for f in nums])
+    assert lib.kfp16_chain_force_general(obj.ptr, general) == 0
     weight = 0.75
     loss_acc = gpu.DeviceF32(n=4)
     assert lib.kfp16_chain_loss(obj.ptr, t_out.Ptr, t_grad.Ptr, P, seq_rows, left, sub, weight, loss_acc.Ptr) == 0, lib.kfp16_last_error()
