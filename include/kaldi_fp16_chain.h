@@ -55,6 +55,9 @@ int kfp16_chain_read_results(kfp16_chain *chain, float *host, int n_seq);
 /* two kernels compute the same thing: one keeps both graphs and the running alpha / beta vectors in shared memory (taken
  * whenever they fit), one works from global memory (any size).  on = 1 forces the second (tests). */
 int kfp16_chain_force_general(kfp16_chain *chain, int on);
+/* profiling: device int64[8] receiving clock64 stamps of the first sequence's phases (start, forward loop start / end,
+ * backward loop start / end); NULL = off */
+int kfp16_chain_set_debug(kfp16_chain *chain, void *dev_i64x8);
 int kfp16_chain_num_sequences(const kfp16_chain *chain);
 int kfp16_chain_frames(const kfp16_chain *chain);
 

@@ -206,6 +206,7 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_chain_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "kfp16_chain_read_results": (c_int, [c_void_p, c_void_p, c_int]),
     "kfp16_chain_force_general": (c_int, [c_void_p, c_int]),
+    "kfp16_chain_set_debug": (c_int, [c_void_p, c_void_p]),
     "kfp16_chain_num_sequences": (c_int, [c_void_p]),
     "kfp16_chain_frames": (c_int, [c_void_p]),
     "kfp16_net_loss_chain": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int, c_float]),

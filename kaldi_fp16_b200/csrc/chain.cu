@@ -64,6 +64,7 @@ struct ChainArgs {
   int snum_max, sden;
   float* result;                        // [n_seq][4]: num_logprob, den_logprob, loss, 0
   float* loss_accum;                    // += loss of every sequence (may be null)
+  long long* dbg;                       // profiling: clock64 stamps of CTA 0's phases (may be null)
 };
 
 __device__ __forceinline__ float log_add(float a, float b) {   // chain.cu:44-66 without the CAS loop
@@ -89,6 +90,26 @@ __device__ __forceinline__ void chain_forward_step(const FstRef& f, const ChainA
     }
     an[d] = acc;
   }
+}
+
+// total over the final states, computed by ONE WARP (lane-strided running max / scaled sum, merged by shuffles): the
+// sequential form below costs a dependent global load + log1p/exp per final state (256 finals: 35 us of a 300 us kernel)
+__device__ float chain_total_warp(const FstRef& f, const float* alphaT) {
+  const int lane = threadIdx.x & 31;
+  float mx = kLogZero, sum = 0.f;
+  for (int i = lane; i < f.F; i += 32) {
+    const float v = alphaT[__ldg(f.final_state + i)] + __ldg(f.final_w + i);
+    if (v <= kLogZero) continue;
+    if (v > mx) { sum = sum * __expf(mx - v) + 1.0f; mx = v; }
+    else sum += __expf(v - mx);
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o), osum = __shfl_xor_sync(0xffffffffu, sum, o);
+    const float nmx = fmaxf(mx, omx);
+    if (nmx > kLogZero) sum = sum * __expf(mx - nmx) + osum * __expf(omx - nmx);
+    mx = nmx;
+  }
+  return mx > kLogZero ? mx + __logf(sum) : kLogZero;
 }
 
 // total = log-sum over the final states of alpha[T][s] + final weight (chain.cu kernel_total_logprob, same order)
@@ -188,42 +209,44 @@ chain_loss_kernel(ChainArgs a, const FstRef* __restrict__ nums, FstRef den) {
   }
 }
 
-// ---- fast path: both FSTs (arcs, pointers) and the running alpha / beta vectors live in shared memory, the next frame's
-// network-output row and alpha values are prefetched while the current frame is processed -- a frame step then costs one
-// or two block barriers plus shared-memory work instead of three dependent global round trips (measured on the
-// benchmark's shape, 64 x 50 frames x 6016 pdfs, 256-state denominator: 490 us -> see profiles/).
-// Used when everything fits: (num + den) states <= kFastStates per thread budget, arcs + rows within the smem budget.
-constexpr int kFastQ = 4;                       // combined states per thread
-constexpr int kFastStates = kFastQ * kChainThreads;
-
+// ---- fast path (graphs of up to kFastArcs * 1024 arcs and kFastQ * 1024 states per sequence pair).
+// A frame step is latency-bound (one CTA, ~1000 arcs), so everything that does not change from frame to frame lives in
+// REGISTERS -- each thread owns up to kFastArcs arcs (source / destination state, weight, pdf) and up to kFastQ states
+// (their arc ranges) for the whole kernel -- and the per-frame data in shared memory: the running alpha / beta vectors,
+// the per-arc path values, the posterior row, and (when it fits) the network outputs of ALL frames gathered per arc by one
+// fully parallel pass up front, so that the frame loops never wait for global memory.  Per frame: an arc-parallel pass
+// (path value, and in the backward direction the arc's posterior), a barrier, a state-parallel log-sum-exp (max, scaled
+// sum, one logarithm) together with the gradient-row write, a barrier.
+// Measured on the benchmark's shape (64 x 50 frames x 6016 pdfs, 256-state / 1024-arc denominator), us per minibatch:
+// global-memory kernel 436, first shared-memory version 302 (a state-parallel loop over dependent shared-memory reads per
+// arc), register-resident arcs with the smallest <arcs, states> per thread: 190 (profiles/r02_chain_kernel.txt).  What
+// bounds it now is instruction issue: ~1000 arcs x ~100 instructions per frame and direction on one SM.
+constexpr int kFastQMax = 4;                     // states per thread (template argument: the smallest that covers the graphs)
+constexpr int kFastArcsMax = 4;                  // arcs per thread
+constexpr int kFastStates = kFastQMax * kChainThreads;
 constexpr size_t kChainSmemMax = 220 * 1024;     // of the 227 KB a CTA may take
+
 struct FastSmem {
   int p_pad, stot_max, atot_max, gathered;
-  size_t rowh, post, ab, ptr, arc_st, arc_pdf, arc_w, arc_id, total;
+  size_t rowh, post, ab, alpha_s, arc_v, total;
 };
-// gathered: the network outputs every arc needs, for ALL frames ([T][arcs] FP16), are collected into shared memory by one
-// fully parallel pass before the frame loops, which then never wait for global memory; otherwise the frame's row is
-// double-buffered and prefetched one frame ahead
 __host__ __device__ inline FastSmem fast_layout(int P, int stot_max, int atot_max, int T) {
   FastSmem L;
   L.p_pad = (P + 7) & ~7; L.stot_max = stot_max; L.atot_max = atot_max;
-  const size_t fixed = (size_t)L.p_pad * sizeof(float) + (size_t)2 * stot_max * sizeof(float) + (size_t)(stot_max + 1) * sizeof(int) +
-                       (size_t)atot_max * 16 + 64;
+  const size_t fixed = (size_t)L.p_pad * sizeof(float) + (size_t)4 * stot_max * sizeof(float) + (size_t)atot_max * sizeof(float) + 64;
   const size_t vals = (((size_t)T * atot_max * sizeof(__half)) + 15) & ~(size_t)15;
   L.gathered = fixed + vals <= kChainSmemMax ? 1 : 0;
   size_t o = 0;
   L.rowh = o; o += L.gathered ? vals : (size_t)2 * L.p_pad * sizeof(__half);
   L.post = o; o += (size_t)L.p_pad * sizeof(float);
   L.ab = o; o += (size_t)2 * stot_max * sizeof(float);
-  L.ptr = o; o += (size_t)(stot_max + 1) * sizeof(int);
-  L.arc_st = o; o += (size_t)atot_max * sizeof(int);
-  L.arc_pdf = o; o += (size_t)atot_max * sizeof(int);
-  L.arc_w = o; o += (size_t)atot_max * sizeof(float);
-  L.arc_id = o; o += (size_t)atot_max * sizeof(int);
+  L.alpha_s = o; o += (size_t)2 * stot_max * sizeof(float);
+  L.arc_v = o; o += (size_t)atot_max * sizeof(float);
   L.total = (o + 15) & ~(size_t)15;
   return L;
 }
 
+template <int kFastArcs, int kFastQ>
 __global__ void __launch_bounds__(kChainThreads)
 chain_loss_fast_kernel(ChainArgs a, const FstRef* __restrict__ nums, FstRef den, int stot_max, int atot_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -231,16 +254,14 @@ chain_loss_fast_kernel(ChainArgs a, const FstRef* __restrict__ nums, FstRef den,
   const bool gathered = L.gathered != 0;
   __half* rowh = reinterpret_cast<__half*>(smem_raw + L.rowh);
   float* post = reinterpret_cast<float*>(smem_raw + L.post);
-  float* ab = reinterpret_cast<float*>(smem_raw + L.ab);
-  int* ptr = reinterpret_cast<int*>(smem_raw + L.ptr);
-  int* arc_st = reinterpret_cast<int*>(smem_raw + L.arc_st);
-  int* arc_pdf = reinterpret_cast<int*>(smem_raw + L.arc_pdf);
-  float* arc_w = reinterpret_cast<float*>(smem_raw + L.arc_w);
-  int* arc_id = reinterpret_cast<int*>(smem_raw + L.arc_id);
+  float* ab = reinterpret_cast<float*>(smem_raw + L.ab);            // alpha (forward) / beta (backward), double-buffered
+  float* alpha_s = reinterpret_cast<float*>(smem_raw + L.alpha_s);  // backward: alpha[t], staged one frame ahead
+  float* arc_v = reinterpret_cast<float*>(smem_raw + L.arc_v);      // per-arc path value of the current frame
   __shared__ float totals[2];
   const int seq = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const FstRef num = nums[seq];
   const int nS = num.S, dS = den.S, stot = nS + dS;
+  const int nA = __ldg(num.out_ptr + nS), dA = __ldg(den.out_ptr + dS), atot = nA + dA;
   const __half* nnet_seq = a.nnet + ((size_t)seq * a.seq_rows + a.row0) * a.ld;
   float* alpha_num = a.alpha_num + (size_t)seq * (a.T + 1) * a.snum_max;
   float* alpha_den = a.alpha_den + (size_t)seq * (a.T + 1) * a.sden;
@@ -248,70 +269,105 @@ chain_loss_fast_kernel(ChainArgs a, const FstRef* __restrict__ nums, FstRef den,
   const size_t row_stride = (size_t)a.row_step * a.ld;
   auto alpha_at = [&](int t, int q) -> float* { return q < nS ? alpha_num + (size_t)t * nS + q : alpha_den + (size_t)t * dS + (q - nS); };
 
-  // combined CSR (numerator states first): incoming arcs for the forward pass, outgoing for the backward pass
-  auto load_fst = [&](bool incoming) {
-    const int* np = incoming ? num.in_ptr : num.out_ptr;   const int* dp = incoming ? den.in_ptr : den.out_ptr;
-    const int* ns = incoming ? num.in_src : num.out_dst;   const int* ds = incoming ? den.in_src : den.out_dst;
-    const int* npdf = incoming ? num.in_pdf : num.out_pdf; const int* dpdf = incoming ? den.in_pdf : den.out_pdf;
-    const float* nw = incoming ? num.in_w : num.out_w;     const float* dw = incoming ? den.in_w : den.out_w;
-    const int nA = __ldg(np + nS), dA = __ldg(dp + dS);
-    for (int q = tid; q <= stot; q += nt) ptr[q] = q < nS ? __ldg(np + q) : nA + __ldg(dp + (q - nS));
-    for (int e = tid; e < nA; e += nt) {
-      arc_st[e] = __ldg(ns + e); arc_pdf[e] = __ldg(npdf + e); arc_w[e] = __ldg(nw + e);
-      arc_id[e] = incoming ? __ldg(num.in_id + e) : e;
+  // ---- this thread's arcs and states (combined numbering: numerator first), loaded once per direction
+  int e_st[kFastArcs], e_src[kFastArcs], e_pdf[kFastArcs], e_col[kFastArcs];
+  float e_w[kFastArcs];
+  int q_e0[kFastQ], q_e1[kFastQ];
+  auto load_mine = [&](bool incoming) {
+#pragma unroll
+    for (int k = 0; k < kFastArcs; ++k) {
+      const int e = tid + k * nt;
+      e_st[k] = 0; e_src[k] = 0; e_pdf[k] = 0; e_col[k] = 0; e_w[k] = 0.f;
+      if (e >= atot) continue;
+      const bool isn = e < nA;
+      const int le = isn ? e : e - nA, base = isn ? 0 : nS;
+      const FstRef& f = isn ? num : den;
+      e_st[k] = base + __ldg((incoming ? f.in_src : f.out_dst) + le);
+      const int pdf = __ldg((incoming ? f.in_pdf : f.out_pdf) + le);
+      e_pdf[k] = (pdf > 0 && pdf <= a.P) ? pdf : 0;
+      e_w[k] = __ldg((incoming ? f.in_w : f.out_w) + le);
+      e_col[k] = (isn ? 0 : nA) + (incoming ? __ldg(f.in_id + le) : le);   // column of the gathered table (outgoing order)
     }
-    for (int e = tid; e < dA; e += nt) {
-      arc_st[nA + e] = nS + __ldg(ds + e); arc_pdf[nA + e] = __ldg(dpdf + e); arc_w[nA + e] = __ldg(dw + e);
-      arc_id[nA + e] = nA + (incoming ? __ldg(den.in_id + e) : e);
+#pragma unroll
+    for (int k = 0; k < kFastQ; ++k) {
+      const int q = tid + k * nt;
+      q_e0[k] = q_e1[k] = 0;
+      if (q >= stot) continue;
+      const bool isn = q < nS;
+      const int* p = isn ? (incoming ? num.in_ptr : num.out_ptr) : (incoming ? den.in_ptr : den.out_ptr);
+      const int lq = isn ? q : q - nS, off = isn ? 0 : nA;
+      q_e0[k] = off + __ldg(p + lq); q_e1[k] = off + __ldg(p + lq + 1);
     }
   };
-  // network output an arc reads at frame t: from the gathered table or from the staged row
-  const int atot = __ldg(num.out_ptr + nS) + __ldg(den.out_ptr + dS);
-  auto arc_val = [&](int t, int e, int pdf) -> float {
-    return __half2float(gathered ? rowh[(size_t)t * atot + arc_id[e]] : rowh[(t & 1) * L.p_pad + pdf - 1]);
+  // network output arc k of this thread reads at frame t
+  auto arc_val = [&](int t, int k) -> float {
+    return __half2float(gathered ? rowh[(size_t)t * atot + e_col[k]] : rowh[(t & 1) * L.p_pad + e_pdf[k] - 1]);
   };
-  if (gathered) {   // vals[t][arc in outgoing order] = nnet[t][pdf(arc) - 1]: all loads independent
-    const int nA = __ldg(num.out_ptr + nS);
-    for (int i = tid; i < a.T * atot; i += nt) {
-      const int t = i / atot, e = i - t * atot;
+  // log-sum-exp over arc_v[e0, e1): max, scaled sum, one logarithm (dead arcs hold log-zero: exp underflows to 0)
+  auto lse = [&](int e0, int e1) -> float {
+    float mx = kLogZero;
+    for (int e = e0; e < e1; ++e) mx = fmaxf(mx, arc_v[e]);
+    if (mx <= kLogZero) return kLogZero;
+    float sum = 0.f;
+    for (int e = e0; e < e1; ++e) sum += __expf(arc_v[e] - mx);
+    return mx + __logf(sum);
+  };
+
+  if (gathered) {   // vals[t][arc in outgoing order] = nnet[t][pdf(arc) - 1]: one arc per thread and pass, 10 frames in flight
+    const unsigned short* nn16 = reinterpret_cast<const unsigned short*>(nnet_seq);
+    unsigned short* vals = reinterpret_cast<unsigned short*>(rowh);
+    for (int e = tid; e < atot; e += nt) {
       const int pdf = e < nA ? __ldg(num.out_pdf + e) : __ldg(den.out_pdf + (e - nA));
-      rowh[i] = (pdf > 0 && pdf <= a.P) ? nnet_seq[(size_t)t * row_stride + pdf - 1] : __float2half(0.f);
+      const bool ok = pdf > 0 && pdf <= a.P;
+      const unsigned short* col = nn16 + (ok ? pdf - 1 : 0);
+#pragma unroll 10
+      for (int t = 0; t < a.T; ++t) vals[(size_t)t * atot + e] = ok ? __ldg(col + (size_t)t * row_stride) : (unsigned short)0;
     }
   }
+  if (a.dbg && seq == 0 && tid == 0) a.dbg[0] = clock64();
 
   // ------------------------------------------------------------------ forward
-  load_fst(true);
-  for (int q = tid; q < stot; q += nt) {
+  load_mine(true);
+#pragma unroll
+  for (int k = 0; k < kFastQ; ++k) {
+    const int q = tid + k * nt;
+    if (q >= stot) continue;
     const float v = (q < nS ? q == num.start : (q - nS) == den.start) ? 0.0f : kLogZero;
     ab[q] = v;
     *alpha_at(0, q) = v;
   }
   if (!gathered && tid < pv) reinterpret_cast<uint4*>(rowh)[tid] = __ldg(reinterpret_cast<const uint4*>(nnet_seq) + tid);
   __syncthreads();
+  if (a.dbg && seq == 0 && tid == 0) a.dbg[1] = clock64();
   for (int t = 0; t < a.T; ++t) {
     uint4 nxt = make_uint4(0, 0, 0, 0);
     if (!gathered && t + 1 < a.T && tid < pv) nxt = __ldg(reinterpret_cast<const uint4*>(nnet_seq + (size_t)(t + 1) * row_stride) + tid);
     const float* cur = ab + (t & 1) * stot_max;
     float* nx = ab + ((t + 1) & 1) * stot_max;
-    for (int q = tid; q < stot; q += nt) {
-      float acc = kLogZero;
-      for (int e = ptr[q]; e < ptr[q + 1]; ++e) {
-        const int pdf = arc_pdf[e];
-        if (pdf <= 0 || pdf > a.P) continue;
-        const float sa = cur[arc_st[e]];
-        if (sa <= kLogZero) continue;
-        acc = log_add(acc, sa + arc_val(t, e, pdf) + arc_w[e]);
-      }
+#pragma unroll
+    for (int k = 0; k < kFastArcs; ++k) {                // per arc: v = alpha[t][src] + network output + weight
+      const int e = tid + k * nt;
+      if (e >= atot) continue;
+      const float sa = cur[e_st[k]];
+      arc_v[e] = (e_pdf[k] == 0 || sa <= kLogZero) ? kLogZero : sa + arc_val(t, k) + e_w[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kFastQ; ++k) {                   // per state: alpha[t+1] = log-sum-exp over its incoming arcs
+      const int q = tid + k * nt;
+      if (q >= stot) continue;
+      const float acc = lse(q_e0[k], q_e1[k]);
       nx[q] = acc;
       *alpha_at(t + 1, q) = acc;
     }
     if (!gathered && tid < pv) reinterpret_cast<uint4*>(rowh + ((t + 1) & 1) * L.p_pad)[tid] = nxt;
     __syncthreads();
   }
+  if (a.dbg && seq == 0 && tid == 0) a.dbg[2] = clock64();
   {
     const float* aT = ab + (a.T & 1) * stot_max;
-    if (tid == 0) totals[0] = chain_total(num, aT);
-    if (tid == 32) totals[1] = chain_total(den, aT + nS);
+    if (tid < 32) { const float v = chain_total_warp(num, aT); if (tid == 0) totals[0] = v; }
+    else if (tid < 64) { const float v = chain_total_warp(den, aT + nS); if (tid == 32) totals[1] = v; }
   }
   __syncthreads();
   const float tot_num = totals[0], tot_den = totals[1];
@@ -324,71 +380,98 @@ chain_loss_fast_kernel(ChainArgs a, const FstRef* __restrict__ nums, FstRef den,
 
   // ------------------------------------------------------------------ backward + posteriors + gradient rows
   __half* grad_seq = a.grad + ((size_t)seq * a.seq_rows + a.row0) * a.ld;
-  load_fst(false);
-  for (int q = tid; q < stot; q += nt) ab[(a.T & 1) * stot_max + q] = kLogZero;
+  load_mine(false);
+  // source state of each of this thread's (outgoing-order) arcs: needed for the posteriors
+#pragma unroll
+  for (int k = 0; k < kFastArcs; ++k) {
+    const int e = tid + k * nt;
+    if (e >= atot) continue;
+    const bool isn = e < nA;
+    const int* p = isn ? num.out_ptr : den.out_ptr;
+    const int le = isn ? e : e - nA, S = isn ? nS : dS;
+    int lo = 0, hi = S - 1;                               // largest s with out_ptr[s] <= le (once per kernel)
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(p + mid) <= le) lo = mid; else hi = mid - 1; }
+    e_src[k] = (isn ? 0 : nS) + lo;
+  }
+#pragma unroll
+  for (int k = 0; k < kFastQ; ++k) {
+    const int q = tid + k * nt;
+    if (q >= stot) continue;
+    ab[(a.T & 1) * stot_max + q] = kLogZero;
+    alpha_s[((a.T - 1) & 1) * stot_max + q] = *alpha_at(a.T - 1, q);
+  }
   for (int p = tid; p < L.p_pad; p += nt) post[p] = 0.f;
   __syncthreads();
   if (tid == 0) for (int i = 0; i < num.F; ++i) ab[(a.T & 1) * stot_max + num.final_state[i]] = num.final_w[i];
   if (tid == 32) for (int i = 0; i < den.F; ++i) ab[(a.T & 1) * stot_max + nS + den.final_state[i]] = den.final_w[i];
-  // alpha[t][q] of this thread's states: fetched two frames ahead (registers), so the loop never waits for them
-  float a_cur[kFastQ], a_n1[kFastQ], a_n2[kFastQ];
-#pragma unroll
-  for (int k = 0; k < kFastQ; ++k) {
-    const int q = tid + k * nt;
-    a_cur[k] = q < stot ? *alpha_at(a.T - 1, q) : kLogZero;
-    a_n1[k] = (q < stot && a.T >= 2) ? *alpha_at(a.T - 2, q) : kLogZero;
-    a_n2[k] = kLogZero;
-  }
   if (!gathered && tid < pv) reinterpret_cast<uint4*>(rowh + ((a.T - 1) & 1) * L.p_pad)[tid] = __ldg(reinterpret_cast<const uint4*>(nnet_seq + (size_t)(a.T - 1) * row_stride) + tid);
   __syncthreads();
+  if (a.dbg && seq == 0 && tid == 0) a.dbg[3] = clock64();
   for (int t = a.T - 1; t >= 0; --t) {
+    // next frame's alpha (and row): issued now, stored to shared memory at the end of this frame
     uint4 nxt = make_uint4(0, 0, 0, 0);
-    if (!gathered && t > 0 && tid < pv) nxt = __ldg(reinterpret_cast<const uint4*>(nnet_seq + (size_t)(t - 1) * row_stride) + tid);
-    if (t > 1) {
+    float a_pre[kFastQ];
+    if (t > 0) {
+      if (!gathered && tid < pv) nxt = __ldg(reinterpret_cast<const uint4*>(nnet_seq + (size_t)(t - 1) * row_stride) + tid);
 #pragma unroll
-      for (int k = 0; k < kFastQ; ++k) { const int q = tid + k * nt; if (q < stot) a_n2[k] = *alpha_at(t - 2, q); }
+      for (int k = 0; k < kFastQ; ++k) { const int q = tid + k * nt; a_pre[k] = q < stot ? *alpha_at(t - 1, q) : kLogZero; }
     }
     const float* bn = ab + ((t + 1) & 1) * stot_max;
     float* bt = ab + (t & 1) * stot_max;
+    const float* al = alpha_s + (t & 1) * stot_max;
+    const bool stamp = a.dbg && seq == 0 && tid == 0 && t == 10;
+    if (stamp) a.dbg[8] = clock64();
 #pragma unroll
-    for (int k = 0; k < kFastQ; ++k) {
-      const int q = tid + k * nt;
-      if (q >= stot) break;
-      const float as = a_cur[k];
-      const float total = q < nS ? tot_num : tot_den, sign = q < nS ? -1.0f : 1.0f;
-      float acc = kLogZero;
-      for (int e = ptr[q]; e < ptr[q + 1]; ++e) {
-        const int pdf = arc_pdf[e];
-        if (pdf <= 0 || pdf > a.P) continue;
-        const float b = bn[arc_st[e]];
-        if (b <= kLogZero) continue;
-        const float v = b + arc_val(t, e, pdf) + arc_w[e];
-        acc = log_add(acc, v);
+    for (int k = 0; k < kFastArcs; ++k) {                // per arc: path value and posterior (chain.cu kernel_chain_posteriors)
+      const int e = tid + k * nt;
+      if (e >= atot) continue;
+      const float b = bn[e_st[k]];
+      float v = kLogZero;
+      if (e_pdf[k] != 0 && b > kLogZero) {
+        v = b + arc_val(t, k) + e_w[k];
+        const float as = al[e_src[k]];
         if (as > kLogZero) {
-          float lp = as + v - total;
-          if (lp > 0.0f) lp = 0.0f;
-          atomicAdd(&post[pdf - 1], sign * expf(lp));
+          const bool isn = e < nA;
+          atomicAdd(&post[e_pdf[k] - 1], (isn ? -1.0f : 1.0f) * __expf(fminf(as + v - (isn ? tot_num : tot_den), 0.0f)));
         }
       }
-      bt[q] = acc;
+      arc_v[e] = v;
     }
-    __syncthreads();                                   // posteriors of frame t and beta[t] complete
-    if (tid < pv) {                                    // gradient row t: 8 pdfs per thread, one 16-byte store (kernel_chain_gradient)
+    if (stamp) a.dbg[9] = clock64();
+    __syncthreads();                                     // path values and the posteriors of frame t complete
+    if (stamp) a.dbg[10] = clock64();
+#pragma unroll
+    for (int k = 0; k < kFastQ; ++k) {                   // per state: beta[t]
+      const int q = tid + k * nt;
+      if (q >= stot) continue;
+      bt[q] = lse(q_e0[k], q_e1[k]);
+    }
+    if (stamp) a.dbg[11] = clock64();
+    if (tid < pv) {                                      // gradient row t: 8 pdfs per thread, one 16-byte store (kernel_chain_gradient)
       __half2 h[4];
+      float4* pp = reinterpret_cast<float4*>(post + tid * 8);       // 16-byte shared-memory accesses (scalar ones at this
+      const float4 p0 = pp[0], p1 = pp[1];                          // stride are 8-way bank conflicts)
+      pp[0] = make_float4(0.f, 0.f, 0.f, 0.f); pp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float pv8[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float g0 = fmaxf(-30.0f, fminf(30.0f, post[tid * 8 + 2 * j] * a.weight));
-        const float g1 = fmaxf(-30.0f, fminf(30.0f, post[tid * 8 + 2 * j + 1] * a.weight));
+        const float g0 = fmaxf(-30.0f, fminf(30.0f, pv8[2 * j] * a.weight));
+        const float g1 = fmaxf(-30.0f, fminf(30.0f, pv8[2 * j + 1] * a.weight));
         h[j] = __floats2half2_rn(g0, g1);
-        post[tid * 8 + 2 * j] = 0.f; post[tid * 8 + 2 * j + 1] = 0.f;
       }
       *reinterpret_cast<uint4*>(grad_seq + (size_t)t * row_stride + tid * 8) = *reinterpret_cast<const uint4*>(h);
       if (!gathered && t > 0) reinterpret_cast<uint4*>(rowh + ((t - 1) & 1) * L.p_pad)[tid] = nxt;
     }
+    if (stamp) a.dbg[12] = clock64();
+    if (t > 0) {
 #pragma unroll
-    for (int k = 0; k < kFastQ; ++k) { a_cur[k] = a_n1[k]; a_n1[k] = a_n2[k]; }
-    __syncthreads();                                   // post cleared, next row staged
+      for (int k = 0; k < kFastQ; ++k) { const int q = tid + k * nt; if (q < stot) alpha_s[((t - 1) & 1) * stot_max + q] = a_pre[k]; }
+    }
+    if (stamp) a.dbg[13] = clock64();
+    __syncthreads();                                     // beta[t], cleared posteriors, next alpha / row staged
+    if (stamp) a.dbg[14] = clock64();
   }
+  if (a.dbg && seq == 0 && tid == 0) a.dbg[4] = clock64();
 }
 
 bool upload(void** dev, const void* host, size_t bytes) {
@@ -451,6 +534,7 @@ struct kfp16_chain {
   std::vector<DevFst> nums;
   FstRef* nums_dev = nullptr;
   int snum_max = 0, anum_max = 0;
+  long long* dbg = nullptr;
   bool force_general = false;   // tests: run the global-memory kernel even when the shared-memory one would fit
   float *alpha_num = nullptr, *alpha_den = nullptr, *beta = nullptr, *result = nullptr;
   size_t alpha_num_elems = 0;
@@ -528,19 +612,28 @@ int kfp16_chain_loss(kfp16_chain* c, const void* nnet_out, void* grad_out, int l
   a.T = c->frames; a.P = c->num_pdfs; a.weight = supervision_weight;
   a.alpha_num = c->alpha_num; a.alpha_den = c->alpha_den; a.beta = c->beta;
   a.snum_max = c->snum_max; a.sden = c->den.S;
-  a.result = c->result; a.loss_accum = loss_accum_dev;
+  a.result = c->result; a.loss_accum = loss_accum_dev; a.dbg = c->dbg;
   static bool attr_done = false;
   if (!attr_done) {
     if (!check_cuda(cudaFuncSetAttribute(chain_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "cudaFuncSetAttribute(chain)") ||
-        !check_cuda(cudaFuncSetAttribute(chain_loss_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax), "cudaFuncSetAttribute(chain fast)")) return -1;
+        !check_cuda(cudaFuncSetAttribute(chain_loss_fast_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax), "cudaFuncSetAttribute(chain fast)") ||
+        !check_cuda(cudaFuncSetAttribute(chain_loss_fast_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax), "cudaFuncSetAttribute(chain fast)") ||
+        !check_cuda(cudaFuncSetAttribute(chain_loss_fast_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax), "cudaFuncSetAttribute(chain fast)") ||
+        !check_cuda(cudaFuncSetAttribute(chain_loss_fast_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemMax), "cudaFuncSetAttribute(chain fast)")) return -1;
     attr_done = true;
   }
   // everything in shared memory when it fits (small graphs: the usual numerator, a compact denominator)
   const int stot_max = c->snum_max + c->den.S, atot_max = c->anum_max + c->den.A;
   const FastSmem L = fast_layout(c->num_pdfs, stot_max, atot_max, c->frames);
   const bool aligned = (c->num_pdfs % 8) == 0 && (ld % 8) == 0 && ((uintptr_t)nnet_out & 15) == 0 && (!grad_out || ((uintptr_t)grad_out & 15) == 0);
-  if (aligned && stot_max <= kFastStates && L.total <= kChainSmemMax && !c->force_general) {
-    chain_loss_fast_kernel<<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, ref_of(c->den), stot_max, atot_max);
+  if (aligned && stot_max <= kFastStates && atot_max <= kFastArcsMax * kChainThreads && L.total <= kChainSmemMax && !c->force_general) {
+    // the smallest per-thread arc / state counts that cover the graphs (less unrolled code, fewer registers)
+    const int ar = (atot_max + kChainThreads - 1) / kChainThreads, qr = (stot_max + kChainThreads - 1) / kChainThreads;
+    const FstRef dref = ref_of(c->den);
+    if (ar <= 1 && qr <= 1) chain_loss_fast_kernel<1, 1><<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, dref, stot_max, atot_max);
+    else if (ar <= 2 && qr <= 1) chain_loss_fast_kernel<2, 1><<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, dref, stot_max, atot_max);
+    else if (qr <= 2) chain_loss_fast_kernel<4, 2><<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, dref, stot_max, atot_max);
+    else chain_loss_fast_kernel<4, 4><<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, dref, stot_max, atot_max);
   } else {
     const size_t smem = (size_t)c->num_pdfs * 2 * sizeof(float);
     chain_loss_kernel<<<c->n_seq, kChainThreads, smem, c->ctx->stream>>>(a, c->nums_dev, ref_of(c->den));
@@ -555,6 +648,7 @@ int kfp16_chain_read_results(kfp16_chain* c, float* host, int n_seq) {
   return check_cuda(cudaMemcpy(host, c->result, (size_t)n_seq * 4 * sizeof(float), cudaMemcpyDeviceToHost), "chain results download") ? 0 : -1;
 }
 
+int kfp16_chain_set_debug(kfp16_chain* c, void* dev_i64x8) { if (!c) return -1; c->dbg = (long long*)dev_i64x8; return 0; }
 int kfp16_chain_force_general(kfp16_chain* c, int on) { if (!c) return -1; c->force_general = on != 0; return 0; }
 int kfp16_chain_num_sequences(const kfp16_chain* c) { return c ? c->n_seq : 0; }
 int kfp16_chain_frames(const kfp16_chain* c) { return c ? c->frames : 0; }
