@@ -136,6 +136,9 @@ typedef struct {
      * mask bit is (ReLU active AND kept).  u is a counter-based hash (kfp16_dropout_uniform); seed = drop_seed XOR
      * *drop_seed_dev when that device word is given (a per-step counter, so CUDA-graph replays draw new masks). */
     const uint32_t *drop_seed_dev;
+    /* zero_row_period > 0: output rows r with (r mod period) outside [lo, hi) are stored as zeros and get a zero mask --
+     * the halo rows of the padded minibatch layout, which the next convolution reads as its zero padding in time */
+    int zero_row_period, zero_row_lo, zero_row_hi;
 } kfp16_gemm_desc;
 /* the dropout hash, for callers that need the mask on the host: uniform in [0,1) */
 float kfp16_dropout_uniform(uint32_t seed, uint32_t row, uint32_t col);

@@ -52,6 +52,7 @@ class GemmDesc(C.Structure):
         ("ws2", c_void_p * 2), ("ws2_ld", c_int), ("ws2_transposed", c_int),
         ("conv", ConvAddr),
         ("drop_seed_dev", c_void_p),
+        ("zero_row_period", c_int), ("zero_row_lo", c_int), ("zero_row_hi", c_int),
     ]
 
 

@@ -433,6 +433,10 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   p.ws_ld = d->ws_ld;
   p.ws_transposed = d->ws_transposed;
   p.drop_p = d->drop_p; p.drop_seed = d->drop_seed; p.drop_seed_dev = d->drop_seed_dev;
+  if (d->zero_row_period > 0) {
+    if (d->zero_row_lo < 0 || d->zero_row_hi < d->zero_row_lo || d->zero_row_hi > d->zero_row_period) { set_error("kfp16_gemm_ex: zero_row window must satisfy 0 <= lo <= hi <= period"); return -1; }
+    p.zero_period = (uint32_t)d->zero_row_period; p.zero_lo = (uint32_t)d->zero_row_lo; p.zero_len = (uint32_t)(d->zero_row_hi - d->zero_row_lo);
+  }
   if ((flags & EPI_DROPOUT) && !(d->drop_p >= 0.0f && d->drop_p < 1.0f)) { set_error("kfp16_gemm_ex: dropout probability must be in [0, 1)"); return -1; }
   if ((flags & EPI_BIAS) && !p.bias) { set_error("kfp16_gemm_ex: EPI_BIAS without bias"); return -1; }
   if ((flags & EPI_BN) && (!p.bn_scale || !p.bn_shift)) { set_error("kfp16_gemm_ex: EPI_BN without scale/shift"); return -1; }

@@ -140,6 +140,9 @@ struct GemmParams {
   int conv_tx;                  // bytes one CTA's loads deliver per k-block
   int8_t conv_dt[kMaxTaps], conv_hq[kMaxTaps], conv_par[kMaxTaps];
   int conv_brow[kMaxTaps];      // conv 1: B row offset of tap s (MN-major B: added to the k row; K-major B: to the n row)
+  // rows whose index modulo zero_period lies outside [zero_lo, zero_lo + zero_len) are written as zeros with a zero mask
+  // (halo rows of the padded minibatch layout: the zero padding the next convolution reads); zero_period == 0: off
+  uint32_t zero_period, zero_lo, zero_len;
   long long* dbg;               // profiling: per-CTA role timestamps [grid][3 roles][8 tiles][16] (nullptr = off)
 };
 
@@ -652,6 +655,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       if (kMerge) g = gg;
       const int row = m_row0 + row_in_tile;
       const int n0 = n_blk * BN;
+      const bool zero_row = p.zero_period != 0 && ((uint32_t)row % p.zero_period - p.zero_lo) >= p.zero_len;
       if (warp == 4) dbg_stamp(p, 2, tile_i, 0);
 
       const uint32_t s_bias = smem_u32(smem_vec + vsel * kVecBytes);            // fp32 [BN] each
@@ -831,8 +835,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
               uint4 ov;
               ov.x = pack_f16x2(xo[0], xo[1]); ov.y = pack_f16x2(xo[2], xo[3]);
               ov.z = pack_f16x2(xo[4], xo[5]); ov.w = pack_f16x2(xo[6], xo[7]);
+              if (zero_row) ov = make_uint4(0u, 0u, 0u, 0u);
               sts128(sptr, ov);
             }
+            if (zero_row) maskword = 0u;
             if ((flags & EPI_MASK) && row < p.M && row_in_tile < ti.tile_rows && n0 + c < p.N)
               p.mask_out[(size_t)row * p.mask_ld + ((n0 + c) >> 5)] = maskword;
           }

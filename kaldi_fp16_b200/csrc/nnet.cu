@@ -1058,6 +1058,10 @@ int forward_layer(kfp16_net* n, Layer& l) {
       d.bias = W16(n, l.pB);
       d.bn_scale = l.bn.scale; d.bn_shift = l.bn.shift;
       d.mask_out = l.mask; d.mask_ld = l.mask_ld;
+      if (n->halo > 0) {   // halo rows of the output (and their mask bits) are written as zeros by the epilogue: they are the
+        // next convolution's zero padding in time, and a zero mask keeps their gradients out of the backward pass
+        d.zero_row_period = n->blk * l.hout; d.zero_row_lo = n->halo * l.hout; d.zero_row_hi = (n->halo + n->opts.seq_len) * l.hout;
+      }
       if (kfp16_gemm_ex(ctx, &d)) return -1;
       break;
     }
@@ -1074,6 +1078,7 @@ int forward_layer(kfp16_net* n, Layer& l) {
     }
     default: break;
   }
+  if (l.type == L_CONV && l.halo_mode == HALO_ZERO) return 0;    // its epilogue already stored zeros there
   if (l.halo_mode != HALO_NONE && fix_halo(n, l, l.out, l.halo_mode)) return -1;
   return 0;
 }
@@ -1086,7 +1091,8 @@ int backward_layer(kfp16_net* n, Layer& l) {
   // adjoint of the halo fix-up applied to this layer's output in the forward pass
   if (!l.per_seq && n->halo > 0) {
     if (l.halo_mode == HALO_REPL && kfp16_fold_edges(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
-    if (l.halo_mode == HALO_ZERO && kfp16_zero_halo(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
+    // (a convolution's halo rows carry a zero ReLU mask from its forward epilogue: dZ is zero there whatever dY holds)
+    if (l.halo_mode == HALO_ZERO && l.type != L_CONV && kfp16_zero_halo(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
   }
   const Buf& X = layer_input(n, l);
   Buf dx = l.wants_dx ? dx_target(n, l) : Buf();
@@ -1183,9 +1189,9 @@ int backward_layer(kfp16_net* n, Layer& l) {
     }
     case L_CONV: {     // transpose of the forward (the reference treats the conv as a dense affine: quirk Q2)
       const int mrows = rows * l.hout;
-      // gradients on halo rows are not part of the minibatch: zero them so that neither the weight gradient (a sum over
-      // ALL padded rows) nor the input gradient of neighbouring real frames sees them
-      if (n->halo > 0 && l.halo_mode == HALO_NONE && kfp16_zero_halo(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
+      // gradients on halo rows are not part of the minibatch: the forward epilogue left a zero ReLU mask on them, so dZ is
+      // zero there and neither the weight gradient (a sum over ALL padded rows) nor the input gradient of neighbouring
+      // real frames sees them
       if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.fout, l.bn.scale, l.mask, l.mask_ld, n->conv_dz, l.fout, mrows, l.fout, G32(n, l.pB))) return -1;
       if (l.conv_implicit) {
         {  // dW[(tap, f), fo] = sum over (t, h) of X[t+dt, h*sub+dh, f] * dZ[(t, h), fo]
