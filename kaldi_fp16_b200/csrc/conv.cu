@@ -11,7 +11,6 @@
 
 #include "../../include/kaldi_fp16_fused.h"
 #include "host_common.h"
-#include "sm100_ptx.cuh"
 
 using namespace kfp16;
 
@@ -65,72 +64,6 @@ __global__ void im2col_kernel(const __half* __restrict__ x, __half* __restrict__
         if ((int)f < g.fin) dst[(size_t)tap * g.fin] = ok ? src[(ptrdiff_t)taps.dt[tap] * (ptrdiff_t)ldx + (size_t)hs * g.fin] : __float2half(0.f);
       }
     }
-  }
-}
-
-// Few input filters (the first layer: fin = 6, K = 54 of Kp = 64): one thread per (patch row, 8 patch columns) assembles the
-// 16 bytes from scalar reads of the small, cache-resident input and writes them with one store, K padding included
-// (the element-wise form above moved 2 bytes per thread: 45 us for 49 MB).
-__global__ void im2col_rows8_kernel(const __half* __restrict__ x, __half* __restrict__ P, ConvGeom g, Taps taps, int K) {
-  const uint32_t kv = (uint32_t)g.Kp / 8;
-  const uint32_t rows = (uint32_t)g.n_seq * g.blk * g.hout;
-  const uint32_t total = rows * kv;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t ldx = (uint32_t)g.hin * g.fin;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const uint32_t k0 = (i % kv) * 8;
-    const uint32_t m = i / kv;
-    const int ho = (int)(m % (uint32_t)g.hout);
-    const uint32_t r = m / (uint32_t)g.hout;
-    const int local = (int)(r % (uint32_t)g.blk) - g.halo;
-    const bool row_ok = local >= 0 && local < g.L;
-    unsigned short v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t k = k0 + j;
-      v[j] = 0;
-      if (row_ok && (int)k < K) {
-        const uint32_t tap = k / (uint32_t)g.fin, f = k - tap * g.fin;
-        const int ts = local + taps.dt[tap], hs = ho * g.sub + taps.dh[tap];
-        if (ts >= 0 && ts < g.L && hs >= 0 && hs < g.hin)
-          v[j] = __ldg(reinterpret_cast<const unsigned short*>(x) + (size_t)(r + taps.dt[tap]) * ldx + (uint32_t)hs * g.fin + f);
-      }
-    }
-    uint4 o;
-    o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
-    o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
-    *reinterpret_cast<uint4*>(P + (size_t)m * g.Kp + k0) = o;
-  }
-}
-// adjoint for few (even) input filters: one thread per input position (r, h) sums, per tap, its fin contiguous values
-// (4-byte loads) in fp32 and stores the fin results
-template <int FIN>
-__global__ void col2im_small_kernel(const __half* __restrict__ dP, __half* __restrict__ dx, ConvGeom g, Taps taps) {
-  const uint32_t total = (uint32_t)g.n_seq * g.blk * g.hin;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int hh = (int)(i % (uint32_t)g.hin);
-    const uint32_t r = i / (uint32_t)g.hin;
-    const int local = (int)(r % (uint32_t)g.blk) - g.halo;
-    float acc[FIN];
-#pragma unroll
-    for (int e = 0; e < FIN; ++e) acc[e] = 0.f;
-    if (local >= 0 && local < g.L) {
-      for (int tap = 0; tap < taps.n; ++tap) {
-        const int to = local - taps.dt[tap];
-        const int hs = hh - taps.dh[tap];
-        int ho = hs;
-        bool hit = to >= 0 && to < g.L && hs >= 0;
-        if (g.sub != 1) { hit = hit && (hs % g.sub) == 0; ho = hs / g.sub; }
-        if (!hit || ho >= g.hout) continue;
-        const __half2* src = reinterpret_cast<const __half2*>(dP + ((size_t)(r - taps.dt[tap]) * g.hout + ho) * g.Kp + tap * FIN);
-#pragma unroll
-        for (int e = 0; e < FIN / 2; ++e) { const float2 t = __half22float2(__ldg(src + e)); acc[2 * e] += t.x; acc[2 * e + 1] += t.y; }
-      }
-    }
-    __half2* dst = reinterpret_cast<__half2*>(dx + (size_t)r * (g.hin * FIN) + hh * FIN);
-#pragma unroll
-    for (int e = 0; e < FIN / 2; ++e) dst[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
   }
 }
 
@@ -245,12 +178,6 @@ int kfp16_im2col(kfp16_ctx* ctx, const void* x, void* P, int Kp, int n_seq, int 
   cudaStream_t s = ctx ? ctx->stream : default_stream();
   const size_t rows = (size_t)n_seq * g.blk * hout;
   const int K = ntaps * fin;
-  if ((fin % 8) != 0 && (Kp % 8) == 0 && ((uintptr_t)P & 15) == 0 && rows * (size_t)(Kp / 8) < 0xFFFFFFFFull) {
-    // few input filters: whole 16-byte patch groups per thread, K padding written in the same pass
-    launch_pdl(im2col_rows8_kernel, grid_for_elems(rows * (Kp / 8)), 256, 0, s, (const __half*)x, (__half*)P, g, t, K);
-    count_launch();
-    return check_launch("kfp16_im2col") ? 0 : -1;
-  }
   if (Kp > K) {
     zero_pad_cols_kernel<<<grid_for_elems(rows * (Kp - K)), 256, 0, s>>>((__half*)P, rows, K, Kp);
     count_launch();
@@ -271,13 +198,6 @@ int kfp16_col2im(kfp16_ctx* ctx, const void* dP, int Kp, void* dx, int n_seq, in
   cudaStream_t s = ctx ? ctx->stream : default_stream();
   const size_t elems = (size_t)n_seq * g.blk * hin;
   if (elems * (size_t)fin >= 0xFFFFFFFFull) { set_error("kfp16_col2im: more than 2^32 input elements"); return -1; }
-  if ((fin == 2 || fin == 4 || fin == 6) && (Kp % 2) == 0 && ((uintptr_t)dx & 3) == 0 && ((uintptr_t)dP & 3) == 0) {
-    if (fin == 2) launch_pdl(col2im_small_kernel<2>, grid_for_elems(elems), 256, 0, s, (const __half*)dP, (__half*)dx, g, t);
-    else if (fin == 4) launch_pdl(col2im_small_kernel<4>, grid_for_elems(elems), 256, 0, s, (const __half*)dP, (__half*)dx, g, t);
-    else launch_pdl(col2im_small_kernel<6>, grid_for_elems(elems), 256, 0, s, (const __half*)dP, (__half*)dx, g, t);
-    count_launch();
-    return check_launch("kfp16_col2im") ? 0 : -1;
-  }
   const bool vec = (fin % 8) == 0 && (Kp % 8) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)dP & 15) == 0;
   if (vec) col2im_kernel<8><<<grid_for_elems(elems * (fin / 8)), 256, 0, s>>>((const __half*)dP, (__half*)dx, g, t);
   else col2im_kernel<1><<<grid_for_elems(elems * fin), 256, 0, s>>>((const __half*)dP, (__half*)dx, g, t);
