@@ -52,7 +52,9 @@ float kaldi_loss_scaler_get_scale(void *scaler);
 void kaldi_loss_scaler_update(void *scaler, int overflow);
 
 /* ---- cnn_fp16.h:24-56: input [B,T,Cin], weight [Cout,Cin,K], bias [Cout] or NULL, output [B,Tout,Cout],
- * Tout = (T + 2*padding - dilation*(K-1) - 1)/stride + 1.  Lowered to a patch gather + one GEMM. */
+ * Tout = (T + 2*padding - dilation*(K-1) - 1)/stride + 1.  Lowered to a patch gather + one GEMM: the tcgen05 / TMA kernel
+ * when Cin*K and Cout are multiples of 8, a dense SIMT GEMM otherwise (any channel count is accepted, like the reference's
+ * kernels).  These are void functions: a failure leaves its message in kaldi_get_last_error(). */
 void launch_conv1d_forward_fp16(const void *input, const void *weight, const void *bias, void *output,
                                 int batch_size, int time_in, int in_channels, int out_channels,
                                 int kernel_size, int stride, int padding, int dilation, void *stream);

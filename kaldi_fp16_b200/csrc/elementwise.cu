@@ -596,6 +596,15 @@ __global__ void colsum_kernel(const __half* __restrict__ X, int ld, size_t rows,
   }
 }
 
+// any column count / leading dimension (odd channel counts of the kaldibridge conv surface): scalar loads
+__global__ void colsum_scalar_kernel(const __half* __restrict__ X, int ld, size_t rows, int cols, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (size_t r = blockIdx.y; r < rows; r += gridDim.y) s += __half2float(X[r * ld + c]);
+  atomicAdd(out + c, s);
+}
+
 // same column sum with the access pattern of the fused backward pass: 8 columns (16 bytes) per thread, kBnBwdRows rows in
 // flight, one wave of blocks; col_mod folds a narrow dense matrix into wide rows (see bn_relu_bwd_colsum_kernel)
 constexpr int kColsumRows = 4;
@@ -1150,10 +1159,15 @@ int kfp16_add_bias(kfp16_ctx* ctx, void* x, int ld, const void* bias, int rows, 
 }
 int kfp16_colsum(kfp16_ctx* ctx, const void* X, int ld, int rows, int cols, float* out_f32, void* out_f16) {
   if (cols <= 0) return 0;
-  if (!X || !out_f32 || (cols % 2) || (ld % 2)) { set_error("kfp16_colsum: needs fp32 output and even cols/ld"); return -1; }
+  if (!X || !out_f32) { set_error("kfp16_colsum: null pointer"); return -1; }
   cudaStream_t s = ctx_stream(ctx);
   if (!check_cuda(cudaMemsetAsync(out_f32, 0, (size_t)cols * sizeof(float), s), "kfp16_colsum memset")) return -1;
-  if (rows > 0) {
+  if (rows > 0 && ((cols % 2) || (ld % 2) || ((uintptr_t)X & 3))) {
+    int gy = rows < 256 ? (int)rows : 256;
+    colsum_scalar_kernel<<<dim3((cols + 127) / 128, gy), 128, 0, s>>>((const __half*)X, ld, (size_t)rows, cols, out_f32);
+    count_launch();
+    if (!check_launch("kfp16_colsum")) return -1;
+  } else if (rows > 0) {
     const int gx = (cols + 63) / 64;
     int gy = (num_sms_cached() * 4 + gx - 1) / gx;
     const int max_gy = (rows + 63) / 64;

@@ -29,20 +29,22 @@ struct LossScaler {   // cgo_interface.cu:405-411
   int growth_interval, steps_since_growth;
 };
 
-// context-free entry points run on a per-device default context bound to the caller's stream
+// context-free entry points (the reference's launch_* kernels were stateless per call) run on a context cached per
+// (device, stream): concurrent callers on different streams never see each other's stream or split-K workspace
 kfp16_ctx* device_ctx(cudaStream_t stream) {
   static std::mutex mu;
-  static std::map<int, kfp16_ctx*> ctxs;
+  static std::map<std::pair<int, cudaStream_t>, kfp16_ctx*> ctxs;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device"); return nullptr; }
   std::lock_guard<std::mutex> lock(mu);
-  auto it = ctxs.find(dev);
+  auto key = std::make_pair(dev, stream);
+  auto it = ctxs.find(key);
   if (it == ctxs.end()) {
     kfp16_ctx* c = kfp16_ctx_create(dev);
     if (!c) return nullptr;
-    it = ctxs.emplace(dev, c).first;
+    c->stream = stream;
+    it = ctxs.emplace(key, c).first;
   }
-  it->second->stream = stream;
   return it->second;
 }
 
@@ -322,11 +324,14 @@ void launch_conv1d_forward_fp16(const void* input, const void* weight, const voi
   if (!ctx) return;
   const size_t rows = (size_t)g.B * g.Tout;
   const int Kd = g.Cin * g.K;
+  // any channel count is accepted, as by the reference kernels (cnn_kernels.cu:19-65): shapes the TMA path cannot
+  // address (Cin*K or Cout not a multiple of 8) run the same lowering on a dense patch matrix through the SIMT GEMM
+  const bool tma = (Kd % 8) == 0 && (out_channels % 8) == 0 && al16(weight) && al16(output);
+  if (!tma) g.ldp = Kd;
   __half* P = nullptr;
   if (!check_cuda(cudaMallocAsync(&P, rows * g.ldp * sizeof(__half), s), "conv1d patch buffer")) return;
   conv1d_gather_k<<<blocks_for(rows * g.ldp), 256, 0, s>>>((const __half*)input, P, g);
   count_launch();
-  const bool tma = (Kd % 8) == 0 && (out_channels % 8) == 0 && al16(weight) && al16(output);
   if (tma) {   // out = P * W^T (+ bias): W stored [Cout x Cin*K] is a K-major B operand
     kfp16_gemm_desc d;
     memset(&d, 0, sizeof(d));
@@ -337,13 +342,11 @@ void launch_conv1d_forward_fp16(const void* input, const void* weight, const voi
     d.groups = 1; d.kslabs = 1; d.kslab_len = g.ldp;
     d.D[0] = output; d.ldd = out_channels; d.alpha = 1.0f;
     if (bias) { d.flags = KFP16_EPI_BIAS; d.bias = bias; }
-    kfp16_gemm_ex(ctx, &d);
-  } else {     // odd channel counts: SIMT GEMM over the zero-padded patch matrix is not addressable -> dense copy path
-    if (g.ldp != Kd) { set_error("launch_conv1d_forward_fp16: in_channels*kernel_size and out_channels must be multiples of 8 (got %d, %d)", Kd, out_channels); }
-    else {
-      kfp16_gemm(ctx, (int)rows, out_channels, Kd, 1.0f, P, 0, weight, 1, 0.0f, output);
-      if (bias) kfp16_add_bias(ctx, output, out_channels, bias, (int)rows, out_channels);
-    }
+    kfp16_gemm_ex(ctx, &d);      // (a failure leaves its message in the thread-local error: kaldi_get_last_error)
+  } else {
+    // bias first (broadcast into the output rows), then C = acc + 1*C in fp32: one rounding, as the reference kernel
+    if (bias && kfp16_bcast_rows(ctx, bias, out_channels, output, out_channels, 0, (int)rows, (int)rows) != 0) { cudaFreeAsync(P, s); return; }
+    kfp16_gemm(ctx, (int)rows, out_channels, Kd, 1.0f, P, 0, weight, 1, bias ? 1.0f : 0.0f, output);
   }
   cudaFreeAsync(P, s);
 }
@@ -359,7 +362,8 @@ void launch_conv1d_backward_fp16(const void* input, const void* grad_output, con
   if (!ctx) return;
   const size_t rows = (size_t)g.B * g.Tout;
   const int Kd = g.Cin * g.K;
-  if ((Kd % 8) || (out_channels % 8)) { set_error("launch_conv1d_backward_fp16: in_channels*kernel_size and out_channels must be multiples of 8 (got %d, %d)", Kd, out_channels); return; }
+  const bool tma = (Kd % 8) == 0 && (out_channels % 8) == 0 && al16(grad_output) && (!weight || al16(weight)) && (!grad_weight || al16(grad_weight));
+  if (!tma) g.ldp = Kd;      // dense patch matrix + SIMT GEMMs for channel counts TMA cannot address
   if (grad_bias) {   // column sum in fp32, one fp16 rounding (cnn_kernels.cu:208-229)
     float* acc = nullptr;
     if (!check_cuda(cudaMallocAsync(&acc, (size_t)out_channels * sizeof(float), s), "conv1d bias-gradient scratch")) return;
@@ -371,6 +375,9 @@ void launch_conv1d_backward_fp16(const void* input, const void* grad_output, con
   if (grad_weight && input) {   // dW[oc, ic*K+k] = sum_rows gout[row, oc] * P[row, ic*K+k]
     conv1d_gather_k<<<blocks_for(rows * g.ldp), 256, 0, s>>>((const __half*)input, P, g);
     count_launch();
+    if (!tma) {
+      kfp16_gemm(ctx, out_channels, Kd, (int)rows, 1.0f, grad_output, 1, P, 0, 0.0f, grad_weight);
+    } else {
     kfp16_gemm_desc d;
     memset(&d, 0, sizeof(d));
     d.M = out_channels; d.N = Kd; d.K = (int)rows;
@@ -380,8 +387,15 @@ void launch_conv1d_backward_fp16(const void* input, const void* grad_output, con
     d.groups = 1; d.kslabs = 1; d.kslab_len = (int)rows;
     d.D[0] = grad_weight; d.ldd = Kd; d.alpha = 1.0f;
     kfp16_gemm_ex(ctx, &d);
+    }
   }
-  if (grad_input && weight) {   // dP = gout * W, then the adjoint of the gather
+  if (grad_input && weight && !tma) {
+    if (kfp16_gemm(ctx, (int)rows, Kd, out_channels, 1.0f, grad_output, 0, weight, 0, 0.0f, P) == 0) {
+      conv1d_scatter_k<<<blocks_for((size_t)g.B * g.T * g.Cin), 256, 0, s>>>(P, (__half*)grad_input, g);
+      count_launch();
+      check_launch("conv1d input gradient");
+    }
+  } else if (grad_input && weight) {   // dP = gout * W, then the adjoint of the gather
     kfp16_gemm_desc d;
     memset(&d, 0, sizeof(d));
     d.M = (int)rows; d.N = Kd; d.K = out_channels;

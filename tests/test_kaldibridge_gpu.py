@@ -81,8 +81,11 @@ def test_kaldi_tensor_api_and_elementwise(lib):
 
 
 @pytest.mark.parametrize("stride,padding,dilation,K", [(1, 1, 1, 3), (2, 2, 2, 3), (1, 0, 1, 5)])
-def test_conv1d_forward_and_backward_vs_reference(lib, reflib, stride, padding, dilation, K):
-    B, T, Cin, Cout = 3, 50, 16, 24
+@pytest.mark.parametrize("Cin,Cout", [(16, 24), (5, 7), (16, 10), (3, 8)])
+def test_conv1d_forward_and_backward_vs_reference(lib, reflib, stride, padding, dilation, K, Cin, Cout):
+    """(16, 24): the tcgen05 / TMA lowering; the other channel counts (Cin*K or Cout not a multiple of 8) must be accepted
+    like the reference's kernels accept them (cnn_kernels.cu:19-65) and run the dense SIMT lowering"""
+    B, T = 3, 50
     Tout = (T + 2 * padding - dilation * (K - 1) - 1) // stride + 1
     rng = np.random.default_rng(K * 10 + stride)
     x, w, b = f16(rng, (B, T, Cin)), f16(rng, (Cout, Cin, K), 0.2), f16(rng, (Cout,), 0.1)
