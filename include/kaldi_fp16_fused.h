@@ -250,6 +250,28 @@ int kfp16_im2col(kfp16_ctx *ctx, const void *x, void *P, int Kp, int n_seq, int 
 int kfp16_col2im(kfp16_ctx *ctx, const void *dP, int Kp, void *dx, int n_seq, int seq_len, int halo, int hin,
                  int hout, int sub, int fin, int ntaps, const int *dt, const int *dh);
 
+/* ---- egs feature decode on the device: Kaldi compressed matrices -> FP16 rows
+ * (the reference decodes on the CPU while parsing: internal/parser/matrix.go:11-165, then converts to FP16 on the CPU,
+ *  internal/gpu/bridge.go:141).  The payload is the matrix body as it sits in the archive, after the global header
+ *  (format token, global min, global range, rows, cols -- parsed on the host, internal/parser/parser.go:300-365):
+ *    KFP16_CM   "CM"  cols x 4 uint16 percentiles, then rows*cols bytes COLUMN-major      (ReadCompressedMatrix)
+ *    KFP16_CM2  "CM2" rows*cols uint16 row-major                                            (ReadCompressedMatrix2)
+ *    KFP16_CM3  "CM3" rows*cols uint8  row-major                                            (ReadCompressedMatrix3)
+ *    KFP16_FM   "FM"  rows*cols float32 row-major                                           (ReadFullMatrix)
+ * Same float32 arithmetic operation for operation, then round-to-nearest-even FP16: bit-identical to decode + convert
+ * on the CPU.  One launch decodes up to 64 matrices (the sequences of a minibatch), each into dst rows [dst_row, +rows). */
+enum { KFP16_CM = 1, KFP16_CM2 = 2, KFP16_CM3 = 3, KFP16_FM = 4 };
+typedef struct {
+    int format;
+    int rows, cols;
+    float global_min, global_range;
+    size_t payload_offset; /* byte offset of this matrix's body inside the payload buffer (even for CM / CM2) */
+    int dst_row;           /* first destination row */
+} kfp16_cm_desc;
+size_t kfp16_cm_payload_bytes(const kfp16_cm_desc *d);
+int kfp16_decode_matrices(kfp16_ctx *ctx, const void *payload_dev, size_t payload_size, const kfp16_cm_desc *descs, int count,
+                          void *dst_f16, int ld, int dst_rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,12 @@ int kfp16_net_commit_input(kfp16_net *net, const char *input_name);
  * the CPU through fp16.ConvertFloat32ToFloat16 (internal/fp16/fp16.go:13-70).  commit_input handles either kind. */
 int kfp16_net_set_input_f32(kfp16_net *net, const char *input_name, const float *host_f32, int rows, int cols);
 int kfp16_net_prefetch_input_f32(kfp16_net *net, const char *input_name, const float *host_pinned_f32, int rows, int cols);
+/* egs payloads straight from the archive: one compressed / full matrix per sequence (descs[i].rows = seq_len frames of
+ * sequence i; dst_row is ignored -- the executor knows where sequence i lives in its padded layout).  The payload bytes
+ * are uploaded (pinned or pageable host memory) and decoded + converted to FP16 on the device (kfp16_decode_matrices):
+ * the on-device form of parser.ReadCompressedMatrix* + gpu.TransferBatch (internal/gpu/bridge.go:123-221). */
+int kfp16_net_set_input_compressed(kfp16_net *net, const char *input_name, const void *payload_host, size_t payload_size,
+                                   const kfp16_cm_desc *descs, int count);
 int kfp16_net_forward(kfp16_net *net);
 /* dense real rows of a layer's output -> host fp16 [n_seq*seq_len x dim] */
 int kfp16_net_get_output(kfp16_net *net, const char *layer, uint16_t *host_f16, int rows, int cols);

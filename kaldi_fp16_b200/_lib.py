@@ -71,6 +71,13 @@ class ChainFst(C.Structure):
                 ("num_states", c_int), ("num_arcs", c_int), ("num_final", c_int), ("start_state", c_int)]
 
 
+class CmDesc(C.Structure):
+    """struct kfp16_cm_desc (include/kaldi_fp16_fused.h)"""
+
+    _fields_ = [("format", c_int), ("rows", c_int), ("cols", c_int), ("global_min", c_float), ("global_range", c_float),
+                ("payload_offset", c_size_t), ("dst_row", c_int)]
+
+
 class NetOpts(C.Structure):
     """struct kfp16_net_opts (include/kaldi_fp16_nnet.h)."""
 
@@ -138,6 +145,9 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_bn_relu_backward_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "kfp16_bn_relu_backward_bias_fold": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "kfp16_colsum_accum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kfp16_cm_payload_bytes": (c_size_t, [C.POINTER(CmDesc)]),
+    "kfp16_decode_matrices": (c_int, [c_void_p, c_void_p, c_size_t, C.POINTER(CmDesc), c_int, c_void_p, c_int, c_int]),
+    "kfp16_net_set_input_compressed": (c_int, [c_void_p, C.c_char_p, c_void_p, c_size_t, C.POINTER(CmDesc), c_int]),
     "kfp16_im2col": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [C.POINTER(c_int), C.POINTER(c_int)]),
     "kfp16_col2im": (c_int, [c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 8 + [C.POINTER(c_int), C.POINTER(c_int)]),
     # ---- kaldi_fp16_nnet.h

@@ -1540,6 +1540,34 @@ int kfp16_net_commit_input(kfp16_net* n, const char* input_name) {
   return check_cuda(cudaEventRecord(l.pf_packed[b], n->ctx->stream), "commit record") ? 0 : -1;
 }
 
+int kfp16_net_set_input_compressed(kfp16_net* n, const char* input_name, const void* payload_host, size_t payload_size,
+                                   const kfp16_cm_desc* descs, int count) {
+  if (!n || !input_name || !payload_host || !descs) { set_error("kfp16_net_set_input_compressed: null argument"); return -1; }
+  const int i = find_layer(n, input_name);
+  if (i < 0 || n->layers[i].type != L_INPUT) { set_error("kfp16_net_set_input_compressed: no input layer named %s", input_name); return -1; }
+  Layer& l = n->layers[i];
+  if (l.per_seq || count != n->opts.n_seq) { set_error("kfp16_net_set_input_compressed: %s takes one matrix per sequence (%d)", input_name, n->opts.n_seq); return -1; }
+  if (payload_size > n->stage_bytes) { set_error("kfp16_net_set_input_compressed: payload of %zu bytes exceeds the staging buffer", payload_size); return -1; }
+  std::vector<kfp16_cm_desc> d(descs, descs + count);
+  for (int q = 0; q < count; ++q) {
+    if (d[q].rows != n->opts.seq_len || d[q].cols != l.out_dim) {
+      set_error("kfp16_net_set_input_compressed: sequence %d is [%d x %d], expected [%d x %d]", q, d[q].rows, d[q].cols, n->opts.seq_len, l.out_dim);
+      return -1;
+    }
+    d[q].dst_row = q * n->blk + n->halo;      // the sequence's real rows inside the padded layout
+  }
+  cudaStream_t st = n->ctx->stream;
+  if (!check_cuda(cudaMemcpyAsync(n->stage_in, payload_host, payload_size, cudaMemcpyHostToDevice, st), "payload upload")) return -1;
+  if (kfp16_decode_matrices(n->ctx, n->stage_in, payload_size, d.data(), count, l.out.p, l.out.cols, n->Tp)) return -1;
+  // halo rows: replicate for spliced consumers, zero otherwise (as kfp16_net_set_input does)
+  if (n->halo > 0) {
+    const int rc = l.halo_mode == HALO_ZERO ? kfp16_zero_halo(n->ctx, l.out.p, l.out.cols, n->opts.n_seq, n->opts.seq_len, l.out.cols, n->halo)
+                                            : kfp16_pad_edges(n->ctx, l.out.p, l.out.cols, n->opts.n_seq, n->opts.seq_len, l.out.cols, n->halo);
+    if (rc) return -1;
+  }
+  return check_cuda(cudaStreamSynchronize(st), "input sync") ? 0 : -1;
+}
+
 int kfp16_net_forward(kfp16_net* n) {
   if (!n) { set_error("kfp16_net_forward: null network"); return -1; }
   for (auto& l : n->layers)

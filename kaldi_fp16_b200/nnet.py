@@ -146,6 +146,25 @@ class Network:
         if self.lib.kfp16_net_set_input_f32(self.ptr, name.encode(), x.ctypes.data, x.shape[0], x.shape[1]) != 0:
             raise _err("SetInputF32")
 
+    def SetInputCompressed(self, name: str, mats) -> None:
+        """egs feature matrices as they sit in the archive, one per sequence: ``mats`` is a list of
+        (format, payload bytes, global_min, global_range) with format in {"CM", "CM2", "CM3", "FM"} (parser.go:300-365);
+        the payload is uploaded and decoded + converted to FP16 on the device"""
+        fmt = {"CM": 1, "CM2": 2, "CM3": 3, "FM": 4}
+        cols = self.layer_dim(name)
+        descs = (_lib.CmDesc * len(mats))()
+        blob = bytearray()
+        for i, (f, payload, gmin, grange) in enumerate(mats):
+            if len(blob) & 1:
+                blob.append(0)
+            d = descs[i]
+            d.format, d.rows, d.cols, d.global_min, d.global_range = fmt[f], self.seq_len, cols, gmin, grange
+            d.payload_offset, d.dst_row = len(blob), 0
+            blob += payload
+        buf = (C.c_ubyte * len(blob)).from_buffer(blob)
+        if self.lib.kfp16_net_set_input_compressed(self.ptr, name.encode(), buf, len(blob), descs, len(mats)) != 0:
+            raise _err("SetInputCompressed")
+
     def PrefetchInputF32(self, name: str, host_ptr: int, rows: int, cols: int) -> None:
         """async H2D of the next minibatch's FP32 rows from pinned host memory; CommitInput converts on the device"""
         if self.lib.kfp16_net_prefetch_input_f32(self.ptr, name.encode(), host_ptr, rows, cols) != 0:

@@ -237,6 +237,42 @@ def subsample_rows(x, stride, row_offset):
 
 
 # ----------------------------------------------------------------------------- backward ops
+# ----------------------------------------------------------------------------- egs feature decode
+def _u16_to_float(gmin, grange, v):
+    """internal/parser/matrix.go:11-14 uint16ToFloat, float32 arithmetic left to right"""
+    return f32(gmin) + (f32(grange) * f32(1.52590218966964e-05)) * v.astype(f32)
+
+
+def decode_cm(payload: bytes, rows: int, cols: int, gmin: float, grange: float) -> np.ndarray:
+    """ReadCompressedMatrix (matrix.go:28-84): cols x 4 uint16 percentiles, then bytes COLUMN-major; charToFloat (17-26)"""
+    hdr = np.frombuffer(payload, np.uint16, cols * 4).reshape(cols, 4)
+    data = np.frombuffer(payload, np.uint8, rows * cols, offset=cols * 8).reshape(cols, rows).T      # [rows x cols]
+    p = _u16_to_float(gmin, grange, hdr)                                                            # [cols x 4] float32
+    p0, p25, p75, p100 = p[:, 0], p[:, 1], p[:, 2], p[:, 3]
+    v = data.astype(f32)
+    b1 = p0 + ((p25 - p0) * v) * f32(1.0 / 64.0)
+    b2 = p25 + ((p75 - p25) * (v - f32(64))) * f32(1.0 / 128.0)
+    b3 = (p75.astype(np.float64) + ((p100 - p75) * (v - f32(192))).astype(np.float64) / 63.0).astype(f32)
+    return np.where(data <= 64, b1, np.where(data <= 192, b2, b3)).astype(f32)
+
+
+def decode_cm2(payload: bytes, rows: int, cols: int, gmin: float, grange: float) -> np.ndarray:
+    """ReadCompressedMatrix2 (matrix.go:86-113): uint16 row-major, min + value * (range / 65535)"""
+    v = np.frombuffer(payload, np.uint16, rows * cols).reshape(rows, cols).astype(f32)
+    return (f32(gmin) + v * (f32(grange) / f32(65535.0))).astype(f32)
+
+
+def decode_cm3(payload: bytes, rows: int, cols: int, gmin: float, grange: float) -> np.ndarray:
+    """ReadCompressedMatrix3 (matrix.go:115-142): uint8 row-major, min + value * (range / 255)"""
+    v = np.frombuffer(payload, np.uint8, rows * cols).reshape(rows, cols).astype(f32)
+    return (f32(gmin) + v * (f32(grange) / f32(255.0))).astype(f32)
+
+
+def decode_fm(payload: bytes, rows: int, cols: int) -> np.ndarray:
+    """ReadFullMatrix (matrix.go:144-165): float32 little-endian row-major"""
+    return np.frombuffer(payload, "<f4", rows * cols).reshape(rows, cols).astype(f32)
+
+
 def dropout_uniform(seed: int, rows: np.ndarray, cols: np.ndarray) -> np.ndarray:
     """counter-based uniform in [0,1) per element (row, col): the integer hash the fused dropout epilogue uses
     (kaldi_fp16_b200/csrc/gemm_sm100.cuh::dropout_uniform), restated with uint32 wrap-around arithmetic.  The reference

@@ -203,3 +203,37 @@ def test_dropout_hash_matches_the_library_host_function():
     y = O.dropout_forward(x, keep, 0.5)
     assert np.array_equal(y, np.where(keep, 2 * x, 0))
     assert np.array_equal(O.dropout_backward(np.ones_like(x), keep, 0.5), np.where(keep, 2.0, 0.0).astype(np.float32))
+
+
+def test_compressed_matrix_decode_matches_the_scalar_restatement():
+    """oracle decode_cm / cm2 / cm3 (vectorised) == internal/parser/matrix.go's loops restated element by element"""
+    rng = np.random.default_rng(2)
+    rows, cols, gmin, grange = 7, 5, np.float32(-13.25), np.float32(97.5)
+    hdr = np.sort(rng.integers(0, 65536, size=(cols, 4)).astype(np.uint16), axis=1)
+    data = rng.integers(0, 256, size=(cols, rows)).astype(np.uint8)
+    data[0, :4] = [0, 64, 192, 255]
+    data[1, :4] = [65, 193, 1, 128]
+    got = O.decode_cm(hdr.tobytes() + data.tobytes(), rows, cols, gmin, grange)
+
+    def u16(v):
+        return np.float32(gmin) + (np.float32(grange) * np.float32(1.52590218966964e-05)) * np.float32(v)
+
+    for c in range(cols):
+        p0, p25, p75, p100 = (u16(hdr[c, k]) for k in range(4))
+        for r in range(rows):
+            v = int(data[c, r])
+            if v <= 64:
+                want = p0 + (p25 - p0) * np.float32(v) * np.float32(1.0 / 64.0)
+            elif v <= 192:
+                want = p25 + (p75 - p25) * np.float32(v - 64) * np.float32(1.0 / 128.0)
+            else:
+                want = np.float32(float(p75) + float((p100 - p75) * np.float32(v - 192)) / 63.0)
+            assert got[r, c] == want, (r, c, v)
+    raw16 = rng.integers(0, 65536, size=(rows, cols)).astype(np.uint16)
+    inc = np.float32(grange) / np.float32(65535.0)
+    assert np.array_equal(O.decode_cm2(raw16.tobytes(), rows, cols, gmin, grange), np.float32(gmin) + raw16.astype(np.float32) * inc)
+    raw8 = rng.integers(0, 256, size=(rows, cols)).astype(np.uint8)
+    inc = np.float32(grange) / np.float32(255.0)
+    assert np.array_equal(O.decode_cm3(raw8.tobytes(), rows, cols, gmin, grange), np.float32(gmin) + raw8.astype(np.float32) * inc)
+    x = rng.standard_normal((rows, cols)).astype("<f4")
+    assert np.array_equal(O.decode_fm(x.tobytes(), rows, cols), x)
