@@ -257,11 +257,12 @@ def main():
     from kaldi_fp16_b200 import _lib, cudart, gpu, nnet
     lib = _lib.load()          # raises if the CUDA library is missing: there is no fallback
     dist = torch = None
-    # N > 1: the FP16 gradient bucket is all-reduced (the reference keeps FP16 gradient tensors: backward_ops.go:195-225).
-    # KFP16_DP_OVERLAP=1 (default on for the CNN-TDNN): the step graph is cut once, where the backward pass leaves the
-    # TDNN-F / output layers -- from there on their gradients (97 % of the bucket) are final and reduce on a second stream
-    # while the convolutional front end back-propagates.
-    overlap = world > 1 and os.environ.get("KFP16_DP_OVERLAP", "1" if args.workload == "cnn_tdnn" else "0") != "0"
+    # N > 1: the FP16 gradient bucket is all-reduced (the reference keeps FP16 gradient tensors: backward_ops.go:195-225):
+    # 36 MB instead of the 72 MB FP32 bucket.  KFP16_DP_OVERLAP=1 additionally cuts the step graph once, where the backward
+    # pass leaves the TDNN-F / output layers, and reduces their gradients (97 % of the bucket) on a second stream while the
+    # convolutional front end back-propagates -- measured on 8 B200 it does NOT pay (3.64 against 3.61 ms per step: the
+    # exposed all-reduce is ~0.2 ms and the compute kernels lose SMs to it), so it is off by default.
+    overlap = world > 1 and os.environ.get("KFP16_DP_OVERLAP", "0") != "0"
     nccl_sms = int(os.environ.get("KFP16_NCCL_SMS", "16"))
     if world > 1:
         # NCCL's own banner / debug lines go to stderr so that stdout carries the one JSON line only
