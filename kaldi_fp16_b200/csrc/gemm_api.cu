@@ -155,6 +155,16 @@ __global__ void gemm_simt_fallback(int M, int N, int K, float alpha, const __hal
   }
 }
 
+// shared memory the epilogue of a kernel with epilogue kind `ek` and tile width `bn` reserves (GemmCfg::kEpiBytes)
+static int epi_bytes_for(int ek, int bn) {
+  const uint32_t f = epi_kind_flags(ek);
+  const bool generic = ek == EK_GENERIC;
+  const bool may_r = generic || (f & (EPI_RESID | EPI_BETA)) != 0;
+  const bool vec = generic || (f & (EPI_BIAS | EPI_BN)) != 0;
+  const int ring = ek == EK_SPLITK ? 0 : (may_r ? (bn <= 160 ? 6 : 4) : 4);
+  return ring * kChunkBytes + (vec ? 2 * kVecBytes : 0);
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace kfp16
@@ -347,6 +357,44 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   }
   const int tile_groups = merge ? 1 : (two ? 2 * groups : groups);     // groups that multiply the tile count
 
+  // ---- convolution forward / input gradient: ONE input box per 64-channel chunk shared by all taps (MODE 5) when the
+  // geometry and shared memory allow; otherwise every tap loads its own box (MODE 0 with conv addressing)
+  bool cshare = false;
+  int cs_sl = 0, cs_tbox = 0, cs_dtmin = 0, cs_hqmin = 0, cs_dtspan = 0, cs_planes = 0, cs_plane_par[2] = {0, 0}, cs_plane_bytes = 0, cs_nstages = 0;
+  if (conv == 1 && d->conv.ntaps >= 2 && d->no_share != 1) {
+    const kfp16_conv_addr& c = d->conv;
+    int dtmax = c.dt[0], hqmax = c.hq[0];
+    cs_dtmin = c.dt[0]; cs_hqmin = c.hq[0];
+    bool planes_ok = true;
+    for (int t = 0; t < c.ntaps; ++t) {
+      cs_dtmin = std::min(cs_dtmin, c.dt[t]); dtmax = std::max(dtmax, c.dt[t]);
+      cs_hqmin = std::min(cs_hqmin, c.hq[t]); hqmax = std::max(hqmax, c.hq[t]);
+      int pl = -1;
+      for (int q = 0; q < cs_planes; ++q) if (cs_plane_par[q] == c.par[t]) pl = q;
+      if (pl < 0) { if (cs_planes < 2) cs_plane_par[cs_planes++] = c.par[t]; else planes_ok = false; }
+    }
+    cs_dtspan = dtmax - cs_dtmin;
+    const int hspan = hqmax - cs_hqmin;
+    cs_sl = c.rows_h + hspan;
+    cs_tbox = cs_sl <= kBM ? kBM / cs_sl : 0;
+    const bool kind_ok = b_mn ? (ek == EK_AFFINE || ek == EK_GENERIC) : ek == EK_PLAIN;
+    if (planes_ok && cs_tbox >= 1 && kind_ok && cs_tbox + cs_dtspan <= 256 && cs_sl <= 256) {
+      const int rows_alloc = cs_dtspan * cs_sl + hspan + kBM;           // furthest row a shifted 128-row read touches
+      cs_plane_bytes = (rows_alloc * 128 + 1023) & ~1023;
+      cshare = true;
+    }
+  }
+  if (cshare) {
+    int cg_s = cg;
+    if (d->M <= cs_tbox * d->conv.rows_h || ek == EK_GENERIC) cg_s = 1;
+    // shared-memory budget with the widest tile this N can get: two box buffers per plane + >= 3 weight-tile stages
+    const int bn_w = d->force_bn ? d->force_bn : (d->N <= 64 ? 64 : d->N <= 128 ? 128 : 256);
+    const int b_tile = b_mn ? ((bn_w / cg_s + 63) / 64) * 8192 : (bn_w / cg_s) * 128;
+    const int fixed = 1024 + 512 + epi_bytes_for(ek, bn_w);
+    if ((227 * 1024 - fixed - 2 * cs_planes * cs_plane_bytes) / b_tile < 3) cshare = false;
+    else { p.tile_rows = cs_tbox * d->conv.rows_h; cg = cg_s; }
+  }
+
   const int tile_m = p.tile_rows * cg;
   const int m_tiles = (d->M + tile_m - 1) / tile_m;
   const int kb_total = conv == 2 ? (d->conv.T + conv_tbox - 1) / conv_tbox
@@ -368,6 +416,14 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   int bn = merge ? 160 : (d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, tile_groups, split_k, units));
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) { set_error("kfp16_gemm_ex: unsupported tile width %d", bn); return -1; }
   if (conv == 2 && bn == 160) bn = 256;
+  if (cshare) {
+    if (bn == 160) bn = 256;
+    const int b_tile = b_mn ? ((bn / cg + 63) / 64) * 8192 : (bn / cg) * 128;
+    const int fixed = 1024 + 512 + epi_bytes_for(ek, bn);
+    cs_nstages = (227 * 1024 - fixed - 2 * cs_planes * cs_plane_bytes) / b_tile;
+    if (cs_nstages > 8) cs_nstages = 8;
+    if (cs_nstages < 3) { set_error("internal: shared convolution box does not fit shared memory (bn %d)", bn); return -1; }   // excluded above
+  }
   if (!(flags & EPI_SPLITK) && (bn % 64) != 0 && d->N > bn) {
     // the last 64-wide store chunk of a 160-wide tile would spill into the next tile
     set_error("kfp16_gemm_ex: tile width %d needs N <= %d unless split-K", bn, bn); return -1;
@@ -379,7 +435,21 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if (conv) {
     const kfp16_conv_addr& c = d->conv;
     if (!make_map_conv(&p.tmA, c.x, c.C, c.P, c.H, c.T, c.rows_h, conv_tbox, "A (convolution)")) return -1;
-    if (conv == 1) {
+    if (cshare) {
+      // the box covers every frame and height any tap of the tile reads: (tbox + time span) frames x conv_sl heights
+      if (!make_map_conv(&p.tmA, c.x, c.C, c.P, c.H, c.T, cs_sl, cs_tbox + cs_dtspan, "A (convolution, shared box)")) return -1;
+      if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? 64 : bn / cg, "B")) return -1;
+      p.conv_sl = cs_sl; p.conv_tbox = cs_tbox;
+      p.conv_box_t0 = cs_dtmin; p.conv_box_h0 = cs_hqmin;
+      p.conv_box_bytes = (cs_tbox + cs_dtspan) * cs_sl * 128;
+      p.conv_plane_bytes = cs_plane_bytes; p.conv_planes = cs_planes;
+      p.conv_plane_par[0] = cs_plane_par[0]; p.conv_plane_par[1] = cs_plane_par[1];
+      p.conv_nstages = cs_nstages;
+      for (int t = 0; t < c.ntaps; ++t) {
+        const int pl = (cs_planes == 2 && c.par[t] == cs_plane_par[1]) ? 1 : 0;
+        p.conv_aoff[t] = (uint32_t)(pl * (cs_plane_bytes >> 4) + ((c.dt[t] - cs_dtmin) * cs_sl + (c.hq[t] - cs_hqmin)) * 8);
+      }
+    } else if (conv == 1) {
       if (!make_map_2d(&p.tmB, b_base, B.cols, (long long)B.rows + 2 * B.halo, B.ld, 64, b_mn ? 64 : bn / cg, "B")) return -1;
       p.conv_tx = p.tile_rows * 128 + (b_mn ? b_chunks * 8192 : (bn / cg) * 128);
     } else {
@@ -478,7 +548,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   }
   bool ok = false;
   GemmLaunch L;
-  L.bn = bn; L.a_mn = a_mn; L.b_mn = b_mn; L.ek = ek; L.cg = cg; L.share = conv == 2 ? 4 : (merge ? 3 : (share ? 1 : 0)); L.grid = grid;
+  L.bn = bn; L.a_mn = a_mn; L.b_mn = b_mn; L.ek = ek; L.cg = cg; L.share = cshare ? 5 : (conv == 2 ? 4 : (merge ? 3 : (share ? 1 : 0))); L.grid = grid;
   switch (bn) {
     case 64: ok = launch_gemm_bn<64>(ctx, p, L); break;
     case 128: ok = launch_gemm_bn<128>(ctx, p, L); break;

@@ -16,7 +16,7 @@ struct GemmLaunch {
   int ek;            // EpiKind
   int cg;            // 1 = one CTA per tile, 2 = CTA pair (cta_group::2, 256-row tiles)
   int share;         // kernel MODE: 1 both splice slabs read one A tile; 3 merged groups (spliced weight gradients, BN 160);
-                     // 4 convolution weight gradient
+                     // 4 convolution weight gradient; 5 convolution forward / input gradient with a shared input box
   int grid;          // CTAs (even when cg == 2)
 };
 
@@ -66,6 +66,19 @@ bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
       set_error("internal: merged-group kernel needs MN-major operands, split-K and CTA pairs");
       return false;
     }
+  }
+  if (L.share == 5) {     // convolution forward / input gradient reading one shared input box per channel chunk
+    if constexpr (BN != 160) {
+      if (!L.a_mn && L.b_mn) {
+        if (L.ek == EK_AFFINE) { if (L.cg == 2) KFP16_CASE(false, true, EK_AFFINE, 2, 5); KFP16_CASE(false, true, EK_AFFINE, 1, 5); }
+        if (L.ek == EK_GENERIC && L.cg == 1) KFP16_CASE(false, true, EK_GENERIC, 1, 5);
+      } else if (!L.a_mn && !L.b_mn && L.ek == EK_PLAIN) {
+        if (L.cg == 2) KFP16_CASE(false, false, EK_PLAIN, 2, 5);
+        KFP16_CASE(false, false, EK_PLAIN, 1, 5);
+      }
+    }
+    set_error("internal: no shared-box convolution kernel for this operand / epilogue combination");
+    return false;
   }
   if (L.share == 4) {     // convolution weight gradient (80-row k-blocks of (time, height), 4-D boxes for A)
     if constexpr (BN != 160) {

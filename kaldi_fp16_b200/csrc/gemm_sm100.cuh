@@ -140,6 +140,17 @@ struct GemmParams {
   int conv_tx;                  // bytes one CTA's loads deliver per k-block
   int8_t conv_dt[kMaxTaps], conv_hq[kMaxTaps], conv_par[kMaxTaps];
   int conv_brow[kMaxTaps];      // conv 1: B row offset of tap s (MN-major B: added to the k row; K-major B: to the n row)
+  // conv 1, shared box (MODE 5): per 64-channel chunk ONE box of (tbox + time span) x conv_sl rows per parity plane is loaded
+  // and every tap reads it through a row-shifted descriptor; the tile's accumulator rows are (frame, slot) with conv_sl slots
+  // per frame, of which the first conv_h are real outputs
+  int conv_sl;                  // slots per frame in the accumulator-row index (conv_h + height span of the taps)
+  int conv_box_t0, conv_box_h0; // box origin relative to the tile's first frame / height 0 (= min dt, min hq)
+  int conv_box_bytes;           // bytes of one plane's box
+  int conv_plane_bytes;         // shared-memory bytes reserved per plane (box + read-ahead slack, multiple of 1024)
+  int conv_planes;              // parity planes loaded (1 or 2)
+  int conv_plane_par[2];        // their parity coordinates
+  int conv_nstages;             // B ring depth (2..8)
+  uint32_t conv_aoff[kMaxTaps]; // descriptor offset (16-byte units) of tap s inside an A buffer
   // rows whose index modulo zero_period lies outside [zero_lo, zero_lo + zero_len) are written as zeros with a zero mask
   // (halo rows of the padded minibatch layout: the zero padding the next convolution reads); zero_period == 0: off
   uint32_t zero_period, zero_lo, zero_len;
@@ -187,14 +198,20 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
 //         k-rows through shifted descriptors and accumulate into the two TMEM accumulator stages)
 //       4 convolution weight gradient: MN-major operands in k-blocks of up to 80 (time, height) rows, the A chunks loaded
 //         as 4-D boxes of the layer input shifted per tap
+//       5 convolution forward / input gradient with a SHARED input box: per 64-channel chunk one box of the layer input
+//         (all frames and heights any tap of the tile touches) is loaded once and the taps read it through row-shifted
+//         descriptors, while their weight tiles stream through the ring -- a 3x3 layer moves 27 KB of input per chunk
+//         instead of 9 x 15 KB
 template <int BN, bool A_MN, bool B_MN, int EK, int CG, int MODE>
 struct GemmCfg {
   static constexpr bool SHARE = MODE == 1;
   static constexpr bool kConvW = MODE == 4;
+  static constexpr bool kConvS = MODE == 5;
   static constexpr bool kMerge = MODE == 3;
   static_assert(CG == 1 || CG == 2, "cta_group 1 or 2");
   static_assert(!SHARE || !A_MN, "the shared splice tile is implemented for a K-major A");
-  static_assert(MODE == 0 || MODE == 1 || MODE == 3 || MODE == 4, "kernel mode");
+  static_assert(MODE == 0 || MODE == 1 || MODE == 3 || MODE == 4 || MODE == 5, "kernel mode");
+  static_assert(!kConvS || (!A_MN && EK != EK_SPLITK), "shared convolution box: K-major A, no split-K");
   static_assert(!kConvW || (A_MN && B_MN && EK == EK_SPLITK), "convolution weight gradient: MN-major operands, split-K");
   static_assert(!kMerge || (A_MN && B_MN && EK == EK_SPLITK && CG == 2), "merged groups: MN-major operands, split-K, CTA pairs");
   static constexpr bool kSplitK = EK == EK_SPLITK;
@@ -217,14 +234,14 @@ struct GemmCfg {
   static constexpr int kABytes = SHARE ? (kBM + 8) * kBK * 2 : (A_MN ? 2 * kMnChunkBytes : kBM * kBK * 2);
   static constexpr int kBTileBytes = B_MN ? kBChunks * kMnChunkBytes : kBNLocal * kBK * 2;
   static constexpr int kNumBTiles = SHARE ? 2 : 1;
-  static constexpr int kStageBytes = kABytes + kNumBTiles * kBTileBytes;
+  static constexpr int kStageBytes = kConvS ? kBTileBytes : kABytes + kNumBTiles * kBTileBytes;   // MODE 5: the ring holds weight tiles only
   static constexpr int kEpiBytes = kRing * kChunkBytes + (kUsesVec ? 2 * kVecBytes : 0);   // vectors double-buffered
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
   static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kConvS ? 8 : (kStagesRaw > 8 ? 8 : kStagesRaw);   // MODE 5: barrier slots; the depth is a launch parameter
   static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kConvS ? 227 * 1024 : kStages * kStageBytes + kEpiBytes + 1024 + 512;
   static_assert(kStages >= 2, "tile too large for shared memory");
   static_assert(kStageBytes % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N; epilogue works on 32-column halves");
@@ -277,8 +294,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_ring = smem;                       // operand stages
-  uint8_t* smem_epi = smem_ring + kStages * Cfg::kStageBytes;
+  const int a_region = Cfg::kConvS ? 2 * p.conv_planes * p.conv_plane_bytes : 0;   // MODE 5: two A buffers in front of the ring
+  const int nstages = Cfg::kConvS ? p.conv_nstages : kStages;
+  uint8_t* smem_ring = smem + a_region;            // operand stages
+  uint8_t* smem_epi = smem_ring + nstages * Cfg::kStageBytes;
   uint8_t* smem_vec = smem_epi + kRing * kChunkBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
   uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA          (CG=2: the leader's is used)
@@ -288,7 +307,9 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
   uint64_t* rfull_bar = tempty_bar + 2;       // [8]        residual TMA -> epilogue
   uint64_t* rempty_bar = rfull_bar + 8;       // [8]        output store drained -> residual TMA / next writer
   uint64_t* cfull_bar = rempty_bar + 8;       // [8]        epilogue warps wrote a chunk -> store warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull_bar + 8);
+  uint64_t* afull_bar = cfull_bar + 8;        // [2]        MODE 5: input box landed (CG=2: the leader's is used)
+  uint64_t* aempty_bar = afull_bar + 2;       // [2]        MODE 5: MMAs on the box done (commit multicast)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -319,6 +340,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       mbar_init(&tempty_bar[i], CG * (kEpiThreads / 32));   // one arrive per epilogue warp (of both CTAs)
     }
     for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&rempty_bar[i], 1); mbar_init(&cfull_bar[i], kEpiThreads / 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull_bar[i], CG); mbar_init(&aempty_bar[i], 1); }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -349,6 +371,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
                               : SHARE ? (uint32_t)(p.a_box_bytes + p.kslabs * Cfg::kBTileBytes)
                                       : (uint32_t)(Cfg::kABytes + Cfg::kBTileBytes);
     int tile_i = 0;
+    uint32_t a_cnt = 0;            // MODE 5: input boxes loaded so far (buffer = a_cnt & 1)
     for (int tile = ti.first; tile < ti.last; tile += ti.step, ++tile_i) {
       int n_blk, m_row0, g, ks;
       ti.decode(tile, n_blk, m_row0, g, ks);
@@ -381,6 +404,48 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           cw_tap[c] = m / p.conv_c; cw_c0[c] = m - cw_tap[c] * p.conv_c;
         }
       }
+      if constexpr (Cfg::kConvS) {
+        // shared input box: per 64-channel chunk ONE box per parity plane (every frame / height a tap of this tile reads),
+        // then the taps' weight tiles through the ring
+        const int f0 = m_row0 / p.conv_h;                 // this CTA's first output frame
+        const int nchunks = p.conv_c / kBK;
+        for (int c = 0; c < nchunks; ++c, ++a_cnt) {
+          const uint32_t ab = a_cnt & 1u;
+          mbar_wait(&aempty_bar[ab], ((a_cnt >> 1) & 1u) ^ 1u);
+          if (elect_one()) {
+            const uint32_t fa = CG == 2 ? mapa_u32(smem_u32(&afull_bar[ab]), 0) : 0;
+            const uint32_t tx = (uint32_t)(p.conv_planes * p.conv_box_bytes);
+            if (CG == 2) mbar_arrive_expect_tx_cluster(fa, tx); else mbar_arrive_expect_tx(&afull_bar[ab], tx);
+            for (int pl = 0; pl < p.conv_planes; ++pl) {
+              uint8_t* dst = smem + (ab * p.conv_planes + pl) * p.conv_plane_bytes;
+              if (CG == 2) tma_load_4d_pair(dst, mapA, fa, c * kBK, p.conv_plane_par[pl], p.conv_box_h0, f0 + p.conv_box_t0);
+              else tma_load_4d(dst, mapA, &afull_bar[ab], c * kBK, p.conv_plane_par[pl], p.conv_box_h0, f0 + p.conv_box_t0);
+            }
+          }
+          __syncwarp();
+          for (int tap = 0; tap < p.conv_taps; ++tap) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              uint8_t* sb = smem_ring + stage * Cfg::kStageBytes;
+              const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[stage]), 0) : 0;
+              if (CG == 2) mbar_arrive_expect_tx_cluster(fb, (uint32_t)Cfg::kBTileBytes);
+              else mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)Cfg::kBTileBytes);
+              auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+                if (CG == 2) tma_load_2d_pair(dst, m, fb, c0, c1);
+                else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
+              };
+              if (!B_MN) load(sb, mapB, c * kBK, n_loc + p.conv_brow[tap]);
+              else {
+#pragma unroll
+                for (int cc = 0; cc < Cfg::kBChunks; ++cc)
+                  load(sb + cc * Cfg::kMnChunkBytes, mapB, n_loc + cc * 64, c * kBK + p.conv_brow[tap]);
+              }
+            }
+            __syncwarp();
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else
       for (int kb = kb0; kb < kb1; ++kb) {
         const int slab = SHARE ? 0 : kb / kb_per_slab;
         const int k_in = (kb - slab * kb_per_slab) * kBK;
@@ -450,7 +515,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         }
         __syncwarp();
         if (kb == kb0) dbg_stamp(p, 0, tile_i, 1);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
       dbg_stamp(p, 0, tile_i, 2);
     }
@@ -464,8 +529,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       constexpr uint32_t b_lbo = B_MN ? Cfg::kMnChunkBytes : 16, b_sbo = 1024;
       constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4;   // descriptor units (16 B) per UMMA K=16
       constexpr uint32_t b_kstep = (B_MN ? 2048 : 32) >> 4;
-      const uint64_t adesc0 = make_smem_desc(smem_u32(smem_ring), a_lbo, a_sbo, kLayoutSW128);
-      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_ring) + Cfg::kABytes, b_lbo, b_sbo, kLayoutSW128);
+      // (MODE 5: A descriptors address the input-box buffers in front of the ring, the ring holds weight tiles only)
+      const uint64_t adesc0 = make_smem_desc(smem_u32(Cfg::kConvS ? smem : smem_ring), a_lbo, a_sbo, kLayoutSW128);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_ring) + (Cfg::kConvS ? 0 : Cfg::kABytes), b_lbo, b_sbo, kLayoutSW128);
+      uint32_t a_cnt = 0;
       auto mma = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t accum) {
         if (CG == 2) umma_f16_pair(d_tmem, ad, bd, idesc, accum);
         else umma_f16(d_tmem, ad, bd, idesc, accum);
@@ -492,6 +559,33 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         tc_fence_after();
         dbg_stamp(p, 1, tile_i, 1);
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
+        if constexpr (Cfg::kConvS) {
+          const int nchunks = p.conv_c / kBK;
+          for (int c = 0; c < nchunks; ++c, ++a_cnt) {
+            const uint32_t ab = a_cnt & 1u;
+            mbar_wait(&afull_bar[ab], (a_cnt >> 1) & 1u);
+            tc_fence_after();
+            const uint64_t abuf = adesc0 + (uint64_t)((uint32_t)(ab * p.conv_planes * p.conv_plane_bytes) >> 4);
+            for (int tap = 0; tap < p.conv_taps; ++tap) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              if (elect_one()) {
+                // the tap reads the box from its (frame, height) offset on: a descriptor start moved by whole 128-byte rows
+                const uint64_t ad = abuf + (uint64_t)p.conv_aoff[tap];
+                const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
+                mma(d_tmem, ad, bd, (c > 0 || tap > 0) ? 1u : 0u);
+                mma(d_tmem, ad + a_kstep, bd + b_kstep, 1u);
+                mma(d_tmem, ad + 2 * a_kstep, bd + 2 * b_kstep, 1u);
+                mma(d_tmem, ad + 3 * a_kstep, bd + 3 * b_kstep, 1u);
+                if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+              }
+              __syncwarp();
+              if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) { if (CG == 2) umma_commit_pair(&aempty_bar[ab]); else umma_commit(&aempty_bar[ab]); }
+            __syncwarp();
+          }
+        } else
         for (int kb = kb0; kb < kb1; ++kb) {
           const int slab = SHARE ? 0 : kb / kb_per_slab;
           const int k_in = (kb - slab * kb_per_slab) * kBK;
@@ -536,7 +630,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (kMerge) {
           if (elect_one()) { umma_commit_pair(&tfull_bar[0]); umma_commit_pair(&tfull_bar[1]); }
@@ -653,7 +747,16 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
       ti.decode(tile, n_blk, m_row0, g, ks);
       const int prob = kMerge ? g : g >> 1;      // grouped launches: index into the problem table
       if (kMerge) g = gg;
-      const int row = m_row0 + row_in_tile;
+      // accumulator row -> row of the output tile.  MODE 5: accumulator rows are (frame, slot) with conv_sl slots per frame,
+      // the first conv_h of which are real outputs; they are compacted to (frame, height) in the staging chunk
+      int out_idx = row_in_tile;
+      bool row_ok = row_in_tile < ti.tile_rows;
+      if (Cfg::kConvS) {
+        const int fl = row_in_tile / p.conv_sl, sl = row_in_tile - fl * p.conv_sl;
+        out_idx = fl * p.conv_h + sl;
+        row_ok = sl < p.conv_h && out_idx < ti.tile_rows;
+      }
+      const int row = m_row0 + out_idx;
       const int n0 = n_blk * BN;
       const bool zero_row = p.zero_period != 0 && ((uint32_t)row % p.zero_period - p.zero_lo) >= p.zero_len;
       if (warp == 4) dbg_stamp(p, 2, tile_i, 0);
@@ -720,7 +823,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
 #pragma unroll 1
         for (int c64 = 0; c64 < BN; c64 += 64, ++k) {
           uint8_t* sbuf = smem_epi + buf * kChunkBytes;
-          const uint32_t srow = smem_u32(sbuf) + row_in_tile * 128;
+          const uint32_t srow = smem_u32(sbuf) + out_idx * 128;
           const int c = c64 + hsel * 32;          // first tile column of this thread's 32
           if (use_r) mbar_wait(&rfull_bar[buf], round & 1);                       // residual tile landed (buffer was free)
           else if (round > 0) mbar_wait(&rempty_bar[buf], (round + 1) & 1);      // the store that last used it drained
@@ -737,7 +840,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
 #pragma unroll(kGeneric ? 1 : 4)
             for (int j = 0; j < 4; ++j) {          // 8 columns = one 16-byte smem unit
               const int ct = c + j * 8;            // column inside the tile
-              const uint32_t sptr = srow + (((hsel * 4 + j) ^ (row_in_tile & 7)) << 4);
+              const uint32_t sptr = srow + (((hsel * 4 + j) ^ (out_idx & 7)) << 4);
               uint32_t v8[8];
               if (kGeneric) {
                 tmem_ld_32x32_x8(t_acc + ct, v8);
@@ -836,10 +939,10 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
               ov.x = pack_f16x2(xo[0], xo[1]); ov.y = pack_f16x2(xo[2], xo[3]);
               ov.z = pack_f16x2(xo[4], xo[5]); ov.w = pack_f16x2(xo[6], xo[7]);
               if (zero_row) ov = make_uint4(0u, 0u, 0u, 0u);
-              sts128(sptr, ov);
+              if (!Cfg::kConvS || row_ok) sts128(sptr, ov);
             }
             if (zero_row) maskword = 0u;
-            if ((flags & EPI_MASK) && row < p.M && row_in_tile < ti.tile_rows && n0 + c < p.N)
+            if ((flags & EPI_MASK) && row < p.M && row_ok && n0 + c < p.N)
               p.mask_out[(size_t)row * p.mask_ld + ((n0 + c) >> 5)] = maskword;
           }
           fence_proxy_async_smem();
