@@ -500,7 +500,10 @@ def main():
     # branch included) + weight- and input-gradient GEMMs of the layers on the gradient path
     flops_fwd = lib.kfp16_net_flops_forward(net.ptr)
     flops_bwd = lib.kfp16_net_flops_backward(net.ptr)
-    step_flops = flops_fwd + flops_bwd
+    # ... minus the rows the step does not compute: with the chain objective (frame subsampling 3) the row-wise layers behind
+    # the objective (prefinal-chain, output, prefinal-l's backward) only run on the objective's output frames
+    flops_skipped = lib.kfp16_net_flops_skipped(net.ptr)
+    step_flops = flops_fwd + flops_bwd - flops_skipped
     ms_step = ms / args.steps
     achieved = step_flops / ms_step / 1e9        # TFLOP/s over the WHOLE timed step (GEMMs, epilogues, elementwise, SGD)
     gemm_ms = g_ms.value / max(args.profile_steps, 1)
@@ -524,7 +527,9 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "kfp16::gemm_f16_sm100 (all tile variants; whole step timed)",
                          "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
-                         "how": "algorithmic 2*M*N*K of the step's GEMMs on real rows (forward incl. xent branch + executed backward) / ms_per_step of the timed region",
+                         "how": "algorithmic 2*M*N*K of the GEMMs the step EXECUTES (forward incl. xent branch + backward; rows outside the chain objective's output frames are not computed behind the last splicing layer and not counted) / ms_per_step of the timed region",
+                         "flops_all_rows": flops_fwd + flops_bwd, "flops_skipped_rows": flops_skipped,
+                         "frac_all_rows": (flops_fwd + flops_bwd) / ms_step / 1e9 / burst,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({src}); sustained {sustained}",
                          "frac_of_sustained": achieved / sustained, "frac_of_nominal_2250": achieved / 2250.0,
                          "flops_per_step": step_flops, "flops_forward": flops_fwd, "flops_backward": flops_bwd,

@@ -121,7 +121,9 @@ typedef struct {
     int force_cg;      /* 0 = heuristic; 1 = one CTA per 128-row tile; 2 = CTA pairs (cta_group::2, 256-row tiles) */
     int no_share;      /* 1 = load each splice slab's A tile separately even when one shifted tile could serve both;
                           4 = merge the two row-shifted groups of a split-K weight gradient into one tile pass (what the
-                          grouped launch does; for a single problem only on request) */
+                          grouped launch does; for a single problem only on request);
+                          convolutions (conv.mode 1): 1 = every tap loads its own input box, 5 = one shared box per channel
+                          chunk whatever the tile width (default: shared for N <= 128, where it measured faster) */
     void *debug_clock_buf; /* profiling: device int64 [grid][3 roles][8 tiles][16] clock64 stamps per warp role; NULL = off */
     /* A second split-K problem of the same shape (M, N, K, majors, groups) sharing the launch -- the two weight
      * gradients of one TDNN-F layer: tile groups [groups, 2*groups) compute A2^T * B2 into ws2[].  One launch and half
@@ -224,6 +226,12 @@ int kfp16_zero_halo(kfp16_ctx *ctx, void *X, int ld, int n_seq, int seq_len, int
 /* y = h(x*scale[c] + shift[c]); shift may be NULL (batch-norm forward / backward with folded params) */
 int kfp16_scale_shift(kfp16_ctx *ctx, const void *x, void *y, int rows, int cols, const float *scale,
                       const float *shift);
+/* the same on row-strided views: row r of x / y starts ldx / ldy elements after row r-1 (cols, ldx, ldy multiples of 8) */
+int kfp16_scale_shift_ld(kfp16_ctx *ctx, const void *x, long long ldx, void *y, long long ldy, int rows, int cols,
+                         const float *scale, const float *shift);
+/* X[r, :] = 0 for every row r that is not row0 + k*step (k >= 0): turns a gradient that was only written on the
+ * objective's output frames (frame subsampling, ops_subsample_rows ops.cu:290-304) into a dense one */
+int kfp16_zero_rows_except(kfp16_ctx *ctx, void *X, int ld, int rows, int cols, int row0, int step);
 /* dY = Y on real rows (0 on halo rows); *loss_dev += 0.5*sum(Y^2)   (cmd/sgdtest/main.go:258-267) */
 int kfp16_half_sq_loss(kfp16_ctx *ctx, const void *Y, void *dY, int n_seq, int seq_len, int halo, int cols,
                        float *loss_dev);

@@ -55,6 +55,9 @@ double kfp16_net_flops_forward(const kfp16_net *net); /* 2*M*N*K over the GEMMs,
 /* same for the backward pass as executed: weight-gradient GEMMs of every layer on the gradient path plus the
  * input-gradient GEMMs that feed a layer with parameters (the xent branch gets no gradient, network_backward.go:104-107) */
 double kfp16_net_flops_backward(const kfp16_net *net);
+/* of those, the flops the last training step (or backward pass) did NOT execute because the objective only reads / writes
+ * its subsampled output frames (kfp16_net_set_sparse_output_grad): executed = forward + backward - skipped */
+double kfp16_net_flops_skipped(const kfp16_net *net);
 
 /* ---- parameters: flat buckets.  name = "<layer>.<param>" as SGDOptimizer.RegisterParam keys
  * (optimize.go:52): W, LinearW, AffineW, AffineBias, BigW, BigBias, SmallW, Bias */
@@ -121,6 +124,19 @@ int kfp16_net_loss_chain(kfp16_net *net, const char *layer, kfp16_chain *chain, 
 /* make the chain objective the one the captured step graph (phase 1) computes instead of 0.5*||out||^2; chain = NULL
  * switches back.  Call before kfp16_net_capture. */
 int kfp16_net_set_chain(kfp16_net *net, kfp16_chain *chain, int subsampling, int left_context, float supervision_weight);
+/* Frame subsampling (ops_subsample_rows before the loss, ops.cu:290-304 / chain_loss.go:221-294) makes the output
+ * gradient zero on every row that is not an output frame.  on = 1 (default): the chain objective writes only the output
+ * frames' rows and the row-wise layers behind the output (output, prefinal, linear, batch-norm) back-propagate exactly
+ * those rows -- a third of their GEMM work at factor 3 -- while the first layer that mixes rows (time splice, convolution)
+ * gets the dense gradient.  Same results as on = 0 (clear everything, dense backward); kfp16_net_get_grad returns the
+ * dense form either way.  The training step (kfp16_net_launch / kfp16_net_capture, phase 1) with a chain objective also
+ * restricts the FORWARD pass of the row-wise layers that feed nothing but the objective (prefinal-chain, output) to those
+ * rows -- Kaldi evaluates only the requested output frames the same way; kfp16_net_forward itself always computes every row. */
+int kfp16_net_set_sparse_output_grad(kfp16_net *net, int on);
+/* on = 1 (default): a conv-relu-batchnorm layer with a single consumer gets dZ = mask ? h(dY * bn_scale) : 0 straight from
+ * that consumer's input-gradient GEMM epilogue (ops_batchnorm_backward + ops_relu_backward, backward_wrappers.cu:41-115,
+ * folded into the producing kernel) and only sums its bias gradient; on = 0: one elementwise pass per conv layer. */
+int kfp16_net_set_fuse_conv_backward(kfp16_net *net, int on);
 int kfp16_net_backward(kfp16_net *net);
 /* gradient wrt a layer's output, dense real rows (tests) */
 int kfp16_net_get_grad(kfp16_net *net, const char *layer, uint16_t *host_f16, int rows, int cols);

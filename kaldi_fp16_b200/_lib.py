@@ -141,6 +141,8 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_seq_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int]),
     "kfp16_zero_halo": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "kfp16_scale_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "kfp16_scale_shift_ld": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
+    "kfp16_zero_rows_except": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "kfp16_half_sq_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "kfp16_bn_relu_backward_bias": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "kfp16_bn_relu_backward_bias_fold": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -161,6 +163,7 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_halo": (c_int, [c_void_p]),
     "kfp16_net_flops_forward": (C.c_double, [c_void_p]),
     "kfp16_net_flops_backward": (C.c_double, [c_void_p]),
+    "kfp16_net_flops_skipped": (C.c_double, [c_void_p]),
     "kfp16_net_num_params": (c_int, [c_void_p]),
     "kfp16_net_param_name": (C.c_char_p, [c_void_p, c_int]),
     "kfp16_net_param_shape": (c_int, [c_void_p, c_int, C.POINTER(c_int), C.POINTER(c_int)]),
@@ -222,6 +225,8 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_chain_frames": (c_int, [c_void_p]),
     "kfp16_net_loss_chain": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int, c_float]),
     "kfp16_net_set_chain": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float]),
+    "kfp16_net_set_sparse_output_grad": (c_int, [c_void_p, c_int]),
+    "kfp16_net_set_fuse_conv_backward": (c_int, [c_void_p, c_int]),
     # ---- kaldi_fp16_ops.h
     "ops_cublas_create": (c_void_p, []),
     "ops_cublas_destroy": (None, [c_void_p]),

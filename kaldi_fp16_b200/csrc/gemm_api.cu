@@ -377,8 +377,12 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     const int hspan = hqmax - cs_hqmin;
     cs_sl = c.rows_h + hspan;
     cs_tbox = cs_sl <= kBM ? kBM / cs_sl : 0;
-    const bool kind_ok = b_mn ? (ek == EK_AFFINE || ek == EK_GENERIC) : ek == EK_PLAIN;
-    if (planes_ok && cs_tbox >= 1 && kind_ok && cs_tbox + cs_dtspan <= 256 && cs_sl <= 256) {
+    const bool kind_ok = b_mn ? (ek == EK_AFFINE || ek == EK_GENERIC) : (ek == EK_PLAIN || ek == EK_BN_GRADMASK);
+    // Measured on B200 (profiles/r02_trace_cnn_*): the shared box pays where the per-tap A boxes bound the tile (N <= 128: 61 vs
+    // 79 us cnn2, 73 vs 81 us cnn4, input gradients 55 vs 75 / 66 vs 79 us); 256-wide tiles are MMA-bound and lose the rows the
+    // (frame, slot) index wastes on the height padding (cnn6: 88 vs 85 us, its input gradient 86 vs 79 us)
+    const bool narrow = d->N <= 128 || d->no_share == 5;
+    if (planes_ok && narrow && cs_tbox >= 1 && kind_ok && cs_tbox + cs_dtspan <= 256 && cs_sl <= 256) {
       const int rows_alloc = cs_dtspan * cs_sl + hspan + kBM;           // furthest row a shifted 128-row read touches
       cs_plane_bytes = (rows_alloc * 128 + 1023) & ~1023;
       cshare = true;

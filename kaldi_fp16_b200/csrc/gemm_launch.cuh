@@ -75,6 +75,9 @@ bool launch_gemm_bn(kfp16_ctx* ctx, const GemmParams& p, const GemmLaunch& L) {
       } else if (!L.a_mn && !L.b_mn && L.ek == EK_PLAIN) {
         if (L.cg == 2) KFP16_CASE(false, false, EK_PLAIN, 2, 5);
         KFP16_CASE(false, false, EK_PLAIN, 1, 5);
+      } else if (!L.a_mn && !L.b_mn && L.ek == EK_BN_GRADMASK) {     // input gradient + the producer's batch-norm / ReLU backward
+        if (L.cg == 2) KFP16_CASE(false, false, EK_BN_GRADMASK, 2, 5);
+        KFP16_CASE(false, false, EK_BN_GRADMASK, 1, 5);
       }
     }
     set_error("internal: no shared-box convolution kernel for this operand / epilogue combination");

@@ -836,7 +836,7 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             }
             uint32_t maskword = 0, gm_word = 0xFFFFFFFFu;
             if (flags & EPI_GRADMASK)
-              gm_word = (row < p.M && n0 + c < p.N) ? __ldg(p.mask_in + (size_t)row * p.mask_ld + ((n0 + c) >> 5)) : 0u;
+              gm_word = (row < p.M && row_ok && n0 + c < p.N) ? __ldg(p.mask_in + (size_t)row * p.mask_ld + ((n0 + c) >> 5)) : 0u;
 #pragma unroll(kGeneric ? 1 : 4)
             for (int j = 0; j < 4; ++j) {          // 8 columns = one 16-byte smem unit
               const int ct = c + j * 8;            // column inside the tile

@@ -33,7 +33,9 @@ enum HaloMode { HALO_NONE = 0, HALO_ZERO = 1, HALO_REPL = 2 };
 struct Buf {
   __half* p = nullptr;
   int rows = 0, cols = 0;
+  int ld = 0;                   // elements between rows; 0 = cols (dense).  Only row-subsampled VIEWS set it.
   size_t bytes() const { return (size_t)rows * cols * sizeof(__half); }
+  int LD() const { return ld ? ld : cols; }
 };
 
 struct BNorm {
@@ -46,6 +48,10 @@ struct BNorm {
   float *scale = nullptr, *shift = nullptr, *zero = nullptr;                  // folded; zero = [dim] of 0
   float *scale_bwd = nullptr;   // scale * bwd_mul: the backward pass's factor (dropout folds 1/(1-p) in here)
   float bwd_mul = 1.0f;
+  // conv layers (per-filter batch-norm): scale repeated for every output height, and as many zeros -- the vectors a consumer
+  // that sees the layer output as [frames x heights*filters] passes to its input-gradient epilogue
+  float *scale_tiled = nullptr, *zero_tiled = nullptr;
+  int tiles = 0;
 };
 
 struct Param {
@@ -103,6 +109,17 @@ struct Layer {
   std::vector<int> tap_dt, tap_dh;
   bool conv_implicit = false;   // implicit GEMM over 4-D TMA boxes (no patch matrix); else im2col + GEMM + col2im
   int grads_seen = 0;
+  // rows of `dout` that carry the gradient in the current backward pass: row g_row0 + k*g_sub (k >= 0).  g_sub > 1 after
+  // an objective that is evaluated on subsampled output frames (chain, frame-subsampling-factor 3): the other rows are
+  // zero by definition and are neither written nor read by the row-wise layers behind the output
+  int g_sub = 1, g_row0 = 0;
+  // conv layers: the consumer's input-gradient epilogue already applied this layer's batch-norm scale and ReLU mask, so
+  // `dout` holds dZ (set per backward pass by the consumer, cleared when the pass begins)
+  bool dz_in_dout = false;
+  // training step with a subsampled objective: this layer's output is only read on rows f_row0 + k*f_sub (it is row-wise
+  // and feeds nothing but the objective's output layer through row-wise layers), so the step computes just those rows
+  int f_sub = 1, f_row0 = 0;
+  double fl_fwd = 0, fl_bwd = 0;   // GEMM flops of this layer over all rows (row-wise layer types only)
 };
 
 }  // namespace
@@ -150,6 +167,11 @@ struct kfp16_net {
   kfp16_chain* chain = nullptr;
   int chain_sub = 3, chain_left = 0;
   float chain_weight = 1.0f;
+  bool sparse_out_grad = true;          // kfp16_net_set_sparse_output_grad
+  double flops_fwd_skipped = 0, flops_bwd_skipped = 0;   // of flops_fwd / flops_bwd, not executed by the last training step (rows outside the objective's frames)
+  bool fwd_rows_now = false;            // inside the training step: honour Layer::f_sub in forward_layer
+  bool fuse_conv_bwd = true;            // conv producers get dZ from their consumer's input-gradient epilogue (KFP16_FUSE_CONV_BWD=0: off)
+  int out_g_sub = 1, out_g_row0 = 0;   // gradient rows the last objective call wrote on the output layer (Layer::g_sub)
 };
 
 namespace {
@@ -295,6 +317,20 @@ bool make_bn(kfp16_net* n, BNorm& bn, int dim, float target_rms, bool rms_only) 
   return kfp16_bn_fold(n->ctx, bn.mean, bn.var, rms_only ? nullptr : bn.gamma, rms_only ? nullptr : bn.beta, bn.eps,
                        target_rms, dim, bn.scale, bn.shift) == 0 &&
          kfp16_scale_f32(n->ctx, bn.scale, bn.scale_bwd, dim, bn.bwd_mul) == 0;
+}
+
+// conv layers: (re)build the per-height repetition of the folded batch-norm scale
+bool retile_bn(kfp16_net* n, BNorm& bn, int tiles) {
+  if (tiles <= 0) return true;
+  if (!bn.scale_tiled) {
+    if (!dev_alloc(n, (void**)&bn.scale_tiled, (size_t)bn.dim * tiles * 2 * sizeof(float))) return false;
+    bn.zero_tiled = bn.scale_tiled + (size_t)bn.dim * tiles;
+    bn.tiles = tiles;
+    if (!check_cuda(cudaMemsetAsync(bn.zero_tiled, 0, (size_t)bn.dim * tiles * sizeof(float), n->ctx->stream), "bn tiled zeros")) return false;
+  }
+  for (int t = 0; t < bn.tiles; ++t)
+    if (!check_cuda(cudaMemcpyAsync(bn.scale_tiled + (size_t)t * bn.dim, bn.scale, (size_t)bn.dim * sizeof(float), cudaMemcpyDeviceToDevice, n->ctx->stream), "bn tiled scale")) return false;
+  return true;
 }
 
 // ------------------------------------------------------------------------------ xconfig
@@ -646,8 +682,9 @@ bool build_plan(kfp16_net* n) {
         break;
       }
       case L_LINEAR:
-        n->flops_fwd += 2.0 * M * l.in_dim * l.out_dim;
-        if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.out_dim;
+        l.fl_fwd = 2.0 * M * l.in_dim * l.out_dim;
+        if (train && l.needs_grad) l.fl_bwd = (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.out_dim;
+        n->flops_fwd += l.fl_fwd; n->flops_bwd += l.fl_bwd;
         break;
       case L_BATCHNORM: {
         const float rms = (float)kv_float(l, "target-rms", 1.0);
@@ -687,19 +724,22 @@ bool build_plan(kfp16_net* n) {
           if (!alloc_buf(n, l.dbig, rows2, l.big_dim)) return false;
           if (!alloc_buf(n, l.dys, rows2, l.small_dim)) return false;
         }
-        n->flops_fwd += 2.0 * M * l.in_dim * l.big_dim + 2.0 * M * l.big_dim * l.small_dim;
-        if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.big_dim + 2 * 2.0 * M * l.big_dim * l.small_dim;
+        l.fl_fwd = 2.0 * M * l.in_dim * l.big_dim + 2.0 * M * l.big_dim * l.small_dim;
+        if (train && l.needs_grad) l.fl_bwd = (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.big_dim + 2 * 2.0 * M * l.big_dim * l.small_dim;
+        n->flops_fwd += l.fl_fwd; n->flops_bwd += l.fl_bwd;
         break;
       }
       case L_OUTPUT:
         if (!check_tma_dim(l, l.in_dim, "input dim")) return false;
-        n->flops_fwd += 2.0 * M * l.in_dim * l.out_dim;
-        if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.out_dim;
+        l.fl_fwd = 2.0 * M * l.in_dim * l.out_dim;
+        if (train && l.needs_grad) l.fl_bwd = (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.out_dim;
+        n->flops_fwd += l.fl_fwd; n->flops_bwd += l.fl_bwd;
         break;
       case L_CONV: {
         if (l.per_seq) { set_error("conv layer %s on a per-sequence input", l.name.c_str()); return false; }
         if (!check_tma_dim(l, l.fout, "num-filters-out")) return false;
         if (!make_bn(n, l.bn, l.fout, 1.0f, false)) return false;   // per filter
+        if (!retile_bn(n, l.bn, l.hout)) return false;
         const size_t mrows = (size_t)n->Tp * l.hout;
         l.mask_ld = (l.fout + 31) / 32;
         if (!dev_alloc(n, (void**)&l.mask, mrows * l.mask_ld * 4)) return false;
@@ -740,6 +780,17 @@ kfp16_gemm_desc mk_desc(int M, int N, int K) {
 }
 void set_A(kfp16_gemm_desc& d, const void* p, int rows, int cols) { d.A.ptr = p; d.A.rows = rows; d.A.cols = cols; d.A.ld = cols; d.A.halo = 0; }
 void set_B(kfp16_gemm_desc& d, const void* p, int rows, int cols) { d.B.ptr = p; d.B.rows = rows; d.B.cols = cols; d.B.ld = cols; d.B.halo = 0; }
+void set_A(kfp16_gemm_desc& d, const Buf& b) { set_A(d, b.p, b.rows, b.cols); d.A.ld = b.LD(); }
+// rows row0 + k*sub of a [rows x cols] buffer as a matrix of its own (sub == 1: the buffer itself)
+Buf row_view(const Buf& b, int row0, int sub) {
+  if (sub <= 1) return b;
+  Buf v;
+  v.p = b.p + (size_t)row0 * b.LD();
+  v.rows = (b.rows - 1 - row0) / sub + 1;
+  v.cols = b.cols;
+  v.ld = b.LD() * sub;
+  return v;
+}
 
 // tap list of a conv layer as implicit-GEMM addressing of its input x[Tp][hin][fin] (height subsampling 2 = parity planes)
 void conv_fwd_addr(const kfp16_net* n, const Layer& l, const void* x, int mode, kfp16_conv_addr& c) {
@@ -792,12 +843,14 @@ int wgrad(kfp16_net* n, const Buf& X, const Buf& dY, int param, int groups, int 
   if (transposed) {
     set_A(d, dY.p, dY.rows, dY.cols);
     set_B(d, X.p, X.rows, X.cols);
+    d.A.ld = dY.LD(); d.B.ld = X.LD();
     d.b_row_off[0][0] = off0;
     d.b_row_off[1][0] = off1;
     d.ws_transposed = 1;
   } else {
     set_A(d, X.p, X.rows, X.cols);
     set_B(d, dY.p, dY.rows, dY.cols);
+    d.A.ld = X.LD(); d.B.ld = dY.LD();
     d.a_row_off[0][0] = off0;
     d.a_row_off[1][0] = off1;
   }
@@ -818,8 +871,8 @@ static bool wgrad_fill(kfp16_net* n, const WgradArgs& a, kfp16_mat& A, kfp16_mat
   M = tr ? out : in; N = tr ? in : out;
   const Buf& am = tr ? *a.dY : *a.X;
   const Buf& bm = tr ? *a.X : *a.dY;
-  A.ptr = am.p; A.rows = am.rows; A.cols = am.cols; A.ld = am.cols; A.halo = 0;
-  B.ptr = bm.p; B.rows = bm.rows; B.cols = bm.cols; B.ld = bm.cols; B.halo = 0;
+  A.ptr = am.p; A.rows = am.rows; A.cols = am.cols; A.ld = am.LD(); A.halo = 0;
+  B.ptr = bm.p; B.rows = bm.rows; B.cols = bm.cols; B.ld = bm.LD(); B.halo = 0;
   a_off[0] = tr ? 0 : a.off0; a_off[1] = tr ? 0 : a.off1;
   b_off[0] = tr ? a.off0 : 0; b_off[1] = tr ? a.off1 : 0;
   ws[0] = G32(n, a.param); ws[1] = G32(n, a.param) + (size_t)in * out;
@@ -896,15 +949,30 @@ int flush_wgrads(kfp16_net* n) {
 }
 
 // route a freshly computed input-gradient into the producer(s) of layer l
-int deliver_dx(kfp16_net* n, Layer& l, const Buf& dx) {
-  // dx: [rows x in_dim]; single producer: dx IS producer.dout when it was written in place
+// make a gradient buffer that only carries rows row0 + k*sub dense: the other rows become zeros
+int densify_rows(kfp16_net* n, const Buf& b, int row0, int sub) {
+  return sub > 1 ? kfp16_zero_rows_except(n->ctx, b.p, b.LD(), b.rows, b.cols, row0, sub) : 0;
+}
+
+int deliver_dx(kfp16_net* n, Layer& l, const Buf& dx, int sub = 1, int row0 = 0) {
+  // dx: [rows x in_dim]; single producer: dx IS producer.dout when it was written in place.
+  // sub > 1: only rows row0 + k*sub of dx were written (the gradient is zero elsewhere)
   int col = 0;
+  bool dx_dense = sub <= 1;
   for (int src : l.in) {
     Layer& s = n->layers[src];
     if (!s.needs_grad || !s.dout.p) { col += s.out_dim; continue; }
     const bool first = s.grads_seen == 0;
     s.grads_seen++;
-    if (l.in.size() == 1 && dx.p == s.dout.p) { col += s.out_dim; continue; }   // written in place
+    if (l.in.size() == 1 && dx.p == s.dout.p) {   // written in place: the producer inherits the row pattern
+      s.g_sub = sub; s.g_row0 = row0;
+      col += s.out_dim; continue;
+    }
+    if (!dx_dense) { if (densify_rows(n, dx, row0, sub)) return -1; dx_dense = true; }
+    if (!first && s.g_sub > 1) {                  // an earlier consumer left a row-subsampled gradient there
+      if (densify_rows(n, s.dout, s.g_row0, s.g_sub)) return -1;
+      s.g_sub = 1; s.g_row0 = 0;
+    }
     if (s.per_seq && !l.per_seq) {
       // adjoint of the per-sequence broadcast
       if (first) {
@@ -961,6 +1029,10 @@ int forward_layer(kfp16_net* n, Layer& l) {
     }
   }
   const Buf& X = layer_input(n, l);
+  // rows this layer has to produce (see Layer::f_sub): every buffer below is addressed through the same row view
+  const int fsub = (n->fwd_rows_now && l.f_sub > 1 && l.in.size() == 1 && !l.per_seq) ? l.f_sub : 1, fr0 = fsub > 1 ? l.f_row0 : 0;
+  const Buf Xv = row_view(X, fr0, fsub), Yv = row_view(l.out, fr0, fsub);
+  const int vrows = fsub > 1 ? Yv.rows : rows;
   switch (l.type) {
     case L_IDCT: {   // Y = h(X*M)  forward.go:317-330
       kfp16_gemm_desc d = mk_desc(rows, l.out_dim, l.in_dim);
@@ -971,10 +1043,10 @@ int forward_layer(kfp16_net* n, Layer& l) {
       break;
     }
     case L_LINEAR: {   // Y = h(X*W)  forward.go:333-346
-      kfp16_gemm_desc d = mk_desc(rows, l.out_dim, X.cols);   // X.cols >= in_dim: zero-padded storage width
-      set_A(d, X.p, rows, X.cols);
+      kfp16_gemm_desc d = mk_desc(vrows, l.out_dim, X.cols);   // X.cols >= in_dim: zero-padded storage width
+      set_A(d, Xv);
       set_B(d, W16(n, l.pW), l.in_dim, l.out_dim);
-      d.D[0] = l.out.p; d.ldd = l.out_dim;
+      d.D[0] = Yv.p; d.ldd = Yv.LD();
       if (kfp16_gemm_ex(ctx, &d)) return -1;
       break;
     }
@@ -1023,19 +1095,20 @@ int forward_layer(kfp16_net* n, Layer& l) {
       break;
     }
     case L_PREFINAL: {   // forward.go:912-968: affine(big) -> ReLU -> BN1 -> linear(small) -> BN2
-      kfp16_gemm_desc d = mk_desc(rows, l.big_dim, l.in_dim);
-      set_A(d, X.p, rows, l.in_dim);
+      const Buf bigv = row_view(l.big, fr0, fsub);
+      kfp16_gemm_desc d = mk_desc(vrows, l.big_dim, l.in_dim);
+      set_A(d, Xv);
       set_B(d, W16(n, l.pBig), l.in_dim, l.big_dim);
-      d.D[0] = l.big.p; d.ldd = l.big_dim;
+      d.D[0] = bigv.p; d.ldd = bigv.LD();
       d.flags = KFP16_EPI_BIAS | KFP16_EPI_RELU | KFP16_EPI_BN | KFP16_EPI_MASK | rr;
       d.bias = W16(n, l.pBigB);
       d.bn_scale = l.bn.scale; d.bn_shift = l.bn.shift;
-      d.mask_out = l.mask; d.mask_ld = l.mask_ld;
+      d.mask_out = l.mask + (size_t)fr0 * l.mask_ld; d.mask_ld = l.mask_ld * fsub;
       if (kfp16_gemm_ex(ctx, &d)) return -1;
-      kfp16_gemm_desc e = mk_desc(rows, l.small_dim, l.big_dim);
-      set_A(e, l.big.p, rows, l.big_dim);
+      kfp16_gemm_desc e = mk_desc(vrows, l.small_dim, l.big_dim);
+      set_A(e, bigv);
       set_B(e, W16(n, l.pSmall), l.big_dim, l.small_dim);
-      e.D[0] = l.out.p; e.ldd = l.small_dim;
+      e.D[0] = Yv.p; e.ldd = Yv.LD();
       e.flags = KFP16_EPI_BN | rr;
       e.bn_scale = l.bn2.scale; e.bn_shift = l.bn2.shift;
       if (kfp16_gemm_ex(ctx, &e)) return -1;
@@ -1066,10 +1139,11 @@ int forward_layer(kfp16_net* n, Layer& l) {
       break;
     }
     case L_OUTPUT: {     // forward.go:971-1001
-      kfp16_gemm_desc d = mk_desc(rows, l.out_dim, l.in_dim);
-      set_A(d, X.p, rows, l.in_dim);
+      const bool view = fsub > 1 && !l.log_softmax;
+      kfp16_gemm_desc d = mk_desc(view ? vrows : rows, l.out_dim, l.in_dim);
+      if (view) set_A(d, Xv); else set_A(d, X.p, rows, l.in_dim);
       set_B(d, W16(n, l.pW), l.in_dim, l.out_dim);
-      d.D[0] = l.out.p; d.ldd = l.out_dim;
+      d.D[0] = view ? Yv.p : l.out.p; d.ldd = view ? Yv.LD() : l.out_dim;
       d.flags = KFP16_EPI_BIAS | rr;
       d.bias = W16(n, l.pB);
       if (kfp16_gemm_ex(ctx, &d)) return -1;
@@ -1084,10 +1158,43 @@ int forward_layer(kfp16_net* n, Layer& l) {
 }
 
 // ------------------------------------------------------------------------------ backward
+// When layer l writes its input gradient straight into the gradient buffer of a conv-relu-batchnorm producer that nobody
+// else feeds, the GEMM's epilogue applies that producer's batch-norm scale and ReLU mask on the way out (EK_BN_GRADMASK):
+// the producer finds dZ in its `dout` and skips its own elementwise pass over the (frames x heights x filters) tensor.
+// ncols = columns of the GEMM output: the producer's filter count (conv consumer) or heights*filters (a dense consumer).
+// row_mul / row_add: GEMM output row r is row r*row_mul + row_add of the producer's output (height-subsampled consumers).
+bool fuse_conv_dz(kfp16_net* n, Layer& l, const Buf& dx, kfp16_gemm_desc& d, int ncols, int row_mul = 1, int row_add = 0) {
+  if (!n->fuse_conv_bwd || l.in.size() != 1) return false;
+  Layer& s = n->layers[l.in[0]];
+  if (s.type != L_CONV || !s.needs_grad || s.n_grad_consumers != 1 || dx.p != s.dout.p || !s.mask) return false;
+  const float *scale, *zero;
+  if (ncols == s.fout) { scale = s.bn.scale; zero = s.bn.zero; }
+  else if (ncols == s.fout * s.bn.tiles && s.bn.scale_tiled) { scale = s.bn.scale_tiled; zero = s.bn.zero_tiled; }
+  else return false;
+  d.flags |= KFP16_EPI_BN | KFP16_EPI_GRADMASK | (n->opts.ref_round ? KFP16_EPI_REF_ROUND : 0);
+  d.bn_scale = scale; d.bn_shift = zero;
+  // mask words per GEMM row: the producer's mask is [frames*heights x fout/32]; a dense consumer sees heights*fout/32 per frame
+  const int words = (ncols / s.fout) * s.mask_ld;
+  d.mask_in = s.mask + (size_t)row_add * words; d.mask_ld = words * row_mul;
+  return true;
+}
+
 int backward_layer(kfp16_net* n, Layer& l) {
   kfp16_ctx* ctx = n->ctx;
   if (!l.needs_grad || l.type == L_INPUT) return 0;
-  const int rows = l.per_seq ? n->opts.n_seq : n->Tp;
+  const int rows_all = l.per_seq ? n->opts.n_seq : n->Tp;
+  // rows of dout that carry the gradient (Layer::g_sub): layers that treat every row on its own work on exactly those
+  // rows -- a third of the GEMM work behind a chain objective with frame-subsampling-factor 3; every other layer first
+  // gets the dense form (zeros on the rows the objective never wrote)
+  int sub = l.g_sub, r0 = l.g_row0;
+  const bool rowwise = !l.per_seq && l.halo_mode == HALO_NONE && l.in.size() == 1 && !n->layers[l.in[0]].per_seq &&
+                       (l.type == L_OUTPUT || l.type == L_PREFINAL || l.type == L_LINEAR || l.type == L_IDCT || l.type == L_BATCHNORM);
+  if (sub > 1 && !rowwise) {
+    if (densify_rows(n, l.dout, r0, sub)) return -1;
+    sub = 1; r0 = 0; l.g_sub = 1; l.g_row0 = 0;
+  }
+  const int rows = sub > 1 ? (rows_all - 1 - r0) / sub + 1 : rows_all;
+  if (sub > 1) n->flops_bwd_skipped += l.fl_bwd * (1.0 - (double)rows / rows_all);
   // adjoint of the halo fix-up applied to this layer's output in the forward pass
   if (!l.per_seq && n->halo > 0) {
     if (l.halo_mode == HALO_REPL && kfp16_fold_edges(ctx, l.dout.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, l.out_dim, n->halo)) return -1;
@@ -1096,23 +1203,26 @@ int backward_layer(kfp16_net* n, Layer& l) {
   }
   const Buf& X = layer_input(n, l);
   Buf dx = l.wants_dx ? dx_target(n, l) : Buf();
+  // the same rows of every buffer the row-wise layers touch (sub == 1: the buffers themselves)
+  const Buf Xv = row_view(X, r0, sub), dYv = row_view(l.dout, r0, sub), dxv = l.wants_dx ? row_view(dx, r0, sub) : Buf();
   switch (l.type) {
     case L_IDCT:
     case L_LINEAR: {
       const __half* W = l.type == L_IDCT ? l.idct_mat : W16(n, l.pW);
       if (l.wants_dx) {   // dX = dY * W^T   (backward_ops.go:162-192)
         kfp16_gemm_desc d = mk_desc(rows, l.in_dim, l.out_dim);
-        set_A(d, l.dout.p, rows, l.out_dim);
+        set_A(d, dYv);
         d.b_major = KFP16_K_MAJOR;
         set_B(d, W, l.in_dim, l.out_dim);
-        d.D[0] = dx.p; d.ldd = l.in_dim;
+        d.D[0] = dxv.p; d.ldd = dxv.LD();
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (l.type == L_LINEAR && wgrad(n, X, l.dout, l.pW, 1, 0, 0)) return -1;   // backward_ops.go:195-225
+      if (l.type == L_LINEAR && wgrad(n, Xv, dYv, l.pW, 1, 0, 0)) return -1;   // backward_ops.go:195-225
       break;
     }
     case L_BATCHNORM:   // dX = dY * gamma/sqrt(var+eps)  (backward_wrappers.cu:104-115)
-      if (l.wants_dx && kfp16_scale_shift(ctx, l.dout.p, dx.p, rows, l.out_dim, l.bn.scale, nullptr)) return -1;
+      if (l.wants_dx && sub > 1 && kfp16_scale_shift_ld(ctx, dYv.p, dYv.LD(), dxv.p, dxv.LD(), rows, l.out_dim, l.bn.scale, nullptr)) return -1;
+      if (l.wants_dx && sub <= 1 && kfp16_scale_shift(ctx, l.dout.p, dx.p, rows, l.out_dim, l.bn.scale, nullptr)) return -1;
       break;
     case L_SPECAUG:
       if (l.wants_dx && !check_cuda(cudaMemcpyAsync(dx.p, l.dout.p, l.dout.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "spec-augment grad")) return -1;
@@ -1156,35 +1266,37 @@ int backward_layer(kfp16_net* n, Layer& l) {
         if (sp == 2) { d.a_row_off[0][0] = s; d.a_row_off[0][1] = 0; d.b_row_off[0][0] = 0; d.b_row_off[0][1] = l.in_dim; }
         d.D[0] = dx.p; d.ldd = l.in_dim;
         if (l.use_bypass) { d.flags |= KFP16_EPI_RESID; d.R[0] = l.dout.p; d.ldr = l.out_dim; d.res_scale = l.bypass; }
+        else if (sp == 1 && fuse_conv_dz(n, l, dx, d, l.in_dim)) n->layers[l.in[0]].dz_in_dout = true;   // first TDNN-F layer behind the CNN
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
       break;
     }
     case L_PREFINAL: {
+      const Buf dysv = row_view(l.dys, r0, sub), dbigv = row_view(l.dbig, r0, sub), bigv = row_view(l.big, r0, sub);
       // dYs = dY * bn2_scale
-      if (kfp16_scale_shift(ctx, l.dout.p, l.dys.p, rows, l.small_dim, l.bn2.scale, nullptr)) return -1;
+      if (kfp16_scale_shift_ld(ctx, dYv.p, dYv.LD(), dysv.p, dysv.LD(), rows, l.small_dim, l.bn2.scale, nullptr)) return -1;
       {  // dG = mask ? h((dYs * Wsmall^T) * bn1_scale) : 0
         kfp16_gemm_desc d = mk_desc(rows, l.big_dim, l.small_dim);
-        set_A(d, l.dys.p, rows, l.small_dim);
+        set_A(d, dysv);
         d.b_major = KFP16_K_MAJOR;
         set_B(d, W16(n, l.pSmall), l.big_dim, l.small_dim);
-        d.D[0] = l.dbig.p; d.ldd = l.big_dim;
+        d.D[0] = dbigv.p; d.ldd = dbigv.LD();
         d.flags = KFP16_EPI_BN | KFP16_EPI_GRADMASK | (n->opts.ref_round ? KFP16_EPI_REF_ROUND : 0);
         d.bn_scale = l.bn.scale; d.bn_shift = l.bn.zero;
-        d.mask_in = l.mask; d.mask_ld = l.mask_ld;
+        d.mask_in = l.mask + (size_t)(sub > 1 ? r0 : 0) * l.mask_ld; d.mask_ld = l.mask_ld * sub;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (wgrad(n, l.big, l.dys, l.pSmall, 1, 0, 0)) return -1;
-      if (kfp16_colsum_accum(ctx, l.dbig.p, l.big_dim, rows, l.big_dim, G32(n, l.pBigB))) return -1;
+      if (wgrad(n, bigv, dysv, l.pSmall, 1, 0, 0)) return -1;
+      if (kfp16_colsum_accum(ctx, dbigv.p, dbigv.LD(), rows, l.big_dim, G32(n, l.pBigB))) return -1;
       if (l.wants_dx) {
         kfp16_gemm_desc d = mk_desc(rows, l.in_dim, l.big_dim);
-        set_A(d, l.dbig.p, rows, l.big_dim);
+        set_A(d, dbigv);
         d.b_major = KFP16_K_MAJOR;
         set_B(d, W16(n, l.pBig), l.in_dim, l.big_dim);
-        d.D[0] = dx.p; d.ldd = l.in_dim;
+        d.D[0] = dxv.p; d.ldd = dxv.LD();
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (wgrad(n, X, l.dbig, l.pBig, 1, 0, 0)) return -1;
+      if (wgrad(n, Xv, dbigv, l.pBig, 1, 0, 0)) return -1;
       break;
     }
     case L_CONV: {     // transpose of the forward (the reference treats the conv as a dense affine: quirk Q2)
@@ -1192,13 +1304,17 @@ int backward_layer(kfp16_net* n, Layer& l) {
       // gradients on halo rows are not part of the minibatch: the forward epilogue left a zero ReLU mask on them, so dZ is
       // zero there and neither the weight gradient (a sum over ALL padded rows) nor the input gradient of neighbouring
       // real frames sees them
-      if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.fout, l.bn.scale, l.mask, l.mask_ld, n->conv_dz, l.fout, mrows, l.fout, G32(n, l.pB))) return -1;
+      __half* dz = n->conv_dz;
+      if (l.dz_in_dout) {   // the consumer's epilogue already produced dZ (fuse_conv_dz): only the bias gradient is left
+        dz = l.dout.p;
+        if (kfp16_colsum_accum(ctx, dz, l.fout, mrows, l.fout, G32(n, l.pB))) return -1;
+      } else if (kfp16_bn_relu_backward_bias(ctx, l.dout.p, l.fout, l.bn.scale, l.mask, l.mask_ld, dz, l.fout, mrows, l.fout, G32(n, l.pB))) return -1;
       if (l.conv_implicit) {
         {  // dW[(tap, f), fo] = sum over (t, h) of X[t+dt, h*sub+dh, f] * dZ[(t, h), fo]
           kfp16_gemm_desc d = mk_desc(l.convK, l.fout, mrows);
           d.a_major = KFP16_MN_MAJOR;
           conv_fwd_addr(n, l, X.p, 2, d.conv);
-          set_B(d, n->conv_dz, mrows, l.fout);
+          set_B(d, dz, mrows, l.fout);
           d.split_k = pick_split_k(n, l.convK, l.fout, 1, mrows);
           d.ws[0] = G32(n, l.pW); d.ws_ld = l.fout;
           if (kfp16_gemm_ex(ctx, &d)) return -1;
@@ -1207,10 +1323,11 @@ int backward_layer(kfp16_net* n, Layer& l) {
           // dX[t, hi, f] = sum over taps of dZ[t-dt, (hi-dh)/sub, :] * W[(tap, f), :]^T: again a convolution, of dZ with the
           // mirrored taps; with height subsampling 2 the even and the odd input heights take different tap subsets and are
           // written as two interleaved row sets of dX
+          bool fused_dz = false;
           for (int par = 0; par < l.hsub; ++par) {
             kfp16_gemm_desc d = mk_desc(rows * l.hout, l.fin, 0);
             kfp16_conv_addr& c = d.conv;
-            c.mode = 1; c.x = n->conv_dz;
+            c.mode = 1; c.x = dz;
             c.T = rows; c.H = l.hout; c.P = 1; c.C = l.fout; c.rows_h = l.hout;
             for (size_t t = 0; t < l.tap_dt.size(); ++t) {
               const int dh = l.tap_dh[t];
@@ -1231,8 +1348,11 @@ int backward_layer(kfp16_net* n, Layer& l) {
             d.b_major = KFP16_K_MAJOR;
             set_B(d, W16(n, l.pW), l.convK, l.fout);
             d.D[0] = dst; d.ldd = ldd;
+            // (rows of this launch are the producer's rows (t, hsub*ho + par): every hsub-th mask row from row `par` on)
+            if (fuse_conv_dz(n, l, dx, d, l.fin, l.hsub, par)) fused_dz = true;
             if (kfp16_gemm_ex(ctx, &d)) return -1;
           }
+          if (fused_dz) n->layers[l.in[0]].dz_in_dout = true;
         }
         break;
       }
@@ -1241,14 +1361,14 @@ int backward_layer(kfp16_net* n, Layer& l) {
         kfp16_gemm_desc d = mk_desc(l.convK, l.fout, mrows);
         d.a_major = KFP16_MN_MAJOR;
         set_A(d, l.convP, mrows, l.convKp);
-        set_B(d, n->conv_dz, mrows, l.fout);
+        set_B(d, dz, mrows, l.fout);
         d.split_k = pick_split_k(n, l.convK, l.fout, 1, mrows);
         d.ws[0] = G32(n, l.pW); d.ws_ld = l.fout;
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
       if (l.wants_dx) {   // dP = dZ W^T, then the adjoint of the patch gather
         kfp16_gemm_desc d = mk_desc(mrows, l.convKp, l.fout);
-        set_A(d, n->conv_dz, mrows, l.fout);
+        set_A(d, dz, mrows, l.fout);
         d.b_major = KFP16_K_MAJOR;
         set_B(d, W16(n, l.pW), l.convK, l.fout);
         d.D[0] = n->conv_dP; d.ldd = l.convKp;
@@ -1261,27 +1381,62 @@ int backward_layer(kfp16_net* n, Layer& l) {
     case L_OUTPUT: {   // log-softmax Jacobian is not applied (network_backward.go:243-244)
       if (l.wants_dx) {
         kfp16_gemm_desc d = mk_desc(rows, l.in_dim, l.out_dim);
-        set_A(d, l.dout.p, rows, l.out_dim);
+        set_A(d, dYv);
         d.b_major = KFP16_K_MAJOR;
         set_B(d, W16(n, l.pW), l.in_dim, l.out_dim);
-        d.D[0] = dx.p; d.ldd = l.in_dim;
+        d.D[0] = dxv.p; d.ldd = dxv.LD();
         if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
-      if (wgrad(n, X, l.dout, l.pW, 1, 0, 0)) return -1;
-      if (kfp16_colsum_accum(ctx, l.dout.p, l.out_dim, rows, l.out_dim, G32(n, l.pB))) return -1;
+      if (wgrad(n, Xv, dYv, l.pW, 1, 0, 0)) return -1;
+      if (kfp16_colsum_accum(ctx, dYv.p, dYv.LD(), rows, l.out_dim, G32(n, l.pB))) return -1;
       break;
     }
     default: break;
   }
-  if (l.wants_dx && deliver_dx(n, l, dx)) return -1;
+  if (l.wants_dx && deliver_dx(n, l, dx, sub, r0)) return -1;
   return 0;
+}
+
+// can the chain objective's gradient be handled as the rows row0 + k*sub of the padded matrix (see kfp16_net_loss_chain)?
+bool chain_by_rows(const kfp16_net* n, int layer, int sub, int frames) {
+  const Layer& l = n->layers[layer];
+  return layer == n->out_layer && n->sparse_out_grad && sub > 1 && n->blk % sub == 0 && n->blk / sub - frames <= 4 && (l.out_dim % 8) == 0;
+}
+
+// Layer::f_sub for the training step: walk back from the objective's output layer through row-wise layers whose every
+// consumer is already restricted to the objective's rows
+void plan_forward_rows(kfp16_net* n) {
+  for (auto& l : n->layers) { l.f_sub = 1; l.f_row0 = 0; }
+  n->flops_fwd_skipped = 0;
+  if (!n->chain || n->out_layer < 0 || !chain_by_rows(n, n->out_layer, n->chain_sub, kfp16_chain_frames(n->chain))) return;
+  const int L = (int)n->layers.size();
+  std::vector<int> consumers(L, 0), restricted(L, 0);
+  for (const auto& l : n->layers) for (int src : l.in) consumers[src]++;
+  std::vector<bool> mark(L, false);
+  mark[n->out_layer] = true;
+  for (int i = n->out_layer; i >= 0; --i) {
+    Layer& l = n->layers[i];
+    if (!mark[i]) continue;
+    const bool rowwise = !l.per_seq && l.halo_mode == HALO_NONE && l.in.size() == 1 && !n->layers[l.in[0]].per_seq &&
+                         ((l.type == L_OUTPUT && !l.log_softmax) || l.type == L_PREFINAL || l.type == L_LINEAR);
+    if (!rowwise) continue;
+    l.f_sub = n->chain_sub; l.f_row0 = n->halo + n->chain_left;
+    n->flops_fwd_skipped += l.fl_fwd * (1.0 - (double)((n->Tp - 1 - l.f_row0) / l.f_sub + 1) / n->Tp);
+    const int src = l.in[0];
+    if (++restricted[src] == consumers[src]) mark[src] = true;
+  }
 }
 
 int run_phases(kfp16_net* n, int phases) {
   if (phases & 1) {
     if (kfp16_bump_counter(n->ctx, n->seed_dev)) return -1;     // a new dropout mask per step, graph replays included
     if (kfp16_net_zero_grads(n)) return -1;
-    if (kfp16_net_forward(n)) return -1;
+    // a chain objective on subsampled output frames: the row-wise layers that feed only the objective compute just its rows
+    plan_forward_rows(n);
+    n->fwd_rows_now = true;
+    const int frc = kfp16_net_forward(n);
+    n->fwd_rows_now = false;
+    if (frc) return -1;
     if (n->chain ? kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight) : kfp16_net_loss_half_sq(n, "")) return -1;
     if (kfp16_net_backward(n)) return -1;
   }
@@ -1348,6 +1503,7 @@ int kfp16_net_padded_rows(const kfp16_net* n) { return n ? n->Tp : 0; }
 int kfp16_net_halo(const kfp16_net* n) { return n ? n->halo : 0; }
 double kfp16_net_flops_forward(const kfp16_net* n) { return n ? n->flops_fwd : 0.0; }
 double kfp16_net_flops_backward(const kfp16_net* n) { return n ? n->flops_bwd : 0.0; }
+double kfp16_net_flops_skipped(const kfp16_net* n) { return n ? n->flops_fwd_skipped + n->flops_bwd_skipped : 0.0; }
 
 int kfp16_net_num_params(const kfp16_net* n) { return n ? (int)n->params.size() : 0; }
 const char* kfp16_net_param_name(const kfp16_net* n, int i) { return (n && i >= 0 && i < (int)n->params.size()) ? n->params[i].name.c_str() : nullptr; }
@@ -1411,6 +1567,7 @@ int kfp16_net_set_bn(kfp16_net* n, const char* layer, const char* which, const f
   const bool rms = bn->rms_only;
   if (kfp16_bn_fold(n->ctx, bn->mean, bn->var, rms ? nullptr : bn->gamma, rms ? nullptr : bn->beta, eps, bn->target_rms, dim, bn->scale, bn->shift)) return -1;
   if (kfp16_scale_f32(n->ctx, bn->scale, bn->scale_bwd, dim, bn->bwd_mul)) return -1;
+  if (!retile_bn(n, *bn, bn->tiles)) return -1;
   return check_cuda(cudaStreamSynchronize(n->ctx->stream), "bn fold sync") ? 0 : -1;
 }
 
@@ -1599,7 +1756,16 @@ int kfp16_net_get_grad(kfp16_net* n, const char* layer, uint16_t* host, int rows
   if (!n || !layer || !host) { set_error("kfp16_net_get_grad: null argument"); return -1; }
   const int i = (layer[0] == 0) ? n->out_layer : find_layer(n, layer);
   if (i < 0) { set_error("kfp16_net_get_grad: no layer %s", layer); return -1; }
-  return read_dense(n, n->layers[i], n->layers[i].dout, host, rows, cols);
+  Layer& l = n->layers[i];
+  // a gradient that was only written on the objective's output frames is read back in its dense form
+  if (i == n->out_layer && n->out_g_sub > 1) {
+    if (densify_rows(n, l.dout, n->out_g_row0, n->out_g_sub)) return -1;
+    n->out_g_sub = 1; n->out_g_row0 = 0; l.g_sub = 1; l.g_row0 = 0;
+  } else if (l.g_sub > 1) {
+    if (densify_rows(n, l.dout, l.g_row0, l.g_sub)) return -1;
+    l.g_sub = 1; l.g_row0 = 0;
+  }
+  return read_dense(n, l, l.dout, host, rows, cols);
 }
 
 // ReLU mask of a tdnnf / prefinal layer as one byte per element, dense real rows (tests: lets the
@@ -1641,6 +1807,7 @@ int kfp16_net_loss_half_sq(kfp16_net* n, const char* layer) {
   if (i < 0) { set_error("kfp16_net_loss_half_sq: no such layer"); return -1; }
   Layer& l = n->layers[i];
   if (!l.dout.p) { set_error("kfp16_net_loss_half_sq: layer %s has no gradient buffer (train = 0?)", l.name.c_str()); return -1; }
+  n->out_g_sub = 1; n->out_g_row0 = 0;
   if (l.per_seq) return kfp16_half_sq_loss(n->ctx, l.out.p, l.dout.p, n->opts.n_seq, 1, 0, l.out_dim, n->loss_dev);
   return kfp16_half_sq_loss(n->ctx, l.out.p, l.dout.p, n->opts.n_seq, n->opts.seq_len, n->halo, l.out_dim, n->loss_dev);
 }
@@ -1656,9 +1823,35 @@ int kfp16_net_loss_chain(kfp16_net* n, const char* layer, kfp16_chain* chain, in
     set_error("kfp16_net_loss_chain: %d output frames at %d + t*%d exceed the %d frames of a sequence", kfp16_chain_frames(chain), left_context, subsampling, n->opts.seq_len);
     return -1;
   }
-  // the gradient is zero on every row that is not an output frame (and on the halo rows)
-  if (!check_cuda(cudaMemsetAsync(l.dout.p, 0, l.dout.bytes(), n->ctx->stream), "chain gradient clear")) return -1;
-  return kfp16_chain_loss(chain, l.out.p, l.dout.p, l.out_dim, n->blk, n->halo + left_context, subsampling, weight, n->loss_dev);
+  // The gradient is zero on every row that is not an output frame (and on the halo rows).  With a subsampling factor
+  // that divides the rows of a sequence block, the rows row0 + k*subsampling of the whole padded matrix are exactly the
+  // output frames plus a few rows per sequence behind its last frame: only those few are cleared, and the backward pass is
+  // told which rows carry the gradient (Layer::g_sub) -- the output / prefinal layers then back-propagate a third of the
+  // rows and nobody reads the rest.  Otherwise: clear everything, dense backward.
+  const int row0 = n->halo + left_context, frames = kfp16_chain_frames(chain);
+  const int per_blk = n->blk / subsampling;
+  const bool by_rows = chain_by_rows(n, i, subsampling, frames);
+  n->out_g_sub = 1; n->out_g_row0 = 0;
+  if (by_rows) {
+    for (int t = frames; t < per_blk; ++t) {
+      const int rb = row0 + t * subsampling;                 // row inside the block (may fall into the next block's head halo)
+      const int count = rb < n->blk ? n->opts.n_seq : n->opts.n_seq - 1;
+      if (count > 0 && !check_cuda(cudaMemset2DAsync(l.dout.p + (size_t)rb * l.out_dim, (size_t)n->blk * l.out_dim * 2, 0, (size_t)l.out_dim * 2,
+                                                       (size_t)count, n->ctx->stream), "chain gradient clear (rows behind the last output frame)")) return -1;
+    }
+    n->out_g_sub = subsampling; n->out_g_row0 = row0;
+  } else if (!check_cuda(cudaMemsetAsync(l.dout.p, 0, l.dout.bytes(), n->ctx->stream), "chain gradient clear")) return -1;
+  return kfp16_chain_loss(chain, l.out.p, l.dout.p, l.out_dim, n->blk, row0, subsampling, weight, n->loss_dev);
+}
+int kfp16_net_set_fuse_conv_backward(kfp16_net* n, int on) {
+  if (!n) { set_error("kfp16_net_set_fuse_conv_backward: null network"); return -1; }
+  n->fuse_conv_bwd = on != 0;
+  return 0;
+}
+int kfp16_net_set_sparse_output_grad(kfp16_net* n, int on) {
+  if (!n) { set_error("kfp16_net_set_sparse_output_grad: null network"); return -1; }
+  n->sparse_out_grad = on != 0;
+  return 0;
 }
 int kfp16_net_set_chain(kfp16_net* n, kfp16_chain* chain, int subsampling, int left_context, float weight) {
   if (!n) { set_error("kfp16_net_set_chain: null network"); return -1; }
@@ -1672,6 +1865,7 @@ int kfp16_net_set_output_grad(kfp16_net* n, const char* layer, const uint16_t* h
   if (i < 0) { set_error("kfp16_net_set_output_grad: no such layer"); return -1; }
   Layer& l = n->layers[i];
   if (!l.dout.p) { set_error("kfp16_net_set_output_grad: layer %s has no gradient buffer", l.name.c_str()); return -1; }
+  n->out_g_sub = 1; n->out_g_row0 = 0;
   const int want_rows = l.per_seq ? n->opts.n_seq : n->T;
   if (rows != want_rows || cols != l.out_dim) { set_error("kfp16_net_set_output_grad: shape mismatch"); return -1; }
   const size_t bytes = (size_t)rows * cols * 2;
@@ -1687,8 +1881,11 @@ int kfp16_net_set_output_grad(kfp16_net* n, const char* layer, const uint16_t* h
 // back-propagate through layers [lo, hi) in reverse order; `begin` starts a new backward pass
 static int backward_range(kfp16_net* n, int hi, int lo, bool begin) {
   if (begin) {
-    for (auto& l : n->layers) l.grads_seen = 0;
+    for (auto& l : n->layers) { l.grads_seen = 0; l.g_sub = 1; l.g_row0 = 0; l.dz_in_dout = false; }
+    n->flops_bwd_skipped = 0;
     n->layers[n->out_layer].grads_seen = 1;
+    n->layers[n->out_layer].g_sub = n->out_g_sub;
+    n->layers[n->out_layer].g_row0 = n->out_g_row0;
   }
   for (int i = hi - 1; i >= lo; --i) {
     Layer& l = n->layers[i];

@@ -305,6 +305,18 @@ class Network:
         if self.lib.kfp16_net_set_momentum(self.ptr, momentum) != 0:
             raise _err("SetMomentum")
 
+    def SetSparseOutputGrad(self, on: bool) -> None:
+        """chain objective with frame subsampling: back-propagate only the output frames' rows through the row-wise layers
+        behind the output (default on; same results as the dense form)"""
+        if self.lib.kfp16_net_set_sparse_output_grad(self.ptr, 1 if on else 0) != 0:
+            raise _err("SetSparseOutputGrad")
+
+    def SetFuseConvBackward(self, on: bool) -> None:
+        """conv layers with one consumer take dZ from that consumer's input-gradient epilogue (default on); Grad(conv layer)
+        then returns dZ instead of dY"""
+        if self.lib.kfp16_net_set_fuse_conv_backward(self.ptr, 1 if on else 0) != 0:
+            raise _err("SetFuseConvBackward")
+
     def Capture(self, phases: int = 3) -> None:
         if self.lib.kfp16_net_capture(self.ptr, phases) != 0:
             raise _err("Capture")

@@ -162,3 +162,39 @@ def test_chain_training_step(handle, lib):
         st.destroy()
     obj.Free()
     net.Free()
+
+
+@pytest.mark.parametrize("n_seq,L,frames,sub,left", [(4, 45, 14, 3, 1), (3, 45, 15, 3, 0), (5, 44, 14, 3, 2)])
+def test_output_frame_rows_backward_equals_dense(handle, lib, n_seq, L, frames, sub, left):
+    """frame subsampling: back-propagating only the output frames' rows through output / prefinal / prefinal-l (the rows
+    row0 + 3k of the padded matrix; the first splicing layer gets the dense gradient) gives the gradients of the dense
+    backward pass over a cleared output gradient.  (5 x 44: the block of 50 rows is not a multiple of 3 -> dense either way)"""
+    P = 104
+    rng = np.random.default_rng(5)
+    on = OracleNet(CHAIN_NET, n_seq, L)
+    on.init_random(rng)
+    den, nums = make_case(rng, n_seq, frames, P, 24, 4)
+    x = O.to_f16_rne(rng.standard_normal((n_seq * L, 64)).astype(np.float32))
+    res = []
+    for sparse in (True, False):
+        net = nnet.NewNetwork(nnet.BuildModelFromString(CHAIN_NET), handle, n_seq, L, ref_round=False)
+        for k, w in on.params.items():
+            net.SetParam(k, w)
+        net.SetSparseOutputGrad(sparse)
+        obj = KC.ChainObjective(handle, P, n_seq, frames, to_kc(den))
+        obj.SetNumerators([to_kc(f) for f in nums])
+        net.SetInput("input", x)
+        net.ZeroGrads()
+        assert lib.kfp16_net_forward(net.ptr) == 0
+        KC.ComputeChainLossBatch(net, obj, sub, left)
+        assert lib.kfp16_net_backward(net.ptr) == 0
+        res.append((net.WeightGrads(), net.Grad("tdnnf2"), net.Grad("output"), net.Grad("prefinal-l")))
+        obj.Free()
+        net.Free()
+    (wa, ga, oa, pa), (wb, gb, ob, pb) = res
+    assert np.array_equal(oa, ob)                       # the objective's gradient itself, dense read-back
+    assert np.array_equal(ga, gb)                       # what the splicing layer receives: same GEMM rows, bit-identical
+    assert np.array_equal(pa, pb)
+    for k in wb:
+        scale = max(np.abs(wb[k]).max(), 1e-12)
+        assert np.abs(wa[k] - wb[k]).max() <= 2e-6 * scale + 1e-7, k      # fp32 sums over a third of the rows: order only

@@ -121,6 +121,16 @@ def test_full_size_cnn_tdnn_layers_match_the_reference_operators(handle, lib, re
     assert np.isfinite(out).all()
     # dY = Y / 64 keeps the FP16 activation gradients of this random-init net in range
     dy = O.to_f16_rne(out * np.float32(1.0 / 64.0))
+    # backward twice: with one elementwise batch-norm / ReLU backward pass per conv layer (the gradient buffers then hold
+    # dY, which the reference operators below start from), and -- the default, what bench.py times -- with that pass
+    # folded into the consumer's input-gradient epilogue (the buffers hold dZ)
+    net.SetFuseConvBackward(False)
+    net.ZeroGrads()
+    net.Backward(dy)
+    gpu.Sync()
+    wg_unfused = net.WeightGrads()
+    douts = {name: net.Grad(name).astype(np.float16) for name, _ in CONV}
+    net.SetFuseConvBackward(True)
     net.ZeroGrads()
     net.Backward(dy)
     gpu.Sync()
@@ -145,12 +155,21 @@ def test_full_size_cnn_tdnn_layers_match_the_reference_operators(handle, lib, re
         err = O.max_err_vs_scale(got, want)
         assert err <= 2e-3, f"{name} forward (M={M} K={K} N={fout}) vs reference operators: err {err:.2e}"
         # weight gradient for THIS library's gradient wrt the layer output
-        dout = net.Grad(name).reshape(M, fout)
+        dout = douts[name].astype(np.float32).reshape(M, fout)
         assert np.isfinite(dout).all() and np.abs(dout).max() > 0, f"{name}: degenerate output gradient"
         dZ = R.zeros(M, fout)
         dO = R.up(dout)
         assert R.lib.ops_batchnorm_backward(dO.ptr, dZ.ptr, bn["gamma"].ptr, bn["var"].ptr, 1e-3, M, fout) == 0
         assert R.lib.ops_relu_backward(relu.ptr, dZ.ptr, M * fout) == 0
+        # fused form: the layer's gradient buffer holds dZ itself (ReLU masks may differ where the pre-activation rounds
+        # across zero: a small fraction of elements, each by its full value)
+        dz_ref, dz_fused = dZ.f32(), net.Grad(name).reshape(M, fout)
+        scale_dz = max(float(np.abs(dz_ref).max()), 1e-12)
+        bad = np.abs(dz_fused - dz_ref) > 4e-3 * scale_dz
+        assert bad.mean() < 2e-3, f"{name}: fused dZ differs from ops_batchnorm_backward + ops_relu_backward on {bad.mean():.2%} of the elements"
+        del dz_ref, dz_fused, bad
+        err = O.max_err_vs_scale(wg[f"{name}.W"], wg_unfused[f"{name}.W"])
+        assert err <= 2e-3, f"{name} weight gradient, fused vs unfused backward: err {err:.2e}"
         Pt = R.transpose(Pr, M, K)
         ours = wg[f"{name}.W"]
         alpha = float(2.0 ** -np.ceil(np.log2(max(np.abs(ours).max() / 1024.0, 1.0))))   # keep the FP16 result in range

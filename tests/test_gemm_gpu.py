@@ -344,7 +344,7 @@ def conv_addr(d, mode, x_t, T, H, P, C, rows_h, taps_addr):
 TAPS9 = [(dt, dh) for dt in (-1, 0, 1) for dh in (-1, 0, 1)]
 
 
-@pytest.mark.parametrize("max_ctas", [0, 6])
+@pytest.mark.parametrize("max_ctas,no_share", [(0, 0), (6, 0), (0, 1), (0, 5)])     # 1: a box per tap; 5: shared box also for 256-wide tiles
 @pytest.mark.parametrize("T,hin,sub,C,N,taps", [
     (300, 40, 1, 64, 64, TAPS9),        # 3 frames x 40 heights = 120-row tiles (the benchmark's cnn2 geometry)
     (190, 40, 2, 64, 128, TAPS9),       # height subsampling: parity planes of the input (cnn3)
@@ -352,7 +352,7 @@ TAPS9 = [(dt, dh) for dt in (-1, 0, 1) for dh in (-1, 0, 1)]
     (97, 8, 1, 128, 64, [(-2, 0), (0, 1), (3, -1)]),   # 16 x 8 = full 128-row tiles, ragged T, irregular taps
     (40, 16, 2, 64, 72, [(0, 0), (1, 1)]),             # N not a tile multiple; the odd parity plane only via dh = 1
 ])
-def test_implicit_conv_forward_gemm(handle, lib, max_ctas, T, hin, sub, C, N, taps):
+def test_implicit_conv_forward_gemm(handle, lib, max_ctas, no_share, T, hin, sub, C, N, taps):
     """conv.mode 1: Y[(t,h), n] = sum_taps x[t+dt, h*sub+dh, :] W[tap] with bias+ReLU+BN+mask epilogue, no patch matrix"""
     hout = hin // sub
     rng = np.random.default_rng(T * hin + C + N)
@@ -369,7 +369,7 @@ def test_implicit_conv_forward_gemm(handle, lib, max_ctas, T, hin, sub, C, N, ta
     tsc, tsh = gpu.DeviceF32(scale), gpu.DeviceF32(shift)
     mask_ld = (N + 31) // 32
     tmask = gpu.DeviceF32(n=T * hout * mask_ld)
-    d = make_desc(T * hout, N, len(taps) * C, tx, tW, tD, flags=EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK)
+    d = make_desc(T * hout, N, len(taps) * C, tx, tW, tD, flags=EPI_BIAS | EPI_RELU | EPI_BN | EPI_MASK, no_share=no_share)
     d.A.ptr = None
     d.bias, d.bn_scale, d.bn_shift = tb.Ptr, tsc.Ptr, tsh.Ptr
     d.mask_out, d.mask_ld = tmask.Ptr, mask_ld
@@ -394,9 +394,11 @@ def test_implicit_conv_forward_gemm(handle, lib, max_ctas, T, hin, sub, C, N, ta
         t.Free()
 
 
+@pytest.mark.parametrize("no_share", [0, 1, 5])
 @pytest.mark.parametrize("T,hin,sub,Cin,Cout,taps", [(300, 40, 1, 64, 64, TAPS9), (190, 40, 2, 64, 128, TAPS9),
-                                                     (156, 10, 1, 256, 128, TAPS9), (60, 16, 2, 64, 64, [(0, 0), (1, 1)])])
-def test_implicit_conv_input_gradient_gemm(handle, lib, T, hin, sub, Cin, Cout, taps):
+                                                     (156, 10, 1, 256, 128, TAPS9), (156, 10, 1, 256, 256, TAPS9),
+                                                     (60, 16, 2, 64, 64, [(0, 0), (1, 1)])])
+def test_implicit_conv_input_gradient_gemm(handle, lib, no_share, T, hin, sub, Cin, Cout, taps):
     """the adjoint: dX[t, hi, :] = sum_taps dZ[t-dt, (hi-dh)/sub, :] W[tap]^T as conv.mode 1 over dZ with mirrored taps
     (one launch per input-height parity when the layer subsamples by 2), K-major B = the forward's weight matrix"""
     hout = hin // sub
@@ -422,7 +424,7 @@ def test_implicit_conv_input_gradient_gemm(handle, lib, T, hin, sub, Cin, Cout, 
         addr = [(-dt, (par - dh) // sub, 0, k * Cin) for k, (dt, dh) in enumerate(taps) if (par - dh) % sub == 0]
         if not addr:
             continue
-        d = make_desc(T * hout, Cin, len(addr) * Cout, tz, tW, tD, b_major=K_MAJOR)
+        d = make_desc(T * hout, Cin, len(addr) * Cout, tz, tW, tD, b_major=K_MAJOR, no_share=no_share)
         d.A.ptr = None
         d.D[0] = tD.Ptr + par * Cin * 2
         d.ldd = sub * Cin

@@ -309,8 +309,9 @@ output-layer name=output include-log-softmax=false dim=72
 # patch matrix; F1 = 32: cnn2 has a 32-channel input and takes the patch-matrix path too
 
 
-def check_conv_net(handle, n_seq, L, seed, ref_round=True, f1=64):
+def check_conv_net(handle, n_seq, L, seed, ref_round=True, f1=64, fuse=True):
     on, net, rng = make_pair(handle, CNN_SMALL.replace("F1", str(f1)), n_seq, L, seed=seed, ref_round=ref_round)
+    net.SetFuseConvBackward(fuse)
     x = O.to_f16_rne((rng.standard_normal((n_seq * L, 16)) * 2).astype(np.float32))
     iv = O.to_f16_rne(np.clip(rng.standard_normal((n_seq, 24)), -3, 3).astype(np.float32))
     inputs = {"input": x, "ivector": iv}
@@ -339,8 +340,16 @@ def check_conv_net(handle, n_seq, L, seed, ref_round=True, f1=64):
         err = rel_to_scale(got_wg[k], g)
         tol = 1e-2 if k.endswith("Bias") else 5e-3
         assert err <= tol, f"weight grad {k}: err {err:.2e} > {tol}"
+    from oracle.nnet_oracle import h
     for name in ("cnn3", "cnn1", "combine_inputs"):
-        err = rel_to_scale(net.Grad(name), dact[name])
+        want = dact[name]
+        if fuse and name.startswith("cnn") and (name != "cnn1" or f1 == 64):     # (f1 = 32: cnn2 takes the patch-matrix path, which does not fuse)
+            # the consumer's input-gradient epilogue already applied this layer's batch-norm scale and ReLU mask: the
+            # buffer holds dZ = mask ? h(dY * scale) : 0 (what backwardConvReluBN computes first)
+            fout = on.saved[name]["mask"].shape[1]
+            sc = on._bn_scale(on.bn[(name, "BN")])
+            want = np.where(masks[name].reshape(-1, fout), h(want.reshape(-1, fout) * sc), np.float32(0)).reshape(want.shape)
+        err = rel_to_scale(net.Grad(name), want)
         assert err <= 5e-3, f"activation grad {name}: err {err:.2e}"
     net.Free()
 
@@ -352,6 +361,12 @@ def test_cnn_front_end_forward_backward(handle, n_seq, L, ref_round):
     tcgen05 GEMMs (implicit GEMM over 4-D TMA boxes; the 3-filter first layer through a patch matrix), against the
     numpy oracle's explicit patch matrices"""
     check_conv_net(handle, n_seq, L, seed=5 + n_seq, ref_round=ref_round)
+
+
+@REF_ROUND
+def test_cnn_front_end_unfused_backward(handle, ref_round):
+    """the same with one elementwise batch-norm / ReLU backward pass per conv layer (kfp16_net_set_fuse_conv_backward 0)"""
+    check_conv_net(handle, 3, 17, seed=8, ref_round=ref_round, fuse=False)
 
 
 def test_cnn_front_end_patch_matrix_path(handle):
