@@ -137,6 +137,11 @@ int kfp16_net_set_sparse_output_grad(kfp16_net *net, int on);
  * that consumer's input-gradient GEMM epilogue (ops_batchnorm_backward + ops_relu_backward, backward_wrappers.cu:41-115,
  * folded into the producing kernel) and only sums its bias gradient; on = 0: one elementwise pass per conv layer. */
 int kfp16_net_set_fuse_conv_backward(kfp16_net *net, int on);
+/* on = 1 (default): in the training step the chain objective is queued on a second stream as soon as the output layer is
+ * done, and the layers it does not depend on (the xent branch, which the reference's Forward computes as well) run beside
+ * it on the SMs the objective's one-CTA-per-sequence kernel leaves free; both join before the backward pass.  Needs a
+ * non-default context stream; on = 0: everything in order on one stream. */
+int kfp16_net_set_overlap_loss(kfp16_net *net, int on);
 int kfp16_net_backward(kfp16_net *net);
 /* gradient wrt a layer's output, dense real rows (tests) */
 int kfp16_net_get_grad(kfp16_net *net, const char *layer, uint16_t *host_f16, int rows, int cols);

@@ -227,6 +227,7 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_set_chain": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float]),
     "kfp16_net_set_sparse_output_grad": (c_int, [c_void_p, c_int]),
     "kfp16_net_set_fuse_conv_backward": (c_int, [c_void_p, c_int]),
+    "kfp16_net_set_overlap_loss": (c_int, [c_void_p, c_int]),
     # ---- kaldi_fp16_ops.h
     "ops_cublas_create": (c_void_p, []),
     "ops_cublas_destroy": (None, [c_void_p]),

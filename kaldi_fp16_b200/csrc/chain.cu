@@ -540,6 +540,26 @@ struct kfp16_chain {
   size_t alpha_num_elems = 0;
 };
 
+// One CTA per sequence.  With an even sequence count the CTAs are launched as clusters of two -- not to cooperate (the kernels
+// never look at their cluster rank) but so that the block scheduler packs them two to a TPC: 64 sequences then hold 32 whole
+// TPCs and leave the other 42 free for the CTA-pair GEMMs the network executor runs beside the objective
+// (nnet.cu run_phases: the xent branch's forward pass overlaps the chain kernel).
+template <typename Kern, typename... Args>
+static void launch_chain(Kern kern, int grid, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kChainThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (grid % 2) == 0 ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+
 extern "C" {
 
 kfp16_chain* kfp16_chain_create(kfp16_ctx* ctx, int num_pdfs, int n_seq, int frames_per_seq, const kfp16_chain_fst* den) {
@@ -630,13 +650,13 @@ int kfp16_chain_loss(kfp16_chain* c, const void* nnet_out, void* grad_out, int l
     // the smallest per-thread arc / state counts that cover the graphs (less unrolled code, fewer registers)
     const int ar = (atot_max + kChainThreads - 1) / kChainThreads, qr = (stot_max + kChainThreads - 1) / kChainThreads;
     const FstRef dref = ref_of(c->den);
-    if (ar <= 1 && qr <= 1) chain_loss_fast_kernel<1, 1><<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, dref, stot_max, atot_max);
-    else if (ar <= 2 && qr <= 1) chain_loss_fast_kernel<2, 1><<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, dref, stot_max, atot_max);
-    else if (qr <= 2) chain_loss_fast_kernel<4, 2><<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, dref, stot_max, atot_max);
-    else chain_loss_fast_kernel<4, 4><<<c->n_seq, kChainThreads, L.total, c->ctx->stream>>>(a, c->nums_dev, dref, stot_max, atot_max);
+    if (ar <= 1 && qr <= 1) launch_chain(chain_loss_fast_kernel<1, 1>, c->n_seq, L.total, c->ctx->stream, a, (const FstRef*)c->nums_dev, dref, stot_max, atot_max);
+    else if (ar <= 2 && qr <= 1) launch_chain(chain_loss_fast_kernel<2, 1>, c->n_seq, L.total, c->ctx->stream, a, (const FstRef*)c->nums_dev, dref, stot_max, atot_max);
+    else if (qr <= 2) launch_chain(chain_loss_fast_kernel<4, 2>, c->n_seq, L.total, c->ctx->stream, a, (const FstRef*)c->nums_dev, dref, stot_max, atot_max);
+    else launch_chain(chain_loss_fast_kernel<4, 4>, c->n_seq, L.total, c->ctx->stream, a, (const FstRef*)c->nums_dev, dref, stot_max, atot_max);
   } else {
     const size_t smem = (size_t)c->num_pdfs * 2 * sizeof(float);
-    chain_loss_kernel<<<c->n_seq, kChainThreads, smem, c->ctx->stream>>>(a, c->nums_dev, ref_of(c->den));
+    launch_chain(chain_loss_kernel, c->n_seq, smem, c->ctx->stream, a, (const FstRef*)c->nums_dev, ref_of(c->den));
   }
   count_launch();
   return check_launch("kfp16_chain_loss") ? 0 : -1;

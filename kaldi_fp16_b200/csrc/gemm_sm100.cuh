@@ -830,13 +830,15 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
           if (warp == 4 && c64 < 256) dbg_stamp(p, 2, tile_i, 2 + 3 * (c64 >> 6));
           if (c < BN) {
             uint32_t v32[32];
+            // (the mask word of this row -- one 4-byte load per lane, rows mask_ld words apart -- is requested before the
+            //  accumulator read so that both latencies overlap)
+            uint32_t maskword = 0, gm_word = 0xFFFFFFFFu;
+            if (flags & EPI_GRADMASK)
+              gm_word = (row < p.M && row_ok && n0 + c < p.N) ? __ldg(p.mask_in + (size_t)row * p.mask_ld + ((n0 + c) >> 5)) : 0u;
             if (!kGeneric) {
               tmem_ld_32x32(t_acc + c, v32);
               tmem_ld_wait();
             }
-            uint32_t maskword = 0, gm_word = 0xFFFFFFFFu;
-            if (flags & EPI_GRADMASK)
-              gm_word = (row < p.M && row_ok && n0 + c < p.N) ? __ldg(p.mask_in + (size_t)row * p.mask_ld + ((n0 + c) >> 5)) : 0u;
 #pragma unroll(kGeneric ? 1 : 4)
             for (int j = 0; j < 4; ++j) {          // 8 columns = one 16-byte smem unit
               const int ct = c + j * 8;            // column inside the tile

@@ -169,6 +169,10 @@ struct kfp16_net {
   float chain_weight = 1.0f;
   bool sparse_out_grad = true;          // kfp16_net_set_sparse_output_grad
   double flops_fwd_skipped = 0, flops_bwd_skipped = 0;   // of flops_fwd / flops_bwd, not executed by the last training step (rows outside the objective's frames)
+  // the objective runs on a second stream beside the forward pass of the layers it does not depend on (xent branch)
+  bool overlap_loss = true;             // kfp16_net_set_overlap_loss
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fwd_rows_now = false;            // inside the training step: honour Layer::f_sub in forward_layer
   bool fuse_conv_bwd = true;            // conv producers get dZ from their consumer's input-gradient epilogue (KFP16_FUSE_CONV_BWD=0: off)
   int out_g_sub = 1, out_g_row0 = 0;   // gradient rows the last objective call wrote on the output layer (Layer::g_sub)
@@ -1433,11 +1437,50 @@ int run_phases(kfp16_net* n, int phases) {
     if (kfp16_net_zero_grads(n)) return -1;
     // a chain objective on subsampled output frames: the row-wise layers that feed only the objective compute just its rows
     plan_forward_rows(n);
+    // Layers the objective does not depend on (the xent branch: prefinal-xent, output-xent + log-softmax -- computed by the
+    // reference's Forward as well, read by nobody in the step) run AFTER the objective has been queued on a second stream:
+    // the chain kernel holds one CTA per sequence (64 of 148 SMs, packed two to a TPC) for ~190 us, the GEMMs beside it
+    // are limited to the remaining SMs.  Both join before the backward pass.
+    const int L = (int)n->layers.size();
+    std::vector<char> anc(L, 0);
+    int n_rest = 0;
+    if (n->out_layer >= 0) {
+      anc[n->out_layer] = 1;
+      for (int i = n->out_layer; i >= 0; --i)
+        if (anc[i]) for (int src : n->layers[i].in) anc[src] = 1;
+      for (int i = 0; i < L; ++i) if (!anc[i] && n->layers[i].type != L_INPUT) ++n_rest;
+    }
+    const int sms = n->ctx->num_sms, held = (n->opts.n_seq + 1) & ~1;
+    const bool overlap = n->chain && n->overlap_loss && n->ctx->stream && n_rest > 0 && held + 16 <= sms && (n->ctx->max_ctas == 0 || n->ctx->max_ctas >= sms);
+    if (overlap && !n->side_stream) {
+      if (!check_cuda(cudaStreamCreateWithFlags(&n->side_stream, cudaStreamNonBlocking), "side stream") ||
+          !check_cuda(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming), "fork event") ||
+          !check_cuda(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming), "join event")) return -1;
+    }
     n->fwd_rows_now = true;
-    const int frc = kfp16_net_forward(n);
+    int frc = 0;
+    for (int i = 0; i < L && !frc; ++i)
+      if (!overlap || anc[i]) frc = forward_layer(n, n->layers[i]);
+    if (!frc && overlap) {
+      cudaStream_t main_stream = n->ctx->stream;
+      frc = !check_cuda(cudaEventRecord(n->ev_fork, main_stream), "fork record") ||
+            !check_cuda(cudaStreamWaitEvent(n->side_stream, n->ev_fork, 0), "fork wait");
+      if (!frc) {
+        n->ctx->stream = n->side_stream;
+        frc = kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight);
+        n->ctx->stream = main_stream;
+      }
+      if (!frc) frc = !check_cuda(cudaEventRecord(n->ev_join, n->side_stream), "join record");
+      const int saved_max = n->ctx->max_ctas;
+      n->ctx->max_ctas = (sms - held - 4) & ~1;            // whole TPCs, a little slack for the block scheduler
+      for (int i = 0; i < L && !frc; ++i)
+        if (!anc[i]) frc = forward_layer(n, n->layers[i]);
+      n->ctx->max_ctas = saved_max;
+      if (!frc) frc = !check_cuda(cudaStreamWaitEvent(main_stream, n->ev_join, 0), "join wait");
+    }
     n->fwd_rows_now = false;
     if (frc) return -1;
-    if (n->chain ? kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight) : kfp16_net_loss_half_sq(n, "")) return -1;
+    if (!overlap && (n->chain ? kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight) : kfp16_net_loss_half_sq(n, ""))) return -1;
     if (kfp16_net_backward(n)) return -1;
   }
   if (phases & 4) {
@@ -1490,6 +1533,9 @@ void kfp16_net_destroy(kfp16_net* n) {
   for (int k = 0; k < 3; ++k) { if (n->copy_extra[k]) cudaStreamDestroy(n->copy_extra[k]); if (n->copy_part[k]) cudaEventDestroy(n->copy_part[k]); }
   for (auto& kv : n->wg_groups) kfp16_wgrad_group_destroy(kv.second);
   for (cudaGraphExec_t g : n->seg_graph) if (g) cudaGraphExecDestroy(g);
+  if (n->side_stream) cudaStreamDestroy(n->side_stream);
+  if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+  if (n->ev_join) cudaEventDestroy(n->ev_join);
   if (n->loss_pinned) cudaFreeHost(n->loss_pinned);
   for (cudaEvent_t e : n->loss_ev) if (e) cudaEventDestroy(e);
   delete n;
@@ -1842,6 +1888,11 @@ int kfp16_net_loss_chain(kfp16_net* n, const char* layer, kfp16_chain* chain, in
     n->out_g_sub = subsampling; n->out_g_row0 = row0;
   } else if (!check_cuda(cudaMemsetAsync(l.dout.p, 0, l.dout.bytes(), n->ctx->stream), "chain gradient clear")) return -1;
   return kfp16_chain_loss(chain, l.out.p, l.dout.p, l.out_dim, n->blk, row0, subsampling, weight, n->loss_dev);
+}
+int kfp16_net_set_overlap_loss(kfp16_net* n, int on) {
+  if (!n) { set_error("kfp16_net_set_overlap_loss: null network"); return -1; }
+  n->overlap_loss = on != 0;
+  return 0;
 }
 int kfp16_net_set_fuse_conv_backward(kfp16_net* n, int on) {
   if (!n) { set_error("kfp16_net_set_fuse_conv_backward: null network"); return -1; }
