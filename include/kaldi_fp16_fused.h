@@ -226,6 +226,26 @@ int kfp16_zero_halo(kfp16_ctx *ctx, void *X, int ld, int n_seq, int seq_len, int
 /* y = h(x*scale[c] + shift[c]); shift may be NULL (batch-norm forward / backward with folded params) */
 int kfp16_scale_shift(kfp16_ctx *ctx, const void *x, void *y, int rows, int cols, const float *scale,
                       const float *shift);
+/* ---- train-mode batch-norm (batch statistics): cpp/cuda/cnn_kernels.cu:236-320 (training branch), go/gotorch/layers.go:257-300.
+ * Row filter of all three calls: period > 0 restricts to rows r with lo <= r % period < lo + len (the real frames of the
+ * padded layout: period = seq_len + 2*halo, lo = halo, len = seq_len; times the height count for conv activations).
+ *  stats[0..cols) = sum, stats[cols..2*cols) = sum of squares (fp32; zeroed by the call).  A data-parallel job sums `stats`
+ *  over the ranks before kfp16_bn_finalize and passes the global row count. */
+int kfp16_bn_batch_stats(kfp16_ctx *ctx, const void *X, int ld, int rows, int cols, float *stats, int period, int lo, int len);
+/* mean = S1/n, var = S2/n - mean^2 (biased); running = (1-momentum)*running + momentum*batch; scale = gamma/sqrt(var+eps)
+ * (gamma NULL: target_rms), shift = beta - mean*scale, scale_bwd = scale*bwd_mul (may be NULL) */
+int kfp16_bn_finalize(kfp16_ctx *ctx, const float *stats, double n_rows, int D, float *run_mean, float *run_var,
+                      const float *gamma, const float *beta, float eps, float target_rms, float momentum, float bwd_mul,
+                      float *scale, float *shift, float *scale_bwd);
+/* Z = h(Z*scale[c % col_mod] + shift[c % col_mod] (+ res_scale*R)) in place on the filtered rows */
+int kfp16_bn_apply(kfp16_ctx *ctx, void *Z, int ld, const float *scale, const float *shift, const void *R, int ldr,
+                   float res_scale, int rows, int cols, int col_mod, int period, int lo, int len);
+/* SpecAugment (go/gotorch/cnn_tdnn.go:612-668) on the padded layout: per sequence nfreq frequency masks of width <= fmax and
+ * ntime time masks of width <= tmax are zeroed (halo rows copied through; x == y allowed).  The masks are drawn from the
+ * counter-based generator kfp16_dropout_uniform(seed ^ *seed_dev, sequence, draw) -- see csrc/elementwise.cu for the draw
+ * order -- so applying the same call to a gradient is the layer's backward pass. */
+int kfp16_spec_augment(kfp16_ctx *ctx, const void *x, void *y, int ld, int n_seq, int seq_len, int halo, int dim, int fmax,
+                       int nfreq, int tmax, int ntime, uint32_t seed, const uint32_t *seed_dev);
 /* the same on row-strided views: row r of x / y starts ldx / ldy elements after row r-1 (cols, ldx, ldy multiples of 8) */
 int kfp16_scale_shift_ld(kfp16_ctx *ctx, const void *x, long long ldx, void *y, long long ldy, int rows, int cols,
                          const float *scale, const float *shift);

@@ -73,6 +73,9 @@ float *kfp16_net_grads_f32(kfp16_net *net);   /* device, fp32 gradient bucket (a
 /* host fp32 [rows x cols] -> truncating fp16 (gpu.TensorFromFP32, tensor.go:67-91) -> device; the
  * FP32 master is set to float(fp16) as RegisterParam does (optimize.go:52-93) */
 int kfp16_net_set_param(kfp16_net *net, const char *name, const float *host, int rows, int cols);
+/* idct-layer: load the matrix instead of computing it (Kaldi's `idct` component, weight_loader.go:766-776); fp32 [dim x dim],
+ * [in x out], through the truncating converter */
+int kfp16_net_set_idct(kfp16_net *net, const char *layer, const float *host_f32, int dim);
 int kfp16_net_get_param(kfp16_net *net, const char *name, uint16_t *host_f16, int rows, int cols);
 /* which: for "batchnorm-component" layers "", for tdnnf "AffBN", prefinal "PfBN" / "BN", conv "BN" */
 int kfp16_net_set_bn(kfp16_net *net, const char *layer, const char *which, const float *mean,
@@ -136,6 +139,25 @@ int kfp16_net_set_sparse_output_grad(kfp16_net *net, int on);
 /* on = 1 (default): a conv-relu-batchnorm layer with a single consumer gets dZ = mask ? h(dY * bn_scale) : 0 straight from
  * that consumer's input-gradient GEMM epilogue (ops_batchnorm_backward + ops_relu_backward, backward_wrappers.cu:41-115,
  * folded into the producing kernel) and only sums its bias gradient; on = 0: one elementwise pass per conv layer. */
+/* Train-mode batch-norm (cpp/cuda/cnn_kernels.cu:236-320 training branch, go/gotorch/layers.go:257-330): on = 1 makes every
+ * batch-norm of a training network normalise with the statistics of the current minibatch (all real frames; per filter over
+ * frames x heights in conv layers; biased variance) and update the stored running statistics with `momentum`
+ * (running = (1-m)*running + m*batch); the backward pass scales by gamma/sqrt(batch var + eps) and, like the reference,
+ * does not differentiate through the statistics.  The producing GEMM then runs with an identity batch-norm and three small
+ * passes follow it (kfp16_bn_batch_stats / _finalize / _apply).  on = 0 (default): running statistics, fused epilogue. */
+int kfp16_net_set_train_batchnorm(kfp16_net *net, int on, float momentum);
+/* Data-parallel training: `hook(user, stats_dev, count, stream)` is called between the statistics pass and the finalize
+ * pass of every batch-norm with the fp32 [sum | sum of squares] vector on the device; it must sum it over the `world` ranks
+ * (stream-ordered on `stream`) and return 0.  The step cannot be captured into a graph while a hook is set. */
+typedef int (*kfp16_bn_stats_hook)(void *user, float *stats_dev, int count, void *stream);
+int kfp16_net_set_bn_stats_hook(kfp16_net *net, kfp16_bn_stats_hook hook, void *user, int world);
+/* running mean / variance of a layer's batch-norm (fp32 [dim]); `which` as in kfp16_net_set_bn */
+int kfp16_net_get_bn(kfp16_net *net, const char *layer, const char *which, float *mean, float *var, int dim);
+/* spec-augment-layer: the reference's GPU executor passes the features through (internal/nnet/forward.go:377-383, a TODO).
+ * on = 1 (training networks): apply kfp16_spec_augment with one frequency mask of width <= freq-max-proportion*dim and
+ * round(time-zeroed-proportion*seq_len / (time-mask-max-frames/2)) time masks of width <= time-mask-max-frames per
+ * sequence, new masks every step (the per-step seed word of the dropout masks); the backward pass masks the gradient. */
+int kfp16_net_set_spec_augment(kfp16_net *net, int on);
 int kfp16_net_set_fuse_conv_backward(kfp16_net *net, int on);
 /* on = 1 (default): in the training step the chain objective is queued on a second stream as soon as the output layer is
  * done, and the layers it does not depend on (the xent branch, which the reference's Forward computes as well) run beside

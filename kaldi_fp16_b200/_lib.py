@@ -141,6 +141,10 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_seq_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int]),
     "kfp16_zero_halo": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "kfp16_scale_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "kfp16_bn_batch_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int]),
+    "kfp16_bn_finalize": (c_int, [c_void_p, c_void_p, C.c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "kfp16_bn_apply": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "kfp16_spec_augment": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_u32, c_void_p]),
     "kfp16_scale_shift_ld": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "kfp16_zero_rows_except": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "kfp16_half_sq_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -228,6 +232,11 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_set_sparse_output_grad": (c_int, [c_void_p, c_int]),
     "kfp16_net_set_fuse_conv_backward": (c_int, [c_void_p, c_int]),
     "kfp16_net_set_overlap_loss": (c_int, [c_void_p, c_int]),
+    "kfp16_net_set_spec_augment": (c_int, [c_void_p, c_int]),
+    "kfp16_net_set_train_batchnorm": (c_int, [c_void_p, c_int, c_float]),
+    "kfp16_net_set_bn_stats_hook": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "kfp16_net_set_idct": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int]),
+    "kfp16_net_get_bn": (c_int, [c_void_p, C.c_char_p, C.c_char_p, c_void_p, c_void_p, c_int]),
     # ---- kaldi_fp16_ops.h
     "ops_cublas_create": (c_void_p, []),
     "ops_cublas_destroy": (None, [c_void_p]),

@@ -11,13 +11,12 @@
 #include "../../include/kaldi_fp16_fused.h"
 #include "../../include/kaldi_fp16_ops.h"
 #include "host_common.h"
+#include "sm100_ptx.cuh"
 
 namespace kfp16 {
 
 constexpr int kThreads = 256;
-// programmatic dependent launch (see sm100_ptx.cuh / host_common.h launch_pdl)
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+// (griddep_wait / griddep_launch -- programmatic dependent launch -- and dropout_uniform come from sm100_ptx.cuh)
 
 static int num_sms_cached() {
   static int n = 0;
@@ -678,6 +677,87 @@ colsum_v2_kernel(const __half* __restrict__ X, int ld, uint32_t rows, int cols, 
   colsum_flush(red, acc, cg, ry, cols, col_mod, out);
 }
 
+// ---- train-mode batch-norm (batch statistics; cpp/cuda/cnn_kernels.cu:236-320 batchnorm1d_forward_fp16 training branch,
+// go/gotorch/layers.go:257-300): three small passes around the producing GEMM instead of one thread per channel looping over
+// the whole batch three times.
+//  (1) per-column sum and sum of squares over the rows that belong to the minibatch: rows r with (r % period - lo) < len
+//      (the real frames of the padded layout; period == 0: every row), fp32, accumulated into stats[0..cols) / stats[cols..2cols)
+__global__ void __launch_bounds__(256, 4)
+bn_stats_kernel(const __half* __restrict__ X, int ld, uint32_t rows, int cols, float* __restrict__ stats, uint32_t period, uint32_t lo,
+                uint32_t len) {
+  __shared__ float red[8][32][8];
+  const int cg = threadIdx.x, ry = threadIdx.y;
+  const int c = (blockIdx.x * 32 + cg) * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  if (c < cols) {
+    const uint32_t rows_per = (rows + gridDim.y - 1) / gridDim.y;
+    const uint32_t r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, rows);
+    for (uint32_t r = r0 + ry; r < r1; r += 8) {
+      if (period != 0 && (r % period - lo) >= len) continue;
+      const uint4 a = *reinterpret_cast<const uint4*>(X + (size_t)r * ld + c);
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_h2(w[j]);
+        s1[2 * j] += f.x; s1[2 * j + 1] += f.y;
+        s2[2 * j] = fmaf(f.x, f.x, s2[2 * j]); s2[2 * j + 1] = fmaf(f.y, f.y, s2[2 * j + 1]);
+      }
+    }
+  }
+  colsum_flush(red, s1, cg, ry, cols, cols, stats);
+  __syncthreads();
+  colsum_flush(red, s2, cg, ry, cols, cols, stats + cols);
+}
+//  (2) statistics -> folded scale / shift (what the epilogues and the backward pass read) + running-statistics update.
+//      mean = S1/n, var = S2/n - mean^2 (biased, as the reference), running = (1 - momentum)*running + momentum*batch
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float n, int D, float* __restrict__ run_mean, float* __restrict__ run_var,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float target_rms,
+                                   float momentum, float bwd_mul, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ scale_bwd) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float mean = stats[d] / n;
+  const float var = fmaxf(stats[D + d] / n - mean * mean, 0.f);
+  run_mean[d] = run_mean[d] * (1.f - momentum) + mean * momentum;
+  run_var[d] = run_var[d] * (1.f - momentum) + var * momentum;
+  const float inv = 1.0f / sqrtf(var + eps);
+  const float g = gamma ? gamma[d] : target_rms;
+  const float b = beta ? beta[d] : 0.0f;
+  const float sc = g * inv;
+  scale[d] = sc;
+  shift[d] = b - mean * sc;
+  if (scale_bwd) scale_bwd[d] = sc * bwd_mul;
+}
+//  (3) y = h(z*scale[c % col_mod] + shift[c % col_mod] (+ res_scale*R)) in place on the minibatch's rows (same row filter)
+__global__ void bn_apply_kernel(__half* __restrict__ Z, int ld, const float* __restrict__ scale, const float* __restrict__ shift,
+                                const __half* __restrict__ R, int ldr, float res_scale, uint32_t rows, int cols, int col_mod, uint32_t period,
+                                uint32_t lo, uint32_t len) {
+  const int cv = cols >> 3;
+  const size_t total = (size_t)rows * cv, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const uint32_t r = (uint32_t)(i / cv);
+    if (period != 0 && (r % period - lo) >= len) continue;
+    const int c = (int)(i % cv) << 3;
+    const int cm = c % col_mod;
+    uint4 v = *reinterpret_cast<const uint4*>(Z + (size_t)r * ld + c);
+    uint4 rv = make_uint4(0, 0, 0, 0);
+    if (R) rv = *reinterpret_cast<const uint4*>(R + (size_t)r * ldr + c);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_h2(w[j]);
+      f.x = fmaf(f.x, scale[cm + 2 * j], shift[cm + 2 * j]);
+      f.y = fmaf(f.y, scale[cm + 2 * j + 1], shift[cm + 2 * j + 1]);
+      if (R) { const float2 q = unpack_h2(rw[j]); f.x = fmaf(res_scale, q.x, f.x); f.y = fmaf(res_scale, q.y, f.y); }
+      w[j] = pack_h2(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(Z + (size_t)r * ld + c) = v;
+  }
+}
+
 // replicate row 0 / row rows-1 of every sequence block into its halo rows
 //   buffer rows: n_seq blocks of (seq_len + 2*halo) rows; X points at the first block's row -halo
 __global__ void pad_edges_kernel(__half* __restrict__ X, int ld, int n_seq, int seq_len, int cols, int halo) {
@@ -821,14 +901,33 @@ __global__ void bcast_rows_kernel(const __half* __restrict__ src, int cols, __ha
   }
 }
 // out[s, c] = h( sum over the real rows of block s of G[r, col0 + c] )   (adjoint of the broadcast)
-__global__ void seq_sum_kernel(const __half* __restrict__ G, int ld, int col0, __half* __restrict__ out, int cols,
-                               int L, int halo) {
+// block = (32 columns) x (8 row lanes), grid = (sequences, column groups): row lane y sums frames y, y+8, ... (four loads in
+// flight), the 8 partial sums are added in lane order -- a fixed summation order, so the result is reproducible
+__global__ void __launch_bounds__(256)
+seq_sum_kernel(const __half* __restrict__ G, int ld, int col0, __half* __restrict__ out, int cols, int L, int halo) {
+  __shared__ float part[8][33];
   const int s = blockIdx.x;
   const int blk = L + 2 * halo;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    float acc = 0.f;
-    for (int t = 0; t < L; ++t) acc += __half2float(G[((size_t)s * blk + halo + t) * ld + col0 + c]);
-    out[(size_t)s * cols + c] = __float2half_rn(acc);
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols) {
+    const __half* g = G + ((size_t)s * blk + halo) * ld + col0 + c;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int t = threadIdx.y;
+    for (; t + 24 < L; t += 32) {
+      a0 += __half2float(g[(size_t)t * ld]); a1 += __half2float(g[(size_t)(t + 8) * ld]);
+      a2 += __half2float(g[(size_t)(t + 16) * ld]); a3 += __half2float(g[(size_t)(t + 24) * ld]);
+    }
+    for (; t < L; t += 8) a0 += __half2float(g[(size_t)t * ld]);
+    acc = (a0 + a1) + (a2 + a3);
+  }
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float tot = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += part[y][threadIdx.x];
+    out[(size_t)s * cols + c] = __float2half_rn(tot);
   }
 }
 __global__ void zero_halo_kernel(__half* __restrict__ X, int ld, int n_seq, int L, int cols, int halo) {
@@ -842,6 +941,40 @@ __global__ void zero_halo_kernel(__half* __restrict__ X, int ld, int n_seq, int 
     const int hr = (int)(rem / cols), c = (int)(rem % cols);
     const size_t row = (size_t)s * blk + (hr < halo ? hr : L + hr);
     X[row * ld + c] = __float2half(0.f);
+  }
+}
+// SpecAugment on the padded minibatch layout (go/gotorch/cnn_tdnn.go:612-668 SpecAugment.Apply: per sequence, frequency
+// masks [f0, f0+f) over every frame and time masks [t0, t0+t) over every bin, masked value 0), with a counter-based
+// generator instead of math/rand: draw k of sequence s is u(seed, s, k) (the hash the dropout epilogue uses), so the masks
+// are a pure function of (seed, sequence) -- the backward pass and the CPU oracle rebuild them.
+//   frequency mask m:  f = floor(u(4m) * (fmax + 1)),   f0 = floor(u(4m+1) * (dim - f + 1))
+//   time mask m:       t = floor(u(4m+2) * (tmax + 1)), t0 = floor(u(4m+3) * (L - t + 1))
+// y = x outside the masks (x == y allowed: in place); halo rows are copied through.
+__global__ void spec_augment_kernel(const __half* __restrict__ x, __half* __restrict__ y, int ld, int L, int halo, int dim,
+                                    int fmax, int nfreq, int tmax, int ntime, uint32_t seed, const uint32_t* __restrict__ seed_dev) {
+  __shared__ int f_lo[8], f_hi[8], t_lo[8], t_hi[8];
+  const int s = blockIdx.x;
+  if (threadIdx.x < 8) {
+    const uint32_t sd = seed ^ (seed_dev ? *seed_dev : 0u);
+    const int m = threadIdx.x;
+    const int f = m < nfreq ? (int)(dropout_uniform(sd, (uint32_t)s, 4u * m) * (float)(fmax + 1)) : 0;
+    const int f0 = (int)(dropout_uniform(sd, (uint32_t)s, 4u * m + 1u) * (float)(dim - f + 1));
+    const int t = m < ntime ? (int)(dropout_uniform(sd, (uint32_t)s, 4u * m + 2u) * (float)(tmax + 1)) : 0;
+    const int t0 = (int)(dropout_uniform(sd, (uint32_t)s, 4u * m + 3u) * (float)(L - t + 1));
+    f_lo[m] = f0; f_hi[m] = f0 + f; t_lo[m] = t0; t_hi[m] = t0 + t;
+  }
+  __syncthreads();
+  const int blk = L + 2 * halo;
+  const size_t base = (size_t)s * blk * ld;
+  for (int i = threadIdx.x; i < blk * dim; i += blockDim.x) {
+    const int r = i / dim, c = i - r * dim;
+    const int tt = r - halo;
+    bool masked = false;
+    if (tt >= 0 && tt < L) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) masked = masked || (c >= f_lo[m] && c < f_hi[m]) || (tt >= t_lo[m] && tt < t_hi[m]);
+    }
+    y[base + (size_t)r * ld + c] = masked ? __float2half(0.f) : x[base + (size_t)r * ld + c];
   }
 }
 // strided-row form of scale_shift_kernel, 8 columns per thread (cols % 8 == 0, 16-byte aligned rows)
@@ -1173,6 +1306,42 @@ int kfp16_bn_fold(kfp16_ctx* ctx, const float* mean, const float* var, const flo
   count_launch();
   return check_launch("kfp16_bn_fold") ? 0 : -1;
 }
+int kfp16_bn_batch_stats(kfp16_ctx* ctx, const void* X, int ld, int rows, int cols, float* stats, int period, int lo, int len) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!X || !stats || (cols % 8) || (ld % 8) || !al16(X) || !al16(stats)) { set_error("kfp16_bn_batch_stats: needs 16-byte aligned buffers and cols / ld %% 8 == 0"); return -1; }
+  if (period < 0 || lo < 0 || len < 0 || (period > 0 && lo + len > period)) { set_error("kfp16_bn_batch_stats: bad row filter"); return -1; }
+  cudaStream_t s = ctx_stream(ctx);
+  if (!check_cuda(cudaMemsetAsync(stats, 0, (size_t)2 * cols * sizeof(float), s), "kfp16_bn_batch_stats memset")) return -1;
+  const int gx = (cols + 255) / 256;
+  int gy = (num_sms_cached() * 4) / gx;
+  const int max_gy = (rows + 63) / 64;
+  if (gy > max_gy) gy = max_gy;
+  if (gy < 1) gy = 1;
+  bn_stats_kernel<<<dim3(gx, gy), dim3(32, 8), 0, s>>>((const __half*)X, ld, (uint32_t)rows, cols, stats, (uint32_t)period, (uint32_t)lo, (uint32_t)len);
+  count_launch();
+  return check_launch("kfp16_bn_batch_stats") ? 0 : -1;
+}
+int kfp16_bn_finalize(kfp16_ctx* ctx, const float* stats, double n_rows, int D, float* run_mean, float* run_var, const float* gamma,
+                      const float* beta, float eps, float target_rms, float momentum, float bwd_mul, float* scale, float* shift,
+                      float* scale_bwd) {
+  if (D <= 0) return 0;
+  if (!stats || !run_mean || !run_var || !scale || !shift || n_rows < 1) { set_error("kfp16_bn_finalize: null pointer / empty batch"); return -1; }
+  bn_finalize_kernel<<<(D + 255) / 256, 256, 0, ctx_stream(ctx)>>>(stats, (float)n_rows, D, run_mean, run_var, gamma, beta, eps, target_rms, momentum,
+                                                                  bwd_mul, scale, shift, scale_bwd);
+  count_launch();
+  return check_launch("kfp16_bn_finalize") ? 0 : -1;
+}
+int kfp16_bn_apply(kfp16_ctx* ctx, void* Z, int ld, const float* scale, const float* shift, const void* R, int ldr, float res_scale, int rows,
+                   int cols, int col_mod, int period, int lo, int len) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!Z || !scale || !shift || (cols % 8) || (ld % 8) || !al16(Z) || (R && ((ldr % 8) || !al16(R))) || col_mod < 8 || (col_mod % 8)) {
+    set_error("kfp16_bn_apply: needs 16-byte aligned buffers and cols / ld / col_mod %% 8 == 0"); return -1;
+  }
+  bn_apply_kernel<<<grid_for((size_t)rows * (cols / 8)), kThreads, 0, ctx_stream(ctx)>>>((__half*)Z, ld, scale, shift, (const __half*)R, ldr, res_scale,
+                                                                                        (uint32_t)rows, cols, col_mod, (uint32_t)period, (uint32_t)lo, (uint32_t)len);
+  count_launch();
+  return check_launch("kfp16_bn_apply") ? 0 : -1;
+}
 int kfp16_bn_relu_backward(kfp16_ctx* ctx, const void* dY, int ldy, const float* scale, const uint32_t* mask,
                            int mask_ld, void* dZ, int ldz, int rows, int cols) {
   if (rows <= 0 || cols <= 0) return 0;
@@ -1331,7 +1500,7 @@ int kfp16_seq_sum(kfp16_ctx* ctx, const void* G, int ld, int col0, void* out, in
                   int halo) {
   if (n_seq <= 0 || cols <= 0) return 0;
   if (!G || !out) { set_error("kfp16_seq_sum: null pointer"); return -1; }
-  seq_sum_kernel<<<n_seq, 256, 0, ctx_stream(ctx)>>>((const __half*)G, ld, col0, (__half*)out, cols, seq_len, halo);
+  seq_sum_kernel<<<dim3(n_seq, (cols + 31) / 32), dim3(32, 8), 0, ctx_stream(ctx)>>>((const __half*)G, ld, col0, (__half*)out, cols, seq_len, halo);
   count_launch();
   return check_launch("kfp16_seq_sum") ? 0 : -1;
 }
@@ -1349,6 +1518,18 @@ int kfp16_scale_shift(kfp16_ctx* ctx, const void* x, void* y, int rows, int cols
   scale_shift_kernel<<<grid_for((size_t)rows * cols), kThreads, 0, ctx_stream(ctx)>>>((const __half*)x, (__half*)y, (size_t)rows * cols, cols, scale, shift);
   count_launch();
   return check_launch("kfp16_scale_shift") ? 0 : -1;
+}
+int kfp16_spec_augment(kfp16_ctx* ctx, const void* x, void* y, int ld, int n_seq, int seq_len, int halo, int dim, int fmax, int nfreq,
+                       int tmax, int ntime, uint32_t seed, const uint32_t* seed_dev) {
+  if (n_seq <= 0 || dim <= 0) return 0;
+  if (!x || !y) { set_error("kfp16_spec_augment: null pointer"); return -1; }
+  if (nfreq < 0 || nfreq > 8 || ntime < 0 || ntime > 8 || fmax < 0 || fmax > dim || tmax < 0 || tmax > seq_len) {
+    set_error("kfp16_spec_augment: up to 8 masks of each kind, widths within the matrix (fmax %d of %d, tmax %d of %d)", fmax, dim, tmax, seq_len);
+    return -1;
+  }
+  spec_augment_kernel<<<n_seq, 256, 0, ctx_stream(ctx)>>>((const __half*)x, (__half*)y, ld, seq_len, halo, dim, fmax, nfreq, tmax, ntime, seed, seed_dev);
+  count_launch();
+  return check_launch("kfp16_spec_augment") ? 0 : -1;
 }
 int kfp16_scale_shift_ld(kfp16_ctx* ctx, const void* x, long long ldx, void* y, long long ldy, int rows, int cols,
                          const float* scale, const float* shift) {

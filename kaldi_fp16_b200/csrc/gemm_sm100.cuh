@@ -157,12 +157,8 @@ struct GemmParams {
   long long* dbg;               // profiling: per-CTA role timestamps [grid][3 roles][8 tiles][16] (nullptr = off)
 };
 
-// counter-based uniform in [0,1): the same integer hash is restated in the CPU oracle (oracle/kaldi_oracle.py::dropout_uniform)
-__host__ __device__ inline float dropout_uniform(uint32_t seed, uint32_t row, uint32_t col) {
-  uint32_t x = seed ^ (row * 0x9E3779B1u) ^ (col * 0x85EBCA77u);
-  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return (float)(x >> 8) * (1.0f / 16777216.0f);
-}
+// (dropout_uniform, the counter-based generator of the dropout masks, lives in sm100_ptx.cuh: elementwise.cu draws the
+//  SpecAugment masks from it too)
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;

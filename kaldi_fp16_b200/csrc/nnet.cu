@@ -47,6 +47,7 @@ struct BNorm {
   float *mean = nullptr, *var = nullptr, *gamma = nullptr, *beta = nullptr;   // fp32 [dim]
   float *scale = nullptr, *shift = nullptr, *zero = nullptr;                  // folded; zero = [dim] of 0
   float *scale_bwd = nullptr;   // scale * bwd_mul: the backward pass's factor (dropout folds 1/(1-p) in here)
+  float *one = nullptr;         // [dim] of 1: identity scale for the producing epilogue when the batch-norm runs in train mode
   float bwd_mul = 1.0f;
   // conv layers (per-filter batch-norm): scale repeated for every output height, and as many zeros -- the vectors a consumer
   // that sees the layer output as [frames x heights*filters] passes to its input-gradient epilogue
@@ -119,6 +120,8 @@ struct Layer {
   // training step with a subsampled objective: this layer's output is only read on rows f_row0 + k*f_sub (it is row-wise
   // and feeds nothing but the objective's output layer through row-wise layers), so the step computes just those rows
   int f_sub = 1, f_row0 = 0;
+  // spec-augment-layer (training, kfp16_net_set_spec_augment): mask geometry derived from the xconfig values
+  int sa_fmax = 0, sa_nfreq = 0, sa_tmax = 0, sa_ntime = 0;
   double fl_fwd = 0, fl_bwd = 0;   // GEMM flops of this layer over all rows (row-wise layer types only)
 };
 
@@ -170,6 +173,15 @@ struct kfp16_net {
   bool sparse_out_grad = true;          // kfp16_net_set_sparse_output_grad
   double flops_fwd_skipped = 0, flops_bwd_skipped = 0;   // of flops_fwd / flops_bwd, not executed by the last training step (rows outside the objective's frames)
   // the objective runs on a second stream beside the forward pass of the layers it does not depend on (xent branch)
+  // train-mode batch-norm (kfp16_net_set_train_batchnorm): batch statistics instead of the stored running statistics
+  bool train_bn = false;
+  float bn_momentum = 0.1f;
+  int bn_world = 1;                     // ranks whose statistics the hook sums (global row count = local rows * bn_world)
+  kfp16_bn_stats_hook bn_hook = nullptr;
+  void* bn_hook_user = nullptr;
+  float* bn_stats = nullptr;            // [2 x widest batch-norm] fp32 scratch
+  size_t bn_stats_dim = 0;
+  bool spec_augment = false;            // kfp16_net_set_spec_augment: spec-augment-layer masks in training (off = the reference's pass-through)
   bool overlap_loss = true;             // kfp16_net_set_overlap_loss
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -305,7 +317,7 @@ bool make_bn(kfp16_net* n, BNorm& bn, int dim, float target_rms, bool rms_only) 
   bn.target_rms = target_rms;
   bn.rms_only = rms_only;
   float* base = nullptr;
-  if (!dev_alloc(n, (void**)&base, (size_t)dim * 8 * sizeof(float))) return false;
+  if (!dev_alloc(n, (void**)&base, (size_t)dim * 9 * sizeof(float))) return false;
   bn.mean = base;
   bn.var = base + dim;
   bn.gamma = base + 2 * dim;
@@ -314,6 +326,13 @@ bool make_bn(kfp16_net* n, BNorm& bn, int dim, float target_rms, bool rms_only) 
   bn.shift = base + 5 * dim;
   bn.zero = base + 6 * dim;
   bn.scale_bwd = base + 7 * dim;
+  bn.one = base + 8 * dim;
+  {
+    std::vector<float> ones((size_t)dim, 1.f);
+    if (!check_cuda(cudaMemcpyAsync(bn.one, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice, n->ctx->stream), "bn ones upload") ||
+        !check_cuda(cudaStreamSynchronize(n->ctx->stream), "bn ones sync")) return false;
+  }
+  if ((size_t)dim > n->bn_stats_dim) n->bn_stats_dim = (size_t)dim;
   std::vector<float> h((size_t)dim * 4, 0.f);   // identity: mean 0, var 1, gamma 1, beta 0
   for (int i = 0; i < dim; ++i) { h[dim + i] = 1.f; h[2 * dim + i] = 1.f; }
   if (!check_cuda(cudaMemcpyAsync(base, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, n->ctx->stream), "bn upload")) return false;
@@ -465,9 +484,20 @@ bool resolve_dims(kfp16_net* n) {
         l.out_dim = kv_int(l, "dim", 0);
         if (l.out_dim <= 0) { set_error("linear-component %s missing dim", l.name.c_str()); return false; }
         break;
-      case L_BATCHNORM: case L_SPECAUG:
+      case L_BATCHNORM:
         l.out_dim = l.in_dim;
         break;
+      case L_SPECAUG: {   // internal/nnet/layers.go:231-240: freq-max-proportion 0.5, time-zeroed-proportion 0, time-mask-max-frames 20
+        l.out_dim = l.in_dim;
+        const double fprop = kv_float(l, "freq-max-proportion", 0.5), tprop = kv_float(l, "time-zeroed-proportion", 0.0);
+        const int tmax = std::min(kv_int(l, "time-mask-max-frames", 20), n->opts.seq_len);
+        l.sa_fmax = std::max(0, std::min(l.in_dim, (int)(fprop * l.in_dim)));
+        l.sa_nfreq = l.sa_fmax > 0 ? 1 : 0;
+        l.sa_tmax = std::max(0, tmax);
+        // masks of mean width tmax/2 until the requested proportion of the frames is zeroed on average
+        l.sa_ntime = (tprop > 0 && tmax > 0) ? std::min(8, std::max(1, (int)(tprop * n->opts.seq_len / (0.5 * tmax) + 0.5))) : 0;
+        break;
+      }
       case L_COMBINE:
         l.out_dim = l.in_dim;
         l.height = kv_int(l, "height", 0);
@@ -1007,6 +1037,27 @@ Buf dx_target(kfp16_net* n, Layer& l) {
 
 const Buf& layer_input(kfp16_net* n, Layer& l) { return l.in.size() > 1 ? l.in_cat : n->layers[l.in[0]].out; }
 
+// Train-mode batch-norm around a producing GEMM: Z (the GEMM's output through an identity batch-norm, i.e. ReLU(XW + b) or
+// XW) -> batch statistics over the minibatch's rows -> [data-parallel hook: sum over ranks] -> folded scale / shift + running
+// statistics -> Z = Z*scale + shift (+ bypass*R) in place.  hmul = heights per frame of a conv activation (1 otherwise);
+// the backward pass then uses the batch-derived scale exactly as the reference's (simplified) BatchNorm backward does
+// (go/gotorch/layers.go:302-330: gradInput = gradOutput * gamma * invStd).
+bool train_bn_on(const kfp16_net* n) { return n->train_bn && n->g32 != nullptr; }
+int train_bn_pass(kfp16_net* n, BNorm& bn, __half* Z, int ld, int rows, int cols, int hmul, const __half* R, int ldr, float res_scale, bool apply) {
+  kfp16_ctx* ctx = n->ctx;
+  if (!n->bn_stats) { set_error("internal: no batch-norm statistics buffer"); return -1; }
+  const int period = n->blk * hmul, lo = n->halo * hmul, len = n->opts.seq_len * hmul;
+  // a conv activation [frames*heights x filters] has one statistic per filter; its rows are folded so that the kernel sees
+  // whole 16-byte column groups of at least 8 filters (cols == bn.dim there, so nothing to fold)
+  if (kfp16_bn_batch_stats(ctx, Z, ld, rows, cols, n->bn_stats, period, lo, len)) return -1;
+  if (n->bn_hook && n->bn_hook(n->bn_hook_user, n->bn_stats, 2 * cols, (void*)ctx->stream)) { set_error("batch-norm statistics hook failed"); return -1; }
+  const double n_rows = (double)n->opts.n_seq * n->opts.seq_len * hmul * n->bn_world;
+  if (kfp16_bn_finalize(ctx, n->bn_stats, n_rows, cols, bn.mean, bn.var, bn.rms_only ? nullptr : bn.gamma, bn.rms_only ? nullptr : bn.beta, bn.eps,
+                        bn.target_rms, n->bn_momentum, bn.bwd_mul, bn.scale, bn.shift, bn.scale_bwd)) return -1;
+  if (apply && kfp16_bn_apply(ctx, Z, ld, bn.scale, bn.shift, R, ldr, res_scale, rows, cols, cols, period, lo, len)) return -1;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ forward
 int fix_halo(kfp16_net* n, Layer& l, Buf& b, int mode) {
   if (l.per_seq || n->halo == 0) return 0;
@@ -1055,10 +1106,14 @@ int forward_layer(kfp16_net* n, Layer& l) {
       break;
     }
     case L_BATCHNORM:   // forward.go:349-374
+      if (train_bn_on(n) && !l.per_seq && train_bn_pass(n, l.bn, X.p, X.cols, rows, l.out_dim, 1, nullptr, 0, 0.f, false)) return -1;
       if (kfp16_scale_shift(ctx, X.p, l.out.p, rows, l.out_dim, l.bn.scale, l.bn.shift)) return -1;
       break;
-    case L_SPECAUG:     // pass-through (forward.go:377-383)
-      if (!check_cuda(cudaMemcpyAsync(l.out.p, X.p, l.out.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "spec-augment copy")) return -1;
+    case L_SPECAUG:     // pass-through in the reference (forward.go:377-383, a TODO); masks when switched on for training
+      if (n->spec_augment && n->g32 && !l.per_seq) {
+        if (kfp16_spec_augment(ctx, X.p, l.out.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, n->halo, l.out_dim, l.sa_fmax, l.sa_nfreq, l.sa_tmax,
+                               l.sa_ntime, (uint32_t)(&l - n->layers.data()) * 0x9E3779B9u, n->seed_dev)) return -1;
+      } else if (!check_cuda(cudaMemcpyAsync(l.out.p, X.p, l.out.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "spec-augment copy")) return -1;
       break;
     case L_COMBINE:     // forward.go:386-405
       if (!check_cuda(cudaMemcpyAsync(l.out.p, X.p, l.out.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "combine copy")) return -1;
@@ -1087,6 +1142,14 @@ int forward_layer(kfp16_net* n, Layer& l) {
         d.bias = W16(n, l.pAffB);
         d.bn_scale = l.bn.scale; d.bn_shift = l.bn.shift;
         d.mask_out = l.mask; d.mask_ld = l.mask_ld;
+        const bool tbn = train_bn_on(n);
+        if (tbn && l.dropout_p > 0.f) { set_error("layer %s: dropout-proportion together with train-mode batch-norm is not supported", l.name.c_str()); return -1; }
+        if (tbn) {   // identity batch-norm in the epilogue (Z = ReLU(.)), statistics + normalisation + bypass in train_bn_pass
+          d.bn_scale = l.bn.one; d.bn_shift = l.bn.zero;
+          if (kfp16_gemm_ex(ctx, &d)) return -1;
+          if (train_bn_pass(n, l.bn, l.out.p, l.out_dim, rows, l.out_dim, 1, l.use_bypass ? X.p : nullptr, l.in_dim, l.bypass, true)) return -1;
+          break;
+        }
         if (l.use_bypass) { d.flags |= KFP16_EPI_RESID; d.R[0] = X.p; d.ldr = l.in_dim; d.res_scale = l.bypass; }
         if (l.dropout_p > 0.f) {   // training: inverted dropout after the batch-norm (go/gotorch/layers.go:365-399), per-step seed word
           d.flags |= KFP16_EPI_DROPOUT;
@@ -1108,14 +1171,19 @@ int forward_layer(kfp16_net* n, Layer& l) {
       d.bias = W16(n, l.pBigB);
       d.bn_scale = l.bn.scale; d.bn_shift = l.bn.shift;
       d.mask_out = l.mask + (size_t)fr0 * l.mask_ld; d.mask_ld = l.mask_ld * fsub;
+      const bool tbn = train_bn_on(n) && fsub == 1;      // (plan_forward_rows leaves every row in place in train-BN mode)
+      if (tbn) { d.bn_scale = l.bn.one; d.bn_shift = l.bn.zero; }
       if (kfp16_gemm_ex(ctx, &d)) return -1;
+      if (tbn && train_bn_pass(n, l.bn, l.big.p, l.big_dim, rows, l.big_dim, 1, nullptr, 0, 0.f, true)) return -1;
       kfp16_gemm_desc e = mk_desc(vrows, l.small_dim, l.big_dim);
       set_A(e, bigv);
       set_B(e, W16(n, l.pSmall), l.big_dim, l.small_dim);
       e.D[0] = Yv.p; e.ldd = Yv.LD();
       e.flags = KFP16_EPI_BN | rr;
       e.bn_scale = l.bn2.scale; e.bn_shift = l.bn2.shift;
+      if (tbn) { e.bn_scale = l.bn2.one; e.bn_shift = l.bn2.zero; }
       if (kfp16_gemm_ex(ctx, &e)) return -1;
+      if (tbn && train_bn_pass(n, l.bn2, l.out.p, l.small_dim, rows, l.small_dim, 1, nullptr, 0, 0.f, true)) return -1;
       break;
     }
     case L_CONV: {       // forward.go:418-524 with the im2col on the device; Z = BN(ReLU(P*W + b)) per filter
@@ -1135,11 +1203,15 @@ int forward_layer(kfp16_net* n, Layer& l) {
       d.bias = W16(n, l.pB);
       d.bn_scale = l.bn.scale; d.bn_shift = l.bn.shift;
       d.mask_out = l.mask; d.mask_ld = l.mask_ld;
+      const bool tbn = train_bn_on(n);
+      if (tbn) { d.bn_scale = l.bn.one; d.bn_shift = l.bn.zero; }
       if (n->halo > 0) {   // halo rows of the output (and their mask bits) are written as zeros by the epilogue: they are the
         // next convolution's zero padding in time, and a zero mask keeps their gradients out of the backward pass
         d.zero_row_period = n->blk * l.hout; d.zero_row_lo = n->halo * l.hout; d.zero_row_hi = (n->halo + n->opts.seq_len) * l.hout;
       }
       if (kfp16_gemm_ex(ctx, &d)) return -1;
+      // per-filter statistics over every (frame, height) of the minibatch; the halo rows stay zero
+      if (tbn && train_bn_pass(n, l.bn, l.out.p, l.fout, mrows, l.fout, l.hout, nullptr, 0, 0.f, true)) return -1;
       break;
     }
     case L_OUTPUT: {     // forward.go:971-1001
@@ -1173,7 +1245,7 @@ bool fuse_conv_dz(kfp16_net* n, Layer& l, const Buf& dx, kfp16_gemm_desc& d, int
   if (s.type != L_CONV || !s.needs_grad || s.n_grad_consumers != 1 || dx.p != s.dout.p || !s.mask) return false;
   const float *scale, *zero;
   if (ncols == s.fout) { scale = s.bn.scale; zero = s.bn.zero; }
-  else if (ncols == s.fout * s.bn.tiles && s.bn.scale_tiled) { scale = s.bn.scale_tiled; zero = s.bn.zero_tiled; }
+  else if (ncols == s.fout * s.bn.tiles && s.bn.scale_tiled && !train_bn_on(n)) { scale = s.bn.scale_tiled; zero = s.bn.zero_tiled; }   // (the tiled copy follows kfp16_net_set_bn only)
   else return false;
   d.flags |= KFP16_EPI_BN | KFP16_EPI_GRADMASK | (n->opts.ref_round ? KFP16_EPI_REF_ROUND : 0);
   d.bn_scale = scale; d.bn_shift = zero;
@@ -1228,8 +1300,11 @@ int backward_layer(kfp16_net* n, Layer& l) {
       if (l.wants_dx && sub > 1 && kfp16_scale_shift_ld(ctx, dYv.p, dYv.LD(), dxv.p, dxv.LD(), rows, l.out_dim, l.bn.scale, nullptr)) return -1;
       if (l.wants_dx && sub <= 1 && kfp16_scale_shift(ctx, l.dout.p, dx.p, rows, l.out_dim, l.bn.scale, nullptr)) return -1;
       break;
-    case L_SPECAUG:
-      if (l.wants_dx && !check_cuda(cudaMemcpyAsync(dx.p, l.dout.p, l.dout.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "spec-augment grad")) return -1;
+    case L_SPECAUG:     // the same masks on the gradient
+      if (l.wants_dx && n->spec_augment && !l.per_seq) {
+        if (kfp16_spec_augment(ctx, l.dout.p, dx.p, l.out_dim, n->opts.n_seq, n->opts.seq_len, n->halo, l.out_dim, l.sa_fmax, l.sa_nfreq, l.sa_tmax,
+                               l.sa_ntime, (uint32_t)(&l - n->layers.data()) * 0x9E3779B9u, n->seed_dev)) return -1;
+      } else if (l.wants_dx && !check_cuda(cudaMemcpyAsync(dx.p, l.dout.p, l.dout.bytes(), cudaMemcpyDeviceToDevice, ctx->stream), "spec-augment grad")) return -1;
       break;
     case L_COMBINE:     // inverse permutation
       if (l.wants_dx) {
@@ -1412,6 +1487,7 @@ bool chain_by_rows(const kfp16_net* n, int layer, int sub, int frames) {
 void plan_forward_rows(kfp16_net* n) {
   for (auto& l : n->layers) { l.f_sub = 1; l.f_row0 = 0; }
   n->flops_fwd_skipped = 0;
+  if (train_bn_on(n)) return;      // batch statistics are taken over every real row of the minibatch
   if (!n->chain || n->out_layer < 0 || !chain_by_rows(n, n->out_layer, n->chain_sub, kfp16_chain_frames(n->chain))) return;
   const int L = (int)n->layers.size();
   std::vector<int> consumers(L, 0), restricted(L, 0);
@@ -1582,6 +1658,19 @@ int kfp16_net_set_param(kfp16_net* n, const char* name, const float* host, int r
     if (!check_cuda(cudaMemset(n->vel + P.off, 0, cnt * 4), "velocity reset")) return -1;
   }
   return 0;
+}
+// idct-layer: replace the computed matrix (makeIDCTMatrix, forward.go:1190-1210) by a loaded one -- Kaldi's `idct` component
+// through the truncating converter, as LoadWeights does (weight_loader.go:766-776).  host: fp32 [dim x dim], [in x out].
+int kfp16_net_set_idct(kfp16_net* n, const char* layer, const float* host, int dim) {
+  if (!n || !layer || !host) { set_error("kfp16_net_set_idct: null argument"); return -1; }
+  const int i = find_layer(n, layer);
+  if (i < 0 || n->layers[i].type != L_IDCT) { set_error("kfp16_net_set_idct: no idct-layer named %s", layer); return -1; }
+  Layer& l = n->layers[i];
+  if (dim != l.in_dim) { set_error("kfp16_net_set_idct: %s is [%d x %d], got dim %d", layer, l.in_dim, l.out_dim, dim); return -1; }
+  std::vector<uint16_t> h16((size_t)dim * dim);
+  for (size_t k = 0; k < h16.size(); ++k) h16[k] = f32_to_f16_trunc(host[k]);
+  if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "sync")) return -1;
+  return check_cuda(cudaMemcpy(l.idct_mat, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice), "idct upload") ? 0 : -1;
 }
 int kfp16_net_get_param(kfp16_net* n, const char* name, uint16_t* host, int rows, int cols) {
   if (!n || !name || !host) { set_error("kfp16_net_get_param: null argument"); return -1; }
@@ -1889,6 +1978,41 @@ int kfp16_net_loss_chain(kfp16_net* n, const char* layer, kfp16_chain* chain, in
   } else if (!check_cuda(cudaMemsetAsync(l.dout.p, 0, l.dout.bytes(), n->ctx->stream), "chain gradient clear")) return -1;
   return kfp16_chain_loss(chain, l.out.p, l.dout.p, l.out_dim, n->blk, row0, subsampling, weight, n->loss_dev);
 }
+int kfp16_net_set_train_batchnorm(kfp16_net* n, int on, float momentum) {
+  if (!n) { set_error("kfp16_net_set_train_batchnorm: null network"); return -1; }
+  if (on && !n->g32) { set_error("kfp16_net_set_train_batchnorm: network was created with train = 0"); return -1; }
+  if (on && !(momentum >= 0.f && momentum <= 1.f)) { set_error("kfp16_net_set_train_batchnorm: momentum must be in [0, 1]"); return -1; }
+  if (on && !n->bn_stats) {
+    if (!check_cuda(cudaMalloc((void**)&n->bn_stats, std::max<size_t>(n->bn_stats_dim, 8) * 2 * sizeof(float)), "batch-norm statistics buffer")) return -1;
+    n->allocs.push_back(n->bn_stats);
+  }
+  n->train_bn = on != 0;
+  if (on) n->bn_momentum = momentum;
+  return 0;
+}
+int kfp16_net_set_bn_stats_hook(kfp16_net* n, kfp16_bn_stats_hook hook, void* user, int world) {
+  if (!n || world < 1) { set_error("kfp16_net_set_bn_stats_hook: bad argument"); return -1; }
+  n->bn_hook = hook; n->bn_hook_user = user; n->bn_world = hook ? world : 1;
+  return 0;
+}
+int kfp16_net_get_bn(kfp16_net* n, const char* layer, const char* which, float* mean, float* var, int dim) {
+  if (!n || !layer || !mean || !var) { set_error("kfp16_net_get_bn: null argument"); return -1; }
+  const int i = find_layer(n, layer);
+  if (i < 0) { set_error("kfp16_net_get_bn: no layer %s", layer); return -1; }
+  Layer& l = n->layers[i];
+  BNorm* bn = &l.bn;
+  if (which && (!strcmp(which, "BN") || !strcmp(which, "bn2")) && l.type == L_PREFINAL) bn = &l.bn2;
+  if (!bn->present || bn->dim != dim) { set_error("kfp16_net_get_bn: layer %s has no batch-norm of dim %d", layer, dim); return -1; }
+  if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "sync")) return -1;
+  return check_cuda(cudaMemcpy(mean, bn->mean, (size_t)dim * 4, cudaMemcpyDeviceToHost), "bn mean download") &&
+         check_cuda(cudaMemcpy(var, bn->var, (size_t)dim * 4, cudaMemcpyDeviceToHost), "bn var download") ? 0 : -1;
+}
+int kfp16_net_set_spec_augment(kfp16_net* n, int on) {
+  if (!n) { set_error("kfp16_net_set_spec_augment: null network"); return -1; }
+  if (on && !n->g32) { set_error("kfp16_net_set_spec_augment: network was created with train = 0"); return -1; }
+  n->spec_augment = on != 0;
+  return 0;
+}
 int kfp16_net_set_overlap_loss(kfp16_net* n, int on) {
   if (!n) { set_error("kfp16_net_set_overlap_loss: null network"); return -1; }
   n->overlap_loss = on != 0;
@@ -2040,6 +2164,7 @@ int kfp16_net_capture(kfp16_net* n, int phases) {
   if (!n || phases < 1 || phases > 15) { set_error("kfp16_net_capture: phases is a bitmask of 1 (step), 2 (SGD), 4 (FP16 gradient export), 8 (SGD from FP16 gradients)"); return -1; }
   if (!n->ctx->stream) { set_error("kfp16_net_capture: graph capture needs a non-default stream (kfp16_ctx_set_stream)"); return -1; }
   if ((phases & ~1) && !n->g32) { set_error("kfp16_net_capture: network was created with train = 0"); return -1; }
+  if ((phases & 1) && n->train_bn && n->bn_hook) { set_error("kfp16_net_capture: a host hook sums the batch-norm statistics over the ranks between kernels -- run the step eagerly (kfp16_net_forward / loss / backward)"); return -1; }
   cudaStream_t st = n->ctx->stream;
   // One eager pass first: kernel attributes (dynamic shared memory opt-in) and the grouped weight-gradient tables are
   // set up outside the capture.  Its side effects on the training state are undone: master / FP16 weights, velocities,

@@ -82,3 +82,22 @@ class GradAllReducer:
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
+
+
+class BNStatsAllReducer:
+    """Cross-rank sum of the batch-norm statistics (train-mode batch-norm): plugged into the executor with
+    Network.SetBNStatsHook(reducer, reducer.world).  The executor calls it between the statistics pass and the finalize
+    pass of every batch-norm with the device address of the fp32 [sum | sum of squares] vector; `as_tensor(ptr, count)`
+    must return a torch tensor aliasing that memory (CUDA: torch.as_tensor over __cuda_array_interface__)."""
+
+    def __init__(self, as_tensor, group=None):
+        import torch.distributed as dist
+
+        self.dist, self.group, self.as_tensor = dist, group, as_tensor
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.calls = 0
+
+    def __call__(self, ptr: int, count: int, stream: int) -> None:
+        self.calls += 1
+        if self.world > 1:
+            self.dist.all_reduce(self.as_tensor(ptr, count), op=self.dist.ReduceOp.SUM, group=self.group)

@@ -117,6 +117,46 @@ class Network:
                                      eps, mean.size) != 0:
             raise _err("SetBN")
 
+    def SetIDCT(self, layer: str, m: np.ndarray) -> None:
+        """idct-layer matrix [in x out] from a loaded model (weight_loader.go:766-776) instead of makeIDCTMatrix"""
+        m = np.ascontiguousarray(m, dtype=np.float32)
+        if m.ndim != 2 or m.shape[0] != m.shape[1] or self.lib.kfp16_net_set_idct(self.ptr, layer.encode(), m.ctypes.data, m.shape[0]) != 0:
+            raise _err("SetIDCT")
+
+    def GetBN(self, layer: str, which: str, dim: int):
+        """running mean / variance of a batch-norm (what train-mode batch-norm updates)"""
+        mean, var = np.empty(dim, np.float32), np.empty(dim, np.float32)
+        if self.lib.kfp16_net_get_bn(self.ptr, layer.encode(), which.encode(), mean.ctypes.data, var.ctypes.data, dim) != 0:
+            raise _err("GetBN")
+        return mean, var
+
+    def SetTrainBatchNorm(self, on: bool, momentum: float = 0.1) -> None:
+        """batch statistics instead of running statistics in every batch-norm of a training network
+        (cpp/cuda/cnn_kernels.cu:236-320 training branch, go/gotorch/layers.go:257-330)"""
+        if self.lib.kfp16_net_set_train_batchnorm(self.ptr, 1 if on else 0, float(momentum)) != 0:
+            raise _err("SetTrainBatchNorm")
+
+    def SetBNStatsHook(self, fn, world: int) -> None:
+        """data-parallel batch-norm: fn(stats_ptr: int, count: int, stream_ptr: int) must sum the fp32 device vector over the
+        `world` ranks, stream-ordered; fn = None removes the hook (see dp.BNStatsAllReducer)"""
+        if fn is None:
+            self._bn_hook = None
+            rc = self.lib.kfp16_net_set_bn_stats_hook(self.ptr, None, None, 1)
+        else:
+            proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+
+            def tramp(_user, stats, count, stream):
+                try:
+                    fn(int(stats or 0), int(count), int(stream or 0))
+                    return 0
+                except Exception:  # noqa: BLE001 - reported through the C error path
+                    return -1
+
+            self._bn_hook = proto(tramp)          # keep the callback alive
+            rc = self.lib.kfp16_net_set_bn_stats_hook(self.ptr, C.cast(self._bn_hook, C.c_void_p), None, int(world))
+        if rc != 0:
+            raise _err("SetBNStatsHook")
+
     def _bucket_f32(self, getter) -> np.ndarray:
         n = self.lib.kfp16_net_bucket_size(self.ptr)
         out = np.empty(n, dtype=np.float32)
@@ -310,6 +350,15 @@ class Network:
         behind the output (default on; same results as the dense form)"""
         if self.lib.kfp16_net_set_sparse_output_grad(self.ptr, 1 if on else 0) != 0:
             raise _err("SetSparseOutputGrad")
+
+    def SetSpecAugment(self, on: bool) -> None:
+        """spec-augment-layer masks in training (go/gotorch/cnn_tdnn.go:612-668); off = the reference executor's pass-through"""
+        if self.lib.kfp16_net_set_spec_augment(self.ptr, 1 if on else 0) != 0:
+            raise _err("SetSpecAugment")
+
+    def SetOverlapLoss(self, on: bool) -> None:
+        if self.lib.kfp16_net_set_overlap_loss(self.ptr, 1 if on else 0) != 0:
+            raise _err("SetOverlapLoss")
 
     def SetFuseConvBackward(self, on: bool) -> None:
         """conv layers with one consumer take dZ from that consumer's input-gradient epilogue (default on); Grad(conv layer)

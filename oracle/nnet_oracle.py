@@ -136,10 +136,20 @@ def identity_bn(dim):
 
 class OracleNet:
     def __init__(self, xconfig: str, n_seq: int, seq_len: int, cartesian: bool = True, train: bool = False,
-                 dropout_seed: int = 0):
+                 dropout_seed: int = 0, spec_augment: bool = False, train_bn: bool = False, bn_momentum: float = 0.1,
+                 stats_allreduce=None, world: int = 1):
         # train = True enables the tdnnf-layer dropout-proportion (inverted dropout after the batch-norm,
         # go/gotorch/layers.go:348-399); the mask of layer index i is dropout_uniform(seed ^ i*0x9E3779B9, padded row, col) > p
         self.train, self.dropout_seed = train, dropout_seed
+        # spec_augment = True (training): spec-augment-layer zeroes frequency / time masks per sequence
+        # (go/gotorch/cnn_tdnn.go:612-668) drawn from the same counter-based generator; False = the reference executor's
+        # pass-through (internal/nnet/forward.go:377-383)
+        self.spec_augment = spec_augment
+        # train_bn = True (training): batch statistics instead of the stored running statistics
+        # (cpp/cuda/cnn_kernels.cu:236-320 training branch, go/gotorch/layers.go:257-330): mean / biased variance over the rows of
+        # the minibatch, running = (1-m)*running + m*batch, backward = gamma/sqrt(batch var + eps) without differentiating through
+        # the statistics.  stats_allreduce(vector) sums [S1 | S2] over `world` data-parallel ranks.
+        self.train_bn, self.bn_momentum, self.stats_allreduce, self.world = train_bn, f32(bn_momentum), stats_allreduce, world
         self.layers = parse_xconfig(xconfig)
         self.by_name = {l.name: l for l in self.layers}
         self.n_seq, self.L = n_seq, seq_len
@@ -214,6 +224,29 @@ class OracleNet:
         seed = (self.dropout_seed ^ ((idx * 0x9E3779B9) & 0xFFFFFFFF)) & 0xFFFFFFFF
         return O.dropout_uniform(seed, rows, np.arange(l.out_dim)) > f32(p)
 
+    def spec_augment_keep(self, l) -> np.ndarray:
+        """keep mask [n_seq*L x dim] of a spec-augment-layer: the draw order and mask geometry of
+        kaldi_fp16_b200/csrc/elementwise.cu::spec_augment_kernel / nnet.cu (L_SPECAUG)"""
+        idx = self.layers.index(l)
+        dim, L = l.out_dim, self.L
+        fprop, tprop = float(l.kv.get("freq-max-proportion", 0.5)), float(l.kv.get("time-zeroed-proportion", 0.0))
+        tmax = max(0, min(int(l.kv.get("time-mask-max-frames", 20)), L))
+        fmax = max(0, min(dim, int(fprop * dim)))
+        nfreq = 1 if fmax > 0 else 0
+        ntime = min(8, max(1, int(tprop * L / (0.5 * tmax) + 0.5))) if (tprop > 0 and tmax > 0) else 0
+        seed = (self.dropout_seed ^ ((idx * 0x9E3779B9) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        u = O.dropout_uniform(seed, np.arange(self.n_seq), np.arange(32))          # [n_seq x draws]
+        keep = np.ones((self.n_seq, L, dim), bool)
+        for m in range(8):
+            f = (u[:, 4 * m] * f32(fmax + 1)).astype(np.int64) if m < nfreq else np.zeros(self.n_seq, np.int64)
+            f0 = (u[:, 4 * m + 1] * (dim - f + 1).astype(f32)).astype(np.int64)
+            t = (u[:, 4 * m + 2] * f32(tmax + 1)).astype(np.int64) if m < ntime else np.zeros(self.n_seq, np.int64)
+            t0 = (u[:, 4 * m + 3] * (L - t + 1).astype(f32)).astype(np.int64)
+            for s_ in range(self.n_seq):
+                keep[s_, :, f0[s_]:f0[s_] + f[s_]] = False
+                keep[s_, t0[s_]:t0[s_] + t[s_], :] = False
+        return keep.reshape(self.n_seq * L, dim)
+
     def _shift(self, x, s):
         """rows t -> t+s inside each sequence, clamped at the sequence edges (forward.go:699-790)"""
         D = x.shape[1]
@@ -231,13 +264,31 @@ class OracleNet:
         return out.reshape(-1, D)
 
     def _bn_fwd(self, x, bn, rms=None):
+        if self.train_bn and self.train and x.shape[0] == self.n_seq * self.L * max(1, x.shape[0] // (self.n_seq * self.L)):
+            x32 = np.asarray(x, f32)
+            stats = np.concatenate([x32.sum(0, dtype=f32), (x32 * x32).sum(0, dtype=f32)]).astype(f32)
+            if self.stats_allreduce is not None:
+                stats = np.asarray(self.stats_allreduce(stats), f32)
+            n = f32(x.shape[0] * self.world)
+            d = x.shape[1]
+            mean = stats[:d] / n
+            var = np.maximum(stats[d:] / n - mean * mean, f32(0))
+            m = self.bn_momentum
+            bn["mean"] = (bn["mean"] * (f32(1) - m) + mean * m).astype(f32)      # running statistics
+            bn["var"] = (bn["var"] * (f32(1) - m) + var * m).astype(f32)
+            bn["cur_mean"], bn["cur_var"] = mean.astype(f32), var.astype(f32)
+            g = bn["gamma"] if rms is None else f32(rms)
+            b = bn["beta"] if rms is None else f32(0)
+            sc = (g / np.sqrt(var + f32(bn["eps"]))).astype(f32)
+            return h(x32 * sc + (b - mean * sc).astype(f32))
         if rms is not None:
             return O.batchnorm_forward_rms(x, bn["mean"], bn["var"], rms, bn["eps"])
         return O.batchnorm_forward(x, bn["mean"], bn["var"], bn["gamma"], bn["beta"], bn["eps"])
 
     def _bn_scale(self, bn, rms=None):
         g = bn["gamma"] if rms is None else f32(rms)
-        return (g / np.sqrt(bn["var"] + f32(bn["eps"]))).astype(f32)
+        var = bn["cur_var"] if (self.train_bn and self.train and "cur_var" in bn) else bn["var"]
+        return (g / np.sqrt(var + f32(bn["eps"]))).astype(f32)
 
     def _input_of(self, l, acts):
         parts = []
@@ -300,6 +351,10 @@ class OracleNet:
                 y = self._bn_fwd(x, self.bn[(l.name, "")], rms if rms != 1.0 else None)
             elif t == "spec-augment-layer":
                 y = x.copy()
+                if self.spec_augment and self.train:
+                    keep = self.spec_augment_keep(l)
+                    saved[l.name].update(keep=keep)
+                    y = np.where(keep, y, f32(0))
             elif t == "combine-feature-maps-layer":
                 y = O.combine_feature_maps(x, int(l.kv["height"]), int(l.kv.get("num-filters1", 1)), int(l.kv.get("num-filters2", 1)))
             elif t == "tdnnf-layer":
@@ -381,6 +436,8 @@ class OracleNet:
                 dx = h(dy * self._bn_scale(self.bn[(l.name, "")], rms if rms != 1.0 else None))
             elif t == "spec-augment-layer":
                 dx = dy.copy()
+                if self.spec_augment and self.train:
+                    dx = np.where(self.saved[l.name]["keep"], dx, f32(0))
             elif t == "combine-feature-maps-layer":
                 H, f1, f2 = int(l.kv["height"]), int(l.kv.get("num-filters1", 1)), int(l.kv.get("num-filters2", 1))
                 g3 = dy.reshape(-1, H, f1 + f2)

@@ -109,3 +109,68 @@ def test_two_rank_step_equals_single_process_step():
     a, _, _ = O.sgd_update(w32, got_bucket, np.zeros_like(w32), 1e-3, 0.9)
     b, _, _ = O.sgd_update(w32, want, np.zeros_like(w32), 1e-3, 0.9)
     assert np.max(np.abs(a - b)) < 1e-4
+
+
+# ------------------------------------------------------------------ train-mode batch-norm across ranks
+def step_train_bn(params, x, n_seq, reducer=None, world=1):
+    allreduce = None
+    if reducer is not None:
+        def allreduce(stats):
+            t = torch.from_numpy(np.ascontiguousarray(stats, np.float32).copy())
+            reducer(t, t.numel(), 0)
+            return t.numpy()
+    net = OracleNet(XCONFIG, n_seq, L, train=True, train_bn=True, bn_momentum=0.1, stats_allreduce=allreduce, world=world)
+    net.params = {k: v.copy() for k, v in params.items()}
+    out = net.forward({"input": x})["output"]
+    wg, _ = net.backward("output", out)
+    running = {k: (v["mean"].copy(), v["var"].copy()) for k, v in net.bn.items()}
+    return wg, out, running
+
+
+def worker_train_bn(rank, world, port, q):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        params, x = make_inputs()
+        sh = dp.shard_sequences(N_SEQ, world, rank)
+        # the reducer the executor hook uses on the GPU box (there: a CUDA tensor over the device vector; here the tensor itself)
+        red = dp.BNStatsAllReducer(lambda t, count: t)
+        wg, out, running = step_train_bn(params, x[sh.rows(L)], sh.n_seq, red, world)
+        assert red.calls == 4      # tdnnf1, tdnnf2, prefinal x 2
+        names = sorted(wg)
+        bucket = torch.from_numpy(flat(wg, names).copy())
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+        q.put((rank, bucket.numpy().copy(), out, {f"{k[0]}/{k[1]}": v for k, v in running.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_train_batchnorm_uses_global_statistics():
+    """train-mode batch-norm under data parallelism: the [sum | sum of squares] vectors are summed over the ranks before
+    the statistics are finalised, so both ranks normalise with the statistics of the WHOLE minibatch -- outputs, running
+    statistics and the all-reduced gradients equal the single-process step"""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker_train_bn, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120), q.get(timeout=120)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    params, x = make_inputs()
+    wg, out, running = step_train_bn(params, x, N_SEQ)
+    want = flat(wg, sorted(wg))
+    got_out = np.concatenate([res[0][2], res[1][2]], axis=0)
+    assert O.max_err_vs_scale(got_out, out) < 2e-3
+    for r in res:
+        assert O.max_err_vs_scale(r[1], want) < 3e-3
+        for k, (m, v) in running.items():
+            gm, gv = r[3][f"{k[0]}/{k[1]}"]
+            assert np.allclose(gm, m, rtol=1e-4, atol=1e-5) and np.allclose(gv, v, rtol=1e-4, atol=1e-5), k
+    assert np.array_equal(res[0][1], res[1][1])
+    # ... and differ from per-rank statistics (what a missing exchange would give)
+    wg_local, out_local, _ = step_train_bn(params, x[:N_SEQ // 2 * L], N_SEQ // 2)
+    assert O.max_err_vs_scale(out_local, out[:N_SEQ // 2 * L]) > 5e-3

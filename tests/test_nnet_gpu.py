@@ -636,3 +636,188 @@ def test_dropout_in_the_training_step(handle, lib, ref_round):
     want = on_inf.forward({"input": x})["output"]
     assert rel_to_scale(inf.Forward(x), want) <= 2e-3
     inf.Free()
+
+
+SPECNET = """
+input name=input dim=40
+spec-augment-layer name=spec-augment freq-max-proportion=0.5 time-zeroed-proportion=0.2 time-mask-max-frames=10
+linear-component name=lin0 dim=128
+tdnnf-layer name=tdnnf1 dim=128 bottleneck-dim=32 time-stride=3 bypass-scale=0.66
+output-layer name=output include-log-softmax=false dim=48
+"""
+
+
+def test_spec_augment_layer_masks(handle, lib):
+    """spec-augment-layer in training (kfp16_net_set_spec_augment): per-sequence frequency / time masks
+    (go/gotorch/cnn_tdnn.go:612-668) from the counter-based generator, bit-identical to the oracle's masks; the backward pass
+    masks the gradient the same way; switched off (the default, = the reference executor's pass-through) features pass unchanged"""
+    n_seq, L, seed = 6, 50, 0xBEEF
+    rng = np.random.default_rng(23)
+    on = OracleNet(SPECNET, n_seq, L, train=True, dropout_seed=seed, spec_augment=True)
+    on.init_random(rng)
+    net = nnet.NewNetwork(nnet.BuildModelFromString(SPECNET), handle, n_seq, L, ref_round=True)
+    for k, w in on.params.items():
+        net.SetParam(k, w)
+    x = O.to_f16_rne((rng.standard_normal((n_seq * L, 40)) + 3.0).astype(np.float32))      # no exact zeros in the input
+    net.SetInput("input", x)
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    assert np.array_equal(net.Output("spec-augment"), x)                    # default: pass-through
+    net.SetSpecAugment(True)
+    assert lib.kfp16_net_set_dropout_seed(net.ptr, seed) == 0
+    acts = on.forward({"input": x})
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    got = net.Output("spec-augment")
+    assert np.array_equal(got, acts["spec-augment"]), "masked features differ from the oracle's"
+    keep = on.saved["spec-augment"]["keep"]
+    zeroed = 1.0 - keep.mean()
+    assert 0.05 < zeroed < 0.8, zeroed
+    per_seq = keep.reshape(n_seq, L, 40)
+    assert len({per_seq[s].tobytes() for s in range(n_seq)}) > 1           # masks differ between sequences
+    for name in ("lin0", "tdnnf1", "output"):
+        assert rel_to_scale(net.Output(name), acts[name]) <= 2e-3, name
+    masks = {"tdnnf1": net.Mask("tdnnf1", 128)}
+    wg, dact = on.backward("output", acts["output"], masks)
+    net.ZeroGrads()
+    net.Backward(None)
+    got_wg = net.WeightGrads()
+    for k, g in wg.items():
+        err = rel_to_scale(got_wg[k], g)
+        assert err <= (1e-2 if k.endswith("Bias") else 5e-3), f"weight grad {k} under SpecAugment: {err:.2e}"
+    net.Free()
+    inf = nnet.NewNetwork(nnet.BuildModelFromString(SPECNET), handle, n_seq, L, train=False)
+    with pytest.raises(nnet.NNetError):
+        inf.SetSpecAugment(True)
+    inf.Free()
+
+
+TRAINBN_NET = CNN_SMALL.replace("F1", "64").replace(
+    "output-layer name=output include-log-softmax=false dim=72",
+    "prefinal-layer name=prefinal small-dim=64 big-dim=256\noutput-layer name=output include-log-softmax=false dim=72")
+
+
+@REF_ROUND
+def test_train_mode_batchnorm(handle, lib, ref_round):
+    """kfp16_net_set_train_batchnorm: every batch-norm of the training network (batchnorm-component, conv per filter, TDNN-F,
+    both prefinal ones) normalises with the minibatch's statistics (cpp/cuda/cnn_kernels.cu:236-320 training branch),
+    updates the running statistics with the momentum, and the backward pass scales by gamma / sqrt(batch var + eps)
+    (go/gotorch/layers.go:302-330) -- against the oracle's train-mode batch-norm; switching it off restores the running
+    statistics path"""
+    n_seq, L, mom = 4, 33, 0.25
+    on, net, rng = make_pair(handle, TRAINBN_NET, n_seq, L, seed=31, ref_round=ref_round)
+    on.train, on.train_bn, on.bn_momentum = True, True, np.float32(mom)
+    x = O.to_f16_rne((rng.standard_normal((n_seq * L, 16)) * 2).astype(np.float32))
+    iv = O.to_f16_rne(np.clip(rng.standard_normal((n_seq, 24)), -3, 3).astype(np.float32))
+    net.MarkPerSequence("ivector", "ivector-linear", "ivector-batchnorm")
+    net.SetInput("input", x)
+    net.SetInput("ivector", iv)
+    net.SetTrainBatchNorm(True, mom)
+    acts = on.forward({"input": x, "ivector": iv})
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    for l in on.layers:
+        if l.type == "input":
+            continue
+        err = rel_to_scale(net.Output(l.name), acts[l.name])
+        assert err <= 3e-3, f"train-BN forward {l.name}: err {err:.2e}"
+    # running statistics moved towards the batch statistics
+    for (layer, which), bn in on.bn.items():
+        if layer == "ivector-batchnorm":
+            continue                                   # per-sequence rows: running statistics in both implementations
+        m, v = net.GetBN(layer, which, bn["mean"].size)
+        assert np.allclose(m, bn["mean"], rtol=2e-3, atol=2e-3), (layer, which)
+        assert np.allclose(v, bn["var"], rtol=5e-3, atol=2e-3), (layer, which)
+    masks = {}
+    for l in on.layers:
+        if l.type in ("tdnnf-layer", "conv-relu-batchnorm-layer", "prefinal-layer"):
+            want = on.saved[l.name]["mask"]
+            got = net.Mask(l.name, want.shape[-1]).reshape(want.shape)
+            assert np.mean(got != want) < 5e-3, f"relu mask {l.name}"
+            masks[l.name] = got
+    wg, _ = on.backward("output", acts["output"], masks)
+    net.ZeroGrads()
+    net.Backward(None)
+    got_wg = net.WeightGrads()
+    for k, g in wg.items():
+        err = rel_to_scale(got_wg[k], g)
+        assert err <= (1e-2 if k.endswith("Bias") else 6e-3), f"train-BN weight grad {k}: err {err:.2e}"
+    # off again: running statistics (now the updated ones) through the fused epilogues
+    net.SetTrainBatchNorm(False)
+    on.train_bn = False
+    acts2 = on.forward({"input": x, "ivector": iv})
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    assert rel_to_scale(net.Output("output"), acts2["output"]) <= 3e-3
+    assert rel_to_scale(acts2["output"], acts["output"]) > 1e-2       # ... which is a different function
+    net.Free()
+
+
+def test_kaldi_weight_import_export(handle, lib):
+    """weight_loader: a network's parameters written as Kaldi nnet3 text ([out x in] matrices, batch-norm statistics), parsed
+    back and loaded into a fresh network (LoadWeights, weight_loader.go:754-946) give the same forward pass as the oracle with
+    those weights; ComponentsFromNetwork exports what was loaded"""
+    from kaldi_fp16_b200 import weight_loader as WL
+    n_seq, L = 2, 30
+    xc = CNN_SMALL.replace("F1", "64").replace(
+        "output-layer name=output include-log-softmax=false dim=72",
+        "prefinal-layer name=prefinal-chain small-dim=64 big-dim=256\noutput-layer name=output include-log-softmax=false dim=72")
+    rng = np.random.default_rng(77)
+    on = OracleNet(xc, n_seq, L)
+    on.init_random(rng)
+    comps = {}
+
+    def add(name, typ, w=None, b=None, bn=None):
+        c = WL.KaldiComponent(Name=name, Type=typ)
+        if w is not None:
+            c.LinearParams = np.ascontiguousarray(w.T, np.float32)
+        if b is not None:
+            c.BiasParams = np.asarray(b, np.float32).reshape(-1)
+        if bn is not None:
+            c.StatsMean, c.StatsVar, c.TargetRms, c.Epsilon = bn
+        comps[name] = c
+
+    def rand_bn(key, rms=1.0):
+        d = on.bn[key]["mean"].size
+        mean, var = (rng.standard_normal(d) * 0.1).astype(np.float32), (rng.random(d) + 0.5).astype(np.float32)
+        on.bn[key].update(mean=mean, var=var, gamma=np.full(d, rms, np.float32), beta=np.zeros(d, np.float32), eps=1e-3)
+        return mean, var, rms, 1e-3
+
+    P = on.params
+    for k in P:
+        if k.endswith("Bias"):
+            P[k] = O.to_f16_trunc((rng.standard_normal(P[k].shape) * 0.1).astype(np.float32))
+    from oracle.nnet_oracle import idct_matrix
+    add("idct", "FixedAffineComponent", w=idct_matrix(16, 22.0))          # [in x out]; Kaldi's component stores the transpose
+    add("ivector-linear", "LinearComponent", w=P["ivector-linear.W"])
+    add("ivector-batchnorm", "BatchNormComponent", bn=rand_bn(("ivector-batchnorm", ""), 0.025))
+    add("idct-batchnorm", "BatchNormComponent", bn=rand_bn(("idct-batchnorm", "")))
+    for cn in ("cnn1", "cnn2", "cnn3"):
+        add(f"{cn}.conv", "TimeHeightConvolutionComponent", w=P[f"{cn}.W"], b=P[f"{cn}.Bias"])
+        add(f"{cn}.batchnorm", "BatchNormComponent", bn=rand_bn((cn, "BN")))
+    for tn in ("tdnnf4", "tdnnf5"):
+        add(f"{tn}.linear", "TdnnComponent", w=P[f"{tn}.LinearW"])
+        add(f"{tn}.affine", "TdnnComponent", w=P[f"{tn}.AffineW"], b=P[f"{tn}.AffineBias"])
+        add(f"{tn}.batchnorm", "BatchNormComponent", bn=rand_bn((tn, "AffBN")))
+    add("prefinal-chain.affine", "NaturalGradientAffineComponent", w=P["prefinal-chain.BigW"], b=P["prefinal-chain.BigBias"])
+    add("prefinal-chain.linear", "LinearComponent", w=P["prefinal-chain.SmallW"])
+    add("prefinal-chain.batchnorm1", "BatchNormComponent", bn=rand_bn(("prefinal-chain", "PfBN")))
+    add("prefinal-chain.batchnorm2", "BatchNormComponent", bn=rand_bn(("prefinal-chain", "BN")))
+    add("output.affine", "NaturalGradientAffineComponent", w=P["output.W"], b=P["output.Bias"])
+    text = WL.WriteNnet3Text(comps)
+    parsed = WL.ParseNnet3Text(text)
+    net = nnet.NewNetwork(nnet.BuildModelFromString(xc), handle, n_seq, L, train=False, seed=5)      # different random init
+    rep = WL.LoadWeights(net, parsed)
+    assert rep["loaded"] == 11 and rep["skipped"] == ["combine_inputs"], rep
+    x = O.to_f16_rne((rng.standard_normal((n_seq * L, 16)) * 2).astype(np.float32))
+    iv = O.to_f16_rne(np.clip(rng.standard_normal((n_seq, 24)), -3, 3).astype(np.float32))
+    net.MarkPerSequence("ivector", "ivector-linear", "ivector-batchnorm")
+    net.SetInput("input", x)
+    net.SetInput("ivector", iv)
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    acts = on.forward({"input": x, "ivector": iv})
+    for name in ("cnn1", "cnn3", "tdnnf5", "prefinal-chain", "output"):
+        assert rel_to_scale(net.Output(name), acts[name]) <= 2e-3, name
+    # export: what was loaded comes back bit for bit (FP16-representable values), statistics included
+    out = WL.ComponentsFromNetwork(net)
+    for name in ("cnn2.conv", "tdnnf4.linear", "tdnnf5.affine", "prefinal-chain.linear", "output.affine"):
+        assert np.array_equal(out[name].LinearParams, O.to_f16_trunc(parsed[name].LinearParams)), name
+    assert np.array_equal(out["tdnnf4.batchnorm"].StatsVar, parsed["tdnnf4.batchnorm"].StatsVar)
+    assert np.array_equal(out["cnn3.batchnorm"].StatsMean, parsed["cnn3.batchnorm"].StatsMean)
+    net.Free()

@@ -201,3 +201,44 @@ def test_gotorch_port_matmul_and_tdnn(port):
     assert np.allclose(gW, S.T @ gy.reshape(-1, dout)) and np.allclose(gb, gy.sum((0, 1)))
     cs = C.c_double()
     assert port.gt_bench_tdnnf_stack(2, 32, 8, 3, 1, 6, 1, C.byref(cs)) > 0 and np.isfinite(cs.value)
+
+
+def test_spec_augment_masks_geometry():
+    """oracle SpecAugment (go/gotorch/cnn_tdnn.go:612-668): one frequency band of width <= freq-max-proportion*dim over every
+    frame and time bands of width <= time-mask-max-frames over every bin, per sequence; deterministic in the seed; the
+    backward pass masks the gradient with the same pattern"""
+    from oracle.nnet_oracle import OracleNet
+    xc = ("input name=input dim=40\n"
+          "linear-component name=pre dim=40\n"
+          "spec-augment-layer name=sa freq-max-proportion=0.25 time-zeroed-proportion=0.3 time-mask-max-frames=8\n"
+          "output-layer name=output include-log-softmax=false dim=16\n")
+    n_seq, L = 5, 60
+    rng = np.random.default_rng(0)
+    on = OracleNet(xc, n_seq, L, train=True, dropout_seed=77, spec_augment=True)
+    on.init_random(rng)
+    x = (rng.standard_normal((n_seq * L, 40)) + 4).astype(np.float16).astype(np.float32)
+    acts = on.forward({"input": x})
+    keep = on.saved["sa"]["keep"].reshape(n_seq, L, 40)
+    for s in range(n_seq):
+        rows_all = ~keep[s].any(axis=1)                   # fully masked frames = time masks
+        cols_all = ~keep[s].any(axis=0)                   # fully masked bins = the frequency mask
+        assert cols_all.sum() <= 10
+        assert np.array_equal(keep[s], ~(rows_all[:, None] | cols_all[None, :]))      # nothing but whole rows / columns
+        if rows_all.any():                                # each band at most 8 frames long
+            runs = np.diff(np.flatnonzero(np.diff(np.r_[0, rows_all.astype(int), 0])))[::2]
+            assert runs.max() <= 8 * 8
+    again = OracleNet(xc, n_seq, L, train=True, dropout_seed=77, spec_augment=True)
+    again.params = on.params
+    again.forward({"input": x})
+    assert np.array_equal(again.saved["sa"]["keep"], on.saved["sa"]["keep"])
+    other = OracleNet(xc, n_seq, L, train=True, dropout_seed=78, spec_augment=True)
+    other.params = on.params
+    other.forward({"input": x})
+    assert not np.array_equal(other.saved["sa"]["keep"], on.saved["sa"]["keep"])
+    # gradient: zero exactly where the features were masked
+    wg, dact = on.backward("output", acts["output"], {})
+    g = dact["pre"].reshape(n_seq, L, 40)
+    assert not g[~keep].any() and np.abs(g[keep]).max() > 0
+    off = OracleNet(xc, n_seq, L, train=True, dropout_seed=77)          # default: the reference executor's pass-through
+    off.params = on.params
+    assert np.array_equal(off.forward({"input": x})["sa"], off.acts["pre"])
