@@ -123,7 +123,8 @@ typedef struct {
                           4 = merge the two row-shifted groups of a split-K weight gradient into one tile pass (what the
                           grouped launch does; for a single problem only on request);
                           convolutions (conv.mode 1): 1 = every tap loads its own input box, 5 = one shared box per channel
-                          chunk whatever the tile width (default: shared for N <= 128, where it measured faster) */
+                          chunk whatever the tile width (default: shared for N <= 128, where it measured faster), 6 = shared box
+                          but stream the weight tiles per M tile even when all of them fit in shared memory (default: resident) */
     void *debug_clock_buf; /* profiling: device int64 [grid][3 roles][8 tiles][16] clock64 stamps per warp role; NULL = off */
     /* A second split-K problem of the same shape (M, N, K, majors, groups) sharing the launch -- the two weight
      * gradients of one TDNN-F layer: tile groups [groups, 2*groups) compute A2^T * B2 into ws2[].  One launch and half

@@ -112,7 +112,7 @@ static int pick_kind(uint32_t flags) {
   return EK_GENERIC;
 }
 
-static int pick_bn(int N, int m_tiles, int groups, int split_k, int ctas) {
+static int pick_bn(int N, int K, int m_tiles, int groups, int split_k, int ctas) {
   if (N <= 64) return 64;
   if (N <= 128) return 128;
   if (N <= 160) return 160;
@@ -125,7 +125,12 @@ static int pick_bn(int N, int m_tiles, int groups, int split_k, int ctas) {
     const int bn = cand[i];
     const long long tiles = (long long)m_tiles * ((N + bn - 1) / bn) * groups * split_k;
     const long long waves = (tiles + ctas - 1) / ctas;
-    const double cost = (double)waves * (bn + 24);
+    // Deep K (the main loop dominates; no layer of the network, but e.g. 4096^3): a k-block costs the larger of its MMA time
+    // (~2.85 cycles per tile column at the measured 1671 TF) and its operand loads (32 KB of A + 128 B per column of B for a CTA
+    // pair at ~90 B/cycle): a 128-wide pair tile is load-bound (546 vs 365 cycles), a 256-wide one balanced (730).  Measured on
+    // 4096^3: 155 us with 128-wide tiles (7 waves) against the 4-wave bound of ~95 us.
+    double cost = (double)waves * (bn + 24);
+    if (K >= 1024) cost = (double)waves * std::max(2.85 * bn, (32768.0 + 128.0 * bn) / 90.0);
     if (cost < best_cost * 0.97) { best_cost = cost; best = bn; }
   }
   return best;
@@ -360,6 +365,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   // ---- convolution forward / input gradient: ONE input box per 64-channel chunk shared by all taps (MODE 5) when the
   // geometry and shared memory allow; otherwise every tap loads its own box (MODE 0 with conv addressing)
   bool cshare = false;
+  int cs_bres = 0;
   int cs_sl = 0, cs_tbox = 0, cs_dtmin = 0, cs_hqmin = 0, cs_dtspan = 0, cs_planes = 0, cs_plane_par[2] = {0, 0}, cs_plane_bytes = 0, cs_nstages = 0;
   if (conv == 1 && d->conv.ntaps >= 2 && d->no_share != 1) {
     const kfp16_conv_addr& c = d->conv;
@@ -417,7 +423,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   if (ctx->max_ctas > 0 && ctx->max_ctas < ctas) ctas = ctx->max_ctas;
   int units = ctas / cg;                 // CTAs or CTA pairs that can be resident
   if (units < 1) { units = 1; }
-  int bn = merge ? 160 : (d->force_bn ? d->force_bn : pick_bn(d->N, m_tiles, tile_groups, split_k, units));
+  int bn = merge ? 160 : (d->force_bn ? d->force_bn : pick_bn(d->N, d->K, m_tiles, tile_groups, split_k, units));
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) { set_error("kfp16_gemm_ex: unsupported tile width %d", bn); return -1; }
   if (conv == 2 && bn == 160) bn = 256;
   if (cshare) {
@@ -425,7 +431,11 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     const int b_tile = b_mn ? ((bn / cg + 63) / 64) * 8192 : (bn / cg) * 128;
     const int fixed = 1024 + 512 + epi_bytes_for(ek, bn);
     cs_nstages = (227 * 1024 - fixed - 2 * cs_planes * cs_plane_bytes) / b_tile;
-    if (cs_nstages > 8) cs_nstages = 8;
+    // one N tile and room for every (chunk, tap) weight tile: keep them resident instead of streaming them per M tile
+    const int all_tiles = d->conv.ntaps * (d->conv.C / 64);
+    if (d->N <= bn && all_tiles <= cs_nstages && d->no_share != 6) cs_bres = all_tiles;
+    if (cs_bres > 0) cs_nstages = cs_bres;
+    else if (cs_nstages > 8) cs_nstages = 8;
     if (cs_nstages < 3) { set_error("internal: shared convolution box does not fit shared memory (bn %d)", bn); return -1; }   // excluded above
   }
   if (!(flags & EPI_SPLITK) && (bn % 64) != 0 && d->N > bn) {
@@ -448,7 +458,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
       p.conv_box_bytes = (cs_tbox + cs_dtspan) * cs_sl * 128;
       p.conv_plane_bytes = cs_plane_bytes; p.conv_planes = cs_planes;
       p.conv_plane_par[0] = cs_plane_par[0]; p.conv_plane_par[1] = cs_plane_par[1];
-      p.conv_nstages = cs_nstages;
+      p.conv_nstages = cs_nstages; p.conv_bres = cs_bres;
       for (int t = 0; t < c.ntaps; ++t) {
         const int pl = (cs_planes == 2 && c.par[t] == cs_plane_par[1]) ? 1 : 0;
         p.conv_aoff[t] = (uint32_t)(pl * (cs_plane_bytes >> 4) + ((c.dt[t] - cs_dtmin) * cs_sl + (c.hq[t] - cs_hqmin)) * 8);

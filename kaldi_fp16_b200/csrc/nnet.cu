@@ -1986,8 +1986,22 @@ int kfp16_net_set_train_batchnorm(kfp16_net* n, int on, float momentum) {
     if (!check_cuda(cudaMalloc((void**)&n->bn_stats, std::max<size_t>(n->bn_stats_dim, 8) * 2 * sizeof(float)), "batch-norm statistics buffer")) return -1;
     n->allocs.push_back(n->bn_stats);
   }
+  const bool was_on = n->train_bn;
   n->train_bn = on != 0;
   if (on) n->bn_momentum = momentum;
+  if (was_on && !on) {
+    // back to the stored statistics: the folded scale / shift still hold the last minibatch's, so fold the (updated) running
+    // statistics again -- what an inference pass or the fused training epilogues read from now on
+    for (auto& l : n->layers)
+      for (BNorm* bn : {&l.bn, &l.bn2}) {
+        if (!bn->present) continue;
+        const bool rms = bn->rms_only;
+        if (kfp16_bn_fold(n->ctx, bn->mean, bn->var, rms ? nullptr : bn->gamma, rms ? nullptr : bn->beta, bn->eps, bn->target_rms, bn->dim, bn->scale, bn->shift)) return -1;
+        if (kfp16_scale_f32(n->ctx, bn->scale, bn->scale_bwd, bn->dim, bn->bwd_mul)) return -1;
+        if (!retile_bn(n, *bn, bn->tiles)) return -1;
+      }
+    if (!check_cuda(cudaStreamSynchronize(n->ctx->stream), "bn refold sync")) return -1;
+  }
   return 0;
 }
 int kfp16_net_set_bn_stats_hook(kfp16_net* n, kfp16_bn_stats_hook hook, void* user, int world) {

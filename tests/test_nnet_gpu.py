@@ -729,7 +729,7 @@ def test_train_mode_batchnorm(handle, lib, ref_round):
     for l in on.layers:
         if l.type in ("tdnnf-layer", "conv-relu-batchnorm-layer", "prefinal-layer"):
             want = on.saved[l.name]["mask"]
-            got = net.Mask(l.name, want.shape[-1]).reshape(want.shape)
+            got = net.Mask(l.name, l.out_dim if l.type == "conv-relu-batchnorm-layer" else want.shape[-1]).reshape(want.shape)
             assert np.mean(got != want) < 5e-3, f"relu mask {l.name}"
             masks[l.name] = got
     wg, _ = on.backward("output", acts["output"], masks)
