@@ -123,8 +123,7 @@ typedef struct {
                           4 = merge the two row-shifted groups of a split-K weight gradient into one tile pass (what the
                           grouped launch does; for a single problem only on request);
                           convolutions (conv.mode 1): 1 = every tap loads its own input box, 5 = one shared box per channel
-                          chunk whatever the tile width (default: shared for N <= 128, where it measured faster), 6 = shared box
-                          but stream the weight tiles per M tile even when all of them fit in shared memory (default: resident) */
+                          chunk whatever the tile width (default: shared for N <= 128, where it measured faster) */
     void *debug_clock_buf; /* profiling: device int64 [grid][3 roles][8 tiles][16] clock64 stamps per warp role; NULL = off */
     /* A second split-K problem of the same shape (M, N, K, majors, groups) sharing the launch -- the two weight
      * gradients of one TDNN-F layer: tile groups [groups, 2*groups) compute A2^T * B2 into ws2[].  One launch and half
@@ -241,6 +240,18 @@ int kfp16_bn_finalize(kfp16_ctx *ctx, const float *stats, double n_rows, int D, 
 /* Z = h(Z*scale[c % col_mod] + shift[c % col_mod] (+ res_scale*R)) in place on the filtered rows */
 int kfp16_bn_apply(kfp16_ctx *ctx, void *Z, int ld, const float *scale, const float *shift, const void *R, int ldr,
                    float res_scale, int rows, int cols, int col_mod, int period, int lo, int len);
+/* ---- restricted self-attention (attention-relu-batchnorm-layer, internal/nnet/forward.go:795-909: a CPU loop nest between a D2H and
+ * an H2D copy in the reference).  proj: [rows x ldp] projection, per head [key (K) | value (V) | query key (K) | query context (C)],
+ * C = 1 + n_left + n_right <= 32; output frame t attends to frames t + (o - n_left)*stride of its own sequence (zeros outside);
+ * rows = the padded layout (n_seq blocks of seq_len + 2*halo, halo rows -> zeros).  z receives ReLU(out) (fp16, kept for the
+ * backward pass: mask + attention weights), y = z*scale + shift (folded batch-norm), both [rows x ldy], heads*(V + C) columns. */
+int kfp16_attention_forward(kfp16_ctx *ctx, const void *proj, int ldp, void *z, void *y, int ldy, const float *scale,
+                            const float *shift, int n_seq, int seq_len, int halo, int heads, int key_dim, int value_dim,
+                            int n_left, int n_right, int stride, float key_scale);
+/* exact transpose: dproj [rows x ldp] from dy [rows x ldy]; db_scratch: fp32 [rows x heads x 32] */
+int kfp16_attention_backward(kfp16_ctx *ctx, const void *proj, int ldp, const void *z, const void *dy, int ldy,
+                             const float *scale, float *db_scratch, void *dproj, int n_seq, int seq_len, int halo, int heads,
+                             int key_dim, int value_dim, int n_left, int n_right, int stride, float key_scale);
 /* SpecAugment (go/gotorch/cnn_tdnn.go:612-668) on the padded layout: per sequence nfreq frequency masks of width <= fmax and
  * ntime time masks of width <= tmax are zeroed (halo rows copied through; x == y allowed).  The masks are drawn from the
  * counter-based generator kfp16_dropout_uniform(seed ^ *seed_dev, sequence, draw) -- see csrc/elementwise.cu for the draw

@@ -144,6 +144,8 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_bn_batch_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int]),
     "kfp16_bn_finalize": (c_int, [c_void_p, c_void_p, C.c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "kfp16_bn_apply": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "kfp16_attention_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 9 + [c_float]),
+    "kfp16_attention_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_float]),
     "kfp16_spec_augment": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_u32, c_void_p]),
     "kfp16_scale_shift_ld": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "kfp16_zero_rows_except": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),

@@ -151,7 +151,8 @@ __global__ void col2im_kernel(const __half* __restrict__ dP, __half* __restrict_
 // from 2-byte shared-memory reads with table-driven offsets (no division in the inner loops).
 // Preconditions (checked by the launchers): sub == 1, hout == hin, Kp <= 64, halo >= max |dt| -- a tap then never leaves
 // the sequence block of its frame, and the block's halo rows are staged as zeros = the zero padding in time.
-constexpr int kSmallFrames = 8;      // frames per block
+constexpr int kSmallFrames = 8;      // frames per block (gather)
+constexpr int kScatterFrames = 4;    // frames per block (scatter: 35 KB of staged patch rows per block -> 6 blocks per SM)
 struct SmallLut { short off[64]; };  // im2col: k -> (dt - dtmin)*4096 + (dh + 1)*fin + f, -1 = padding column
 
 __device__ __forceinline__ bool real_row(const ConvGeom& g, int r, int total_rows) {
@@ -213,35 +214,35 @@ im2col_small_kernel(const __half* __restrict__ x, __half* __restrict__ P, ConvGe
 // dx[r, h, f] = sum over taps of dP[((r - dt)*hout + (h - dh)), tap*fin + f]; one thread per (h, f), looping over the block's frames
 __global__ void __launch_bounds__(256)
 col2im_small_kernel2(const __half* __restrict__ dP, __half* __restrict__ dx, ConvGeom g, Taps taps, int dtmin, int dtspan) {
-  extern __shared__ __align__(16) __half sp[];       // [(kSmallFrames + dtspan) frames][hout][Kp + 8]: rows 16 bytes apart in
+  extern __shared__ __align__(16) __half sp[];       // [(kScatterFrames + dtspan) frames][hout][Kp + 8]: rows 16 bytes apart in
   const int pitch = g.Kp + 8;                        // bank phase (a 128-byte pitch put every height on the same banks)
-  __shared__ int srow_ok[kSmallFrames];
-  const int r0 = blockIdx.x * kSmallFrames;
+  __shared__ int srow_ok[kScatterFrames];
+  const int r0 = blockIdx.x * kScatterFrames;
   const int total_rows = g.n_seq * g.blk;
-  const int nfr = kSmallFrames + dtspan;
+  const int nfr = kScatterFrames + dtspan;
   const int frame_units = g.hout * (g.Kp >> 3);
   const int dtmax = dtmin + dtspan;
-  __shared__ int sfr_ok[kSmallFrames + 8];
-  if (threadIdx.x < kSmallFrames) srow_ok[threadIdx.x] = real_row(g, r0 + threadIdx.x, total_rows) ? 1 : 0;
+  __shared__ int sfr_ok[kScatterFrames + 8];
+  if (threadIdx.x < kScatterFrames) srow_ok[threadIdx.x] = real_row(g, r0 + threadIdx.x, total_rows) ? 1 : 0;
   if (threadIdx.x < nfr) sfr_ok[threadIdx.x] = real_row(g, r0 - dtmax + (int)threadIdx.x, total_rows) ? 1 : 0;
   __syncthreads();
-  // output frame r reads patch rows of frames r - dt: stage frames r0 - dtmax .. r0 + kSmallFrames - 1 - dtmin (zeros for halo
-  // rows).  Four 16-byte loads in flight per thread: with one at a time the block spent ~12 load latencies here (measured
+  // output frame r reads patch rows of frames r - dt: stage frames r0 - dtmax .. r0 + kScatterFrames - 1 - dtmin (zeros for halo
+  // rows).  Eight 16-byte loads in flight per thread: with one at a time the block spent ~12 load latencies here (measured
   // 47 us for the whole kernel, twice what the 64 MB it moves need)
   {
     const int upr = g.Kp >> 3;                        // 16-byte units per patch row
     const int total = nfr * frame_units;
     const uint4* src = reinterpret_cast<const uint4*>(dP) + (ptrdiff_t)(r0 - dtmax) * frame_units;
-    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
-      uint4 v[4];
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+      uint4 v[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         const int i = i0 + k * (int)blockDim.x;
         v[k] = make_uint4(0, 0, 0, 0);
         if (i < total && sfr_ok[i / frame_units]) v[k] = src[i];
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         const int i = i0 + k * (int)blockDim.x;
         if (i < total) {
           const int fr = i / frame_units, u = i - fr * frame_units;
@@ -255,7 +256,7 @@ col2im_small_kernel2(const __half* __restrict__ dP, __half* __restrict__ dx, Con
   const int frame_halves = g.hout * pitch;
   for (int idx = threadIdx.x; idx < ldx; idx += blockDim.x) {
     const int hh = idx / g.fin, f = idx - hh * g.fin;
-    for (int fl = 0; fl < kSmallFrames; ++fl) {
+    for (int fl = 0; fl < kScatterFrames; ++fl) {
       const int r = r0 + fl;
       if (r >= total_rows) break;
       float acc = 0.f;
@@ -355,14 +356,14 @@ int kfp16_col2im(kfp16_ctx* ctx, const void* dP, int Kp, void* dx, int n_seq, in
   for (int i = 1; i < ntaps; ++i) { dtmin = std::min(dtmin, dt[i]); dtmax = std::max(dtmax, dt[i]); }
   if (sub == 1 && hin == hout && (fin % 8) != 0 && Kp <= 64 && (Kp % 8) == 0 && dtmax - dtmin <= 6 && halo >= std::max(dtmax, -dtmin) &&
       ((uintptr_t)dP & 15) == 0) {
-    const size_t smem = (size_t)(kSmallFrames + dtmax - dtmin) * hout * (Kp + 8) * 2;
+    const size_t smem = (size_t)(kScatterFrames + dtmax - dtmin) * hout * (Kp + 8) * 2;
     if (smem <= 99 * 1024) {
       static bool attr = false;
       if (!attr) {
         if (!check_cuda(cudaFuncSetAttribute(col2im_small_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 99 * 1024), "col2im smem attribute")) return -1;
         attr = true;
       }
-      const int blocks = (n_seq * g.blk + kSmallFrames - 1) / kSmallFrames;
+      const int blocks = (n_seq * g.blk + kScatterFrames - 1) / kScatterFrames;
       col2im_small_kernel2<<<blocks, 256, smem, s>>>((const __half*)dP, (__half*)dx, g, t, dtmin, dtmax - dtmin);
       count_launch();
       return check_launch("kfp16_col2im") ? 0 : -1;

@@ -365,7 +365,6 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
   // ---- convolution forward / input gradient: ONE input box per 64-channel chunk shared by all taps (MODE 5) when the
   // geometry and shared memory allow; otherwise every tap loads its own box (MODE 0 with conv addressing)
   bool cshare = false;
-  int cs_bres = 0;
   int cs_sl = 0, cs_tbox = 0, cs_dtmin = 0, cs_hqmin = 0, cs_dtspan = 0, cs_planes = 0, cs_plane_par[2] = {0, 0}, cs_plane_bytes = 0, cs_nstages = 0;
   if (conv == 1 && d->conv.ntaps >= 2 && d->no_share != 1) {
     const kfp16_conv_addr& c = d->conv;
@@ -387,6 +386,10 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     // Measured on B200 (profiles/r02_trace_cnn_*): the shared box pays where the per-tap A boxes bound the tile (N <= 128: 61 vs
     // 79 us cnn2, 73 vs 81 us cnn4, input gradients 55 vs 75 / 66 vs 79 us); 256-wide tiles are MMA-bound and lose the rows the
     // (frame, slot) index wastes on the height padding (cnn6: 88 vs 85 us, its input gradient 86 vs 79 us)
+    // (Keeping the weight tiles of a narrow layer resident in shared memory instead of streaming them per M tile was measured
+    //  too: cnn2 60 -> 62 us, cnn3 39 -> 44 us -- those kernels are bound by the per-tile epilogue / accumulator hand-over of
+    //  their 120 x 64 tiles, not by the 73 KB of weights per tile -- and the extra branches in the issue loop cost the wider
+    //  layers 10 %.  Not kept.)
     const bool narrow = d->N <= 128 || d->no_share == 5;
     if (planes_ok && narrow && cs_tbox >= 1 && kind_ok && cs_tbox + cs_dtspan <= 256 && cs_sl <= 256) {
       const int rows_alloc = cs_dtspan * cs_sl + hspan + kBM;           // furthest row a shifted 128-row read touches
@@ -431,11 +434,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     const int b_tile = b_mn ? ((bn / cg + 63) / 64) * 8192 : (bn / cg) * 128;
     const int fixed = 1024 + 512 + epi_bytes_for(ek, bn);
     cs_nstages = (227 * 1024 - fixed - 2 * cs_planes * cs_plane_bytes) / b_tile;
-    // one N tile and room for every (chunk, tap) weight tile: keep them resident instead of streaming them per M tile
-    const int all_tiles = d->conv.ntaps * (d->conv.C / 64);
-    if (d->N <= bn && all_tiles <= cs_nstages && d->no_share != 6) cs_bres = all_tiles;
-    if (cs_bres > 0) cs_nstages = cs_bres;
-    else if (cs_nstages > 8) cs_nstages = 8;
+    if (cs_nstages > 8) cs_nstages = 8;
     if (cs_nstages < 3) { set_error("internal: shared convolution box does not fit shared memory (bn %d)", bn); return -1; }   // excluded above
   }
   if (!(flags & EPI_SPLITK) && (bn % 64) != 0 && d->N > bn) {
@@ -458,7 +457,7 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
       p.conv_box_bytes = (cs_tbox + cs_dtspan) * cs_sl * 128;
       p.conv_plane_bytes = cs_plane_bytes; p.conv_planes = cs_planes;
       p.conv_plane_par[0] = cs_plane_par[0]; p.conv_plane_par[1] = cs_plane_par[1];
-      p.conv_nstages = cs_nstages; p.conv_bres = cs_bres;
+      p.conv_nstages = cs_nstages;
       for (int t = 0; t < c.ntaps; ++t) {
         const int pl = (cs_planes == 2 && c.par[t] == cs_plane_par[1]) ? 1 : 0;
         p.conv_aoff[t] = (uint32_t)(pl * (cs_plane_bytes >> 4) + ((c.dt[t] - cs_dtmin) * cs_sl + (c.hq[t] - cs_hqmin)) * 8);

@@ -149,10 +149,7 @@ struct GemmParams {
   int conv_plane_bytes;         // shared-memory bytes reserved per plane (box + read-ahead slack, multiple of 1024)
   int conv_planes;              // parity planes loaded (1 or 2)
   int conv_plane_par[2];        // their parity coordinates
-  int conv_nstages;             // B ring depth (2..8), or the number of resident weight tiles
-  int conv_bres;                // > 0: every weight tile (taps x channel chunks, one N tile) is loaded ONCE per CTA and stays in shared
-                                // memory while the CTA walks its M tiles -- narrow layers (64 / 128 filters) otherwise re-load their
-                                // whole weight matrix per 120-row tile (measured on cnn2: 335 MB through L2->SM, 73 of every 100 KB weights)
+  int conv_nstages;             // B ring depth (2..8)
   uint32_t conv_aoff[kMaxTaps]; // descriptor offset (16-byte units) of tap s inside an A buffer
   // rows whose index modulo zero_period lies outside [zero_lo, zero_lo + zero_len) are written as zeros with a zero mask
   // (halo rows of the padded minibatch layout: the zero padding the next convolution reads); zero_period == 0: off
@@ -408,29 +405,6 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         // then the taps' weight tiles through the ring
         const int f0 = m_row0 / p.conv_h;                 // this CTA's first output frame
         const int nchunks = p.conv_c / kBK;
-        if (p.conv_bres > 0 && tile_i == 0) {
-          // resident weights: all (chunk, tap) tiles of this CTA's N columns, one barrier (stage 0's) for the lot
-          if (elect_one()) {
-            const uint32_t fb = CG == 2 ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0;
-            const uint32_t tx = (uint32_t)(p.conv_bres * Cfg::kBTileBytes);
-            if (CG == 2) mbar_arrive_expect_tx_cluster(fb, tx); else mbar_arrive_expect_tx(&full_bar[0], tx);
-            for (int c = 0; c < nchunks; ++c)
-              for (int tap = 0; tap < p.conv_taps; ++tap) {
-                uint8_t* sb = smem_ring + (c * p.conv_taps + tap) * Cfg::kStageBytes;
-                auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
-                  if (CG == 2) tma_load_2d_pair(dst, m, fb, c0, c1);
-                  else tma_load_2d(dst, m, &full_bar[0], c0, c1);
-                };
-                if (!B_MN) load(sb, mapB, c * kBK, n_loc + p.conv_brow[tap]);
-                else {
-#pragma unroll
-                  for (int cc = 0; cc < Cfg::kBChunks; ++cc)
-                    load(sb + cc * Cfg::kMnChunkBytes, mapB, n_loc + cc * 64, c * kBK + p.conv_brow[tap]);
-                }
-              }
-          }
-          __syncwarp();
-        }
         for (int c = 0; c < nchunks; ++c, ++a_cnt) {
           const uint32_t ab = a_cnt & 1u;
           mbar_wait(&aempty_bar[ab], ((a_cnt >> 1) & 1u) ^ 1u);
@@ -445,7 +419,6 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
             }
           }
           __syncwarp();
-          if (p.conv_bres > 0) continue;                  // weights are resident: nothing to stream
           for (int tap = 0; tap < p.conv_taps; ++tap) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
@@ -584,31 +557,26 @@ gemm_f16_sm100(const __grid_constant__ GemmParams p) {
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
         if constexpr (Cfg::kConvS) {
           const int nchunks = p.conv_c / kBK;
-          const bool bres = p.conv_bres > 0;
-          if (bres && tile_i == 0) { mbar_wait(&full_bar[0], 0); tc_fence_after(); }     // the resident weight tiles have landed
           for (int c = 0; c < nchunks; ++c, ++a_cnt) {
             const uint32_t ab = a_cnt & 1u;
             mbar_wait(&afull_bar[ab], (a_cnt >> 1) & 1u);
             tc_fence_after();
             const uint64_t abuf = adesc0 + (uint64_t)((uint32_t)(ab * p.conv_planes * p.conv_plane_bytes) >> 4);
             for (int tap = 0; tap < p.conv_taps; ++tap) {
-              if (!bres) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-              }
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
               if (elect_one()) {
                 // the tap reads the box from its (frame, height) offset on: a descriptor start moved by whole 128-byte rows
                 const uint64_t ad = abuf + (uint64_t)p.conv_aoff[tap];
-                const int bslot = bres ? c * p.conv_taps + tap : stage;
-                const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(bslot * Cfg::kStageBytes) >> 4);
+                const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
                 mma(d_tmem, ad, bd, (c > 0 || tap > 0) ? 1u : 0u);
                 mma(d_tmem, ad + a_kstep, bd + b_kstep, 1u);
                 mma(d_tmem, ad + 2 * a_kstep, bd + 2 * b_kstep, 1u);
                 mma(d_tmem, ad + 3 * a_kstep, bd + 3 * b_kstep, 1u);
-                if (!bres) { if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]); }
+                if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
               }
               __syncwarp();
-              if (!bres && ++stage == nstages) { stage = 0; phase ^= 1; }
+              if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
             if (elect_one()) { if (CG == 2) umma_commit_pair(&aempty_bar[ab]); else umma_commit(&aempty_bar[ab]); }
             __syncwarp();

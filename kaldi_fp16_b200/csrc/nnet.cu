@@ -27,7 +27,7 @@ using namespace kfp16;
 
 namespace {
 
-enum LType { L_INPUT, L_IDCT, L_LINEAR, L_BATCHNORM, L_SPECAUG, L_COMBINE, L_CONV, L_TDNNF, L_PREFINAL, L_OUTPUT };
+enum LType { L_INPUT, L_IDCT, L_LINEAR, L_BATCHNORM, L_SPECAUG, L_COMBINE, L_CONV, L_TDNNF, L_PREFINAL, L_OUTPUT, L_ATTENTION };
 enum HaloMode { HALO_NONE = 0, HALO_ZERO = 1, HALO_REPL = 2 };
 
 struct Buf {
@@ -120,6 +120,11 @@ struct Layer {
   // training step with a subsampled objective: this layer's output is only read on rows f_row0 + k*f_sub (it is row-wise
   // and feeds nothing but the objective's output layer through row-wise layers), so the step computes just those rows
   int f_sub = 1, f_row0 = 0;
+  // attention-relu-batchnorm-layer (internal/nnet/layers.go:298-318): heads, key / value dims, context; `big` holds the projection
+  // [rows x att_affine], `dz` the ReLU'd pre-batch-norm output, `dbig` the projection gradient, att_db the score gradients
+  int att_heads = 0, att_key = 0, att_value = 0, att_left = 0, att_right = 0, att_stride = 1, att_affine = 0;
+  float att_scale = 1.0f;
+  float* att_db = nullptr;
   // spec-augment-layer (training, kfp16_net_set_spec_augment): mask geometry derived from the xconfig values
   int sa_fmax = 0, sa_nfreq = 0, sa_tmax = 0, sa_ntime = 0;
   double fl_fwd = 0, fl_bwd = 0;   // GEMM flops of this layer over all rows (row-wise layer types only)
@@ -411,7 +416,8 @@ bool parse_xconfig(kfp16_net* n, const char* text) {
       {"input", L_INPUT}, {"idct-layer", L_IDCT}, {"linear-component", L_LINEAR},
       {"batchnorm-component", L_BATCHNORM}, {"spec-augment-layer", L_SPECAUG},
       {"combine-feature-maps-layer", L_COMBINE}, {"conv-relu-batchnorm-layer", L_CONV},
-      {"tdnnf-layer", L_TDNNF}, {"prefinal-layer", L_PREFINAL}, {"output-layer", L_OUTPUT}};
+      {"tdnnf-layer", L_TDNNF}, {"prefinal-layer", L_PREFINAL}, {"output-layer", L_OUTPUT},
+      {"attention-relu-batchnorm-layer", L_ATTENTION}};
   std::stringstream ss(text);
   std::string line;
   int lineno = 0;
@@ -426,8 +432,7 @@ bool parse_xconfig(kfp16_net* n, const char* text) {
     l.type_name = tk[0];
     auto tt = types.find(tk[0]);
     if (tt == types.end()) {
-      set_error("xconfig line %d: unsupported layer type \"%s\"%s", lineno, tk[0].c_str(),
-                tk[0] == "attention-relu-batchnorm-layer" ? " (restricted self-attention runs on the CPU in the reference and is out of scope)" : "");
+      set_error("xconfig line %d: unsupported layer type \"%s\"", lineno, tk[0].c_str());
       return false;
     }
     l.type = tt->second;
@@ -552,6 +557,23 @@ bool resolve_dims(kfp16_net* n) {
         if (l.small_dim <= 0 || l.big_dim <= 0) { set_error("prefinal-layer %s missing small-dim or big-dim", l.name.c_str()); return false; }
         l.out_dim = l.small_dim;
         break;
+      case L_ATTENTION: {   // internal/nnet/layers.go:298-318; key-scale default 1/sqrt(key-dim) (weight_loader.go:267-271)
+        l.att_heads = kv_int(l, "num-heads", 1);
+        l.att_value = kv_int(l, "value-dim", 0);
+        l.att_key = kv_int(l, "key-dim", 0);
+        l.att_left = kv_int(l, "num-left-inputs", 0);
+        l.att_right = kv_int(l, "num-right-inputs", 0);
+        l.att_stride = kv_int(l, "time-stride", 1);
+        if (l.att_heads <= 0 || l.att_value <= 0 || l.att_key <= 0 || l.att_left < 0 || l.att_right < 0 || l.att_stride < 1) {
+          set_error("attention-relu-batchnorm-layer %s: num-heads, value-dim, key-dim must be positive, time-stride >= 1", l.name.c_str()); return false;
+        }
+        const int ctx_dim = 1 + l.att_left + l.att_right;
+        if (ctx_dim > 32) { set_error("attention-relu-batchnorm-layer %s: at most 32 context positions", l.name.c_str()); return false; }
+        l.att_scale = (float)kv_float(l, "key-scale", 1.0 / sqrt((double)l.att_key));
+        l.att_affine = l.att_heads * (2 * l.att_key + l.att_value + ctx_dim);
+        l.out_dim = l.att_heads * (l.att_value + ctx_dim);
+        break;
+      }
       case L_OUTPUT:
         l.out_dim = kv_int(l, "dim", 0);
         if (l.out_dim <= 0) { set_error("output-layer %s missing dim", l.name.c_str()); return false; }
@@ -606,7 +628,7 @@ bool resolve_dims(kfp16_net* n) {
       bool up = false;
       for (int src : l.in) {
         const Layer& s = n->layers[src];
-        bool own = s.type == L_LINEAR || s.type == L_TDNNF || s.type == L_PREFINAL || s.type == L_OUTPUT || s.type == L_CONV;
+        bool own = s.type == L_LINEAR || s.type == L_TDNNF || s.type == L_PREFINAL || s.type == L_OUTPUT || s.type == L_CONV || s.type == L_ATTENTION;
         up = up || own || has_params_upstream[src];
       }
       has_params_upstream[i] = up;
@@ -645,6 +667,10 @@ bool build_plan(kfp16_net* n) {
       case L_OUTPUT:
         l.pW = add_param(n, l.name + ".W", l.in_dim, l.out_dim);
         l.pB = add_param(n, l.name + ".Bias", 1, l.out_dim, true);
+        break;
+      case L_ATTENTION:   // the projection's true shape [in x heads*(2*key + value + context)] (forward.go:803-812; quirk Q1)
+        l.pW = add_param(n, l.name + ".W", l.in_dim, l.att_affine);
+        l.pB = add_param(n, l.name + ".Bias", 1, l.att_affine, true);
         break;
       case L_CONV:
         l.pW = add_param(n, l.name + ".W", l.convK, l.fout);
@@ -744,6 +770,22 @@ bool build_plan(kfp16_net* n) {
         }
         n->flops_fwd += 2.0 * M * (sp * l.in_dim) * l.bott_dim + 2.0 * M * (sp * l.bott_dim) * l.out_dim;
         if (train && l.needs_grad) n->flops_bwd += (l.wants_dx ? 2 : 1) * 2.0 * M * (sp * l.in_dim) * l.bott_dim + 2 * 2.0 * M * (sp * l.bott_dim) * l.out_dim;
+        break;
+      }
+      case L_ATTENTION: {
+        if (l.per_seq) { set_error("attention layer %s on a per-sequence input", l.name.c_str()); return false; }
+        if (!check_tma_dim(l, l.in_dim, "input dim") || !check_tma_dim(l, l.att_affine, "heads*(2*key-dim + value-dim + context)") ||
+            !check_tma_dim(l, l.out_dim, "heads*(value-dim + context)")) return false;
+        if (!alloc_buf(n, l.big, n->Tp, l.att_affine)) return false;         // projection
+        if (!alloc_buf(n, l.dz, n->Tp, l.out_dim)) return false;             // ReLU'd pre-batch-norm output (mask + attention weights)
+        if (!make_bn(n, l.bn, l.out_dim, 1.0f, false)) return false;
+        if (train && l.needs_grad) {
+          if (!alloc_buf(n, l.dbig, n->Tp, l.att_affine)) return false;
+          if (!dev_alloc(n, (void**)&l.att_db, (size_t)n->Tp * l.att_heads * 32 * sizeof(float))) return false;
+        }
+        l.fl_fwd = 2.0 * M * l.in_dim * l.att_affine;
+        if (train && l.needs_grad) l.fl_bwd = (l.wants_dx ? 2 : 1) * 2.0 * M * l.in_dim * l.att_affine;
+        n->flops_fwd += l.fl_fwd; n->flops_bwd += l.fl_bwd;
         break;
       }
       case L_PREFINAL: {
@@ -1214,6 +1256,19 @@ int forward_layer(kfp16_net* n, Layer& l) {
       if (tbn && train_bn_pass(n, l.bn, l.out.p, l.fout, mrows, l.fout, l.hout, nullptr, 0, 0.f, true)) return -1;
       break;
     }
+    case L_ATTENTION: {  // forward.go:795-909: projection GEMM, then the attention + ReLU + batch-norm in one kernel
+      kfp16_gemm_desc d = mk_desc(rows, l.att_affine, l.in_dim);
+      set_A(d, X.p, rows, l.in_dim);
+      set_B(d, W16(n, l.pW), l.in_dim, l.att_affine);
+      d.D[0] = l.big.p; d.ldd = l.att_affine;
+      d.flags = KFP16_EPI_BIAS | rr;
+      d.bias = W16(n, l.pB);
+      if (kfp16_gemm_ex(ctx, &d)) return -1;
+      if (train_bn_on(n)) { set_error("layer %s: train-mode batch-norm is not implemented for the attention layer", l.name.c_str()); return -1; }
+      if (kfp16_attention_forward(ctx, l.big.p, l.att_affine, l.dz.p, l.out.p, l.out_dim, l.bn.scale, l.bn.shift, n->opts.n_seq, n->opts.seq_len,
+                                  n->halo, l.att_heads, l.att_key, l.att_value, l.att_left, l.att_right, l.att_stride, l.att_scale)) return -1;
+      break;
+    }
     case L_OUTPUT: {     // forward.go:971-1001
       const bool view = fsub > 1 && !l.log_softmax;
       kfp16_gemm_desc d = mk_desc(view ? vrows : rows, l.out_dim, l.in_dim);
@@ -1454,6 +1509,21 @@ int backward_layer(kfp16_net* n, Layer& l) {
         if (kfp16_gemm_ex(ctx, &d)) return -1;
         if (kfp16_col2im(ctx, n->conv_dP, l.convKp, dx.p, n->opts.n_seq, n->opts.seq_len, n->halo, l.hin, l.hout, l.hsub, l.fin,
                          (int)l.tap_dt.size(), l.tap_dt.data(), l.tap_dh.data())) return -1;
+      }
+      break;
+    }
+    case L_ATTENTION: {   // exact transpose of the forward (the reference treats the layer as a plain affine: quirk Q2)
+      if (kfp16_attention_backward(ctx, l.big.p, l.att_affine, l.dz.p, l.dout.p, l.out_dim, l.bn.scale, l.att_db, l.dbig.p, n->opts.n_seq,
+                                   n->opts.seq_len, n->halo, l.att_heads, l.att_key, l.att_value, l.att_left, l.att_right, l.att_stride, l.att_scale)) return -1;
+      if (kfp16_colsum_accum(ctx, l.dbig.p, l.att_affine, rows, l.att_affine, G32(n, l.pB))) return -1;
+      if (wgrad(n, X, l.dbig, l.pW, 1, 0, 0)) return -1;
+      if (l.wants_dx) {
+        kfp16_gemm_desc d = mk_desc(rows, l.in_dim, l.att_affine);
+        set_A(d, l.dbig.p, rows, l.att_affine);
+        d.b_major = KFP16_K_MAJOR;
+        set_B(d, W16(n, l.pW), l.in_dim, l.att_affine);
+        d.D[0] = dx.p; d.ldd = l.in_dim;
+        if (kfp16_gemm_ex(ctx, &d)) return -1;
       }
       break;
     }

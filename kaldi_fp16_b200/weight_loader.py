@@ -248,6 +248,12 @@ def LoadWeights(net, components: Dict[str, KaldiComponent], strict: bool = True)
             elif ltype == "output-layer":
                 c = _need(components, f"{name}.affine")
                 total += _matrix(net, f"{name}.W", c) + _vector(net, f"{name}.Bias", c)
+            elif ltype == "attention-relu-batchnorm-layer":
+                # weight_loader.go:253-275: <name>.affine (projection), <name>.attention (<KeyScale>; the executor takes key-scale=
+                # from the xconfig, default 1/sqrt(key-dim) as the reference), <name>.batchnorm
+                aff = _need(components, f"{name}.affine")
+                total += _matrix(net, f"{name}.W", aff) + _vector(net, f"{name}.Bias", aff)
+                total += _bn(net, name, "BN", _need(components, f"{name}.batchnorm"), dim)
             else:
                 if ltype != "input":
                     skipped.append(name)

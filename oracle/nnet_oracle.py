@@ -111,6 +111,9 @@ def parse_xconfig(text: str) -> list:
             l.out_dim = gi("height-out", hin) * gi("num-filters-out", 0)
         elif t == "prefinal-layer":
             l.out_dim = gi("small-dim", 0)
+        elif t == "attention-relu-batchnorm-layer":
+            # internal/nnet/layers.go:298-318: output = num_heads * (value_dim + context_dim)
+            l.out_dim = gi("num-heads", 1) * (gi("value-dim", 0) + 1 + gi("num-left-inputs", 0) + gi("num-right-inputs", 0))
         else:
             raise ValueError(f"unsupported layer type {t}")
     return layers
@@ -180,6 +183,12 @@ class OracleNet:
                 self.params[f"{l.name}.Bias"] = np.zeros((1, l.out_dim), f32)
             elif t == "batchnorm-component":
                 self.bn[(l.name, "")] = identity_bn(l.in_dim)
+            elif t == "attention-relu-batchnorm-layer":
+                g = self.attention_geom(l)
+                # true shape of the projection (forward.go:803-812); the reference's random init allocates [in x out] (quirk Q1)
+                self.params[f"{l.name}.W"] = np.zeros((l.in_dim, g["affine"]), f32)
+                self.params[f"{l.name}.Bias"] = np.zeros((1, g["affine"]), f32)
+                self.bn[(l.name, "BN")] = identity_bn(l.out_dim)
             elif t == "conv-relu-batchnorm-layer":
                 taps = self.conv_taps(l)
                 fin = l.in_dim // int(l.kv["height-in"])
@@ -187,6 +196,72 @@ class OracleNet:
                 self.params[f"{l.name}.W"] = np.zeros((len(taps) * fin, fout), f32)
                 self.params[f"{l.name}.Bias"] = np.zeros((1, fout), f32)
                 self.bn[(l.name, "BN")] = identity_bn(fout)
+
+    def attention_geom(self, l: OLayer) -> dict:
+        """restricted self-attention geometry (internal/nnet/forward.go:795-812): per head the projection row holds
+        [key (key-dim) | value (value-dim) | query key part (key-dim) | query context part (context)]"""
+        gi = lambda k, d: int(l.kv.get(k, d))
+        H, V, K = gi("num-heads", 1), gi("value-dim", 0), gi("key-dim", 0)
+        nl, nr = gi("num-left-inputs", 0), gi("num-right-inputs", 0)
+        C = 1 + nl + nr
+        per = K + V + K + C
+        ks = float(l.kv["key-scale"]) if "key-scale" in l.kv else 1.0 / math.sqrt(K)      # weight_loader.go:267-271
+        return dict(H=H, V=V, K=K, nl=nl, nr=nr, C=C, per=per, affine=H * per, stride=gi("time-stride", 1), ks=f32(ks))
+
+    def _ctx_rows(self, a, shift):
+        """a: [n_seq, L, ...]; result[t] = a[t + shift], zeros outside the sequence (the reference pads the whole minibatch
+        matrix with zeros, forward.go:833-845: per sequence here, quirk Q3)"""
+        out = np.zeros_like(a)
+        L = a.shape[1]
+        lo, hi = max(0, -shift), min(L, L - shift)
+        if hi > lo:
+            out[:, lo:hi] = a[:, lo + shift:hi + shift]
+        return out
+
+    def _attention_fwd(self, l, x, P, saved):
+        """forward.go:795-909: affine projection -> per head and frame: b[o] = q_ctx[o] + key_scale * <q_key, key[t + (o-nl)*s]>,
+        w = softmax(b), out = [sum_o w[o] * value[t + (o-nl)*s] | w] -> ReLU -> batch-norm (the attention itself in fp32)"""
+        g = self.attention_geom(l)
+        H, V, K, C, per = g["H"], g["V"], g["K"], g["C"], g["per"]
+        proj = O.add_bias(O.gemm(x, P[f"{l.name}.W"]), P[f"{l.name}.Bias"])
+        p4 = proj.reshape(self.n_seq, self.L, H, per).astype(f32)
+        key, val, qk, qc = p4[..., :K], p4[..., K:K + V], p4[..., K + V:2 * K + V], p4[..., 2 * K + V:]
+        keys = [self._ctx_rows(key, (o - g["nl"]) * g["stride"]) for o in range(C)]
+        vals = [self._ctx_rows(val, (o - g["nl"]) * g["stride"]) for o in range(C)]
+        b = np.stack([qc[..., o] + g["ks"] * np.sum(qk * keys[o], axis=-1, dtype=f32) for o in range(C)], axis=-1).astype(f32)
+        e = np.exp(b - b.max(axis=-1, keepdims=True)).astype(f32)
+        w = (e / e.sum(axis=-1, keepdims=True, dtype=f32)).astype(f32)
+        u = np.zeros(p4.shape[:3] + (V,), f32)
+        for o in range(C):
+            u += w[..., o:o + 1] * vals[o]
+        out = np.concatenate([u, w], axis=-1).reshape(self.n_seq * self.L, H * (V + C))
+        z = h(np.maximum(out, f32(0)))
+        saved[l.name].update(proj=proj, w=w, keys=keys, vals=vals, qk=qk, mask=z > 0, geom=g)
+        return self._bn_fwd(z, self.bn[(l.name, "BN")])
+
+    def _attention_bwd(self, l, dy, sv, P, wg):
+        """exact transpose of _attention_fwd (the reference back-propagates the layer as a plain affine + ReLU + BN,
+        network_backward.go:539-545: quirk Q2)"""
+        g = sv["geom"]
+        H, V, K, C, per = g["H"], g["V"], g["K"], g["C"], g["per"]
+        dz = np.where(sv["mask"], h(dy * self._bn_scale(self.bn[(l.name, "BN")])), f32(0)).reshape(self.n_seq, self.L, H, V + C)
+        dU, dWt = dz[..., :V], dz[..., V:]
+        w = sv["w"]
+        gw = np.stack([dWt[..., o] + np.sum(dU * sv["vals"][o], axis=-1, dtype=f32) for o in range(C)], axis=-1).astype(f32)
+        db = (w * (gw - np.sum(w * gw, axis=-1, keepdims=True, dtype=f32))).astype(f32)
+        dp = np.zeros((self.n_seq, self.L, H, per), f32)
+        dp[..., 2 * K + V:] = db
+        for o in range(C):
+            shift = (o - g["nl"]) * g["stride"]
+            dp[..., K + V:2 * K + V] += g["ks"] * db[..., o:o + 1] * sv["keys"][o]
+            # rows t + shift received key / value gradients from query frame t: the adjoint of _ctx_rows is the opposite shift
+            dp[..., :K] += self._ctx_rows(g["ks"] * db[..., o:o + 1] * sv["qk"], -shift)
+            dp[..., K:K + V] += self._ctx_rows(w[..., o:o + 1] * dU, -shift)
+        dproj = h(dp.reshape(self.n_seq * self.L, H * per))
+        x = sv["x"]
+        wg[f"{l.name}.W"] = x.T.astype(f32) @ dproj
+        wg[f"{l.name}.Bias"] = dproj.sum(0, dtype=f32).reshape(1, -1)
+        return O.gemm(dproj, P[f"{l.name}.W"], transB=True)
 
     def conv_taps(self, l: OLayer) -> list:
         to = [int(v) for v in l.kv.get("time-offsets", "0").split(",")]
@@ -385,6 +460,8 @@ class OracleNet:
                 y = O.gemm(g, P[f"{l.name}.SmallW"])
                 y = self._bn_fwd(y, self.bn[(l.name, "BN")])
                 saved[l.name].update(g=g, mask=mask)
+            elif t == "attention-relu-batchnorm-layer":
+                y = self._attention_fwd(l, x, P, saved)
             elif t == "output-layer":
                 y = O.gemm(x, P[f"{l.name}.W"])
                 y = O.add_bias(y, P[f"{l.name}.Bias"])
@@ -473,6 +550,8 @@ class OracleNet:
                 wg[f"{l.name}.BigBias"] = dg.sum(0, dtype=f32).reshape(1, -1)
                 wg[f"{l.name}.BigW"] = x.T.astype(f32) @ dg
                 dx = O.gemm(dg, P[f"{l.name}.BigW"], transB=True)
+            elif t == "attention-relu-batchnorm-layer":
+                dx = self._attention_bwd(l, dy, sv, P, wg)
             elif t == "output-layer":
                 wg[f"{l.name}.W"] = x.T.astype(f32) @ dy
                 wg[f"{l.name}.Bias"] = dy.sum(0, dtype=f32).reshape(1, -1)

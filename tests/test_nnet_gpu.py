@@ -821,3 +821,51 @@ def test_kaldi_weight_import_export(handle, lib):
     assert np.array_equal(out["tdnnf4.batchnorm"].StatsVar, parsed["tdnnf4.batchnorm"].StatsVar)
     assert np.array_equal(out["cnn3.batchnorm"].StatsMean, parsed["cnn3.batchnorm"].StatsMean)
     net.Free()
+
+
+ATTNET = """
+input name=input dim=40
+linear-component name=lin0 dim=64
+tdnnf-layer name=tdnnf1 dim=64 bottleneck-dim=32 time-stride=1 bypass-scale=0.66
+attention-relu-batchnorm-layer name=attention1 num-heads=4 value-dim=10 key-dim=8 num-left-inputs=3 num-right-inputs=2 time-stride=3
+tdnnf-layer name=tdnnf2 dim=64 bottleneck-dim=32 time-stride=3 bypass-scale=0.66
+output-layer name=output include-log-softmax=false dim=48
+"""
+
+
+@REF_ROUND
+@pytest.mark.parametrize("n_seq,L", [(3, 29), (1, 7)])
+def test_restricted_self_attention_layer(handle, lib, n_seq, L, ref_round):
+    """attention-relu-batchnorm-layer on the device (the reference runs it on the CPU between a D2H and an H2D copy,
+    internal/nnet/forward.go:795-909): projection GEMM + one attention / ReLU / batch-norm kernel, per-sequence zero padding of
+    the context; backward = the exact transpose in two gather passes -- against the oracle (itself checked against the
+    reference's loop nest and a float64 autograd in tests/test_nnet_oracle_cpu.py).  4 heads x (10 + 6) = 64 outputs,
+    4 x (8 + 10 + 8 + 6) = 128 projection columns; L = 7 is shorter than the context span."""
+    on, net, rng = make_pair(handle, ATTNET, n_seq, L, seed=41 + L, ref_round=ref_round)
+    x = O.to_f16_rne(rng.standard_normal((n_seq * L, 40)).astype(np.float32))
+    acts = on.forward({"input": x})
+    net.SetInput("input", x)
+    assert lib.kfp16_net_forward(net.ptr) == 0
+    for name in ("tdnnf1", "attention1", "tdnnf2", "output"):
+        err = rel_to_scale(net.Output(name), acts[name])
+        assert err <= 2e-3, f"forward {name}: err {err:.2e}"
+    att = net.Output("attention1").reshape(n_seq * L, 4, 16)
+    masks = {name: net.Mask(name, 64) for name in ("tdnnf1", "tdnnf2")}
+    for name, m in masks.items():
+        assert np.mean(m != on.saved[name]["mask"]) < 5e-3
+    wg, dact = on.backward("output", acts["output"], masks)
+    net.ZeroGrads()
+    net.Backward(None)
+    got = net.WeightGrads()
+    for k, g in wg.items():
+        err = rel_to_scale(got[k], g)
+        assert err <= (1e-2 if k.endswith("Bias") else 5e-3), f"weight grad {k}: err {err:.2e}"
+    assert rel_to_scale(net.Grad("tdnnf1"), dact["tdnnf1"]) <= 5e-3
+    # identity-free check of the softmax: before the batch-norm the last 6 columns of every head are weights that sum to 1;
+    # with the randomised batch-norm undone they still do
+    bn = on.bn[("attention1", "BN")]
+    sc = (bn["gamma"] / np.sqrt(bn["var"] + np.float32(bn["eps"]))).reshape(4, 16)
+    sh = (bn["beta"] - bn["mean"] * sc.reshape(-1)).reshape(4, 16)
+    wsum = ((att - sh) / sc)[..., 10:].sum(-1)
+    assert np.abs(wsum - 1.0).max() < 2e-2
+    net.Free()

@@ -242,3 +242,72 @@ def test_spec_augment_masks_geometry():
     off = OracleNet(xc, n_seq, L, train=True, dropout_seed=77)          # default: the reference executor's pass-through
     off.params = on.params
     assert np.array_equal(off.forward({"input": x})["sa"], off.acts["pre"])
+
+
+def test_attention_backward_matches_float64_autograd(monkeypatch):
+    """restricted self-attention (internal/nnet/forward.go:795-909): the oracle's forward against a direct restatement of
+    the reference's loop nest (padded rows, per-head softmax over the context positions) and its backward -- the exact
+    transpose, which the reference replaces by a plain affine backward (quirk Q2) -- against a float64 autograd"""
+    import torch
+
+    import oracle.nnet_oracle as NO
+
+    ident = lambda v: np.asarray(v, dtype=np.float32)   # noqa: E731
+    monkeypatch.setattr(O, "h", ident)
+    monkeypatch.setattr(NO, "h", ident)
+    H, V, K, nl, nr, s = 2, 8, 6, 2, 1, 2
+    C = 1 + nl + nr
+    per = 2 * K + V + C
+    xc = ("input name=input dim=24\nlinear-component name=lin dim=32\n"
+          f"attention-relu-batchnorm-layer name=att num-heads={H} value-dim={V} key-dim={K} num-left-inputs={nl} num-right-inputs={nr} time-stride={s}\n"
+          "output-layer name=output dim=16 include-log-softmax=false\n")
+    n_seq, L = 2, 11
+    rng = np.random.default_rng(5)
+    net = OracleNet(xc, n_seq, L)
+    net.init_random(rng)
+    assert net.params["att.W"].shape == (32, H * per) and net.by_name["att"].out_dim == H * (V + C)
+    net.params["att.Bias"] = (rng.standard_normal((1, H * per)) * 0.1).astype(np.float32)
+    x = rng.standard_normal((n_seq * L, 24)).astype(np.float32)
+    acts = net.forward({"input": x})
+    out = acts["output"]
+    wg, _ = net.backward("output", out)
+    ks = 1.0 / np.sqrt(K)
+    bn = 1.0 / np.sqrt(1.0 + 1e-3)
+    # the reference's loop nest on one sequence (forward.go:833-895), float64
+    proj = (acts["lin"].astype(np.float64) @ net.params["att.W"] + net.params["att.Bias"])[:L]
+    padded = np.zeros((L + (nl + nr) * s, H * per))
+    padded[nl * s:nl * s + L] = proj
+    want = np.zeros((L, H * (V + C)))
+    for hd in range(H):
+        for t in range(L):
+            q = padded[t + nl * s, hd * per:(hd + 1) * per]
+            b = np.array([q[2 * K + V + o] + ks * np.dot(q[K + V:2 * K + V], padded[t + o * s, hd * per:hd * per + K]) for o in range(C)])
+            w = np.exp(b - b.max())
+            w /= w.sum()
+            for o in range(C):
+                want[t, hd * (V + C):hd * (V + C) + V] += w[o] * padded[t + o * s, hd * per + K:hd * per + K + V]
+            want[t, hd * (V + C) + V:(hd + 1) * (V + C)] = w
+    assert np.abs(acts["att"][:L] - np.maximum(want, 0) * bn).max() < 1e-5
+    # float64 autograd of the whole net
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in net.params.items()}
+    h1 = torch.tensor(x, dtype=torch.float64) @ P["lin.W"]
+    pj = (h1 @ P["att.W"] + P["att.Bias"]).reshape(n_seq, L, H, per)
+
+    def ctx(a, d):
+        o = torch.zeros_like(a)
+        lo, hi = max(0, -d), min(L, L - d)
+        if hi > lo:
+            o[:, lo:hi] = a[:, lo + d:hi + d]
+        return o
+
+    key, val, qk, qc = pj[..., :K], pj[..., K:K + V], pj[..., K + V:2 * K + V], pj[..., 2 * K + V:]
+    bb = torch.stack([qc[..., o] + ks * (qk * ctx(key, (o - nl) * s)).sum(-1) for o in range(C)], -1)
+    ww = torch.softmax(bb, -1)
+    u = sum(ww[..., o:o + 1] * ctx(val, (o - nl) * s) for o in range(C))
+    a = torch.relu(torch.cat([u, ww], -1).reshape(n_seq * L, H * (V + C))) * bn
+    o_ = a @ P["output.W"] + P["output.Bias"]
+    (0.5 * (o_ ** 2).sum()).backward()
+    assert np.abs(o_.detach().numpy() - out).max() < 1e-4
+    for k, gk in wg.items():
+        want_g = P[k].grad.numpy()
+        assert np.abs(want_g - gk).max() <= 2e-5 * np.abs(want_g).max(), k
