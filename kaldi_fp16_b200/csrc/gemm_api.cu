@@ -389,7 +389,10 @@ int kfp16_gemm_ex(kfp16_ctx* ctx, const kfp16_gemm_desc* d) {
     // (Keeping the weight tiles of a narrow layer resident in shared memory instead of streaming them per M tile was measured
     //  too: cnn2 60 -> 62 us, cnn3 39 -> 44 us -- those kernels are bound by the per-tile epilogue / accumulator hand-over of
     //  their 120 x 64 tiles, not by the 73 KB of weights per tile -- and the extra branches in the issue loop cost the wider
-    //  layers 10 %.  Not kept.)
+    //  layers 10 %.  Not kept.  Four input-box buffers instead of two: no change either.  The per-role clock stamps
+    //  (scripts/conv_tile_profile.py) show the MMA phase itself taking ~4.5k cycles per 240 x 64 pair tile: with N = 64 every
+    //  UMMA re-reads 4 KB of A from shared memory for 64 output columns, so the tensor core is bound by its operand reads,
+    //  not by its math -- inherent to 64-filter layers.)
     const bool narrow = d->N <= 128 || d->no_share == 5;
     if (planes_ok && narrow && cs_tbox >= 1 && kind_ok && cs_tbox + cs_dtspan <= 256 && cs_sl <= 256) {
       const int rows_alloc = cs_dtspan * cs_sl + hspan + kBM;           // furthest row a shifted 128-row read touches

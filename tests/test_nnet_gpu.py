@@ -280,7 +280,8 @@ def test_graph_replay_equals_eager(handle, lib):
 
 def test_xconfig_errors(handle, lib):
     """unsupported / malformed models fail loudly with a message (no silent fallback)"""
-    for bad, frag in [("input name=input dim=40\nattention-relu-batchnorm-layer name=a num-heads=2", b"out of scope"),
+    for bad, frag in [("input name=input dim=40\nattention-relu-batchnorm-layer name=a num-heads=2", b"value-dim, key-dim must be positive"),
+                      ("input name=input dim=40\nlstm-layer name=l cell-dim=64", b"unsupported layer type"),
                       ("input name=input dim=40\nlinear-component name=l", b"missing dim"),
                       ("input name=input dim=40\nlinear-component name=l dim=64 input=nope", b"not found"),
                       ("input name=input dim=40\ntdnnf-layer name=t dim=100 bottleneck-dim=20 time-stride=3", b"multiple")]:
