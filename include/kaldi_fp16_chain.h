@@ -8,8 +8,11 @@
  * FST, loss = -(num_logprob - den_logprob), grad = clamp((den_post - num_post) * weight, +-30) stored as FP16 -- as ONE
  * kernel launch for the whole minibatch and no host involvement per frame or per sequence.
  *
- * The reference's own chain_* / den_* symbols (cpp/include/chain.h, chain_den.h, chain_backward_api.h) are NOT redefined
- * here: a Go build that still wants them links the reference's chain objects beside this library.
+ * The reference's core chain entry points (cpp/include/chain.h:47-160: chain_forward_backward, chain_compute_posteriors,
+ * chain_compute_loss, chain_workspace_bytes, chain_last_error / chain_clear_error) are exported too, with the reference's
+ * signatures, on top of these kernels (csrc/chain_compat.cu) -- internal/nnet/chain_loss.go links unchanged.  The den_* (leaky-HMM
+ * denominator on host buffers), chain_num_* / chain_*_det and chain_backward_api.h symbols are NOT redefined: a Go build that
+ * still wants them links those reference objects beside this library.
  */
 #ifndef KALDI_FP16_CHAIN_H
 #define KALDI_FP16_CHAIN_H
@@ -60,6 +63,34 @@ int kfp16_chain_force_general(kfp16_chain *chain, int on);
 int kfp16_chain_set_debug(kfp16_chain *chain, void *dev_i64x8);
 int kfp16_chain_num_sequences(const kfp16_chain *chain);
 int kfp16_chain_frames(const kfp16_chain *chain);
+
+/* ---- the reference's own interface (cpp/include/chain.h:24-160), same names / structs / semantics ------------------------- */
+/* FST in CSR form with DEVICE pointers (chain.h:24-36) */
+typedef struct {
+    int32_t *row_ptr;      /* [num_states + 1] */
+    int32_t *col_idx;      /* [num_arcs] destination states */
+    int32_t *labels;       /* [num_arcs] pdf-ids, 1-indexed, 0 = epsilon */
+    float *weights;        /* [num_arcs] log-weights */
+    int32_t *final_states; /* [num_final] */
+    float *final_weights;  /* [num_final] */
+    int num_states, num_arcs, num_final, start_state;
+} ChainFstGPU;
+typedef struct { float num_logprob, den_logprob, loss; } ChainLossResult; /* chain.h:39-45 */
+
+/* alpha / beta: caller-allocated fp32 [(T+1) x num_states] on the device (chain_workspace_bytes covers both);
+ * *total_logprob (host) = logsum over final states of alpha[T][s] + final weight.  chain.h:47-66 */
+int chain_forward_backward(const void *nnet_output, const ChainFstGPU *fst, int T, int num_pdfs, float *alpha, float *beta,
+                           float *total_logprob);
+/* posteriors: fp32 [T x num_pdfs] on the device, zeroed by the call.  chain.h:68-84 */
+int chain_compute_posteriors(const void *nnet_output, const ChainFstGPU *fst, int T, int num_pdfs, const float *alpha,
+                             const float *beta, float total_logprob, float *posteriors);
+/* loss = -(num_logprob - den_logprob); grad_output (FP16 [T x num_pdfs], may be NULL) = clamp(den_post - num_post, +-30).
+ * chain.h:86-108; here one launch of the batched objective kernel for a single sequence */
+int chain_compute_loss(const void *nnet_output, const ChainFstGPU *num_fst, const ChainFstGPU *den_fst, int T, int num_pdfs,
+                       void *grad_output, ChainLossResult *result);
+size_t chain_workspace_bytes(int T, int num_states);
+const char *chain_last_error(void);
+void chain_clear_error(void);
 
 #ifdef __cplusplus
 }

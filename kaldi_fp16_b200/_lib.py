@@ -227,6 +227,13 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_chain_read_results": (c_int, [c_void_p, c_void_p, c_int]),
     "kfp16_chain_force_general": (c_int, [c_void_p, c_int]),
     "kfp16_chain_set_debug": (c_int, [c_void_p, c_void_p]),
+    # the reference's own chain interface (cpp/include/chain.h), exported on top of the kernels above (csrc/chain_compat.cu)
+    "chain_forward_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, FP]),
+    "chain_compute_posteriors": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
+    "chain_compute_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "chain_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "chain_last_error": (C.c_char_p, []),
+    "chain_clear_error": (None, []),
     "kfp16_chain_num_sequences": (c_int, [c_void_p]),
     "kfp16_chain_frames": (c_int, [c_void_p]),
     "kfp16_net_loss_chain": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int, c_float]),

@@ -52,6 +52,9 @@ def load_ref():
     sig.update({
         "bridge_transfer_int32": (ci, [vp, vp, C.c_size_t]),
         "chain_compute_loss": (ci, [vp, vp, vp, ci, ci, vp, vp]),
+        "chain_forward_backward": (ci, [vp, vp, ci, ci, vp, vp, C.POINTER(C.c_float)]),
+        "chain_compute_posteriors": (ci, [vp, vp, ci, ci, vp, vp, cf, vp]),
+        "chain_workspace_bytes": (C.c_size_t, [ci, ci]),
         "chain_last_error": (C.c_char_p, []),
     })
     for name, (res, args) in sig.items():
@@ -135,3 +138,12 @@ def ref_chain_fst(lib, fst) -> tuple:
     f.final_states, f.final_weights = up_i32(fst.final_states), up_f32(fst.final_weights)
     f.num_states, f.num_arcs, f.num_final, f.start_state = fst.num_states, fst.num_arcs, len(fst.final_states), fst.start_state
     return f, bufs
+
+
+def read_f32(ptr: int, shape) -> np.ndarray:
+    """device fp32 buffer -> host (plain cudaMemcpy: the pointer may come from either library's allocator)"""
+    from kaldi_fp16_b200 import cudart
+    out = np.empty(shape, np.float32)
+    cudart.synchronize()
+    cudart.check(cudart.rt().cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(ptr), C.c_size_t(out.nbytes), C.c_int(2)), "cudaMemcpy D2H")
+    return out

@@ -22,7 +22,7 @@ def declared_functions() -> dict:
         text = re.sub(r"//[^\n]*", "", text)
         text = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
         text = re.sub(r"enum\s*\{.*?\}\s*;", "", text, flags=re.S)
-        for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b((?:kfp16|ops|bridge|kaldi|launch)_\w+)\s*\(", text):
+        for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b((?:kfp16|ops|bridge|kaldi|launch|chain)_\w+)\s*\(", text):
             out[m.group(2)] = hdr.name
     return out
 

@@ -13,7 +13,7 @@ from kaldi_fp16_b200 import gpu, nnet
 from oracle import chain_oracle as CO
 from oracle import kaldi_oracle as O
 from oracle.nnet_oracle import OracleNet
-from tests.refbind import RefBuf, RefChainResult, ref_chain_fst
+from tests.refbind import RefBuf, RefChainResult, read_f32, ref_chain_fst
 
 pytestmark = pytest.mark.gpu
 
@@ -198,3 +198,73 @@ def test_output_frame_rows_backward_equals_dense(handle, lib, n_seq, L, frames, 
     for k in wb:
         scale = max(np.abs(wb[k]).max(), 1e-12)
         assert np.abs(wa[k] - wb[k]).max() <= 2e-6 * scale + 1e-7, k      # fp32 sums over a third of the rows: order only
+
+
+@pytest.mark.parametrize("T,P,S,arcs,branch", [(14, 104, 24, 4, False), (50, 6016, 256, 4, False), (9, 40, 7, 3, True)])
+def test_reference_chain_entry_points(handle, lib, reflib, T, P, S, arcs, branch):
+    """chain_forward_backward / chain_compute_posteriors / chain_compute_loss / chain_workspace_bytes exported with the
+    reference's signatures (cpp/include/chain.h:47-160; internal/nnet/chain_loss.go:189,309,325 binds them): against the numpy
+    oracle and against the same calls into the reference's own library (oracle/_ref), FSTs with device pointers as the Go side
+    uploads them"""
+    rng = np.random.default_rng(T * 7 + P)
+    den, nums = make_case(rng, 1, T, P, S, arcs, branch)
+    num = nums[0]
+    out = O.to_f16_rne((rng.standard_normal((T, P)) * 0.7).astype(np.float32))
+    # inputs live in the reference library's allocations (plain cudaMalloc): both libraries read the same buffers
+    t_out = RefBuf(reflib, out.astype(np.float16).view(np.uint16))
+    assert lib.chain_workspace_bytes(T, S) == reflib.chain_workspace_bytes(T, S) == 2 * (T + 1) * S * 4
+    for fst in (num, den):
+        f_ref, bufs = ref_chain_fst(reflib, fst)
+        Sn = fst.num_states
+        res = {}
+        for name, L in (("ours", lib), ("ref", reflib)):
+            alpha = RefBuf(reflib, np.zeros(((T + 1), Sn), np.float32))
+            beta = RefBuf(reflib, np.zeros(((T + 1), Sn), np.float32))
+            post = RefBuf(reflib, np.full((T, P), 5.0, np.float32))
+            total = C.c_float(0)
+            assert L.chain_forward_backward(t_out.ptr, C.byref(f_ref), T, P, alpha.ptr, beta.ptr, C.byref(total)) == 0, L.chain_last_error()
+            assert L.chain_compute_posteriors(t_out.ptr, C.byref(f_ref), T, P, alpha.ptr, beta.ptr, total.value, post.ptr) == 0
+            host = [read_f32(alpha.ptr, (T + 1, Sn)), read_f32(beta.ptr, (T + 1, Sn)), read_f32(post.ptr, (T, P))]
+            res[name] = (total.value, host)
+            for b_ in (alpha, beta, post):
+                b_.free()
+        a_o, b_o, tot_o = CO.forward_backward(out, fst)
+        p_o = CO.posteriors(out, fst, a_o, b_o, tot_o)
+        assert abs(res["ours"][0] - tot_o) <= 1e-3 * T and abs(res["ours"][0] - res["ref"][0]) <= 1e-3 * T
+        ga, gb, gp = res["ours"][1]
+        live = a_o > CO.LOG_ZERO / 2
+        assert np.array_equal(ga > CO.LOG_ZERO / 2, live) and np.abs(ga[live] - a_o[live]).max() <= 1e-3 * T      # alpha, state by state
+        live = b_o > CO.LOG_ZERO / 2
+        assert np.array_equal(gb > CO.LOG_ZERO / 2, live) and np.abs(gb[live] - b_o[live]).max() <= 1e-3 * T      # beta
+        assert np.abs(gp - p_o).max() <= 2e-3 and np.abs(gp - res["ref"][1][2]).max() <= 2e-3                      # posteriors
+        assert np.abs(gp.sum(1) - 1.0).max() <= 5e-3          # every frame's posteriors sum to one
+        for p in bufs:
+            reflib.bridge_gpu_free(p)
+    # chain_compute_loss: same struct, same buffers
+    num_ref, nb = ref_chain_fst(reflib, num)
+    den_ref, db = ref_chain_fst(reflib, den)
+    want = CO.chain_loss(out, num, den)
+    got = {}
+    for name, L in (("ours", lib), ("ref", reflib)):
+        g = RefBuf(reflib, np.zeros((T, P), np.uint16))
+        r = RefChainResult()
+        assert L.chain_compute_loss(t_out.ptr, C.byref(num_ref), C.byref(den_ref), T, P, g.ptr, C.byref(r)) == 0, L.chain_last_error()
+        got[name] = (r.num_logprob, r.den_logprob, r.loss, g.f32())
+        g.free()
+    for k in range(3):
+        assert abs(got["ours"][k] - want[k]) / T <= 1e-3, (k, got["ours"][k], want[k])
+        assert abs(got["ours"][k] - got["ref"][k]) / T <= 1e-3
+    assert np.abs(got["ours"][3] - want[3]).max() <= 2e-3
+    assert np.abs(got["ours"][3] - got["ref"][3]).max() <= 2e-3 + 2.0 ** -10
+    # no gradient requested
+    r = RefChainResult()
+    assert lib.chain_compute_loss(t_out.ptr, C.byref(num_ref), C.byref(den_ref), T, P, None, C.byref(r)) == 0
+    assert abs(r.loss - want[2]) / T <= 1e-3
+    # errors are reported through chain_last_error
+    assert lib.chain_compute_loss(None, C.byref(num_ref), C.byref(den_ref), T, P, None, C.byref(r)) == -1
+    assert b"bad argument" in lib.chain_last_error()
+    lib.chain_clear_error()
+    assert lib.chain_last_error() is None
+    for p in nb + db:
+        reflib.bridge_gpu_free(p)
+    t_out.free()
