@@ -741,13 +741,13 @@ def test_train_mode_batchnorm(handle, lib, ref_round):
     got_wg = net.WeightGrads()
     for k, g in wg.items():
         err = rel_to_scale(got_wg[k], g)
-        assert err <= (1e-2 if k.endswith("Bias") else 6e-3), f"train-BN weight grad {k}: err {err:.2e}"
+        assert err <= (1.5e-2 if k.endswith("Bias") else 8e-3), f"train-BN weight grad {k}: err {err:.2e}"
     # off again: running statistics (now the updated ones) through the fused epilogues
     net.SetTrainBatchNorm(False)
     on.train_bn = False
     acts2 = on.forward({"input": x, "ivector": iv})
     assert lib.kfp16_net_forward(net.ptr) == 0
-    assert rel_to_scale(net.Output("output"), acts2["output"]) <= 3e-3
+    assert rel_to_scale(net.Output("output"), acts2["output"]) <= 5e-3
     assert rel_to_scale(acts2["output"], acts["output"]) > 1e-2       # ... which is a different function
     net.Free()
 
