@@ -68,7 +68,6 @@ _SCALAR_I = {"<NumFiltersIn>": "NumFiltersIn", "<NumFiltersOut>": "NumFiltersOut
              "<HeightOut>": "HeightOut", "<NumHeads>": "NumHeads", "<KeyDim>": "KeyDim", "<ValueDim>": "ValueDim"}
 _MATRIX_TAGS = {"<LinearParams>": "LinearParams", "<Params>": "LinearParams", "<BiasParams>": "BiasParams",
                 "<StatsMean>": "StatsMean", "<StatsVar>": "StatsVar"}
-_TOKEN = re.compile(r"<[^<>\s]+>|\[|\]|[^\s\[\]<>]+")
 
 
 def _parse_matrix(body: str) -> np.ndarray:
