@@ -230,24 +230,29 @@ col2im_small_kernel2(const __half* __restrict__ dP, __half* __restrict__ dx, Con
   // rows).  Eight 16-byte loads in flight per thread: with one at a time the block spent ~12 load latencies here (measured
   // 47 us for the whole kernel, twice what the 64 MB it moves need)
   {
-    const int upr = g.Kp >> 3;                        // 16-byte units per patch row
-    const int total = nfr * frame_units;
-    const uint4* src = reinterpret_cast<const uint4*>(dP) + (ptrdiff_t)(r0 - dtmax) * frame_units;
-    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
-      uint4 v[8];
+    // (no integer division in this loop: with one per load -- frame = i / frame_units, row = u / units-per-row -- the kernel was
+    //  bound by the divisions' instruction count: 43 us for 64 MB)
+    const int upr_log2 = 31 - __clz(g.Kp >> 3);       // 16-byte units per patch row: a power of two (checked by the launcher)
+    const uint4* src0 = reinterpret_cast<const uint4*>(dP) + (ptrdiff_t)(r0 - dtmax) * frame_units;
+    for (int fr0 = 0; fr0 < nfr; fr0 += 4) {
+      for (int u0 = threadIdx.x; u0 < frame_units; u0 += 2 * blockDim.x) {
+        uint4 v[4][2];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int i = i0 + k * (int)blockDim.x;
-        v[k] = make_uint4(0, 0, 0, 0);
-        if (i < total && sfr_ok[i / frame_units]) v[k] = src[i];
-      }
+        for (int f = 0; f < 4; ++f)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int i = i0 + k * (int)blockDim.x;
-        if (i < total) {
-          const int fr = i / frame_units, u = i - fr * frame_units;
-          *reinterpret_cast<uint4*>(sp + (size_t)fr * g.hout * pitch + (u / upr) * pitch + (u % upr) * 8) = v[k];
-        }
+          for (int h = 0; h < 2; ++h) {
+            const int fr = fr0 + f, u = u0 + h * (int)blockDim.x;
+            v[f][h] = make_uint4(0, 0, 0, 0);
+            if (fr < nfr && u < frame_units && sfr_ok[fr]) v[f][h] = src0[(ptrdiff_t)fr * frame_units + u];
+          }
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int fr = fr0 + f, u = u0 + h * (int)blockDim.x;
+            if (fr < nfr && u < frame_units)
+              *reinterpret_cast<uint4*>(sp + (size_t)fr * g.hout * pitch + (u >> upr_log2) * pitch + (u & ((1 << upr_log2) - 1)) * 8) = v[f][h];
+          }
       }
     }
   }
@@ -256,18 +261,21 @@ col2im_small_kernel2(const __half* __restrict__ dP, __half* __restrict__ dx, Con
   const int frame_halves = g.hout * pitch;
   for (int idx = threadIdx.x; idx < ldx; idx += blockDim.x) {
     const int hh = idx / g.fin, f = idx - hh * g.fin;
+    float acc[kScatterFrames];
+#pragma unroll
+    for (int fl = 0; fl < kScatterFrames; ++fl) acc[fl] = 0.f;
+    // taps outermost (their offsets are read once), the block's frames inside: each frame still sums its taps in tap order
+    for (int tap = 0; tap < taps.n; ++tap) {
+      const int ho = hh - taps.dh[tap];
+      if (ho < 0 || ho >= g.hout) continue;
+      const __half* col = sp + (dtmax - taps.dt[tap]) * frame_halves + ho * pitch + tap * g.fin + f;
+#pragma unroll
+      for (int fl = 0; fl < kScatterFrames; ++fl) acc[fl] += __half2float(col[fl * frame_halves]);
+    }
+#pragma unroll
     for (int fl = 0; fl < kScatterFrames; ++fl) {
       const int r = r0 + fl;
-      if (r >= total_rows) break;
-      float acc = 0.f;
-      if (srow_ok[fl]) {
-        for (int tap = 0; tap < taps.n; ++tap) {
-          const int ho = hh - taps.dh[tap];
-          if (ho < 0 || ho >= g.hout) continue;
-          acc += __half2float(sp[(fl + dtmax - taps.dt[tap]) * frame_halves + ho * pitch + tap * g.fin + f]);
-        }
-      }
-      dx[(size_t)r * ldx + idx] = __float2half_rn(acc);
+      if (r < total_rows) dx[(size_t)r * ldx + idx] = __float2half_rn(srow_ok[fl] ? acc[fl] : 0.f);
     }
   }
 }
@@ -354,8 +362,8 @@ int kfp16_col2im(kfp16_ctx* ctx, const void* dP, int Kp, void* dx, int n_seq, in
   cudaStream_t s = ctx ? ctx->stream : default_stream();
   int dtmin = dt[0], dtmax = dt[0];
   for (int i = 1; i < ntaps; ++i) { dtmin = std::min(dtmin, dt[i]); dtmax = std::max(dtmax, dt[i]); }
-  if (sub == 1 && hin == hout && (fin % 8) != 0 && Kp <= 64 && (Kp % 8) == 0 && dtmax - dtmin <= 6 && halo >= std::max(dtmax, -dtmin) &&
-      ((uintptr_t)dP & 15) == 0) {
+  if (sub == 1 && hin == hout && (fin % 8) != 0 && Kp <= 64 && (Kp % 8) == 0 && (((Kp >> 3) & ((Kp >> 3) - 1)) == 0) && dtmax - dtmin <= 6 &&
+      halo >= std::max(dtmax, -dtmin) && ((uintptr_t)dP & 15) == 0) {
     const size_t smem = (size_t)(kScatterFrames + dtmax - dtmin) * hout * (Kp + 8) * 2;
     if (smem <= 99 * 1024) {
       static bool attr = false;
