@@ -244,6 +244,8 @@ def main():
                     help="chain = LF-MMI on 50 output frames per sequence (default for cnn_tdnn: BASELINE configs[2] is a "
                          "chain-model SGD step); half_sq = 0.5*||out||^2, dY = Y (cmd/sgdtest/main.go:258-267)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 64 sequences per GPU (the contract's default); strong: 64 sequences in total, 64 / N per GPU (SURVEY 8d config 4)")
     ap.add_argument("--profile-steps", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -253,6 +255,13 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    global N_SEQ
+    global_seqs = N_SEQ * world
+    if args.scaling == "strong":
+        if N_SEQ % world:
+            raise SystemExit(f"--scaling strong: {N_SEQ} sequences do not divide over {world} ranks")
+        global_seqs = N_SEQ
+        N_SEQ = N_SEQ // world        # every use below (network, inputs, supervision) is per rank
 
     from kaldi_fp16_b200 import _lib, cudart, gpu, nnet
     lib = _lib.load()          # raises if the CUDA library is missing: there is no fallback
@@ -288,7 +297,10 @@ def main():
     out_dim = {"tdnnf_stack": 1536, "cnn_tdnn": 6016}[args.workload]
     objective = args.objective or ("chain" if args.workload == "cnn_tdnn" else "half_sq")
     # chain: posterior gradients in [-1, 1] on the output frames, averaged over them; half_sq: mean over frames x dims
-    grad_scale = 1.0 / (N_SEQ * CHAIN_FRAMES) if objective == "chain" else 1.0 / (N_SEQ * SEQ_LEN * out_dim)
+    # weak scaling keeps the per-rank scale (sum semantics over the ranks); strong scaling scales by the GLOBAL
+    # minibatch, so that the N-GPU step equals the 1-GPU step on the same 64 sequences
+    gs_seqs = global_seqs if args.scaling == "strong" else N_SEQ
+    grad_scale = 1.0 / (gs_seqs * CHAIN_FRAMES) if objective == "chain" else 1.0 / (gs_seqs * SEQ_LEN * out_dim)
     lr = LR_CHAIN if objective == "chain" else LR
     net = nnet.NewNetwork(nnet.BuildModelFromString(wl["xconfig"]()), handle, N_SEQ, SEQ_LEN, train=True, lr=lr,
                           momentum=0.9, ref_round=False, seed=42, grad_scale=grad_scale)
@@ -512,8 +524,9 @@ def main():
         out = {
             "impl": "ours", "metric": metric_name(args.workload), "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": wl["desc"], "frames_per_gpu_step": T, "global_frames_per_step": frames_per_step,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": wl["desc"] if args.scaling == "weak" else wl["desc"].replace("64 seqs x 150 frames per GPU", f"64 seqs x 150 frames in total, {N_SEQ} per GPU"),
+                       "frames_per_gpu_step": T, "global_frames_per_step": frames_per_step,
                        "parallelism": f"dp{world}" + (f", FP16 gradient all-reduce in {n_seg} buckets, the first overlapped with the conv front end's backward pass ({nccl_sms} SMs left to NCCL there)" if overlap else (", FP16 gradient all-reduce" if world > 1 else "")),
                        "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush",
                        "loss": ("chain LF-MMI (log-semiring numerator / denominator forward-backward, 50 output frames per sequence, one batched launch)"
