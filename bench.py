@@ -341,6 +341,7 @@ def main():
     #         N > 1: [step + FP16 gradient export] all-reduce(g16) [SGD on the reduced FP16 bucket]
     n_seg, seg_ranges = 0, []
     reducer = None
+    exchange = "nccl"
     if world > 1:
         from kaldi_fp16_b200 import dp
         if overlap:
@@ -350,7 +351,16 @@ def main():
         else:
             net.Capture(1 | 4)
         net.Capture(8)
-        reducer = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(f16=True), device=f"cuda:{local}"))
+        # the exchange: the library's own kernel over NVLink peer memory (KFP16_DP_EXCHANGE=nccl: torch.distributed's
+        # all-reduce; also what is left when the peers' buckets cannot be mapped -- the JSON line says which ran)
+        if not overlap and os.environ.get("KFP16_DP_EXCHANGE", "peer") == "peer":
+            try:
+                reducer = dp.PeerGradAllReducer(lib, handle.ptr, lib.kfp16_net_grads_f16(net.ptr), lib.kfp16_net_bucket_size(net.ptr))
+                exchange = "peer"
+            except RuntimeError as e:
+                print(f"[bench] rank {rank}: {e}; using the NCCL all-reduce", file=sys.stderr)
+        if exchange != "peer":
+            reducer = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(f16=True), device=f"cuda:{local}"))
         comm_stream = torch.cuda.Stream(device=local, priority=-1)
     else:
         net.Capture(1)
@@ -361,6 +371,10 @@ def main():
         concatenated batch (up to FP16 rounding of the per-rank gradients)"""
         if world == 1:
             net.Launch(1)
+            return
+        if exchange == "peer":
+            net.Launch(1 | 4)
+            reducer.all_reduce()                           # one kernel on the step's stream
             return
         if not overlap:
             net.Launch(1 | 4)
@@ -474,6 +488,9 @@ def main():
 
     # ---- data-parallel invariant: every rank holds the same master weights after the timed loops
     ranks_identical = None
+    if exchange == "peer":
+        reducer.check()           # raises if a peer failed to arrive in any exchange
+        reducer.close()
     if world > 1:
         w = torch.as_tensor(net.params_as_cuda_array(), device=f"cuda:{local}")
         wmax, wmin = w.clone(), w.clone()
@@ -527,7 +544,7 @@ def main():
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": wl["desc"] if args.scaling == "weak" else wl["desc"].replace("64 seqs x 150 frames per GPU", f"64 seqs x 150 frames in total, {N_SEQ} per GPU"),
                        "frames_per_gpu_step": T, "global_frames_per_step": frames_per_step,
-                       "parallelism": f"dp{world}" + (f", FP16 gradient all-reduce in {n_seg} buckets, the first overlapped with the conv front end's backward pass ({nccl_sms} SMs left to NCCL there)" if overlap else (", FP16 gradient all-reduce" if world > 1 else "")),
+                       "parallelism": f"dp{world}" + (f", FP16 gradient all-reduce in {n_seg} buckets, the first overlapped with the conv front end's backward pass ({nccl_sms} SMs left to NCCL there)" if overlap else ((", FP16 gradient bucket summed by one kernel per rank over NVLink peer memory (kfp16_peer_allreduce_f16)" if exchange == "peer" else ", FP16 gradient all-reduce (NCCL)") if world > 1 else "")),
                        "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush",
                        "loss": ("chain LF-MMI (log-semiring numerator / denominator forward-backward, 50 output frames per sequence, one batched launch)"
                                 if objective == "chain" else "0.5*||out||^2, dY=Y"),

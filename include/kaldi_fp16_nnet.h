@@ -218,6 +218,28 @@ int kfp16_net_segment_grads(const kfp16_net *net, int seg, size_t *first_elem, s
 /* kernels launched by one forward+loss+backward(+sgd) pass of this network */
 int kfp16_net_launches_per_step(const kfp16_net *net, int phases);
 
+/* ---- Gradient exchange of the data-parallel step over NVLink peer memory (the reference is single-GPU,
+ * cpp/cuda/bridge.cu:38-47 -- the exchange sits between Backward and the optimizer updates of
+ * internal/nnet/train_step.go:212-221).  One process per GPU, up to 8 GPUs of one node.  Every rank creates a
+ * communicator over its FP16 gradient bucket (kfp16_net_grads_f16; any 16-byte aligned cudaMalloc'ed buffer of `count`
+ * FP16 elements, the same count on every rank), publishes its handle, and connects with the handles of all ranks in
+ * rank order (the host exchanges the bytes: torch.distributed / MPI / a file).  kfp16_peer_allreduce_f16 then queues ONE
+ * kernel on the context's stream that replaces the buckets of all ranks by their sum: each rank adds the slice it owns
+ * over all ranks (FP32 accumulation in rank order, one rounding to FP16) through loads from, and stores to, the peers'
+ * memory; flags in peer memory order the ranks, so every rank must queue the call once per step -- it can be captured
+ * into a CUDA graph.  The result is bit-identical on all ranks.  A peer that does not arrive within the time limit
+ * (default 20 s) makes the kernel give up; kfp16_peer_comm_status (synchronises the stream) then returns -1. */
+#define KFP16_PEER_HANDLE_BYTES 128
+typedef struct kfp16_peer_comm kfp16_peer_comm;
+kfp16_peer_comm *kfp16_peer_comm_create(kfp16_ctx *ctx, int rank, int world, void *bucket_f16, size_t count);
+int kfp16_peer_comm_handle(kfp16_peer_comm *comm, void *handle_out /* KFP16_PEER_HANDLE_BYTES */);
+int kfp16_peer_comm_connect(kfp16_peer_comm *comm, const void *handles /* world x KFP16_PEER_HANDLE_BYTES */);
+int kfp16_peer_comm_set_timeout(kfp16_peer_comm *comm, double seconds);
+int kfp16_peer_allreduce_f16(kfp16_peer_comm *comm);
+int kfp16_peer_comm_status(kfp16_peer_comm *comm);
+/* every rank must have finished its last exchange before any rank destroys its communicator */
+void kfp16_peer_comm_destroy(kfp16_peer_comm *comm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,6 +219,13 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_net_capture": (c_int, [c_void_p, c_int]),
     "kfp16_net_launch": (c_int, [c_void_p, c_int]),
     "kfp16_net_launches_per_step": (c_int, [c_void_p, c_int]),
+    "kfp16_peer_comm_create": (c_void_p, [c_void_p, c_int, c_int, c_void_p, c_size_t]),
+    "kfp16_peer_comm_handle": (c_int, [c_void_p, c_void_p]),
+    "kfp16_peer_comm_connect": (c_int, [c_void_p, c_void_p]),
+    "kfp16_peer_comm_set_timeout": (c_int, [c_void_p, C.c_double]),
+    "kfp16_peer_allreduce_f16": (c_int, [c_void_p]),
+    "kfp16_peer_comm_status": (c_int, [c_void_p]),
+    "kfp16_peer_comm_destroy": (None, [c_void_p]),
     # ---- kaldi_fp16_chain.h
     "kfp16_chain_create": (c_void_p, [c_void_p, c_int, c_int, c_int, C.POINTER(ChainFst)]),
     "kfp16_chain_destroy": (None, [c_void_p]),

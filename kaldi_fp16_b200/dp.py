@@ -1,13 +1,15 @@
 """Data-parallel plumbing for the training step: one process per GPU, sequences of the
-egs minibatch sharded across ranks, ONE exchange step per minibatch -- a sum all-reduce of the flat
-FP32 weight-gradient bucket -- then the identical SGD update on every rank.
+egs minibatch sharded across ranks, ONE exchange step per minibatch -- the sum of the flat gradient
+bucket over the ranks -- then the identical SGD update on every rank.
 
 The reference has no multi-GPU path (single process, device 0: cpp/cuda/bridge.cu:38-47); this is
 where nnet.TrainStep (internal/nnet/train_step.go:142-283) is split: shard before TransferBatch,
-all-reduce between Backward (212) and the optimizer updates (221).
+exchange between Backward (212) and the optimizer updates (221).
 
-torch.distributed is plumbing only (NCCL over NVLink on the GPU box, gloo in the CPU tests); the
-buffer that is reduced is the library's own gradient bucket (kfp16_net_grads_f32), in place.
+PeerGradAllReducer: the library's own exchange kernel over NVLink peer memory (FP16 bucket, what
+bench.py --gpus N runs).  GradAllReducer: torch.distributed's all-reduce on the same bucket (NCCL
+on the GPU box, gloo in the CPU tests).  torch.distributed is plumbing only; the buffer that is
+summed is the library's own gradient bucket (kfp16_net_grads_f16 / kfp16_net_grads_f32), in place.
 """
 from __future__ import annotations
 
@@ -101,3 +103,72 @@ class BNStatsAllReducer:
         self.calls += 1
         if self.world > 1:
             self.dist.all_reduce(self.as_tensor(ptr, count), op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class PeerGradAllReducer:
+    """Sum all-reduce of the FP16 gradient bucket by the library's own kernel over NVLink peer memory
+    (kfp16_peer_allreduce_f16, include/kaldi_fp16_nnet.h): every rank reduces the slice it owns through loads from the
+    peers' buckets and stores the rounded sums into all of them -- one launch on the step's stream between the step graph
+    and the SGD graph, no library collective.  torch.distributed only carries the 128-byte memory handles at set-up.
+
+    `bucket_ptr` / `count`: kfp16_net_grads_f16 and kfp16_net_bucket_size (any cudaMalloc'ed FP16 buffer).  Raises when
+    the peers cannot be mapped (GPUs of different nodes, no peer access): the caller then keeps GradAllReducer."""
+
+    def __init__(self, lib, handle_ptr, bucket_ptr, count, group=None, timeout_s: float = 20.0):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self.lib, self.dist, self.group = lib, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.comm = lib.kfp16_peer_comm_create(handle_ptr, self.rank, self.world, bucket_ptr, count)
+        ok = bool(self.comm)
+        err = "" if ok else _lib.last_error()
+        mine = b""
+        if ok:
+            buf = C.create_string_buffer(128)
+            ok = lib.kfp16_peer_comm_handle(self.comm, buf) == 0
+            err = "" if ok else _lib.last_error()
+            mine = bytes(buf.raw)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, mine, int(count)), group=group)
+        if ok and all(g[0] for g in gathered):
+            if len({g[2] for g in gathered}) != 1:
+                ok, err = False, f"bucket sizes differ between the ranks: {[g[2] for g in gathered]}"
+            else:
+                ok = lib.kfp16_peer_comm_connect(self.comm, b"".join(g[1] for g in gathered)) == 0 and \
+                    lib.kfp16_peer_comm_set_timeout(self.comm, float(timeout_s)) == 0
+                err = "" if ok else _lib.last_error()
+        elif ok:
+            ok, err = False, "a peer could not export its bucket"
+        # all ranks agree on the outcome before anyone launches (a rank that waits for a peer that gave up would time out)
+        agreed = [None] * self.world
+        dist.all_gather_object(agreed, ok, group=group)
+        if not all(agreed):
+            if self.comm:
+                lib.kfp16_peer_comm_destroy(self.comm)
+            self.comm = None
+            raise RuntimeError(f"peer-memory gradient exchange unavailable on rank {self.rank}: {err or 'a peer failed'}")
+
+    def all_reduce(self) -> None:
+        """queue the exchange on the context's stream (every rank, once per step)"""
+        from . import _lib
+
+        if self.lib.kfp16_peer_allreduce_f16(self.comm) != 0:
+            raise RuntimeError(_lib.last_error())
+
+    def check(self) -> None:
+        """synchronise the stream and raise if a peer failed to arrive in an exchange"""
+        from . import _lib
+
+        if self.lib.kfp16_peer_comm_status(self.comm) != 0:
+            raise RuntimeError(_lib.last_error())
+
+    def close(self) -> None:
+        if self.comm:
+            self.lib.kfp16_peer_comm_status(self.comm)
+            self.dist.barrier(self.group)        # nobody unmaps memory a peer's kernel may still touch
+            self.lib.kfp16_peer_comm_destroy(self.comm)
+            self.comm = None

@@ -108,6 +108,10 @@ def test_fails_loudly_without_a_gpu(built_lib):
     assert not lib.kfp16_net_create(None, b"input name=input dim=8\n", C.byref(opts))
     x = np.zeros(8, np.uint16)
     assert lib.ops_gemm(None, 1, 8, 8, 1.0, x.ctypes.data, 8, x.ctypes.data, 8, 0.0, x.ctypes.data, 8) == -1
+    # the peer-memory gradient exchange: no context, no communicator -- and no silent no-op
+    assert not lib.kfp16_peer_comm_create(None, 0, 2, x.ctypes.data, 8)
+    assert b"kfp16_peer_comm_create" in lib.kfp16_last_error()
+    assert lib.kfp16_peer_allreduce_f16(None) == -1 and lib.kfp16_peer_comm_status(None) == -1
 
 
 def test_product_package_never_imports_the_oracle():

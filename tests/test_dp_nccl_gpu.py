@@ -4,7 +4,8 @@ their shard of the minibatch's sequences, exchange gradients with one sum all-re
   * FP32 bucket exchange: the all-reduced gradient equals the 1-rank gradient on the concatenated minibatch to FP32
     summation order (<= 1e-5 of the tensor scale);
   * FP16 bucket exchange (what bench.py --gpus N runs; the reference keeps FP16 gradient tensors,
-    internal/gpu/backward_ops.go:195-225): equal to <= 3 FP16 ulps of the tensor scale;
+    internal/gpu/backward_ops.go:195-225): equal to <= 3 FP16 ulps of the tensor scale -- through NCCL and through the
+    library's own exchange kernel over NVLink peer memory (kfp16_peer_allreduce_f16);
   * after 3 steps the master weights are bit-identical on both ranks and match the 1-rank run at FP16 resolution.
 
 Skipped when fewer than 2 GPUs are visible (run with `gpurun --gpus 2`)."""
@@ -60,7 +61,13 @@ def run_rank(rank, world, port, f16, q):
     sh = dp.shard_sequences(N_SEQ, world, rank)
     net = nnet.NewNetwork(nnet.BuildModelFromString(XCONFIG), h, sh.n_seq, L, train=True, lr=1e-2, momentum=0.9,
                           ref_round=False, seed=42, grad_scale=SCALE)
-    red = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(f16=f16), device=f"cuda:{rank}")) if world > 1 else None
+    peer = f16 == "peer"          # the FP16 bucket exchanged by the library's own kernel over NVLink peer memory
+    f16 = bool(f16)
+    red = None
+    if world > 1 and peer:
+        red = dp.PeerGradAllReducer(lib, h.ptr, lib.kfp16_net_grads_f16(net.ptr), lib.kfp16_net_bucket_size(net.ptr))
+    elif world > 1:
+        red = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(f16=f16), device=f"cuda:{rank}"))
     first_grad = None
     for step, x in enumerate(make_data()):
         net.SetInput("input", x[sh.rows(L)])
@@ -69,7 +76,9 @@ def run_rank(rank, world, port, f16, q):
         net.Backward(None)
         if f16:
             net.GradsToF16()
-        if red is not None:
+        if red is not None and peer:
+            red.all_reduce()
+        elif red is not None:
             with torch.cuda.stream(ts):
                 red.all_reduce()
         cudart.synchronize()
@@ -87,6 +96,8 @@ def run_rank(rank, world, port, f16, q):
     cudart.synchronize()
     w = net._bucket_f32(lib.kfp16_net_params_f32)
     q.put((rank, first_grad, w))
+    if red is not None and peer:
+        red.close()
     net.Free()
     if world > 1:
         dist.destroy_process_group()
@@ -112,7 +123,7 @@ def launch(world, f16):
     return res
 
 
-@pytest.mark.parametrize("f16", [False, True], ids=["fp32_bucket", "fp16_bucket"])
+@pytest.mark.parametrize("f16", [False, True, "peer"], ids=["fp32_bucket", "fp16_bucket", "fp16_bucket_peer_memory"])
 def test_two_rank_step_equals_one_rank_step(f16):
     if n_gpus() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
