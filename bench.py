@@ -344,24 +344,27 @@ def main():
     exchange = "nccl"
     if world > 1:
         from kaldi_fp16_b200 import dp
-        if overlap:
-            n_seg = net.CaptureSegments(2, cut_layers=wl.get("dp_cut"), export_f16=True,
-                                        tail_max_ctas=(148 - nccl_sms) if nccl_sms > 0 else 0)
-            seg_ranges = [net.SegmentGrads(k) for k in range(n_seg)]
-        else:
-            net.Capture(1 | 4)
-        net.Capture(8)
         # the exchange: the library's own kernel over NVLink peer memory (KFP16_DP_EXCHANGE=nccl: torch.distributed's
         # all-reduce; also what is left when the peers' buckets cannot be mapped -- the JSON line says which ran)
-        if not overlap and os.environ.get("KFP16_DP_EXCHANGE", "peer") == "peer":
+        if os.environ.get("KFP16_DP_EXCHANGE", "peer") == "peer":
             try:
                 reducer = dp.PeerGradAllReducer(lib, handle.ptr, lib.kfp16_net_grads_f16(net.ptr), lib.kfp16_net_bucket_size(net.ptr))
                 exchange = "peer"
             except RuntimeError as e:
                 print(f"[bench] rank {rank}: {e}; using the NCCL all-reduce", file=sys.stderr)
+        if overlap:
+            # the peer kernel runs as small CTAs beside the compute kernels on every SM; NCCL gets SMs of its own
+            tail_ctas = 0 if exchange == "peer" else ((148 - nccl_sms) if nccl_sms > 0 else 0)
+            n_seg = net.CaptureSegments(2, cut_layers=wl.get("dp_cut"), export_f16=True, tail_max_ctas=tail_ctas)
+            seg_ranges = [net.SegmentGrads(k) for k in range(n_seg)]
+        else:
+            net.Capture(1 | 4)
+        net.Capture(8)
         if exchange != "peer":
             reducer = dp.GradAllReducer(torch.as_tensor(net.grads_as_cuda_array(f16=True), device=f"cuda:{local}"))
         comm_stream = torch.cuda.Stream(device=local, priority=-1)
+        seg_ev = [torch.cuda.Event() for _ in range(max(n_seg, 1))]
+        peer_threads = int(os.environ.get("KFP16_PEER_THREADS", "64"))
     else:
         net.Capture(1)
         net.Capture(2)
@@ -372,9 +375,21 @@ def main():
         if world == 1:
             net.Launch(1)
             return
-        if exchange == "peer":
+        if exchange == "peer" and not overlap:
             net.Launch(1 | 4)
             reducer.all_reduce()                           # one kernel on the step's stream
+            return
+        if exchange == "peer":
+            for k in range(n_seg):
+                net.LaunchSegment(k)                       # backward of one layer group (+ its FP16 export) ...
+                if k < n_seg - 1:                          # ... its gradients are exchanged beside the next segment
+                    seg_ev[k].record(tstream)
+                    comm_stream.wait_event(seg_ev[k])
+                    reducer.all_reduce_range(*seg_ranges[k], channel=1 + k, stream_ptr=comm_stream.cuda_stream, threads=peer_threads)
+                else:
+                    reducer.all_reduce_range(*seg_ranges[k], channel=0)
+            seg_ev[n_seg - 1].record(comm_stream)
+            tstream.wait_event(seg_ev[n_seg - 1])          # the SGD graph waits for both exchanges
             return
         if not overlap:
             net.Launch(1 | 4)
@@ -544,7 +559,7 @@ def main():
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": wl["desc"] if args.scaling == "weak" else wl["desc"].replace("64 seqs x 150 frames per GPU", f"64 seqs x 150 frames in total, {N_SEQ} per GPU"),
                        "frames_per_gpu_step": T, "global_frames_per_step": frames_per_step,
-                       "parallelism": f"dp{world}" + (f", FP16 gradient all-reduce in {n_seg} buckets, the first overlapped with the conv front end's backward pass ({nccl_sms} SMs left to NCCL there)" if overlap else ((", FP16 gradient bucket summed by one kernel per rank over NVLink peer memory (kfp16_peer_allreduce_f16)" if exchange == "peer" else ", FP16 gradient all-reduce (NCCL)") if world > 1 else "")),
+                       "parallelism": f"dp{world}" + ((f", FP16 gradient bucket summed by the library's kernel over NVLink peer memory in {n_seg} parts, the first beside the conv front end's backward pass ({peer_threads}-thread CTAs on every SM)" if exchange == "peer" else f", FP16 gradient all-reduce in {n_seg} buckets, the first overlapped with the conv front end's backward pass ({nccl_sms} SMs left to NCCL there)") if overlap else ((", FP16 gradient bucket summed by one kernel per rank over NVLink peer memory (kfp16_peer_allreduce_f16)" if exchange == "peer" else ", FP16 gradient all-reduce (NCCL)") if world > 1 else "")),
                        "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush",
                        "loss": ("chain LF-MMI (log-semiring numerator / denominator forward-backward, 50 output frames per sequence, one batched launch)"
                                 if objective == "chain" else "0.5*||out||^2, dY=Y"),

@@ -228,7 +228,7 @@ int kfp16_net_launches_per_step(const kfp16_net *net, int phases);
  * over all ranks (FP32 accumulation in rank order, one rounding to FP16) through loads from, and stores to, the peers'
  * memory; flags in peer memory order the ranks, so every rank must queue the call once per step -- it can be captured
  * into a CUDA graph.  The result is bit-identical on all ranks.  A peer that does not arrive within the time limit
- * (default 20 s) makes the kernel give up; kfp16_peer_comm_status (synchronises the stream) then returns -1. */
+ * (default 20 s) makes the kernel give up; kfp16_peer_comm_status (synchronises the device) then returns -1. */
 #define KFP16_PEER_HANDLE_BYTES 128
 typedef struct kfp16_peer_comm kfp16_peer_comm;
 kfp16_peer_comm *kfp16_peer_comm_create(kfp16_ctx *ctx, int rank, int world, void *bucket_f16, size_t count);
@@ -236,6 +236,13 @@ int kfp16_peer_comm_handle(kfp16_peer_comm *comm, void *handle_out /* KFP16_PEER
 int kfp16_peer_comm_connect(kfp16_peer_comm *comm, const void *handles /* world x KFP16_PEER_HANDLE_BYTES */);
 int kfp16_peer_comm_set_timeout(kfp16_peer_comm *comm, double seconds);
 int kfp16_peer_allreduce_f16(kfp16_peer_comm *comm);
+/* The same exchange for the elements [first, first + count) of the bucket only (any alignment), on `stream` (NULL: the
+ * context's stream), with CTAs of `threads` threads (0: 512) and at most `max_ctas` CTAs (0: one per SM).  Exchanges that may
+ * be in flight at the same time -- a finished part of the gradient exchanged on a second stream beside the rest of the
+ * backward pass (kfp16_net_capture_segments_ex) -- must use different channels (0..3); all ranks use the same channel for the
+ * same range.  Small CTAs on every SM (threads = 64) keep the exchange thin beside the compute kernels. */
+int kfp16_peer_allreduce_f16_range(kfp16_peer_comm *comm, size_t first, size_t count, int channel, int threads, int max_ctas,
+                                   void *stream);
 int kfp16_peer_comm_status(kfp16_peer_comm *comm);
 /* every rank must have finished its last exchange before any rank destroys its communicator */
 void kfp16_peer_comm_destroy(kfp16_peer_comm *comm);

@@ -224,6 +224,7 @@ SIGNATURES: dict[str, tuple] = {
     "kfp16_peer_comm_connect": (c_int, [c_void_p, c_void_p]),
     "kfp16_peer_comm_set_timeout": (c_int, [c_void_p, C.c_double]),
     "kfp16_peer_allreduce_f16": (c_int, [c_void_p]),
+    "kfp16_peer_allreduce_f16_range": (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p]),
     "kfp16_peer_comm_status": (c_int, [c_void_p]),
     "kfp16_peer_comm_destroy": (None, [c_void_p]),
     # ---- kaldi_fp16_chain.h

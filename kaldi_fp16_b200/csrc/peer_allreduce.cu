@@ -35,13 +35,15 @@ constexpr int kEpoch = 32;      // exchanges completed by this rank
 constexpr int kDone = 33;       // CTAs of the running exchange that have stored their part
 constexpr int kError = 34;      // set when a wait ran into the time limit (a peer never arrived)
 constexpr int kFlagWords = 64;
+constexpr int kChannels = 4;
 
 struct PeerArgs {
   __half* buf[kMaxPeers];
   unsigned* flag[kMaxPeers];
   int rank, world;
-  unsigned long long count;        // FP16 elements in the bucket
+  unsigned long long first, count;  // the FP16 elements [first, first + count) of the bucket are exchanged
   unsigned long long timeout_ns;
+  int flag_off;                     // channel * kFlagWords: exchanges on different channels may be in flight together
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -77,18 +79,26 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// threads < world each wait for one peer's flag to reach `epoch`; the block continues together
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// threads < world each wait for one peer's flag to reach `epoch`; the block continues together.  Relaxed polls and ONE
+// acquire fence at the end: an acquire load per poll would invalidate the SM's L1 every time, and the exchange may share
+// its SMs with the kernels of the backward pass.
 __device__ __forceinline__ void wait_peers(unsigned* lf, int base, int world, unsigned epoch, unsigned long long timeout_ns) {
   if ((int)threadIdx.x < world) {
     const unsigned* f = lf + base + threadIdx.x;
     const unsigned long long t0 = global_ns();
     unsigned spins = 0;
-    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+    while ((int)(ld_relaxed_sys(f) - epoch) < 0) {
       if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) {
-        atomicExch(lf + kError, 1u);
+        atomicExch(lf + kError, 1u);     // (lf already points at the channel's block)
         break;
       }
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
   }
   __syncthreads();
 }
@@ -106,16 +116,20 @@ __device__ __forceinline__ void add8(float (&acc)[8], uint4 x) {
 // WORLD: compile-time bound of the rank loop (a.world <= WORLD), U vectors of 8 elements per thread and pass
 template <int WORLD, int U>
 __global__ void __launch_bounds__(512) peer_allreduce_f16_kernel(const PeerArgs a) {
-  unsigned* lf = a.flag[a.rank];
+  unsigned* lf = a.flag[a.rank] + a.flag_off;
   // every CTA reads the counter before the last one to finish advances it
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(lf + kEpoch) + 1u;
-  if (blockIdx.x == 0 && (int)threadIdx.x < a.world) st_release_sys(a.flag[threadIdx.x] + kFlagA + a.rank, epoch);
+  if (blockIdx.x == 0 && (int)threadIdx.x < a.world) st_release_sys(a.flag[threadIdx.x] + a.flag_off + kFlagA + a.rank, epoch);
   wait_peers(lf, kFlagA, a.world, epoch, a.timeout_ns);
 
-  const unsigned long long nvec = a.count >> 3;
+  // whole 16-byte vectors of the range are split over the ranks; the up to 7 + 7 elements in front of / behind them are
+  // the last rank's
+  const unsigned long long end = a.first + a.count;
+  const unsigned long long vf = (a.first + 7) >> 3, vl = end >> 3;         // vectors [vf, vl)
+  const unsigned long long nvec = vl > vf ? vl - vf : 0;
   const unsigned long long per = (nvec + a.world - 1) / a.world;
-  const unsigned long long v0 = per * a.rank;
-  const unsigned long long v1 = v0 + per < nvec ? v0 + per : nvec;
+  const unsigned long long v0 = vf + per * a.rank;
+  const unsigned long long v1 = v0 + per < vf + nvec ? v0 + per : vf + nvec;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long v = v0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < v1; v += stride * U) {
     uint4 x[U][WORLD];
@@ -140,10 +154,21 @@ __global__ void __launch_bounds__(512) peer_allreduce_f16_kernel(const PeerArgs 
         if (p < a.world) st_sys_v4(a.buf[p] + ((v + u * stride) << 3), r);
     }
   }
-  // the last count % 8 elements: the last rank, one thread each
-  if (a.rank == a.world - 1 && blockIdx.x == 0) {
-    const unsigned long long e = (nvec << 3) + threadIdx.x;
-    if (e < a.count) {
+  if (a.rank == a.world - 1 && blockIdx.x == 0 && threadIdx.x < 16) {
+    // thread i < 8: element first + i while in front of the first whole vector; thread 8 + i: element vl*8 + i
+    unsigned long long e;
+    bool mine;
+    if (nvec == 0) {                       // no whole vector: at most 14 elements, one thread each
+      e = a.first + threadIdx.x;
+      mine = e < end;
+    } else if (threadIdx.x < 8) {
+      e = a.first + threadIdx.x;
+      mine = e < (vf << 3);
+    } else {
+      e = (vl << 3) + (threadIdx.x - 8);
+      mine = e < end;
+    }
+    if (mine) {
       float acc = 0.f;
       for (int p = 0; p < a.world; ++p) {
         __half_raw raw;
@@ -172,7 +197,7 @@ __global__ void __launch_bounds__(512) peer_allreduce_f16_kernel(const PeerArgs 
   // only that CTA stays: the kernel -- and with it the stream -- must not complete before every peer has delivered, but
   // CTAs that merely wait would keep the SMs from CTAs that have not run yet (a grid larger than one wave)
   if (!s_last) return;
-  if ((int)threadIdx.x < a.world) st_release_sys(a.flag[threadIdx.x] + kFlagB + a.rank, epoch);
+  if ((int)threadIdx.x < a.world) st_release_sys(a.flag[threadIdx.x] + a.flag_off + kFlagB + a.rank, epoch);
   wait_peers(lf, kFlagB, a.world, epoch, a.timeout_ns);
 }
 
@@ -185,6 +210,7 @@ struct kfp16_peer_comm {
   void* opened[2 * kMaxPeers] = {};     // IPC mappings to close
   int n_opened = 0;
   bool connected = false;
+  size_t count = 0;                     // FP16 elements in the bucket
 };
 
 extern "C" {
@@ -199,15 +225,17 @@ kfp16_peer_comm* kfp16_peer_comm_create(kfp16_ctx* ctx, int rank, int world, voi
   if (!check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice")) return nullptr;
   kfp16_peer_comm* c = new kfp16_peer_comm();
   c->ctx = ctx;
-  if (!check_cuda(cudaMalloc(&c->flags, kFlagWords * sizeof(unsigned)), "cudaMalloc (peer flags)") ||
-      !check_cuda(cudaMemset(c->flags, 0, kFlagWords * sizeof(unsigned)), "cudaMemset (peer flags)")) {
+  if (!check_cuda(cudaMalloc(&c->flags, kChannels * kFlagWords * sizeof(unsigned)), "cudaMalloc (peer flags)") ||
+      !check_cuda(cudaMemset(c->flags, 0, kChannels * kFlagWords * sizeof(unsigned)), "cudaMemset (peer flags)")) {
     if (c->flags) cudaFree(c->flags);
     delete c;
     return nullptr;
   }
   c->args.rank = rank;
   c->args.world = world;
+  c->args.first = 0;
   c->args.count = count;
+  c->count = count;
   c->args.timeout_ns = 20ull * 1000 * 1000 * 1000;
   c->args.buf[rank] = static_cast<__half*>(bucket_f16);
   c->args.flag[rank] = c->flags;
@@ -253,30 +281,50 @@ int kfp16_peer_comm_set_timeout(kfp16_peer_comm* c, double seconds) {
   return 0;
 }
 
-int kfp16_peer_allreduce_f16(kfp16_peer_comm* c) {
+int kfp16_peer_allreduce_f16_range(kfp16_peer_comm* c, size_t first, size_t count, int channel, int threads, int max_ctas, void* stream) {
   if (!c) { set_error("kfp16_peer_allreduce_f16: null communicator"); return -1; }
   if (!c->connected) { set_error("kfp16_peer_allreduce_f16: peers are not connected (kfp16_peer_comm_connect)"); return -1; }
+  if (first > c->count || count > c->count - first) { set_error("kfp16_peer_allreduce_f16_range: [%zu, +%zu) is outside the bucket of %zu elements", first, count, c->count); return -1; }
+  if (channel < 0 || channel >= kChannels) { set_error("kfp16_peer_allreduce_f16_range: channel %d (0..%d)", channel, kChannels - 1); return -1; }
+  if (threads == 0) threads = 512;
+  if (threads < 32 || threads > 512 || (threads & 31)) { set_error("kfp16_peer_allreduce_f16_range: %d threads per CTA (32..512, whole warps)", threads); return -1; }
   const int world = c->args.world;
-  if (world == 1) return 0;
+  if (world == 1 || count == 0) return 0;
+  PeerArgs a = c->args;
+  a.first = first;
+  a.count = count;
+  a.flag_off = channel * kFlagWords;
   const int wt = world <= 2 ? 2 : (world <= 4 ? 4 : 8), unroll = 8 / wt;
-  const unsigned long long nvec = c->args.count >> 3, per = (nvec + world - 1) / world;
-  unsigned long long ctas = (per + 512ull * unroll - 1) / (512ull * unroll);
+  const unsigned long long nvec = count >> 3, per = (nvec + world - 1) / world;
+  unsigned long long ctas = (per + (unsigned long long)threads * unroll - 1) / ((unsigned long long)threads * unroll);
+  const unsigned long long cap = max_ctas > 0 ? (unsigned long long)max_ctas : (unsigned long long)c->ctx->num_sms;
   if (ctas < 1) ctas = 1;
-  if (ctas > (unsigned long long)c->ctx->num_sms) ctas = c->ctx->num_sms;
-  const dim3 grid((unsigned)ctas), block(512);
-  if (wt == 2) peer_allreduce_f16_kernel<2, 4><<<grid, block, 0, c->ctx->stream>>>(c->args);
-  else if (wt == 4) peer_allreduce_f16_kernel<4, 2><<<grid, block, 0, c->ctx->stream>>>(c->args);
-  else peer_allreduce_f16_kernel<8, 1><<<grid, block, 0, c->ctx->stream>>>(c->args);
+  if (ctas > cap) ctas = cap;
+  const dim3 grid((unsigned)ctas), block((unsigned)threads);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->ctx->stream;
+  if (wt == 2) peer_allreduce_f16_kernel<2, 4><<<grid, block, 0, st>>>(a);
+  else if (wt == 4) peer_allreduce_f16_kernel<4, 2><<<grid, block, 0, st>>>(a);
+  else peer_allreduce_f16_kernel<8, 1><<<grid, block, 0, st>>>(a);
   count_launch();
   return check_launch("kfp16_peer_allreduce_f16") ? 0 : -1;
 }
 
+int kfp16_peer_allreduce_f16(kfp16_peer_comm* c) {
+  if (!c) { set_error("kfp16_peer_allreduce_f16: null communicator"); return -1; }
+  return kfp16_peer_allreduce_f16_range(c, 0, c->count, 0, 512, 0, nullptr);
+}
+
 int kfp16_peer_comm_status(kfp16_peer_comm* c) {
   if (!c) { set_error("kfp16_peer_comm_status: null communicator"); return -1; }
-  unsigned err = 0;
-  if (!check_cuda(cudaStreamSynchronize(c->ctx->stream), "cudaStreamSynchronize") ||
-      !check_cuda(cudaMemcpy(&err, c->flags + kError, sizeof(err), cudaMemcpyDeviceToHost), "cudaMemcpy (peer status)")) return -1;
-  if (err) { set_error("kfp16_peer_allreduce_f16: a peer did not arrive within the time limit; the buckets are not reduced"); return -1; }
+  // exchanges may have been queued on other streams (kfp16_peer_allreduce_f16_range): wait for the device
+  if (!check_cuda(cudaSetDevice(c->ctx->device), "cudaSetDevice") || !check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return -1;
+  unsigned words[kChannels * kFlagWords];
+  if (!check_cuda(cudaMemcpy(words, c->flags, sizeof(words), cudaMemcpyDeviceToHost), "cudaMemcpy (peer status)")) return -1;
+  for (int ch = 0; ch < kChannels; ++ch)
+    if (words[ch * kFlagWords + kError]) {
+      set_error("kfp16_peer_allreduce_f16: a peer did not arrive within the time limit (channel %d); the buckets are not reduced", ch);
+      return -1;
+    }
   return 0;
 }
 

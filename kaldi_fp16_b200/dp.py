@@ -159,8 +159,17 @@ class PeerGradAllReducer:
         if self.lib.kfp16_peer_allreduce_f16(self.comm) != 0:
             raise RuntimeError(_lib.last_error())
 
+    def all_reduce_range(self, first: int, count: int, channel: int = 0, stream_ptr: int = 0, threads: int = 0,
+                         max_ctas: int = 0) -> None:
+        """the exchange for bucket[first : first + count] only, on `stream_ptr` (0: the context's stream); ranges that may
+        be in flight together (one beside the rest of the backward pass) use different channels"""
+        from . import _lib
+
+        if self.lib.kfp16_peer_allreduce_f16_range(self.comm, first, count, channel, threads, max_ctas, stream_ptr or None) != 0:
+            raise RuntimeError(_lib.last_error())
+
     def check(self) -> None:
-        """synchronise the stream and raise if a peer failed to arrive in an exchange"""
+        """synchronise the device and raise if a peer failed to arrive in an exchange"""
         from . import _lib
 
         if self.lib.kfp16_peer_comm_status(self.comm) != 0:

@@ -3,7 +3,8 @@ buckets mapped into each other through CUDA IPC handles, one kernel per rank and
 
   * the exchanged bucket is, on EVERY rank, bit for bit half(sum over the ranks in FP32, in rank order) -- the numpy
     restatement below; repeated exchanges (the flags carry a step counter, nothing is reset) and a bucket whose size is not
-    a multiple of the 16-byte vectors are covered;
+    a multiple of the 16-byte vectors are covered, and so are two ranges of the bucket exchanged at the same time on two
+    streams / flag channels with an unaligned cut, and a range shorter than one vector;
   * the time of one exchange of the benchmark's 36 MB bucket is written to gpurun_out/ (not asserted).
 
 Skipped when fewer than 2 GPUs are visible (run with `gpurun --gpus 2`)."""
@@ -72,6 +73,26 @@ def run_rank(rank, world, port, q):
                 f.write(f"rank {rank} epoch {epoch}: {idx.size} differ, first at {idx[:12].tolist()}: got {got[idx[:4]].tolist()} "
                         f"want {want[idx[:4]].tolist()}\n")
             bad += int(idx.size)
+    # the same sum as two ranges in flight together (an unaligned cut, small CTAs on a second stream and channel: what the
+    # bucketed exchange beside the backward pass does), then a range without a whole 16-byte vector
+    cut = 333_331
+    bits = rank_data(rank, EPOCHS).view(np.uint16)
+    assert lib.bridge_transfer_fp16(t.Ptr, bits.ctypes.data, COUNT) == 0
+    cudart.synchronize()
+    st2 = cudart.Stream()
+    red.all_reduce_range(0, cut, channel=1, stream_ptr=st2.ptr, threads=64)
+    red.all_reduce_range(cut, COUNT - cut, channel=0)
+    red.check()
+    want = expected(world, EPOCHS)
+    bad += int(np.sum(t.ToBits().reshape(-1) != want.view(np.uint16)))
+    red.all_reduce_range(5, 9, channel=2, threads=32)
+    red.check()
+    acc = np.zeros(9, np.float32)
+    for _ in range(world):
+        acc = acc + want[5:14].astype(np.float32)
+    want[5:14] = acc.astype(np.float16)
+    bad += int(np.sum(t.ToBits().reshape(-1) != want.view(np.uint16)))
+    st2.destroy()
     red.close()
     t.Free()
     # one exchange of the benchmark's bucket, timed on the device between host barriers (zeros: sums stay finite)
