@@ -1577,56 +1577,63 @@ void plan_forward_rows(kfp16_net* n) {
   }
 }
 
+// Forward pass + objective of one step (after the gradient accumulators were cleared, before the backward pass): shared by
+// the whole-step graph (run_phases) and by segment 0 of the segmented step (run_segment).
+int forward_and_objective(kfp16_net* n) {
+  // a chain objective on subsampled output frames: the row-wise layers that feed only the objective compute just its rows
+  plan_forward_rows(n);
+  // Layers the objective does not depend on (the xent branch: prefinal-xent, output-xent + log-softmax -- computed by the
+  // reference's Forward as well, read by nobody in the step) run AFTER the objective has been queued on a second stream:
+  // the chain kernel holds one CTA per sequence (64 of 148 SMs, packed two to a TPC) for ~190 us, the GEMMs beside it
+  // are limited to the remaining SMs.  Both join before the backward pass.
+  const int L = (int)n->layers.size();
+  std::vector<char> anc(L, 0);
+  int n_rest = 0;
+  if (n->out_layer >= 0) {
+    anc[n->out_layer] = 1;
+    for (int i = n->out_layer; i >= 0; --i)
+      if (anc[i]) for (int src : n->layers[i].in) anc[src] = 1;
+    for (int i = 0; i < L; ++i) if (!anc[i] && n->layers[i].type != L_INPUT) ++n_rest;
+  }
+  const int sms = n->ctx->num_sms, held = (n->opts.n_seq + 1) & ~1;
+  const bool overlap = n->chain && n->overlap_loss && n->ctx->stream && n_rest > 0 && held + 16 <= sms && (n->ctx->max_ctas == 0 || n->ctx->max_ctas >= sms);
+  if (overlap && !n->side_stream) {
+    if (!check_cuda(cudaStreamCreateWithFlags(&n->side_stream, cudaStreamNonBlocking), "side stream") ||
+        !check_cuda(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming), "fork event") ||
+        !check_cuda(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming), "join event")) return -1;
+  }
+  n->fwd_rows_now = true;
+  int frc = 0;
+  for (int i = 0; i < L && !frc; ++i)
+    if (!overlap || anc[i]) frc = forward_layer(n, n->layers[i]);
+  if (!frc && overlap) {
+    cudaStream_t main_stream = n->ctx->stream;
+    frc = !check_cuda(cudaEventRecord(n->ev_fork, main_stream), "fork record") ||
+          !check_cuda(cudaStreamWaitEvent(n->side_stream, n->ev_fork, 0), "fork wait");
+    if (!frc) {
+      n->ctx->stream = n->side_stream;
+      frc = kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight);
+      n->ctx->stream = main_stream;
+    }
+    if (!frc) frc = !check_cuda(cudaEventRecord(n->ev_join, n->side_stream), "join record");
+    const int saved_max = n->ctx->max_ctas;
+    n->ctx->max_ctas = (sms - held - 4) & ~1;            // whole TPCs, a little slack for the block scheduler
+    for (int i = 0; i < L && !frc; ++i)
+      if (!anc[i]) frc = forward_layer(n, n->layers[i]);
+    n->ctx->max_ctas = saved_max;
+    if (!frc) frc = !check_cuda(cudaStreamWaitEvent(main_stream, n->ev_join, 0), "join wait");
+  }
+  n->fwd_rows_now = false;
+  if (frc) return -1;
+  if (!overlap && (n->chain ? kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight) : kfp16_net_loss_half_sq(n, ""))) return -1;
+  return 0;
+}
+
 int run_phases(kfp16_net* n, int phases) {
   if (phases & 1) {
     if (kfp16_bump_counter(n->ctx, n->seed_dev)) return -1;     // a new dropout mask per step, graph replays included
     if (kfp16_net_zero_grads(n)) return -1;
-    // a chain objective on subsampled output frames: the row-wise layers that feed only the objective compute just its rows
-    plan_forward_rows(n);
-    // Layers the objective does not depend on (the xent branch: prefinal-xent, output-xent + log-softmax -- computed by the
-    // reference's Forward as well, read by nobody in the step) run AFTER the objective has been queued on a second stream:
-    // the chain kernel holds one CTA per sequence (64 of 148 SMs, packed two to a TPC) for ~190 us, the GEMMs beside it
-    // are limited to the remaining SMs.  Both join before the backward pass.
-    const int L = (int)n->layers.size();
-    std::vector<char> anc(L, 0);
-    int n_rest = 0;
-    if (n->out_layer >= 0) {
-      anc[n->out_layer] = 1;
-      for (int i = n->out_layer; i >= 0; --i)
-        if (anc[i]) for (int src : n->layers[i].in) anc[src] = 1;
-      for (int i = 0; i < L; ++i) if (!anc[i] && n->layers[i].type != L_INPUT) ++n_rest;
-    }
-    const int sms = n->ctx->num_sms, held = (n->opts.n_seq + 1) & ~1;
-    const bool overlap = n->chain && n->overlap_loss && n->ctx->stream && n_rest > 0 && held + 16 <= sms && (n->ctx->max_ctas == 0 || n->ctx->max_ctas >= sms);
-    if (overlap && !n->side_stream) {
-      if (!check_cuda(cudaStreamCreateWithFlags(&n->side_stream, cudaStreamNonBlocking), "side stream") ||
-          !check_cuda(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming), "fork event") ||
-          !check_cuda(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming), "join event")) return -1;
-    }
-    n->fwd_rows_now = true;
-    int frc = 0;
-    for (int i = 0; i < L && !frc; ++i)
-      if (!overlap || anc[i]) frc = forward_layer(n, n->layers[i]);
-    if (!frc && overlap) {
-      cudaStream_t main_stream = n->ctx->stream;
-      frc = !check_cuda(cudaEventRecord(n->ev_fork, main_stream), "fork record") ||
-            !check_cuda(cudaStreamWaitEvent(n->side_stream, n->ev_fork, 0), "fork wait");
-      if (!frc) {
-        n->ctx->stream = n->side_stream;
-        frc = kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight);
-        n->ctx->stream = main_stream;
-      }
-      if (!frc) frc = !check_cuda(cudaEventRecord(n->ev_join, n->side_stream), "join record");
-      const int saved_max = n->ctx->max_ctas;
-      n->ctx->max_ctas = (sms - held - 4) & ~1;            // whole TPCs, a little slack for the block scheduler
-      for (int i = 0; i < L && !frc; ++i)
-        if (!anc[i]) frc = forward_layer(n, n->layers[i]);
-      n->ctx->max_ctas = saved_max;
-      if (!frc) frc = !check_cuda(cudaStreamWaitEvent(main_stream, n->ev_join, 0), "join wait");
-    }
-    n->fwd_rows_now = false;
-    if (frc) return -1;
-    if (!overlap && (n->chain ? kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight) : kfp16_net_loss_half_sq(n, ""))) return -1;
+    if (forward_and_objective(n)) return -1;
     if (kfp16_net_backward(n)) return -1;
   }
   if (phases & 4) {
@@ -2305,9 +2312,8 @@ static int first_param_of_layer(const Layer& l) {
 }
 static int run_segment(kfp16_net* n, int seg) {
   const int hi = seg == 0 ? (int)n->layers.size() : n->seg_lo[seg - 1];
-  if (seg == 0) {
-    if (kfp16_net_zero_grads(n) || kfp16_net_forward(n)) return -1;
-    if (n->chain ? kfp16_net_loss_chain(n, "", n->chain, n->chain_sub, n->chain_left, n->chain_weight) : kfp16_net_loss_half_sq(n, "")) return -1;
+  if (seg == 0) {      // exactly what the whole-step graph starts with
+    if (kfp16_bump_counter(n->ctx, n->seed_dev) || kfp16_net_zero_grads(n) || forward_and_objective(n)) return -1;
   }
   if (backward_range(n, hi, n->seg_lo[seg], seg == 0)) return -1;
   if (flush_wgrads(n)) return -1;      // the segment's gradient range must be complete when it ends
