@@ -13,9 +13,15 @@ both directions (Q5), prefinal backward = transpose of its forward (Q8), conv ac
 height-major [T x H*F] with batch-norm per filter (the reference's filter-major re-layout is not
 consumed consistently by its next layer, forward.go:450 vs 503-513).
 
-Parity unpinned at this level: the Go executor cannot be run here (no Go toolchain, and it links
-Kaldi); the operator-level pieces it is built from (GEMM, elementwise) ARE pinned against the
-compiled reference library (tests/test_ops_gpu.py, tests/test_gemm_gpu.py).
+Pinning.  The Go executor itself cannot be run here (no Go toolchain, and it links Kaldi).  FORWARD: pinned on
+the GPU box against the reference's own compiled operator library driven in forward.go's operator order, layer by
+layer over a whole network (tests/test_network_vs_reference_ops_gpu.py; full-size layers:
+tests/test_layer_vs_reference_gpu.py, tests/test_cnn_tdnn_fullsize_gpu.py), and every operator it composes is
+pinned bit for bit (tests/test_ops_gpu.py, tests/test_gemm_gpu.py, tests/golden/ref_ops.npz).  BACKWARD: the
+orchestration is unpinned -- the reference's own Network.Backward is inconsistent with its forward (quirks
+Q2/Q8), so there is nothing to pin it to; the formulas are checked against an independent float64 autograd
+(tests/test_nnet_oracle_cpu.py) and, per layer at full size, against the reference's backward OPERATORS
+(tests/test_layer_vs_reference_gpu.py).
 """
 from __future__ import annotations
 
