@@ -2,7 +2,7 @@
  *
  * Every symbol below has the name, argument order and error convention (0 / -1, message via
  * ops_last_error) of the declaration it replaces in /root/reference/cpp/include/ops.h; the
- * citation after each prototype is that declaration.  Callers: internal/gpu/*.go (cgo, LDFLAGS
+ * citation after each prototype is that declaration.  Callers: the Go files of internal/gpu (cgo, LDFLAGS
  * -lkaldi_fp16) -- see INTEGRATION.md.  All matrices are FP16, row-major, device pointers.
  */
 #ifndef KALDI_FP16_B200_OPS_H
